@@ -1,0 +1,175 @@
+/*
+ * lbm_b200.h -- C ABI of liblbm_b200.so: the B200-native (sm_100a) D3Q19 hot path
+ * of pour-over-coffee-lbm.
+ *
+ * This is the drop-in boundary.  Each entry point names the reference interface
+ * (file:line under the reference root) whose Taichi kernels it replaces.  The
+ * reference is Python, so the binding a maintainer adds is a ctypes stub; it is
+ * shown in INTEGRATION.md and implemented in pour_over_coffee_lbm_b200/_lib.py.
+ *
+ * Conventions
+ *   - plain C: device pointers + sizes, no torch / Taichi types;
+ *   - every function returns 0 on success, non-zero on failure (lbm_last_error());
+ *   - all device work is enqueued on the caller's stream (cudaStream_t as void*),
+ *     there is no hidden synchronisation except where stated;
+ *   - device memory is owned by the CALLER (torch tensors in the Python host).
+ *
+ * Memory layout in HBM (x fastest, z slowest; SoA):
+ *   populations  g[q][zp][y][x]   f32, q = 0..18 (config/core.py:36-38 ordering),
+ *                zp = z + zghost, zghost in {0,1} ghost planes on each side of a slab
+ *   scalars      s[zp][y][x]      (rho, phase, flags u8, nu_sgs)
+ *   vectors      v[c][zp][y][x]   c = 0..2   (u, body_force)
+ * The populations stored are POST-COLLISION values; streaming happens on read
+ * (pull scheme).  lbm_export_f / lbm_import_f convert to/from the reference's
+ * pre-collision `f[q,i,j,k]` view exactly (pure data movement).
+ */
+#ifndef LBM_B200_H
+#define LBM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LBM_Q 19
+
+/* compat modes */
+#define LBM_COMPAT_PHYSICAL  0   /* consistent lattice, standard Guo, local-stress LES, Guo-Zhao drag */
+#define LBM_COMPAT_REFERENCE 1   /* legacy LBMSolver arithmetic, quirks Q1..Q7 kept verbatim */
+
+/* feature bits (lbm_params.features) */
+#define LBM_FEAT_WALLS   1    /* flags consulted: solid cells skipped, halfway bounce-back, open faces */
+#define LBM_FEAT_FORCE   2    /* body_force field enters through the forcing term */
+#define LBM_FEAT_PHASE   4    /* phase field read: tau by phase, gravity*phase */
+#define LBM_FEAT_LES     8    /* Smagorinsky eddy viscosity (physical: local Pi^neq; reference: FD on lagged u) */
+#define LBM_FEAT_POROUS  16   /* filter-zone drag (physical: force; reference: post-step u damping) */
+#define LBM_FEAT_STRICT  64   /* use the -fmad=false build: bit-exact against the CPU oracle */
+
+/* flag byte per cell (lbm_fields.flags) */
+#define LBM_FLAG_SOLID   1    /* LBMSolver.solid != 0           legacy/lbm_solver.py:293 */
+#define LBM_FLAG_FILTER  2    /* FilterPaperSystem.filter_zone   filter_paper.py:288-364 */
+#define LBM_FLAG_LES     4    /* LBMSolver.les_mask != 0         legacy/lbm_solver.py:203-205 */
+#define LBM_FLAG_NEAR    8    /* some D3Q19 neighbour is solid or outside an open face (derived) */
+
+typedef struct lbm_ctx lbm_ctx;
+
+typedef struct {
+    int nx, ny, nz;           /* local extent; nz = owned planes of this slab */
+    int nz_global, z0;        /* global z extent, global index of owned plane 0 */
+    int zghost;               /* ghost planes on each z side of every field (0 single GPU, 1 slabs) */
+    int periodic;             /* bit0 x, bit1 y, bit2 z (global) */
+    int compat;               /* LBM_COMPAT_* */
+    int features;             /* LBM_FEAT_* */
+    float tau_water, tau_air; /* config.TAU_WATER / TAU_AIR (0.53 / 0.8) */
+    float gravity_lu;         /* config.GRAVITY_LU */
+    float cs_smag;            /* Smagorinsky constant (reference hard-codes 0.18, les_turbulence.py:95) */
+    float tau_min, tau_max;   /* clamp on tau_eff (0.55 / 1.90, legacy/lbm_solver.py:571) */
+    float porous_darcy;       /* physical: nu/K   [1/ts]  */
+    float porous_forch;       /* physical: F_eps/sqrt(K) [1/lu] */
+    float K_lu, beta_lu;      /* reference: filter_paper.py:423-469 */
+    float c_darcy, c_forch;   /* reference: constant folds of filter_paper.py:578-586 */
+    int vec;                  /* tuning: cells per thread along x (1, 2 or 4; 0 = auto) */
+    int block;                /* tuning: threads per CTA (0 = auto) */
+} lbm_params;
+
+typedef struct {
+    float *f_src, *f_dst;     /* populations (post-collision), ping-pong; lbm_step swaps them */
+    float *rho;               /* written when write_macro */
+    float *u_src, *u_dst;     /* velocity ping-pong: u_src = previous step's u (FD-LES input), u_dst written */
+    float *body_force;        /* may be NULL unless LBM_FEAT_FORCE */
+    float *phase;             /* may be NULL unless LBM_FEAT_PHASE */
+    float *blockage;          /* FilterPaperSystem.filter_blockage, may be NULL */
+    uint8_t *flags;           /* may be NULL unless LBM_FEAT_WALLS */
+} lbm_fields;
+
+/* ---- life cycle -------------------------------------------------------------------------- */
+int  lbm_version(void);
+const char *lbm_last_error(lbm_ctx *ctx);      /* ctx may be NULL: last global error */
+/* Replaces backend construction + validate_platform(): src/core/lbm_unified.py:58-126,
+ * src/core/backends/cuda_backend.py:40-75.  Fails (non-zero) unless `device` is sm_100. */
+int  lbm_create(lbm_ctx **out, int device, const lbm_params *p);
+int  lbm_set_params(lbm_ctx *ctx, const lbm_params *p);
+void lbm_destroy(lbm_ctx *ctx);
+/* number of kernels this library has launched since creation (bench.py gpu_launches) */
+long long lbm_launch_count(lbm_ctx *ctx);
+
+/* ---- initialisation ---------------------------------------------------------------------- */
+/* LBMSolver.init_fields legacy/lbm_solver.py:1067-1112 and UnifiedLBMSolver._init_equilibrium
+ * lbm_unified.py:236-248: g[q] = f_eq(rho,u) with the mode's equilibrium.  rho/u may be NULL
+ * (=> rho0, u0 uniform). */
+int  lbm_init_equilibrium(lbm_ctx *ctx, float *g, const float *rho, const float *u,
+                          float rho0, const float u0[3], void *stream);
+/* FilterPaperSystem._setup_v60_geometry / _setup_filter_zones, filter_paper.py:206-364.
+ * geom = {top_radius_lu, bottom_radius_lu, cup_height_lu, air_gap_lu, paper_thickness_lu}
+ * (f32-rounded Python-scope constants).  Writes solid (u8) and filter_zone (i32), either may be NULL. */
+int  lbm_build_v60_geometry(lbm_ctx *ctx, uint8_t *solid, int32_t *filter_zone, const float geom[5], void *stream);
+/* Packs solid/filter_zone/les_mask into the flag byte and derives LBM_FLAG_NEAR.
+ * filter_zone / les_mask may be NULL (=> 0 / 1). */
+int  lbm_pack_flags(lbm_ctx *ctx, uint8_t *flags, const uint8_t *solid, const int32_t *filter_zone,
+                    const int32_t *les_mask, void *stream);
+
+/* ---- the hot path ------------------------------------------------------------------------ */
+/* Replaces LBMSolver.step() legacy/lbm_solver.py:817-867 (LES pre-pass, macroscopic,
+ * collide+stream, swap, filter damping) and ComputeBackend.execute_collision_streaming
+ * backends/cuda_backend.py:197-241 by ONE fused pull kernel per step.
+ * Runs `nsteps` steps; rho/u are written on every step when write_macro_every == 1, on every
+ * k-th and the last step when k > 1, never when 0.  f_src/f_dst (and u_src/u_dst) in *fields are
+ * swapped in place so that f_src always holds the newest state on return.
+ * comm_stream is used only when a communicator is attached (slab halo exchange). */
+int  lbm_step(lbm_ctx *ctx, lbm_fields *fields, int nsteps, int write_macro_every,
+              void *compute_stream, void *comm_stream);
+/* LBMSolver._compute_macroscopic_quantities legacy/lbm_solver.py:488-535 on the current state
+ * (streams g on the fly, writes rho and u_dst; no collision). */
+int  lbm_macroscopic(lbm_ctx *ctx, const lbm_fields *fields, void *stream);
+/* TopBoundary/BottomBoundary/OutletBoundary boundary_conditions.py:178-324 (observable part:
+ * rho on open faces). */
+int  lbm_face_bc(lbm_ctx *ctx, const lbm_fields *fields, void *stream);
+/* Exact conversion between the device's post-collision populations and the reference's
+ * `f[q,i,j,k]` (pre-collision, after streaming) in the SAME [q][zp][y][x] layout. */
+int  lbm_export_f(lbm_ctx *ctx, const float *g, const uint8_t *flags, float *f_out, void *stream);
+int  lbm_import_f(lbm_ctx *ctx, const float *f_in, const uint8_t *flags, float *g, void *stream);
+
+/* ---- neighbours that feed body_force --------------------- */
+/* PressureGradientDrive.compute_pressure_gradient + _accumulate_* pressure_gradient_drive.py:124-193,274-279:
+ * body_force += scale * clamp(-cs^2 grad(rho)/rho, max_force) on fluid cells. */
+int  lbm_pressure_gradient_force(lbm_ctx *ctx, const float *rho, const uint8_t *flags, float *body_force,
+                                 float max_force, float scale, void *stream);
+/* FilterPaperSystem.compute_forchheimer_resistance filter_paper.py:471-536: body_force += F_drag. */
+int  lbm_forchheimer_force(lbm_ctx *ctx, const float *u, const uint8_t *flags, float *body_force,
+                           float fmax, void *stream);
+/* LBMSolver.add_particle_reaction_forces legacy/lbm_solver.py:1478-1483: body_force += reaction on fluid. */
+int  lbm_add_reaction_force(lbm_ctx *ctx, const float *reaction, const uint8_t *flags, float *body_force, void *stream);
+
+/* ---- coffee particles (src/physics/coffee_particles.py) ------------------------------- */
+typedef struct {
+    float *pos, *vel;             /* [3][n] SoA, lattice units */
+    float *radius, *mass;         /* [n] SI (quirk Q9) */
+    int32_t *active;              /* [n] */
+    float *drag_new, *drag_old, *drag;  /* [3][n] */
+    float *u_fluid;               /* [3][n]  fluid_velocity_at_particle */
+    float *reynolds, *cd;         /* [n] */
+    int32_t *cell;                /* [3][n] base cell (i,j,k) -- bit-exact parity target */
+    int n;
+} lbm_particles;
+/* CoffeeParticleSystem.compute_two_way_coupling_forces + apply_under_relaxation,
+ * coffee_particles.py:1107-1212: trilinear gather of u, Schiller-Naumann drag, warp-aggregated
+ * atomic scatter of -drag into `reaction` ([3][zp][y][x], zeroed here first), under-relaxation. */
+int  lbm_particles_couple(lbm_ctx *ctx, const float *u, float *reaction, lbm_particles *ps,
+                          float water_density, float water_viscosity, float relax, void *stream);
+
+/* ---- multi-GPU slabs -------------------------------------------------------------------- */
+/* Attach an NCCL communicator over the ranks of one box (z-slab chain).  unique_id is the
+ * 128-byte ncclUniqueId produced by lbm_nccl_unique_id on rank 0 and broadcast by the host
+ * (torch.distributed).  Replaces CUDADualGPULBMSolver.exchange_boundary_data,
+ * legacy/cuda_dual_gpu_lbm.py:358-386. */
+int  lbm_nccl_unique_id(void *out128);
+int  lbm_attach_nccl(lbm_ctx *ctx, const void *unique_id128, int rank, int nranks);
+/* exchange the 5+5 outgoing populations of the slab's boundary planes of g (and optionally the
+ * ghost planes of a 3-component vector field) with the z neighbours. */
+int  lbm_halo_exchange(lbm_ctx *ctx, float *g, float *vec3_or_null, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LBM_B200_H */

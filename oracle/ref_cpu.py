@@ -1,0 +1,111 @@
+"""ctypes wrapper around oracle/ref_cpu.c (TEST INFRASTRUCTURE, not product code).
+
+Builds oracle/_build/libref_cpu.so on demand with the recipe in oracle/Makefile.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from . import d3q19_ref as R
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libref_cpu.so")
+
+
+class RefParams(C.Structure):
+    _fields_ = [("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int),
+                ("use_les", C.c_int), ("apply_filter", C.c_int), ("apply_faces", C.c_int),
+                ("tau_water", C.c_float), ("tau_air", C.c_float), ("gravity_lu", C.c_float),
+                ("les_cs", C.c_float), ("K_lu", C.c_float), ("beta_lu", C.c_float),
+                ("c_darcy", C.c_float), ("c_forch", C.c_float)]
+
+
+class RefFields(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in
+                ("f", "f_new", "rho", "u", "u_sq", "phase", "body_force", "nu_sgs",
+                 "solid", "les_mask", "filter_zone", "filter_blockage")]
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "ref_cpu.c")
+    stale = (not os.path.exists(_SO)) or os.path.getmtime(_SO) < os.path.getmtime(src)
+    if force or stale:
+        subprocess.run(["make", "-C", _HERE, "-s"] + (["-B"] if force else []), check=True)
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        try:
+            _lib = C.CDLL(_SO)
+        except OSError:
+            build(force=True)
+            _lib = C.CDLL(_SO)
+        for name in ("ref_les_update", "ref_macroscopic", "ref_collide_stream", "ref_swap_copy",
+                     "ref_apply_filter_effects", "ref_face_bcs", "ref_init_fields"):
+            getattr(_lib, name).argtypes = [C.POINTER(RefParams), C.POINTER(RefFields)]
+            getattr(_lib, name).restype = None
+        for name in ("ref_step", "ref_step_fused"):
+            getattr(_lib, name).argtypes = [C.POINTER(RefParams), C.POINTER(RefFields), C.c_int]
+            getattr(_lib, name).restype = None
+        _lib.ref_v60_solid.argtypes = [C.c_int] * 3 + [C.c_float] * 4 + [C.c_void_p]
+        _lib.ref_v60_solid.restype = None
+        _lib.ref_num_threads.restype = C.c_int
+    return _lib
+
+
+def num_threads() -> int:
+    return int(lib().ref_num_threads())
+
+
+class CState:
+    """Owns contiguous f32 arrays in the reference layout and the C structs pointing at them."""
+
+    def __init__(self, st: R.State):
+        cfg = st.cfg
+        self.cfg = cfg
+        ca = np.ascontiguousarray
+        self.f = ca(st.f, np.float32).copy(); self.f_new = ca(st.f_new, np.float32).copy()
+        self.rho = ca(st.rho, np.float32).copy(); self.u = ca(st.u, np.float32).copy()
+        self.u_sq = ca(st.u_sq, np.float32).copy(); self.phase = ca(st.phase, np.float32).copy()
+        self.body_force = ca(st.body_force, np.float32).copy(); self.nu_sgs = ca(st.nu_sgs, np.float32).copy()
+        self.solid = ca(st.solid, np.uint8).copy(); self.les_mask = ca(st.les_mask, np.int32).copy()
+        self.filter_zone = None if st.filter_zone is None else ca(st.filter_zone, np.int32).copy()
+        self.filter_blockage = None if st.filter_blockage is None else ca(st.filter_blockage, np.float32).copy()
+        c_darcy, c_forch = R.filter_constants(cfg)
+        self.params = RefParams(cfg.NX, cfg.NY, cfg.NZ, int(cfg.USE_LES), int(st.apply_filter),
+                                int(st.apply_faces), cfg.TAU_WATER, cfg.TAU_AIR, cfg.GRAVITY_LU,
+                                cfg.LES_CS, float(st.K_lu), float(st.beta_lu), float(c_darcy), float(c_forch))
+        self._sync_ptrs()
+
+    def _sync_ptrs(self):
+        p = lambda a: None if a is None else a.ctypes.data
+        self.fields = RefFields(p(self.f), p(self.f_new), p(self.rho), p(self.u), p(self.u_sq),
+                                p(self.phase), p(self.body_force), p(self.nu_sgs), p(self.solid),
+                                p(self.les_mask), p(self.filter_zone), p(self.filter_blockage))
+
+    def step(self, n: int = 1, fused: bool = False):
+        self._sync_ptrs()
+        fn = lib().ref_step_fused if fused else lib().ref_step
+        fn(C.byref(self.params), C.byref(self.fields), int(n))
+        if fused and (n % 2 == 1):   # pointer swap happened inside C: mirror it
+            self.f, self.f_new = self.f_new, self.f
+
+
+def v60_solid(cfg: R.RefConfig) -> np.ndarray:
+    out = np.empty((cfg.NX, cfg.NY, cfg.NZ), np.uint8)
+    f32 = np.float32
+    lib().ref_v60_solid(cfg.NX, cfg.NY, cfg.NZ,
+                        float(f32(cfg.TOP_RADIUS / cfg.SCALE_LENGTH)), float(f32(cfg.BOTTOM_RADIUS / cfg.SCALE_LENGTH)),
+                        float(f32(cfg.CUP_HEIGHT / cfg.SCALE_LENGTH)), float(f32(0.002 / cfg.SCALE_LENGTH)),
+                        out.ctypes.data)
+    return out

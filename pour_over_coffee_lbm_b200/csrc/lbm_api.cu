@@ -1,0 +1,419 @@
+// C ABI of liblbm_b200.so (see include/lbm_b200.h).  Host-side only: parameter checking,
+// kernel selection, launch geometry, slab halo exchange over NCCL.
+#include <dlfcn.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+
+#include "lbm_common.cuh"
+
+namespace lbm {
+using StepKernel = void (*)(const StepArgs);
+#define DECL_LOOKUP(name) StepKernel name(int forced, int les, int porous, int vec, int collide, int *block);
+DECL_LOOKUP(lookup_fast_g0_fn) DECL_LOOKUP(lookup_fast_g1_fn) DECL_LOOKUP(lookup_fast_g2_fn) DECL_LOOKUP(lookup_fast_g3_fn)
+DECL_LOOKUP(lookup_strict_g0_fn) DECL_LOOKUP(lookup_strict_g1_fn) DECL_LOOKUP(lookup_strict_g2_fn) DECL_LOOKUP(lookup_strict_g3_fn)
+
+cudaError_t launch_init_equilibrium(const Grid &, int, float *, const float *, const float *, float, const float[3], cudaStream_t);
+cudaError_t launch_v60_geometry(const Grid &, uint8_t *, int32_t *, const float[5], cudaStream_t);
+cudaError_t launch_pack_flags(const Grid &, uint8_t *, const uint8_t *, const int32_t *, const int32_t *, cudaStream_t);
+cudaError_t launch_convert_f(const Grid &, bool, const float *, const uint8_t *, float *, cudaStream_t);
+cudaError_t launch_face_bc(const Grid &, float *, const uint8_t *, cudaStream_t, int *);
+cudaError_t launch_pressure_gradient(const Grid &, const float *, const uint8_t *, float *, float, float, cudaStream_t);
+cudaError_t launch_forchheimer_force(const Grid &, const float *, const uint8_t *, float *, float, float, float, float, float, cudaStream_t);
+cudaError_t launch_add_reaction(const Grid &, const float *, const uint8_t *, float *, cudaStream_t);
+cudaError_t launch_particles_couple(const Grid &, const float *, float *, const lbm_particles &, float, float, float, cudaStream_t);
+}  // namespace lbm
+
+using namespace lbm;
+
+// ---- minimal NCCL binding, resolved at run time (no link-time dependency) ------------------
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclSuccess = 0 };
+enum { ncclFloat32 = 7, ncclUint8 = 1 };
+struct NcclApi {
+    void *handle = nullptr;
+    int (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static std::string g_error;
+
+static int load_nccl() {
+    if (g_nccl.handle) return 0;
+    // torch's bundled libnccl.so.2 is already in the process when the host is PyTorch: reuse it
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { g_error = std::string("cannot load libnccl: ") + dlerror(); return 1; }
+#define SYM(field, name) *(void **)(&g_nccl.field) = dlsym(h, name); if (!g_nccl.field) { g_error = "libnccl lacks " name; return 1; }
+    SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
+    SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd") SYM(Send, "ncclSend") SYM(Recv, "ncclRecv")
+    SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    g_nccl.handle = h;
+    return 0;
+}
+
+struct lbm_ctx {
+    int device = 0;
+    lbm_params p{};
+    Grid g{};
+    std::string error;
+    long long launches = 0;
+    ncclComm_t comm = nullptr;
+    int rank = 0, nranks = 1;
+    cudaEvent_t ev_boundary = nullptr, ev_comm = nullptr;
+};
+
+static int fail(lbm_ctx *ctx, const std::string &msg) {
+    g_error = msg;
+    if (ctx) ctx->error = msg;
+    return 1;
+}
+#define CUDA_OK(ctx, expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return fail(ctx, std::string(#expr ": ") + cudaGetErrorString(e_)); } while (0)
+#define NCCL_OK(ctx, expr) do { int e_ = (expr); if (e_ != ncclSuccess) return fail(ctx, std::string(#expr ": ") + g_nccl.GetErrorString(e_)); } while (0)
+
+static int make_grid(lbm_ctx *ctx, const lbm_params *p, Grid *g) {
+    if (p->nx <= 0 || p->ny <= 0 || p->nz <= 0) return fail(ctx, "grid extents must be positive");
+    if (p->zghost != 0 && p->zghost != 1) return fail(ctx, "zghost must be 0 or 1");
+    if (p->zghost == 0 && (p->z0 != 0 || p->nz_global != p->nz)) return fail(ctx, "zghost=0 requires the whole domain on one slab");
+    if (p->z0 < 0 || p->z0 + p->nz > p->nz_global) return fail(ctx, "slab outside the global z range");
+    if (!(p->features & LBM_FEAT_WALLS) && (p->periodic & 7) != 7) return fail(ctx, "without LBM_FEAT_WALLS the box must be fully periodic");
+    if ((p->features & LBM_FEAT_POROUS) && !(p->features & LBM_FEAT_WALLS)) return fail(ctx, "LBM_FEAT_POROUS needs LBM_FEAT_WALLS (filter zone lives in the flag byte)");
+    if (p->compat != LBM_COMPAT_PHYSICAL && p->compat != LBM_COMPAT_REFERENCE) return fail(ctx, "unknown compat mode");
+    g->nx = p->nx; g->ny = p->ny; g->nz = p->nz; g->zg = p->zghost; g->nz_global = p->nz_global; g->z0 = p->z0;
+    g->per_x = p->periodic & 1; g->per_y = (p->periodic >> 1) & 1; g->per_z = (p->periodic >> 2) & 1;
+    g->plane = (long long)p->nx * p->ny;
+    g->vol = g->plane * (p->nz + 2 * p->zghost);
+    return 0;
+}
+
+extern "C" {
+
+int lbm_version(void) { return 100; }
+
+const char *lbm_last_error(lbm_ctx *ctx) { return ctx ? ctx->error.c_str() : g_error.c_str(); }
+
+int lbm_create(lbm_ctx **out, int device, const lbm_params *p) {
+    if (!out || !p) return fail(nullptr, "null argument");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail(nullptr, std::string("no CUDA device: ") + cudaGetErrorString(e) + " (liblbm_b200 has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(nullptr, "device index out of range");
+    cudaDeviceProp prop;
+    CUDA_OK(nullptr, cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "device %d is sm_%d%d; liblbm_b200 is built for sm_100a (B200) only", device, prop.major, prop.minor);
+        return fail(nullptr, buf);
+    }
+    lbm_ctx *ctx = new lbm_ctx();
+    ctx->device = device;
+    if (make_grid(nullptr, p, &ctx->g)) { delete ctx; return 1; }
+    ctx->p = *p;
+    CUDA_OK(nullptr, cudaSetDevice(device));
+    cudaEventCreateWithFlags(&ctx->ev_boundary, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_comm, cudaEventDisableTiming);
+    *out = ctx;
+    return 0;
+}
+
+int lbm_set_params(lbm_ctx *ctx, const lbm_params *p) {
+    if (!ctx || !p) return fail(ctx, "null argument");
+    Grid g;
+    if (make_grid(ctx, p, &g)) return 1;
+    ctx->g = g; ctx->p = *p;
+    return 0;
+}
+
+void lbm_destroy(lbm_ctx *ctx) {
+    if (!ctx) return;
+    if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+    if (ctx->ev_boundary) cudaEventDestroy(ctx->ev_boundary);
+    if (ctx->ev_comm) cudaEventDestroy(ctx->ev_comm);
+    delete ctx;
+}
+
+long long lbm_launch_count(lbm_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int lbm_init_equilibrium(lbm_ctx *ctx, float *g, const float *rho, const float *u, float rho0, const float u0[3], void *stream) {
+    if (!ctx || !g) return fail(ctx, "null argument");
+    const float z[3] = {0, 0, 0};
+    CUDA_OK(ctx, launch_init_equilibrium(ctx->g, ctx->p.compat, g, rho, u, rho0, u0 ? u0 : z, (cudaStream_t)stream));
+    ctx->launches++;
+    return 0;
+}
+
+int lbm_build_v60_geometry(lbm_ctx *ctx, uint8_t *solid, int32_t *filter_zone, const float geom[5], void *stream) {
+    if (!ctx || !geom) return fail(ctx, "null argument");
+    CUDA_OK(ctx, launch_v60_geometry(ctx->g, solid, filter_zone, geom, (cudaStream_t)stream));
+    ctx->launches++;
+    return 0;
+}
+
+int lbm_pack_flags(lbm_ctx *ctx, uint8_t *flags, const uint8_t *solid, const int32_t *filter_zone, const int32_t *les_mask, void *stream) {
+    if (!ctx || !flags || !solid) return fail(ctx, "null argument");
+    CUDA_OK(ctx, launch_pack_flags(ctx->g, flags, solid, filter_zone, les_mask, (cudaStream_t)stream));
+    ctx->launches++;
+    return 0;
+}
+
+}  // extern "C"
+
+// ---- step ---------------------------------------------------------------------------------------
+static StepKernel lookup(const lbm_params &p, int vec, int collide, int *block) {
+    const int walls = (p.features & LBM_FEAT_WALLS) != 0;
+    const int forced = (p.features & (LBM_FEAT_FORCE | LBM_FEAT_PHASE)) != 0;
+    const int les = (p.features & LBM_FEAT_LES) != 0;
+    const int porous = (p.features & LBM_FEAT_POROUS) != 0;
+    const int group = p.compat * 2 + walls;
+    const bool strict = (p.features & LBM_FEAT_STRICT) != 0;
+    switch (group) {
+        case 0: return strict ? lookup_strict_g0_fn(forced, les, porous, vec, collide, block) : lookup_fast_g0_fn(forced, les, porous, vec, collide, block);
+        case 1: return strict ? lookup_strict_g1_fn(forced, les, porous, vec, collide, block) : lookup_fast_g1_fn(forced, les, porous, vec, collide, block);
+        case 2: return strict ? lookup_strict_g2_fn(forced, les, porous, vec, collide, block) : lookup_fast_g2_fn(forced, les, porous, vec, collide, block);
+        default: return strict ? lookup_strict_g3_fn(forced, les, porous, vec, collide, block) : lookup_fast_g3_fn(forced, les, porous, vec, collide, block);
+    }
+}
+
+static int fill_args(lbm_ctx *ctx, const lbm_fields *f, StepArgs *a) {
+    const lbm_params &p = ctx->p;
+    memset(a, 0, sizeof *a);
+    a->g = ctx->g;
+    a->src = f->f_src; a->dst = f->f_dst; a->rho = f->rho; a->u_src = f->u_src; a->u_dst = f->u_dst;
+    a->force = (p.features & LBM_FEAT_FORCE) ? f->body_force : nullptr;
+    a->phase = (p.features & LBM_FEAT_PHASE) ? f->phase : nullptr;
+    a->blockage = f->blockage; a->flags = f->flags;
+    a->tau_water = p.tau_water; a->tau_air = p.tau_air; a->gravity_lu = p.gravity_lu;
+    a->tau_min = p.tau_min; a->tau_max = p.tau_max;
+    if (p.compat == LBM_COMPAT_REFERENCE) a->les_k = (p.cs_smag * 1.0f) * (p.cs_smag * 1.0f);     // les_turbulence.py:369
+    else a->les_k = (float)(18.0 * sqrt(2.0) * (double)p.cs_smag * (double)p.cs_smag);
+    a->porous_darcy = p.porous_darcy; a->porous_forch = p.porous_forch;
+    a->K_lu = p.K_lu; a->beta_lu = p.beta_lu; a->c_darcy = p.c_darcy; a->c_forch = p.c_forch;
+    if (!f->f_src) return fail(ctx, "f_src is NULL");
+    if ((p.features & LBM_FEAT_WALLS) && !f->flags) return fail(ctx, "LBM_FEAT_WALLS requires a flags field");
+    if ((p.features & LBM_FEAT_FORCE) && !f->body_force) return fail(ctx, "LBM_FEAT_FORCE requires body_force");
+    if ((p.features & LBM_FEAT_PHASE) && !f->phase) return fail(ctx, "LBM_FEAT_PHASE requires phase");
+    return 0;
+}
+
+static int pick_vec(const lbm_ctx *ctx) {
+    int vec = ctx->p.vec;
+    if (vec == 0) vec = 4;
+    if (vec == 2) vec = 1;
+    if (ctx->g.nx % 4 != 0 || ctx->g.nx < 8) vec = 1;
+    return vec;
+}
+
+// launch the step kernel on owned planes [z_begin, z_end)
+static int launch_planes(lbm_ctx *ctx, StepArgs &a, StepKernel k, int block, int vec, int z_begin, int z_end, cudaStream_t s) {
+    if (z_end <= z_begin) return 0;
+    a.z_begin = z_begin; a.z_end = z_end;
+    const long long per_plane = (long long)(ctx->g.nx / vec) * ctx->g.ny;
+    dim3 grid((unsigned)((per_plane + block - 1) / block), (unsigned)(z_end - z_begin));
+    k<<<grid, block, 0, s>>>(a);
+    CUDA_OK(ctx, cudaGetLastError());
+    ctx->launches++;
+    return 0;
+}
+
+// q-planes that cross a z interface: cz=+1 travel up, cz=-1 travel down
+static const int UP_Q[5] = {5, 11, 12, 15, 16};
+static const int DOWN_Q[5] = {6, 13, 14, 17, 18};
+
+static int exchange(lbm_ctx *ctx, float *g, float *vec3, cudaStream_t s) {
+    const Grid &G = ctx->g;
+    if (!G.zg) return 0;
+    const size_t plane = (size_t)G.plane;
+    float *top_owned = g + (size_t)(G.nz) * plane;          // physical plane nz   (last owned)
+    float *bot_owned = g + (size_t)1 * plane;               // physical plane 1    (first owned)
+    float *ghost_lo = g;                                    // physical plane 0
+    float *ghost_hi = g + (size_t)(G.nz + 1) * plane;       // physical plane nz+1
+    const int up = ctx->rank + 1, down = ctx->rank - 1;
+    const bool has_up = up < ctx->nranks || G.per_z, has_down = down >= 0 || G.per_z;
+    const int up_r = (up % ctx->nranks + ctx->nranks) % ctx->nranks, down_r = (down % ctx->nranks + ctx->nranks) % ctx->nranks;
+    if (ctx->nranks == 1) {     // single slab with ghosts ("virtual slab" test mode): periodic wrap onto itself
+        if (!G.per_z) return 0;
+        for (int i = 0; i < 5; ++i) {
+            CUDA_OK(ctx, cudaMemcpyAsync(ghost_lo + (size_t)UP_Q[i] * G.vol, top_owned + (size_t)UP_Q[i] * G.vol, plane * 4, cudaMemcpyDeviceToDevice, s));
+            CUDA_OK(ctx, cudaMemcpyAsync(ghost_hi + (size_t)DOWN_Q[i] * G.vol, bot_owned + (size_t)DOWN_Q[i] * G.vol, plane * 4, cudaMemcpyDeviceToDevice, s));
+        }
+        if (vec3) for (int d = 0; d < 3; ++d) {
+            float *v = vec3 + (size_t)d * G.vol;
+            CUDA_OK(ctx, cudaMemcpyAsync(v, v + (size_t)G.nz * plane, plane * 4, cudaMemcpyDeviceToDevice, s));
+            CUDA_OK(ctx, cudaMemcpyAsync(v + (size_t)(G.nz + 1) * plane, v + plane, plane * 4, cudaMemcpyDeviceToDevice, s));
+        }
+        return 0;
+    }
+    if (!ctx->comm) return fail(ctx, "slab exchange requested but no NCCL communicator attached");
+    NCCL_OK(ctx, g_nccl.GroupStart());
+    for (int i = 0; i < 5; ++i) {
+        if (has_up) {
+            NCCL_OK(ctx, g_nccl.Send(top_owned + (size_t)UP_Q[i] * G.vol, plane, ncclFloat32, up_r, ctx->comm, s));
+            NCCL_OK(ctx, g_nccl.Recv(ghost_hi + (size_t)DOWN_Q[i] * G.vol, plane, ncclFloat32, up_r, ctx->comm, s));
+        }
+        if (has_down) {
+            NCCL_OK(ctx, g_nccl.Send(bot_owned + (size_t)DOWN_Q[i] * G.vol, plane, ncclFloat32, down_r, ctx->comm, s));
+            NCCL_OK(ctx, g_nccl.Recv(ghost_lo + (size_t)UP_Q[i] * G.vol, plane, ncclFloat32, down_r, ctx->comm, s));
+        }
+    }
+    if (vec3) for (int d = 0; d < 3; ++d) {
+        float *v = vec3 + (size_t)d * G.vol;
+        if (has_up) {
+            NCCL_OK(ctx, g_nccl.Send(v + (size_t)G.nz * plane, plane, ncclFloat32, up_r, ctx->comm, s));
+            NCCL_OK(ctx, g_nccl.Recv(v + (size_t)(G.nz + 1) * plane, plane, ncclFloat32, up_r, ctx->comm, s));
+        }
+        if (has_down) {
+            NCCL_OK(ctx, g_nccl.Send(v + plane, plane, ncclFloat32, down_r, ctx->comm, s));
+            NCCL_OK(ctx, g_nccl.Recv(v, plane, ncclFloat32, down_r, ctx->comm, s));
+        }
+    }
+    NCCL_OK(ctx, g_nccl.GroupEnd());
+    return 0;
+}
+
+extern "C" {
+
+int lbm_step(lbm_ctx *ctx, lbm_fields *f, int nsteps, int write_macro_every, void *compute_stream, void *comm_stream) {
+    if (!ctx || !f) return fail(ctx, "null argument");
+    if (!f->f_dst) return fail(ctx, "f_dst is NULL");
+    const lbm_params &p = ctx->p;
+    const int vec = pick_vec(ctx);
+    int block = 0;
+    StepKernel k = lookup(p, vec, 1, &block);
+    if (!k) return fail(ctx, "no step kernel built for this feature combination");
+    const bool ref_les = p.compat == LBM_COMPAT_REFERENCE && (p.features & LBM_FEAT_LES);
+    if (ref_les && write_macro_every != 1) return fail(ctx, "compat=reference with LES needs u every step (write_macro_every must be 1)");
+    if (ref_les && (!f->u_src || !f->u_dst || f->u_src == f->u_dst)) return fail(ctx, "compat=reference with LES needs distinct u_src/u_dst");
+    cudaStream_t cs = (cudaStream_t)compute_stream, ms = (cudaStream_t)comm_stream;
+    const bool slabs = ctx->g.zg == 1;
+    const bool overlap = slabs && ctx->nranks > 1 && ms != nullptr && ms != cs && ctx->g.nz >= 3;
+    for (int s = 0; s < nsteps; ++s) {
+        StepArgs a;
+        if (fill_args(ctx, f, &a)) return 1;
+        const bool last = s == nsteps - 1;
+        a.write_macro = write_macro_every > 0 && (write_macro_every == 1 || last || ((s + 1) % write_macro_every) == 0);
+        if (a.write_macro && (!f->rho || !f->u_dst)) return fail(ctx, "write_macro requested but rho/u_dst is NULL");
+        if (overlap) {
+            // boundary planes first, then the halo travels on the comm stream while the interior runs
+            if (launch_planes(ctx, a, k, block, vec, 0, 1, cs)) return 1;
+            if (launch_planes(ctx, a, k, block, vec, ctx->g.nz - 1, ctx->g.nz, cs)) return 1;
+            CUDA_OK(ctx, cudaEventRecord(ctx->ev_boundary, cs));
+            CUDA_OK(ctx, cudaStreamWaitEvent(ms, ctx->ev_boundary, 0));
+            if (launch_planes(ctx, a, k, block, vec, 1, ctx->g.nz - 1, cs)) return 1;
+            if (exchange(ctx, f->f_dst, (ref_les && a.write_macro) ? f->u_dst : nullptr, ms)) return 1;
+            CUDA_OK(ctx, cudaEventRecord(ctx->ev_comm, ms));
+            CUDA_OK(ctx, cudaStreamWaitEvent(cs, ctx->ev_comm, 0));
+        } else {
+            if (launch_planes(ctx, a, k, block, vec, 0, ctx->g.nz, cs)) return 1;
+            if (slabs && exchange(ctx, f->f_dst, (ref_les && a.write_macro) ? f->u_dst : nullptr, cs)) return 1;
+        }
+        float *t = f->f_src; f->f_src = f->f_dst; f->f_dst = t;
+        if (a.write_macro && f->u_src && f->u_src != f->u_dst) { t = f->u_src; f->u_src = f->u_dst; f->u_dst = t; }
+    }
+    return 0;
+}
+
+int lbm_macroscopic(lbm_ctx *ctx, const lbm_fields *f, void *stream) {
+    if (!ctx || !f) return fail(ctx, "null argument");
+    int block = 0;
+    lbm_params p = ctx->p;
+    p.features &= ~LBM_FEAT_LES;
+    if (p.compat == LBM_COMPAT_REFERENCE) p.features &= ~LBM_FEAT_POROUS;
+    StepKernel k = lookup(p, 1, 0, &block);
+    if (!k) return fail(ctx, "no macroscopic kernel built for this feature combination");
+    StepArgs a;
+    if (fill_args(ctx, f, &a)) return 1;
+    if (!f->rho || !f->u_dst) return fail(ctx, "rho/u_dst is NULL");
+    a.write_macro = 1;
+    return launch_planes(ctx, a, k, block, 1, 0, ctx->g.nz, (cudaStream_t)stream);
+}
+
+int lbm_face_bc(lbm_ctx *ctx, const lbm_fields *f, void *stream) {
+    if (!ctx || !f || !f->rho) return fail(ctx, "null argument");
+    int n = 0;
+    CUDA_OK(ctx, launch_face_bc(ctx->g, f->rho, f->flags, (cudaStream_t)stream, &n));
+    ctx->launches += n;
+    return 0;
+}
+
+int lbm_export_f(lbm_ctx *ctx, const float *g, const uint8_t *flags, float *f_out, void *stream) {
+    if (!ctx || !g || !f_out || g == f_out) return fail(ctx, "bad argument");
+    CUDA_OK(ctx, launch_convert_f(ctx->g, true, g, flags, f_out, (cudaStream_t)stream));
+    ctx->launches++;
+    return 0;
+}
+
+int lbm_import_f(lbm_ctx *ctx, const float *f_in, const uint8_t *flags, float *g, void *stream) {
+    if (!ctx || !g || !f_in || g == f_in) return fail(ctx, "bad argument");
+    CUDA_OK(ctx, launch_convert_f(ctx->g, false, f_in, flags, g, (cudaStream_t)stream));
+    ctx->launches++;
+    return 0;
+}
+
+int lbm_pressure_gradient_force(lbm_ctx *ctx, const float *rho, const uint8_t *flags, float *body_force, float max_force, float scale, void *stream) {
+    if (!ctx || !rho || !body_force) return fail(ctx, "null argument");
+    CUDA_OK(ctx, launch_pressure_gradient(ctx->g, rho, flags, body_force, max_force, scale, (cudaStream_t)stream));
+    ctx->launches++;
+    return 0;
+}
+
+int lbm_forchheimer_force(lbm_ctx *ctx, const float *u, const uint8_t *flags, float *body_force, float fmax, void *stream) {
+    if (!ctx || !u || !flags || !body_force) return fail(ctx, "null argument");
+    const lbm_params &p = ctx->p;
+    CUDA_OK(ctx, launch_forchheimer_force(ctx->g, u, flags, body_force, p.K_lu, p.beta_lu, p.c_darcy, p.c_forch, fmax, (cudaStream_t)stream));
+    ctx->launches++;
+    return 0;
+}
+
+int lbm_add_reaction_force(lbm_ctx *ctx, const float *reaction, const uint8_t *flags, float *body_force, void *stream) {
+    if (!ctx || !reaction || !body_force) return fail(ctx, "null argument");
+    CUDA_OK(ctx, launch_add_reaction(ctx->g, reaction, flags, body_force, (cudaStream_t)stream));
+    ctx->launches++;
+    return 0;
+}
+
+int lbm_particles_couple(lbm_ctx *ctx, const float *u, float *reaction, lbm_particles *ps, float water_density,
+                         float water_viscosity, float relax, void *stream) {
+    if (!ctx || !u || !reaction || !ps) return fail(ctx, "null argument");
+    CUDA_OK(ctx, cudaMemsetAsync(reaction, 0, (size_t)ctx->g.vol * 3 * sizeof(float), (cudaStream_t)stream));
+    CUDA_OK(ctx, launch_particles_couple(ctx->g, u, reaction, *ps, water_density, water_viscosity, relax, (cudaStream_t)stream));
+    ctx->launches += 1;
+    return 0;
+}
+
+int lbm_nccl_unique_id(void *out128) {
+    if (!out128) return fail(nullptr, "null argument");
+    if (load_nccl()) return 1;
+    ncclUniqueId id;
+    NCCL_OK(nullptr, g_nccl.GetUniqueId(&id));
+    memcpy(out128, &id, sizeof id);
+    return 0;
+}
+
+int lbm_attach_nccl(lbm_ctx *ctx, const void *unique_id128, int rank, int nranks) {
+    if (!ctx || !unique_id128) return fail(ctx, "null argument");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(ctx, "bad rank/nranks");
+    ctx->rank = rank; ctx->nranks = nranks;
+    if (nranks == 1) return 0;
+    if (load_nccl()) return fail(ctx, g_error);
+    ncclUniqueId id;
+    memcpy(&id, unique_id128, sizeof id);
+    CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    NCCL_OK(ctx, g_nccl.CommInitRank(&ctx->comm, nranks, id, rank));
+    return 0;
+}
+
+int lbm_halo_exchange(lbm_ctx *ctx, float *g, float *vec3_or_null, void *stream) {
+    if (!ctx || !g) return fail(ctx, "null argument");
+    return exchange(ctx, g, vec3_or_null, (cudaStream_t)stream);
+}
+
+}  // extern "C"

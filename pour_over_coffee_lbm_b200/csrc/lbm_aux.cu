@@ -1,0 +1,296 @@
+// Initialisation, geometry, flag packing, f<->g conversion, face BCs and the small
+// stencil kernels that feed body_force.  Compiled with -fmad=false so that every value is
+// bit-identical to oracle/d3q19_ref.py (these kernels are not on the roofline path).
+#include "lbm_common.cuh"
+
+namespace lbm {
+
+// ---- equilibrium initialisation ---------------------------------------------------------
+// legacy/lbm_solver.py:1067-1112, lbm_unified.py:236-248 (mode's own equilibrium table).
+template <int COMPAT>
+__global__ void init_equilibrium_kernel(Grid G, float *g, const float *rho, const float *u, float rho0,
+                                        float u0x, float u0y, float u0z) {
+    const long long n = G.vol;
+    for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x) {
+        const float r = rho ? rho[c] : rho0;
+        const float ux = u ? u[c] : u0x, uy = u ? u[n + c] : u0y, uz = u ? u[2 * n + c] : u0z;
+        const float u_sq = dot3(ux, uy, uz, ux, uy, uz);
+        static_for<0, Q>([&](auto qq) {
+            constexpr int q = decltype(qq)::value;
+            float eu;
+            if constexpr (COMPAT == LBM_COMPAT_REFERENCE) eu = edot<ex(q), ey(q), ez(q)>(ux, uy, uz);
+            else eu = edot<cx(q), cy(q), cz(q)>(ux, uy, uz);
+            g[(long long)q * n + c] = (wq(q) * r) * (((1.0f + 3.0f * eu) + (4.5f * eu) * eu) - 1.5f * u_sq);
+        });
+    }
+}
+
+// ---- V60 geometry ---------------------------------------------------------------------------
+// FilterPaperSystem._setup_v60_geometry / _setup_filter_zones, filter_paper.py:206-364.
+// Predicates in f32 without contraction; constants arrive f32-rounded from the host.
+__global__ void v60_geometry_kernel(Grid G, uint8_t *solid, int32_t *zone, float top_r, float bot_r, float cup_h,
+                                    float gap, float thick) {
+    const long long n = G.vol;
+    const float cxf = (float)(G.nx * 0.5), cyf = (float)(G.ny * 0.5);
+    const float bottom_z = 5.0f, wall = 2.0f;
+    const float top_z = bottom_z + cup_h;
+    for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(c % G.nx);
+        const int y = (int)((c / G.nx) % G.ny);
+        const int zp = (int)(c / G.plane);
+        const int k = G.z0 + zp - G.zg;                 // global z (ghost planes included)
+        const float dx = (float)x - cxf, dy = (float)y - cyf;
+        const float r = sqrtf(dx * dx + dy * dy);
+        const float z = (float)k;
+        if (solid) {
+            bool is = false;
+            if (z <= bottom_z) { if (r > bot_r) is = true; }
+            else if (z <= top_z) {
+                const float hr = (z - bottom_z) / cup_h;
+                const float inner = bot_r + (top_r - bot_r) * hr;
+                if (r > (inner + gap) + wall) is = true;
+            } else { if (r > top_r + wall) is = true; }
+            if (x <= 2 || x >= G.nx - 3 || y <= 2 || y >= G.ny - 3 || k <= 2 || k >= G.nz_global - 3) is = true;
+            if (k < 0 || k >= G.nz_global) is = true;   // ghost planes outside the global box
+            solid[c] = is ? 1 : 0;
+        }
+        if (zone) {
+            int zn = 0;
+            const float f_bot = 5.0f, f_top = 5.0f + cup_h;
+            if (z >= f_bot && z <= f_top) {
+                float hr = (z - f_bot) / cup_h;
+                hr = fmaxf(0.0f, fminf(1.0f, hr));
+                const float inner_r = bot_r + (top_r - bot_r) * hr;
+                const float f_out = inner_r - gap;
+                const float f_in = f_out - thick;
+                if (f_in <= r && r <= f_out) zn = 1;
+            } else if (z >= f_bot - thick && z < f_bot) {
+                if (r <= bot_r - gap) zn = 1;
+            }
+            zone[c] = zn;
+        }
+    }
+}
+
+// ---- flag packing ---------------------------------------------------------------------------
+__device__ __forceinline__ bool wrap_or_oob(int &v, int n, int per) {
+    if (v < 0) { v = n - 1; return !per; }
+    if (v >= n) { v = 0; return !per; }
+    return false;
+}
+
+__global__ void pack_flags_kernel(Grid G, uint8_t *flags, const uint8_t *solid, const int32_t *zone, const int32_t *les) {
+    const long long n = G.vol;
+    for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(c % G.nx);
+        const int y = (int)((c / G.nx) % G.ny);
+        const int zp = (int)(c / G.plane);
+        const int z = zp - G.zg;
+        unsigned f = 0;
+        if (solid[c]) f |= LBM_FLAG_SOLID;
+        if (zone && zone[c] == 1) f |= LBM_FLAG_FILTER;
+        if (!les || les[c] != 0) f |= LBM_FLAG_LES;
+        bool near = false;
+        if (z >= 0 && z < G.nz) {
+            for (int q = 1; q < Q; ++q) {
+                int xs = x - cx(q), ys = y - cy(q), zs = z - cz(q);
+                bool oob = wrap_or_oob(xs, G.nx, G.per_x) | wrap_or_oob(ys, G.ny, G.per_y);
+                const int zs_g = G.z0 + zs;
+                if (zs_g < 0 || zs_g >= G.nz_global) oob |= !G.per_z;
+                int zsp = zs + G.zg;
+                if (!G.zg) { if (zs < 0) zsp = G.nz - 1; else if (zs >= G.nz) zsp = 0; }
+                if (oob) { near = true; break; }
+                if (solid[((long long)zsp * G.ny + ys) * G.nx + xs]) { near = true; break; }
+            }
+        }
+        if (near) f |= LBM_FLAG_NEAR;
+        flags[c] = (uint8_t)f;
+    }
+}
+
+// ---- exact f <-> g conversion ---------------------------------------------------------------
+// export: f[q,x] = g[q,x-e] (fluid source) | g[opp q,x] (solid source) | w_q (source outside an open face)
+// import: g[q,x] = f[q,x+e] (fluid target) | f[opp q,x] (solid target) | f[q,x] (target outside: dropped later)
+template <bool EXPORT>
+__global__ void convert_f_kernel(Grid G, const float *in, const uint8_t *flags, float *out) {
+    const long long n = G.vol;
+    for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(c % G.nx);
+        const int y = (int)((c / G.nx) % G.ny);
+        const int zp = (int)(c / G.plane);
+        const int z = zp - G.zg;
+        const bool ghost = z < 0 || z >= G.nz;
+        const bool self_solid = flags && (flags[c] & LBM_FLAG_SOLID);
+        for (int q = 0; q < Q; ++q) {
+            float v = in[(long long)q * n + c];
+            if (q > 0 && !ghost && !self_solid) {
+                const int s = EXPORT ? -1 : 1;
+                int xs = x + s * cx(q), ys = y + s * cy(q), zs = z + s * cz(q);
+                bool oob = wrap_or_oob(xs, G.nx, G.per_x) | wrap_or_oob(ys, G.ny, G.per_y);
+                const int zs_g = G.z0 + zs;
+                if (zs_g < 0 || zs_g >= G.nz_global) oob |= !G.per_z;
+                int zsp = zs + G.zg;
+                if (!G.zg) { if (zs < 0) zsp = G.nz - 1; else if (zs >= G.nz) zsp = 0; }
+                if (oob) { if (EXPORT) v = wq(q); }
+                else {
+                    const long long nb = ((long long)zsp * G.ny + ys) * G.nx + xs;
+                    if (flags && (flags[nb] & LBM_FLAG_SOLID)) v = in[(long long)opp(q) * n + c];
+                    else v = in[(long long)q * n + nb];
+                }
+            }
+            out[(long long)q * n + c] = v;
+        }
+    }
+}
+
+// ---- face density writes ----------------------------------------------------------------------
+// boundary_conditions.py:178-324 (SoA branch): only rho is observable (quirk Q5).  One launch
+// per serial Taichi offload: top, bottom, x faces, y faces, z=0 again.
+__global__ void face_bc_kernel(Grid G, float *rho, const uint8_t *flags, int pass) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    auto idx = [&](int x, int y, int zglob) { return ((long long)(zglob - G.z0 + G.zg) * G.ny + y) * G.nx + x; };
+    auto fluid = [&](long long c) { return !(flags && (flags[c] & LBM_FLAG_SOLID)); };
+    auto own = [&](int zglob) { return zglob >= G.z0 && zglob < G.z0 + G.nz; };
+    const int NZ = G.nz_global;
+    if (pass == 0) {            // top
+        if (a < G.nx && b < G.ny && own(NZ - 1)) { long long c = idx(a, b, NZ - 1); if (fluid(c)) rho[c] = 1.0f; }
+    } else if (pass == 1 || pass == 4) {   // bottom / outlet bottom
+        if (a < G.nx && b < G.ny && own(0)) { long long c = idx(a, b, 0); if (fluid(c)) rho[c] = rho[idx(a, b, 1)]; }
+    } else if (pass == 2) {     // x faces: a = y, b = local z
+        if (a < G.ny && b < G.nz) {
+            const int zg_ = G.z0 + b;
+            long long c0 = idx(0, a, zg_), c1 = idx(G.nx - 1, a, zg_);
+            if (fluid(c0)) rho[c0] = rho[idx(1, a, zg_)];
+            if (fluid(c1)) rho[c1] = rho[idx(G.nx - 2, a, zg_)];
+        }
+    } else if (pass == 3) {     // y faces: a = x, b = local z
+        if (a < G.nx && b < G.nz) {
+            const int zg_ = G.z0 + b;
+            long long c0 = idx(a, 0, zg_), c1 = idx(a, G.ny - 1, zg_);
+            if (fluid(c0)) rho[c0] = rho[idx(a, 1, zg_)];
+            if (fluid(c1)) rho[c1] = rho[idx(a, G.ny - 2, zg_)];
+        }
+    }
+}
+
+// ---- neighbours feeding body_force ------------------------------------------------------------
+// pressure_gradient_drive.py:124-193, 274-279
+__global__ void pressure_gradient_kernel(Grid G, const float *rho, const uint8_t *flags, float *bf, float max_force, float scale) {
+    const long long n = G.vol;
+    const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const int x = (int)(c % G.nx);
+    const int y = (int)((c / G.nx) % G.ny);
+    const int zp = (int)(c / G.plane);
+    const int z = zp - G.zg;
+    if (z < 0 || z >= G.nz) return;
+    if (flags && (flags[c] & LBM_FLAG_SOLID)) return;
+    const int k = G.z0 + z;
+    const float r0 = rho[c];
+    float gx, gy, gz;
+    if (x > 0 && x < G.nx - 1) gx = (rho[c + 1] - rho[c - 1]) * 0.5f; else if (x == 0) gx = rho[c + 1] - r0; else gx = r0 - rho[c - 1];
+    if (y > 0 && y < G.ny - 1) gy = (rho[c + G.nx] - rho[c - G.nx]) * 0.5f; else if (y == 0) gy = rho[c + G.nx] - r0; else gy = r0 - rho[c - G.nx];
+    if (k > 0 && k < G.nz_global - 1) gz = (rho[c + G.plane] - rho[c - G.plane]) * 0.5f; else if (k == 0) gz = rho[c + G.plane] - r0; else gz = r0 - rho[c - G.plane];
+    const float cs2 = (float)(1.0 / 3.0);
+    float fx = 0.0f, fy = 0.0f, fz = 0.0f;
+    if (r0 > 1e-12f) {
+        fx = -(gx * cs2) / r0; fy = -(gy * cs2) / r0; fz = -(gz * cs2) / r0;
+        const float mag = sqrtf(dot3(fx, fy, fz, fx, fy, fz));
+        if (mag > max_force) { const float s = max_force / mag; fx = fx * s; fy = fy * s; fz = fz * s; }
+    }
+    if (scale != 1.0f) { fx = scale * fx; fy = scale * fy; fz = scale * fz; }
+    bf[c] = bf[c] + fx; bf[n + c] = bf[n + c] + fy; bf[2 * n + c] = bf[2 * n + c] + fz;
+}
+
+// filter_paper.py:471-536
+__global__ void forchheimer_force_kernel(Grid G, const float *u, const uint8_t *flags, float *bf, float K, float beta,
+                                         float c_darcy, float c_forch, float fmax) {
+    const long long n = G.vol;
+    const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const int x = (int)(c % G.nx);
+    const int y = (int)((c / G.nx) % G.ny);
+    const int zp = (int)(c / G.plane);
+    const int k = G.z0 + zp - G.zg;
+    if (zp - G.zg < 0 || zp - G.zg >= G.nz) return;
+    if (x < 1 || x > G.nx - 2 || y < 1 || y > G.ny - 2 || k < 1 || k > G.nz_global - 2) return;
+    const unsigned f = flags[c];
+    if (!(f & LBM_FLAG_FILTER) || (f & LBM_FLAG_SOLID)) return;
+    const float ux = u[c], uy = u[n + c], uz = u[2 * n + c];
+    const float umag = sqrtf(dot3(ux, uy, uz, ux, uy, uz));
+    if (!(umag > 1e-8f) || !(K > 1e-12f)) return;
+    const float coeff = c_darcy / K + ((c_forch * beta) * umag) / sqrtf(K);
+    float rx = (-coeff) * ux, ry = (-coeff) * uy, rz = (-coeff) * uz;
+    const float mag = sqrtf(dot3(rx, ry, rz, rx, ry, rz));
+    if (mag > fmax) { const float s = fmax / mag; rx = rx * s; ry = ry * s; rz = rz * s; }
+    bf[c] = bf[c] + rx; bf[n + c] = bf[n + c] + ry; bf[2 * n + c] = bf[2 * n + c] + rz;
+}
+
+// legacy/lbm_solver.py:1478-1483
+__global__ void add_reaction_kernel(Grid G, const float *reaction, const uint8_t *flags, float *bf) {
+    const long long n = G.vol;
+    for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x) {
+        if (flags && (flags[c] & LBM_FLAG_SOLID)) continue;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) bf[d * n + c] = bf[d * n + c] + reaction[d * n + c];
+    }
+}
+
+// ---- host launchers (called from lbm_api.cu) -----------------------------------------------
+static inline int grid_for(long long n, int block) { long long g = (n + block - 1) / block; return (int)(g > 148LL * 32 ? 148 * 32 : g); }
+
+cudaError_t launch_init_equilibrium(const Grid &G, int compat, float *g, const float *rho, const float *u, float rho0,
+                                    const float u0[3], cudaStream_t s) {
+    const int b = 256, gr = grid_for(G.vol, b);
+    if (compat == LBM_COMPAT_REFERENCE) init_equilibrium_kernel<LBM_COMPAT_REFERENCE><<<gr, b, 0, s>>>(G, g, rho, u, rho0, u0[0], u0[1], u0[2]);
+    else init_equilibrium_kernel<LBM_COMPAT_PHYSICAL><<<gr, b, 0, s>>>(G, g, rho, u, rho0, u0[0], u0[1], u0[2]);
+    return cudaGetLastError();
+}
+cudaError_t launch_v60_geometry(const Grid &G, uint8_t *solid, int32_t *zone, const float geom[5], cudaStream_t s) {
+    const int b = 256, gr = grid_for(G.vol, b);
+    v60_geometry_kernel<<<gr, b, 0, s>>>(G, solid, zone, geom[0], geom[1], geom[2], geom[3], geom[4]);
+    return cudaGetLastError();
+}
+cudaError_t launch_pack_flags(const Grid &G, uint8_t *flags, const uint8_t *solid, const int32_t *zone, const int32_t *les, cudaStream_t s) {
+    const int b = 256, gr = grid_for(G.vol, b);
+    pack_flags_kernel<<<gr, b, 0, s>>>(G, flags, solid, zone, les);
+    return cudaGetLastError();
+}
+cudaError_t launch_convert_f(const Grid &G, bool to_reference_f, const float *in, const uint8_t *flags, float *out, cudaStream_t s) {
+    const int b = 256, gr = grid_for(G.vol, b);
+    if (to_reference_f) convert_f_kernel<true><<<gr, b, 0, s>>>(G, in, flags, out);
+    else convert_f_kernel<false><<<gr, b, 0, s>>>(G, in, flags, out);
+    return cudaGetLastError();
+}
+// returns the number of launches through *count
+cudaError_t launch_face_bc(const Grid &G, float *rho, const uint8_t *flags, cudaStream_t s, int *count) {
+    const int b = 128;
+    for (int pass = 0; pass < 5; ++pass) {
+        dim3 grid;
+        if (pass == 0 || pass == 1 || pass == 4) grid = dim3((G.nx + b - 1) / b, G.ny);
+        else if (pass == 2) grid = dim3((G.ny + b - 1) / b, G.nz);
+        else grid = dim3((G.nx + b - 1) / b, G.nz);
+        face_bc_kernel<<<grid, b, 0, s>>>(G, rho, flags, pass);
+    }
+    *count = 5;
+    return cudaGetLastError();
+}
+cudaError_t launch_pressure_gradient(const Grid &G, const float *rho, const uint8_t *flags, float *bf, float max_force, float scale, cudaStream_t s) {
+    const int b = 256; const long long gr = (G.vol + b - 1) / b;
+    pressure_gradient_kernel<<<(unsigned)gr, b, 0, s>>>(G, rho, flags, bf, max_force, scale);
+    return cudaGetLastError();
+}
+cudaError_t launch_forchheimer_force(const Grid &G, const float *u, const uint8_t *flags, float *bf, float K, float beta,
+                                     float c_darcy, float c_forch, float fmax, cudaStream_t s) {
+    const int b = 256; const long long gr = (G.vol + b - 1) / b;
+    forchheimer_force_kernel<<<(unsigned)gr, b, 0, s>>>(G, u, flags, bf, K, beta, c_darcy, c_forch, fmax);
+    return cudaGetLastError();
+}
+cudaError_t launch_add_reaction(const Grid &G, const float *reaction, const uint8_t *flags, float *bf, cudaStream_t s) {
+    const int b = 256, gr = grid_for(G.vol, b);
+    add_reaction_kernel<<<gr, b, 0, s>>>(G, reaction, flags, bf);
+    return cudaGetLastError();
+}
+
+}  // namespace lbm

@@ -1,0 +1,68 @@
+// Shared device-side definitions for liblbm_b200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/lbm_b200.h"
+
+namespace lbm {
+
+constexpr int Q = LBM_Q;
+
+// config/core.py:36-38 -- the lattice used for moments, streaming, forcing, opposite table.
+__host__ __device__ constexpr int cx(int q) { constexpr int t[Q] = {0, 1, -1, 0, 0, 0, 0, 1, -1, 1, -1, 1, -1, 1, -1, 0, 0, 0, 0}; return t[q]; }
+__host__ __device__ constexpr int cy(int q) { constexpr int t[Q] = {0, 0, 0, 1, -1, 0, 0, 1, 1, -1, -1, 0, 0, 0, 0, 1, -1, 1, -1}; return t[q]; }
+__host__ __device__ constexpr int cz(int q) { constexpr int t[Q] = {0, 0, 0, 0, 0, 1, -1, 0, 0, 0, 0, 1, 1, -1, -1, 1, 1, -1, -1}; return t[q]; }
+// src/core/lbm_algorithms.py:158-164 -- the table the reference's equilibrium uses (quirk Q1).
+__host__ __device__ constexpr int ex(int q) { return cx(q); }
+__host__ __device__ constexpr int ey(int q) { constexpr int t[Q] = {0, 0, 0, 1, -1, 0, 0, 1, -1, -1, 1, 0, 0, 0, 0, 1, -1, 1, -1}; return t[q]; }
+__host__ __device__ constexpr int ez(int q) { constexpr int t[Q] = {0, 0, 0, 0, 0, 1, -1, 0, 0, 0, 0, 1, -1, -1, 1, 1, -1, -1, 1}; return t[q]; }
+// legacy/lbm_solver.py:431-439 evaluated on the config table.
+__host__ __device__ constexpr int opp(int q) { constexpr int t[Q] = {0, 2, 1, 4, 3, 6, 5, 10, 9, 8, 7, 14, 13, 12, 11, 18, 17, 16, 15}; return t[q]; }
+__host__ __device__ constexpr float wq(int q) { return q == 0 ? (float)(1.0 / 3.0) : (q < 7 ? (float)(1.0 / 18.0) : (float)(1.0 / 36.0)); }
+
+// Geometry of one slab as the kernels see it.
+struct Grid {
+    int nx, ny, nz;        // owned extent
+    int zg;                // ghost planes per z side
+    int nz_global, z0;
+    int per_x, per_y, per_z;
+    long long plane;       // nx*ny
+    long long vol;         // nx*ny*(nz+2*zg): stride between populations / vector components
+};
+
+struct StepArgs {
+    Grid g;
+    const float *src; float *dst;
+    float *rho; const float *u_src; float *u_dst;
+    const float *force; const float *phase; const float *blockage;
+    const uint8_t *flags;
+    int z_begin, z_end;    // owned planes processed by this launch
+    int write_macro;
+    float tau_water, tau_air, gravity_lu;
+    float tau_min, tau_max;
+    float les_k;           // physical: 18*sqrt(2)*Cs^2 ; reference: (Cs*1)*(Cs*1)
+    float porous_darcy, porous_forch;
+    float K_lu, beta_lu, c_darcy, c_forch;
+};
+
+// e . v for e components in {0,+1,-1}: sum of the non-zero terms in x,y,z order (one rounding per add).
+template <int EX, int EY, int EZ>
+__device__ __forceinline__ float edot(float vx, float vy, float vz) {
+    float acc = 0.0f;
+    if (EX != 0) acc = EX > 0 ? vx : -vx;
+    if (EY != 0) { float t = EY > 0 ? vy : -vy; acc = (EX != 0) ? acc + t : t; }
+    if (EZ != 0) { float t = EZ > 0 ? vz : -vz; acc = (EX != 0 || EY != 0) ? acc + t : t; }
+    return acc;
+}
+__device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, float by, float bz) {
+    return (ax * bx + ay * by) + az * bz;
+}
+
+template <int N> struct IC { static constexpr int value = N; };
+// compile-time loop: f(IC<0>{}), f(IC<1>{}), ...
+template <int B, int E, class F>
+__device__ __forceinline__ void static_for(F &&f) {
+    if constexpr (B < E) { f(IC<B>{}); static_for<B + 1, E>(f); }
+}
+
+}  // namespace lbm

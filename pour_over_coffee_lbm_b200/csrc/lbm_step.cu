@@ -1,0 +1,63 @@
+// Instantiates one group of step-kernel variants and exports a lookup function for it.
+// Compiled 8 times: LBM_GROUP in {0..3} = COMPAT*2 + WALLS, LBM_STRICT_BUILD in {0,1}
+// (strict adds -fmad=false on the nvcc command line; see csrc/Makefile).
+#include "lbm_step_kernel.cuh"
+
+#ifndef LBM_GROUP
+#error "LBM_GROUP must be defined (0..3)"
+#endif
+#ifndef LBM_STRICT_BUILD
+#error "LBM_STRICT_BUILD must be defined (0/1)"
+#endif
+
+namespace lbm {
+
+using StepKernel = void (*)(const StepArgs);
+
+constexpr int G_COMPAT = LBM_GROUP / 2;
+constexpr bool G_WALLS = (LBM_GROUP % 2) != 0;
+
+template <bool FORCED, bool LES, bool POROUS, int VEC, bool COLLIDE>
+static StepKernel pick() {
+    if constexpr (POROUS && !G_WALLS) return nullptr;          // the filter zone lives in the flag byte
+    else if constexpr (!COLLIDE && (LES || VEC != 1)) return nullptr;
+    else return step_kernel<G_COMPAT, G_WALLS, FORCED, LES, POROUS, VEC, (VEC == 1 ? 256 : 128), COLLIDE>;
+}
+
+template <int VEC, bool COLLIDE>
+static StepKernel pick_feat(int forced, int les, int porous) {
+    const int key = (forced ? 4 : 0) | (les ? 2 : 0) | (porous ? 1 : 0);
+    switch (key) {
+        case 0: return pick<false, false, false, VEC, COLLIDE>();
+        case 1: return pick<false, false, true, VEC, COLLIDE>();
+        case 2: return pick<false, true, false, VEC, COLLIDE>();
+        case 3: return pick<false, true, true, VEC, COLLIDE>();
+        case 4: return pick<true, false, false, VEC, COLLIDE>();
+        case 5: return pick<true, false, true, VEC, COLLIDE>();
+        case 6: return pick<true, true, false, VEC, COLLIDE>();
+        default: return pick<true, true, true, VEC, COLLIDE>();
+    }
+}
+
+#define LBM_CAT2(a, b, c) a##b##_##c
+#define LBM_CAT(a, b, c) LBM_CAT2(a, b, c)
+#if LBM_STRICT_BUILD
+#define LBM_LOOKUP LBM_CAT(lookup_strict_g, LBM_GROUP, fn)
+#else
+#define LBM_LOOKUP LBM_CAT(lookup_fast_g, LBM_GROUP, fn)
+#endif
+
+// returns the kernel and its CTA size, or nullptr when the combination is not built
+StepKernel LBM_LOOKUP(int forced, int les, int porous, int vec, int collide, int *block) {
+    StepKernel k = nullptr;
+    if (collide) {
+        if (vec == 4) k = pick_feat<4, true>(forced, les, porous);
+        else if (vec == 1) k = pick_feat<1, true>(forced, les, porous);
+    } else {
+        if (vec == 1) k = pick_feat<1, false>(forced, les, porous);
+    }
+    *block = (vec == 1) ? 256 : 128;
+    return k;
+}
+
+}  // namespace lbm

@@ -1,0 +1,471 @@
+// The fused D3Q19 pull-scheme collide-stream kernel (sm_100a).
+//
+// One launch = one time step of LBMSolver.step() (legacy/lbm_solver.py:817-867):
+//   stream-on-read (pull) of the 19 post-collision populations, halfway bounce-back
+//   against the solid mask, macroscopic moments, body force (Guo), Smagorinsky LES,
+//   filter-paper drag, BGK relaxation, 128-bit coalesced write-back.
+// The kernel is HBM-bound (152 B of populations per cell update, ~2.7 flop/B); it uses no
+// tensor cores.  Every population element is read exactly once and written exactly once
+// per step, so loads/stores carry streaming (evict-first) hints.
+//
+// Template parameters
+//   COMPAT  LBM_COMPAT_PHYSICAL | LBM_COMPAT_REFERENCE   
+//   WALLS   flag byte consulted (solid skip, bounce-back, open faces); else fully periodic
+//   FORCED  body_force / phase inputs active (either pointer may still be NULL)
+//   LES     Smagorinsky: physical = local Pi^neq closed form, reference = FD on lagged u
+//   POROUS  filter-zone drag: physical = Guo-Zhao force, reference = post-step u damping
+//   VEC     cells per thread along x (1 or 4): VEC=4 uses aligned 128-bit loads and takes
+//           the x+-1 neighbours of the shifted populations from the adjacent lane (shuffle).
+// Arithmetic order follows oracle/d3q19_ref.py exactly; the translation unit is compiled
+// twice, with -fmad=false ("strict", bit-exact against the oracle) and with FMA contraction.
+#pragma once
+#include "lbm_common.cuh"
+
+namespace lbm {
+
+template <int VEC> __device__ __forceinline__ void ld_stream(const float *p, float (&v)[VEC]);
+template <> __device__ __forceinline__ void ld_stream<1>(const float *p, float (&v)[1]) { v[0] = __ldcs(p); }
+template <> __device__ __forceinline__ void ld_stream<2>(const float *p, float (&v)[2]) {
+    float2 t = __ldcs(reinterpret_cast<const float2 *>(p)); v[0] = t.x; v[1] = t.y;
+}
+template <> __device__ __forceinline__ void ld_stream<4>(const float *p, float (&v)[4]) {
+    float4 t = __ldcs(reinterpret_cast<const float4 *>(p)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <int VEC> __device__ __forceinline__ void ld_cached(const float *p, float (&v)[VEC]);
+template <> __device__ __forceinline__ void ld_cached<1>(const float *p, float (&v)[1]) { v[0] = __ldg(p); }
+template <> __device__ __forceinline__ void ld_cached<2>(const float *p, float (&v)[2]) {
+    float2 t = __ldg(reinterpret_cast<const float2 *>(p)); v[0] = t.x; v[1] = t.y;
+}
+template <> __device__ __forceinline__ void ld_cached<4>(const float *p, float (&v)[4]) {
+    float4 t = __ldg(reinterpret_cast<const float4 *>(p)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <int VEC> __device__ __forceinline__ void st_stream(float *p, const float (&v)[VEC]);
+template <> __device__ __forceinline__ void st_stream<1>(float *p, const float (&v)[1]) { __stcs(p, v[0]); }
+template <> __device__ __forceinline__ void st_stream<2>(float *p, const float (&v)[2]) {
+    __stcs(reinterpret_cast<float2 *>(p), make_float2(v[0], v[1]));
+}
+template <> __device__ __forceinline__ void st_stream<4>(float *p, const float (&v)[4]) {
+    __stcs(reinterpret_cast<float4 *>(p), make_float4(v[0], v[1], v[2], v[3]));
+}
+
+struct CellAux {
+    float Fx, Fy, Fz;   // body_force at the cell
+    float phase;
+    float nu_sgs;       // reference-mode FD eddy viscosity
+    float blockage;
+    unsigned flag;
+    bool interior;      // 1 <= x,y,z <= N-2 in global coordinates
+};
+struct CellOut { float rho, ux, uy, uz; };
+
+// ---------------------------------------------------------------------------------------------
+// compat = reference: legacy/lbm_solver.py:488-628, 688-764; lbm_algorithms.py:183-218;
+// filter_paper.py:538-614.  Same order of operations as oracle/ref_cpu.c.
+// ---------------------------------------------------------------------------------------------
+template <bool FORCED, bool LES, bool POROUS>
+__device__ __forceinline__ void collide_reference(float (&f)[Q], const CellAux &a, CellOut &o, const StepArgs &P) {
+    float rho = 0.0f;
+    static_for<0, Q>([&](auto qq) { constexpr int q = decltype(qq)::value; rho += f[q]; });
+    float mx = 0.0f, my = 0.0f, mz = 0.0f;
+    static_for<0, Q>([&](auto qq) {
+        constexpr int q = decltype(qq)::value;
+        if constexpr (cx(q) != 0) mx += f[q] * (float)cx(q);
+        if constexpr (cy(q) != 0) my += f[q] * (float)cy(q);
+        if constexpr (cz(q) != 0) mz += f[q] * (float)cz(q);
+    });
+    float Fx = 0.0f, Fy = 0.0f, Fz = 0.0f;
+    const float ph = FORCED ? a.phase : 0.0f;
+    if constexpr (FORCED) {
+        const float gz = ph > 0.001f ? -(P.gravity_lu * ph) : 0.0f;
+        Fx = 0.0f + a.Fx; Fy = 0.0f + a.Fy; Fz = gz + a.Fz;
+    }
+    float ux = 0.0f, uy = 0.0f, uz = 0.0f;
+    if (rho > 1e-12f) {
+        ux = (mx + 0.5f * Fx) / rho; uy = (my + 0.5f * Fy) / rho; uz = (mz + 0.5f * Fz) / rho;
+    }
+    float tau = ph > 0.5f ? P.tau_water : P.tau_air;
+    if constexpr (LES) tau = tau + 3.0f * a.nu_sgs;
+    tau = fmaxf(P.tau_min, fminf(P.tau_max, tau));
+    const float omega = 1.0f / tau;
+    // forcing prerequisites (identical for all q)
+    bool forced = false;
+    float tau_safe = 0.0f, fsx = 0.0f, fsy = 0.0f, fsz = 0.0f, usx = ux, usy = uy, usz = uz, uf = 0.0f;
+    if constexpr (FORCED) {
+        const float fnorm = sqrtf(dot3(Fx, Fy, Fz, Fx, Fy, Fz));
+        forced = fnorm > 1e-15f;
+        tau_safe = fminf(fmaxf(tau, 0.6f), 1.5f);
+        const float sf = fnorm > 10.0f ? 10.0f / fnorm : 1.0f;
+        fsx = Fx * sf; fsy = Fy * sf; fsz = Fz * sf;
+        const float unorm = sqrtf(dot3(ux, uy, uz, ux, uy, uz));
+        if (unorm > 0.2f) { const float s = 0.2f / unorm; usx = ux * s; usy = uy * s; usz = uz * s; }
+        uf = dot3(usx, usy, usz, fsx, fsy, fsz);
+    }
+    const float u_sq = dot3(ux, uy, uz, ux, uy, uz);
+    static_for<0, Q>([&](auto qq) {
+        constexpr int q = decltype(qq)::value;
+        constexpr float w = wq(q);
+        const float eu = edot<ex(q), ey(q), ez(q)>(ux, uy, uz);           // quirk Q1: equilibrium table
+        const float feq = (w * rho) * (((1.0f + 3.0f * eu) + (4.5f * eu) * eu) - 1.5f * u_sq);
+        float Fq = 0.0f;
+        if constexpr (FORCED) {
+            if (forced) {
+                const float eus = edot<cx(q), cy(q), cz(q)>(usx, usy, usz);
+                const float ef = edot<cx(q), cy(q), cz(q)>(fsx, fsy, fsz);
+                const float coeff = w * (1.0f - 0.5f / tau_safe);
+                Fq = coeff * (3.0f * ef + (9.0f * eus) * uf);
+                Fq = fmaxf(-0.5f, fminf(0.5f, Fq));
+            }
+        }
+        f[q] = (f[q] - omega * (f[q] - feq)) + Fq;
+    });
+    // externally visible u: filter damping applied after the step (quirk Q5)
+    if constexpr (POROUS) {
+        if ((a.flag & LBM_FLAG_FILTER) && a.interior) {
+            const float umag = sqrtf(dot3(ux, uy, uz, ux, uy, uz));
+            if (umag > 1e-8f && P.K_lu > 1e-12f) {
+                const float darcy = P.c_darcy / P.K_lu;
+                const float forch = ((P.c_forch * P.beta_lu) * umag) / sqrtf(P.K_lu);
+                const float total = (darcy + forch) * (1.0f + a.blockage);
+                float r = expf((-total) * 0.5f);
+                r = fmaxf(0.1f, r);
+                const float hf = (r + 1.0f) * 0.5f;
+                uz = uz * r; ux = ux * hf; uy = uy * hf;
+            }
+        }
+    }
+    o.rho = rho; o.ux = ux; o.uy = uy; o.uz = uz;
+}
+
+// ---------------------------------------------------------------------------------------------
+// compat = physical: consistent lattice, Guo forcing (Guo, Zheng, Shi 2002), local-stress
+// Smagorinsky (Hou et al. 1996), Guo-Zhao (2002) porous drag.  Same order as
+// oracle/d3q19_ref.py:step_physical.
+// ---------------------------------------------------------------------------------------------
+template <bool FORCED, bool LES, bool POROUS>
+__device__ __forceinline__ void collide_physical(float (&f)[Q], const CellAux &a, CellOut &o, const StepArgs &P,
+                                                 bool has_phase, bool has_force) {
+    float rho = 0.0f;
+    static_for<0, Q>([&](auto qq) { constexpr int q = decltype(qq)::value; rho += f[q]; });
+    float mx = 0.0f, my = 0.0f, mz = 0.0f;
+    static_for<0, Q>([&](auto qq) {
+        constexpr int q = decltype(qq)::value;
+        if constexpr (cx(q) != 0) mx += f[q] * (float)cx(q);
+        if constexpr (cy(q) != 0) my += f[q] * (float)cy(q);
+        if constexpr (cz(q) != 0) mz += f[q] * (float)cz(q);
+    });
+    const float inv_rho = 1.0f / rho;
+    float Fx = 0.0f, Fy = 0.0f, Fz = 0.0f, ux, uy, uz;
+    bool forced = false;
+    if constexpr (FORCED) {
+        forced = has_force;
+        if (has_force) {
+            Fx = a.Fx; Fy = a.Fy; Fz = a.Fz;
+            if (has_phase && P.gravity_lu != 0.0f) Fz = Fz - P.gravity_lu * a.phase;
+            ux = (mx + 0.5f * Fx) * inv_rho; uy = (my + 0.5f * Fy) * inv_rho; uz = (mz + 0.5f * Fz) * inv_rho;
+        } else {
+            ux = mx * inv_rho; uy = my * inv_rho; uz = mz * inv_rho;
+        }
+    } else {
+        ux = mx * inv_rho; uy = my * inv_rho; uz = mz * inv_rho;
+    }
+    if constexpr (POROUS) {
+        const bool zone = (a.flag & LBM_FLAG_FILTER) != 0;
+        const float vmag = sqrtf(dot3(ux, uy, uz, ux, uy, uz));
+        const float c0 = 0.5f * (1.0f + 0.5f * P.porous_darcy);
+        const float c1 = 0.5f * P.porous_forch;
+        const float den = c0 + sqrtf(c0 * c0 + c1 * vmag);
+        const float s = zone ? 1.0f / den : 1.0f;
+        ux = ux * s; uy = uy * s; uz = uz * s;
+        const float umag = vmag * s;
+        const float cdrag = zone ? P.porous_darcy + P.porous_forch * umag : 0.0f;
+        const float dx = -(cdrag * rho) * ux, dy = -(cdrag * rho) * uy, dz = -(cdrag * rho) * uz;
+        if (forced) { Fx = Fx + dx; Fy = Fy + dy; Fz = Fz + dz; }
+        else { Fx = dx; Fy = dy; Fz = dz; }
+        forced = true;
+    }
+    float tau0 = P.tau_water;
+    if constexpr (FORCED) { if (has_phase) tau0 = a.phase > 0.5f ? P.tau_water : P.tau_air; }
+    const float u_sq = dot3(ux, uy, uz, ux, uy, uz);
+    float feq[Q];
+    static_for<0, Q>([&](auto qq) {
+        constexpr int q = decltype(qq)::value;
+        constexpr float w = wq(q);
+        const float eu = edot<cx(q), cy(q), cz(q)>(ux, uy, uz);
+        feq[q] = (w * rho) * (((1.0f + 3.0f * eu) + (4.5f * eu) * eu) - 1.5f * u_sq);
+    });
+    float tau = tau0;
+    if constexpr (LES) {
+        float pxx = 0.0f, pyy = 0.0f, pzz = 0.0f, pxy = 0.0f, pxz = 0.0f, pyz = 0.0f;
+        static_for<0, Q>([&](auto qq) {
+            constexpr int q = decltype(qq)::value;
+            const float d = f[q] - feq[q];
+            if constexpr (cx(q) != 0) pxx += d;
+            if constexpr (cy(q) != 0) pyy += d;
+            if constexpr (cz(q) != 0) pzz += d;
+            if constexpr (cx(q) * cy(q) != 0) pxy += d * (float)(cx(q) * cy(q));
+            if constexpr (cx(q) * cz(q) != 0) pxz += d * (float)(cx(q) * cz(q));
+            if constexpr (cy(q) * cz(q) != 0) pyz += d * (float)(cy(q) * cz(q));
+        });
+        const float qn = sqrtf(((pxx * pxx + pyy * pyy) + pzz * pzz) + 2.0f * ((pxy * pxy + pxz * pxz) + pyz * pyz));
+        tau = 0.5f * (tau0 + sqrtf(tau0 * tau0 + (P.les_k * qn) * inv_rho));
+        if (!(a.flag & LBM_FLAG_LES)) tau = tau0;
+        tau = fmaxf(P.tau_min, fminf(P.tau_max, tau));
+    }
+    const float omega = 1.0f / tau;
+    const float pref = 1.0f - 0.5f * omega;
+    const float uF = dot3(ux, uy, uz, Fx, Fy, Fz);
+    static_for<0, Q>([&](auto qq) {
+        constexpr int q = decltype(qq)::value;
+        constexpr float w = wq(q);
+        float out = f[q] - omega * (f[q] - feq[q]);
+        if constexpr (FORCED || POROUS) {
+            if (forced) {
+                const float eu = edot<cx(q), cy(q), cz(q)>(ux, uy, uz);
+                const float eF = edot<cx(q), cy(q), cz(q)>(Fx, Fy, Fz);
+                out = out + (w * pref) * ((3.0f * (eF - uF)) + (9.0f * eu) * eF);
+            }
+        }
+        f[q] = out;
+    });
+    o.rho = rho; o.ux = ux; o.uy = uy; o.uz = uz;
+}
+
+// ---------------------------------------------------------------------------------------------
+// reference-mode LES pre-pass fused as a stencil read of the previous step's u
+// (les_turbulence.py:318-380).  `c` = linear index of the cell in a scalar volume.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float les_fd_nu(const float *__restrict__ u, long long c, long long sy, long long sz,
+                                           long long vol, float phase, float csd) {
+    const float *ux = u, *uy = u + vol, *uz = u + 2 * vol;
+    const float dudx = (__ldg(ux + c + 1) - __ldg(ux + c - 1)) * 0.5f;
+    const float dudy = (__ldg(ux + c + sy) - __ldg(ux + c - sy)) * 0.5f;
+    const float dudz = (__ldg(ux + c + sz) - __ldg(ux + c - sz)) * 0.5f;
+    const float dvdx = (__ldg(uy + c + 1) - __ldg(uy + c - 1)) * 0.5f;
+    const float dvdy = (__ldg(uy + c + sy) - __ldg(uy + c - sy)) * 0.5f;
+    const float dvdz = (__ldg(uy + c + sz) - __ldg(uy + c - sz)) * 0.5f;
+    const float dwdx = (__ldg(uz + c + 1) - __ldg(uz + c - 1)) * 0.5f;
+    const float dwdy = (__ldg(uz + c + sy) - __ldg(uz + c - sy)) * 0.5f;
+    const float dwdz = (__ldg(uz + c + sz) - __ldg(uz + c - sz)) * 0.5f;
+    const float S11 = dudx, S22 = dvdy, S33 = dwdz;
+    const float S12 = 0.5f * (dudy + dvdx), S13 = 0.5f * (dudz + dwdx), S23 = 0.5f * (dvdz + dwdy);
+    const float mag = sqrtf(2.0f * (((S11 * S11 + S22 * S22) + S33 * S33) + 2.0f * ((S12 * S12 + S13 * S13) + S23 * S23)));
+    if (mag < 1e-3f) return 0.0f;
+    if (fabsf(phase) < 0.9f) return 0.0f;
+    return fminf(csd * mag, 0.1f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+template <int COMPAT, bool WALLS, bool FORCED, bool LES, bool POROUS, int VEC, int BLOCK, bool COLLIDE = true>
+__global__ void __launch_bounds__(BLOCK) step_kernel(const StepArgs P) {
+    const Grid &G = P.g;
+    const int nxv = G.nx / VEC;
+    const int per_plane = nxv * G.ny;
+    int t = blockIdx.x * BLOCK + threadIdx.x;
+    const bool active = t < per_plane;
+    if (!active) t = per_plane - 1;
+    const int y = t / nxv;
+    const int xv = t - y * nxv;
+    const int x0 = xv * VEC;
+    const int z = P.z_begin + blockIdx.y;
+    const int zp = z + G.zg;
+    const long long own = ((long long)zp * G.ny + y) * G.nx + x0;
+    const unsigned lane = threadIdx.x & 31u;
+    constexpr unsigned FULL = 0xffffffffu;
+
+    unsigned fl[VEC];
+    bool any_solid = false, all_solid = true, any_near = false;
+    if constexpr (WALLS) {
+        if constexpr (VEC == 4) {
+            const unsigned w = __ldg(reinterpret_cast<const unsigned *>(P.flags + own));
+#pragma unroll
+            for (int c = 0; c < 4; ++c) fl[c] = (w >> (8 * c)) & 0xffu;
+        } else if constexpr (VEC == 2) {
+            const unsigned short w = __ldg(reinterpret_cast<const unsigned short *>(P.flags + own));
+            fl[0] = w & 0xffu; fl[1] = (w >> 8) & 0xffu;
+        } else {
+            fl[0] = __ldg(P.flags + own);
+        }
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) {
+            const bool s = (fl[c] & LBM_FLAG_SOLID) != 0;
+            any_solid |= s; all_solid &= s; any_near |= (!s && (fl[c] & LBM_FLAG_NEAR));
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) fl[c] = LBM_FLAG_LES;
+        all_solid = false;
+    }
+    const bool skip = !active || all_solid;
+    if (__all_sync(FULL, skip)) return;   // whole warp solid (65 % of a V60 box): 1 B/cell and done
+
+    // neighbour rows / columns with periodic wrap (open faces clamp; the value is replaced below)
+    int ym = y - 1; if (ym < 0) ym = G.per_y ? G.ny - 1 : 0;
+    int yq = y + 1; if (yq >= G.ny) yq = G.per_y ? 0 : G.ny - 1;
+    int zm, zq;
+    if (G.zg) { zm = zp - 1; zq = zp + 1; }
+    else {
+        zm = z - 1; if (zm < 0) zm = G.per_z ? G.nz - 1 : 0;
+        zq = z + 1; if (zq >= G.nz) zq = G.per_z ? 0 : G.nz - 1;
+    }
+    int xm = x0 - 1; if (xm < 0) xm = G.per_x ? G.nx - 1 : 0;
+    int xq = x0 + VEC; if (xq >= G.nx) xq = G.per_x ? 0 : G.nx - 1;
+
+    float f[Q][VEC];
+    static_for<0, Q>([&](auto qq) {
+        constexpr int q = decltype(qq)::value;
+        const int rz = cz(q) > 0 ? zm : (cz(q) < 0 ? zq : zp);
+        const int ry = cy(q) > 0 ? ym : (cy(q) < 0 ? yq : y);
+        const float *row = P.src + (long long)q * G.vol + ((long long)rz * G.ny + ry) * G.nx;
+        if constexpr (VEC == 1 && cx(q) != 0) {
+            f[q][0] = skip ? 0.0f : __ldcs(row + (cx(q) > 0 ? xm : xq));
+        } else {
+            float a[VEC];
+            if (!skip) ld_stream<VEC>(row + x0, a);
+            else {
+#pragma unroll
+                for (int c = 0; c < VEC; ++c) a[c] = 0.0f;
+            }
+            if constexpr (cx(q) == 0) {
+#pragma unroll
+                for (int c = 0; c < VEC; ++c) f[q][c] = a[c];
+            } else if constexpr (cx(q) > 0) {      // source is x-1: take it from the left lane
+                float left = __shfl_up_sync(FULL, a[VEC - 1], 1);
+                if ((lane == 0 || xv == 0) && !skip) left = __ldg(row + xm);
+                f[q][0] = left;
+#pragma unroll
+                for (int c = 1; c < VEC; ++c) f[q][c] = a[c - 1];
+            } else {                               // source is x+1: take it from the right lane
+                float right = __shfl_down_sync(FULL, a[0], 1);
+                if ((lane == 31 || xv == nxv - 1) && !skip) right = __ldg(row + xq);
+#pragma unroll
+                for (int c = 0; c < VEC - 1; ++c) f[q][c] = a[c + 1];
+                f[q][VEC - 1] = right;
+            }
+        }
+    });
+    if (skip) return;
+
+    // halfway bounce-back + open-face inflow for near-wall cells (legacy/lbm_solver.py:609-628)
+    if constexpr (WALLS) {
+        if (any_near) {
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) {
+                if ((fl[c] & LBM_FLAG_NEAR) && !(fl[c] & LBM_FLAG_SOLID)) {
+                    const int x = x0 + c;
+                    static_for<1, Q>([&](auto qq) {
+                        constexpr int q = decltype(qq)::value;
+                        int xs = x - cx(q), ys = y - cy(q), zs = z - cz(q);
+                        const int zs_g = G.z0 + zs;
+                        bool oob = false;
+                        if (cx(q) != 0) { if (xs < 0) { oob |= !G.per_x; xs = G.nx - 1; } else if (xs >= G.nx) { oob |= !G.per_x; xs = 0; } }
+                        if (cy(q) != 0) { if (ys < 0) { oob |= !G.per_y; ys = G.ny - 1; } else if (ys >= G.ny) { oob |= !G.per_y; ys = 0; } }
+                        int zsp = zs + G.zg;
+                        if (cz(q) != 0) {
+                            if (zs_g < 0 || zs_g >= G.nz_global) oob |= !G.per_z;
+                            if (!G.zg) { if (zs < 0) zsp = G.nz - 1; else if (zs >= G.nz) zsp = 0; }
+                        }
+                        if (oob) {
+                            f[q][c] = wq(q);    // stale inflow, SURVEY.md A.2-Q6
+                        } else {
+                            const unsigned nf = __ldg(P.flags + ((long long)zsp * G.ny + ys) * G.nx + xs);
+                            if (nf & LBM_FLAG_SOLID) f[q][c] = __ldg(P.src + (long long)opp(q) * G.vol + own + c);
+                        }
+                    });
+                }
+            }
+        }
+    }
+
+    // auxiliary inputs
+    float bf[3][VEC], ph[VEC];
+    bool has_force = false, has_phase = false;
+    if constexpr (FORCED) {
+        has_phase = P.phase != nullptr;
+        has_force = P.force != nullptr || (has_phase && P.gravity_lu != 0.0f);
+        if (P.force != nullptr) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) ld_cached<VEC>(P.force + (long long)d * G.vol + own, bf[d]);
+        } else {
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+#pragma unroll
+                for (int c = 0; c < VEC; ++c) bf[d][c] = 0.0f;
+        }
+        if (has_phase) ld_cached<VEC>(P.phase + own, ph);
+        else {
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) ph[c] = 0.0f;
+        }
+    }
+
+    CellOut out[VEC];
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) {
+        CellAux a;
+        a.flag = fl[c];
+        a.Fx = FORCED ? bf[0][c] : 0.0f; a.Fy = FORCED ? bf[1][c] : 0.0f; a.Fz = FORCED ? bf[2][c] : 0.0f;
+        a.phase = FORCED ? ph[c] : 0.0f;
+        a.blockage = 0.0f; a.nu_sgs = 0.0f;
+        const int x = x0 + c, zg_ = G.z0 + z;
+        a.interior = x >= 1 && x <= G.nx - 2 && y >= 1 && y <= G.ny - 2 && zg_ >= 1 && zg_ <= G.nz_global - 2;
+        if constexpr (COMPAT == LBM_COMPAT_REFERENCE) {
+            if constexpr (POROUS) { if (P.blockage) a.blockage = __ldg(P.blockage + own + c); }
+            if constexpr (LES) {
+                if (a.interior && (fl[c] & LBM_FLAG_LES) && !(fl[c] & LBM_FLAG_SOLID))
+                    a.nu_sgs = les_fd_nu(P.u_src, own + c, G.nx, G.plane, G.vol, a.phase, P.les_k);
+            }
+        }
+        float fc[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) fc[q] = f[q][c];
+        if constexpr (COLLIDE) {
+            if constexpr (COMPAT == LBM_COMPAT_REFERENCE) collide_reference<FORCED, LES, POROUS>(fc, a, out[c], P);
+            else collide_physical<FORCED, LES, POROUS>(fc, a, out[c], P, has_phase, has_force);
+#pragma unroll
+            for (int q = 0; q < Q; ++q) f[q][c] = fc[q];
+        } else {
+            // moments only (lbm_macroscopic): reuse the collide routine on a scratch copy
+            if constexpr (COMPAT == LBM_COMPAT_REFERENCE) collide_reference<FORCED, false, false>(fc, a, out[c], P);
+            else collide_physical<FORCED, false, POROUS>(fc, a, out[c], P, has_phase, has_force);
+        }
+    }
+
+    // write-back
+    if constexpr (COLLIDE) {
+        if (!any_solid) {
+            static_for<0, Q>([&](auto qq) {
+                constexpr int q = decltype(qq)::value;
+                st_stream<VEC>(P.dst + (long long)q * G.vol + own, f[q]);
+            });
+        } else {
+#pragma unroll
+            for (int c = 0; c < VEC; ++c)
+                if (!(fl[c] & LBM_FLAG_SOLID)) {
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) P.dst[(long long)q * G.vol + own + c] = f[q][c];
+                }
+        }
+    }
+    if (P.write_macro) {
+        if (!any_solid) {
+            float r[VEC], a0[VEC], a1[VEC], a2[VEC];
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) { r[c] = out[c].rho; a0[c] = out[c].ux; a1[c] = out[c].uy; a2[c] = out[c].uz; }
+            st_stream<VEC>(P.rho + own, r);
+            st_stream<VEC>(P.u_dst + own, a0);
+            st_stream<VEC>(P.u_dst + G.vol + own, a1);
+            st_stream<VEC>(P.u_dst + 2 * G.vol + own, a2);
+        } else {
+#pragma unroll
+            for (int c = 0; c < VEC; ++c)
+                if (!(fl[c] & LBM_FLAG_SOLID)) {
+                    P.rho[own + c] = out[c].rho;
+                    P.u_dst[own + c] = out[c].ux; P.u_dst[G.vol + own + c] = out[c].uy; P.u_dst[2 * G.vol + own + c] = out[c].uz;
+                }
+        }
+    }
+}
+
+}  // namespace lbm
