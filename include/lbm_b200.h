@@ -158,6 +158,10 @@ typedef struct {
 int  lbm_particles_couple(lbm_ctx *ctx, const float *u, float *reaction, lbm_particles *ps,
                           float water_density, float water_viscosity, float relax, void *stream);
 
+/* CoffeeParticleSystem.apply_under_relaxation coffee_particles.py:1200-1212 as a separate call
+ * (lbm_particles_couple fuses it when relax >= 0; pass relax < 0 there to skip). */
+int  lbm_particles_under_relax(lbm_ctx *ctx, lbm_particles *ps, float relax, void *stream);
+
 /* ---- multi-GPU slabs -------------------------------------------------------------------- */
 /* Attach an NCCL communicator over the ranks of one box (z-slab chain).  unique_id is the
  * 128-byte ncclUniqueId produced by lbm_nccl_unique_id on rank 0 and broadcast by the host

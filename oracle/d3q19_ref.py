@@ -778,7 +778,8 @@ def step_physical(g, p: PhysParams, solid=None, body_force=None, phase=None, fil
             if ey * ez: pyz = pyz + d * F32(ey * ez)
         qn = np.sqrt(((pxx * pxx + pyy * pyy) + pzz * pzz)
                      + F32(2.0) * ((pxy * pxy + pxz * pxz) + pyz * pyz))
-        k = F32(18.0 * np.sqrt(2.0) * p.cs_smag * p.cs_smag)
+        cs = float(F32(p.cs_smag))      # the C ABI carries Cs as f32
+        k = F32(18.0 * np.sqrt(2.0) * cs * cs)
         tau = F32(0.5) * (tau0 + np.sqrt(tau0 * tau0 + (k * qn) * inv_rho))
         if les_mask is not None:
             tau = np.where(les_mask != 0, tau, tau0)

@@ -23,6 +23,7 @@ cudaError_t launch_pressure_gradient(const Grid &, const float *, const uint8_t 
 cudaError_t launch_forchheimer_force(const Grid &, const float *, const uint8_t *, float *, float, float, float, float, float, cudaStream_t);
 cudaError_t launch_add_reaction(const Grid &, const float *, const uint8_t *, float *, cudaStream_t);
 cudaError_t launch_particles_couple(const Grid &, const float *, float *, const lbm_particles &, float, float, float, cudaStream_t);
+cudaError_t launch_particles_under_relax(const lbm_particles &, float, cudaStream_t);
 }  // namespace lbm
 
 using namespace lbm;
@@ -253,29 +254,34 @@ static int exchange(lbm_ctx *ctx, float *g, float *vec3, cudaStream_t s) {
         return 0;
     }
     if (!ctx->comm) return fail(ctx, "slab exchange requested but no NCCL communicator attached");
+    // NCCL matches the sends/recvs between one pair of ranks in posting order.  On a 2-rank periodic ring both
+    // neighbours are the same peer, so the odd rank posts its (down, up) blocks in the opposite order.
+    const bool swap_order = has_up && has_down && up_r == down_r && (ctx->rank & 1);
+    auto post = [&](bool upward, const float *send, float *recv) -> int {
+        const int peer = upward ? up_r : down_r;
+        if (g_nccl.Send(send, plane, ncclFloat32, peer, ctx->comm, s) != ncclSuccess) return 1;
+        if (g_nccl.Recv(recv, plane, ncclFloat32, peer, ctx->comm, s) != ncclSuccess) return 1;
+        return 0;
+    };
+    int bad = 0;
     NCCL_OK(ctx, g_nccl.GroupStart());
     for (int i = 0; i < 5; ++i) {
-        if (has_up) {
-            NCCL_OK(ctx, g_nccl.Send(top_owned + (size_t)UP_Q[i] * G.vol, plane, ncclFloat32, up_r, ctx->comm, s));
-            NCCL_OK(ctx, g_nccl.Recv(ghost_hi + (size_t)DOWN_Q[i] * G.vol, plane, ncclFloat32, up_r, ctx->comm, s));
-        }
-        if (has_down) {
-            NCCL_OK(ctx, g_nccl.Send(bot_owned + (size_t)DOWN_Q[i] * G.vol, plane, ncclFloat32, down_r, ctx->comm, s));
-            NCCL_OK(ctx, g_nccl.Recv(ghost_lo + (size_t)UP_Q[i] * G.vol, plane, ncclFloat32, down_r, ctx->comm, s));
+        for (int pass = 0; pass < 2; ++pass) {
+            const bool upward = (pass == 0) != swap_order;
+            if (upward && has_up) bad |= post(true, top_owned + (size_t)UP_Q[i] * G.vol, ghost_hi + (size_t)DOWN_Q[i] * G.vol);
+            if (!upward && has_down) bad |= post(false, bot_owned + (size_t)DOWN_Q[i] * G.vol, ghost_lo + (size_t)UP_Q[i] * G.vol);
         }
     }
     if (vec3) for (int d = 0; d < 3; ++d) {
         float *v = vec3 + (size_t)d * G.vol;
-        if (has_up) {
-            NCCL_OK(ctx, g_nccl.Send(v + (size_t)G.nz * plane, plane, ncclFloat32, up_r, ctx->comm, s));
-            NCCL_OK(ctx, g_nccl.Recv(v + (size_t)(G.nz + 1) * plane, plane, ncclFloat32, up_r, ctx->comm, s));
-        }
-        if (has_down) {
-            NCCL_OK(ctx, g_nccl.Send(v + plane, plane, ncclFloat32, down_r, ctx->comm, s));
-            NCCL_OK(ctx, g_nccl.Recv(v, plane, ncclFloat32, down_r, ctx->comm, s));
+        for (int pass = 0; pass < 2; ++pass) {
+            const bool upward = (pass == 0) != swap_order;
+            if (upward && has_up) bad |= post(true, v + (size_t)G.nz * plane, v + (size_t)(G.nz + 1) * plane);
+            if (!upward && has_down) bad |= post(false, v + plane, v);
         }
     }
     NCCL_OK(ctx, g_nccl.GroupEnd());
+    if (bad) return fail(ctx, "ncclSend/ncclRecv failed while posting the halo exchange");
     return 0;
 }
 
@@ -385,6 +391,13 @@ int lbm_particles_couple(lbm_ctx *ctx, const float *u, float *reaction, lbm_part
     if (!ctx || !u || !reaction || !ps) return fail(ctx, "null argument");
     CUDA_OK(ctx, cudaMemsetAsync(reaction, 0, (size_t)ctx->g.vol * 3 * sizeof(float), (cudaStream_t)stream));
     CUDA_OK(ctx, launch_particles_couple(ctx->g, u, reaction, *ps, water_density, water_viscosity, relax, (cudaStream_t)stream));
+    ctx->launches += 1;
+    return 0;
+}
+
+int lbm_particles_under_relax(lbm_ctx *ctx, lbm_particles *ps, float relax, void *stream) {
+    if (!ctx || !ps) return fail(ctx, "null argument");
+    CUDA_OK(ctx, launch_particles_under_relax(*ps, relax, (cudaStream_t)stream));
     ctx->launches += 1;
     return 0;
 }

@@ -88,12 +88,14 @@ __global__ void __launch_bounds__(256) particles_couple_kernel(const ParticleArg
         }
         P.reynolds[p] = re; P.cd[p] = cd;
         P.drag_new[p] = dnx; P.drag_new[n + p] = dny; P.drag_new[2 * n + p] = dnz;
-        // under-relaxation (coffee_particles.py:1200-1212)
-        const float a = A.relax, b = 1.0f - A.relax;
-        const float ox = P.drag_old[p], oy = P.drag_old[n + p], oz = P.drag_old[2 * n + p];
-        const float fxr = a * dnx + b * ox, fyr = a * dny + b * oy, fzr = a * dnz + b * oz;
-        P.drag[p] = fxr; P.drag[n + p] = fyr; P.drag[2 * n + p] = fzr;
-        P.drag_old[p] = fxr; P.drag_old[n + p] = fyr; P.drag_old[2 * n + p] = fzr;
+        // under-relaxation (coffee_particles.py:1200-1212), fused when relax >= 0
+        if (A.relax >= 0.0f) {
+            const float a = A.relax, b = 1.0f - A.relax;
+            const float ox = P.drag_old[p], oy = P.drag_old[n + p], oz = P.drag_old[2 * n + p];
+            const float fxr = a * dnx + b * ox, fyr = a * dny + b * oy, fzr = a * dnz + b * oz;
+            P.drag[p] = fxr; P.drag[n + p] = fyr; P.drag[2 * n + p] = fzr;
+            P.drag_old[p] = fxr; P.drag_old[n + p] = fyr; P.drag_old[2 * n + p] = fzr;
+        }
     }   // inactive particles keep their previous drag (the reference only touches active ones)
 
     // Warp-aggregated scatter: lanes whose particles share a base cell are combined with
@@ -128,6 +130,25 @@ __global__ void __launch_bounds__(256) particles_couple_kernel(const ParticleArg
 #pragma unroll
             for (int d = 0; d < 3; ++d) atomicAdd(A.reaction + (long long)d * G.vol + base + off[k], c[3 * k + d]);
     }
+}
+
+// CoffeeParticleSystem.apply_under_relaxation as a stand-alone call (coffee_particles.py:1200-1212)
+__global__ void particles_under_relax_kernel(lbm_particles P, float relax) {
+    const int n = P.n;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n || P.active[p] == 0) return;
+    const float a = relax, b = 1.0f - relax;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const float v = a * P.drag_new[d * n + p] + b * P.drag_old[d * n + p];
+        P.drag[d * n + p] = v; P.drag_old[d * n + p] = v;
+    }
+}
+
+cudaError_t launch_particles_under_relax(const lbm_particles &ps, float relax, cudaStream_t s) {
+    const int b = 256, gr = (ps.n + b - 1) / b;
+    if (ps.n > 0) particles_under_relax_kernel<<<gr, b, 0, s>>>(ps, relax);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_particles_couple(const Grid &G, const float *u, float *reaction, const lbm_particles &ps,

@@ -21,7 +21,7 @@ template <bool FORCED, bool LES, bool POROUS, int VEC, bool COLLIDE>
 static StepKernel pick() {
     if constexpr (POROUS && !G_WALLS) return nullptr;          // the filter zone lives in the flag byte
     else if constexpr (!COLLIDE && (LES || VEC != 1)) return nullptr;
-    else return step_kernel<G_COMPAT, G_WALLS, FORCED, LES, POROUS, VEC, (VEC == 1 ? 256 : 128), COLLIDE>;
+    else return step_kernel<LBM_STRICT_BUILD, G_COMPAT, G_WALLS, FORCED, LES, POROUS, VEC, (VEC == 1 ? 256 : 128), COLLIDE>;
 }
 
 template <int VEC, bool COLLIDE>

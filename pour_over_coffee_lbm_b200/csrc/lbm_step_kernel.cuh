@@ -257,7 +257,9 @@ __device__ __forceinline__ float les_fd_nu(const float *__restrict__ u, long lon
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <int COMPAT, bool WALLS, bool FORCED, bool LES, bool POROUS, int VEC, int BLOCK, bool COLLIDE = true>
+// BUILD (0 = fast, 1 = strict/-fmad=false) only makes the two builds distinct symbols: without it the
+// linker would merge the identically-named instantiations of the two translation units (ODR).
+template <int BUILD, int COMPAT, bool WALLS, bool FORCED, bool LES, bool POROUS, int VEC, int BLOCK, bool COLLIDE = true>
 __global__ void __launch_bounds__(BLOCK) step_kernel(const StepArgs P) {
     const Grid &G = P.g;
     const int nxv = G.nx / VEC;

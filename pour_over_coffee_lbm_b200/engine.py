@@ -1,0 +1,307 @@
+"""D3Q19Engine: device state + calls into liblbm_b200.so.
+
+PyTorch is plumbing here (device memory, streams, torch.distributed rendezvous); every
+kernel is hand-written CUDA behind the C ABI.  There is no fallback path: constructing an
+engine without the shared library or without an sm_100 device raises.
+
+HBM layout (see include/lbm_b200.h): x fastest, z slowest, SoA.
+    g          [19, nzp, ny, nx]  post-collision populations, ping-pong pair
+    rho/phase  [nzp, ny, nx]
+    u, force   [3, nzp, ny, nx]
+    flags      [nzp, ny, nx] u8 (solid | filter | les | near)
+nzp = nz + 2*zghost.  The reference's logical index order ([q,i,j,k], [i,j,k,c]) is exposed by
+`fields.py` as permuted views over these buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .config import LBMConfig
+from .errors import BackendInitializationError, ComputeExecutionError
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class D3Q19Engine:
+    def __init__(self, nx: int, ny: int, nz: int, *, compat: str = "physical",
+                 periodic: Sequence[bool] = (True, True, True), walls: bool = False, force: bool = False,
+                 phase: bool = False, les: bool = False, porous: bool = False, strict: bool = False,
+                 config: Optional[LBMConfig] = None, device: int = 0, zghost: int = 0, z0: int = 0,
+                 nz_global: Optional[int] = None, tau: Optional[float] = None, tau_air: Optional[float] = None,
+                 gravity_lu: Optional[float] = None, cs_smag: Optional[float] = None,
+                 porous_darcy: float = 0.0, porous_forch: float = 0.0, vec: int = 0,
+                 macro_fields: bool = True):
+        if not torch.cuda.is_available():
+            raise BackendInitializationError(
+                "no CUDA device visible: pour_over_coffee_lbm_b200 runs on B200 (sm_100a) only, there is no CPU fallback",
+                "b200", "NO_DEVICE")
+        self.lib = L.lib()
+        self.cfg = config or LBMConfig(NX=nx, NY=ny, NZ=nz_global or nz)
+        self.nx, self.ny, self.nz = int(nx), int(ny), int(nz)
+        self.zghost, self.z0 = int(zghost), int(z0)
+        self.nz_global = int(nz_global or nz)
+        self.nzp = self.nz + 2 * self.zghost
+        self.compat = L.COMPAT_REFERENCE if compat == "reference" else L.COMPAT_PHYSICAL
+        self.compat_name = "reference" if self.compat == L.COMPAT_REFERENCE else "physical"
+        self.device = torch.device("cuda", device)
+        self.device_index = device
+        self.periodic = tuple(bool(b) for b in periodic)
+        feats = 0
+        if walls: feats |= L.FEAT_WALLS
+        if force: feats |= L.FEAT_FORCE
+        if phase: feats |= L.FEAT_PHASE
+        if les: feats |= L.FEAT_LES
+        if porous: feats |= L.FEAT_POROUS
+        if strict: feats |= L.FEAT_STRICT
+        self.features = feats
+        k_lu, beta_lu = self.cfg.forchheimer_parameters()
+        c_darcy, c_forch = self.cfg.filter_constants()
+        self.params = L.LbmParams(
+            nx=self.nx, ny=self.ny, nz=self.nz, nz_global=self.nz_global, z0=self.z0, zghost=self.zghost,
+            periodic=(1 if self.periodic[0] else 0) | (2 if self.periodic[1] else 0) | (4 if self.periodic[2] else 0),
+            compat=self.compat, features=feats,
+            tau_water=self.cfg.TAU_WATER if tau is None else tau,
+            tau_air=self.cfg.TAU_AIR if tau_air is None else tau_air,
+            gravity_lu=self.cfg.GRAVITY_LU if gravity_lu is None else gravity_lu,
+            cs_smag=self.cfg.LES_CS if cs_smag is None else cs_smag, tau_min=0.55, tau_max=1.90,
+            porous_darcy=porous_darcy, porous_forch=porous_forch,
+            K_lu=k_lu, beta_lu=beta_lu, c_darcy=c_darcy, c_forch=c_forch, vec=vec, block=0)
+        self._ctx = C.c_void_p()
+        rc = self.lib.lbm_create(C.byref(self._ctx), device, C.byref(self.params))
+        if rc != 0:
+            raise BackendInitializationError(self.lib.lbm_last_error(None).decode(), "b200", "INIT_FAILED")
+
+        dev = self.device
+        shp = (self.nzp, self.ny, self.nx)
+        with torch.cuda.device(dev):
+            self.g = [torch.empty((L.Q,) + shp, dtype=torch.float32, device=dev) for _ in range(2)]
+            self.cur = 0                      # index of the buffer holding the newest populations
+            self.rho = torch.ones(shp, dtype=torch.float32, device=dev) if macro_fields else None
+            self.ref_les = self.compat == L.COMPAT_REFERENCE and les
+            nu = 2 if self.ref_les else 1
+            self.u_buf = [torch.zeros((3,) + shp, dtype=torch.float32, device=dev) for _ in range(nu)] if macro_fields else []
+            self.u_cur = 0
+            self.body_force = torch.zeros((3,) + shp, dtype=torch.float32, device=dev) if force else None
+            self.phase = torch.zeros(shp, dtype=torch.float32, device=dev) if phase else None
+            self.flags = torch.full(shp, L.FLAG_LES, dtype=torch.uint8, device=dev) if walls else None
+            self.solid = torch.zeros(shp, dtype=torch.uint8, device=dev) if walls else None
+            self.filter_zone = torch.zeros(shp, dtype=torch.int32, device=dev) if walls else None
+            self.les_mask = torch.ones(shp, dtype=torch.int32, device=dev) if walls else None
+            self.blockage = None
+        self.comm_stream = None
+        self.rank, self.nranks = 0, 1
+        self.steps_done = 0
+        self.init_equilibrium(1.0, (0.0, 0.0, 0.0))
+
+    # ---------------------------------------------------------------------------------------
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise ComputeExecutionError(f"{what}: {self.lib.lbm_last_error(self._ctx).decode()}", "b200", "EXECUTION_FAILED")
+
+    @property
+    def stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @property
+    def u(self) -> torch.Tensor:
+        return self.u_buf[self.u_cur]
+
+    @property
+    def populations(self) -> torch.Tensor:
+        """post-collision populations g[q, zp, y, x] (newest state)"""
+        return self.g[self.cur]
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self.lib.lbm_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def launch_count(self) -> int:
+        return int(self.lib.lbm_launch_count(self._ctx))
+
+    def set_params(self, **kw):
+        for k, v in kw.items():
+            setattr(self.params, k, v)
+        self._check(self.lib.lbm_set_params(self._ctx, C.byref(self.params)), "lbm_set_params")
+
+    # ---- initialisation ------------------------------------------------------------------------
+    def init_equilibrium(self, rho0: float = 1.0, u0=(0.0, 0.0, 0.0), rho: Optional[torch.Tensor] = None,
+                         u: Optional[torch.Tensor] = None):
+        """g <- f_eq(rho, u); both ping-pong buffers (LBMSolver.init_fields sets f and f_new)."""
+        arr = (C.c_float * 3)(*[float(x) for x in u0])
+        for buf in self.g:
+            self._check(self.lib.lbm_init_equilibrium(self._ctx, _ptr(buf), _ptr(rho), _ptr(u), float(rho0), arr, self.stream),
+                        "lbm_init_equilibrium")
+        if self.rho is not None:
+            if rho is None: self.rho.fill_(rho0)
+            else: self.rho.copy_(rho)
+            for ub in self.u_buf:
+                if u is None:
+                    for c in range(3): ub[c].fill_(float(u0[c]))
+                else:
+                    ub.copy_(u)
+        if self.zghost:
+            self.halo_exchange()
+
+    def build_v60_geometry(self):
+        """FilterPaperSystem.initialize_filter_geometry: solid, filter_zone, les_mask punch-out."""
+        geom = (C.c_float * 5)(*self.cfg.v60_geometry_constants())
+        self._check(self.lib.lbm_build_v60_geometry(self._ctx, _ptr(self.solid), _ptr(self.filter_zone), geom, self.stream),
+                    "lbm_build_v60_geometry")
+        self.les_mask[self.filter_zone == 1] = 0          # filter_paper.py:199-204
+        self.pack_flags()
+
+    def pack_flags(self):
+        self._check(self.lib.lbm_pack_flags(self._ctx, _ptr(self.flags), _ptr(self.solid), _ptr(self.filter_zone),
+                                            _ptr(self.les_mask), self.stream), "lbm_pack_flags")
+        if len(self.u_buf) == 2:      # keep the u ping-pong pair identical on cells the kernel never writes
+            self.u_buf[1 - self.u_cur].copy_(self.u_buf[self.u_cur])
+
+    def set_geometry_preserving_f(self, mutate):
+        """Change the solid mask exactly as the reference would see it: the reference streams with the
+        mask current at collision time, so convert g -> f with the old flags, mutate, f -> g with the new."""
+        f = torch.empty_like(self.g[self.cur])
+        self._check(self.lib.lbm_export_f(self._ctx, _ptr(self.g[self.cur]), _ptr(self.flags), _ptr(f), self.stream), "lbm_export_f")
+        mutate()
+        self.pack_flags()
+        self._check(self.lib.lbm_import_f(self._ctx, _ptr(f), _ptr(self.flags), _ptr(self.g[self.cur]), self.stream), "lbm_import_f")
+        self.g[1 - self.cur].copy_(self.g[self.cur])
+
+    # ---- the hot path --------------------------------------------------------------------------
+    def _fields(self) -> L.LbmFields:
+        if self.ref_les:
+            u_src, u_dst = self.u_buf[self.u_cur], self.u_buf[1 - self.u_cur]
+        else:
+            u_src, u_dst = None, (self.u_buf[0] if self.u_buf else None)
+        return L.LbmFields(f_src=_ptr(self.g[self.cur]), f_dst=_ptr(self.g[1 - self.cur]), rho=_ptr(self.rho),
+                           u_src=_ptr(u_src), u_dst=_ptr(u_dst), body_force=_ptr(self.body_force),
+                           phase=_ptr(self.phase), blockage=_ptr(self.blockage), flags=_ptr(self.flags))
+
+    def step(self, nsteps: int = 1, write_macro_every: int = 1):
+        """nsteps fused collide-stream updates (one kernel launch each)."""
+        if self.rho is None:
+            write_macro_every = 0
+        f = self._fields()
+        comm = C.c_void_p(self.comm_stream.cuda_stream) if self.comm_stream is not None else None
+        self._check(self.lib.lbm_step(self._ctx, C.byref(f), int(nsteps), int(write_macro_every), self.stream, comm), "lbm_step")
+        if nsteps % 2 == 1:
+            self.cur = 1 - self.cur
+        if self.ref_les and write_macro_every == 1 and nsteps % 2 == 1:
+            self.u_cur = 1 - self.u_cur
+        self.steps_done += nsteps
+
+    def macroscopic(self):
+        f = self._fields()
+        if self.ref_les:
+            f.u_dst = _ptr(self.u_buf[self.u_cur])
+        self._check(self.lib.lbm_macroscopic(self._ctx, C.byref(f), self.stream), "lbm_macroscopic")
+
+    def face_bc(self):
+        f = self._fields()
+        self._check(self.lib.lbm_face_bc(self._ctx, C.byref(f), self.stream), "lbm_face_bc")
+
+    # ---- reference `f` view ------------------------------------------------------------------
+    def export_f(self) -> torch.Tensor:
+        """The reference's pre-collision f in device layout [19, nzp, ny, nx] (exact data movement)."""
+        out = torch.empty_like(self.g[self.cur])
+        self._check(self.lib.lbm_export_f(self._ctx, _ptr(self.g[self.cur]), _ptr(self.flags), _ptr(out), self.stream), "lbm_export_f")
+        return out
+
+    def import_f(self, f: torch.Tensor):
+        f = f.to(self.device, torch.float32).contiguous()
+        self._check(self.lib.lbm_import_f(self._ctx, _ptr(f), _ptr(self.flags), _ptr(self.g[self.cur]), self.stream), "lbm_import_f")
+        self.g[1 - self.cur].copy_(self.g[self.cur])
+        if self.zghost:
+            self.halo_exchange()
+
+    # ---- neighbours that feed body_force ----------------------------------------------------
+    def clear_body_force(self):
+        self.body_force.zero_()
+
+    def add_pressure_gradient_force(self, max_force: float = 0.12, scale: float = 1.0):
+        self._check(self.lib.lbm_pressure_gradient_force(self._ctx, _ptr(self.rho), _ptr(self.flags), _ptr(self.body_force),
+                                                         float(max_force), float(scale), self.stream), "lbm_pressure_gradient_force")
+
+    def add_forchheimer_force(self, fmax: Optional[float] = None):
+        fmax = 0.01 * self.cfg.SCALE_VELOCITY / self.cfg.DT if fmax is None else fmax
+        self._check(self.lib.lbm_forchheimer_force(self._ctx, _ptr(self.u), _ptr(self.flags), _ptr(self.body_force), float(fmax),
+                                                   self.stream), "lbm_forchheimer_force")
+
+    def add_reaction_force(self, reaction: torch.Tensor):
+        self._check(self.lib.lbm_add_reaction_force(self._ctx, _ptr(reaction), _ptr(self.flags), _ptr(self.body_force), self.stream),
+                    "lbm_add_reaction_force")
+
+    # ---- slabs ----------------------------------------------------------------------------------
+    def attach_process_group(self, group=None):
+        """Create the NCCL communicator of the z-slab chain; the unique id travels through
+        torch.distributed (any backend)."""
+        import torch.distributed as dist
+        self.rank, self.nranks = dist.get_rank(group), dist.get_world_size(group)
+        uid = (C.c_char * 128)()
+        if self.rank == 0:
+            self._check(self.lib.lbm_nccl_unique_id(C.cast(uid, C.c_void_p)), "lbm_nccl_unique_id")
+        box = [bytes(uid.raw)]
+        dist.broadcast_object_list(box, src=0, group=group)
+        uid = (C.c_char * 128).from_buffer_copy(box[0])
+        with torch.cuda.device(self.device):
+            self._check(self.lib.lbm_attach_nccl(self._ctx, C.cast(uid, C.c_void_p), self.rank, self.nranks), "lbm_attach_nccl")
+            self.comm_stream = torch.cuda.Stream(self.device)
+
+    def halo_exchange(self, with_u: bool = False):
+        v = _ptr(self.u) if (with_u and self.u_buf) else None
+        self._check(self.lib.lbm_halo_exchange(self._ctx, _ptr(self.g[self.cur]), v, self.stream), "lbm_halo_exchange")
+
+    # ---- sizes ---------------------------------------------------------------------------------
+    def cells(self) -> int:
+        return self.nx * self.ny * self.nz
+
+    def fluid_cells(self) -> int:
+        if self.solid is None:
+            return self.cells()
+        own = self.solid[self.zghost:self.zghost + self.nz]
+        return int((own == 0).sum().item())
+
+
+class ParticleState:
+    """SoA particle arrays on the device (CoffeeParticleSystem fields, coffee_particles.py:30-60)."""
+
+    def __init__(self, n: int, device):
+        z3 = lambda: torch.zeros((3, n), dtype=torch.float32, device=device)
+        z1 = lambda: torch.zeros((n,), dtype=torch.float32, device=device)
+        self.n = n
+        self.pos, self.vel = z3(), z3()
+        self.radius, self.mass = z1(), z1()
+        self.active = torch.zeros((n,), dtype=torch.int32, device=device)
+        self.drag_new, self.drag_old, self.drag, self.u_fluid = z3(), z3(), z3(), z3()
+        self.reynolds, self.cd = z1(), z1()
+        self.cell = torch.zeros((3, n), dtype=torch.int32, device=device)
+
+    def struct(self) -> L.LbmParticles:
+        return L.LbmParticles(pos=_ptr(self.pos), vel=_ptr(self.vel), radius=_ptr(self.radius), mass=_ptr(self.mass),
+                              active=_ptr(self.active), drag_new=_ptr(self.drag_new), drag_old=_ptr(self.drag_old),
+                              drag=_ptr(self.drag), u_fluid=_ptr(self.u_fluid), reynolds=_ptr(self.reynolds),
+                              cd=_ptr(self.cd), cell=_ptr(self.cell), n=self.n)
+
+
+def particles_couple(engine: D3Q19Engine, ps: ParticleState, reaction: torch.Tensor, relax: float = 0.8,
+                     water_density: Optional[float] = None, water_viscosity: Optional[float] = None):
+    """CoffeeParticleSystem.compute_two_way_coupling_forces + apply_under_relaxation (one kernel)."""
+    cfg = engine.cfg
+    rho_w = np.float32(cfg.WATER_DENSITY_90C if water_density is None else water_density)
+    mu_w = np.float32(cfg.WATER_VISCOSITY_90C * cfg.WATER_DENSITY_90C if water_viscosity is None else water_viscosity)
+    st = ps.struct()
+    engine._check(engine.lib.lbm_particles_couple(engine._ctx, _ptr(engine.u), _ptr(reaction), C.byref(st), float(rho_w),
+                                                  float(mu_w), float(relax), engine.stream), "lbm_particles_couple")

@@ -1,0 +1,121 @@
+"""z-slab domain decomposition across the GPUs of one box (replaces legacy/cuda_dual_gpu_lbm.py).
+
+Rank r owns the contiguous planes [z0, z0+nz) of the global box plus one ghost plane on each
+side.  Per step and per interface only the populations that cross it travel: cz=+1 go up,
+cz=-1 go down -- 5 contiguous x-y planes each (device layout [q][z][y][x]), so no pack kernel.
+The production exchange is ncclSend/ncclRecv inside liblbm_b200 (lbm_step / lbm_halo_exchange);
+`exchange_halo` below performs the identical plan through torch.distributed P2P so the host-side
+logic can be exercised on CPU tensors with the gloo backend (tests/test_slab_gloo.py).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Tuple
+
+import torch
+
+from .config import CZ_3D
+
+UP_Q: Tuple[int, ...] = tuple(int(q) for q in range(19) if CZ_3D[q] == 1)      # (5, 11, 12, 15, 16)
+DOWN_Q: Tuple[int, ...] = tuple(int(q) for q in range(19) if CZ_3D[q] == -1)   # (6, 13, 14, 17, 18)
+
+
+@dataclass(frozen=True)
+class Slab:
+    rank: int
+    world: int
+    z0: int
+    nz: int
+    nz_global: int
+
+    @property
+    def zghost(self) -> int:
+        return 1
+
+
+def partition_z(nz_global: int, world: int) -> List[Slab]:
+    """Equal-thickness slabs; the remainder planes go to the lowest ranks."""
+    if world < 1 or nz_global < world:
+        raise ValueError("need at least one plane per rank")
+    base, rem = divmod(nz_global, world)
+    out, z0 = [], 0
+    for r in range(world):
+        nz = base + (1 if r < rem else 0)
+        out.append(Slab(r, world, z0, nz, nz_global))
+        z0 += nz
+    return out
+
+
+def neighbours(rank: int, world: int, periodic_z: bool) -> Tuple[Optional[int], Optional[int]]:
+    """(rank below, rank above) or None at a non-periodic end of the chain."""
+    down = rank - 1 if rank > 0 else (world - 1 if periodic_z else None)
+    up = rank + 1 if rank < world - 1 else (0 if periodic_z else None)
+    return down, up
+
+
+def halo_bytes_per_step(nx: int, ny: int, interfaces: int = 1) -> int:
+    """bytes one rank sends per step: 5 populations x nx*ny x 4 B per direction per interface."""
+    return 5 * nx * ny * 4 * 2 * interfaces
+
+
+def exchange_halo(g: torch.Tensor, rank: int, world: int, periodic_z: bool, group=None,
+                  vec3: Optional[torch.Tensor] = None) -> None:
+    """Fill the ghost planes of g [19, nz+2, ny, nx] (and of a [3, nz+2, ny, nx] field) from the z neighbours,
+    sending only the outgoing populations.  Backend-agnostic mirror of liblbm_b200's NCCL exchange."""
+    import torch.distributed as dist
+    down, up = neighbours(rank, world, periodic_z)
+    nzp = g.shape[1]
+    if world == 1:
+        if periodic_z:
+            for q in UP_Q: g[q, 0].copy_(g[q, nzp - 2])
+            for q in DOWN_Q: g[q, nzp - 1].copy_(g[q, 1])
+            if vec3 is not None:
+                vec3[:, 0].copy_(vec3[:, nzp - 2]); vec3[:, nzp - 1].copy_(vec3[:, 1])
+        return
+    ops, recv_bufs = [], []
+    if up is not None:
+        send = torch.stack([g[q, nzp - 2] for q in UP_Q]).contiguous()
+        recv = torch.empty_like(send)
+        ops += [dist.P2POp(dist.isend, send, up, group), dist.P2POp(dist.irecv, recv, up, group)]
+        recv_bufs.append(("hi", recv))
+    if down is not None:
+        send = torch.stack([g[q, 1] for q in DOWN_Q]).contiguous()
+        recv = torch.empty_like(send)
+        ops += [dist.P2POp(dist.isend, send, down, group), dist.P2POp(dist.irecv, recv, down, group)]
+        recv_bufs.append(("lo", recv))
+    vec_bufs = []
+    if vec3 is not None:
+        if up is not None:
+            s = vec3[:, nzp - 2].contiguous(); r = torch.empty_like(s)
+            ops += [dist.P2POp(dist.isend, s, up, group), dist.P2POp(dist.irecv, r, up, group)]
+            vec_bufs.append(("hi", r))
+        if down is not None:
+            s = vec3[:, 1].contiguous(); r = torch.empty_like(s)
+            ops += [dist.P2POp(dist.isend, s, down, group), dist.P2POp(dist.irecv, r, down, group)]
+            vec_bufs.append(("lo", r))
+    if world == 2 and periodic_z:
+        # both neighbours are the same peer: order the two message streams deterministically
+        ops = ops if rank == 0 else [ops[i] for i in _swap_pairs(len(ops))]
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    for where, buf in recv_bufs:
+        if where == "hi":       # from the rank above: its bottom plane's down-going populations
+            for i, q in enumerate(DOWN_Q): g[q, nzp - 1].copy_(buf[i])
+        else:                   # from the rank below: its top plane's up-going populations
+            for i, q in enumerate(UP_Q): g[q, 0].copy_(buf[i])
+    for where, buf in vec_bufs:
+        if where == "hi": vec3[:, nzp - 1].copy_(buf)
+        else: vec3[:, 0].copy_(buf)
+
+
+def _swap_pairs(n: int) -> List[int]:
+    """rank 1 of a 2-rank periodic ring posts its (send,recv) pairs in the opposite neighbour order so that
+    message k of rank 0 meets message k of rank 1."""
+    idx = list(range(n))
+    pairs = [idx[i:i + 2] for i in range(0, n, 2)]        # (send,recv) pairs: up, down, [vec up, vec down]
+    out = []
+    for i in range(0, len(pairs) - 1, 2):
+        out += pairs[i + 1] + pairs[i]
+    if len(pairs) % 2:
+        out += pairs[-1]
+    return out

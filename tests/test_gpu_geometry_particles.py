@@ -1,0 +1,241 @@
+"""GPU parity of geometry/flag building, particle coupling and the small force kernels vs the oracle."""
+import numpy as np
+import pytest
+
+import helpers as H
+from oracle import d3q19_ref as R
+from oracle import ref_cpu as RC
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(*a, **k):
+    from pour_over_coffee_lbm_b200.engine import D3Q19Engine
+    return D3Q19Engine(*a, **k)
+
+
+def _torch(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+# ---- solid / filter-zone flags: bit-exact ------------------------------------------
+@pytest.mark.parametrize("n", [64, 224, 256])
+def test_v60_solid_and_filter_zone_bit_exact(n):
+    cfg = R.RefConfig(NX=n, NY=n, NZ=n)
+    solid_ref = RC.v60_solid(cfg) if n > 64 else R.v60_solid(cfg)
+    zone_ref = R.filter_zones(cfg)
+    eng = _engine(n, n, n, compat="reference", periodic=(False, False, False), walls=True, macro_fields=False)
+    eng.build_v60_geometry()
+    solid = H.from_dev_scalar(eng.solid); zone = H.from_dev_scalar(eng.filter_zone)
+    assert solid.dtype == np.uint8
+    assert int((solid != solid_ref).sum()) == 0
+    assert int((zone != zone_ref).sum()) == 0
+    les = H.from_dev_scalar(eng.les_mask)
+    assert np.array_equal(les, np.where(zone_ref == 1, 0, 1))
+    if n == 224:      # fluid fraction of the default V60 mask (~35.3 %)
+        assert abs((solid == 0).mean() - 0.3535) < 5e-4
+
+
+def test_flag_byte_packing_and_near_bit():
+    from pour_over_coffee_lbm_b200 import _lib as L
+    n = 40
+    cfg = R.RefConfig(NX=n, NY=n, NZ=n)
+    solid = R.v60_solid(cfg); zone = R.filter_zones(cfg)
+    eng = _engine(n, n, n, compat="reference", periodic=(False, False, False), walls=True, macro_fields=False)
+    eng.build_v60_geometry()
+    flags = H.from_dev_scalar(eng.flags)
+    assert np.array_equal((flags & L.FLAG_SOLID) != 0, solid != 0)
+    assert np.array_equal((flags & L.FLAG_FILTER) != 0, zone == 1)
+    assert np.array_equal((flags & L.FLAG_LES) != 0, zone != 1)
+    # NEAR = any of the 18 neighbours solid or outside the (open) box
+    pad = np.pad(solid, 1, constant_values=1)
+    near = np.zeros(solid.shape, bool)
+    for q in range(1, 19):
+        ex, ey, ez = int(R.CX[q]), int(R.CY[q]), int(R.CZ[q])
+        near |= pad[1 - ex:1 - ex + n, 1 - ey:1 - ey + n, 1 - ez:1 - ez + n] != 0
+    assert np.array_equal((flags & L.FLAG_NEAR) != 0, near)
+
+
+# ---- f <-> g conversion is exact data movement -----------------------------------------------------
+def test_export_import_f_roundtrip_and_oracle():
+    import torch
+    n = 24
+    cfg = R.RefConfig(NX=n, NY=n, NZ=n)
+    solid = R.v60_solid(cfg)
+    eng = _engine(n, n, n, compat="reference", periodic=(False, False, False), walls=True, macro_fields=False)
+    eng.solid.copy_(_torch(H.to_dev_scalar(solid))); eng.pack_flags()
+    rng = np.random.default_rng(0)
+    g = rng.random((19, n, n, n), dtype=np.float32)
+    eng.g[eng.cur].copy_(_torch(H.to_dev_pop(g)))
+    f = H.from_dev_pop(eng.export_f())
+    f_ref = R.stream_from_post_collision(g, solid)
+    fluid = solid == 0
+    assert np.array_equal(f[:, fluid], f_ref[:, fluid])
+    # import(export(g)) reproduces every population that can ever be read again
+    eng.import_f(torch.from_numpy(H.to_dev_pop(f)))
+    f2 = H.from_dev_pop(eng.export_f())
+    assert np.array_equal(f2[:, fluid], f[:, fluid])
+
+
+# ---- particles -----------------------------------------------------------------------------------------
+# tests/test_trilinear_interpolation.py:24-38,143-159 of the reference: v=(x,y,z) on 16^3, ten positions
+# must interpolate to themselves.
+TRILINEAR_POSITIONS = [
+    (5.0, 5.0, 5.0), (5.5, 5.5, 5.5), (5.25, 6.75, 7.1), (0.1, 0.1, 0.1), (14.9, 14.9, 14.9),
+    (2.3, 8.7, 11.2), (7.8, 3.4, 9.6), (12.1, 13.5, 4.8), (1.7, 5.9, 14.3), (8.4, 11.2, 6.7)]
+
+
+def _particle_solver(n):
+    from pour_over_coffee_lbm_b200.solver import LBMSolver
+    from pour_over_coffee_lbm_b200.physics import CoffeeParticleSystem
+    s = LBMSolver(nx=n, ny=n, nz=n, compat="reference", strict=True)
+    ps = CoffeeParticleSystem(max_particles=4096, solver=s)
+    return s, ps
+
+
+def test_trilinear_known_answers():
+    n = 16
+    s, ps = _particle_solver(n)
+    i, j, k = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
+    s.u.from_numpy(np.stack([i, j, k], axis=-1).astype(np.float32))
+    pos = np.array(TRILINEAR_POSITIONS, np.float32)
+    ps.set_particles(pos)
+    ps.compute_two_way_coupling_forces(s.u)
+    got = ps.fluid_velocity_at_particle[: len(pos)].cpu().numpy()
+    assert np.abs(got - pos).max() < 5e-6        # f32 (reference reports 4.8e-7 relative on this table)
+
+
+def test_particle_cell_indices_bit_exact_and_forces():
+    n, P = 48, 3000
+    s, ps = _particle_solver(n)
+    cfg = R.RefConfig(NX=n, NY=n, NZ=n)
+    rng = np.random.default_rng(42)
+    u = H.smooth_velocity(n, 0.05, 3)
+    s.u.from_numpy(u)
+    pos = rng.uniform(-1.0, n + 1.0, size=(P, 3)).astype(np.float32)      # includes out-of-range positions (clamped)
+    pos[:64] = np.round(pos[:64])                                         # exact-integer positions (truncation edge)
+    pos[64:128] = pos[0]                                                   # many particles in ONE cell (warp aggregation)
+    vel = (0.01 * rng.standard_normal((P, 3))).astype(np.float32)
+    radius = np.clip(rng.normal(3.25e-4, 0.3 * 3.25e-4, P), 0.5 * 3.25e-4, 1.5 * 3.25e-4).astype(np.float32)
+    mass = (np.float32(1200.0) * np.float32(4.0 / 3.0 * np.pi) * radius ** 3).astype(np.float32)
+    ps.set_particles(pos, vel, radius, mass)
+    ps.state.active[P - 10:P] = 0                                          # inactive tail
+    active = np.ones(P, np.int32); active[P - 10:] = 0
+    ps.state.drag_old[:, :P] = _torch(np.full((3, P), 1e-9, np.float32))
+    ps.compute_two_way_coupling_forces(s.u, relax=0.8)
+    drag_new, react, u_fl, re_p, cd, cell = R.two_way_coupling(cfg, u, pos, vel, radius, mass, active)
+    act = active != 0
+    # particle cell indices: bit-exact
+    assert np.array_equal(ps.cell_index[:P].cpu().numpy()[act], cell[act])
+    # gather: same operation order -> bit-exact
+    assert np.array_equal(ps.fluid_velocity_at_particle[:P].cpu().numpy()[act], u_fl[act])
+    # Reynolds exact; C_D / drag carry powf (<= 2 ulp)
+    assert np.array_equal(ps.particle_reynolds[:P].cpu().numpy()[act], re_p[act])
+    np.testing.assert_allclose(ps.drag_coefficient[:P].cpu().numpy()[act], cd[act], rtol=5e-7)
+    np.testing.assert_allclose(ps.drag_force_new[:P].cpu().numpy()[act], drag_new[act], rtol=1e-6, atol=1e-20)
+    # scatter: atomics are unordered -> tolerance scaled by the largest nodal force
+    got = ps.reaction_force_field.to_numpy()
+    assert np.abs(got - react).max() <= 1e-5 * np.abs(react).max()
+    # momentum conservation of the scatter: sum of nodal forces = - sum of particle drags
+    np.testing.assert_allclose(got.reshape(-1, 3).sum(0, dtype=np.float64), -drag_new[act].sum(0, dtype=np.float64), rtol=1e-4)
+    # under-relaxation F = a F_new + (1-a) F_old
+    drag, new_old = R.under_relax(drag_new, np.full((P, 3), 1e-9, np.float32), active, 0.8)
+    np.testing.assert_allclose(ps.drag_force[:P].cpu().numpy()[act], drag[act], rtol=1e-6, atol=1e-20)
+    # add_particle_reaction_forces: body_force += reaction on fluid cells only
+    s.clear_body_force(); s.add_particle_reaction_forces(ps)
+    np.testing.assert_array_equal(s.body_force.to_numpy(), got)
+
+
+def test_empty_and_single_particle():
+    n = 16
+    s, ps = _particle_solver(n)
+    ps.compute_two_way_coupling_forces(s.u, relax=0.8)              # zero active particles
+    assert float(ps.reaction_force_tensor.abs().max()) == 0.0
+    s.u.fill([0.01, 0.0, 0.0])
+    ps.set_particles(np.array([[8.25, 8.5, 8.75]], np.float32))
+    ps.compute_two_way_coupling_forces(s.u, relax=0.8)
+    r = ps.reaction_force_field.to_numpy()
+    assert (r[..., 0] <= 0).all() and r[..., 0].min() < 0          # reaction opposes the drag (+x)
+    assert np.count_nonzero(r[..., 0]) == 8
+
+
+# ---- neighbours that feed body_force -------------------------------------------------------------------
+def test_pressure_gradient_and_forchheimer_force_bit_exact():
+    n = 32
+    st = H.reference_v60_state(n, seed=5)
+    rng = np.random.default_rng(1)
+    st.rho = (1.0 + 0.05 * rng.standard_normal(st.rho.shape)).astype(np.float32)
+    st.u = (0.02 * rng.standard_normal(st.u.shape)).astype(np.float32)
+    from pour_over_coffee_lbm_b200.config import LBMConfig
+    eng = _engine(n, n, n, compat="reference", periodic=(False, False, False), walls=True, force=True, phase=True, porous=True,
+                  config=LBMConfig(NX=n, NY=n, NZ=n))
+    eng.solid.copy_(_torch(H.to_dev_scalar(st.solid))); eng.filter_zone.copy_(_torch(H.to_dev_scalar(st.filter_zone)))
+    eng.pack_flags()
+    eng.rho.copy_(_torch(H.to_dev_scalar(st.rho))); eng.u.copy_(_torch(H.to_dev_vec(st.u)))
+    # PressureGradientDrive force mode and mixed (0.5x) mode
+    for scale in (1.0, 0.5):
+        st.body_force[:] = 0; eng.clear_body_force()
+        pf = R.pressure_gradient_force(st, 0.12)
+        R.accumulate_pressure_force(st, pf, scale)
+        eng.add_pressure_gradient_force(0.12, scale)
+        assert np.array_equal(H.from_dev_vec(eng.body_force), st.body_force)
+    # FilterPaperSystem.compute_forchheimer_resistance on top
+    R.compute_forchheimer_resistance(st)
+    eng.add_forchheimer_force()
+    got = H.from_dev_vec(eng.body_force)
+    assert np.array_equal(got, st.body_force)
+    zone = (st.filter_zone == 1) & (st.solid == 0)
+    assert np.abs(got[zone]).max() > 0          # tests/test_forchheimer.py:31-74: non-zero in the zone
+
+
+# ---- facades ----------------------------------------------------------------------------------------------
+def test_solver_facade_surface_and_protocol():
+    from pour_over_coffee_lbm_b200.solver import LBMSolver, UnifiedLBMSolver
+    from pour_over_coffee_lbm_b200.physics import FilterPaperSystem, PressureGradientDrive
+    n = 32
+    s = LBMSolver(nx=n, ny=n, nz=n)
+    for name in ("f", "f_new", "rho", "u", "solid", "phase", "ux", "uy", "uz", "body_force", "boundary_manager", "les_mask",
+                 "opposite_dir"):
+        assert hasattr(s, name)
+    for name in ("step", "collision_step", "streaming_step", "compute_macroscopic_quantities", "apply_boundary_conditions",
+                 "initialize_fields", "set_geometry", "get_diagnostics", "check_stability", "get_kinetic_energy",
+                 "get_mass_conservation_error", "get_memory_usage", "optimize_memory_layout", "enable_les_turbulence",
+                 "add_force_term", "export_vtk", "init_fields", "clear_body_force", "swap_fields",
+                 "step_with_two_way_coupling", "get_velocity_magnitude"):
+        assert callable(getattr(s, name))
+    s.init_fields()
+    assert s.f.shape == (19, n, n, n) and s.u.shape == (n, n, n, 3) and s.rho.shape == (n, n, n)
+    # init state: f = w_q, rho = 1 (legacy/lbm_solver.py:1067-1112)
+    f = s.f.to_numpy()
+    assert np.array_equal(f[0], np.full((n, n, n), np.float32(1 / 3)))
+    fp = FilterPaperSystem(s); fp.initialize_filter_geometry()
+    assert np.array_equal(s.solid.to_numpy(), R.v60_solid(R.RefConfig(NX=n, NY=n, NZ=n)))
+    frac = fp.get_filter_statistics()["filter_fraction"]
+    assert 0 < frac < 0.5                                   # tests/test_filter_paper.py:38-65
+    drive = PressureGradientDrive(s); drive.activate_force_drive(True)
+    s.phase.fill(0.3)
+    for _ in range(3):                                      # tests/test_lbm_solver_unit.py:50-60: (apply; step) x3, no NaN
+        s.clear_body_force(); drive.apply(); s.step()
+    assert s.check_stability()
+    rho = s.rho.to_numpy()
+    assert np.isfinite(rho).all() and (rho > 0).all()
+    us = UnifiedLBMSolver(nx=n, ny=n, nz=n)
+    us.initialize_fields(); us.step(); us.step()
+    m = us.backend.get_performance_metrics()
+    assert m["throughput_mlups"] > 0 and us.backend.validate_platform()
+
+
+def test_body_force_accumulation_fluid_only():
+    """tests/test_lbm_body_force.py:77-100,218-239 of the reference: body_force += semantics, fluid cells only."""
+    from pour_over_coffee_lbm_b200.solver import LBMSolver
+    from pour_over_coffee_lbm_b200.physics import CoffeeParticleSystem, FilterPaperSystem
+    n = 32
+    s = LBMSolver(nx=n, ny=n, nz=n)
+    FilterPaperSystem(s).initialize_filter_geometry()
+    ps = CoffeeParticleSystem(64, solver=s)
+    ps.reaction_force_tensor.fill_(1e-3)
+    s.clear_body_force()
+    s.add_particle_reaction_forces(ps); s.add_particle_reaction_forces(ps)
+    bf = s.body_force.to_numpy(); solid = s.solid.to_numpy()
+    assert np.allclose(bf[solid == 0], 2e-3) and np.all(bf[solid != 0] == 0)

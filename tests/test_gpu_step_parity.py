@@ -1,0 +1,258 @@
+"""GPU parity of the fused step kernel against the CPU oracle, through the C ABI.
+
+Bars: the strict build (-fmad=false) must be BIT-EXACT against the oracle; the
+fast build (FMA contraction) must agree within 1e-5 relative (max|d|/max|ref|) after the run.
+"""
+import numpy as np
+import pytest
+
+import helpers as H
+from oracle import d3q19_ref as R
+from oracle import ref_cpu as RC
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5   # f32 tolerance named by BASELINE.json's north_star
+
+
+def _engine(*a, **k):
+    from pour_over_coffee_lbm_b200.engine import D3Q19Engine
+    return D3Q19Engine(*a, **k)
+
+
+def _torch(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+# ------------------------------------------------------------------------------------------------
+# compat = physical, fully periodic (BASELINE config 1 family)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("les", [False, True])
+@pytest.mark.parametrize("vec", [1, 4])
+def test_physical_periodic_strict_bit_exact(les, vec):
+    n, steps = 32, 40
+    u0 = H.smooth_velocity(n, 0.05, 3); rho0 = H.smooth_density(n, 0.02, 3)
+    p = R.PhysParams(nx=n, ny=n, nz=n, tau_water=0.53, les=les)
+    g = R.init_equilibrium_phys(rho0, u0)
+    for _ in range(steps):
+        g, rho, u = R.step_physical(g, p)
+    eng = _engine(n, n, n, compat="physical", les=les, strict=True, vec=vec, tau=0.53)
+    eng.init_equilibrium(rho=_torch(H.to_dev_scalar(rho0)), u=_torch(H.to_dev_vec(u0)))
+    eng.step(steps)
+    assert np.array_equal(H.from_dev_pop(eng.populations), g)
+    assert np.array_equal(H.from_dev_scalar(eng.rho), rho)
+    assert np.array_equal(H.from_dev_vec(eng.u), u)
+
+
+@pytest.mark.parametrize("vec", [1, 4])
+def test_physical_periodic_fast_1000_steps(vec):
+    """rho,u within 1e-5 of the oracle after 1000 steps (fast build vs NumPy oracle, 24^3)."""
+    n, steps = 24, 1000
+    u0 = H.smooth_velocity(n, 0.04, 5); rho0 = H.smooth_density(n, 0.01, 5)
+    p = R.PhysParams(nx=n, ny=n, nz=n, tau_water=0.6)
+    g = R.init_equilibrium_phys(rho0, u0)
+    for _ in range(steps):
+        g, rho, u = R.step_physical(g, p)
+    eng = _engine(n, n, n, compat="physical", strict=False, vec=vec, tau=0.6)
+    eng.init_equilibrium(rho=_torch(H.to_dev_scalar(rho0)), u=_torch(H.to_dev_vec(u0)))
+    eng.step(steps)
+    assert H.rel_err(H.from_dev_scalar(eng.rho), rho) <= TOL
+    # u has decayed by then; the criterion is relative to the initial velocity scale
+    assert np.abs(H.from_dev_vec(eng.u) - u).max() / 0.04 <= TOL
+
+
+def test_physical_nonsquare_box_and_macro_every_k():
+    """ragged extents (nx != ny != nz, nx not a multiple of 4 -> scalar path) and write_macro_every=k."""
+    nx, ny, nz, steps = 20, 12, 9, 7
+    u0 = H.smooth_velocity(nx, 0.03, 9, nz=nz, ny=ny); rho0 = H.smooth_density(nx, 0.01, 9, nz=nz, ny=ny)
+    p = R.PhysParams(nx=nx, ny=ny, nz=nz, tau_water=0.7)
+    g = R.init_equilibrium_phys(rho0, u0)
+    for _ in range(steps):
+        g, rho, u = R.step_physical(g, p)
+    for vec in (1, 4):
+        eng = _engine(nx, ny, nz, compat="physical", strict=True, vec=vec, tau=0.7)
+        eng.init_equilibrium(rho=_torch(H.to_dev_scalar(rho0)), u=_torch(H.to_dev_vec(u0)))
+        eng.step(steps, write_macro_every=3)      # macro written at steps 3, 6 and the last (7)
+        assert np.array_equal(H.from_dev_pop(eng.populations), g)
+        assert np.array_equal(H.from_dev_vec(eng.u), u)
+    nx = 18   # not a multiple of 4: library must fall back to the scalar kernel, same answer
+    u0 = H.smooth_velocity(nx, 0.03, 9, nz=nz, ny=ny); rho0 = H.smooth_density(nx, 0.01, 9, nz=nz, ny=ny)
+    p = R.PhysParams(nx=nx, ny=ny, nz=nz, tau_water=0.7)
+    g = R.init_equilibrium_phys(rho0, u0)
+    for _ in range(3):
+        g, rho, u = R.step_physical(g, p)
+    eng = _engine(nx, ny, nz, compat="physical", strict=True, vec=4, tau=0.7)
+    eng.init_equilibrium(rho=_torch(H.to_dev_scalar(rho0)), u=_torch(H.to_dev_vec(u0)))
+    eng.step(3)
+    assert np.array_equal(H.from_dev_pop(eng.populations), g)
+
+
+# ------------------------------------------------------------------------------------------------
+# compat = physical with the V60 mask, force, phase, LES and porous drag (BASELINE config 2 family)
+# ------------------------------------------------------------------------------------------------
+def _physical_v60_case(n, seed):
+    cfg = R.RefConfig(NX=n, NY=n, NZ=n)
+    solid = R.v60_solid(cfg); zone = R.filter_zones(cfg)
+    les_mask = np.where(zone == 1, 0, 1).astype(np.int32)
+    rng = np.random.default_rng(seed)
+    phase = np.zeros((n, n, n), np.float32); phase[:, :, : int(0.6 * n)] = 1.0
+    bf = (2e-5 * rng.standard_normal((n, n, n, 3))).astype(np.float32)
+    u0 = H.smooth_velocity(n, 0.02, seed); rho0 = H.smooth_density(n, 0.01, seed)
+    return cfg, solid, zone, les_mask, phase, bf, u0, rho0
+
+
+@pytest.mark.parametrize("vec", [1, 4])
+@pytest.mark.parametrize("strict", [True, False])
+def test_physical_v60_full_features(vec, strict):
+    n, steps = 32, 30
+    cfg, solid, zone, les_mask, phase, bf, u0, rho0 = _physical_v60_case(n, 11)
+    p = R.PhysParams(nx=n, ny=n, nz=n, tau_water=0.53, tau_air=0.8, gravity_lu=1e-5, periodic=(False, False, False),
+                     use_force=True, use_phase=True, les=True, porous=True, porous_darcy=0.37, porous_forch=0.9)
+    g = R.init_equilibrium_phys(rho0, u0)
+    for _ in range(steps):
+        g, rho, u = R.step_physical(g, p, solid=solid, body_force=bf, phase=phase, filter_zone=zone, les_mask=les_mask)
+    eng = _engine(n, n, n, compat="physical", periodic=(False, False, False), walls=True, force=True, phase=True, les=True,
+                  porous=True, strict=strict, vec=vec, tau=0.53, tau_air=0.8, gravity_lu=1e-5, porous_darcy=0.37,
+                  porous_forch=0.9)
+    eng.solid.copy_(_torch(H.to_dev_scalar(solid))); eng.filter_zone.copy_(_torch(H.to_dev_scalar(zone)))
+    eng.les_mask.copy_(_torch(H.to_dev_scalar(les_mask))); eng.pack_flags()
+    eng.phase.copy_(_torch(H.to_dev_scalar(phase))); eng.body_force.copy_(_torch(H.to_dev_vec(bf)))
+    eng.init_equilibrium(rho=_torch(H.to_dev_scalar(rho0)), u=_torch(H.to_dev_vec(u0)))
+    eng.step(steps)
+    fluid = solid == 0
+    gg = H.from_dev_pop(eng.populations); rr = H.from_dev_scalar(eng.rho); uu = H.from_dev_vec(eng.u)
+    if strict:
+        assert np.array_equal(gg[:, fluid], g[:, fluid])
+        assert np.array_equal(rr[fluid], rho[fluid])
+        assert np.array_equal(uu[fluid], u[fluid])
+    else:
+        assert H.rel_err(rr[fluid], rho[fluid]) <= TOL
+        assert H.rel_err(uu[fluid], u[fluid]) <= TOL
+
+
+# ------------------------------------------------------------------------------------------------
+# compat = reference: the legacy LBMSolver.step() with all quirks, against the C oracle
+# ------------------------------------------------------------------------------------------------
+def _load_reference_state(eng, st):
+    """Put an oracle State into the engine: solid/zone/les mask, phase, force, u, rho, f (un-streamed)."""
+    eng.solid.copy_(_torch(H.to_dev_scalar(st.solid)))
+    if st.filter_zone is not None:
+        eng.filter_zone.copy_(_torch(H.to_dev_scalar(st.filter_zone)))
+    eng.les_mask.copy_(_torch(H.to_dev_scalar(st.les_mask)))
+    eng.pack_flags()
+    eng.phase.copy_(_torch(H.to_dev_scalar(st.phase)))
+    eng.body_force.copy_(_torch(H.to_dev_vec(st.body_force)))
+    eng.rho.copy_(_torch(H.to_dev_scalar(st.rho)))
+    for ub in eng.u_buf:
+        ub.copy_(_torch(H.to_dev_vec(st.u)))
+    eng.import_f(_torch(H.to_dev_pop(st.f)))
+
+
+def _compare_reference(eng, cs, strict):
+    fluid = cs.solid == 0
+    rr = H.from_dev_scalar(eng.rho); uu = H.from_dev_vec(eng.u); ff = H.from_dev_pop(eng.export_f())
+    if strict:
+        assert np.array_equal(rr[fluid], cs.rho[fluid], equal_nan=True)
+        assert np.array_equal(uu[fluid], cs.u[fluid], equal_nan=True)
+        assert np.array_equal(ff[:, fluid], cs.f[:, fluid], equal_nan=True)
+    else:
+        assert H.rel_err(rr[fluid], cs.rho[fluid]) <= TOL
+        assert H.rel_err(uu[fluid], cs.u[fluid]) <= TOL
+
+
+@pytest.mark.parametrize("vec", [1, 4])
+@pytest.mark.parametrize("strict", [True, False])
+def test_reference_v60_1000_steps_air(vec, strict):
+    """V60 mask, tau_air (phase <= 0.5), gravity*phase, seeded body force, filter damping: 1000 steps.
+    (With phase > 0.5 the legacy solver itself is linearly unstable because of quirk Q1 -- DESIGN.md.)"""
+    n, steps = 48, 1000
+    st = H.reference_v60_state(n, seed=2, gravity=2e-5, body=1e-5, phase_mode="none")
+    rng = np.random.default_rng(4)
+    st.phase[:] = rng.uniform(0.0, 0.5, size=st.phase.shape).astype(np.float32)
+    cs = RC.CState(st)
+    cs.step(steps)
+    assert np.isfinite(cs.rho).all() and np.abs(cs.u).max() < 0.3
+    eng = _engine(n, n, n, compat="reference", periodic=(False, False, False), walls=True, force=True, phase=True, les=True,
+                  porous=True, strict=strict, vec=vec, config=_cfg_for(st), gravity_lu=2e-5)
+    _load_reference_state(eng, st)
+    eng.step(steps)
+    _compare_reference(eng, cs, strict)
+
+
+@pytest.mark.parametrize("vec", [1, 4])
+def test_reference_water_phase_les_default_gravity_short(vec):
+    """phase=1 (tau_water, LES active, default GRAVITY_LU=44.145 saturating every Guo clamp): 12 steps, bit-exact."""
+    n, steps = 32, 12
+    st = H.reference_v60_state(n, seed=6, gravity=R.RefConfig().GRAVITY_LU, body=1e-4, phase_mode="split")
+    cs = RC.CState(st)
+    cs.step(steps)
+    assert cs.nu_sgs.max() > 0.0          # the FD-LES branch really ran
+    eng = _engine(n, n, n, compat="reference", periodic=(False, False, False), walls=True, force=True, phase=True, les=True,
+                  porous=True, strict=True, vec=vec, config=_cfg_for(st), gravity_lu=R.RefConfig().GRAVITY_LU)
+    _load_reference_state(eng, st)
+    eng.step(steps)
+    _compare_reference(eng, cs, True)
+
+
+def test_reference_no_geometry_open_faces_and_face_bc():
+    """`init_fields` state without geometry (first 30 steps of main.py): open faces keep w_q inflow (quirk Q6),
+    boundary manager writes rho on the faces (quirk Q5)."""
+    n, steps = 24, 25
+    cfg = R.RefConfig(NX=n, NY=n, NZ=n, GRAVITY_LU=1e-4)
+    st = R.init_fields(cfg)
+    u0 = H.smooth_velocity(n, 0.02, 8); rho0 = H.smooth_density(n, 0.01, 8)
+    for q in range(R.Q):
+        st.f[q] = R.equilibrium_ref(rho0, u0[..., 0], u0[..., 1], u0[..., 2], q, "config"); st.f_new[q] = st.f[q]
+    # populations that enter through a face are never written by the reference: they hold w_q
+    st.f = R.stream_from_post_collision(_unstream_np(st.f), None)
+    st.f_new = st.f.copy()
+    cs = RC.CState(st)
+    eng = _engine(n, n, n, compat="reference", periodic=(False, False, False), walls=True, force=True, phase=True, les=True,
+                  strict=True, config=_cfg_for(st), gravity_lu=1e-4)
+    _load_reference_state(eng, st)
+    for _ in range(steps):
+        cs.step(1)
+        eng.step(1); eng.face_bc()
+    _compare_reference(eng, cs, True)
+
+
+def _unstream_np(f):
+    """inverse of stream_from_post_collision for an all-fluid open box (values leaving the box are dropped)."""
+    g = f.copy()
+    for q in range(R.Q):
+        ex, ey, ez = int(R.CX[q]), int(R.CY[q]), int(R.CZ[q])
+        g[q] = np.roll(f[q], shift=(-ex, -ey, -ez), axis=(0, 1, 2))
+    return g
+
+
+def _cfg_for(st):
+    from pour_over_coffee_lbm_b200.config import LBMConfig
+    c = st.cfg
+    return LBMConfig(NX=c.NX, NY=c.NY, NZ=c.NZ, TAU_FLUID=c.TAU_WATER, TAU_AIR=c.TAU_AIR, GRAVITY_LU=c.GRAVITY_LU)
+
+
+def test_geometry_change_mid_run_matches_reference():
+    """main.py applies the V60 mask after 30 steps: the engine converts g -> f -> g around the change so
+    the trajectory equals the reference's (which streamed with the old mask)."""
+    n = 32
+    cfg = R.RefConfig(NX=n, NY=n, NZ=n, GRAVITY_LU=1e-4)
+    st = R.init_fields(cfg)
+    st.body_force[:] = (1e-5 * np.random.default_rng(3).standard_normal(st.body_force.shape)).astype(np.float32)
+    cs = RC.CState(st)
+    eng = _engine(n, n, n, compat="reference", periodic=(False, False, False), walls=True, force=True, phase=True, les=True,
+                  porous=True, strict=True, config=_cfg_for(st), gravity_lu=1e-4)
+    _load_reference_state(eng, st)
+    cs.step(10); eng.step(10)
+    # geometry arrives now (filter_paper.initialize_filter_geometry)
+    tmp = R.init_fields(cfg); R.attach_filter_system(tmp)
+    cs.solid[:] = tmp.solid; cs.filter_zone = tmp.filter_zone.copy(); cs.filter_blockage = np.zeros_like(cs.rho)
+    cs.les_mask[:] = tmp.les_mask; cs.params.apply_filter = 1
+    cs.params.K_lu = float(tmp.K_lu); cs.params.beta_lu = float(tmp.beta_lu)
+
+    def mutate():
+        eng.solid.copy_(_torch(H.to_dev_scalar(tmp.solid)))
+        eng.filter_zone.copy_(_torch(H.to_dev_scalar(tmp.filter_zone)))
+        eng.les_mask.copy_(_torch(H.to_dev_scalar(tmp.les_mask)))
+    eng.set_geometry_preserving_f(mutate)
+    cs.step(15); eng.step(15)
+    _compare_reference(eng, cs, True)

@@ -1,0 +1,87 @@
+"""Taylor-Green decay rate (within 0.5 % of 4 nu k^2) and the ghost-plane slab path on one GPU."""
+import numpy as np
+import pytest
+
+import helpers as H
+from oracle import d3q19_ref as R
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(*a, **k):
+    from pour_over_coffee_lbm_b200.engine import D3Q19Engine
+    return D3Q19Engine(*a, **k)
+
+
+def _tgv2d(n, u0):
+    import torch
+    k = 2 * np.pi / n
+    x = torch.arange(n, dtype=torch.float64, device="cuda") * k
+    X = x[None, None, :]; Y = x[None, :, None]
+    one = torch.ones((n, 1, 1), dtype=torch.float64, device="cuda")
+    ux = u0 * torch.sin(X) * torch.cos(Y) * one
+    uy = -u0 * torch.cos(X) * torch.sin(Y) * one
+    rho = (1.0 - (3.0 * u0 * u0 / 4.0) * (torch.cos(2 * X) + torch.cos(2 * Y))) * one
+    return rho.float().contiguous(), torch.stack([ux, uy, torch.zeros_like(ux)]).float().contiguous()
+
+
+@pytest.mark.parametrize("tau", [0.53, 0.8])
+def test_taylor_green_decay_rate_256(tau):
+    """z-invariant Taylor-Green vortex on periodic 256^3 (exact Navier-Stokes solution): kinetic energy decays as
+    exp(-4 nu k^2 t), nu = (tau - 1/2)/3.  Fit ln E over steps 200..1000."""
+    import torch
+    n, u0 = 256, 0.04
+    eng = _engine(n, n, n, compat="physical", tau=tau)
+    rho0, uinit = _tgv2d(n, u0)
+    eng.init_equilibrium(rho=rho0, u=uinit)
+    steps, every = 1000, 50
+    ts, es = [], []
+    for s in range(0, steps, every):
+        eng.step(every, write_macro_every=every)
+        e = float((0.5 * eng.rho.double() * (eng.u.double() ** 2).sum(0)).sum())
+        # rho,u written by step k are the moments of the state entering step k (t = s + every - 1)
+        ts.append(s + every - 1); es.append(e)
+    ts, es = np.array(ts, float), np.array(es, float)
+    sel = ts >= 200
+    slope = np.polyfit(ts[sel], np.log(es[sel]), 1)[0]
+    nu = (tau - 0.5) / 3.0
+    k = 2 * np.pi / n
+    expected = -4.0 * nu * k * k
+    assert abs(slope / expected - 1.0) <= 5e-3, (slope, expected)
+    # uz stays exactly zero and the flow stays z-invariant
+    assert float(eng.u[2].abs().max()) == 0.0
+    assert float((eng.u[0][0] - eng.u[0][n // 2]).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("vec", [1, 4])
+def test_ghost_plane_slab_equals_wrapped_single_slab(vec):
+    """zghost=1 with the periodic self-exchange (single-GPU 'virtual slab' mode) must reproduce the zghost=0
+    in-kernel wrap bit for bit: validates the halo population set {5,11,12,15,16 | 6,13,14,17,18}."""
+    import torch
+    n, steps = 32, 25
+    u0 = H.smooth_velocity(n, 0.04, 21); rho0 = H.smooth_density(n, 0.01, 21)
+    ru = torch.from_numpy(H.to_dev_scalar(rho0)).cuda(); uu = torch.from_numpy(H.to_dev_vec(u0)).cuda()
+    a = _engine(n, n, n, compat="physical", les=True, strict=True, vec=vec, tau=0.6)
+    a.init_equilibrium(rho=ru, u=uu)
+    a.step(steps)
+    b = _engine(n, n, n, compat="physical", les=True, strict=True, vec=vec, tau=0.6, zghost=1, z0=0, nz_global=n)
+    pad = lambda t: torch.nn.functional.pad(t, (0, 0, 0, 0, 1, 1))
+    b.init_equilibrium(rho=pad(ru), u=pad(uu))
+    b.step(steps)
+    assert torch.equal(a.populations, b.populations[:, 1:-1])
+    assert torch.equal(a.rho, b.rho[1:-1]) and torch.equal(a.u, b.u[:, 1:-1])
+
+
+def test_strict_and_fast_builds_are_distinct_kernels():
+    """Guards against the two builds being merged at link time: FMA contraction must change some low bits."""
+    import torch
+    n = 32
+    u0 = H.smooth_velocity(n, 0.05, 3); rho0 = H.smooth_density(n, 0.02, 3)
+    out = []
+    for strict in (True, False):
+        e = _engine(n, n, n, compat="physical", les=True, strict=strict, tau=0.53)
+        e.init_equilibrium(rho=torch.from_numpy(H.to_dev_scalar(rho0)).cuda(), u=torch.from_numpy(H.to_dev_vec(u0)).cuda())
+        e.step(20)
+        out.append(e.populations.clone())
+    assert not torch.equal(out[0], out[1])
+    assert float((out[0] - out[1]).abs().max()) < 1e-6

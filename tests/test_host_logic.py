@@ -1,0 +1,67 @@
+"""Host-side logic that needs no GPU: field shims (logical <-> device layout), slab partitioning, backend errors."""
+import numpy as np
+import pytest
+import torch
+
+from pour_over_coffee_lbm_b200 import slab
+from pour_over_coffee_lbm_b200.fields import ComponentField, ScalarField, VectorField
+from pour_over_coffee_lbm_b200.errors import BackendError, ComputeExecutionError
+
+
+def test_scalar_and_vector_field_views_are_logical_order():
+    nz, ny, nx = 5, 4, 8
+    t = torch.arange(nz * ny * nx, dtype=torch.float32).reshape(nz, ny, nx)
+    f = ScalarField(lambda: t)
+    assert f.shape == (nx, ny, nz)
+    assert f[3, 2, 1] == float(t[1, 2, 3])
+    f[3, 2, 1] = -1.0
+    assert float(t[1, 2, 3]) == -1.0                         # a view, not a copy
+    a = f.to_numpy()
+    assert a.shape == (nx, ny, nz) and a[3, 2, 1] == -1.0 and a.flags["C_CONTIGUOUS"]
+    f.from_numpy(np.full((nx, ny, nz), 2.5, np.float32)); assert float(t.min()) == 2.5
+    f.fill(0.0); assert float(t.abs().max()) == 0.0
+    v = torch.zeros(3, nz, ny, nx)
+    vf = VectorField(lambda: v)
+    assert vf.shape == (nx, ny, nz, 3)
+    vf[1, 2, 3] = [1.0, 2.0, 3.0]
+    assert v[:, 3, 2, 1].tolist() == [1.0, 2.0, 3.0]
+    assert ComponentField(lambda: v, 2)[1, 2, 3] == 3.0
+    vf.fill([0.5, 0.0, -0.5]); assert float(v[0].min()) == 0.5 and float(v[2].max()) == -0.5
+
+
+def test_ghost_planes_hidden_and_dirty_callback():
+    t = torch.zeros(6, 3, 4)
+    hits = []
+    f = ScalarField(lambda: t, zghost=1, on_write=lambda: hits.append(1))
+    assert f.shape == (4, 3, 4)
+    f.fill(1.0)
+    assert float(t[0].sum()) == 0 and float(t[-1].sum()) == 0 and float(t[1:-1].min()) == 1.0 and hits == [1]
+    f[0, 0, 0] = 3.0; assert len(hits) == 2 and float(t[1, 0, 0]) == 3.0
+
+
+def test_partition_and_neighbours():
+    parts = slab.partition_z(1024, 8)
+    assert [p.nz for p in parts] == [128] * 8 and [p.z0 for p in parts] == list(range(0, 1024, 128))
+    parts = slab.partition_z(10, 4)
+    assert [p.nz for p in parts] == [3, 3, 2, 2] and sum(p.nz for p in parts) == 10 and parts[-1].z0 + parts[-1].nz == 10
+    with pytest.raises(ValueError):
+        slab.partition_z(3, 4)
+    assert slab.neighbours(0, 4, False) == (None, 1) and slab.neighbours(3, 4, False) == (2, None)
+    assert slab.neighbours(0, 4, True) == (3, 1) and slab.neighbours(3, 4, True) == (2, 0)
+    assert slab.UP_Q == (5, 11, 12, 15, 16) and slab.DOWN_Q == (6, 13, 14, 17, 18)
+    assert slab.halo_bytes_per_step(1024, 1024) == 2 * 20971520                       # 20.97 MB per direction
+
+
+def test_error_hierarchy_names():
+    e = ComputeExecutionError("x", "b200", "EXECUTION_FAILED")
+    assert isinstance(e, BackendError) and e.backend_type == "b200" and e.error_code == "EXECUTION_FAILED"
+    assert BackendError("y").error_code == "UNKNOWN_ERROR"
+
+
+def test_single_rank_periodic_self_exchange():
+    g = torch.rand(19, 6, 3, 4)
+    before = g.clone()
+    slab.exchange_halo(g, 0, 1, True)
+    for q in slab.UP_Q: assert torch.equal(g[q, 0], before[q, 4])
+    for q in slab.DOWN_Q: assert torch.equal(g[q, 5], before[q, 1])
+    assert torch.equal(g[:, 1:5], before[:, 1:5])
