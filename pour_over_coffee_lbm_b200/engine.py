@@ -32,7 +32,7 @@ def _ptr(t: Optional[torch.Tensor]):
 class D3Q19Engine:
     def __init__(self, nx: int, ny: int, nz: int, *, compat: str = "physical",
                  periodic: Sequence[bool] = (True, True, True), walls: bool = False, force: bool = False,
-                 phase: bool = False, les: bool = False, porous: bool = False, strict: bool = False,
+                 phase: bool = False, les: bool = False, porous: bool = False, strict: bool = True,
                  config: Optional[LBMConfig] = None, device: int = 0, zghost: int = 0, z0: int = 0,
                  nz_global: Optional[int] = None, tau: Optional[float] = None, tau_air: Optional[float] = None,
                  gravity_lu: Optional[float] = None, cs_smag: Optional[float] = None,

@@ -28,7 +28,7 @@ class LBMSolver:
     def __init__(self, nx: Optional[int] = None, ny: Optional[int] = None, nz: Optional[int] = None, *,
                  config: Optional[LBMConfig] = None, compat: str = "reference", periodic=(False, False, False),
                  geometry: bool = True, force: bool = True, phase: bool = True, les: Optional[bool] = None,
-                 porous: Optional[bool] = None, strict: bool = False, device: int = 0, **engine_kw):
+                 porous: Optional[bool] = None, strict: bool = True, device: int = 0, **engine_kw):
         cfg = config or LBMConfig(NX=nx or cfgmod.DEFAULT.NX, NY=ny or cfgmod.DEFAULT.NY,
                                   NZ=engine_kw.get("nz_global") or nz or cfgmod.DEFAULT.NZ)
         self.config = cfg

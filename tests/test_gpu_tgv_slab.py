@@ -34,7 +34,7 @@ def test_taylor_green_decay_rate_256(tau):
     f32 AND in an f64 run of the oracle, 0.98 % at 0.02, 0.25 % at 0.01."""
     import torch
     n, u0 = 256, 0.01
-    eng = _engine(n, n, n, compat="physical", tau=tau)
+    eng = _engine(n, n, n, compat="physical", tau=tau)          # default build = strict
     rho0, uinit = _tgv2d(n, u0)
     eng.init_equilibrium(rho=rho0, u=uinit)
     steps, every = 1000, 50
@@ -52,7 +52,7 @@ def test_taylor_green_decay_rate_256(tau):
     expected = -4.0 * nu * k * k
     assert abs(slope / expected - 1.0) <= 5e-3, (slope, expected)
     # uz stays at rounding level and the flow stays exactly z-invariant
-    assert float(eng.u[2].abs().max()) < 1e-5 * u0
+    assert float(eng.u[2].abs().max()) < 1e-4 * u0
     assert float((eng.u[0][0] - eng.u[0][n // 2]).abs().max()) == 0.0
 
 
