@@ -5,18 +5,20 @@
 #include <stdio.h>
 #include <string.h>
 #include <string>
+#include <vector>
 
 #include "lbm_common.cuh"
 
 namespace lbm {
 using StepKernel = void (*)(const StepArgs);
-#define DECL_LOOKUP(name) StepKernel name(int forced, int les, int porous, int vec, int collide, int *block);
+#define DECL_LOOKUP(name) StepKernel name(int forced, int les, int porous, int vec, int collide, int boundary, int *block);
 DECL_LOOKUP(lookup_fast_g0_fn) DECL_LOOKUP(lookup_fast_g1_fn) DECL_LOOKUP(lookup_fast_g2_fn) DECL_LOOKUP(lookup_fast_g3_fn)
 DECL_LOOKUP(lookup_strict_g0_fn) DECL_LOOKUP(lookup_strict_g1_fn) DECL_LOOKUP(lookup_strict_g2_fn) DECL_LOOKUP(lookup_strict_g3_fn)
 
 cudaError_t launch_init_equilibrium(const Grid &, int, float *, const float *, const float *, float, const float[3], cudaStream_t);
 cudaError_t launch_v60_geometry(const Grid &, uint8_t *, int32_t *, const float[5], cudaStream_t);
 cudaError_t launch_pack_flags(const Grid &, uint8_t *, const uint8_t *, const int32_t *, const int32_t *, cudaStream_t);
+cudaError_t build_work_lists(const Grid &, const uint8_t *, int, int, int **, std::vector<int> &, int **, std::vector<int> &, cudaStream_t);
 cudaError_t launch_convert_f(const Grid &, bool, const float *, const uint8_t *, float *, cudaStream_t);
 cudaError_t launch_face_bc(const Grid &, float *, const uint8_t *, cudaStream_t, int *);
 cudaError_t launch_pressure_gradient(const Grid &, const float *, const uint8_t *, float *, float, float, cudaStream_t);
@@ -71,6 +73,11 @@ struct lbm_ctx {
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
     cudaEvent_t ev_boundary = nullptr, ev_comm = nullptr;
+    // work lists of the walls path (built by lbm_pack_flags for the flag field it packed)
+    int *d_tiles = nullptr, *d_bcells = nullptr;
+    std::vector<int> tile_off, bcell_off;      // per owned plane offsets into the lists (nz+1 entries)
+    const uint8_t *list_flags = nullptr;
+    int list_vec = 0;
 };
 
 static int fail(lbm_ctx *ctx, const std::string &msg) {
@@ -94,6 +101,14 @@ static int make_grid(lbm_ctx *ctx, const lbm_params *p, Grid *g) {
     g->plane = (long long)p->nx * p->ny;
     g->vol = g->plane * (p->nz + 2 * p->zghost);
     return 0;
+}
+
+static int pick_vec(const lbm_ctx *ctx) {
+    int vec = ctx->p.vec;
+    if (vec == 0) vec = 4;
+    if (vec == 2) vec = 1;
+    if (ctx->g.nx % 4 != 0 || ctx->g.nx < 8) vec = 1;
+    return vec;
 }
 
 extern "C" {
@@ -130,6 +145,7 @@ int lbm_set_params(lbm_ctx *ctx, const lbm_params *p) {
     if (!ctx || !p) return fail(ctx, "null argument");
     Grid g;
     if (make_grid(ctx, p, &g)) return 1;
+    if (g.nx != ctx->g.nx || g.ny != ctx->g.ny || g.nz != ctx->g.nz || g.zg != ctx->g.zg || p->vec != ctx->p.vec) ctx->list_flags = nullptr;
     ctx->g = g; ctx->p = *p;
     return 0;
 }
@@ -139,6 +155,8 @@ void lbm_destroy(lbm_ctx *ctx) {
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     if (ctx->ev_boundary) cudaEventDestroy(ctx->ev_boundary);
     if (ctx->ev_comm) cudaEventDestroy(ctx->ev_comm);
+    if (ctx->d_tiles) cudaFree(ctx->d_tiles);
+    if (ctx->d_bcells) cudaFree(ctx->d_bcells);
     delete ctx;
 }
 
@@ -163,25 +181,34 @@ int lbm_pack_flags(lbm_ctx *ctx, uint8_t *flags, const uint8_t *solid, const int
     if (!ctx || !flags || !solid) return fail(ctx, "null argument");
     CUDA_OK(ctx, launch_pack_flags(ctx->g, flags, solid, filter_zone, les_mask, (cudaStream_t)stream));
     ctx->launches++;
+    // active-tile list for the bulk kernel and the compact list of near-wall cells (synchronises the stream)
+    const int vec = pick_vec(ctx);
+    CUDA_OK(ctx, build_work_lists(ctx->g, flags, vec, vec == 1 ? 256 : 128, &ctx->d_tiles, ctx->tile_off, &ctx->d_bcells,
+                                  ctx->bcell_off, (cudaStream_t)stream));
+    ctx->launches += 5;
+    ctx->list_flags = flags; ctx->list_vec = vec;
     return 0;
 }
 
 }  // extern "C"
 
 // ---- step ---------------------------------------------------------------------------------------
-static StepKernel lookup(const lbm_params &p, int vec, int collide, int *block) {
+static StepKernel lookup(const lbm_params &p, int vec, int collide, int boundary, int *block) {
     const int walls = (p.features & LBM_FEAT_WALLS) != 0;
     const int forced = (p.features & (LBM_FEAT_FORCE | LBM_FEAT_PHASE)) != 0;
     const int les = (p.features & LBM_FEAT_LES) != 0;
     const int porous = (p.features & LBM_FEAT_POROUS) != 0;
     const int group = p.compat * 2 + walls;
     const bool strict = (p.features & LBM_FEAT_STRICT) != 0;
+#define LBM_PICK(g) (strict ? lookup_strict_g##g##_fn(forced, les, porous, vec, collide, boundary, block) \
+                            : lookup_fast_g##g##_fn(forced, les, porous, vec, collide, boundary, block))
     switch (group) {
-        case 0: return strict ? lookup_strict_g0_fn(forced, les, porous, vec, collide, block) : lookup_fast_g0_fn(forced, les, porous, vec, collide, block);
-        case 1: return strict ? lookup_strict_g1_fn(forced, les, porous, vec, collide, block) : lookup_fast_g1_fn(forced, les, porous, vec, collide, block);
-        case 2: return strict ? lookup_strict_g2_fn(forced, les, porous, vec, collide, block) : lookup_fast_g2_fn(forced, les, porous, vec, collide, block);
-        default: return strict ? lookup_strict_g3_fn(forced, les, porous, vec, collide, block) : lookup_fast_g3_fn(forced, les, porous, vec, collide, block);
+        case 0: return LBM_PICK(0);
+        case 1: return LBM_PICK(1);
+        case 2: return LBM_PICK(2);
+        default: return LBM_PICK(3);
     }
+#undef LBM_PICK
 }
 
 static int fill_args(lbm_ctx *ctx, const lbm_fields *f, StepArgs *a) {
@@ -205,23 +232,53 @@ static int fill_args(lbm_ctx *ctx, const lbm_fields *f, StepArgs *a) {
     return 0;
 }
 
-static int pick_vec(const lbm_ctx *ctx) {
-    int vec = ctx->p.vec;
-    if (vec == 0) vec = 4;
-    if (vec == 2) vec = 1;
-    if (ctx->g.nx % 4 != 0 || ctx->g.nx < 8) vec = 1;
-    return vec;
+// The kernels of one step: dense grid (periodic, no flags) or bulk-over-active-tiles + near-wall list (walls).
+struct Launcher {
+    StepKernel main = nullptr, boundary = nullptr;
+    int block = 0, bblock = 0, vec = 1;
+    bool walls = false;
+};
+
+static int make_launcher(lbm_ctx *ctx, const lbm_params &p, const lbm_fields *f, int vec, int collide, Launcher *L) {
+    L->vec = vec;
+    L->walls = (p.features & LBM_FEAT_WALLS) != 0;
+    L->main = lookup(p, vec, collide, 0, &L->block);
+    if (!L->main) return fail(ctx, "no step kernel built for this feature combination");
+    if (L->walls) {
+        L->boundary = lookup(p, 1, collide, 1, &L->bblock);
+        if (!L->boundary) return fail(ctx, "no boundary kernel built for this feature combination");
+        if (ctx->list_flags != f->flags || ctx->list_vec != vec || (int)ctx->tile_off.size() != ctx->g.nz + 1)
+            return fail(ctx, "work lists are stale: call lbm_pack_flags on this flags field (after any geometry or vec change)");
+    }
+    return 0;
 }
 
-// launch the step kernel on owned planes [z_begin, z_end)
-static int launch_planes(lbm_ctx *ctx, StepArgs &a, StepKernel k, int block, int vec, int z_begin, int z_end, cudaStream_t s) {
+// launch one step on owned planes [z_begin, z_end)
+static int launch_planes(lbm_ctx *ctx, StepArgs &a, const Launcher &L, int z_begin, int z_end, cudaStream_t s) {
     if (z_end <= z_begin) return 0;
-    a.z_begin = z_begin; a.z_end = z_end;
-    const long long per_plane = (long long)(ctx->g.nx / vec) * ctx->g.ny;
-    dim3 grid((unsigned)((per_plane + block - 1) / block), (unsigned)(z_end - z_begin));
-    k<<<grid, block, 0, s>>>(a);
-    CUDA_OK(ctx, cudaGetLastError());
-    ctx->launches++;
+    if (!L.walls) {
+        a.z_begin = z_begin; a.z_end = z_end;
+        const long long per_plane = (long long)(ctx->g.nx / L.vec) * ctx->g.ny;
+        dim3 grid((unsigned)((per_plane + L.block - 1) / L.block), (unsigned)(z_end - z_begin));
+        L.main<<<grid, L.block, 0, s>>>(a);
+        CUDA_OK(ctx, cudaGetLastError());
+        ctx->launches++;
+        return 0;
+    }
+    const int t0 = ctx->tile_off[z_begin], t1 = ctx->tile_off[z_end];
+    if (t1 > t0) {
+        a.items = ctx->d_tiles; a.item_begin = t0; a.n_items = t1 - t0;
+        L.main<<<(unsigned)(t1 - t0), L.block, 0, s>>>(a);
+        CUDA_OK(ctx, cudaGetLastError());
+        ctx->launches++;
+    }
+    const int b0 = ctx->bcell_off[z_begin], b1 = ctx->bcell_off[z_end];
+    if (b1 > b0) {
+        a.items = ctx->d_bcells; a.item_begin = b0; a.n_items = b1 - b0;
+        L.boundary<<<(unsigned)((b1 - b0 + L.bblock - 1) / L.bblock), L.bblock, 0, s>>>(a);
+        CUDA_OK(ctx, cudaGetLastError());
+        ctx->launches++;
+    }
     return 0;
 }
 
@@ -292,9 +349,8 @@ int lbm_step(lbm_ctx *ctx, lbm_fields *f, int nsteps, int write_macro_every, voi
     if (!f->f_dst) return fail(ctx, "f_dst is NULL");
     const lbm_params &p = ctx->p;
     const int vec = pick_vec(ctx);
-    int block = 0;
-    StepKernel k = lookup(p, vec, 1, &block);
-    if (!k) return fail(ctx, "no step kernel built for this feature combination");
+    Launcher L;
+    if (make_launcher(ctx, p, f, vec, 1, &L)) return 1;
     const bool ref_les = p.compat == LBM_COMPAT_REFERENCE && (p.features & LBM_FEAT_LES);
     if (ref_les && write_macro_every != 1) return fail(ctx, "compat=reference with LES needs u every step (write_macro_every must be 1)");
     if (ref_les && (!f->u_src || !f->u_dst || f->u_src == f->u_dst)) return fail(ctx, "compat=reference with LES needs distinct u_src/u_dst");
@@ -309,16 +365,16 @@ int lbm_step(lbm_ctx *ctx, lbm_fields *f, int nsteps, int write_macro_every, voi
         if (a.write_macro && (!f->rho || !f->u_dst)) return fail(ctx, "write_macro requested but rho/u_dst is NULL");
         if (overlap) {
             // boundary planes first, then the halo travels on the comm stream while the interior runs
-            if (launch_planes(ctx, a, k, block, vec, 0, 1, cs)) return 1;
-            if (launch_planes(ctx, a, k, block, vec, ctx->g.nz - 1, ctx->g.nz, cs)) return 1;
+            if (launch_planes(ctx, a, L, 0, 1, cs)) return 1;
+            if (launch_planes(ctx, a, L, ctx->g.nz - 1, ctx->g.nz, cs)) return 1;
             CUDA_OK(ctx, cudaEventRecord(ctx->ev_boundary, cs));
             CUDA_OK(ctx, cudaStreamWaitEvent(ms, ctx->ev_boundary, 0));
-            if (launch_planes(ctx, a, k, block, vec, 1, ctx->g.nz - 1, cs)) return 1;
+            if (launch_planes(ctx, a, L, 1, ctx->g.nz - 1, cs)) return 1;
             if (exchange(ctx, f->f_dst, (ref_les && a.write_macro) ? f->u_dst : nullptr, ms)) return 1;
             CUDA_OK(ctx, cudaEventRecord(ctx->ev_comm, ms));
             CUDA_OK(ctx, cudaStreamWaitEvent(cs, ctx->ev_comm, 0));
         } else {
-            if (launch_planes(ctx, a, k, block, vec, 0, ctx->g.nz, cs)) return 1;
+            if (launch_planes(ctx, a, L, 0, ctx->g.nz, cs)) return 1;
             if (slabs && exchange(ctx, f->f_dst, (ref_les && a.write_macro) ? f->u_dst : nullptr, cs)) return 1;
         }
         float *t = f->f_src; f->f_src = f->f_dst; f->f_dst = t;
@@ -329,17 +385,30 @@ int lbm_step(lbm_ctx *ctx, lbm_fields *f, int nsteps, int write_macro_every, voi
 
 int lbm_macroscopic(lbm_ctx *ctx, const lbm_fields *f, void *stream) {
     if (!ctx || !f) return fail(ctx, "null argument");
-    int block = 0;
     lbm_params p = ctx->p;
     p.features &= ~LBM_FEAT_LES;
     if (p.compat == LBM_COMPAT_REFERENCE) p.features &= ~LBM_FEAT_POROUS;
-    StepKernel k = lookup(p, 1, 0, &block);
-    if (!k) return fail(ctx, "no macroscopic kernel built for this feature combination");
+    Launcher L;
+    {
+        // the moments-only variants exist for VEC = 1; the tile list was built for pick_vec(): rebuild on demand
+        const int vec = pick_vec(ctx);
+        if ((p.features & LBM_FEAT_WALLS) && vec != 1) {
+            CUDA_OK(ctx, build_work_lists(ctx->g, f->flags, 1, 256, &ctx->d_tiles, ctx->tile_off, &ctx->d_bcells, ctx->bcell_off, (cudaStream_t)stream));
+            ctx->list_vec = 1; ctx->list_flags = f->flags;
+        }
+        const int rc = make_launcher(ctx, p, f, 1, 0, &L);
+        if (rc) return rc;
+    }
     StepArgs a;
     if (fill_args(ctx, f, &a)) return 1;
     if (!f->rho || !f->u_dst) return fail(ctx, "rho/u_dst is NULL");
     a.write_macro = 1;
-    return launch_planes(ctx, a, k, block, 1, 0, ctx->g.nz, (cudaStream_t)stream);
+    int rc = launch_planes(ctx, a, L, 0, ctx->g.nz, (cudaStream_t)stream);
+    if ((p.features & LBM_FEAT_WALLS) && pick_vec(ctx) != 1) {      // restore the lists of the step kernel
+        CUDA_OK(ctx, build_work_lists(ctx->g, f->flags, pick_vec(ctx), 128, &ctx->d_tiles, ctx->tile_off, &ctx->d_bcells, ctx->bcell_off, (cudaStream_t)stream));
+        ctx->list_vec = pick_vec(ctx);
+    }
+    return rc;
 }
 
 int lbm_face_bc(lbm_ctx *ctx, const lbm_fields *f, void *stream) {

@@ -1,6 +1,11 @@
 // Initialisation, geometry, flag packing, f<->g conversion, face BCs and the small
 // stencil kernels that feed body_force.  Compiled with -fmad=false so that every value is
 // bit-identical to oracle/d3q19_ref.py (these kernels are not on the roofline path).
+#include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
+
+#include <vector>
+
 #include "lbm_common.cuh"
 
 namespace lbm {
@@ -235,6 +240,104 @@ __global__ void add_reaction_kernel(Grid G, const float *reaction, const uint8_t
 #pragma unroll
         for (int d = 0; d < 3; ++d) bf[d * n + c] = bf[d * n + c] + reaction[d * n + c];
     }
+}
+
+// ---- work lists for the step kernel ---------------------------------------------------------------
+// active tiles: a tile = BLOCK consecutive threads of the bulk mapping inside one z-plane; it is active when at
+// least one of its cells is bulk fluid (fluid and not NEAR).  boundary cells: fluid and NEAR, owned planes only.
+__global__ void tile_flags_kernel(Grid G, const uint8_t *flags, int vec, int block, int tpp, uint8_t *tile_flag, int *plane_count) {
+    const int nxv = G.nx / vec;
+    const int per_plane = nxv * G.ny;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int z = blockIdx.y;
+    if (t >= per_plane) return;
+    const int y = t / nxv, x0 = (t - y * nxv) * vec;
+    const long long own = ((long long)(z + G.zg) * G.ny + y) * G.nx + x0;
+    bool bulk = false;
+    for (int c = 0; c < vec; ++c) {
+        const unsigned f = flags[own + c];
+        bulk |= !(f & LBM_FLAG_SOLID) && !(f & LBM_FLAG_NEAR);
+    }
+    if (bulk) {
+        const int tile = z * tpp + t / block;
+        (void)plane_count;
+        tile_flag[tile] = 1;
+    }
+}
+
+__global__ void count_flagged_per_plane_kernel(const uint8_t *tile_flag, int tpp, int nz, int *plane_count) {
+    const int z = blockIdx.x;
+    int n = 0;
+    for (int i = threadIdx.x; i < tpp; i += blockDim.x) n += tile_flag[(long long)z * tpp + i] ? 1 : 0;
+    typedef cub::BlockReduce<int, 256> BR;
+    __shared__ typename BR::TempStorage tmp;
+    const int tot = BR(tmp).Sum(n);
+    if (threadIdx.x == 0 && z < nz) plane_count[z] = tot;
+}
+
+struct IsBoundaryCell {
+    const uint8_t *flags; int plane, zg, nz;
+    __device__ __forceinline__ bool operator()(const int &c) const {
+        const int z = c / plane - zg;
+        if (z < 0 || z >= nz) return false;
+        const unsigned f = flags[c];
+        return !(f & LBM_FLAG_SOLID) && (f & LBM_FLAG_NEAR);
+    }
+};
+
+__global__ void count_boundary_per_plane_kernel(Grid G, const uint8_t *flags, int *plane_count) {
+    const int z = blockIdx.x;
+    const long long base = (long long)(z + G.zg) * G.plane;
+    int n = 0;
+    for (long long i = threadIdx.x; i < G.plane; i += blockDim.x) {
+        const unsigned f = flags[base + i];
+        n += (!(f & LBM_FLAG_SOLID) && (f & LBM_FLAG_NEAR)) ? 1 : 0;
+    }
+    typedef cub::BlockReduce<int, 256> BR;
+    __shared__ typename BR::TempStorage tmp;
+    const int tot = BR(tmp).Sum(n);
+    if (threadIdx.x == 0) plane_count[z] = tot;
+}
+
+// Builds both lists (device arrays allocated here, owned by the caller = lbm_ctx) and their per-plane offsets
+// (host vectors of nz+1 entries).  Synchronises the stream: geometry changes are rare, init-time events.
+cudaError_t build_work_lists(const Grid &G, const uint8_t *flags, int vec, int block, int **d_tiles, std::vector<int> &tile_off,
+                             int **d_bcells, std::vector<int> &bcell_off, cudaStream_t s) {
+    cudaError_t e;
+    const int nxv = G.nx / vec, per_plane = nxv * G.ny, tpp = (per_plane + block - 1) / block;
+    const long long ntiles = (long long)tpp * G.nz;
+    uint8_t *tile_flag = nullptr; int *d_count = nullptr, *d_num = nullptr; void *tmp = nullptr; size_t tmp_bytes = 0;
+    if ((e = cudaMalloc(&tile_flag, (size_t)ntiles)) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&d_count, sizeof(int) * (size_t)G.nz * 2)) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&d_num, sizeof(int))) != cudaSuccess) return e;
+    cudaMemsetAsync(tile_flag, 0, (size_t)ntiles, s);
+    tile_flags_kernel<<<dim3((per_plane + 255) / 256, G.nz), 256, 0, s>>>(G, flags, vec, block, tpp, tile_flag, nullptr);
+    count_flagged_per_plane_kernel<<<G.nz, 256, 0, s>>>(tile_flag, tpp, G.nz, d_count);
+    count_boundary_per_plane_kernel<<<G.nz, 256, 0, s>>>(G, flags, d_count + G.nz);
+    std::vector<int> counts((size_t)G.nz * 2);
+    if ((e = cudaMemcpyAsync(counts.data(), d_count, sizeof(int) * counts.size(), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+    tile_off.assign(G.nz + 1, 0); bcell_off.assign(G.nz + 1, 0);
+    for (int z = 0; z < G.nz; ++z) { tile_off[z + 1] = tile_off[z] + counts[z]; bcell_off[z + 1] = bcell_off[z] + counts[G.nz + z]; }
+    if (*d_tiles) { cudaFree(*d_tiles); *d_tiles = nullptr; }
+    if (*d_bcells) { cudaFree(*d_bcells); *d_bcells = nullptr; }
+    const int n_t = tile_off[G.nz], n_b = bcell_off[G.nz];
+    if ((e = cudaMalloc(d_tiles, sizeof(int) * (size_t)(n_t > 0 ? n_t : 1))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(d_bcells, sizeof(int) * (size_t)(n_b > 0 ? n_b : 1))) != cudaSuccess) return e;
+    thrust::counting_iterator<int> idx(0);
+    // tiles: ids in ascending (z, tile) order -> launch order follows memory order
+    cub::DeviceSelect::Flagged(nullptr, tmp_bytes, idx, tile_flag, *d_tiles, d_num, (int)ntiles, s);
+    size_t need = tmp_bytes;
+    IsBoundaryCell pred{flags, (int)G.plane, G.zg, G.nz};
+    cub::DeviceSelect::If(nullptr, tmp_bytes, idx, *d_bcells, d_num, (int)G.vol, pred, s);
+    if (tmp_bytes > need) need = tmp_bytes;
+    if ((e = cudaMalloc(&tmp, need)) != cudaSuccess) return e;
+    if (n_t > 0) cub::DeviceSelect::Flagged(tmp, need, idx, tile_flag, *d_tiles, d_num, (int)ntiles, s);
+    if (n_b > 0) cub::DeviceSelect::If(tmp, need, idx, *d_bcells, d_num, (int)G.vol, pred, s);
+    e = cudaStreamSynchronize(s);
+    cudaFree(tmp); cudaFree(tile_flag); cudaFree(d_count); cudaFree(d_num);
+    if (e != cudaSuccess) return e;
+    return cudaGetLastError();
 }
 
 // ---- host launchers (called from lbm_api.cu) -----------------------------------------------

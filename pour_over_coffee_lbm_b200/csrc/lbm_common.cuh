@@ -36,7 +36,9 @@ struct StepArgs {
     float *rho; const float *u_src; float *u_dst;
     const float *force; const float *phase; const float *blockage;
     const uint8_t *flags;
-    int z_begin, z_end;    // owned planes processed by this launch
+    int z_begin, z_end;    // owned planes processed by this launch (dense mode)
+    const int *items;      // bulk mode: active-tile ids; boundary mode: linear indices of NEAR fluid cells
+    int item_begin, n_items;
     int write_macro;
     float tau_water, tau_air, gravity_lu;
     float tau_min, tau_max;

@@ -17,25 +17,26 @@ using StepKernel = void (*)(const StepArgs);
 constexpr int G_COMPAT = LBM_GROUP / 2;
 constexpr bool G_WALLS = (LBM_GROUP % 2) != 0;
 
-template <bool FORCED, bool LES, bool POROUS, int VEC, bool COLLIDE>
+template <int MODE, bool FORCED, bool LES, bool POROUS, int VEC, bool COLLIDE>
 static StepKernel pick() {
     if constexpr (POROUS && !G_WALLS) return nullptr;          // the filter zone lives in the flag byte
     else if constexpr (!COLLIDE && (LES || VEC != 1)) return nullptr;
-    else return step_kernel<LBM_STRICT_BUILD, G_COMPAT, G_WALLS, FORCED, LES, POROUS, VEC, (VEC == 1 ? 256 : 128), COLLIDE>;
+    else if constexpr (MODE == MODE_BOUNDARY && VEC != 1) return nullptr;
+    else return step_kernel<LBM_STRICT_BUILD, G_COMPAT, MODE, FORCED, LES, POROUS, VEC, (VEC == 1 ? 256 : 128), COLLIDE>;
 }
 
-template <int VEC, bool COLLIDE>
+template <int MODE, int VEC, bool COLLIDE>
 static StepKernel pick_feat(int forced, int les, int porous) {
     const int key = (forced ? 4 : 0) | (les ? 2 : 0) | (porous ? 1 : 0);
     switch (key) {
-        case 0: return pick<false, false, false, VEC, COLLIDE>();
-        case 1: return pick<false, false, true, VEC, COLLIDE>();
-        case 2: return pick<false, true, false, VEC, COLLIDE>();
-        case 3: return pick<false, true, true, VEC, COLLIDE>();
-        case 4: return pick<true, false, false, VEC, COLLIDE>();
-        case 5: return pick<true, false, true, VEC, COLLIDE>();
-        case 6: return pick<true, true, false, VEC, COLLIDE>();
-        default: return pick<true, true, true, VEC, COLLIDE>();
+        case 0: return pick<MODE, false, false, false, VEC, COLLIDE>();
+        case 1: return pick<MODE, false, false, true, VEC, COLLIDE>();
+        case 2: return pick<MODE, false, true, false, VEC, COLLIDE>();
+        case 3: return pick<MODE, false, true, true, VEC, COLLIDE>();
+        case 4: return pick<MODE, true, false, false, VEC, COLLIDE>();
+        case 5: return pick<MODE, true, false, true, VEC, COLLIDE>();
+        case 6: return pick<MODE, true, true, false, VEC, COLLIDE>();
+        default: return pick<MODE, true, true, true, VEC, COLLIDE>();
     }
 }
 
@@ -47,14 +48,23 @@ static StepKernel pick_feat(int forced, int les, int porous) {
 #define LBM_LOOKUP LBM_CAT(lookup_fast_g, LBM_GROUP, fn)
 #endif
 
-// returns the kernel and its CTA size, or nullptr when the combination is not built
-StepKernel LBM_LOOKUP(int forced, int les, int porous, int vec, int collide, int *block) {
+// `boundary` = 0: the main kernel (dense when the group has no walls, bulk-over-tiles otherwise);
+// `boundary` = 1: the near-wall list kernel (walls groups only).  Returns nullptr when not built.
+StepKernel LBM_LOOKUP(int forced, int les, int porous, int vec, int collide, int boundary, int *block) {
     StepKernel k = nullptr;
+    constexpr int MAIN = G_WALLS ? MODE_BULK : MODE_DENSE;
+    if (boundary) {
+        if constexpr (G_WALLS) {
+            k = collide ? pick_feat<MODE_BOUNDARY, 1, true>(forced, les, porous) : pick_feat<MODE_BOUNDARY, 1, false>(forced, les, porous);
+        }
+        *block = 256;
+        return k;
+    }
     if (collide) {
-        if (vec == 4) k = pick_feat<4, true>(forced, les, porous);
-        else if (vec == 1) k = pick_feat<1, true>(forced, les, porous);
+        if (vec == 4) k = pick_feat<MAIN, 4, true>(forced, les, porous);
+        else if (vec == 1) k = pick_feat<MAIN, 1, true>(forced, les, porous);
     } else {
-        if (vec == 1) k = pick_feat<1, false>(forced, les, porous);
+        if (vec == 1) k = pick_feat<MAIN, 1, false>(forced, les, porous);
     }
     *block = (vec == 1) ? 256 : 128;
     return k;

@@ -10,7 +10,8 @@
 //
 // Template parameters
 //   COMPAT  LBM_COMPAT_PHYSICAL | LBM_COMPAT_REFERENCE   
-//   WALLS   flag byte consulted (solid skip, bounce-back, open faces); else fully periodic
+//   MODE    dense (fully periodic, no flags) | bulk (active-tile list, near-wall cells skipped) |
+//           boundary (compact list of near-wall cells: bounce-back, open faces) -- see the kernel
 //   FORCED  body_force / phase inputs active (either pointer may still be NULL)
 //   LES     Smagorinsky: physical = local Pi^neq closed form, reference = FD on lagged u
 //   POROUS  filter-zone drag: physical = Guo-Zhao force, reference = post-step u damping
@@ -253,60 +254,95 @@ __device__ __forceinline__ float les_fd_nu(const float *__restrict__ u, long lon
     if (fabsf(phase) < 0.9f) return 0.0f;
     return fminf(csd * mag, 0.1f);
 }
-
 // ---------------------------------------------------------------------------------------------
 // the kernel
+//
+// MODE selects how threads map to cells:
+//   MODE_DENSE     every cell of planes [z_begin, z_end) -- fully periodic boxes without a flag field.
+//   MODE_BULK      one CTA per entry of the ACTIVE-TILE list (tiles that hold at least one bulk-fluid cell;
+//                  the 65 % solid part of a V60 box is never launched).  Cells flagged NEAR (a solid or
+//                  out-of-box D3Q19 neighbour) are skipped here, so this path carries no bounce-back code.
+//   MODE_BOUNDARY  one thread per entry of the compact list of NEAR fluid cells (VEC = 1): halfway bounce-back
+//                  and open-face inflow, legacy/lbm_solver.py:609-628.  A few percent of the fluid cells.
 // ---------------------------------------------------------------------------------------------
+enum { MODE_DENSE = 0, MODE_BULK = 1, MODE_BOUNDARY = 2 };
+
 // BUILD (0 = fast, 1 = strict/-fmad=false) only makes the two builds distinct symbols: without it the
 // linker would merge the identically-named instantiations of the two translation units (ODR).
-template <int BUILD, int COMPAT, bool WALLS, bool FORCED, bool LES, bool POROUS, int VEC, int BLOCK, bool COLLIDE = true>
+template <int BUILD, int COMPAT, int MODE, bool FORCED, bool LES, bool POROUS, int VEC, int BLOCK, bool COLLIDE = true>
 __global__ void __launch_bounds__(BLOCK) step_kernel(const StepArgs P) {
+    constexpr bool WALLS = MODE != MODE_DENSE;
+    static_assert(MODE != MODE_BOUNDARY || VEC == 1, "the boundary list is processed one cell per thread");
     const Grid &G = P.g;
     const int nxv = G.nx / VEC;
     const int per_plane = nxv * G.ny;
-    int t = blockIdx.x * BLOCK + threadIdx.x;
-    const bool active = t < per_plane;
-    if (!active) t = per_plane - 1;
-    const int y = t / nxv;
-    const int xv = t - y * nxv;
+    constexpr unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+
+    bool active;
+    int xv, y, z;
+    if constexpr (MODE == MODE_BOUNDARY) {
+        int i = blockIdx.x * BLOCK + threadIdx.x;
+        active = i < P.n_items;
+        if (!active) i = P.n_items - 1;
+        const int cell = __ldg(P.items + P.item_begin + i);
+        const int zp_ = cell / (int)G.plane;
+        const int rem = cell - zp_ * (int)G.plane;
+        y = rem / G.nx; xv = rem - y * G.nx; z = zp_ - G.zg;
+    } else {
+        int t;
+        if constexpr (MODE == MODE_BULK) {
+            const int tile = __ldg(P.items + P.item_begin + blockIdx.x);
+            const int tpp = (per_plane + BLOCK - 1) / BLOCK;
+            z = tile / tpp;
+            t = (tile - z * tpp) * BLOCK + threadIdx.x;
+        } else {
+            t = blockIdx.x * BLOCK + threadIdx.x;
+            z = P.z_begin + blockIdx.y;
+        }
+        active = t < per_plane;
+        if (!active) t = per_plane - 1;
+        y = t / nxv;
+        xv = t - y * nxv;
+    }
     const int x0 = xv * VEC;
-    const int z = P.z_begin + blockIdx.y;
     const int zp = z + G.zg;
     const long long own = ((long long)zp * G.ny + y) * G.nx + x0;
-    const unsigned lane = threadIdx.x & 31u;
-    constexpr unsigned FULL = 0xffffffffu;
 
+    // flag byte: which of this thread's cells does THIS launch update?
     unsigned fl[VEC];
-    bool any_solid = false, all_solid = true, any_near = false;
+    bool mine[VEC];
+    bool any_mine = false, all_mine = true;
     if constexpr (WALLS) {
         if constexpr (VEC == 4) {
             const unsigned w = __ldg(reinterpret_cast<const unsigned *>(P.flags + own));
 #pragma unroll
             for (int c = 0; c < 4; ++c) fl[c] = (w >> (8 * c)) & 0xffu;
-        } else if constexpr (VEC == 2) {
-            const unsigned short w = __ldg(reinterpret_cast<const unsigned short *>(P.flags + own));
-            fl[0] = w & 0xffu; fl[1] = (w >> 8) & 0xffu;
         } else {
             fl[0] = __ldg(P.flags + own);
         }
 #pragma unroll
         for (int c = 0; c < VEC; ++c) {
-            const bool s = (fl[c] & LBM_FLAG_SOLID) != 0;
-            any_solid |= s; all_solid &= s; any_near |= (!s && (fl[c] & LBM_FLAG_NEAR));
+            const bool fluid = !(fl[c] & LBM_FLAG_SOLID);
+            const bool near = (fl[c] & LBM_FLAG_NEAR) != 0;
+            mine[c] = fluid && (MODE == MODE_BOUNDARY ? near : !near);
+            any_mine |= mine[c]; all_mine &= mine[c];
         }
     } else {
 #pragma unroll
-        for (int c = 0; c < VEC; ++c) fl[c] = LBM_FLAG_LES;
-        all_solid = false;
+        for (int c = 0; c < VEC; ++c) { fl[c] = LBM_FLAG_LES; mine[c] = true; }
+        any_mine = true;
     }
-    const bool skip = !active || all_solid;
-    if (__all_sync(FULL, skip)) return;   // whole warp solid (65 % of a V60 box): 1 B/cell and done
-    // In a mixed warp every lane loads (VEC > 1): a lane whose own cells are solid still supplies the x+-1
-    // neighbours of the shifted populations to the adjacent lane, and those come from rows y-+1 / z-+1 whose
-    // cells may be fluid.  For VEC == 1 nothing is exchanged, so solid/inactive lanes skip their loads.
-    const bool noload = (VEC == 1) && skip;
+    const bool skip = !active || !any_mine;
+    if constexpr (VEC > 1) {
+        if (__all_sync(FULL, skip)) return;
+    } else {
+        if (skip) return;      // no lane exchange when VEC == 1
+    }
+    // VEC > 1: in a mixed warp every lane loads -- a lane whose own cells are skipped still supplies the x+-1
+    // neighbours of the shifted populations to the adjacent lane, and those come from rows y-+1 / z-+1.
 
-    // neighbour rows / columns with periodic wrap (open faces clamp; the value is replaced below)
+    // neighbour rows / columns with periodic wrap (open faces clamp; such cells are NEAR and handled below)
     int ym = y - 1; if (ym < 0) ym = G.per_y ? G.ny - 1 : 0;
     int yq = y + 1; if (yq >= G.ny) yq = G.per_y ? 0 : G.ny - 1;
     int zm, zq;
@@ -324,27 +360,23 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const StepArgs P) {
         const int rz = cz(q) > 0 ? zm : (cz(q) < 0 ? zq : zp);
         const int ry = cy(q) > 0 ? ym : (cy(q) < 0 ? yq : y);
         const float *row = P.src + (long long)q * G.vol + ((long long)rz * G.ny + ry) * G.nx;
-        if constexpr (VEC == 1 && cx(q) != 0) {
-            f[q][0] = noload ? 0.0f : __ldcs(row + (cx(q) > 0 ? xm : xq));
+        if constexpr (VEC == 1) {
+            f[q][0] = __ldcs(row + (cx(q) > 0 ? xm : (cx(q) < 0 ? xq : x0)));
         } else {
             float a[VEC];
-            if (!noload) ld_stream<VEC>(row + x0, a);
-            else {
-#pragma unroll
-                for (int c = 0; c < VEC; ++c) a[c] = 0.0f;
-            }
+            ld_stream<VEC>(row + x0, a);
             if constexpr (cx(q) == 0) {
 #pragma unroll
                 for (int c = 0; c < VEC; ++c) f[q][c] = a[c];
             } else if constexpr (cx(q) > 0) {      // source is x-1: take it from the left lane
                 float left = __shfl_up_sync(FULL, a[VEC - 1], 1);
-                if ((lane == 0 || xv == 0) && !noload) left = __ldg(row + xm);
+                if (lane == 0 || xv == 0) left = __ldg(row + xm);
                 f[q][0] = left;
 #pragma unroll
                 for (int c = 1; c < VEC; ++c) f[q][c] = a[c - 1];
             } else {                               // source is x+1: take it from the right lane
                 float right = __shfl_down_sync(FULL, a[0], 1);
-                if ((lane == 31 || xv == nxv - 1) && !noload) right = __ldg(row + xq);
+                if (lane == 31 || xv == nxv - 1) right = __ldg(row + xq);
 #pragma unroll
                 for (int c = 0; c < VEC - 1; ++c) f[q][c] = a[c + 1];
                 f[q][VEC - 1] = right;
@@ -353,35 +385,27 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const StepArgs P) {
     });
     if (skip) return;
 
-    // halfway bounce-back + open-face inflow for near-wall cells (legacy/lbm_solver.py:609-628)
-    if constexpr (WALLS) {
-        if (any_near) {
-#pragma unroll
-            for (int c = 0; c < VEC; ++c) {
-                if ((fl[c] & LBM_FLAG_NEAR) && !(fl[c] & LBM_FLAG_SOLID)) {
-                    const int x = x0 + c;
-                    static_for<1, Q>([&](auto qq) {
-                        constexpr int q = decltype(qq)::value;
-                        int xs = x - cx(q), ys = y - cy(q), zs = z - cz(q);
-                        const int zs_g = G.z0 + zs;
-                        bool oob = false;
-                        if (cx(q) != 0) { if (xs < 0) { oob |= !G.per_x; xs = G.nx - 1; } else if (xs >= G.nx) { oob |= !G.per_x; xs = 0; } }
-                        if (cy(q) != 0) { if (ys < 0) { oob |= !G.per_y; ys = G.ny - 1; } else if (ys >= G.ny) { oob |= !G.per_y; ys = 0; } }
-                        int zsp = zs + G.zg;
-                        if (cz(q) != 0) {
-                            if (zs_g < 0 || zs_g >= G.nz_global) oob |= !G.per_z;
-                            if (!G.zg) { if (zs < 0) zsp = G.nz - 1; else if (zs >= G.nz) zsp = 0; }
-                        }
-                        if (oob) {
-                            f[q][c] = wq(q);    // stale inflow, SURVEY.md A.2-Q6
-                        } else {
-                            const unsigned nf = __ldg(P.flags + ((long long)zsp * G.ny + ys) * G.nx + xs);
-                            if (nf & LBM_FLAG_SOLID) f[q][c] = __ldg(P.src + (long long)opp(q) * G.vol + own + c);
-                        }
-                    });
-                }
+    // halfway bounce-back + open-face inflow (legacy/lbm_solver.py:609-628) -- boundary list only
+    if constexpr (MODE == MODE_BOUNDARY) {
+        static_for<1, Q>([&](auto qq) {
+            constexpr int q = decltype(qq)::value;
+            int xs = x0 - cx(q), ys = y - cy(q), zs = z - cz(q);
+            const int zs_g = G.z0 + zs;
+            bool oob = false;
+            if (cx(q) != 0) { if (xs < 0) { oob |= !G.per_x; xs = G.nx - 1; } else if (xs >= G.nx) { oob |= !G.per_x; xs = 0; } }
+            if (cy(q) != 0) { if (ys < 0) { oob |= !G.per_y; ys = G.ny - 1; } else if (ys >= G.ny) { oob |= !G.per_y; ys = 0; } }
+            int zsp = zs + G.zg;
+            if (cz(q) != 0) {
+                if (zs_g < 0 || zs_g >= G.nz_global) oob |= !G.per_z;
+                if (!G.zg) { if (zs < 0) zsp = G.nz - 1; else if (zs >= G.nz) zsp = 0; }
             }
-        }
+            if (oob) {
+                f[q][0] = wq(q);    // stale inflow, SURVEY.md A.2-Q6
+            } else {
+                const unsigned nf = __ldg(P.flags + ((long long)zsp * G.ny + ys) * G.nx + xs);
+                if (nf & LBM_FLAG_SOLID) f[q][0] = __ldg(P.src + (long long)opp(q) * G.vol + own);
+            }
+        });
     }
 
     // auxiliary inputs
@@ -418,8 +442,8 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const StepArgs P) {
         a.interior = x >= 1 && x <= G.nx - 2 && y >= 1 && y <= G.ny - 2 && zg_ >= 1 && zg_ <= G.nz_global - 2;
         if constexpr (COMPAT == LBM_COMPAT_REFERENCE) {
             if constexpr (POROUS) { if (P.blockage) a.blockage = __ldg(P.blockage + own + c); }
-            if constexpr (LES) {
-                if (a.interior && (fl[c] & LBM_FLAG_LES) && !(fl[c] & LBM_FLAG_SOLID))
+            if constexpr (LES && COLLIDE) {
+                if (mine[c] && a.interior && (fl[c] & LBM_FLAG_LES))
                     a.nu_sgs = les_fd_nu(P.u_src, own + c, G.nx, G.plane, G.vol, a.phase, P.les_k);
             }
         }
@@ -432,7 +456,7 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const StepArgs P) {
 #pragma unroll
             for (int q = 0; q < Q; ++q) f[q][c] = fc[q];
         } else {
-            // moments only (lbm_macroscopic): reuse the collide routine on a scratch copy
+            // moments only (lbm_macroscopic): the collide routine on a scratch copy, populations untouched
             if constexpr (COMPAT == LBM_COMPAT_REFERENCE) collide_reference<FORCED, false, false>(fc, a, out[c], P);
             else collide_physical<FORCED, false, POROUS>(fc, a, out[c], P, has_phase, has_force);
         }
@@ -440,7 +464,7 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const StepArgs P) {
 
     // write-back
     if constexpr (COLLIDE) {
-        if (!any_solid) {
+        if (all_mine || !WALLS) {
             static_for<0, Q>([&](auto qq) {
                 constexpr int q = decltype(qq)::value;
                 st_stream<VEC>(P.dst + (long long)q * G.vol + own, f[q]);
@@ -448,14 +472,14 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const StepArgs P) {
         } else {
 #pragma unroll
             for (int c = 0; c < VEC; ++c)
-                if (!(fl[c] & LBM_FLAG_SOLID)) {
+                if (mine[c]) {
 #pragma unroll
                     for (int q = 0; q < Q; ++q) P.dst[(long long)q * G.vol + own + c] = f[q][c];
                 }
         }
     }
     if (P.write_macro) {
-        if (!any_solid) {
+        if (all_mine || !WALLS) {
             float r[VEC], a0[VEC], a1[VEC], a2[VEC];
 #pragma unroll
             for (int c = 0; c < VEC; ++c) { r[c] = out[c].rho; a0[c] = out[c].ux; a1[c] = out[c].uy; a2[c] = out[c].uz; }
@@ -466,7 +490,7 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const StepArgs P) {
         } else {
 #pragma unroll
             for (int c = 0; c < VEC; ++c)
-                if (!(fl[c] & LBM_FLAG_SOLID)) {
+                if (mine[c]) {
                     P.rho[own + c] = out[c].rho;
                     P.u_dst[own + c] = out[c].ux; P.u_dst[G.vol + own + c] = out[c].uy; P.u_dst[2 * G.vol + own + c] = out[c].uz;
                 }

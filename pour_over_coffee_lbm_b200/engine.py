@@ -98,6 +98,8 @@ class D3Q19Engine:
         self.comm_stream = None
         self.rank, self.nranks = 0, 1
         self.steps_done = 0
+        if walls:
+            self.pack_flags()          # all-fluid box: NEAR on open faces, work lists for the step kernels
         self.init_equilibrium(1.0, (0.0, 0.0, 0.0))
 
     # ---------------------------------------------------------------------------------------
