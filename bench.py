@@ -200,7 +200,9 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
+    t_host0 = time.perf_counter()
     eng.step(args.steps, write_macro_every=0)
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps
     ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
@@ -240,6 +242,7 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "e2e": e2e,
             "gpu_launches": int(launches),
+            "host_enqueue_ms_per_step": host_enqueue_ms,
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

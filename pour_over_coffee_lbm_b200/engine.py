@@ -260,7 +260,10 @@ class D3Q19Engine:
         uid = (C.c_char * 128).from_buffer_copy(box[0])
         with torch.cuda.device(self.device):
             self._check(self.lib.lbm_attach_nccl(self._ctx, C.cast(uid, C.c_void_p), self.rank, self.nranks), "lbm_attach_nccl")
-            self.comm_stream = torch.cuda.Stream(self.device)
+            # high priority: the NCCL send/recv kernel must get SM slots while the interior kernel (tens of
+            # thousands of queued CTAs on the compute stream) is still being dispatched, otherwise the halo
+            # exchange only starts at the interior kernel's tail and nothing overlaps
+            self.comm_stream = torch.cuda.Stream(self.device, priority=-1)
 
     def halo_exchange(self, with_u: bool = False):
         v = _ptr(self.u) if (with_u and self.u_buf) else None
