@@ -3,6 +3,7 @@
 #include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -11,14 +12,14 @@
 
 namespace lbm {
 using StepKernel = void (*)(const StepArgs);
-#define DECL_LOOKUP(name) StepKernel name(int forced, int les, int porous, int vec, int collide, int boundary, int *block);
+#define DECL_LOOKUP(name) StepKernel name(int forced, int les, int porous, int vec, int collide, int boundary, int hi, int *block);
 DECL_LOOKUP(lookup_fast_g0_fn) DECL_LOOKUP(lookup_fast_g1_fn) DECL_LOOKUP(lookup_fast_g2_fn) DECL_LOOKUP(lookup_fast_g3_fn)
 DECL_LOOKUP(lookup_strict_g0_fn) DECL_LOOKUP(lookup_strict_g1_fn) DECL_LOOKUP(lookup_strict_g2_fn) DECL_LOOKUP(lookup_strict_g3_fn)
 
 cudaError_t launch_init_equilibrium(const Grid &, int, float *, const float *, const float *, float, const float[3], cudaStream_t);
 cudaError_t launch_v60_geometry(const Grid &, uint8_t *, int32_t *, const float[5], cudaStream_t);
 cudaError_t launch_pack_flags(const Grid &, uint8_t *, const uint8_t *, const int32_t *, const int32_t *, cudaStream_t);
-cudaError_t build_work_lists(const Grid &, const uint8_t *, int, int, int **, std::vector<int> &, int **, std::vector<int> &, cudaStream_t);
+cudaError_t build_work_lists(const Grid &, const uint8_t *, int, int, int **, std::vector<int> &, int **, unsigned long long **, std::vector<int> &, cudaStream_t);
 cudaError_t launch_convert_f(const Grid &, bool, const float *, const uint8_t *, float *, cudaStream_t);
 cudaError_t launch_face_bc(const Grid &, float *, const uint8_t *, cudaStream_t, int *);
 cudaError_t launch_pressure_gradient(const Grid &, const float *, const uint8_t *, float *, float, float, cudaStream_t);
@@ -75,6 +76,8 @@ struct lbm_ctx {
     cudaEvent_t ev_boundary = nullptr, ev_comm = nullptr;
     // work lists of the walls path (built by lbm_pack_flags for the flag field it packed)
     int *d_tiles = nullptr, *d_bcells = nullptr;
+    unsigned long long *d_bmasks = nullptr;
+    int list_block = 0;
     std::vector<int> tile_off, bcell_off;      // per owned plane offsets into the lists (nz+1 entries)
     const uint8_t *list_flags = nullptr;
     int list_vec = 0;
@@ -106,9 +109,23 @@ static int make_grid(lbm_ctx *ctx, const lbm_params *p, Grid *g) {
 static int pick_vec(const lbm_ctx *ctx) {
     int vec = ctx->p.vec;
     if (vec == 0) vec = 4;
-    if (vec == 2) vec = 1;
+    if (vec == 2 && !((ctx->p.features & LBM_FEAT_WALLS) && ctx->p.compat == LBM_COMPAT_PHYSICAL)) vec = 1;   // VEC=2: tuning set only
     if (ctx->g.nx % 4 != 0 || ctx->g.nx < 8) vec = 1;
     return vec;
+}
+
+// CTA size of the main kernel: lbm_params.block when it is one of the built sizes, else the default for `vec`
+static int pick_block(const lbm_ctx *ctx, int vec) {
+    const int b = ctx->p.block;
+    if (b == 64 || b == 128 || b == 256) return b;
+    return vec == 1 ? 256 : 128;
+}
+
+static int rebuild_lists(lbm_ctx *ctx, const uint8_t *flags, int vec, int block, cudaStream_t s) {
+    CUDA_OK(ctx, build_work_lists(ctx->g, flags, vec, block, &ctx->d_tiles, ctx->tile_off, &ctx->d_bcells, &ctx->d_bmasks, ctx->bcell_off, s));
+    ctx->launches += 6;
+    ctx->list_flags = flags; ctx->list_vec = vec; ctx->list_block = block;
+    return 0;
 }
 
 extern "C" {
@@ -145,7 +162,7 @@ int lbm_set_params(lbm_ctx *ctx, const lbm_params *p) {
     if (!ctx || !p) return fail(ctx, "null argument");
     Grid g;
     if (make_grid(ctx, p, &g)) return 1;
-    if (g.nx != ctx->g.nx || g.ny != ctx->g.ny || g.nz != ctx->g.nz || g.zg != ctx->g.zg || p->vec != ctx->p.vec) ctx->list_flags = nullptr;
+    if (g.nx != ctx->g.nx || g.ny != ctx->g.ny || g.nz != ctx->g.nz || g.zg != ctx->g.zg || p->vec != ctx->p.vec || p->block != ctx->p.block) ctx->list_flags = nullptr;
     ctx->g = g; ctx->p = *p;
     return 0;
 }
@@ -157,6 +174,7 @@ void lbm_destroy(lbm_ctx *ctx) {
     if (ctx->ev_comm) cudaEventDestroy(ctx->ev_comm);
     if (ctx->d_tiles) cudaFree(ctx->d_tiles);
     if (ctx->d_bcells) cudaFree(ctx->d_bcells);
+    if (ctx->d_bmasks) cudaFree(ctx->d_bmasks);
     delete ctx;
 }
 
@@ -183,11 +201,7 @@ int lbm_pack_flags(lbm_ctx *ctx, uint8_t *flags, const uint8_t *solid, const int
     ctx->launches++;
     // active-tile list for the bulk kernel and the compact list of near-wall cells (synchronises the stream)
     const int vec = pick_vec(ctx);
-    CUDA_OK(ctx, build_work_lists(ctx->g, flags, vec, vec == 1 ? 256 : 128, &ctx->d_tiles, ctx->tile_off, &ctx->d_bcells,
-                                  ctx->bcell_off, (cudaStream_t)stream));
-    ctx->launches += 5;
-    ctx->list_flags = flags; ctx->list_vec = vec;
-    return 0;
+    return rebuild_lists(ctx, flags, vec, pick_block(ctx, vec), (cudaStream_t)stream);
 }
 
 }  // extern "C"
@@ -200,8 +214,9 @@ static StepKernel lookup(const lbm_params &p, int vec, int collide, int boundary
     const int porous = (p.features & LBM_FEAT_POROUS) != 0;
     const int group = p.compat * 2 + walls;
     const bool strict = (p.features & LBM_FEAT_STRICT) != 0;
-#define LBM_PICK(g) (strict ? lookup_strict_g##g##_fn(forced, les, porous, vec, collide, boundary, block) \
-                            : lookup_fast_g##g##_fn(forced, les, porous, vec, collide, boundary, block))
+    static const int hi = getenv("LBM_TUNE_HI_OCC") ? atoi(getenv("LBM_TUNE_HI_OCC")) : 0;     // tuning hook
+#define LBM_PICK(g) (strict ? lookup_strict_g##g##_fn(forced, les, porous, vec, collide, boundary, hi, block) \
+                            : lookup_fast_g##g##_fn(forced, les, porous, vec, collide, boundary, hi, block))
     switch (group) {
         case 0: return LBM_PICK(0);
         case 1: return LBM_PICK(1);
@@ -242,12 +257,13 @@ struct Launcher {
 static int make_launcher(lbm_ctx *ctx, const lbm_params &p, const lbm_fields *f, int vec, int collide, Launcher *L) {
     L->vec = vec;
     L->walls = (p.features & LBM_FEAT_WALLS) != 0;
-    L->main = lookup(p, vec, collide, 0, &L->block);
+    L->block = collide ? pick_block(ctx, vec) : 256;
+    L->main = lookup(p, vec, collide, 0, &L->block);      // may fall back to the default CTA size for this variant
     if (!L->main) return fail(ctx, "no step kernel built for this feature combination");
     if (L->walls) {
         L->boundary = lookup(p, 1, collide, 1, &L->bblock);
         if (!L->boundary) return fail(ctx, "no boundary kernel built for this feature combination");
-        if (ctx->list_flags != f->flags || ctx->list_vec != vec || (int)ctx->tile_off.size() != ctx->g.nz + 1)
+        if (ctx->list_flags != f->flags || ctx->list_vec != vec || ctx->list_block != L->block || (int)ctx->tile_off.size() != ctx->g.nz + 1)
             return fail(ctx, "work lists are stale: call lbm_pack_flags on this flags field (after any geometry or vec change)");
     }
     return 0;
@@ -274,7 +290,7 @@ static int launch_planes(lbm_ctx *ctx, StepArgs &a, const Launcher &L, int z_beg
     }
     const int b0 = ctx->bcell_off[z_begin], b1 = ctx->bcell_off[z_end];
     if (b1 > b0) {
-        a.items = ctx->d_bcells; a.item_begin = b0; a.n_items = b1 - b0;
+        a.items = ctx->d_bcells; a.masks = ctx->d_bmasks; a.item_begin = b0; a.n_items = b1 - b0;
         L.boundary<<<(unsigned)((b1 - b0 + L.bblock - 1) / L.bblock), L.bblock, 0, s>>>(a);
         CUDA_OK(ctx, cudaGetLastError());
         ctx->launches++;
@@ -393,8 +409,7 @@ int lbm_macroscopic(lbm_ctx *ctx, const lbm_fields *f, void *stream) {
         // the moments-only variants exist for VEC = 1; the tile list was built for pick_vec(): rebuild on demand
         const int vec = pick_vec(ctx);
         if ((p.features & LBM_FEAT_WALLS) && vec != 1) {
-            CUDA_OK(ctx, build_work_lists(ctx->g, f->flags, 1, 256, &ctx->d_tiles, ctx->tile_off, &ctx->d_bcells, ctx->bcell_off, (cudaStream_t)stream));
-            ctx->list_vec = 1; ctx->list_flags = f->flags;
+            if (rebuild_lists(ctx, f->flags, 1, 256, (cudaStream_t)stream)) return 1;
         }
         const int rc = make_launcher(ctx, p, f, 1, 0, &L);
         if (rc) return rc;
@@ -405,8 +420,7 @@ int lbm_macroscopic(lbm_ctx *ctx, const lbm_fields *f, void *stream) {
     a.write_macro = 1;
     int rc = launch_planes(ctx, a, L, 0, ctx->g.nz, (cudaStream_t)stream);
     if ((p.features & LBM_FEAT_WALLS) && pick_vec(ctx) != 1) {      // restore the lists of the step kernel
-        CUDA_OK(ctx, build_work_lists(ctx->g, f->flags, pick_vec(ctx), 128, &ctx->d_tiles, ctx->tile_off, &ctx->d_bcells, ctx->bcell_off, (cudaStream_t)stream));
-        ctx->list_vec = pick_vec(ctx);
+        if (rebuild_lists(ctx, f->flags, pick_vec(ctx), pick_block(ctx, pick_vec(ctx)), (cudaStream_t)stream)) return 1;
     }
     return rc;
 }

@@ -299,10 +299,32 @@ __global__ void count_boundary_per_plane_kernel(Grid G, const uint8_t *flags, in
     if (threadIdx.x == 0) plane_count[z] = tot;
 }
 
+// per listed near-wall cell: bit q of the low word = the source cell x - e_q is solid (bounce-back), bit q of the high
+// word = the source lies outside an open face (stale inflow w_q).  Replaces 18 neighbour-flag loads per cell per step.
+__global__ void boundary_mask_kernel(Grid G, const uint8_t *flags, const int *cells, int n, unsigned long long *masks) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int cell = cells[i];
+    const int zp = cell / (int)G.plane, rem = cell - zp * (int)G.plane;
+    const int y = rem / G.nx, x = rem - y * G.nx, z = zp - G.zg;
+    unsigned solid_bits = 0, oob_bits = 0;
+    for (int q = 1; q < Q; ++q) {
+        int xs = x - cx(q), ys = y - cy(q), zs = z - cz(q);
+        bool oob = wrap_or_oob(xs, G.nx, G.per_x) | wrap_or_oob(ys, G.ny, G.per_y);
+        const int zs_g = G.z0 + zs;
+        if (zs_g < 0 || zs_g >= G.nz_global) oob |= !G.per_z;
+        int zsp = zs + G.zg;
+        if (!G.zg) { if (zs < 0) zsp = G.nz - 1; else if (zs >= G.nz) zsp = 0; }
+        if (oob) oob_bits |= 1u << q;
+        else if (flags[((long long)zsp * G.ny + ys) * G.nx + xs] & LBM_FLAG_SOLID) solid_bits |= 1u << q;
+    }
+    masks[i] = (unsigned long long)solid_bits | ((unsigned long long)oob_bits << 32);
+}
+
 // Builds both lists (device arrays allocated here, owned by the caller = lbm_ctx) and their per-plane offsets
 // (host vectors of nz+1 entries).  Synchronises the stream: geometry changes are rare, init-time events.
 cudaError_t build_work_lists(const Grid &G, const uint8_t *flags, int vec, int block, int **d_tiles, std::vector<int> &tile_off,
-                             int **d_bcells, std::vector<int> &bcell_off, cudaStream_t s) {
+                             int **d_bcells, unsigned long long **d_masks, std::vector<int> &bcell_off, cudaStream_t s) {
     cudaError_t e;
     const int nxv = G.nx / vec, per_plane = nxv * G.ny, tpp = (per_plane + block - 1) / block;
     const long long ntiles = (long long)tpp * G.nz;
@@ -321,9 +343,11 @@ cudaError_t build_work_lists(const Grid &G, const uint8_t *flags, int vec, int b
     for (int z = 0; z < G.nz; ++z) { tile_off[z + 1] = tile_off[z] + counts[z]; bcell_off[z + 1] = bcell_off[z] + counts[G.nz + z]; }
     if (*d_tiles) { cudaFree(*d_tiles); *d_tiles = nullptr; }
     if (*d_bcells) { cudaFree(*d_bcells); *d_bcells = nullptr; }
+    if (*d_masks) { cudaFree(*d_masks); *d_masks = nullptr; }
     const int n_t = tile_off[G.nz], n_b = bcell_off[G.nz];
     if ((e = cudaMalloc(d_tiles, sizeof(int) * (size_t)(n_t > 0 ? n_t : 1))) != cudaSuccess) return e;
     if ((e = cudaMalloc(d_bcells, sizeof(int) * (size_t)(n_b > 0 ? n_b : 1))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(d_masks, sizeof(unsigned long long) * (size_t)(n_b > 0 ? n_b : 1))) != cudaSuccess) return e;
     thrust::counting_iterator<int> idx(0);
     // tiles: ids in ascending (z, tile) order -> launch order follows memory order
     cub::DeviceSelect::Flagged(nullptr, tmp_bytes, idx, tile_flag, *d_tiles, d_num, (int)ntiles, s);
@@ -333,7 +357,10 @@ cudaError_t build_work_lists(const Grid &G, const uint8_t *flags, int vec, int b
     if (tmp_bytes > need) need = tmp_bytes;
     if ((e = cudaMalloc(&tmp, need)) != cudaSuccess) return e;
     if (n_t > 0) cub::DeviceSelect::Flagged(tmp, need, idx, tile_flag, *d_tiles, d_num, (int)ntiles, s);
-    if (n_b > 0) cub::DeviceSelect::If(tmp, need, idx, *d_bcells, d_num, (int)G.vol, pred, s);
+    if (n_b > 0) {
+        cub::DeviceSelect::If(tmp, need, idx, *d_bcells, d_num, (int)G.vol, pred, s);
+        boundary_mask_kernel<<<(n_b + 255) / 256, 256, 0, s>>>(G, flags, *d_bcells, n_b, *d_masks);
+    }
     e = cudaStreamSynchronize(s);
     cudaFree(tmp); cudaFree(tile_flag); cudaFree(d_count); cudaFree(d_num);
     if (e != cudaSuccess) return e;

@@ -39,6 +39,7 @@ struct StepArgs {
     int z_begin, z_end;    // owned planes processed by this launch (dense mode)
     const int *items;      // bulk mode: active-tile ids; boundary mode: linear indices of NEAR fluid cells
     int item_begin, n_items;
+    const unsigned long long *masks;   // boundary mode: per listed cell, solid-source bits | out-of-box bits << 32
     int write_macro;
     float tau_water, tau_air, gravity_lu;
     float tau_min, tau_max;

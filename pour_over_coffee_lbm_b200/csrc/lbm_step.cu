@@ -48,9 +48,32 @@ static StepKernel pick_feat(int forced, int les, int porous) {
 #define LBM_LOOKUP LBM_CAT(lookup_fast_g, LBM_GROUP, fn)
 #endif
 
+// Tuning set (physical walls group, every feature on = the V60 config): VEC x BLOCK x occupancy target.
+// hi = 1 caps registers through __launch_bounds__ so that 1024 / 640 / 512 threads per SM stay resident (VEC 1/2/4).
+template <int VEC, int BLOCK, int MINB>
+static StepKernel tuned() {
+    if constexpr (G_WALLS && G_COMPAT == LBM_COMPAT_PHYSICAL)
+        return step_kernel<LBM_STRICT_BUILD, G_COMPAT, MODE_BULK, true, true, true, VEC, BLOCK, true, MINB>;
+    else return nullptr;
+}
+static StepKernel pick_tuned(int vec, int block, int hi) {
+    switch (vec * 1000 + block) {
+        case 1064: return hi ? tuned<1, 64, 16>() : tuned<1, 64, 1>();
+        case 1128: return hi ? tuned<1, 128, 8>() : tuned<1, 128, 1>();
+        case 1256: return hi ? tuned<1, 256, 4>() : tuned<1, 256, 1>();
+        case 2064: return hi ? tuned<2, 64, 10>() : tuned<2, 64, 1>();
+        case 2128: return hi ? tuned<2, 128, 5>() : tuned<2, 128, 1>();
+        case 4064: return hi ? tuned<4, 64, 8>() : tuned<4, 64, 1>();
+        case 4128: return hi ? tuned<4, 128, 4>() : tuned<4, 128, 1>();
+        default: return nullptr;
+    }
+}
+
 // `boundary` = 0: the main kernel (dense when the group has no walls, bulk-over-tiles otherwise);
-// `boundary` = 1: the near-wall list kernel (walls groups only).  Returns nullptr when not built.
-StepKernel LBM_LOOKUP(int forced, int les, int porous, int vec, int collide, int boundary, int *block) {
+// `boundary` = 1: the near-wall list kernel (walls groups only).  *block: in = requested CTA size (0 = default),
+// out = CTA size of the returned kernel.  `hi` = high-occupancy register cap (tuning set only).
+// Returns nullptr when the combination is not built.
+StepKernel LBM_LOOKUP(int forced, int les, int porous, int vec, int collide, int boundary, int hi, int *block) {
     StepKernel k = nullptr;
     constexpr int MAIN = G_WALLS ? MODE_BULK : MODE_DENSE;
     if (boundary) {
@@ -60,13 +83,19 @@ StepKernel LBM_LOOKUP(int forced, int les, int porous, int vec, int collide, int
         *block = 256;
         return k;
     }
+    const int def_block = (vec == 1) ? 256 : 128;
+    if (collide && forced && les && porous && (*block != def_block || hi || vec == 2)) {
+        const int b = *block ? *block : def_block;
+        k = pick_tuned(vec, b, hi);
+        if (k) { *block = b; return k; }
+    }
     if (collide) {
         if (vec == 4) k = pick_feat<MAIN, 4, true>(forced, les, porous);
         else if (vec == 1) k = pick_feat<MAIN, 1, true>(forced, les, porous);
     } else {
         if (vec == 1) k = pick_feat<MAIN, 1, false>(forced, les, porous);
     }
-    *block = (vec == 1) ? 256 : 128;
+    *block = def_block;
     return k;
 }
 

@@ -269,8 +269,8 @@ enum { MODE_DENSE = 0, MODE_BULK = 1, MODE_BOUNDARY = 2 };
 
 // BUILD (0 = fast, 1 = strict/-fmad=false) only makes the two builds distinct symbols: without it the
 // linker would merge the identically-named instantiations of the two translation units (ODR).
-template <int BUILD, int COMPAT, int MODE, bool FORCED, bool LES, bool POROUS, int VEC, int BLOCK, bool COLLIDE = true>
-__global__ void __launch_bounds__(BLOCK) step_kernel(const StepArgs P) {
+template <int BUILD, int COMPAT, int MODE, bool FORCED, bool LES, bool POROUS, int VEC, int BLOCK, bool COLLIDE = true, int MINB = 1>
+__global__ void __launch_bounds__(BLOCK, MINB) step_kernel(const StepArgs P) {
     constexpr bool WALLS = MODE != MODE_DENSE;
     static_assert(MODE != MODE_BOUNDARY || VEC == 1, "the boundary list is processed one cell per thread");
     const Grid &G = P.g;
@@ -318,6 +318,9 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const StepArgs P) {
             const unsigned w = __ldg(reinterpret_cast<const unsigned *>(P.flags + own));
 #pragma unroll
             for (int c = 0; c < 4; ++c) fl[c] = (w >> (8 * c)) & 0xffu;
+        } else if constexpr (VEC == 2) {
+            const unsigned short w = __ldg(reinterpret_cast<const unsigned short *>(P.flags + own));
+            fl[0] = w & 0xffu; fl[1] = (w >> 8) & 0xffu;
         } else {
             fl[0] = __ldg(P.flags + own);
         }
@@ -385,26 +388,18 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const StepArgs P) {
     });
     if (skip) return;
 
-    // halfway bounce-back + open-face inflow (legacy/lbm_solver.py:609-628) -- boundary list only
+    // halfway bounce-back + open-face inflow (legacy/lbm_solver.py:609-628) -- boundary list only.
+    // masks[i]: bit q (1..18) = the source cell x - e_q is solid; bit q+13... see build_work_lists: two words per cell
+    // are packed as (solid bits) | (out-of-box bits << 32) in one 64-bit entry.
     if constexpr (MODE == MODE_BOUNDARY) {
+        int i = blockIdx.x * BLOCK + threadIdx.x;
+        if (i >= P.n_items) i = P.n_items - 1;
+        const unsigned long long m = __ldg(P.masks + P.item_begin + i);
+        const unsigned solid_bits = (unsigned)m, oob_bits = (unsigned)(m >> 32);
         static_for<1, Q>([&](auto qq) {
             constexpr int q = decltype(qq)::value;
-            int xs = x0 - cx(q), ys = y - cy(q), zs = z - cz(q);
-            const int zs_g = G.z0 + zs;
-            bool oob = false;
-            if (cx(q) != 0) { if (xs < 0) { oob |= !G.per_x; xs = G.nx - 1; } else if (xs >= G.nx) { oob |= !G.per_x; xs = 0; } }
-            if (cy(q) != 0) { if (ys < 0) { oob |= !G.per_y; ys = G.ny - 1; } else if (ys >= G.ny) { oob |= !G.per_y; ys = 0; } }
-            int zsp = zs + G.zg;
-            if (cz(q) != 0) {
-                if (zs_g < 0 || zs_g >= G.nz_global) oob |= !G.per_z;
-                if (!G.zg) { if (zs < 0) zsp = G.nz - 1; else if (zs >= G.nz) zsp = 0; }
-            }
-            if (oob) {
-                f[q][0] = wq(q);    // stale inflow, SURVEY.md A.2-Q6
-            } else {
-                const unsigned nf = __ldg(P.flags + ((long long)zsp * G.ny + ys) * G.nx + xs);
-                if (nf & LBM_FLAG_SOLID) f[q][0] = __ldg(P.src + (long long)opp(q) * G.vol + own);
-            }
+            if (oob_bits & (1u << q)) f[q][0] = wq(q);                    // stale inflow, SURVEY.md A.2-Q6
+            else if (solid_bits & (1u << q)) f[q][0] = __ldg(P.src + (long long)opp(q) * G.vol + own);
         });
     }
 

@@ -36,7 +36,7 @@ class D3Q19Engine:
                  config: Optional[LBMConfig] = None, device: int = 0, zghost: int = 0, z0: int = 0,
                  nz_global: Optional[int] = None, tau: Optional[float] = None, tau_air: Optional[float] = None,
                  gravity_lu: Optional[float] = None, cs_smag: Optional[float] = None,
-                 porous_darcy: float = 0.0, porous_forch: float = 0.0, vec: int = 0,
+                 porous_darcy: float = 0.0, porous_forch: float = 0.0, vec: int = 0, block: int = 0,
                  macro_fields: bool = True):
         if not torch.cuda.is_available():
             raise BackendInitializationError(
@@ -72,7 +72,7 @@ class D3Q19Engine:
             gravity_lu=self.cfg.GRAVITY_LU if gravity_lu is None else gravity_lu,
             cs_smag=self.cfg.LES_CS if cs_smag is None else cs_smag, tau_min=0.55, tau_max=1.90,
             porous_darcy=porous_darcy, porous_forch=porous_forch,
-            K_lu=k_lu, beta_lu=beta_lu, c_darcy=c_darcy, c_forch=c_forch, vec=vec, block=0)
+            K_lu=k_lu, beta_lu=beta_lu, c_darcy=c_darcy, c_forch=c_forch, vec=vec, block=block)
         self._ctx = C.c_void_p()
         rc = self.lib.lbm_create(C.byref(self._ctx), device, C.byref(self.params))
         if rc != 0:

@@ -1,0 +1,29 @@
+#!/usr/bin/env python
+"""Tuning sweep of the V60 full-feature step (physical) over VEC x BLOCK x build; run once per LBM_TUNE_HI_OCC value."""
+import argparse, json, os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+from scripts.bench_configs import timed, v60_engine  # noqa: E402
+from pour_over_coffee_lbm_b200.config import LBMConfig  # noqa: E402
+from pour_over_coffee_lbm_b200.engine import D3Q19Engine  # noqa: E402
+
+ap = argparse.ArgumentParser(); ap.add_argument("--n", type=int, default=512); ap.add_argument("--steps", type=int, default=20)
+args = ap.parse_args()
+n = args.n
+hi = os.environ.get("LBM_TUNE_HI_OCC", "0")
+for strict in (True, False):
+    for vec, block in ((1, 64), (1, 128), (1, 256), (2, 64), (2, 128), (4, 64), (4, 128)):
+        cfg = LBMConfig(NX=n, NY=n, NZ=n, GRAVITY_LU=1e-5)
+        eng = D3Q19Engine(n, n, n, compat="physical", periodic=(False, False, False), walls=True, force=True, phase=True, les=True,
+                          porous=True, strict=strict, vec=vec, block=block, config=cfg, gravity_lu=1e-5, porous_darcy=0.37, porous_forch=0.9)
+        eng.build_v60_geometry()
+        z = torch.arange(n, device="cuda")[:, None, None]
+        eng.phase.copy_(((z < int(0.6 * n)) & (eng.solid == 0)).float())
+        g = torch.Generator(device="cuda"); g.manual_seed(1234)
+        eng.init_equilibrium(rho=torch.ones((n, n, n), device="cuda"), u=1e-3 * torch.randn((3, n, n, n), device="cuda", generator=g))
+        ms = timed(lambda: eng.step(1, write_macro_every=0), args.steps, 5)
+        fluid = eng.fluid_cells()
+        print(json.dumps({"hi_occ": hi, "strict": strict, "vec": vec, "block": block, "ms": round(ms, 4),
+                          "MFLUPS": round(fluid / ms / 1e3), "frac": round((fluid * 165 + (n ** 3 - fluid)) / ms / 1e6 / 6540.8, 3)}), flush=True)
+        del eng
+        torch.cuda.empty_cache()
