@@ -12,14 +12,14 @@
 
 namespace lbm {
 using StepKernel = void (*)(const StepArgs);
-#define DECL_LOOKUP(name) StepKernel name(int forced, int les, int porous, int vec, int collide, int boundary, int hi, int *block);
+#define DECL_LOOKUP(name) StepKernel name(int forced, int les, int porous, int vec, int collide, int *block);
 DECL_LOOKUP(lookup_fast_g0_fn) DECL_LOOKUP(lookup_fast_g1_fn) DECL_LOOKUP(lookup_fast_g2_fn) DECL_LOOKUP(lookup_fast_g3_fn)
 DECL_LOOKUP(lookup_strict_g0_fn) DECL_LOOKUP(lookup_strict_g1_fn) DECL_LOOKUP(lookup_strict_g2_fn) DECL_LOOKUP(lookup_strict_g3_fn)
 
 cudaError_t launch_init_equilibrium(const Grid &, int, float *, const float *, const float *, float, const float[3], cudaStream_t);
 cudaError_t launch_v60_geometry(const Grid &, uint8_t *, int32_t *, const float[5], cudaStream_t);
 cudaError_t launch_pack_flags(const Grid &, uint8_t *, const uint8_t *, const int32_t *, const int32_t *, cudaStream_t);
-cudaError_t build_work_lists(const Grid &, const uint8_t *, int, int, int **, std::vector<int> &, int **, unsigned long long **, std::vector<int> &, cudaStream_t);
+cudaError_t build_work_lists(const Grid &, const uint8_t *, int, int, int **, std::vector<int> &, unsigned long long **, cudaStream_t);
 cudaError_t launch_convert_f(const Grid &, bool, const float *, const uint8_t *, float *, cudaStream_t);
 cudaError_t launch_face_bc(const Grid &, float *, const uint8_t *, cudaStream_t, int *);
 cudaError_t launch_pressure_gradient(const Grid &, const float *, const uint8_t *, float *, float, float, cudaStream_t);
@@ -75,10 +75,10 @@ struct lbm_ctx {
     int rank = 0, nranks = 1;
     cudaEvent_t ev_boundary = nullptr, ev_comm = nullptr;
     // work lists of the walls path (built by lbm_pack_flags for the flag field it packed)
-    int *d_tiles = nullptr, *d_bcells = nullptr;
-    unsigned long long *d_bmasks = nullptr;
+    int *d_tiles = nullptr;
+    unsigned long long *d_nbr = nullptr;       // neighbour masks [vol]
     int list_block = 0;
-    std::vector<int> tile_off, bcell_off;      // per owned plane offsets into the lists (nz+1 entries)
+    std::vector<int> tile_off;                 // per owned plane offsets into the tile list (nz+1 entries)
     const uint8_t *list_flags = nullptr;
     int list_vec = 0;
 };
@@ -121,9 +121,11 @@ static int pick_block(const lbm_ctx *ctx, int vec) {
     return vec == 1 ? 256 : 128;
 }
 
+static StepKernel lookup(const lbm_params &p, int vec, int collide, int *block);
+
 static int rebuild_lists(lbm_ctx *ctx, const uint8_t *flags, int vec, int block, cudaStream_t s) {
-    CUDA_OK(ctx, build_work_lists(ctx->g, flags, vec, block, &ctx->d_tiles, ctx->tile_off, &ctx->d_bcells, &ctx->d_bmasks, ctx->bcell_off, s));
-    ctx->launches += 6;
+    CUDA_OK(ctx, build_work_lists(ctx->g, flags, vec, block, &ctx->d_tiles, ctx->tile_off, &ctx->d_nbr, s));
+    ctx->launches += 4;
     ctx->list_flags = flags; ctx->list_vec = vec; ctx->list_block = block;
     return 0;
 }
@@ -162,7 +164,11 @@ int lbm_set_params(lbm_ctx *ctx, const lbm_params *p) {
     if (!ctx || !p) return fail(ctx, "null argument");
     Grid g;
     if (make_grid(ctx, p, &g)) return 1;
-    if (g.nx != ctx->g.nx || g.ny != ctx->g.ny || g.nz != ctx->g.nz || g.zg != ctx->g.zg || p->vec != ctx->p.vec || p->block != ctx->p.block) ctx->list_flags = nullptr;
+    if (g.nx != ctx->g.nx || g.ny != ctx->g.ny || g.nz != ctx->g.nz || g.zg != ctx->g.zg) {
+        if (ctx->d_nbr) { cudaFree(ctx->d_nbr); ctx->d_nbr = nullptr; }
+        ctx->list_flags = nullptr;
+    }
+    if (p->vec != ctx->p.vec || p->block != ctx->p.block) ctx->list_flags = nullptr;
     ctx->g = g; ctx->p = *p;
     return 0;
 }
@@ -173,8 +179,7 @@ void lbm_destroy(lbm_ctx *ctx) {
     if (ctx->ev_boundary) cudaEventDestroy(ctx->ev_boundary);
     if (ctx->ev_comm) cudaEventDestroy(ctx->ev_comm);
     if (ctx->d_tiles) cudaFree(ctx->d_tiles);
-    if (ctx->d_bcells) cudaFree(ctx->d_bcells);
-    if (ctx->d_bmasks) cudaFree(ctx->d_bmasks);
+    if (ctx->d_nbr) cudaFree(ctx->d_nbr);
     delete ctx;
 }
 
@@ -201,22 +206,23 @@ int lbm_pack_flags(lbm_ctx *ctx, uint8_t *flags, const uint8_t *solid, const int
     ctx->launches++;
     // active-tile list for the bulk kernel and the compact list of near-wall cells (synchronises the stream)
     const int vec = pick_vec(ctx);
-    return rebuild_lists(ctx, flags, vec, pick_block(ctx, vec), (cudaStream_t)stream);
+    int block = pick_block(ctx, vec);
+    lookup(ctx->p, vec, 1, &block);                 // the CTA size the step kernel will really use
+    return rebuild_lists(ctx, flags, vec, block, (cudaStream_t)stream);
 }
 
 }  // extern "C"
 
 // ---- step ---------------------------------------------------------------------------------------
-static StepKernel lookup(const lbm_params &p, int vec, int collide, int boundary, int *block) {
+static StepKernel lookup(const lbm_params &p, int vec, int collide, int *block) {
     const int walls = (p.features & LBM_FEAT_WALLS) != 0;
     const int forced = (p.features & (LBM_FEAT_FORCE | LBM_FEAT_PHASE)) != 0;
     const int les = (p.features & LBM_FEAT_LES) != 0;
     const int porous = (p.features & LBM_FEAT_POROUS) != 0;
     const int group = p.compat * 2 + walls;
     const bool strict = (p.features & LBM_FEAT_STRICT) != 0;
-    static const int hi = getenv("LBM_TUNE_HI_OCC") ? atoi(getenv("LBM_TUNE_HI_OCC")) : 0;     // tuning hook
-#define LBM_PICK(g) (strict ? lookup_strict_g##g##_fn(forced, les, porous, vec, collide, boundary, hi, block) \
-                            : lookup_fast_g##g##_fn(forced, les, porous, vec, collide, boundary, hi, block))
+#define LBM_PICK(g) (strict ? lookup_strict_g##g##_fn(forced, les, porous, vec, collide, block) \
+                            : lookup_fast_g##g##_fn(forced, les, porous, vec, collide, block))
     switch (group) {
         case 0: return LBM_PICK(0);
         case 1: return LBM_PICK(1);
@@ -247,10 +253,10 @@ static int fill_args(lbm_ctx *ctx, const lbm_fields *f, StepArgs *a) {
     return 0;
 }
 
-// The kernels of one step: dense grid (periodic, no flags) or bulk-over-active-tiles + near-wall list (walls).
+// The kernel of one step: dense grid (periodic, no flags) or bulk over the active-tile list (walls).
 struct Launcher {
-    StepKernel main = nullptr, boundary = nullptr;
-    int block = 0, bblock = 0, vec = 1;
+    StepKernel main = nullptr;
+    int block = 0, vec = 1;
     bool walls = false;
 };
 
@@ -258,14 +264,11 @@ static int make_launcher(lbm_ctx *ctx, const lbm_params &p, const lbm_fields *f,
     L->vec = vec;
     L->walls = (p.features & LBM_FEAT_WALLS) != 0;
     L->block = collide ? pick_block(ctx, vec) : 256;
-    L->main = lookup(p, vec, collide, 0, &L->block);      // may fall back to the default CTA size for this variant
+    L->main = lookup(p, vec, collide, &L->block);      // may fall back to the default CTA size for this variant
     if (!L->main) return fail(ctx, "no step kernel built for this feature combination");
-    if (L->walls) {
-        L->boundary = lookup(p, 1, collide, 1, &L->bblock);
-        if (!L->boundary) return fail(ctx, "no boundary kernel built for this feature combination");
-        if (ctx->list_flags != f->flags || ctx->list_vec != vec || ctx->list_block != L->block || (int)ctx->tile_off.size() != ctx->g.nz + 1)
-            return fail(ctx, "work lists are stale: call lbm_pack_flags on this flags field (after any geometry or vec change)");
-    }
+    if (L->walls && (ctx->list_flags != f->flags || ctx->list_vec != vec || ctx->list_block != L->block ||
+                     (int)ctx->tile_off.size() != ctx->g.nz + 1 || !ctx->d_nbr))
+        return fail(ctx, "work lists are stale: call lbm_pack_flags on this flags field (after any geometry, vec or block change)");
     return 0;
 }
 
@@ -277,24 +280,14 @@ static int launch_planes(lbm_ctx *ctx, StepArgs &a, const Launcher &L, int z_beg
         const long long per_plane = (long long)(ctx->g.nx / L.vec) * ctx->g.ny;
         dim3 grid((unsigned)((per_plane + L.block - 1) / L.block), (unsigned)(z_end - z_begin));
         L.main<<<grid, L.block, 0, s>>>(a);
-        CUDA_OK(ctx, cudaGetLastError());
-        ctx->launches++;
-        return 0;
-    }
-    const int t0 = ctx->tile_off[z_begin], t1 = ctx->tile_off[z_end];
-    if (t1 > t0) {
-        a.items = ctx->d_tiles; a.item_begin = t0; a.n_items = t1 - t0;
+    } else {
+        const int t0 = ctx->tile_off[z_begin], t1 = ctx->tile_off[z_end];
+        if (t1 <= t0) return 0;
+        a.items = ctx->d_tiles; a.item_begin = t0; a.n_items = t1 - t0; a.nbr = ctx->d_nbr;
         L.main<<<(unsigned)(t1 - t0), L.block, 0, s>>>(a);
-        CUDA_OK(ctx, cudaGetLastError());
-        ctx->launches++;
     }
-    const int b0 = ctx->bcell_off[z_begin], b1 = ctx->bcell_off[z_end];
-    if (b1 > b0) {
-        a.items = ctx->d_bcells; a.masks = ctx->d_bmasks; a.item_begin = b0; a.n_items = b1 - b0;
-        L.boundary<<<(unsigned)((b1 - b0 + L.bblock - 1) / L.bblock), L.bblock, 0, s>>>(a);
-        CUDA_OK(ctx, cudaGetLastError());
-        ctx->launches++;
-    }
+    CUDA_OK(ctx, cudaGetLastError());
+    ctx->launches++;
     return 0;
 }
 
@@ -420,7 +413,9 @@ int lbm_macroscopic(lbm_ctx *ctx, const lbm_fields *f, void *stream) {
     a.write_macro = 1;
     int rc = launch_planes(ctx, a, L, 0, ctx->g.nz, (cudaStream_t)stream);
     if ((p.features & LBM_FEAT_WALLS) && pick_vec(ctx) != 1) {      // restore the lists of the step kernel
-        if (rebuild_lists(ctx, f->flags, pick_vec(ctx), pick_block(ctx, pick_vec(ctx)), (cudaStream_t)stream)) return 1;
+        int block = pick_block(ctx, pick_vec(ctx));
+        lookup(ctx->p, pick_vec(ctx), 1, &block);
+        if (rebuild_lists(ctx, f->flags, pick_vec(ctx), block, (cudaStream_t)stream)) return 1;
     }
     return rc;
 }

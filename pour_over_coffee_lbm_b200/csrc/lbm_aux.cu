@@ -242,10 +242,10 @@ __global__ void add_reaction_kernel(Grid G, const float *reaction, const uint8_t
     }
 }
 
-// ---- work lists for the step kernel ---------------------------------------------------------------
+// ---- work list + neighbour masks for the step kernel ---------------------------------------------
 // active tiles: a tile = BLOCK consecutive threads of the bulk mapping inside one z-plane; it is active when at
-// least one of its cells is bulk fluid (fluid and not NEAR).  boundary cells: fluid and NEAR, owned planes only.
-__global__ void tile_flags_kernel(Grid G, const uint8_t *flags, int vec, int block, int tpp, uint8_t *tile_flag, int *plane_count) {
+// least one of its cells is fluid.
+__global__ void tile_flags_kernel(Grid G, const uint8_t *flags, int vec, int block, int tpp, uint8_t *tile_flag) {
     const int nxv = G.nx / vec;
     const int per_plane = nxv * G.ny;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -253,16 +253,9 @@ __global__ void tile_flags_kernel(Grid G, const uint8_t *flags, int vec, int blo
     if (t >= per_plane) return;
     const int y = t / nxv, x0 = (t - y * nxv) * vec;
     const long long own = ((long long)(z + G.zg) * G.ny + y) * G.nx + x0;
-    bool bulk = false;
-    for (int c = 0; c < vec; ++c) {
-        const unsigned f = flags[own + c];
-        bulk |= !(f & LBM_FLAG_SOLID) && !(f & LBM_FLAG_NEAR);
-    }
-    if (bulk) {
-        const int tile = z * tpp + t / block;
-        (void)plane_count;
-        tile_flag[tile] = 1;
-    }
+    bool fluid = false;
+    for (int c = 0; c < vec; ++c) fluid |= !(flags[own + c] & LBM_FLAG_SOLID);
+    if (fluid) tile_flag[z * tpp + t / block] = 1;
 }
 
 __global__ void count_flagged_per_plane_kernel(const uint8_t *tile_flag, int tpp, int nz, int *plane_count) {
@@ -275,92 +268,62 @@ __global__ void count_flagged_per_plane_kernel(const uint8_t *tile_flag, int tpp
     if (threadIdx.x == 0 && z < nz) plane_count[z] = tot;
 }
 
-struct IsBoundaryCell {
-    const uint8_t *flags; int plane, zg, nz;
-    __device__ __forceinline__ bool operator()(const int &c) const {
-        const int z = c / plane - zg;
-        if (z < 0 || z >= nz) return false;
+// per near-wall fluid cell: bit q of the low word = the source cell x - e_q is solid (bounce-back), bit q of the high
+// word = the source lies outside an open face (stale inflow w_q).  Replaces 18 neighbour-flag loads per cell per step;
+// the array is dense ([vol] u64) but the step kernel reads it only where the NEAR flag is set.
+__global__ void neighbour_mask_kernel(Grid G, const uint8_t *flags, unsigned long long *nbr) {
+    const long long n = G.vol;
+    for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x) {
         const unsigned f = flags[c];
-        return !(f & LBM_FLAG_SOLID) && (f & LBM_FLAG_NEAR);
+        unsigned solid_bits = 0, oob_bits = 0;
+        if ((f & LBM_FLAG_NEAR) && !(f & LBM_FLAG_SOLID)) {
+            const int x = (int)(c % G.nx);
+            const int y = (int)((c / G.nx) % G.ny);
+            const int z = (int)(c / G.plane) - G.zg;
+            for (int q = 1; q < Q; ++q) {
+                int xs = x - cx(q), ys = y - cy(q), zs = z - cz(q);
+                bool oob = wrap_or_oob(xs, G.nx, G.per_x) | wrap_or_oob(ys, G.ny, G.per_y);
+                const int zs_g = G.z0 + zs;
+                if (zs_g < 0 || zs_g >= G.nz_global) oob |= !G.per_z;
+                int zsp = zs + G.zg;
+                if (!G.zg) { if (zs < 0) zsp = G.nz - 1; else if (zs >= G.nz) zsp = 0; }
+                if (oob) oob_bits |= 1u << q;
+                else if (flags[((long long)zsp * G.ny + ys) * G.nx + xs] & LBM_FLAG_SOLID) solid_bits |= 1u << q;
+            }
+        }
+        nbr[c] = (unsigned long long)solid_bits | ((unsigned long long)oob_bits << 32);
     }
-};
-
-__global__ void count_boundary_per_plane_kernel(Grid G, const uint8_t *flags, int *plane_count) {
-    const int z = blockIdx.x;
-    const long long base = (long long)(z + G.zg) * G.plane;
-    int n = 0;
-    for (long long i = threadIdx.x; i < G.plane; i += blockDim.x) {
-        const unsigned f = flags[base + i];
-        n += (!(f & LBM_FLAG_SOLID) && (f & LBM_FLAG_NEAR)) ? 1 : 0;
-    }
-    typedef cub::BlockReduce<int, 256> BR;
-    __shared__ typename BR::TempStorage tmp;
-    const int tot = BR(tmp).Sum(n);
-    if (threadIdx.x == 0) plane_count[z] = tot;
 }
 
-// per listed near-wall cell: bit q of the low word = the source cell x - e_q is solid (bounce-back), bit q of the high
-// word = the source lies outside an open face (stale inflow w_q).  Replaces 18 neighbour-flag loads per cell per step.
-__global__ void boundary_mask_kernel(Grid G, const uint8_t *flags, const int *cells, int n, unsigned long long *masks) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int cell = cells[i];
-    const int zp = cell / (int)G.plane, rem = cell - zp * (int)G.plane;
-    const int y = rem / G.nx, x = rem - y * G.nx, z = zp - G.zg;
-    unsigned solid_bits = 0, oob_bits = 0;
-    for (int q = 1; q < Q; ++q) {
-        int xs = x - cx(q), ys = y - cy(q), zs = z - cz(q);
-        bool oob = wrap_or_oob(xs, G.nx, G.per_x) | wrap_or_oob(ys, G.ny, G.per_y);
-        const int zs_g = G.z0 + zs;
-        if (zs_g < 0 || zs_g >= G.nz_global) oob |= !G.per_z;
-        int zsp = zs + G.zg;
-        if (!G.zg) { if (zs < 0) zsp = G.nz - 1; else if (zs >= G.nz) zsp = 0; }
-        if (oob) oob_bits |= 1u << q;
-        else if (flags[((long long)zsp * G.ny + ys) * G.nx + xs] & LBM_FLAG_SOLID) solid_bits |= 1u << q;
-    }
-    masks[i] = (unsigned long long)solid_bits | ((unsigned long long)oob_bits << 32);
-}
-
-// Builds both lists (device arrays allocated here, owned by the caller = lbm_ctx) and their per-plane offsets
-// (host vectors of nz+1 entries).  Synchronises the stream: geometry changes are rare, init-time events.
+// Builds the active-tile list (device array allocated here, owned by the caller = lbm_ctx), its per-plane offsets
+// (host vector of nz+1 entries) and the neighbour masks.  Synchronises the stream: geometry changes are rare.
 cudaError_t build_work_lists(const Grid &G, const uint8_t *flags, int vec, int block, int **d_tiles, std::vector<int> &tile_off,
-                             int **d_bcells, unsigned long long **d_masks, std::vector<int> &bcell_off, cudaStream_t s) {
+                             unsigned long long **d_nbr, cudaStream_t s) {
     cudaError_t e;
     const int nxv = G.nx / vec, per_plane = nxv * G.ny, tpp = (per_plane + block - 1) / block;
     const long long ntiles = (long long)tpp * G.nz;
     uint8_t *tile_flag = nullptr; int *d_count = nullptr, *d_num = nullptr; void *tmp = nullptr; size_t tmp_bytes = 0;
+    if (!*d_nbr) { if ((e = cudaMalloc(d_nbr, sizeof(unsigned long long) * (size_t)G.vol)) != cudaSuccess) return e; }
+    neighbour_mask_kernel<<<148 * 16, 256, 0, s>>>(G, flags, *d_nbr);
     if ((e = cudaMalloc(&tile_flag, (size_t)ntiles)) != cudaSuccess) return e;
-    if ((e = cudaMalloc(&d_count, sizeof(int) * (size_t)G.nz * 2)) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&d_count, sizeof(int) * (size_t)G.nz)) != cudaSuccess) return e;
     if ((e = cudaMalloc(&d_num, sizeof(int))) != cudaSuccess) return e;
     cudaMemsetAsync(tile_flag, 0, (size_t)ntiles, s);
-    tile_flags_kernel<<<dim3((per_plane + 255) / 256, G.nz), 256, 0, s>>>(G, flags, vec, block, tpp, tile_flag, nullptr);
+    tile_flags_kernel<<<dim3((per_plane + 255) / 256, G.nz), 256, 0, s>>>(G, flags, vec, block, tpp, tile_flag);
     count_flagged_per_plane_kernel<<<G.nz, 256, 0, s>>>(tile_flag, tpp, G.nz, d_count);
-    count_boundary_per_plane_kernel<<<G.nz, 256, 0, s>>>(G, flags, d_count + G.nz);
-    std::vector<int> counts((size_t)G.nz * 2);
+    std::vector<int> counts((size_t)G.nz);
     if ((e = cudaMemcpyAsync(counts.data(), d_count, sizeof(int) * counts.size(), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
     if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
-    tile_off.assign(G.nz + 1, 0); bcell_off.assign(G.nz + 1, 0);
-    for (int z = 0; z < G.nz; ++z) { tile_off[z + 1] = tile_off[z] + counts[z]; bcell_off[z + 1] = bcell_off[z] + counts[G.nz + z]; }
+    tile_off.assign(G.nz + 1, 0);
+    for (int z = 0; z < G.nz; ++z) tile_off[z + 1] = tile_off[z] + counts[z];
     if (*d_tiles) { cudaFree(*d_tiles); *d_tiles = nullptr; }
-    if (*d_bcells) { cudaFree(*d_bcells); *d_bcells = nullptr; }
-    if (*d_masks) { cudaFree(*d_masks); *d_masks = nullptr; }
-    const int n_t = tile_off[G.nz], n_b = bcell_off[G.nz];
+    const int n_t = tile_off[G.nz];
     if ((e = cudaMalloc(d_tiles, sizeof(int) * (size_t)(n_t > 0 ? n_t : 1))) != cudaSuccess) return e;
-    if ((e = cudaMalloc(d_bcells, sizeof(int) * (size_t)(n_b > 0 ? n_b : 1))) != cudaSuccess) return e;
-    if ((e = cudaMalloc(d_masks, sizeof(unsigned long long) * (size_t)(n_b > 0 ? n_b : 1))) != cudaSuccess) return e;
     thrust::counting_iterator<int> idx(0);
-    // tiles: ids in ascending (z, tile) order -> launch order follows memory order
+    // ids in ascending (z, tile) order -> launch order follows memory order
     cub::DeviceSelect::Flagged(nullptr, tmp_bytes, idx, tile_flag, *d_tiles, d_num, (int)ntiles, s);
-    size_t need = tmp_bytes;
-    IsBoundaryCell pred{flags, (int)G.plane, G.zg, G.nz};
-    cub::DeviceSelect::If(nullptr, tmp_bytes, idx, *d_bcells, d_num, (int)G.vol, pred, s);
-    if (tmp_bytes > need) need = tmp_bytes;
-    if ((e = cudaMalloc(&tmp, need)) != cudaSuccess) return e;
-    if (n_t > 0) cub::DeviceSelect::Flagged(tmp, need, idx, tile_flag, *d_tiles, d_num, (int)ntiles, s);
-    if (n_b > 0) {
-        cub::DeviceSelect::If(tmp, need, idx, *d_bcells, d_num, (int)G.vol, pred, s);
-        boundary_mask_kernel<<<(n_b + 255) / 256, 256, 0, s>>>(G, flags, *d_bcells, n_b, *d_masks);
-    }
+    if ((e = cudaMalloc(&tmp, tmp_bytes)) != cudaSuccess) return e;
+    if (n_t > 0) cub::DeviceSelect::Flagged(tmp, tmp_bytes, idx, tile_flag, *d_tiles, d_num, (int)ntiles, s);
     e = cudaStreamSynchronize(s);
     cudaFree(tmp); cudaFree(tile_flag); cudaFree(d_count); cudaFree(d_num);
     if (e != cudaSuccess) return e;

@@ -37,9 +37,9 @@ struct StepArgs {
     const float *force; const float *phase; const float *blockage;
     const uint8_t *flags;
     int z_begin, z_end;    // owned planes processed by this launch (dense mode)
-    const int *items;      // bulk mode: active-tile ids; boundary mode: linear indices of NEAR fluid cells
+    const int *items;      // bulk mode: active-tile ids
     int item_begin, n_items;
-    const unsigned long long *masks;   // boundary mode: per listed cell, solid-source bits | out-of-box bits << 32
+    const unsigned long long *nbr;     // per cell (valid where NEAR): solid-source bits | out-of-box bits << 32
     int write_macro;
     float tau_water, tau_air, gravity_lu;
     float tau_min, tau_max;

@@ -17,12 +17,19 @@ using StepKernel = void (*)(const StepArgs);
 constexpr int G_COMPAT = LBM_GROUP / 2;
 constexpr bool G_WALLS = (LBM_GROUP % 2) != 0;
 
+// Resident-thread target per SM, enforced through __launch_bounds__(BLOCK, MINB): it caps registers at 64 / 96 / 128
+// per thread for VEC = 1 / 2 / 4.  Without the cap ptxas takes 160+ registers for the VEC=4 kernels, only 12 warps stay
+// resident and the headline kernel drops from 0.40 to 0.63 ms (measured); the few bytes of spill this costs the
+// full-feature variants stay in L1.
+template <int VEC, int BLOCK>
+constexpr int min_blocks() { return (VEC == 1 ? 1024 : (VEC == 2 ? 640 : 512)) / BLOCK; }
+
 template <int MODE, bool FORCED, bool LES, bool POROUS, int VEC, bool COLLIDE>
 static StepKernel pick() {
+    constexpr int BLOCK = (VEC == 1 ? 256 : 128);
     if constexpr (POROUS && !G_WALLS) return nullptr;          // the filter zone lives in the flag byte
     else if constexpr (!COLLIDE && (LES || VEC != 1)) return nullptr;
-    else if constexpr (MODE == MODE_BOUNDARY && VEC != 1) return nullptr;
-    else return step_kernel<LBM_STRICT_BUILD, G_COMPAT, MODE, FORCED, LES, POROUS, VEC, (VEC == 1 ? 256 : 128), COLLIDE>;
+    else return step_kernel<LBM_STRICT_BUILD, G_COMPAT, MODE, FORCED, LES, POROUS, VEC, BLOCK, COLLIDE, min_blocks<VEC, BLOCK>()>;
 }
 
 template <int MODE, int VEC, bool COLLIDE>
@@ -48,45 +55,34 @@ static StepKernel pick_feat(int forced, int les, int porous) {
 #define LBM_LOOKUP LBM_CAT(lookup_fast_g, LBM_GROUP, fn)
 #endif
 
-// Tuning set (physical walls group, every feature on = the V60 config): VEC x BLOCK x occupancy target.
-// hi = 1 caps registers through __launch_bounds__ so that 1024 / 640 / 512 threads per SM stay resident (VEC 1/2/4).
-template <int VEC, int BLOCK, int MINB>
+// Tuning set (physical walls group, every feature on = the V60 config): VEC x BLOCK.
+template <int VEC, int BLOCK>
 static StepKernel tuned() {
     if constexpr (G_WALLS && G_COMPAT == LBM_COMPAT_PHYSICAL)
-        return step_kernel<LBM_STRICT_BUILD, G_COMPAT, MODE_BULK, true, true, true, VEC, BLOCK, true, MINB>;
+        return step_kernel<LBM_STRICT_BUILD, G_COMPAT, MODE_BULK, true, true, true, VEC, BLOCK, true, min_blocks<VEC, BLOCK>()>;
     else return nullptr;
 }
-static StepKernel pick_tuned(int vec, int block, int hi) {
+static StepKernel pick_tuned(int vec, int block) {
     switch (vec * 1000 + block) {
-        case 1064: return hi ? tuned<1, 64, 16>() : tuned<1, 64, 1>();
-        case 1128: return hi ? tuned<1, 128, 8>() : tuned<1, 128, 1>();
-        case 1256: return hi ? tuned<1, 256, 4>() : tuned<1, 256, 1>();
-        case 2064: return hi ? tuned<2, 64, 10>() : tuned<2, 64, 1>();
-        case 2128: return hi ? tuned<2, 128, 5>() : tuned<2, 128, 1>();
-        case 4064: return hi ? tuned<4, 64, 8>() : tuned<4, 64, 1>();
-        case 4128: return hi ? tuned<4, 128, 4>() : tuned<4, 128, 1>();
+        case 1064: return tuned<1, 64>();
+        case 1128: return tuned<1, 128>();
+        case 2064: return tuned<2, 64>();
+        case 2128: return tuned<2, 128>();
+        case 4064: return tuned<4, 64>();
         default: return nullptr;
     }
 }
 
-// `boundary` = 0: the main kernel (dense when the group has no walls, bulk-over-tiles otherwise);
-// `boundary` = 1: the near-wall list kernel (walls groups only).  *block: in = requested CTA size (0 = default),
-// out = CTA size of the returned kernel.  `hi` = high-occupancy register cap (tuning set only).
+// The step kernel of this group (dense when the group has no walls, bulk-over-active-tiles otherwise).
+// *block: in = requested CTA size (0 = default), out = CTA size of the returned kernel.
 // Returns nullptr when the combination is not built.
-StepKernel LBM_LOOKUP(int forced, int les, int porous, int vec, int collide, int boundary, int hi, int *block) {
+StepKernel LBM_LOOKUP(int forced, int les, int porous, int vec, int collide, int *block) {
     StepKernel k = nullptr;
     constexpr int MAIN = G_WALLS ? MODE_BULK : MODE_DENSE;
-    if (boundary) {
-        if constexpr (G_WALLS) {
-            k = collide ? pick_feat<MODE_BOUNDARY, 1, true>(forced, les, porous) : pick_feat<MODE_BOUNDARY, 1, false>(forced, les, porous);
-        }
-        *block = 256;
-        return k;
-    }
     const int def_block = (vec == 1) ? 256 : 128;
-    if (collide && forced && les && porous && (*block != def_block || hi || vec == 2)) {
+    if (collide && forced && les && porous && ((*block && *block != def_block) || vec == 2)) {
         const int b = *block ? *block : def_block;
-        k = pick_tuned(vec, b, hi);
+        k = pick_tuned(vec, b);
         if (k) { *block = b; return k; }
     }
     if (collide) {

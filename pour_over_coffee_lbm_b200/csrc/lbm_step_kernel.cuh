@@ -258,21 +258,20 @@ __device__ __forceinline__ float les_fd_nu(const float *__restrict__ u, long lon
 // the kernel
 //
 // MODE selects how threads map to cells:
-//   MODE_DENSE     every cell of planes [z_begin, z_end) -- fully periodic boxes without a flag field.
-//   MODE_BULK      one CTA per entry of the ACTIVE-TILE list (tiles that hold at least one bulk-fluid cell;
-//                  the 65 % solid part of a V60 box is never launched).  Cells flagged NEAR (a solid or
-//                  out-of-box D3Q19 neighbour) are skipped here, so this path carries no bounce-back code.
-//   MODE_BOUNDARY  one thread per entry of the compact list of NEAR fluid cells (VEC = 1): halfway bounce-back
-//                  and open-face inflow, legacy/lbm_solver.py:609-628.  A few percent of the fluid cells.
+//   MODE_DENSE  every cell of planes [z_begin, z_end) -- fully periodic boxes without a flag field.
+//   MODE_BULK   one CTA per entry of the ACTIVE-TILE list (tiles that hold at least one fluid cell; the 65 % solid
+//               part of a V60 box is never launched).  Near-wall cells (flag NEAR) fetch a precomputed 64-bit
+//               neighbour mask and replace only the populations whose source is solid (halfway bounce-back: own
+//               opposite post-collision population) or outside an open face (w_q) -- legacy/lbm_solver.py:609-628.
+//               The coalesced 128-bit loads already brought everything else.
 // ---------------------------------------------------------------------------------------------
-enum { MODE_DENSE = 0, MODE_BULK = 1, MODE_BOUNDARY = 2 };
+enum { MODE_DENSE = 0, MODE_BULK = 1 };
 
 // BUILD (0 = fast, 1 = strict/-fmad=false) only makes the two builds distinct symbols: without it the
 // linker would merge the identically-named instantiations of the two translation units (ODR).
 template <int BUILD, int COMPAT, int MODE, bool FORCED, bool LES, bool POROUS, int VEC, int BLOCK, bool COLLIDE = true, int MINB = 1>
 __global__ void __launch_bounds__(BLOCK, MINB) step_kernel(const StepArgs P) {
     constexpr bool WALLS = MODE != MODE_DENSE;
-    static_assert(MODE != MODE_BOUNDARY || VEC == 1, "the boundary list is processed one cell per thread");
     const Grid &G = P.g;
     const int nxv = G.nx / VEC;
     const int per_plane = nxv * G.ny;
@@ -281,15 +280,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) step_kernel(const StepArgs P) {
 
     bool active;
     int xv, y, z;
-    if constexpr (MODE == MODE_BOUNDARY) {
-        int i = blockIdx.x * BLOCK + threadIdx.x;
-        active = i < P.n_items;
-        if (!active) i = P.n_items - 1;
-        const int cell = __ldg(P.items + P.item_begin + i);
-        const int zp_ = cell / (int)G.plane;
-        const int rem = cell - zp_ * (int)G.plane;
-        y = rem / G.nx; xv = rem - y * G.nx; z = zp_ - G.zg;
-    } else {
+    {
         int t;
         if constexpr (MODE == MODE_BULK) {
             const int tile = __ldg(P.items + P.item_begin + blockIdx.x);
@@ -312,7 +303,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) step_kernel(const StepArgs P) {
     // flag byte: which of this thread's cells does THIS launch update?
     unsigned fl[VEC];
     bool mine[VEC];
-    bool any_mine = false, all_mine = true;
+    bool any_mine = false, all_mine = true, any_near = false;
     if constexpr (WALLS) {
         if constexpr (VEC == 4) {
             const unsigned w = __ldg(reinterpret_cast<const unsigned *>(P.flags + own));
@@ -326,10 +317,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) step_kernel(const StepArgs P) {
         }
 #pragma unroll
         for (int c = 0; c < VEC; ++c) {
-            const bool fluid = !(fl[c] & LBM_FLAG_SOLID);
-            const bool near = (fl[c] & LBM_FLAG_NEAR) != 0;
-            mine[c] = fluid && (MODE == MODE_BOUNDARY ? near : !near);
+            mine[c] = !(fl[c] & LBM_FLAG_SOLID);
             any_mine |= mine[c]; all_mine &= mine[c];
+            any_near |= mine[c] && (fl[c] & LBM_FLAG_NEAR);
         }
     } else {
 #pragma unroll
@@ -388,19 +378,23 @@ __global__ void __launch_bounds__(BLOCK, MINB) step_kernel(const StepArgs P) {
     });
     if (skip) return;
 
-    // halfway bounce-back + open-face inflow (legacy/lbm_solver.py:609-628) -- boundary list only.
-    // masks[i]: bit q (1..18) = the source cell x - e_q is solid; bit q+13... see build_work_lists: two words per cell
-    // are packed as (solid bits) | (out-of-box bits << 32) in one 64-bit entry.
-    if constexpr (MODE == MODE_BOUNDARY) {
-        int i = blockIdx.x * BLOCK + threadIdx.x;
-        if (i >= P.n_items) i = P.n_items - 1;
-        const unsigned long long m = __ldg(P.masks + P.item_begin + i);
-        const unsigned solid_bits = (unsigned)m, oob_bits = (unsigned)(m >> 32);
-        static_for<1, Q>([&](auto qq) {
-            constexpr int q = decltype(qq)::value;
-            if (oob_bits & (1u << q)) f[q][0] = wq(q);                    // stale inflow, SURVEY.md A.2-Q6
-            else if (solid_bits & (1u << q)) f[q][0] = __ldg(P.src + (long long)opp(q) * G.vol + own);
-        });
+    // halfway bounce-back + open-face inflow (legacy/lbm_solver.py:609-628) for near-wall cells: the neighbour mask
+    // (low word: source x - e_q is solid, high word: source outside an open face) says which populations to replace.
+    if constexpr (WALLS) {
+        if (any_near) {
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) {
+                if (mine[c] && (fl[c] & LBM_FLAG_NEAR)) {
+                    const unsigned long long m = __ldg(P.nbr + own + c);
+                    const unsigned solid_bits = (unsigned)m, oob_bits = (unsigned)(m >> 32);
+                    static_for<1, Q>([&](auto qq) {
+                        constexpr int q = decltype(qq)::value;
+                        if (oob_bits & (1u << q)) f[q][c] = wq(q);                    // stale inflow, SURVEY.md A.2-Q6
+                        else if (solid_bits & (1u << q)) f[q][c] = __ldg(P.src + (long long)opp(q) * G.vol + own + c);
+                    });
+                }
+            }
+        }
     }
 
     // auxiliary inputs

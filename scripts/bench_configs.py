@@ -25,10 +25,17 @@ from pour_over_coffee_lbm_b200.config import LBMConfig  # noqa: E402
 from pour_over_coffee_lbm_b200.engine import D3Q19Engine, ParticleState, particles_couple  # noqa: E402
 
 
-def timed(fn, steps, warmup):
-    for _ in range(warmup):
-        fn()
+def timed(fn, steps, warmup, min_seconds=0.4):
+    """ms per call.  Warm up until the GPU has been busy for >= min_seconds (clock ramp from idle takes ~100 ms on
+    B200: a 20 ms window reads 40 % slow), then time enough calls to cover >= min_seconds."""
+    import time
+    t0 = time.perf_counter(); n = 0
+    while n < warmup or time.perf_counter() - t0 < min_seconds:
+        fn(); n += 1
+        if n % 8 == 0: torch.cuda.synchronize()
     torch.cuda.synchronize()
+    per = max(1e-6, (time.perf_counter() - t0) / n)
+    steps = max(steps, int(min_seconds / per) + 1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):

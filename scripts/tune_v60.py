@@ -7,7 +7,7 @@ from scripts.bench_configs import timed, v60_engine  # noqa: E402
 from pour_over_coffee_lbm_b200.config import LBMConfig  # noqa: E402
 from pour_over_coffee_lbm_b200.engine import D3Q19Engine  # noqa: E402
 
-ap = argparse.ArgumentParser(); ap.add_argument("--n", type=int, default=512); ap.add_argument("--steps", type=int, default=20)
+ap = argparse.ArgumentParser(); ap.add_argument("--n", type=int, default=512); ap.add_argument("--steps", type=int, default=20); ap.add_argument("--box", action="store_true", help="all-fluid box with solid faces instead of the V60 mask")
 args = ap.parse_args()
 n = args.n
 hi = os.environ.get("LBM_TUNE_HI_OCC", "0")
@@ -16,7 +16,11 @@ for strict in (True, False):
         cfg = LBMConfig(NX=n, NY=n, NZ=n, GRAVITY_LU=1e-5)
         eng = D3Q19Engine(n, n, n, compat="physical", periodic=(False, False, False), walls=True, force=True, phase=True, les=True,
                           porous=True, strict=strict, vec=vec, block=block, config=cfg, gravity_lu=1e-5, porous_darcy=0.37, porous_forch=0.9)
-        eng.build_v60_geometry()
+        if args.box:
+            eng.solid.zero_(); eng.solid[0] = 1; eng.solid[-1] = 1; eng.solid[:, 0] = 1; eng.solid[:, -1] = 1; eng.solid[:, :, 0] = 1; eng.solid[:, :, -1] = 1
+            eng.filter_zone.zero_(); eng.filter_zone[n // 2] = 1; eng.pack_flags()
+        else:
+            eng.build_v60_geometry()
         z = torch.arange(n, device="cuda")[:, None, None]
         eng.phase.copy_(((z < int(0.6 * n)) & (eng.solid == 0)).float())
         g = torch.Generator(device="cuda"); g.manual_seed(1234)
