@@ -40,6 +40,25 @@ def measured_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
+def box_copy_bandwidth():
+    """STREAM-style copy on THIS box, same recipe as MEASURED_PEAKS.json (b.copy_(a) over 1 Gi bf16 elements, read+write
+    bytes, best of 10, CUDA events).  Reported next to the official peak because the leases of this pool differ."""
+    import torch
+    a = torch.empty(1 << 30, dtype=torch.bfloat16, device="cuda"); b = torch.empty_like(a)
+    a.fill_(1.0)
+    best = 0.0
+    for _ in range(3):
+        b.copy_(a)
+    torch.cuda.synchronize()
+    for _ in range(10):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); b.copy_(a); e1.record(); torch.cuda.synchronize()
+        best = max(best, 2 * a.numel() * 2 / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+    del a, b
+    torch.cuda.empty_cache()
+    return best
+
+
 def profile_traffic():
     """dram bytes per launch of the dominant kernel from the committed ncu capture, or None."""
     try:
@@ -219,6 +238,7 @@ def run_ours(args):
     # ---- end-to-end through the public API with HOST buffers ("e2e") --------------------------
     e2e = run_e2e(args, eng if world == 1 else None, world, rank, local)
 
+    box_gbs = box_copy_bandwidth() if rank == 0 else None
     if rank == 0:
         peak, peak_src = measured_peak()
         achieved = BYTES_PER_CELL * n * n * n / (ms_step * 1e-3) / 1e9          # per GPU, per launch
@@ -238,6 +258,7 @@ def run_ours(args):
                        "macro_writeout": "rho,u materialised on demand, not inside the timed steps"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": profile_traffic(), "peak_source": peak_src,
+                         "copy_gbs_this_box": box_gbs, "frac_of_this_box_copy": achieved / box_gbs if box_gbs else None,
                          "algorithmic_bytes_per_launch": BYTES_PER_CELL * n * n * n},
             "cpu_baseline": cpu,
             "e2e": e2e,

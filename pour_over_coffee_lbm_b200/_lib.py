@@ -11,7 +11,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblbm_b200.so")
+LIB_PATH = os.environ.get("LBM_B200_LIB", os.path.join(_HERE, "liblbm_b200.so"))   # env override: perf bisects only
 CSRC = os.path.join(_HERE, "csrc")
 
 # ---- constants mirrored from include/lbm_b200.h -------------------------------------------

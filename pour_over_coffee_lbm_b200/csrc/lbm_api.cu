@@ -19,7 +19,7 @@ DECL_LOOKUP(lookup_strict_g0_fn) DECL_LOOKUP(lookup_strict_g1_fn) DECL_LOOKUP(lo
 cudaError_t launch_init_equilibrium(const Grid &, int, float *, const float *, const float *, float, const float[3], cudaStream_t);
 cudaError_t launch_v60_geometry(const Grid &, uint8_t *, int32_t *, const float[5], cudaStream_t);
 cudaError_t launch_pack_flags(const Grid &, uint8_t *, const uint8_t *, const int32_t *, const int32_t *, cudaStream_t);
-cudaError_t build_work_lists(const Grid &, const uint8_t *, int, int, int **, std::vector<int> &, unsigned long long **, cudaStream_t);
+cudaError_t build_work_lists(const Grid &, const uint8_t *, int, unsigned **, std::vector<int> &, unsigned long long **, cudaStream_t);
 cudaError_t launch_convert_f(const Grid &, bool, const float *, const uint8_t *, float *, cudaStream_t);
 cudaError_t launch_face_bc(const Grid &, float *, const uint8_t *, cudaStream_t, int *);
 cudaError_t launch_pressure_gradient(const Grid &, const float *, const uint8_t *, float *, float, float, cudaStream_t);
@@ -73,9 +73,12 @@ struct lbm_ctx {
     long long launches = 0;
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
+    int sm_count = 148;
+    size_t max_window = 0;
     cudaEvent_t ev_boundary = nullptr, ev_comm = nullptr;
     // work lists of the walls path (built by lbm_pack_flags for the flag field it packed)
-    int *d_tiles = nullptr;
+    unsigned *d_tiles = nullptr;               // active warp-tiles, packed x_segment | y << 8 | z << 20
+    cudaStream_t window_stream = nullptr; bool window_set = false;
     unsigned long long *d_nbr = nullptr;       // neighbour masks [vol]
     int list_block = 0;
     std::vector<int> tile_off;                 // per owned plane offsets into the tile list (nz+1 entries)
@@ -124,9 +127,9 @@ static int pick_block(const lbm_ctx *ctx, int vec) {
 static StepKernel lookup(const lbm_params &p, int vec, int collide, int *block);
 
 static int rebuild_lists(lbm_ctx *ctx, const uint8_t *flags, int vec, int block, cudaStream_t s) {
-    CUDA_OK(ctx, build_work_lists(ctx->g, flags, vec, block, &ctx->d_tiles, ctx->tile_off, &ctx->d_nbr, s));
-    ctx->launches += 4;
-    ctx->list_flags = flags; ctx->list_vec = vec; ctx->list_block = block;
+    CUDA_OK(ctx, build_work_lists(ctx->g, flags, vec, &ctx->d_tiles, ctx->tile_off, &ctx->d_nbr, s));
+    ctx->launches += 5;
+    ctx->list_flags = flags; ctx->list_vec = vec; ctx->list_block = block; ctx->window_set = false;
     return 0;
 }
 
@@ -151,6 +154,8 @@ int lbm_create(lbm_ctx **out, int device, const lbm_params *p) {
     }
     lbm_ctx *ctx = new lbm_ctx();
     ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->max_window = (size_t)prop.accessPolicyMaxWindowSize;
     if (make_grid(nullptr, p, &ctx->g)) { delete ctx; return 1; }
     ctx->p = *p;
     CUDA_OK(nullptr, cudaSetDevice(device));
@@ -168,7 +173,7 @@ int lbm_set_params(lbm_ctx *ctx, const lbm_params *p) {
         if (ctx->d_nbr) { cudaFree(ctx->d_nbr); ctx->d_nbr = nullptr; }
         ctx->list_flags = nullptr;
     }
-    if (p->vec != ctx->p.vec || p->block != ctx->p.block) ctx->list_flags = nullptr;
+    if (p->vec != ctx->p.vec) ctx->list_flags = nullptr;
     ctx->g = g; ctx->p = *p;
     return 0;
 }
@@ -266,9 +271,8 @@ static int make_launcher(lbm_ctx *ctx, const lbm_params &p, const lbm_fields *f,
     L->block = collide ? pick_block(ctx, vec) : 256;
     L->main = lookup(p, vec, collide, &L->block);      // may fall back to the default CTA size for this variant
     if (!L->main) return fail(ctx, "no step kernel built for this feature combination");
-    if (L->walls && (ctx->list_flags != f->flags || ctx->list_vec != vec || ctx->list_block != L->block ||
-                     (int)ctx->tile_off.size() != ctx->g.nz + 1 || !ctx->d_nbr))
-        return fail(ctx, "work lists are stale: call lbm_pack_flags on this flags field (after any geometry, vec or block change)");
+    if (L->walls && (ctx->list_flags != f->flags || ctx->list_vec != vec || (int)ctx->tile_off.size() != ctx->g.nz + 1 || !ctx->d_nbr))
+        return fail(ctx, "work lists are stale: call lbm_pack_flags on this flags field (after any geometry or vec change)");
     return 0;
 }
 
@@ -284,7 +288,9 @@ static int launch_planes(lbm_ctx *ctx, StepArgs &a, const Launcher &L, int z_beg
         const int t0 = ctx->tile_off[z_begin], t1 = ctx->tile_off[z_end];
         if (t1 <= t0) return 0;
         a.items = ctx->d_tiles; a.item_begin = t0; a.n_items = t1 - t0; a.nbr = ctx->d_nbr;
-        L.main<<<(unsigned)(t1 - t0), L.block, 0, s>>>(a);
+        const int warps_per_cta = L.block / 32;
+        const long long grid = (t1 - t0 + warps_per_cta - 1) / warps_per_cta;
+        L.main<<<(unsigned)grid, L.block, 0, s>>>(a);
     }
     CUDA_OK(ctx, cudaGetLastError());
     ctx->launches++;

@@ -243,29 +243,38 @@ __global__ void add_reaction_kernel(Grid G, const float *reaction, const uint8_t
 }
 
 // ---- work list + neighbour masks for the step kernel ---------------------------------------------
-// active tiles: a tile = BLOCK consecutive threads of the bulk mapping inside one z-plane; it is active when at
-// least one of its cells is fluid.
-__global__ void tile_flags_kernel(Grid G, const uint8_t *flags, int vec, int block, int tpp, uint8_t *tile_flag) {
-    const int nxv = G.nx / vec;
-    const int per_plane = nxv * G.ny;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int z = blockIdx.y;
-    if (t >= per_plane) return;
-    const int y = t / nxv, x0 = (t - y * nxv) * vec;
-    const long long own = ((long long)(z + G.zg) * G.ny + y) * G.nx + x0;
+// warp-tile = 32*vec x-consecutive cells of one row of an owned plane; active when at least one cell is fluid.
+// id = (z*ny + y)*segs + seg, ascending ids follow memory order.
+__global__ void tile_flags_kernel(Grid G, const uint8_t *flags, int vec, int segs, uint8_t *tile_flag) {
+    const long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long n = (long long)G.nz * G.ny * segs;
+    if (id >= n) return;
+    const int seg = (int)(id % segs);
+    const long long row = id / segs;               // z*ny + y
+    const int y = (int)(row % G.ny), z = (int)(row / G.ny);
+    const int xs = seg * 32 * vec, xe = min(G.nx, xs + 32 * vec);
+    const uint8_t *f = flags + ((long long)(z + G.zg) * G.ny + y) * G.nx;
     bool fluid = false;
-    for (int c = 0; c < vec; ++c) fluid |= !(flags[own + c] & LBM_FLAG_SOLID);
-    if (fluid) tile_flag[z * tpp + t / block] = 1;
+    for (int x = xs; x < xe; ++x) fluid |= !(f[x] & LBM_FLAG_SOLID);
+    tile_flag[id] = fluid ? 1 : 0;
 }
 
-__global__ void count_flagged_per_plane_kernel(const uint8_t *tile_flag, int tpp, int nz, int *plane_count) {
+__global__ void count_flagged_per_plane_kernel(const uint8_t *tile_flag, int per_plane, int nz, int *plane_count) {
     const int z = blockIdx.x;
     int n = 0;
-    for (int i = threadIdx.x; i < tpp; i += blockDim.x) n += tile_flag[(long long)z * tpp + i] ? 1 : 0;
+    for (int i = threadIdx.x; i < per_plane; i += blockDim.x) n += tile_flag[(long long)z * per_plane + i] ? 1 : 0;
     typedef cub::BlockReduce<int, 256> BR;
     __shared__ typename BR::TempStorage tmp;
     const int tot = BR(tmp).Sum(n);
     if (threadIdx.x == 0 && z < nz) plane_count[z] = tot;
+}
+
+__global__ void expand_tiles_kernel(const int *ids, int n, int ny, int segs, unsigned *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int id = ids[i];
+    const int seg = id % segs, row = id / segs;
+    out[i] = (unsigned)seg | ((unsigned)(row % ny) << 8) | ((unsigned)(row / ny) << 20);
 }
 
 // per near-wall fluid cell: bit q of the low word = the source cell x - e_q is solid (bounce-back), bit q of the high
@@ -295,22 +304,23 @@ __global__ void neighbour_mask_kernel(Grid G, const uint8_t *flags, unsigned lon
     }
 }
 
-// Builds the active-tile list (device array allocated here, owned by the caller = lbm_ctx), its per-plane offsets
-// (host vector of nz+1 entries) and the neighbour masks.  Synchronises the stream: geometry changes are rare.
-cudaError_t build_work_lists(const Grid &G, const uint8_t *flags, int vec, int block, int **d_tiles, std::vector<int> &tile_off,
+// Builds the active warp-tile list (device array allocated here, owned by the caller = lbm_ctx), its per-plane
+// offsets (host vector of nz+1 entries) and the neighbour masks.  Synchronises the stream: geometry changes are rare.
+cudaError_t build_work_lists(const Grid &G, const uint8_t *flags, int vec, unsigned **d_tiles, std::vector<int> &tile_off,
                              unsigned long long **d_nbr, cudaStream_t s) {
     cudaError_t e;
-    const int nxv = G.nx / vec, per_plane = nxv * G.ny, tpp = (per_plane + block - 1) / block;
-    const long long ntiles = (long long)tpp * G.nz;
-    uint8_t *tile_flag = nullptr; int *d_count = nullptr, *d_num = nullptr; void *tmp = nullptr; size_t tmp_bytes = 0;
+    const int segs = (G.nx + 32 * vec - 1) / (32 * vec);
+    if (segs > 256 || G.ny > 4096 || G.nz > 4096) return cudaErrorInvalidValue;      // packing limits of a list entry
+    const int per_plane = G.ny * segs;
+    const long long ntiles = (long long)per_plane * G.nz;
+    uint8_t *tile_flag = nullptr; int *d_count = nullptr, *d_num = nullptr, *d_ids = nullptr; void *tmp = nullptr; size_t tmp_bytes = 0;
     if (!*d_nbr) { if ((e = cudaMalloc(d_nbr, sizeof(unsigned long long) * (size_t)G.vol)) != cudaSuccess) return e; }
     neighbour_mask_kernel<<<148 * 16, 256, 0, s>>>(G, flags, *d_nbr);
     if ((e = cudaMalloc(&tile_flag, (size_t)ntiles)) != cudaSuccess) return e;
     if ((e = cudaMalloc(&d_count, sizeof(int) * (size_t)G.nz)) != cudaSuccess) return e;
     if ((e = cudaMalloc(&d_num, sizeof(int))) != cudaSuccess) return e;
-    cudaMemsetAsync(tile_flag, 0, (size_t)ntiles, s);
-    tile_flags_kernel<<<dim3((per_plane + 255) / 256, G.nz), 256, 0, s>>>(G, flags, vec, block, tpp, tile_flag);
-    count_flagged_per_plane_kernel<<<G.nz, 256, 0, s>>>(tile_flag, tpp, G.nz, d_count);
+    tile_flags_kernel<<<(unsigned)((ntiles + 255) / 256), 256, 0, s>>>(G, flags, vec, segs, tile_flag);
+    count_flagged_per_plane_kernel<<<G.nz, 256, 0, s>>>(tile_flag, per_plane, G.nz, d_count);
     std::vector<int> counts((size_t)G.nz);
     if ((e = cudaMemcpyAsync(counts.data(), d_count, sizeof(int) * counts.size(), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
     if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
@@ -318,14 +328,17 @@ cudaError_t build_work_lists(const Grid &G, const uint8_t *flags, int vec, int b
     for (int z = 0; z < G.nz; ++z) tile_off[z + 1] = tile_off[z] + counts[z];
     if (*d_tiles) { cudaFree(*d_tiles); *d_tiles = nullptr; }
     const int n_t = tile_off[G.nz];
-    if ((e = cudaMalloc(d_tiles, sizeof(int) * (size_t)(n_t > 0 ? n_t : 1))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(d_tiles, sizeof(unsigned) * (size_t)(n_t > 0 ? n_t : 1))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&d_ids, sizeof(int) * (size_t)(n_t > 0 ? n_t : 1))) != cudaSuccess) return e;
     thrust::counting_iterator<int> idx(0);
-    // ids in ascending (z, tile) order -> launch order follows memory order
-    cub::DeviceSelect::Flagged(nullptr, tmp_bytes, idx, tile_flag, *d_tiles, d_num, (int)ntiles, s);
+    cub::DeviceSelect::Flagged(nullptr, tmp_bytes, idx, tile_flag, d_ids, d_num, (int)ntiles, s);
     if ((e = cudaMalloc(&tmp, tmp_bytes)) != cudaSuccess) return e;
-    if (n_t > 0) cub::DeviceSelect::Flagged(tmp, tmp_bytes, idx, tile_flag, *d_tiles, d_num, (int)ntiles, s);
+    if (n_t > 0) {
+        cub::DeviceSelect::Flagged(tmp, tmp_bytes, idx, tile_flag, d_ids, d_num, (int)ntiles, s);
+        expand_tiles_kernel<<<(n_t + 255) / 256, 256, 0, s>>>(d_ids, n_t, G.ny, segs, *d_tiles);
+    }
     e = cudaStreamSynchronize(s);
-    cudaFree(tmp); cudaFree(tile_flag); cudaFree(d_count); cudaFree(d_num);
+    cudaFree(tmp); cudaFree(tile_flag); cudaFree(d_count); cudaFree(d_num); cudaFree(d_ids);
     if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }

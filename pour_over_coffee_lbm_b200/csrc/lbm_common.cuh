@@ -37,7 +37,7 @@ struct StepArgs {
     const float *force; const float *phase; const float *blockage;
     const uint8_t *flags;
     int z_begin, z_end;    // owned planes processed by this launch (dense mode)
-    const int *items;      // bulk mode: active-tile ids
+    const unsigned *items; // bulk mode: active warp-tiles (32*VEC x-consecutive cells): x_segment | y << 8 | z << 20
     int item_begin, n_items;
     const unsigned long long *nbr;     // per cell (valid where NEAR): solid-source bits | out-of-box bits << 32
     int write_macro;

@@ -49,6 +49,15 @@ template <> __device__ __forceinline__ void st_stream<4>(float *p, const float (
     __stcs(reinterpret_cast<float4 *>(p), make_float4(v[0], v[1], v[2], v[3]));
 }
 
+// Predicated scalar load (never a branch): the two edge lanes of a row segment fetch the x-+1 neighbour that no
+// adjacent lane holds.  Written in PTX because the compiler otherwise turns the 10 conditional loads into divergent
+// regions (+80 issue slots per warp, measured 0.408 -> 0.430 ms on the headline config).
+__device__ __forceinline__ float ldg_if(const float *p, bool pred, float other) {
+    float v = other;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p ld.global.nc.f32 %0, [%1];\n\t}" : "+f"(v) : "l"(p), "r"((int)pred));
+    return v;
+}
+
 struct CellAux {
     float Fx, Fy, Fz;   // body_force at the cell
     float phase;
@@ -259,81 +268,37 @@ __device__ __forceinline__ float les_fd_nu(const float *__restrict__ u, long lon
 //
 // MODE selects how threads map to cells:
 //   MODE_DENSE  every cell of planes [z_begin, z_end) -- fully periodic boxes without a flag field.
-//   MODE_BULK   one CTA per entry of the ACTIVE-TILE list (tiles that hold at least one fluid cell; the 65 % solid
-//               part of a V60 box is never launched).  Near-wall cells (flag NEAR) fetch a precomputed 64-bit
+//   MODE_BULK   one WARP per entry of the active warp-tile list (32*VEC x-consecutive cells of one row holding at
+//               least one fluid cell; the 65 % solid part of a V60 box is never launched).  The population loads
+//               do not depend on the flag byte, so they are issued together with it (a dependent flag -> branch ->
+//               load chain costs a full memory round trip per thread and halves the throughput at 16 warps/SM).
+//               Near-wall cells (flag NEAR) fetch a precomputed 64-bit
 //               neighbour mask and replace only the populations whose source is solid (halfway bounce-back: own
 //               opposite post-collision population) or outside an open face (w_q) -- legacy/lbm_solver.py:609-628.
 //               The coalesced 128-bit loads already brought everything else.
 // ---------------------------------------------------------------------------------------------
 enum { MODE_DENSE = 0, MODE_BULK = 1 };
 
-// BUILD (0 = fast, 1 = strict/-fmad=false) only makes the two builds distinct symbols: without it the
-// linker would merge the identically-named instantiations of the two translation units (ODR).
-template <int BUILD, int COMPAT, int MODE, bool FORCED, bool LES, bool POROUS, int VEC, int BLOCK, bool COLLIDE = true, int MINB = 1>
-__global__ void __launch_bounds__(BLOCK, MINB) step_kernel(const StepArgs P) {
+// The work of one thread: VEC x-consecutive cells starting at (x0, y, z).  No early exit and no branch on the flag
+// byte before the loads (see the comments inside).
+template <int COMPAT, int MODE, bool FORCED, bool LES, bool POROUS, int VEC, bool COLLIDE>
+__device__ __forceinline__ void step_cells(const StepArgs &P, const int x0, const int y, const int z, const bool active,
+                                           const unsigned lane) {
     constexpr bool WALLS = MODE != MODE_DENSE;
     const Grid &G = P.g;
-    const int nxv = G.nx / VEC;
-    const int per_plane = nxv * G.ny;
     constexpr unsigned FULL = 0xffffffffu;
-    const unsigned lane = threadIdx.x & 31u;
-
-    bool active;
-    int xv, y, z;
-    {
-        int t;
-        if constexpr (MODE == MODE_BULK) {
-            const int tile = __ldg(P.items + P.item_begin + blockIdx.x);
-            const int tpp = (per_plane + BLOCK - 1) / BLOCK;
-            z = tile / tpp;
-            t = (tile - z * tpp) * BLOCK + threadIdx.x;
-        } else {
-            t = blockIdx.x * BLOCK + threadIdx.x;
-            z = P.z_begin + blockIdx.y;
-        }
-        active = t < per_plane;
-        if (!active) t = per_plane - 1;
-        y = t / nxv;
-        xv = t - y * nxv;
-    }
-    const int x0 = xv * VEC;
     const int zp = z + G.zg;
     const long long own = ((long long)zp * G.ny + y) * G.nx + x0;
 
-    // flag byte: which of this thread's cells does THIS launch update?
-    unsigned fl[VEC];
-    bool mine[VEC];
-    bool any_mine = false, all_mine = true, any_near = false;
+    // Raw flag word of this thread's cells.  It is only DECODED after every independent load below has been issued:
+    // a flag -> branch -> load chain costs one full memory round trip per thread (measured: 0.42 -> 0.70 ms on an
+    // all-fluid 256^3 box), so nothing may branch on the flags before the population / force / phase loads.
+    unsigned flag_word = 0;
     if constexpr (WALLS) {
-        if constexpr (VEC == 4) {
-            const unsigned w = __ldg(reinterpret_cast<const unsigned *>(P.flags + own));
-#pragma unroll
-            for (int c = 0; c < 4; ++c) fl[c] = (w >> (8 * c)) & 0xffu;
-        } else if constexpr (VEC == 2) {
-            const unsigned short w = __ldg(reinterpret_cast<const unsigned short *>(P.flags + own));
-            fl[0] = w & 0xffu; fl[1] = (w >> 8) & 0xffu;
-        } else {
-            fl[0] = __ldg(P.flags + own);
-        }
-#pragma unroll
-        for (int c = 0; c < VEC; ++c) {
-            mine[c] = !(fl[c] & LBM_FLAG_SOLID);
-            any_mine |= mine[c]; all_mine &= mine[c];
-            any_near |= mine[c] && (fl[c] & LBM_FLAG_NEAR);
-        }
-    } else {
-#pragma unroll
-        for (int c = 0; c < VEC; ++c) { fl[c] = LBM_FLAG_LES; mine[c] = true; }
-        any_mine = true;
+        if constexpr (VEC == 4) flag_word = __ldg(reinterpret_cast<const unsigned *>(P.flags + own));
+        else if constexpr (VEC == 2) flag_word = __ldg(reinterpret_cast<const unsigned short *>(P.flags + own));
+        else flag_word = __ldg(P.flags + own);
     }
-    const bool skip = !active || !any_mine;
-    if constexpr (VEC > 1) {
-        if (__all_sync(FULL, skip)) return;
-    } else {
-        if (skip) return;      // no lane exchange when VEC == 1
-    }
-    // VEC > 1: in a mixed warp every lane loads -- a lane whose own cells are skipped still supplies the x+-1
-    // neighbours of the shifted populations to the adjacent lane, and those come from rows y-+1 / z-+1.
 
     // neighbour rows / columns with periodic wrap (open faces clamp; such cells are NEAR and handled below)
     int ym = y - 1; if (ym < 0) ym = G.per_y ? G.ny - 1 : 0;
@@ -344,10 +309,14 @@ __global__ void __launch_bounds__(BLOCK, MINB) step_kernel(const StepArgs P) {
         zm = z - 1; if (zm < 0) zm = G.per_z ? G.nz - 1 : 0;
         zq = z + 1; if (zq >= G.nz) zq = G.per_z ? 0 : G.nz - 1;
     }
+    const bool edge_lo = lane == 0 || x0 == 0, edge_hi = lane == 31 || x0 == G.nx - VEC;   // no lane holds my x-1 / x+VEC
     int xm = x0 - 1; if (xm < 0) xm = G.per_x ? G.nx - 1 : 0;
     int xq = x0 + VEC; if (xq >= G.nx) xq = G.per_x ? 0 : G.nx - 1;
 
     float f[Q][VEC];
+    // (1) all loads first, straight-line: 19 aligned vector loads + (VEC > 1) the predicated scalar loads of the two
+    //     edge lanes.  Nothing here may branch or consume a loaded value, or the memory-level parallelism collapses.
+    float edge[Q];
     static_for<0, Q>([&](auto qq) {
         constexpr int q = decltype(qq)::value;
         const int rz = cz(q) > 0 ? zm : (cz(q) < 0 ? zq : zp);
@@ -356,48 +325,30 @@ __global__ void __launch_bounds__(BLOCK, MINB) step_kernel(const StepArgs P) {
         if constexpr (VEC == 1) {
             f[q][0] = __ldcs(row + (cx(q) > 0 ? xm : (cx(q) < 0 ? xq : x0)));
         } else {
-            float a[VEC];
-            ld_stream<VEC>(row + x0, a);
-            if constexpr (cx(q) == 0) {
-#pragma unroll
-                for (int c = 0; c < VEC; ++c) f[q][c] = a[c];
-            } else if constexpr (cx(q) > 0) {      // source is x-1: take it from the left lane
-                float left = __shfl_up_sync(FULL, a[VEC - 1], 1);
-                if (lane == 0 || xv == 0) left = __ldg(row + xm);
-                f[q][0] = left;
-#pragma unroll
-                for (int c = 1; c < VEC; ++c) f[q][c] = a[c - 1];
-            } else {                               // source is x+1: take it from the right lane
-                float right = __shfl_down_sync(FULL, a[0], 1);
-                if (lane == 31 || xv == nxv - 1) right = __ldg(row + xq);
-#pragma unroll
-                for (int c = 0; c < VEC - 1; ++c) f[q][c] = a[c + 1];
-                f[q][VEC - 1] = right;
-            }
+            ld_stream<VEC>(row + x0, f[q]);
+            if constexpr (cx(q) > 0) edge[q] = ldg_if(row + xm, edge_lo, 0.0f);
+            if constexpr (cx(q) < 0) edge[q] = ldg_if(row + xq, edge_hi, 0.0f);
         }
     });
-    if (skip) return;
-
-    // halfway bounce-back + open-face inflow (legacy/lbm_solver.py:609-628) for near-wall cells: the neighbour mask
-    // (low word: source x - e_q is solid, high word: source outside an open face) says which populations to replace.
-    if constexpr (WALLS) {
-        if (any_near) {
+    // (2) shift the populations with cx != 0 by one cell: the x-+1 neighbour comes from the adjacent lane
+    if constexpr (VEC > 1) {
+        static_for<0, Q>([&](auto qq) {
+            constexpr int q = decltype(qq)::value;
+            if constexpr (cx(q) > 0) {             // source is x-1: lane-1 holds it in its last element
+                const float t = __shfl_up_sync(FULL, f[q][VEC - 1], 1);
 #pragma unroll
-            for (int c = 0; c < VEC; ++c) {
-                if (mine[c] && (fl[c] & LBM_FLAG_NEAR)) {
-                    const unsigned long long m = __ldg(P.nbr + own + c);
-                    const unsigned solid_bits = (unsigned)m, oob_bits = (unsigned)(m >> 32);
-                    static_for<1, Q>([&](auto qq) {
-                        constexpr int q = decltype(qq)::value;
-                        if (oob_bits & (1u << q)) f[q][c] = wq(q);                    // stale inflow, SURVEY.md A.2-Q6
-                        else if (solid_bits & (1u << q)) f[q][c] = __ldg(P.src + (long long)opp(q) * G.vol + own + c);
-                    });
-                }
+                for (int c = VEC - 1; c > 0; --c) f[q][c] = f[q][c - 1];
+                f[q][0] = edge_lo ? edge[q] : t;
+            } else if constexpr (cx(q) < 0) {      // source is x+1: lane+1 holds it in its first element
+                const float t = __shfl_down_sync(FULL, f[q][0], 1);
+#pragma unroll
+                for (int c = 0; c < VEC - 1; ++c) f[q][c] = f[q][c + 1];
+                f[q][VEC - 1] = edge_hi ? edge[q] : t;
             }
-        }
+        });
     }
 
-    // auxiliary inputs
+    // auxiliary inputs: issued together with the populations (independent of the flags)
     float bf[3][VEC], ph[VEC];
     bool has_force = false, has_phase = false;
     if constexpr (FORCED) {
@@ -416,6 +367,38 @@ __global__ void __launch_bounds__(BLOCK, MINB) step_kernel(const StepArgs P) {
         else {
 #pragma unroll
             for (int c = 0; c < VEC; ++c) ph[c] = 0.0f;
+        }
+    }
+
+    // decode the flags: which of this thread's cells does this launch update?  (no early exit: lanes without fluid
+    // cells run through with their stores predicated off -- an exit here would be hoisted above the loads)
+    unsigned fl[VEC];
+    bool mine[VEC];
+    bool all_mine = true, any_near = false;
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) {
+        fl[c] = WALLS ? ((flag_word >> (8 * c)) & 0xffu) : (unsigned)LBM_FLAG_LES;
+        mine[c] = active && !(fl[c] & LBM_FLAG_SOLID);
+        all_mine &= mine[c];
+        any_near |= mine[c] && (fl[c] & LBM_FLAG_NEAR);
+    }
+
+    // halfway bounce-back + open-face inflow (legacy/lbm_solver.py:609-628) for near-wall cells: the neighbour mask
+    // (low word: source x - e_q is solid, high word: source outside an open face) says which populations to replace.
+    if constexpr (WALLS) {
+        if (any_near) {
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) {
+                if (mine[c] && (fl[c] & LBM_FLAG_NEAR)) {
+                    const unsigned long long m = __ldg(P.nbr + own + c);
+                    const unsigned solid_bits = (unsigned)m, oob_bits = (unsigned)(m >> 32);
+                    static_for<1, Q>([&](auto qq) {
+                        constexpr int q = decltype(qq)::value;
+                        if (oob_bits & (1u << q)) f[q][c] = wq(q);                    // stale inflow, SURVEY.md A.2-Q6
+                        else if (solid_bits & (1u << q)) f[q][c] = __ldg(P.src + (long long)opp(q) * G.vol + own + c);
+                    });
+                }
+            }
         }
     }
 
@@ -453,7 +436,14 @@ __global__ void __launch_bounds__(BLOCK, MINB) step_kernel(const StepArgs P) {
 
     // write-back
     if constexpr (COLLIDE) {
-        if (all_mine || !WALLS) {
+        if constexpr (!WALLS) {
+            if (active) {
+                static_for<0, Q>([&](auto qq) {
+                    constexpr int q = decltype(qq)::value;
+                    st_stream<VEC>(P.dst + (long long)q * G.vol + own, f[q]);
+                });
+            }
+        } else if (all_mine) {
             static_for<0, Q>([&](auto qq) {
                 constexpr int q = decltype(qq)::value;
                 st_stream<VEC>(P.dst + (long long)q * G.vol + own, f[q]);
@@ -468,7 +458,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) step_kernel(const StepArgs P) {
         }
     }
     if (P.write_macro) {
-        if (all_mine || !WALLS) {
+        if (WALLS ? all_mine : active) {
             float r[VEC], a0[VEC], a1[VEC], a2[VEC];
 #pragma unroll
             for (int c = 0; c < VEC; ++c) { r[c] = out[c].rho; a0[c] = out[c].ux; a1[c] = out[c].uy; a2[c] = out[c].uz; }
@@ -484,6 +474,36 @@ __global__ void __launch_bounds__(BLOCK, MINB) step_kernel(const StepArgs P) {
                     P.u_dst[own + c] = out[c].ux; P.u_dst[G.vol + own + c] = out[c].uy; P.u_dst[2 * G.vol + own + c] = out[c].uz;
                 }
         }
+    }
+}
+
+
+// BUILD (0 = fast, 1 = strict/-fmad=false) only makes the two builds distinct symbols: without it the
+// linker would merge the identically-named instantiations of the two translation units (ODR).
+template <int BUILD, int COMPAT, int MODE, bool FORCED, bool LES, bool POROUS, int VEC, int BLOCK, bool COLLIDE = true, int MINB = 1>
+__global__ void __launch_bounds__(BLOCK, MINB) step_kernel(const __grid_constant__ StepArgs P) {
+    const Grid &G = P.g;
+    const unsigned lane = threadIdx.x & 31u;
+    if constexpr (MODE == MODE_BULK) {
+        // one warp per entry of the active warp-tile list; entry = x_segment | y << 8 | z << 20 (4 B, the list is kept
+        // L2-resident through an access-policy window: a DRAM miss here would sit in front of every other load)
+        const int w = (blockIdx.x * BLOCK + threadIdx.x) >> 5;
+        if (w >= P.n_items) return;
+        const unsigned e = __ldg(P.items + P.item_begin + w);
+        int x0 = (int)(e & 0xffu) * (32 * VEC) + (int)lane * VEC;
+        const bool active = x0 < G.nx;
+        if (!active) x0 = G.nx - VEC;                                    // duplicate of the last lane: loads stay in bounds
+        step_cells<COMPAT, MODE, FORCED, LES, POROUS, VEC, COLLIDE>(P, x0, (int)((e >> 8) & 0xfffu), (int)(e >> 20), active, lane);
+    } else {
+        const int nxv = G.nx / VEC;
+        const int per_plane = nxv * G.ny;
+        int t = blockIdx.x * BLOCK + threadIdx.x;
+        const int z = P.z_begin + blockIdx.y;
+        const bool active = t < per_plane;
+        if (!active) t = per_plane - 1;
+        const int y = t / nxv;
+        const int x0 = (t - y * nxv) * VEC;
+        step_cells<COMPAT, MODE, FORCED, LES, POROUS, VEC, COLLIDE>(P, x0, y, z, active, lane);
     }
 }
 
