@@ -111,7 +111,9 @@ static int make_grid(lbm_ctx *ctx, const lbm_params *p, Grid *g) {
 
 static int pick_vec(const lbm_ctx *ctx) {
     int vec = ctx->p.vec;
-    if (vec == 0) vec = 4;
+    // default: 128-bit path for dense periodic boxes (99 % of the copy bandwidth); one cell per thread behind a flag
+    // field (V60 512^3: VEC=1 2.2 ms, VEC=2 2.3 ms, VEC=4 3.6 ms -- partially filled warps at every chord end)
+    if (vec == 0) vec = (ctx->p.features & LBM_FEAT_WALLS) ? 1 : 4;
     if (vec == 2 && !((ctx->p.features & LBM_FEAT_WALLS) && ctx->p.compat == LBM_COMPAT_PHYSICAL)) vec = 1;   // VEC=2: tuning set only
     if (ctx->g.nx % 4 != 0 || ctx->g.nx < 8) vec = 1;
     return vec;
@@ -121,7 +123,7 @@ static int pick_vec(const lbm_ctx *ctx) {
 static int pick_block(const lbm_ctx *ctx, int vec) {
     const int b = ctx->p.block;
     if (b == 64 || b == 128 || b == 256) return b;
-    return vec == 1 ? 256 : 128;
+    return vec == 1 ? ((ctx->p.features & LBM_FEAT_WALLS) ? 64 : 256) : 128;
 }
 
 static StepKernel lookup(const lbm_params &p, int vec, int collide, int *block);
@@ -268,7 +270,7 @@ struct Launcher {
 static int make_launcher(lbm_ctx *ctx, const lbm_params &p, const lbm_fields *f, int vec, int collide, Launcher *L) {
     L->vec = vec;
     L->walls = (p.features & LBM_FEAT_WALLS) != 0;
-    L->block = collide ? pick_block(ctx, vec) : 256;
+    L->block = pick_block(ctx, vec);
     L->main = lookup(p, vec, collide, &L->block);      // may fall back to the default CTA size for this variant
     if (!L->main) return fail(ctx, "no step kernel built for this feature combination");
     if (L->walls && (ctx->list_flags != f->flags || ctx->list_vec != vec || (int)ctx->tile_off.size() != ctx->g.nz + 1 || !ctx->d_nbr))

@@ -24,9 +24,14 @@ constexpr bool G_WALLS = (LBM_GROUP % 2) != 0;
 template <int VEC, int BLOCK>
 constexpr int min_blocks() { return (VEC == 1 ? 1024 : (VEC == 2 ? 640 : 512)) / BLOCK; }
 
+// CTA size: the walls path runs best with small CTAs (near-wall warps take longer; a CTA slot is held until its
+// slowest warp retires -- V60 512^3 sweep: 64 threads 2.17 ms, 128: 2.20, 256: 2.34)
+template <int MODE, int VEC>
+constexpr int default_block() { return VEC == 1 ? (MODE == MODE_BULK ? 64 : 256) : 128; }
+
 template <int MODE, bool FORCED, bool LES, bool POROUS, int VEC, bool COLLIDE>
 static StepKernel pick() {
-    constexpr int BLOCK = (VEC == 1 ? 256 : 128);
+    constexpr int BLOCK = default_block<MODE, VEC>();
     if constexpr (POROUS && !G_WALLS) return nullptr;          // the filter zone lives in the flag byte
     else if constexpr (!COLLIDE && (LES || VEC != 1)) return nullptr;
     else return step_kernel<LBM_STRICT_BUILD, G_COMPAT, MODE, FORCED, LES, POROUS, VEC, BLOCK, COLLIDE, min_blocks<VEC, BLOCK>()>;
@@ -64,7 +69,7 @@ static StepKernel tuned() {
 }
 static StepKernel pick_tuned(int vec, int block) {
     switch (vec * 1000 + block) {
-        case 1064: return tuned<1, 64>();
+        case 1256: return tuned<1, 256>();
         case 1128: return tuned<1, 128>();
         case 2064: return tuned<2, 64>();
         case 2128: return tuned<2, 128>();
@@ -79,7 +84,7 @@ static StepKernel pick_tuned(int vec, int block) {
 StepKernel LBM_LOOKUP(int forced, int les, int porous, int vec, int collide, int *block) {
     StepKernel k = nullptr;
     constexpr int MAIN = G_WALLS ? MODE_BULK : MODE_DENSE;
-    const int def_block = (vec == 1) ? 256 : 128;
+    const int def_block = (vec == 1) ? default_block<MAIN, 1>() : 128;
     if (collide && forced && les && porous && ((*block && *block != def_block) || vec == 2)) {
         const int b = *block ? *block : def_block;
         k = pick_tuned(vec, b);
