@@ -710,26 +710,33 @@ def _pull(g_q, q, solid, g_opp, periodic, w_q):
     return out.astype(F32)
 
 
+# opposite-direction pairs (p, pbar), e_pbar = -e_p: (1,2) (3,4) (5,6) (7,10) (9,8) (11,14) (13,12) (15,18) (17,16)
+PAIR_P = (1, 3, 5, 7, 9, 11, 13, 15, 17)
+PAIR_M = (2, 4, 6, 10, 8, 14, 12, 18, 16)
+
+
 def step_physical(g, p: PhysParams, solid=None, body_force=None, phase=None, filter_zone=None,
                   les_mask=None):
     """One fused pull step on post-collision populations g[q,i,j,k].
     Returns (g_next, rho, u) with rho,u the moments of the streamed (pre-collision) state.
     Standard BGK + Guo forcing (Guo, Zheng, Shi 2002) + local Smagorinsky (Hou et al. 1996)
-    + Guo-Zhao (2002) porous drag; see SURVEY.md A.3 last paragraph."""
+    + Guo-Zhao (2002) porous drag; see SURVEY.md A.3 last paragraph.
+
+    This mode is a NEW capability (the reference has no consistent-lattice / periodic step), so its order of
+    operations is ours to define: everything is evaluated pairwise over opposite directions (p, pbar), which shares
+    e.u, e.F and the even part of equilibrium and forcing between the two members.  The CUDA kernel
+    (csrc/lbm_step_kernel.cuh:collide_physical) follows exactly this order; the strict build is bit-exact."""
     f = [None] * Q
     for q in range(Q):
         f[q] = _pull(g[q], q, solid, g[int(OPP[q])], p.periodic, W[q])
-    rho = np.zeros_like(f[0])
-    for q in range(Q):
-        rho = rho + f[q]
-    mx = np.zeros_like(rho); my = np.zeros_like(rho); mz = np.zeros_like(rho)
-    for q in range(Q):
-        if CX[q]:
-            mx = mx + f[q] * F32(CX[q])
-        if CY[q]:
-            my = my + f[q] * F32(CY[q])
-        if CZ[q]:
-            mz = mz + f[q] * F32(CZ[q])
+    s = [f[PAIR_P[k]] + f[PAIR_M[k]] for k in range(9)]
+    d = [f[PAIR_P[k]] - f[PAIR_M[k]] for k in range(9)]
+    rho = f[0]
+    for k in range(9):
+        rho = rho + s[k]
+    mx = (((d[0] + d[3]) + d[4]) + d[5]) + d[6]
+    my = (((d[1] + d[3]) - d[4]) + d[7]) + d[8]
+    mz = (((d[2] + d[5]) - d[6]) + d[7]) - d[8]
     inv_rho = F32(1.0) / rho
     if p.use_force:
         Fx = body_force[..., 0].astype(F32); Fy = body_force[..., 1].astype(F32)
@@ -748,9 +755,9 @@ def step_physical(g, p: PhysParams, solid=None, body_force=None, phase=None, fil
         c0 = F32(0.5) * (F32(1.0) + F32(0.5) * F32(p.porous_darcy))
         c1 = F32(0.5) * F32(p.porous_forch)
         den = c0 + np.sqrt(c0 * c0 + c1 * vmag)
-        s = np.where(zone, F32(1.0) / den, F32(1.0)).astype(F32)
-        ux = vx * s; uy = vy * s; uz = vz * s
-        umag = vmag * s
+        sc = np.where(zone, F32(1.0) / den, F32(1.0)).astype(F32)
+        ux = vx * sc; uy = vy * sc; uz = vz * sc
+        umag = vmag * sc
         cdrag = np.where(zone, F32(p.porous_darcy) + F32(p.porous_forch) * umag, F32(0.0)).astype(F32)
         dx = -(cdrag * rho) * ux; dy = -(cdrag * rho) * uy; dz = -(cdrag * rho) * uz
         if Fx is None:
@@ -763,50 +770,61 @@ def step_physical(g, p: PhysParams, solid=None, body_force=None, phase=None, fil
         tau0 = np.where(phase > F32(0.5), F32(p.tau_water), F32(p.tau_air)).astype(F32)
     else:
         tau0 = np.full(rho.shape, F32(p.tau_water), F32)
-    feq = [equilibrium_phys(rho, ux, uy, uz, q) for q in range(Q)]
+    u_sq = _dot3(ux, uy, uz, ux, uy, uz)
+    base = F32(1.0) - F32(1.5) * u_sq
+    wr0 = W[0] * rho; wr1 = W[1] * rho; wr2 = W[7] * rho
+    feq = [None] * Q
+    feq[0] = wr0 * base
+    eu = [None] * 9; ns = [None] * 9
+    for k in range(9):
+        pp, pm = PAIR_P[k], PAIR_M[k]
+        eu[k] = _edot(int(CX[pp]), int(CY[pp]), int(CZ[pp]), ux, uy, uz)
+        A = base + (F32(4.5) * eu[k]) * eu[k]
+        B = F32(3.0) * eu[k]
+        wr = wr1 if k < 3 else wr2
+        sA = wr * A; sB = wr * B
+        feq[pp] = sA + sB
+        feq[pm] = sA - sB
+        ns[k] = s[k] - (sA + sA)
     if p.les:
-        pxx = np.zeros_like(rho); pyy = np.zeros_like(rho); pzz = np.zeros_like(rho)
-        pxy = np.zeros_like(rho); pxz = np.zeros_like(rho); pyz = np.zeros_like(rho)
-        for q in range(Q):
-            d = f[q] - feq[q]
-            ex, ey, ez = int(CX[q]), int(CY[q]), int(CZ[q])
-            if ex: pxx = pxx + d
-            if ey: pyy = pyy + d
-            if ez: pzz = pzz + d
-            if ex * ey: pxy = pxy + d * F32(ex * ey)
-            if ex * ez: pxz = pxz + d * F32(ex * ez)
-            if ey * ez: pyz = pyz + d * F32(ey * ez)
+        pxx = (((ns[0] + ns[3]) + ns[4]) + ns[5]) + ns[6]
+        pyy = (((ns[1] + ns[3]) + ns[4]) + ns[7]) + ns[8]
+        pzz = (((ns[2] + ns[5]) + ns[6]) + ns[7]) + ns[8]
+        pxy = ns[3] - ns[4]; pxz = ns[5] - ns[6]; pyz = ns[7] - ns[8]
         qn = np.sqrt(((pxx * pxx + pyy * pyy) + pzz * pzz)
                      + F32(2.0) * ((pxy * pxy + pxz * pxz) + pyz * pyz))
         cs = float(F32(p.cs_smag))      # the C ABI carries Cs as f32
-        k = F32(18.0 * np.sqrt(2.0) * cs * cs)
-        tau = F32(0.5) * (tau0 + np.sqrt(tau0 * tau0 + (k * qn) * inv_rho))
+        kk = F32(18.0 * np.sqrt(2.0) * cs * cs)
+        tau = F32(0.5) * (tau0 + np.sqrt(tau0 * tau0 + (kk * qn) * inv_rho))
         if les_mask is not None:
             tau = np.where(les_mask != 0, tau, tau0)
         tau = np.maximum(F32(p.tau_min), np.minimum(F32(p.tau_max), tau)).astype(F32)
     else:
         tau = tau0
     omega = (F32(1.0) / tau).astype(F32)
-    g_next = np.empty_like(g)
+    out = [f[q] - omega * (f[q] - feq[q]) for q in range(Q)]
     if Fx is not None:
         pref = F32(1.0) - F32(0.5) * omega
-        uF = _dot3(ux, uy, uz, Fx, Fy, Fz)
+        uF3 = F32(3.0) * _dot3(ux, uy, uz, Fx, Fy, Fz)
+        wp0 = W[0] * pref; wp1 = W[1] * pref; wp2 = W[7] * pref
+        out[0] = out[0] - wp0 * uF3
+        for k in range(9):
+            pp, pm = PAIR_P[k], PAIR_M[k]
+            eF = _edot(int(CX[pp]), int(CY[pp]), int(CZ[pp]), Fx, Fy, Fz)
+            C = (F32(9.0) * eu[k]) * eF - uF3
+            T = F32(3.0) * eF
+            wp = wp1 if k < 3 else wp2
+            out[pp] = out[pp] + wp * (C + T)
+            out[pm] = out[pm] + wp * (C - T)
     fluid = (solid == 0) if solid is not None else None
+    g_next = np.empty_like(g)
     for q in range(Q):
-        out = f[q] - omega * (f[q] - feq[q])
-        if Fx is not None:
-            ex, ey, ez = int(CX[q]), int(CY[q]), int(CZ[q])
-            eu = _edot(ex, ey, ez, ux, uy, uz)
-            eF = _edot(ex, ey, ez, Fx, Fy, Fz)
-            out = out + (W[q] * pref) * ((F32(3.0) * (eF - uF)) + (F32(9.0) * eu) * eF)
-        if fluid is not None:
-            out = np.where(fluid, out, g[q])
-        g_next[q] = out
+        g_next[q] = out[q] if fluid is None else np.where(fluid, out[q], g[q])
     if fluid is not None:
         rho = np.where(fluid, rho, F32(0.0)).astype(F32)
         ux = np.where(fluid, ux, F32(0.0)); uy = np.where(fluid, uy, F32(0.0)); uz = np.where(fluid, uz, F32(0.0))
     u = np.stack([ux, uy, uz], axis=-1).astype(F32)
-    return g_next, rho.astype(F32), u
+    return g_next.astype(F32), rho.astype(F32), u
 
 
 # --------------------------------------------------------------------------
