@@ -44,7 +44,8 @@ extern "C" {
 #define LBM_FEAT_PHASE   4    /* phase field read: tau by phase, gravity*phase */
 #define LBM_FEAT_LES     8    /* Smagorinsky eddy viscosity (physical: local Pi^neq; reference: FD on lagged u) */
 #define LBM_FEAT_POROUS  16   /* filter-zone drag (physical: force; reference: post-step u damping) */
-#define LBM_FEAT_STRICT  64   /* use the -fmad=false build: bit-exact against the CPU oracle */
+#define LBM_FEAT_STRICT  64   /* compat=reference: use the -fmad=false build, bit-exact against the CPU oracle
+                                 (compat=physical rounds every operation explicitly: one build, always bit-exact) */
 
 /* flag byte per cell (lbm_fields.flags) */
 #define LBM_FLAG_SOLID   1    /* LBMSolver.solid != 0           legacy/lbm_solver.py:293 */
@@ -119,6 +120,18 @@ int  lbm_pack_flags(lbm_ctx *ctx, uint8_t *flags, const uint8_t *solid, const in
  * comm_stream is used only when a communicator is attached (slab halo exchange). */
 int  lbm_step(lbm_ctx *ctx, lbm_fields *fields, int nsteps, int write_macro_every,
               void *compute_stream, void *comm_stream);
+/* compat = physical behind walls implements halfway bounce-back (legacy/lbm_solver.py:609-628) on the WRITE side:
+ * a fluid cell next to a solid cell also stores its post-collision f_q into the solid cell's slot g[opp q][x+e_q],
+ * where the next step's pull finds it, so solid-cell slots of g are scratch in that mode.  The library rebuilds the
+ * slots itself after lbm_init_equilibrium / lbm_import_f / lbm_pack_flags / lbm_halo_exchange; a caller that writes
+ * the population buffers directly (cudaMemcpy, torch ops) announces it here before the next lbm_step. */
+int  lbm_populations_changed(lbm_ctx *ctx);
+/* Self-test of the step kernel's packed (two cells per instruction, f32x2) arithmetic against the scalar IEEE
+ * operations.  mismatches[0], [1]: correctly rounded reciprocal / square root over all 2^32 f32 bit patterns;
+ * [2..5]: packed add, sub, mul, fma on pseudo-random operands (register, broadcast and literal operand forms);
+ * [6]: cells whose packed collision result differs from the scalar operator's.  All must be 0.
+ * Synchronises the stream. */
+int  lbm_selftest_math(lbm_ctx *ctx, unsigned long long mismatches[7], void *stream);
 /* LBMSolver._compute_macroscopic_quantities legacy/lbm_solver.py:488-535 on the current state
  * (streams g on the fly, writes rho and u_dst; no collision). */
 int  lbm_macroscopic(lbm_ctx *ctx, const lbm_fields *fields, void *stream);

@@ -17,9 +17,12 @@ this module.  The product path (pour_over_coffee_lbm_b200) never does.
 
 Conventions
 -----------
-* All arithmetic is IEEE f32 with the reference's left-to-right evaluation
-  order and NO fused multiply-add (NumPy never contracts).  The CUDA "strict"
-  build (-fmad=false) follows the same order, so parity is bit-exact there.
+* compat = reference: all arithmetic is IEEE f32 with the reference's
+  left-to-right evaluation order and NO fused multiply-add (NumPy never
+  contracts).  The CUDA "strict" build (-fmad=false) follows the same order, so
+  parity is bit-exact there.
+* compat = physical: an explicit operation-by-operation contract that includes
+  fused multiply-adds (`_fma`, exact C99 fmaf); see step_physical.
 * Arrays use the reference's logical index order: f[q, i, j, k], u[i, j, k, c]
   (x=i, y=j, z=k; Taichi dense layout, k fastest).
 * Two modes:
@@ -714,6 +717,31 @@ def _pull(g_q, q, solid, g_opp, periodic, w_q):
 PAIR_P = (1, 3, 5, 7, 9, 11, 13, 15, 17)
 PAIR_M = (2, 4, 6, 10, 8, 14, 12, 18, 16)
 
+# f32 lattice constants of the physical operator (csrc/lbm_phys.cuh:phys_const): f32 products of the f32 weights
+W1X2 = F32(2.0) * W[1]; W2X2 = F32(2.0) * W[7]
+W1X6 = F32(6.0) * W[1]; W2X6 = F32(6.0) * W[7]
+W1X18 = F32(18.0) * W[1]; W2X18 = F32(18.0) * W[7]
+
+
+def _fma(a, b, c):
+    """round(a*b + c) with ONE rounding (C99 fmaf through oracle/ref_cpu.c; NumPy has no fused operation)."""
+    from . import ref_cpu
+    return ref_cpu.fmaf(a, b, c)
+
+
+def _vedot(ex: int, ey: int, ez: int, vx, vy, vz):
+    """e . v for the + member of a pair: x, y, z order, one rounding per add/sub (lbm_phys.cuh:vedot)."""
+    acc = None
+    for e, v in ((ex, vx), (ey, vy), (ez, vz)):
+        if e == 0:
+            continue
+        if acc is None:
+            assert e > 0
+            acc = v
+        else:
+            acc = (acc + v) if e > 0 else (acc - v)
+    return acc
+
 
 def step_physical(g, p: PhysParams, solid=None, body_force=None, phase=None, filter_zone=None,
                   les_mask=None):
@@ -722,10 +750,14 @@ def step_physical(g, p: PhysParams, solid=None, body_force=None, phase=None, fil
     Standard BGK + Guo forcing (Guo, Zheng, Shi 2002) + local Smagorinsky (Hou et al. 1996)
     + Guo-Zhao (2002) porous drag; see SURVEY.md A.3 last paragraph.
 
-    This mode is a NEW capability (the reference has no consistent-lattice / periodic step), so its order of
-    operations is ours to define: everything is evaluated pairwise over opposite directions (p, pbar), which shares
-    e.u, e.F and the even part of equilibrium and forcing between the two members.  The CUDA kernel
-    (csrc/lbm_step_kernel.cuh:collide_physical) follows exactly this order; the strict build is bit-exact."""
+    This mode is a NEW capability (the reference has no consistent-lattice / periodic step), so its arithmetic is
+    ours to define.  The contract, shared operation by operation with csrc/lbm_phys.cuh:collide_phys: every step is
+    an explicit IEEE f32 add / sub / mul / fused multiply-add (`_fma`), a correctly rounded reciprocal (1/x) or a
+    correctly rounded square root.  The operator works on the pair sums s_k = f_p + f_m and differences
+    d_k = f_p - f_m of opposite directions, and the Smagorinsky stress is the second moment of f minus its
+    equilibrium value rho (I/3 + u u).  The CUDA kernels are bit-exact against this function.
+    g_next is defined on fluid cells; solid cells keep g (on the device their slots are bounce-back scratch)."""
+    one = F32(1.0); half = F32(0.5)
     f = [None] * Q
     for q in range(Q):
         f[q] = _pull(g[q], q, solid, g[int(OPP[q])], p.periodic, W[q])
@@ -737,85 +769,108 @@ def step_physical(g, p: PhysParams, solid=None, body_force=None, phase=None, fil
     mx = (((d[0] + d[3]) + d[4]) + d[5]) + d[6]
     my = (((d[1] + d[3]) - d[4]) + d[7]) + d[8]
     mz = (((d[2] + d[5]) - d[6]) + d[7]) - d[8]
-    inv_rho = F32(1.0) / rho
-    if p.use_force:
-        Fx = body_force[..., 0].astype(F32); Fy = body_force[..., 1].astype(F32)
-        Fz = body_force[..., 2].astype(F32)
-        if phase is not None and p.gravity_lu != 0.0:
-            Fz = Fz - F32(p.gravity_lu) * phase
-        vx = (mx + F32(0.5) * Fx) * inv_rho
-        vy = (my + F32(0.5) * Fy) * inv_rho
-        vz = (mz + F32(0.5) * Fz) * inv_rho
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        inv_rho = (one / rho).astype(F32)
+    zero = np.zeros(rho.shape, F32)
+    forced = False
+    Fx, Fy, Fz = zero, zero, zero
+    has_phase = phase is not None and p.use_phase
+    has_force = (p.use_force and body_force is not None) or (has_phase and p.gravity_lu != 0.0)
+    if has_force:
+        forced = True
+        if p.use_force and body_force is not None:
+            Fx = body_force[..., 0].astype(F32); Fy = body_force[..., 1].astype(F32); Fz = body_force[..., 2].astype(F32)
+        if has_phase and p.gravity_lu != 0.0:
+            Fz = _fma(-F32(p.gravity_lu), phase.astype(F32), Fz)
+        ux = _fma(half, Fx, mx) * inv_rho
+        uy = _fma(half, Fy, my) * inv_rho
+        uz = _fma(half, Fz, mz) * inv_rho
     else:
-        Fx = Fy = Fz = None
-        vx = mx * inv_rho; vy = my * inv_rho; vz = mz * inv_rho
+        ux = mx * inv_rho; uy = my * inv_rho; uz = mz * inv_rho
     if p.porous:
         zone = (filter_zone != 0)
-        vmag = np.sqrt(_dot3(vx, vy, vz, vx, vy, vz))
-        c0 = F32(0.5) * (F32(1.0) + F32(0.5) * F32(p.porous_darcy))
-        c1 = F32(0.5) * F32(p.porous_forch)
-        den = c0 + np.sqrt(c0 * c0 + c1 * vmag)
-        sc = np.where(zone, F32(1.0) / den, F32(1.0)).astype(F32)
-        ux = vx * sc; uy = vy * sc; uz = vz * sc
-        umag = vmag * sc
-        cdrag = np.where(zone, F32(p.porous_darcy) + F32(p.porous_forch) * umag, F32(0.0)).astype(F32)
-        dx = -(cdrag * rho) * ux; dy = -(cdrag * rho) * uy; dz = -(cdrag * rho) * uz
-        if Fx is None:
-            Fx, Fy, Fz = dx, dy, dz
-        else:
-            Fx = Fx + dx; Fy = Fy + dy; Fz = Fz + dz
-    else:
-        ux, uy, uz = vx, vy, vz
-    if p.use_phase and phase is not None:
-        tau0 = np.where(phase > F32(0.5), F32(p.tau_water), F32(p.tau_air)).astype(F32)
+        darcy = F32(p.porous_darcy); forch = F32(p.porous_forch)
+        with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+            vmag = np.sqrt(_fma(uz, uz, _fma(uy, uy, ux * ux)))
+            c0 = half * _fma(half, darcy, one)
+            c1 = half * forch
+            den = c0 + np.sqrt(_fma(c1, vmag, c0 * c0))
+            sc = (one / den).astype(F32)
+            vx = ux * sc; vy = uy * sc; vz = uz * sc
+            umag = vmag * sc
+            cdrag = _fma(forch, umag, darcy)
+            cr = -(cdrag * rho)
+            ddx = _fma(cr, vx, Fx); ddy = _fma(cr, vy, Fy); ddz = _fma(cr, vz, Fz)
+        ux = np.where(zone, vx, ux).astype(F32); uy = np.where(zone, vy, uy).astype(F32); uz = np.where(zone, vz, uz).astype(F32)
+        Fx = np.where(zone, ddx, Fx).astype(F32)
+        Fy = np.where(zone, ddy, Fy).astype(F32)
+        Fz = np.where(zone, ddz, Fz).astype(F32)
+        forced = True
+    if has_phase:
+        tau0 = np.where(phase > half, F32(p.tau_water), F32(p.tau_air)).astype(F32)
     else:
         tau0 = np.full(rho.shape, F32(p.tau_water), F32)
-    u_sq = _dot3(ux, uy, uz, ux, uy, uz)
-    base = F32(1.0) - F32(1.5) * u_sq
-    wr0 = W[0] * rho; wr1 = W[1] * rho; wr2 = W[7] * rho
-    feq = [None] * Q
-    feq[0] = wr0 * base
-    eu = [None] * 9; ns = [None] * 9
-    for k in range(9):
-        pp, pm = PAIR_P[k], PAIR_M[k]
-        eu[k] = _edot(int(CX[pp]), int(CY[pp]), int(CZ[pp]), ux, uy, uz)
-        A = base + (F32(4.5) * eu[k]) * eu[k]
-        B = F32(3.0) * eu[k]
-        wr = wr1 if k < 3 else wr2
-        sA = wr * A; sB = wr * B
-        feq[pp] = sA + sB
-        feq[pm] = sA - sB
-        ns[k] = s[k] - (sA + sA)
+    tau = tau0
     if p.les:
-        pxx = (((ns[0] + ns[3]) + ns[4]) + ns[5]) + ns[6]
-        pyy = (((ns[1] + ns[3]) + ns[4]) + ns[7]) + ns[8]
-        pzz = (((ns[2] + ns[5]) + ns[6]) + ns[7]) + ns[8]
-        pxy = ns[3] - ns[4]; pxz = ns[5] - ns[6]; pyz = ns[7] - ns[8]
-        qn = np.sqrt(((pxx * pxx + pyy * pyy) + pzz * pzz)
-                     + F32(2.0) * ((pxy * pxy + pxz * pxz) + pyz * pyz))
+        Mxx = (((s[0] + s[3]) + s[4]) + s[5]) + s[6]
+        Myy = (((s[1] + s[3]) + s[4]) + s[7]) + s[8]
+        Mzz = (((s[2] + s[5]) + s[6]) + s[7]) + s[8]
+        Mxy = s[3] - s[4]; Mxz = s[5] - s[6]; Myz = s[7] - s[8]
+        nr = F32(-1.0) * rho
+        nrux = nr * ux; nruy = nr * uy
+        third = W[0]
+        pxx = _fma(nr, _fma(ux, ux, third), Mxx)
+        pyy = _fma(nr, _fma(uy, uy, third), Myy)
+        pzz = _fma(nr, _fma(uz, uz, third), Mzz)
+        pxy = _fma(nrux, uy, Mxy); pxz = _fma(nrux, uz, Mxz); pyz = _fma(nruy, uz, Myz)
+        qa = _fma(pzz, pzz, _fma(pyy, pyy, pxx * pxx))
+        qb = _fma(pyz, pyz, _fma(pxz, pxz, pxy * pxy))
+        qsum = _fma(F32(2.0), qb, qa)
         cs = float(F32(p.cs_smag))      # the C ABI carries Cs as f32
         kk = F32(18.0 * np.sqrt(2.0) * cs * cs)
-        tau = F32(0.5) * (tau0 + np.sqrt(tau0 * tau0 + (kk * qn) * inv_rho))
+        with np.errstate(invalid="ignore"):
+            qn = np.sqrt(qsum)
+            arg = _fma(kk * qn, inv_rho, tau0 * tau0)
+            tles = half * (tau0 + np.sqrt(arg))
         if les_mask is not None:
-            tau = np.where(les_mask != 0, tau, tau0)
-        tau = np.maximum(F32(p.tau_min), np.minimum(F32(p.tau_max), tau)).astype(F32)
-    else:
-        tau = tau0
-    omega = (F32(1.0) / tau).astype(F32)
-    out = [f[q] - omega * (f[q] - feq[q]) for q in range(Q)]
-    if Fx is not None:
-        pref = F32(1.0) - F32(0.5) * omega
-        uF3 = F32(3.0) * _dot3(ux, uy, uz, Fx, Fy, Fz)
-        wp0 = W[0] * pref; wp1 = W[1] * pref; wp2 = W[7] * pref
-        out[0] = out[0] - wp0 * uF3
-        for k in range(9):
-            pp, pm = PAIR_P[k], PAIR_M[k]
-            eF = _edot(int(CX[pp]), int(CY[pp]), int(CZ[pp]), Fx, Fy, Fz)
-            C = (F32(9.0) * eu[k]) * eF - uF3
-            T = F32(3.0) * eF
-            wp = wp1 if k < 3 else wp2
-            out[pp] = out[pp] + wp * (C + T)
-            out[pm] = out[pm] + wp * (C - T)
+            tles = np.where(les_mask != 0, tles, tau0)
+        tau = np.maximum(F32(p.tau_min), np.minimum(F32(p.tau_max), tles)).astype(F32)
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        omega = (one / tau).astype(F32)
+    nom = F32(-1.0) * omega
+    u_sq = _fma(uz, uz, _fma(uy, uy, ux * ux))
+    base = _fma(F32(-1.5), u_sq, one)
+    # "f - w rho (...)" is ONE fma with the negated prefactor: no product feeds an add / sub (lbm_phys.cuh header)
+    nws1 = (-W1X2) * rho; nws2 = (-W2X2) * rho
+    nwd1 = (-W1X6) * rho; nwd2 = (-W2X6) * rho
+    out = [None] * Q
+    f0 = _fma(nom, _fma((-W[0]) * rho, base, f[0]), f[0])
+    if forced:
+        pref = _fma(F32(-0.5), omega, one)
+        uF3 = F32(3.0) * _fma(uz, Fz, _fma(uy, Fy, ux * Fx))
+        f0 = _fma((-W[0]) * pref, uF3, f0)
+        c18 = (W1X18 * pref, W2X18 * pref)
+        c6 = (W1X6 * pref, W2X6 * pref)
+        nc2 = ((-W1X2) * pref, (-W2X2) * pref)
+    out[0] = f0
+    for k in range(9):
+        pp, pm = PAIR_P[k], PAIR_M[k]
+        e = (int(CX[pp]), int(CY[pp]), int(CZ[pp]))
+        a = 0 if k < 3 else 1
+        eu = _vedot(*e, ux, uy, uz)
+        A = _fma(F32(4.5) * eu, eu, base)
+        ns = _fma(nws1 if a == 0 else nws2, A, s[k])
+        nd = _fma(nwd1 if a == 0 else nwd2, eu, d[k])
+        sp = _fma(nom, ns, s[k])
+        dp = _fma(nom, nd, d[k])
+        if forced:
+            eF = _vedot(*e, Fx, Fy, Fz)
+            sp = _fma(eu * eF, c18[a], sp)
+            sp = _fma(nc2[a], uF3, sp)
+            dp = _fma(eF, c6[a], dp)
+        hs = half * sp
+        out[pp] = _fma(half, dp, hs)
+        out[pm] = _fma(F32(-0.5), dp, hs)
     fluid = (solid == 0) if solid is not None else None
     g_next = np.empty_like(g)
     for q in range(Q):

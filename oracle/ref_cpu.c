@@ -310,3 +310,11 @@ int ref_num_threads(void) {
 #endif
     return n;
 }
+
+/* Exact f32 fused multiply-add on arrays: out[i] = round(a[i]*b[i] + c[i]) with a single rounding (C99 fmaf).
+ * oracle/d3q19_ref.py:step_physical calls it for every FMA of the compat=physical arithmetic contract (NumPy has no
+ * fused operation; emulating it in f64 double-rounds). */
+void ref_fmaf_array(const float *a, const float *b, const float *c, float *out, long n) {
+#pragma omp parallel for schedule(static) if (n > 65536)
+    for (long i = 0; i < n; ++i) out[i] = fmaf(a[i], b[i], c[i]);
+}

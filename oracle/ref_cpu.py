@@ -60,7 +60,18 @@ def lib():
         _lib.ref_v60_solid.argtypes = [C.c_int] * 3 + [C.c_float] * 4 + [C.c_void_p]
         _lib.ref_v60_solid.restype = None
         _lib.ref_num_threads.restype = C.c_int
+        _lib.ref_fmaf_array.argtypes = [C.c_void_p] * 4 + [C.c_long]
+        _lib.ref_fmaf_array.restype = None
     return _lib
+
+
+def fmaf(a, b, c) -> np.ndarray:
+    """Exact f32 fused multiply-add, element-wise with NumPy broadcasting (C99 fmaf, single rounding)."""
+    a, b, c = np.broadcast_arrays(np.asarray(a, np.float32), np.asarray(b, np.float32), np.asarray(c, np.float32))
+    a = np.ascontiguousarray(a); b = np.ascontiguousarray(b); c = np.ascontiguousarray(c)
+    out = np.empty(a.shape, np.float32)
+    lib().ref_fmaf_array(a.ctypes.data, b.ctypes.data, c.ctypes.data, out.ctypes.data, out.size)
+    return out
 
 
 def num_threads() -> int:

@@ -52,6 +52,8 @@ SIGNATURES = {
     "lbm_set_params": (C.c_int, [_P, C.POINTER(LbmParams)]),
     "lbm_destroy": (None, [_P]),
     "lbm_launch_count": (C.c_longlong, [_P]),
+    "lbm_populations_changed": (C.c_int, [_P]),
+    "lbm_selftest_math": (C.c_int, [_P, C.POINTER(C.c_ulonglong), _P]),
     "lbm_init_equilibrium": (C.c_int, [_P, _P, _P, _P, C.c_float, C.POINTER(C.c_float), _P]),
     "lbm_build_v60_geometry": (C.c_int, [_P, _P, _P, C.POINTER(C.c_float), _P]),
     "lbm_pack_flags": (C.c_int, [_P, _P, _P, _P, _P, _P]),

@@ -13,7 +13,7 @@
 namespace lbm {
 using StepKernel = void (*)(const StepArgs);
 #define DECL_LOOKUP(name) StepKernel name(int forced, int les, int porous, int vec, int collide, int *block);
-DECL_LOOKUP(lookup_fast_g0_fn) DECL_LOOKUP(lookup_fast_g1_fn) DECL_LOOKUP(lookup_fast_g2_fn) DECL_LOOKUP(lookup_fast_g3_fn)
+DECL_LOOKUP(lookup_fast_g2_fn) DECL_LOOKUP(lookup_fast_g3_fn)
 DECL_LOOKUP(lookup_strict_g0_fn) DECL_LOOKUP(lookup_strict_g1_fn) DECL_LOOKUP(lookup_strict_g2_fn) DECL_LOOKUP(lookup_strict_g3_fn)
 
 cudaError_t launch_init_equilibrium(const Grid &, int, float *, const float *, const float *, float, const float[3], cudaStream_t);
@@ -25,6 +25,8 @@ cudaError_t launch_face_bc(const Grid &, float *, const uint8_t *, cudaStream_t,
 cudaError_t launch_pressure_gradient(const Grid &, const float *, const uint8_t *, float *, float, float, cudaStream_t);
 cudaError_t launch_forchheimer_force(const Grid &, const float *, const uint8_t *, float *, float, float, float, float, float, cudaStream_t);
 cudaError_t launch_add_reaction(const Grid &, const float *, const uint8_t *, float *, cudaStream_t);
+cudaError_t run_selftest_math(unsigned long long[7], const StepArgs &, cudaStream_t);
+cudaError_t launch_bounce_slots(const Grid &, float *, const uint8_t *, const unsigned long long *, int, int, cudaStream_t);
 cudaError_t launch_particles_couple(const Grid &, const float *, float *, const lbm_particles &, float, float, float, cudaStream_t);
 cudaError_t launch_particles_under_relax(const lbm_particles &, float, cudaStream_t);
 }  // namespace lbm
@@ -84,6 +86,9 @@ struct lbm_ctx {
     std::vector<int> tile_off;                 // per owned plane offsets into the tile list (nz+1 entries)
     const uint8_t *list_flags = nullptr;
     int list_vec = 0;
+    // compat = physical, walls: the population buffer whose bounce-back slots (solid-cell slots next to fluid cells,
+    // see lbm_phys.cuh) are known to be current; anything else gets them rebuilt before it is stepped
+    const float *slots_valid = nullptr;
 };
 
 static int fail(lbm_ctx *ctx, const std::string &msg) {
@@ -109,12 +114,20 @@ static int make_grid(lbm_ctx *ctx, const lbm_params *p, Grid *g) {
     return 0;
 }
 
+static bool phys_walls(const lbm_params &p) { return p.compat == LBM_COMPAT_PHYSICAL && (p.features & LBM_FEAT_WALLS); }
+
 static int pick_vec(const lbm_ctx *ctx) {
     int vec = ctx->p.vec;
-    // default: 128-bit path for dense periodic boxes (99 % of the copy bandwidth); one cell per thread behind a flag
-    // field (V60 512^3: VEC=1 2.2 ms, VEC=2 2.3 ms, VEC=4 3.6 ms -- partially filled warps at every chord end)
+    if (phys_walls(ctx->p)) {
+        // two cells per thread on packed f32x2 registers (lbm_phys.cuh); one when the rows are not 8-byte aligned
+        if (vec != 1) vec = 2;
+        if (ctx->g.nx % 2 != 0 || ctx->g.nx < 4) vec = 1;
+        return vec;
+    }
+    // 128-bit path for dense periodic boxes (99 % of the copy bandwidth); compat = reference behind a flag field
+    // runs one cell per thread (partially filled warps at every chord end make wider threads slower there)
     if (vec == 0) vec = (ctx->p.features & LBM_FEAT_WALLS) ? 1 : 4;
-    if (vec == 2 && !((ctx->p.features & LBM_FEAT_WALLS) && ctx->p.compat == LBM_COMPAT_PHYSICAL)) vec = 1;   // VEC=2: tuning set only
+    if (vec == 2) vec = 1;
     if (ctx->g.nx % 4 != 0 || ctx->g.nx < 8) vec = 1;
     return vec;
 }
@@ -123,7 +136,8 @@ static int pick_vec(const lbm_ctx *ctx) {
 static int pick_block(const lbm_ctx *ctx, int vec) {
     const int b = ctx->p.block;
     if (b == 64 || b == 128 || b == 256) return b;
-    return vec == 1 ? ((ctx->p.features & LBM_FEAT_WALLS) ? 64 : 256) : 128;
+    if (ctx->p.features & LBM_FEAT_WALLS) return 64;
+    return vec == 1 ? 256 : 128;
 }
 
 static StepKernel lookup(const lbm_params &p, int vec, int collide, int *block);
@@ -132,6 +146,7 @@ static int rebuild_lists(lbm_ctx *ctx, const uint8_t *flags, int vec, int block,
     CUDA_OK(ctx, build_work_lists(ctx->g, flags, vec, &ctx->d_tiles, ctx->tile_off, &ctx->d_nbr, s));
     ctx->launches += 5;
     ctx->list_flags = flags; ctx->list_vec = vec; ctx->list_block = block; ctx->window_set = false;
+    ctx->slots_valid = nullptr;
     return 0;
 }
 
@@ -176,6 +191,7 @@ int lbm_set_params(lbm_ctx *ctx, const lbm_params *p) {
         ctx->list_flags = nullptr;
     }
     if (p->vec != ctx->p.vec) ctx->list_flags = nullptr;
+    if (p->compat != ctx->p.compat || p->periodic != ctx->p.periodic || p->features != ctx->p.features) ctx->slots_valid = nullptr;
     ctx->g = g; ctx->p = *p;
     return 0;
 }
@@ -192,11 +208,30 @@ void lbm_destroy(lbm_ctx *ctx) {
 
 long long lbm_launch_count(lbm_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+int lbm_selftest_math(lbm_ctx *ctx, unsigned long long mismatches[7], void *stream) {
+    if (!ctx || !mismatches) return fail(ctx, "null argument");
+    StepArgs a;
+    memset(&a, 0, sizeof a);
+    a.g = ctx->g;
+    a.tau_water = 0.53f; a.tau_air = 0.8f; a.gravity_lu = 1e-5f; a.tau_min = 0.55f; a.tau_max = 1.9f;
+    a.les_k = (float)(18.0 * sqrt(2.0) * 0.18 * 0.18); a.porous_darcy = 0.37f; a.porous_forch = 0.9f;
+    CUDA_OK(ctx, run_selftest_math(mismatches, a, (cudaStream_t)stream));
+    ctx->launches += 2;
+    return 0;
+}
+
+int lbm_populations_changed(lbm_ctx *ctx) {
+    if (!ctx) return fail(ctx, "null argument");
+    ctx->slots_valid = nullptr;
+    return 0;
+}
+
 int lbm_init_equilibrium(lbm_ctx *ctx, float *g, const float *rho, const float *u, float rho0, const float u0[3], void *stream) {
     if (!ctx || !g) return fail(ctx, "null argument");
     const float z[3] = {0, 0, 0};
     CUDA_OK(ctx, launch_init_equilibrium(ctx->g, ctx->p.compat, g, rho, u, rho0, u0 ? u0 : z, (cudaStream_t)stream));
     ctx->launches++;
+    ctx->slots_valid = nullptr;
     return 0;
 }
 
@@ -231,8 +266,9 @@ static StepKernel lookup(const lbm_params &p, int vec, int collide, int *block) 
 #define LBM_PICK(g) (strict ? lookup_strict_g##g##_fn(forced, les, porous, vec, collide, block) \
                             : lookup_fast_g##g##_fn(forced, les, porous, vec, collide, block))
     switch (group) {
-        case 0: return LBM_PICK(0);
-        case 1: return LBM_PICK(1);
+        // compat = physical: explicitly rounded operations, one build (LBM_FEAT_STRICT has nothing to select)
+        case 0: return lookup_strict_g0_fn(forced, les, porous, vec, collide, block);
+        case 1: return lookup_strict_g1_fn(forced, les, porous, vec, collide, block);
         case 2: return LBM_PICK(2);
         default: return LBM_PICK(3);
     }
@@ -359,6 +395,26 @@ static int exchange(lbm_ctx *ctx, float *g, float *vec3, cudaStream_t s) {
     return 0;
 }
 
+// compat = physical, walls: make sure the bounce-back slots of `g` are current (no-op when the step kernel wrote them)
+static int ensure_slots(lbm_ctx *ctx, float *g, const uint8_t *flags, cudaStream_t s) {
+    if (!phys_walls(ctx->p) || ctx->slots_valid == g) return 0;
+    CUDA_OK(ctx, launch_bounce_slots(ctx->g, g, flags, ctx->d_nbr, 0, ctx->g.nz, s));
+    ctx->launches++;
+    ctx->slots_valid = g;
+    return 0;
+}
+// after a halo exchange the incoming ghost planes have overwritten the slots that live in them
+static int refresh_boundary_slots(lbm_ctx *ctx, float *g, const uint8_t *flags, cudaStream_t s) {
+    if (!phys_walls(ctx->p) || !ctx->g.zg) return 0;
+    CUDA_OK(ctx, launch_bounce_slots(ctx->g, g, flags, ctx->d_nbr, 0, 1, s));
+    ctx->launches++;
+    if (ctx->g.nz > 1) {
+        CUDA_OK(ctx, launch_bounce_slots(ctx->g, g, flags, ctx->d_nbr, ctx->g.nz - 1, ctx->g.nz, s));
+        ctx->launches++;
+    }
+    return 0;
+}
+
 extern "C" {
 
 int lbm_step(lbm_ctx *ctx, lbm_fields *f, int nsteps, int write_macro_every, void *compute_stream, void *comm_stream) {
@@ -374,6 +430,7 @@ int lbm_step(lbm_ctx *ctx, lbm_fields *f, int nsteps, int write_macro_every, voi
     cudaStream_t cs = (cudaStream_t)compute_stream, ms = (cudaStream_t)comm_stream;
     const bool slabs = ctx->g.zg == 1;
     const bool overlap = slabs && ctx->nranks > 1 && ms != nullptr && ms != cs && ctx->g.nz >= 3;
+    if (L.walls && nsteps > 0 && ensure_slots(ctx, f->f_src, f->flags, cs)) return 1;
     for (int s = 0; s < nsteps; ++s) {
         StepArgs a;
         if (fill_args(ctx, f, &a)) return 1;
@@ -394,6 +451,8 @@ int lbm_step(lbm_ctx *ctx, lbm_fields *f, int nsteps, int write_macro_every, voi
             if (launch_planes(ctx, a, L, 0, ctx->g.nz, cs)) return 1;
             if (slabs && exchange(ctx, f->f_dst, (ref_les && a.write_macro) ? f->u_dst : nullptr, cs)) return 1;
         }
+        if (slabs && L.walls && refresh_boundary_slots(ctx, f->f_dst, f->flags, cs)) return 1;
+        if (phys_walls(p)) ctx->slots_valid = f->f_dst;
         float *t = f->f_src; f->f_src = f->f_dst; f->f_dst = t;
         if (a.write_macro && f->u_src && f->u_src != f->u_dst) { t = f->u_src; f->u_src = f->u_dst; f->u_dst = t; }
     }
@@ -405,25 +464,25 @@ int lbm_macroscopic(lbm_ctx *ctx, const lbm_fields *f, void *stream) {
     lbm_params p = ctx->p;
     p.features &= ~LBM_FEAT_LES;
     if (p.compat == LBM_COMPAT_REFERENCE) p.features &= ~LBM_FEAT_POROUS;
+    const bool walls = (p.features & LBM_FEAT_WALLS) != 0;
+    const int step_vec = pick_vec(ctx);
+    // moments-only variants: compat = physical behind walls shares the step kernel's tile list (VEC = 1 or 2); every
+    // other group has them for VEC = 1 only, so a list built for a wider step kernel is rebuilt around the call
+    const int vec = phys_walls(p) ? step_vec : 1;
+    const bool relist = walls && vec != step_vec;
     Launcher L;
-    {
-        // the moments-only variants exist for VEC = 1; the tile list was built for pick_vec(): rebuild on demand
-        const int vec = pick_vec(ctx);
-        if ((p.features & LBM_FEAT_WALLS) && vec != 1) {
-            if (rebuild_lists(ctx, f->flags, 1, 256, (cudaStream_t)stream)) return 1;
-        }
-        const int rc = make_launcher(ctx, p, f, 1, 0, &L);
-        if (rc) return rc;
-    }
+    if (relist && rebuild_lists(ctx, f->flags, 1, 256, (cudaStream_t)stream)) return 1;
+    if (make_launcher(ctx, p, f, vec, 0, &L)) return 1;
     StepArgs a;
     if (fill_args(ctx, f, &a)) return 1;
     if (!f->rho || !f->u_dst) return fail(ctx, "rho/u_dst is NULL");
+    if (walls && ensure_slots(ctx, f->f_src, f->flags, (cudaStream_t)stream)) return 1;
     a.write_macro = 1;
     int rc = launch_planes(ctx, a, L, 0, ctx->g.nz, (cudaStream_t)stream);
-    if ((p.features & LBM_FEAT_WALLS) && pick_vec(ctx) != 1) {      // restore the lists of the step kernel
-        int block = pick_block(ctx, pick_vec(ctx));
-        lookup(ctx->p, pick_vec(ctx), 1, &block);
-        if (rebuild_lists(ctx, f->flags, pick_vec(ctx), block, (cudaStream_t)stream)) return 1;
+    if (relist) {      // restore the lists of the step kernel
+        int block = pick_block(ctx, step_vec);
+        lookup(ctx->p, step_vec, 1, &block);
+        if (rebuild_lists(ctx, f->flags, step_vec, block, (cudaStream_t)stream)) return 1;
     }
     return rc;
 }
@@ -447,6 +506,7 @@ int lbm_import_f(lbm_ctx *ctx, const float *f_in, const uint8_t *flags, float *g
     if (!ctx || !g || !f_in || g == f_in) return fail(ctx, "bad argument");
     CUDA_OK(ctx, launch_convert_f(ctx->g, false, f_in, flags, g, (cudaStream_t)stream));
     ctx->launches++;
+    ctx->slots_valid = nullptr;
     return 0;
 }
 
@@ -512,6 +572,7 @@ int lbm_attach_nccl(lbm_ctx *ctx, const void *unique_id128, int rank, int nranks
 
 int lbm_halo_exchange(lbm_ctx *ctx, float *g, float *vec3_or_null, void *stream) {
     if (!ctx || !g) return fail(ctx, "null argument");
+    ctx->slots_valid = nullptr;      // the incoming ghost planes overwrite the bounce-back slots that live in them
     return exchange(ctx, g, vec3_or_null, (cudaStream_t)stream);
 }
 

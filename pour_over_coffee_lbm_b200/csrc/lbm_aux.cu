@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "lbm_common.cuh"
+#include "lbm_phys.cuh"
 
 namespace lbm {
 
@@ -343,6 +344,130 @@ cudaError_t build_work_lists(const Grid &G, const uint8_t *flags, int vec, unsig
     return cudaGetLastError();
 }
 
+// ---- write-side bounce-back slots (compat = physical, walls path; see lbm_phys.cuh) ---------------------
+// Re-creates the bounce-back slots of a population buffer from the cells' own values:
+//   g[opp q][x + e_q] = g[q][x]   for every fluid cell x of planes [z_begin, z_end) whose neighbour x + e_q is solid.
+// Needed once after the populations were written from outside the step kernel (initialisation, lbm_import_f, a
+// geometry change) and, in slab mode, for the two boundary planes after each halo exchange (the incoming ghost
+// planes overwrite the slots that live in them).
+__global__ void bounce_slots_kernel(Grid G, float *g, const uint8_t *flags, const unsigned long long *nbr, int z_begin, int z_end) {
+    const long long per = G.plane;
+    const long long n = per * (z_end - z_begin);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int z = z_begin + (int)(i / per);
+        const int rem = (int)(i % per);
+        const int y = rem / G.nx, x = rem % G.nx;
+        const int zp = z + G.zg;
+        const long long c = ((long long)zp * G.ny + y) * G.nx + x;
+        const unsigned fl = flags[c];
+        if ((fl & LBM_FLAG_SOLID) || !(fl & LBM_FLAG_NEAR)) continue;
+        const unsigned solid_src = (unsigned)nbr[c];
+        if (!solid_src) continue;
+        for (int q = 1; q < Q; ++q) {
+            if (!(solid_src & (1u << opp(q)))) continue;
+            int xt = x + cx(q), yt = y + cy(q), zt = zp + cz(q);
+            if (xt < 0) xt = G.nx - 1; else if (xt >= G.nx) xt = 0;
+            if (yt < 0) yt = G.ny - 1; else if (yt >= G.ny) yt = 0;
+            if (!G.zg) { if (zt < 0) zt = G.nz - 1; else if (zt >= G.nz) zt = 0; }
+            const long long t = ((long long)zt * G.ny + yt) * G.nx + xt;
+            g[(long long)opp(q) * G.vol + t] = g[(long long)q * G.vol + c];
+        }
+    }
+}
+
+
+// ---- self-test of the packed reciprocal / square root (lbm_phys.cuh) -----------------------------------
+// Every f32 bit pattern goes through both lanes of Ops<P2>::rcp / ::sqrt and is compared, bit for bit, with the
+// correctly rounded scalar intrinsics.  counts[0] = reciprocal mismatches, counts[1] = square-root mismatches.
+__global__ void selftest_math_kernel(unsigned long long *counts) {
+    unsigned long long bad_r = 0, bad_s = 0;
+    const unsigned long long n = 1ull << 32;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned a = (unsigned)i, b = (unsigned)i * 2654435761u + 12345u;
+        const float x0 = __uint_as_float(a), x1 = __uint_as_float(b);
+        const P2 v = p2_make(x0, x1);
+        const P2 r = Ops<P2>::rcp(v), s = Ops<P2>::sqrt(v);
+        auto same = [](float p, float q) { return __float_as_uint(p) == __float_as_uint(q) || (p != p && q != q); };
+        if (!same(p2_lo(r), __frcp_rn(x0)) || !same(p2_hi(r), __frcp_rn(x1))) ++bad_r;
+        if (!same(p2_lo(s), __fsqrt_rn(x0)) || !same(p2_hi(s), __fsqrt_rn(x1))) ++bad_s;
+    }
+    if (bad_r) atomicAdd(counts, bad_r);
+    if (bad_s) atomicAdd(counts + 1, bad_s);
+}
+
+// packed add / sub / mul / fma (all operand forms the collision uses: registers, broadcast scalars, literals) and the
+// whole collision operator, packed against scalar, on pseudo-random near-equilibrium states.
+// counts[2..5] = add, sub, mul, fma mismatches; counts[6] = cells whose packed collision differs from the scalar one.
+__device__ __forceinline__ unsigned lcg(unsigned &s) { s = s * 1664525u + 1013904223u; return s; }
+__device__ __forceinline__ float unit(unsigned &s) { return (float)(lcg(s) >> 8) * (1.0f / 16777216.0f); }
+__global__ void selftest_packed_kernel(unsigned long long *counts, StepArgs P, int iters) {
+    using O = Ops<P2>;
+    unsigned seed = (blockIdx.x * blockDim.x + threadIdx.x) * 747796405u + 2891336453u;
+    unsigned long long bad[5] = {0, 0, 0, 0, 0};
+    auto same = [](float p, float q) { return __float_as_uint(p) == __float_as_uint(q) || (p != p && q != q); };
+    for (int it = 0; it < iters; ++it) {
+        const float a0 = unit(seed) - 0.5f, a1 = (unit(seed) - 0.5f) * 1e-3f, b0 = unit(seed) * 3.0f - 1.0f, b1 = unit(seed) - 0.3f;
+        const float c0 = -a0 * b0 + (unit(seed) - 0.5f) * 1e-7f, c1 = unit(seed);
+        const P2 a = p2_make(a0, a1), b = p2_make(b0, b1), c = p2_make(c0, c1);
+        P2 r = O::add(a, b); if (!same(p2_lo(r), __fadd_rn(a0, b0)) || !same(p2_hi(r), __fadd_rn(a1, b1))) ++bad[0];
+        r = O::sub(a, b); if (!same(p2_lo(r), __fsub_rn(a0, b0)) || !same(p2_hi(r), __fsub_rn(a1, b1))) ++bad[1];
+        r = O::mul(a, b); if (!same(p2_lo(r), __fmul_rn(a0, b0)) || !same(p2_hi(r), __fmul_rn(a1, b1))) ++bad[2];
+        r = O::mul(O::bc(4.5f), b); if (!same(p2_lo(r), __fmul_rn(4.5f, b0)) || !same(p2_hi(r), __fmul_rn(4.5f, b1))) ++bad[2];
+        r = O::fma(a, b, c); if (!same(p2_lo(r), __fmaf_rn(a0, b0, c0)) || !same(p2_hi(r), __fmaf_rn(a1, b1, c1))) ++bad[3];
+        r = O::fma(O::bc(-1.5f), b, O::bc(1.0f)); if (!same(p2_lo(r), __fmaf_rn(-1.5f, b0, 1.0f)) || !same(p2_hi(r), __fmaf_rn(-1.5f, b1, 1.0f))) ++bad[3];
+        r = O::fma(O::bc(P.tau_water), b, c); if (!same(p2_lo(r), __fmaf_rn(P.tau_water, b0, c0)) || !same(p2_hi(r), __fmaf_rn(P.tau_water, b1, c1))) ++bad[3];
+        // collision: two random near-equilibrium cells
+        float fs[2][Q]; P2 fp[Q];
+        CellIn<P2> ip; float F[2][3], ph[2];
+        for (int l = 0; l < 2; ++l) {
+            const float rho = 0.9f + 0.2f * unit(seed);
+            const float ux = 0.1f * (unit(seed) - 0.5f), uy = 0.1f * (unit(seed) - 0.5f), uz = 0.1f * (unit(seed) - 0.5f);
+            for (int q = 0; q < Q; ++q) {
+                const float eu = cx(q) * ux + cy(q) * uy + cz(q) * uz;
+                fs[l][q] = wq(q) * rho * (1.0f + 3.0f * eu + 4.5f * eu * eu - 1.5f * (ux * ux + uy * uy + uz * uz)) * (1.0f + 1e-3f * (unit(seed) - 0.5f));
+            }
+            for (int d = 0; d < 3; ++d) F[l][d] = 1e-4f * (unit(seed) - 0.5f);
+            ph[l] = unit(seed);
+            ip.flag[l] = (lcg(seed) >> 16) & (LBM_FLAG_FILTER | LBM_FLAG_LES);
+        }
+        for (int q = 0; q < Q; ++q) fp[q] = p2_make(fs[0][q], fs[1][q]);
+        ip.Fx = p2_make(F[0][0], F[1][0]); ip.Fy = p2_make(F[0][1], F[1][1]); ip.Fz = p2_make(F[0][2], F[1][2]);
+        ip.phase = p2_make(ph[0], ph[1]);
+        CellMacro<P2> mp;
+        collide_phys<P2, true, true, true, true>(fp, ip, mp, P, true, true);
+        for (int l = 0; l < 2; ++l) {
+            CellIn<float> is; is.Fx = F[l][0]; is.Fy = F[l][1]; is.Fz = F[l][2]; is.phase = ph[l]; is.flag[0] = ip.flag[l];
+            CellMacro<float> ms;
+            collide_phys<float, true, true, true, true>(fs[l], is, ms, P, true, true);
+            bool ok = same(O::get(mp.rho, l), ms.rho) && same(O::get(mp.ux, l), ms.ux) && same(O::get(mp.uy, l), ms.uy) && same(O::get(mp.uz, l), ms.uz);
+            for (int q = 0; q < Q; ++q) ok = ok && same(O::get(fp[q], l), fs[l][q]);
+            if (!ok) ++bad[4];
+#ifdef LBM_SELFTEST_DEBUG
+            if (!ok && blockIdx.x == 0 && threadIdx.x == 0 && it < 2) {
+                printf("it %d lane %d flag %u: rho %08x %08x ux %08x %08x uy %08x %08x uz %08x %08x\n", it, l, ip.flag[l],
+                       __float_as_uint(O::get(mp.rho, l)), __float_as_uint(ms.rho), __float_as_uint(O::get(mp.ux, l)), __float_as_uint(ms.ux),
+                       __float_as_uint(O::get(mp.uy, l)), __float_as_uint(ms.uy), __float_as_uint(O::get(mp.uz, l)), __float_as_uint(ms.uz));
+                for (int q = 0; q < Q; ++q)
+                    printf("   q %d packed %08x scalar %08x (%.9g %.9g)\n", q, __float_as_uint(O::get(fp[q], l)), __float_as_uint(fs[l][q]), O::get(fp[q], l), fs[l][q]);
+            }
+#endif
+        }
+    }
+    for (int k = 0; k < 5; ++k) if (bad[k]) atomicAdd(counts + 2 + k, bad[k]);
+}
+cudaError_t run_selftest_math(unsigned long long out[7], const StepArgs &args, cudaStream_t s) {
+    unsigned long long *d = nullptr;
+    cudaError_t e = cudaMalloc(&d, 7 * sizeof(unsigned long long));
+    if (e != cudaSuccess) return e;
+    cudaMemsetAsync(d, 0, 7 * sizeof(unsigned long long), s);
+    selftest_math_kernel<<<148 * 16, 256, 0, s>>>(d);
+    selftest_packed_kernel<<<148 * 4, 128, 0, s>>>(d, args, 64);
+    e = cudaMemcpyAsync(out, d, 7 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(d);
+    return e != cudaSuccess ? e : cudaGetLastError();
+}
+
 // ---- host launchers (called from lbm_api.cu) -----------------------------------------------
 static inline int grid_for(long long n, int block) { long long g = (n + block - 1) / block; return (int)(g > 148LL * 32 ? 148 * 32 : g); }
 
@@ -391,6 +516,12 @@ cudaError_t launch_forchheimer_force(const Grid &G, const float *u, const uint8_
                                      float c_darcy, float c_forch, float fmax, cudaStream_t s) {
     const int b = 256; const long long gr = (G.vol + b - 1) / b;
     forchheimer_force_kernel<<<(unsigned)gr, b, 0, s>>>(G, u, flags, bf, K, beta, c_darcy, c_forch, fmax);
+    return cudaGetLastError();
+}
+cudaError_t launch_bounce_slots(const Grid &G, float *g, const uint8_t *flags, const unsigned long long *nbr, int z_begin, int z_end, cudaStream_t s) {
+    if (z_end <= z_begin) return cudaSuccess;
+    const int b = 256, gr = grid_for(G.plane * (z_end - z_begin), b);
+    bounce_slots_kernel<<<gr, b, 0, s>>>(G, g, flags, nbr, z_begin, z_end);
     return cudaGetLastError();
 }
 cudaError_t launch_add_reaction(const Grid &G, const float *reaction, const uint8_t *flags, float *bf, cudaStream_t s) {

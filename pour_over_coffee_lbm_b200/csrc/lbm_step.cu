@@ -1,6 +1,8 @@
 // Instantiates one group of step-kernel variants and exports a lookup function for it.
-// Compiled 8 times: LBM_GROUP in {0..3} = COMPAT*2 + WALLS, LBM_STRICT_BUILD in {0,1}
-// (strict adds -fmad=false on the nvcc command line; see csrc/Makefile).
+// LBM_GROUP in {0..3} = COMPAT*2 + WALLS.
+//   compat = physical (groups 0, 1): every operation is explicitly rounded (lbm_phys.cuh), so there is one build.
+//   compat = reference (groups 2, 3): compiled twice, LBM_STRICT_BUILD in {0,1}; strict adds -fmad=false on the nvcc
+//   command line (bit-exact against the CPU oracle, which never contracts), see csrc/Makefile.
 #include "lbm_step_kernel.cuh"
 
 #ifndef LBM_GROUP
@@ -17,23 +19,28 @@ using StepKernel = void (*)(const StepArgs);
 constexpr int G_COMPAT = LBM_GROUP / 2;
 constexpr bool G_WALLS = (LBM_GROUP % 2) != 0;
 
-// Resident-thread target per SM, enforced through __launch_bounds__(BLOCK, MINB): it caps registers at 64 / 96 / 128
+// Resident-thread target per SM, enforced through __launch_bounds__(BLOCK, MINB): it caps registers at 64 / 128 / 128
 // per thread for VEC = 1 / 2 / 4.  Without the cap ptxas takes 160+ registers for the VEC=4 kernels, only 12 warps stay
-// resident and the headline kernel drops from 0.40 to 0.63 ms (measured); the few bytes of spill this costs the
-// full-feature variants stay in L1.
+// resident and the headline kernel drops from 0.40 to 0.63 ms (measured).
 template <int VEC, int BLOCK>
-constexpr int min_blocks() { return (VEC == 1 ? 1024 : (VEC == 2 ? 640 : 512)) / BLOCK; }
+constexpr int min_blocks() { return (VEC == 1 ? 1024 : 512) / BLOCK; }
 
 // CTA size: the walls path runs best with small CTAs (near-wall warps take longer; a CTA slot is held until its
 // slowest warp retires -- V60 512^3 sweep: 64 threads 2.17 ms, 128: 2.20, 256: 2.34)
 template <int MODE, int VEC>
-constexpr int default_block() { return VEC == 1 ? (MODE == MODE_BULK ? 64 : 256) : 128; }
+constexpr int default_block() { return MODE == MODE_BULK ? 64 : (VEC == 1 ? 256 : 128); }
 
 template <int MODE, bool FORCED, bool LES, bool POROUS, int VEC, bool COLLIDE>
 static StepKernel pick() {
     constexpr int BLOCK = default_block<MODE, VEC>();
     if constexpr (POROUS && !G_WALLS) return nullptr;          // the filter zone lives in the flag byte
-    else if constexpr (!COLLIDE && (LES || VEC != 1)) return nullptr;
+    else if constexpr (!COLLIDE && LES) return nullptr;
+    else if constexpr (G_WALLS && G_COMPAT == LBM_COMPAT_PHYSICAL) {
+        if constexpr (VEC == 4) return nullptr;
+        else return phys_walls_kernel<FORCED, LES, POROUS, VEC, BLOCK, COLLIDE, min_blocks<VEC, BLOCK>()>;
+    }
+    else if constexpr (VEC == 2) return nullptr;
+    else if constexpr (!COLLIDE && VEC != 1) return nullptr;
     else return step_kernel<LBM_STRICT_BUILD, G_COMPAT, MODE, FORCED, LES, POROUS, VEC, BLOCK, COLLIDE, min_blocks<VEC, BLOCK>()>;
 }
 
@@ -64,37 +71,36 @@ static StepKernel pick_feat(int forced, int les, int porous) {
 template <int VEC, int BLOCK>
 static StepKernel tuned() {
     if constexpr (G_WALLS && G_COMPAT == LBM_COMPAT_PHYSICAL)
-        return step_kernel<LBM_STRICT_BUILD, G_COMPAT, MODE_BULK, true, true, true, VEC, BLOCK, true, min_blocks<VEC, BLOCK>()>;
+        return phys_walls_kernel<true, true, true, VEC, BLOCK, true, min_blocks<VEC, BLOCK>()>;
     else return nullptr;
 }
 static StepKernel pick_tuned(int vec, int block) {
     switch (vec * 1000 + block) {
-        case 1256: return tuned<1, 256>();
         case 1128: return tuned<1, 128>();
-        case 2064: return tuned<2, 64>();
         case 2128: return tuned<2, 128>();
-        case 4064: return tuned<4, 64>();
+        case 2256: return tuned<2, 256>();
         default: return nullptr;
     }
 }
 
-// The step kernel of this group (dense when the group has no walls, bulk-over-active-tiles otherwise).
+// The step kernel of this group (dense when the group has no walls, one warp per active tile otherwise).
 // *block: in = requested CTA size (0 = default), out = CTA size of the returned kernel.
 // Returns nullptr when the combination is not built.
 StepKernel LBM_LOOKUP(int forced, int les, int porous, int vec, int collide, int *block) {
     StepKernel k = nullptr;
     constexpr int MAIN = G_WALLS ? MODE_BULK : MODE_DENSE;
-    const int def_block = (vec == 1) ? default_block<MAIN, 1>() : 128;
-    if (collide && forced && les && porous && ((*block && *block != def_block) || vec == 2)) {
-        const int b = *block ? *block : def_block;
-        k = pick_tuned(vec, b);
-        if (k) { *block = b; return k; }
+    const int def_block = vec == 1 ? default_block<MAIN, 1>() : (vec == 2 ? default_block<MAIN, 2>() : default_block<MAIN, 4>());
+    if (collide && forced && les && porous && *block && *block != def_block) {
+        k = pick_tuned(vec, *block);
+        if (k) return k;
     }
     if (collide) {
         if (vec == 4) k = pick_feat<MAIN, 4, true>(forced, les, porous);
+        else if (vec == 2) k = pick_feat<MAIN, 2, true>(forced, les, porous);
         else if (vec == 1) k = pick_feat<MAIN, 1, true>(forced, les, porous);
     } else {
-        if (vec == 1) k = pick_feat<MAIN, 1, false>(forced, les, porous);
+        if (vec == 2) k = pick_feat<MAIN, 2, false>(forced, false, porous);
+        else if (vec == 1) k = pick_feat<MAIN, 1, false>(forced, false, porous);
     }
     *block = def_block;
     return k;

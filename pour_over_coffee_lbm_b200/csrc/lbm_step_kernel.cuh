@@ -21,6 +21,7 @@
 // twice, with -fmad=false ("strict", bit-exact against the oracle) and with FMA contraction.
 #pragma once
 #include "lbm_common.cuh"
+#include "lbm_phys.cuh"
 
 namespace lbm {
 
@@ -141,118 +142,6 @@ __device__ __forceinline__ void collide_reference(float (&f)[Q], const CellAux &
                 const float hf = (r + 1.0f) * 0.5f;
                 uz = uz * r; ux = ux * hf; uy = uy * hf;
             }
-        }
-    }
-    o.rho = rho; o.ux = ux; o.uy = uy; o.uz = uz;
-}
-
-// ---------------------------------------------------------------------------------------------
-// compat = physical: consistent lattice, Guo forcing (Guo, Zheng, Shi 2002), local-stress
-// Smagorinsky (Hou et al. 1996), Guo-Zhao (2002) porous drag.
-// Evaluated pairwise over opposite directions (p, pbar): e_pbar = -e_p, so the pair shares e.u, e.F and the even
-// part of the equilibrium / forcing -- ~25 % fewer FP instructions than direction by direction (the V60 kernel is
-// issue-bound: ncu 71 % issue utilisation, 534 of 1054 executed instructions per warp were FADD/FMUL).
-// Same order of operations as oracle/d3q19_ref.py:step_physical.
-// ---------------------------------------------------------------------------------------------
-// pairs k = 0..8: (1,2) (3,4) (5,6) (7,10) (9,8) (11,14) (13,12) (15,18) (17,16)
-__host__ __device__ constexpr int pair_p(int k) { constexpr int t[9] = {1, 3, 5, 7, 9, 11, 13, 15, 17}; return t[k]; }
-__host__ __device__ constexpr int pair_m(int k) { constexpr int t[9] = {2, 4, 6, 10, 8, 14, 12, 18, 16}; return t[k]; }
-
-template <bool FORCED, bool LES, bool POROUS>
-__device__ __forceinline__ void collide_physical(float (&f)[Q], const CellAux &a, CellOut &o, const StepArgs &P,
-                                                 bool has_phase, bool has_force) {
-    float s[9], d[9];
-    static_for<0, 9>([&](auto kk) {
-        constexpr int k = decltype(kk)::value;
-        s[k] = f[pair_p(k)] + f[pair_m(k)];
-        d[k] = f[pair_p(k)] - f[pair_m(k)];
-    });
-    float rho = f[0];
-    static_for<0, 9>([&](auto kk) { constexpr int k = decltype(kk)::value; rho = rho + s[k]; });
-    const float mx = (((d[0] + d[3]) + d[4]) + d[5]) + d[6];
-    const float my = (((d[1] + d[3]) - d[4]) + d[7]) + d[8];
-    const float mz = (((d[2] + d[5]) - d[6]) + d[7]) - d[8];
-    const float inv_rho = 1.0f / rho;
-    float Fx = 0.0f, Fy = 0.0f, Fz = 0.0f, ux, uy, uz;
-    bool forced = false;
-    if constexpr (FORCED) {
-        forced = has_force;
-        if (has_force) {
-            Fx = a.Fx; Fy = a.Fy; Fz = a.Fz;
-            if (has_phase && P.gravity_lu != 0.0f) Fz = Fz - P.gravity_lu * a.phase;
-            ux = (mx + 0.5f * Fx) * inv_rho; uy = (my + 0.5f * Fy) * inv_rho; uz = (mz + 0.5f * Fz) * inv_rho;
-        } else {
-            ux = mx * inv_rho; uy = my * inv_rho; uz = mz * inv_rho;
-        }
-    } else {
-        ux = mx * inv_rho; uy = my * inv_rho; uz = mz * inv_rho;
-    }
-    if constexpr (POROUS) {
-        const bool zone = (a.flag & LBM_FLAG_FILTER) != 0;
-        const float vmag = sqrtf(dot3(ux, uy, uz, ux, uy, uz));
-        const float c0 = 0.5f * (1.0f + 0.5f * P.porous_darcy);
-        const float c1 = 0.5f * P.porous_forch;
-        const float den = c0 + sqrtf(c0 * c0 + c1 * vmag);
-        const float sc = zone ? 1.0f / den : 1.0f;
-        ux = ux * sc; uy = uy * sc; uz = uz * sc;
-        const float umag = vmag * sc;
-        const float cdrag = zone ? P.porous_darcy + P.porous_forch * umag : 0.0f;
-        const float dx = -(cdrag * rho) * ux, dy = -(cdrag * rho) * uy, dz = -(cdrag * rho) * uz;
-        if (forced) { Fx = Fx + dx; Fy = Fy + dy; Fz = Fz + dz; }
-        else { Fx = dx; Fy = dy; Fz = dz; }
-        forced = true;
-    }
-    float tau0 = P.tau_water;
-    if constexpr (FORCED) { if (has_phase) tau0 = a.phase > 0.5f ? P.tau_water : P.tau_air; }
-    const float u_sq = dot3(ux, uy, uz, ux, uy, uz);
-    const float base = 1.0f - 1.5f * u_sq;
-    const float wr0 = wq(0) * rho, wr1 = wq(1) * rho, wr2 = wq(7) * rho;
-    float feq[Q], eu[9], ns[9];
-    feq[0] = wr0 * base;
-    static_for<0, 9>([&](auto kk) {
-        constexpr int k = decltype(kk)::value;
-        constexpr int p = pair_p(k), m = pair_m(k);
-        eu[k] = edot<cx(p), cy(p), cz(p)>(ux, uy, uz);
-        const float A = base + (4.5f * eu[k]) * eu[k];
-        const float B = 3.0f * eu[k];
-        const float wr = k < 3 ? wr1 : wr2;
-        const float sA = wr * A, sB = wr * B;
-        feq[p] = sA + sB;
-        feq[m] = sA - sB;
-        if constexpr (LES) ns[k] = s[k] - (sA + sA);       // non-equilibrium part of the pair sum
-    });
-    float tau = tau0;
-    if constexpr (LES) {
-        const float pxx = (((ns[0] + ns[3]) + ns[4]) + ns[5]) + ns[6];
-        const float pyy = (((ns[1] + ns[3]) + ns[4]) + ns[7]) + ns[8];
-        const float pzz = (((ns[2] + ns[5]) + ns[6]) + ns[7]) + ns[8];
-        const float pxy = ns[3] - ns[4], pxz = ns[5] - ns[6], pyz = ns[7] - ns[8];
-        const float qn = sqrtf(((pxx * pxx + pyy * pyy) + pzz * pzz) + 2.0f * ((pxy * pxy + pxz * pxz) + pyz * pyz));
-        tau = 0.5f * (tau0 + sqrtf(tau0 * tau0 + (P.les_k * qn) * inv_rho));
-        if (!(a.flag & LBM_FLAG_LES)) tau = tau0;
-        tau = fmaxf(P.tau_min, fminf(P.tau_max, tau));
-    }
-    const float omega = 1.0f / tau;
-    static_for<0, Q>([&](auto qq) {
-        constexpr int q = decltype(qq)::value;
-        f[q] = f[q] - omega * (f[q] - feq[q]);
-    });
-    if constexpr (FORCED || POROUS) {
-        if (forced) {
-            const float pref = 1.0f - 0.5f * omega;
-            const float uF3 = 3.0f * dot3(ux, uy, uz, Fx, Fy, Fz);
-            const float wp0 = wq(0) * pref, wp1 = wq(1) * pref, wp2 = wq(7) * pref;
-            f[0] = f[0] - wp0 * uF3;
-            static_for<0, 9>([&](auto kk) {
-                constexpr int k = decltype(kk)::value;
-                constexpr int p = pair_p(k), m = pair_m(k);
-                const float eF = edot<cx(p), cy(p), cz(p)>(Fx, Fy, Fz);
-                const float C = (9.0f * eu[k]) * eF - uF3;
-                const float T = 3.0f * eF;
-                const float wp = k < 3 ? wp1 : wp2;
-                f[p] = f[p] + wp * (C + T);
-                f[m] = f[m] + wp * (C - T);
-            });
         }
     }
     o.rho = rho; o.ux = ux; o.uy = uy; o.uz = uz;
@@ -421,6 +310,49 @@ __device__ __forceinline__ void step_cells(const StepArgs &P, const int x0, cons
     }
 
     CellOut out[VEC];
+    if constexpr (COMPAT == LBM_COMPAT_PHYSICAL) {
+        // compat = physical: lbm_phys.cuh (explicitly rounded operations; packed f32x2 on cell pairs when VEC is even)
+        if constexpr (VEC % 2 == 0) {
+#pragma unroll
+            for (int c = 0; c < VEC; c += 2) {
+                P2 fp[Q];
+#pragma unroll
+                for (int q = 0; q < Q; ++q) fp[q] = p2_make(f[q][c], f[q][c + 1]);
+                CellIn<P2> in;
+                in.Fx = FORCED ? p2_make(bf[0][c], bf[0][c + 1]) : p2_make(0.0f, 0.0f);
+                in.Fy = FORCED ? p2_make(bf[1][c], bf[1][c + 1]) : p2_make(0.0f, 0.0f);
+                in.Fz = FORCED ? p2_make(bf[2][c], bf[2][c + 1]) : p2_make(0.0f, 0.0f);
+                in.phase = FORCED ? p2_make(ph[c], ph[c + 1]) : p2_make(0.0f, 0.0f);
+                in.flag[0] = fl[c]; in.flag[1] = fl[c + 1];
+                CellMacro<P2> m;
+                collide_phys<P2, FORCED, LES && COLLIDE, POROUS, COLLIDE>(fp, in, m, P, has_phase, has_force);
+                if constexpr (COLLIDE) {
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) { f[q][c] = p2_lo(fp[q]); f[q][c + 1] = p2_hi(fp[q]); }
+                }
+                out[c].rho = p2_lo(m.rho); out[c].ux = p2_lo(m.ux); out[c].uy = p2_lo(m.uy); out[c].uz = p2_lo(m.uz);
+                out[c + 1].rho = p2_hi(m.rho); out[c + 1].ux = p2_hi(m.ux); out[c + 1].uy = p2_hi(m.uy); out[c + 1].uz = p2_hi(m.uz);
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) {
+                float fc[Q];
+#pragma unroll
+                for (int q = 0; q < Q; ++q) fc[q] = f[q][c];
+                CellIn<float> in;
+                in.Fx = FORCED ? bf[0][c] : 0.0f; in.Fy = FORCED ? bf[1][c] : 0.0f; in.Fz = FORCED ? bf[2][c] : 0.0f;
+                in.phase = FORCED ? ph[c] : 0.0f;
+                in.flag[0] = fl[c];
+                CellMacro<float> m;
+                collide_phys<float, FORCED, LES && COLLIDE, POROUS, COLLIDE>(fc, in, m, P, has_phase, has_force);
+                if constexpr (COLLIDE) {
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) f[q][c] = fc[q];
+                }
+                out[c].rho = m.rho; out[c].ux = m.ux; out[c].uy = m.uy; out[c].uz = m.uz;
+            }
+        }
+    } else {
 #pragma unroll
     for (int c = 0; c < VEC; ++c) {
         CellAux a;
@@ -430,26 +362,23 @@ __device__ __forceinline__ void step_cells(const StepArgs &P, const int x0, cons
         a.blockage = 0.0f; a.nu_sgs = 0.0f;
         const int x = x0 + c, zg_ = G.z0 + z;
         a.interior = x >= 1 && x <= G.nx - 2 && y >= 1 && y <= G.ny - 2 && zg_ >= 1 && zg_ <= G.nz_global - 2;
-        if constexpr (COMPAT == LBM_COMPAT_REFERENCE) {
-            if constexpr (POROUS) { if (P.blockage) a.blockage = __ldg(P.blockage + own + c); }
-            if constexpr (LES && COLLIDE) {
-                if (mine[c] && a.interior && (fl[c] & LBM_FLAG_LES))
-                    a.nu_sgs = les_fd_nu(P.u_src, own + c, G.nx, G.plane, G.vol, a.phase, P.les_k);
-            }
+        if constexpr (POROUS) { if (P.blockage) a.blockage = __ldg(P.blockage + own + c); }
+        if constexpr (LES && COLLIDE) {
+            if (mine[c] && a.interior && (fl[c] & LBM_FLAG_LES))
+                a.nu_sgs = les_fd_nu(P.u_src, own + c, G.nx, G.plane, G.vol, a.phase, P.les_k);
         }
         float fc[Q];
 #pragma unroll
         for (int q = 0; q < Q; ++q) fc[q] = f[q][c];
         if constexpr (COLLIDE) {
-            if constexpr (COMPAT == LBM_COMPAT_REFERENCE) collide_reference<FORCED, LES, POROUS>(fc, a, out[c], P);
-            else collide_physical<FORCED, LES, POROUS>(fc, a, out[c], P, has_phase, has_force);
+            collide_reference<FORCED, LES, POROUS>(fc, a, out[c], P);
 #pragma unroll
             for (int q = 0; q < Q; ++q) f[q][c] = fc[q];
         } else {
             // moments only (lbm_macroscopic): the collide routine on a scratch copy, populations untouched
-            if constexpr (COMPAT == LBM_COMPAT_REFERENCE) collide_reference<FORCED, false, false>(fc, a, out[c], P);
-            else collide_physical<FORCED, false, POROUS>(fc, a, out[c], P, has_phase, has_force);
+            collide_reference<FORCED, false, false>(fc, a, out[c], P);
         }
+    }
     }
 
     // write-back

@@ -131,6 +131,16 @@ class D3Q19Engine:
         except Exception:
             pass
 
+    def populations_changed(self):
+        """Call after writing `populations` / `g[...]` directly (torch ops): compat = physical behind walls keeps
+        bounce-back copies in the solid cells' slots and must rebuild them (include/lbm_b200.h)."""
+        self._check(self.lib.lbm_populations_changed(self._ctx), "lbm_populations_changed")
+
+    def selftest_math(self):
+        out = (C.c_ulonglong * 7)()
+        self._check(self.lib.lbm_selftest_math(self._ctx, out, self.stream), "lbm_selftest_math")
+        return tuple(int(v) for v in out)
+
     def launch_count(self) -> int:
         return int(self.lib.lbm_launch_count(self._ctx))
 

@@ -1,7 +1,10 @@
 """GPU parity of the fused step kernel against the CPU oracle, through the C ABI.
 
-Bars: the strict build (-fmad=false) must be BIT-EXACT against the oracle; the
-fast build (FMA contraction) must agree within 1e-5 relative (max|d|/max|ref|) after the run.
+Bars:
+  compat = physical   every operation of the kernels is explicitly rounded (csrc/lbm_phys.cuh), one build:
+                      BIT-EXACT against the oracle for every vec / strict setting (1e-5 is met with zero error).
+  compat = reference  the strict build (-fmad=false) must be BIT-EXACT; the fast build (FMA contraction) must
+                      agree within the documented tolerance after the run.
 """
 import numpy as np
 import pytest
@@ -46,8 +49,9 @@ def test_physical_periodic_strict_bit_exact(les, vec):
 
 
 @pytest.mark.parametrize("vec", [1, 4])
-def test_physical_periodic_fast_1000_steps(vec):
-    """rho,u within 1e-5 of the oracle after 1000 steps (fast build vs NumPy oracle, 24^3)."""
+def test_physical_periodic_1000_steps(vec):
+    """rho,u after 1000 steps (24^3): the north star asks for 1e-5 relative; the kernels are bit-exact, with or
+    without LBM_FEAT_STRICT (compat = physical has a single build)."""
     n, steps = 24, 1000
     u0 = H.smooth_velocity(n, 0.04, 5); rho0 = H.smooth_density(n, 0.01, 5)
     p = R.PhysParams(nx=n, ny=n, nz=n, tau_water=0.6)
@@ -57,8 +61,10 @@ def test_physical_periodic_fast_1000_steps(vec):
     eng = _engine(n, n, n, compat="physical", strict=False, vec=vec, tau=0.6)
     eng.init_equilibrium(rho=_torch(H.to_dev_scalar(rho0)), u=_torch(H.to_dev_vec(u0)))
     eng.step(steps)
-    H.assert_fast_build_close(H.from_dev_scalar(eng.rho), rho, 1.0, FAST_TOL, "rho")
-    H.assert_fast_build_close(H.from_dev_vec(eng.u), u, 0.04, FAST_TOL, "u")
+    assert H.rel_err(H.from_dev_scalar(eng.rho), rho) <= TOL and H.rel_err(H.from_dev_vec(eng.u), u) <= TOL
+    assert np.array_equal(H.from_dev_scalar(eng.rho), rho)
+    assert np.array_equal(H.from_dev_vec(eng.u), u)
+    assert np.array_equal(H.from_dev_pop(eng.populations), g)
 
 
 def test_physical_nonsquare_box_and_macro_every_k():
@@ -101,9 +107,10 @@ def _physical_v60_case(n, seed):
     return cfg, solid, zone, les_mask, phase, bf, u0, rho0
 
 
-@pytest.mark.parametrize("vec", [1, 4])
+@pytest.mark.parametrize("vec", [1, 2])
 @pytest.mark.parametrize("strict", [True, False])
 def test_physical_v60_full_features(vec, strict):
+    """vec = 2 is the packed f32x2 kernel (two cells per thread), vec = 1 the scalar fallback for odd nx."""
     n, steps = 32, 30
     cfg, solid, zone, les_mask, phase, bf, u0, rho0 = _physical_v60_case(n, 11)
     p = R.PhysParams(nx=n, ny=n, nz=n, tau_water=0.53, tau_air=0.8, gravity_lu=1e-5, periodic=(False, False, False),
@@ -121,13 +128,75 @@ def test_physical_v60_full_features(vec, strict):
     eng.step(steps)
     fluid = solid == 0
     gg = H.from_dev_pop(eng.populations); rr = H.from_dev_scalar(eng.rho); uu = H.from_dev_vec(eng.u)
-    if strict:
-        assert np.array_equal(gg[:, fluid], g[:, fluid])
-        assert np.array_equal(rr[fluid], rho[fluid])
-        assert np.array_equal(uu[fluid], u[fluid])
-    else:
-        H.assert_fast_build_close(rr[fluid], rho[fluid], 1.0, FAST_TOL, "rho")
-        H.assert_fast_build_close(uu[fluid], u[fluid], 0.02, FAST_TOL, "u")
+    assert np.array_equal(gg[:, fluid], g[:, fluid])
+    assert np.array_equal(rr[fluid], rho[fluid])
+    assert np.array_equal(uu[fluid], u[fluid])
+
+
+@pytest.mark.parametrize("periodic", [(True, True, True), (True, False, True), (False, False, False)])
+@pytest.mark.parametrize("nx", [32, 27])
+def test_physical_walls_obstacles_open_and_periodic_faces(periodic, nx):
+    """Write-side bounce-back, open-face inflow (w_q) and periodic wrap of the walls kernel: random obstacles that
+    touch the faces, ragged box, odd nx (scalar kernel) and even nx (packed kernel); moments-only pass at the end."""
+    ny, nz, steps = 20, 14, 25
+    rng = np.random.default_rng(5)
+    solid = (rng.random((nx, ny, nz)) < 0.12).astype(np.uint8)
+    solid[0:2, 3:9, :] = 1; solid[nx - 1, :, 2:5] = 1; solid[:, 0, 6:9] = 1; solid[5:9, 5:9, 0] = 1; solid[4:7, ny - 1, nz - 1] = 1
+    zone = (rng.random((nx, ny, nz)) < 0.1).astype(np.int32)
+    les_mask = (rng.random((nx, ny, nz)) < 0.8).astype(np.int32)
+    phase = (rng.random((nx, ny, nz)) < 0.5).astype(np.float32)
+    bf = (2e-5 * rng.standard_normal((nx, ny, nz, 3))).astype(np.float32)
+    u0 = H.smooth_velocity(nx, 0.02, 4, nz=nz, ny=ny); rho0 = H.smooth_density(nx, 0.01, 4, nz=nz, ny=ny)
+    p = R.PhysParams(nx=nx, ny=ny, nz=nz, tau_water=0.56, tau_air=0.8, gravity_lu=2e-5, periodic=periodic,
+                     use_force=True, use_phase=True, les=True, porous=True, porous_darcy=0.2, porous_forch=0.5)
+    g = R.init_equilibrium_phys(rho0, u0)
+    for _ in range(steps):
+        g, rho, u = R.step_physical(g, p, solid=solid, body_force=bf, phase=phase, filter_zone=zone, les_mask=les_mask)
+    eng = _engine(nx, ny, nz, compat="physical", periodic=periodic, walls=True, force=True, phase=True, les=True,
+                  porous=True, tau=0.56, tau_air=0.8, gravity_lu=2e-5, porous_darcy=0.2, porous_forch=0.5)
+    eng.solid.copy_(_torch(H.to_dev_scalar(solid))); eng.filter_zone.copy_(_torch(H.to_dev_scalar(zone)))
+    eng.les_mask.copy_(_torch(H.to_dev_scalar(les_mask))); eng.pack_flags()
+    eng.phase.copy_(_torch(H.to_dev_scalar(phase))); eng.body_force.copy_(_torch(H.to_dev_vec(bf)))
+    eng.init_equilibrium(rho=_torch(H.to_dev_scalar(rho0)), u=_torch(H.to_dev_vec(u0)))
+    eng.step(steps - 5)
+    eng.step(5, write_macro_every=0)
+    fluid = solid == 0
+    assert np.array_equal(H.from_dev_pop(eng.populations)[:, fluid], g[:, fluid])
+    # moments of the NEXT streamed state through lbm_macroscopic == what one more oracle step reports
+    _, rho1, u1 = R.step_physical(g, p, solid=solid, body_force=bf, phase=phase, filter_zone=zone, les_mask=les_mask)
+    eng.macroscopic()
+    assert np.array_equal(H.from_dev_scalar(eng.rho)[fluid], rho1[fluid])
+    assert np.array_equal(H.from_dev_vec(eng.u)[fluid], u1[fluid])
+
+
+def test_physical_walls_direct_population_write_needs_notification():
+    """Solid-cell slots of g are bounce-back scratch: after a direct write of the population buffer the caller
+    announces it (lbm_populations_changed) and the library rebuilds the slots before the next step."""
+    n, steps = 16, 6
+    rng = np.random.default_rng(9)
+    solid = (rng.random((n, n, n)) < 0.15).astype(np.uint8)
+    u0 = H.smooth_velocity(n, 0.02, 2); rho0 = H.smooth_density(n, 0.01, 2)
+    p = R.PhysParams(nx=n, ny=n, nz=n, tau_water=0.6, periodic=(True, True, True))
+    g0 = R.init_equilibrium_phys(rho0, u0)
+    g = g0
+    for _ in range(steps):
+        g, rho, u = R.step_physical(g, p, solid=solid)
+    eng = _engine(n, n, n, compat="physical", walls=True, tau=0.6)
+    eng.solid.copy_(_torch(H.to_dev_scalar(solid))); eng.pack_flags()
+    eng.step(3)                                                   # slots now valid for some other state
+    eng.populations.copy_(_torch(H.to_dev_pop(g0)))               # direct write: solid slots hold g0, not bounce copies
+    eng.populations_changed()
+    eng.step(steps)
+    fluid = solid == 0
+    assert np.array_equal(H.from_dev_pop(eng.populations)[:, fluid], g[:, fluid])
+
+
+def test_packed_reciprocal_and_sqrt_exhaustive():
+    """The packed (f32x2) correctly rounded 1/x and sqrt of the step kernel against the scalar IEEE intrinsics on all
+    2^32 bit patterns, both lanes; packed add/sub/mul/fma and the whole packed collision against the scalar operator
+    (lbm_selftest_math)."""
+    eng = _engine(8, 8, 8, compat="physical")
+    assert eng.selftest_math() == (0,) * 7
 
 
 # ------------------------------------------------------------------------------------------------

@@ -75,8 +75,48 @@ def test_ghost_plane_slab_equals_wrapped_single_slab(vec):
     assert torch.equal(a.rho, b.rho[1:-1]) and torch.equal(a.u, b.u[:, 1:-1])
 
 
+def test_ghost_plane_slab_with_walls_equals_wrapped_single_slab():
+    """Same as above behind walls (compat = physical): obstacles straddle the slab interface, so bounce-back slots
+    that live in the ghost planes are overwritten by every exchange and must be rebuilt (refresh after the halo)."""
+    import torch
+    n, steps = 32, 25
+    rng = np.random.default_rng(12)
+    solid = (rng.random((n, n, n)) < 0.1).astype(np.uint8)
+    solid[10:14, 10:14, 0:2] = 1; solid[20:24, 5:9, n - 2:] = 1
+    sd = torch.from_numpy(H.to_dev_scalar(solid)).cuda()
+    u0 = H.smooth_velocity(n, 0.03, 22); rho0 = H.smooth_density(n, 0.01, 22)
+    ru = torch.from_numpy(H.to_dev_scalar(rho0)).cuda(); uu = torch.from_numpy(H.to_dev_vec(u0)).cuda()
+    a = _engine(n, n, n, compat="physical", walls=True, les=True, tau=0.6)
+    a.solid.copy_(sd); a.pack_flags()
+    a.init_equilibrium(rho=ru, u=uu)
+    a.step(steps)
+    b = _engine(n, n, n, compat="physical", walls=True, les=True, tau=0.6, zghost=1, z0=0, nz_global=n)
+    b.solid[1:-1].copy_(sd); b.solid[0].copy_(sd[-1]); b.solid[-1].copy_(sd[0]); b.pack_flags()
+    pad = lambda t: torch.nn.functional.pad(t, (0, 0, 0, 0, 1, 1))
+    b.init_equilibrium(rho=pad(ru), u=pad(uu))
+    b.step(steps)
+    fluid = sd == 0
+    assert torch.equal(a.populations[:, fluid], b.populations[:, 1:-1][:, fluid])
+    assert torch.equal(a.rho[fluid], b.rho[1:-1][fluid]) and torch.equal(a.u[:, fluid], b.u[:, 1:-1][:, fluid])
+
+
 def test_strict_and_fast_builds_are_distinct_kernels():
-    """Guards against the two builds being merged at link time: FMA contraction must change some low bits."""
+    """compat = reference is built twice (-fmad=false / FMA contraction).  Guards against the two builds being
+    merged at link time: contraction must change some low bits.  (compat = physical has one build.)"""
+    import torch
+    n = 32
+    u0 = H.smooth_velocity(n, 0.05, 3); rho0 = H.smooth_density(n, 0.02, 3)
+    out = []
+    for strict in (True, False):
+        e = _engine(n, n, n, compat="reference", strict=strict, tau=0.8)
+        e.init_equilibrium(rho=torch.from_numpy(H.to_dev_scalar(rho0)).cuda(), u=torch.from_numpy(H.to_dev_vec(u0)).cuda())
+        e.step(20)
+        out.append(e.populations.clone())
+    assert not torch.equal(out[0], out[1])
+    assert float((out[0] - out[1]).abs().max()) < 1e-6
+
+
+def test_physical_ignores_strict_flag():
     import torch
     n = 32
     u0 = H.smooth_velocity(n, 0.05, 3); rho0 = H.smooth_density(n, 0.02, 3)
@@ -86,5 +126,4 @@ def test_strict_and_fast_builds_are_distinct_kernels():
         e.init_equilibrium(rho=torch.from_numpy(H.to_dev_scalar(rho0)).cuda(), u=torch.from_numpy(H.to_dev_vec(u0)).cuda())
         e.step(20)
         out.append(e.populations.clone())
-    assert not torch.equal(out[0], out[1])
-    assert float((out[0] - out[1]).abs().max()) < 1e-6
+    assert torch.equal(out[0], out[1])
