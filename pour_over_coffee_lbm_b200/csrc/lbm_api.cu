@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -19,7 +20,7 @@ DECL_LOOKUP(lookup_strict_g0_fn) DECL_LOOKUP(lookup_strict_g1_fn) DECL_LOOKUP(lo
 cudaError_t launch_init_equilibrium(const Grid &, int, float *, const float *, const float *, float, const float[3], cudaStream_t);
 cudaError_t launch_v60_geometry(const Grid &, uint8_t *, int32_t *, const float[5], cudaStream_t);
 cudaError_t launch_pack_flags(const Grid &, uint8_t *, const uint8_t *, const int32_t *, const int32_t *, cudaStream_t);
-cudaError_t build_work_lists(const Grid &, const uint8_t *, int, unsigned **, std::vector<int> &, unsigned long long **, cudaStream_t);
+cudaError_t build_work_lists(const Grid &, const uint8_t *, int, int, unsigned **, std::vector<int> &, unsigned long long **, cudaStream_t);
 cudaError_t launch_convert_f(const Grid &, bool, const float *, const uint8_t *, float *, cudaStream_t);
 cudaError_t launch_face_bc(const Grid &, float *, const uint8_t *, cudaStream_t, int *);
 cudaError_t launch_pressure_gradient(const Grid &, const float *, const uint8_t *, float *, float, float, cudaStream_t);
@@ -29,6 +30,13 @@ cudaError_t run_selftest_math(unsigned long long[7], const StepArgs &, cudaStrea
 cudaError_t launch_bounce_slots(const Grid &, float *, const uint8_t *, const unsigned long long *, int, int, cudaStream_t);
 cudaError_t launch_particles_couple(const Grid &, const float *, float *, const lbm_particles &, float, float, float, cudaStream_t);
 cudaError_t launch_particles_under_relax(const lbm_particles &, float, cudaStream_t);
+// TMA-staged walls kernels of compat = physical (lbm_step_tma.cu)
+struct TmaKernelInfo {
+    void (*kernel)(const StepArgs, const TmaMaps);
+    int ty, stages, threads, smem_bytes, ctas_per_sm;
+};
+int tma_variant_ty(int variant);
+bool lookup_tma(int forced, int les, int porous, int collide, int variant, TmaKernelInfo *out);
 }  // namespace lbm
 
 using namespace lbm;
@@ -89,6 +97,13 @@ struct lbm_ctx {
     // compat = physical, walls: the population buffer whose bounce-back slots (solid-cell slots next to fluid cells,
     // see lbm_phys.cuh) are known to be current; anything else gets them rebuilt before it is stepped
     const float *slots_valid = nullptr;
+    // TMA-staged walls path (lbm_phys_tma.cuh): tile height of the current list (1 = warp-tile list of the
+    // register-staged kernels), tuning variant, and the tensor maps of the field sets seen so far
+    int list_ty = 1;
+    int tma_variant = 0;
+    bool tma_disabled = false;
+    struct MapEntry { const float *pops, *force, *phase; const uint8_t *flags; int ty; TmaMaps maps; };
+    std::vector<MapEntry> maps;
 };
 
 static int fail(lbm_ctx *ctx, const std::string &msg) {
@@ -142,11 +157,81 @@ static int pick_block(const lbm_ctx *ctx, int vec) {
 
 static StepKernel lookup(const lbm_params &p, int vec, int collide, int *block);
 
-static int rebuild_lists(lbm_ctx *ctx, const uint8_t *flags, int vec, int block, cudaStream_t s) {
-    CUDA_OK(ctx, build_work_lists(ctx->g, flags, vec, &ctx->d_tiles, ctx->tile_off, &ctx->d_nbr, s));
+// The TMA-staged kernel serves compat = physical behind walls when the box does not wrap in x or y (the copy engine
+// zero-fills sources outside the tensor; a periodic wrap inside a box is not expressible), rows are 16-byte multiples
+// for every field incl. the u8 flags, and the caller left `vec` on auto (vec = 1 / 2 select the register-staged kernels).
+static bool tma_eligible(const lbm_ctx *ctx) {
+    const lbm_params &p = ctx->p;
+    return phys_walls(p) && !ctx->tma_disabled && p.vec == 0 && !(p.periodic & 3) && p.nx % 16 == 0 && p.nx >= 16;
+}
+static void feature_bits(const lbm_params &p, int *forced, int *les, int *porous) {
+    *forced = (p.features & (LBM_FEAT_FORCE | LBM_FEAT_PHASE)) != 0;
+    *les = (p.features & LBM_FEAT_LES) != 0;
+    *porous = (p.features & LBM_FEAT_POROUS) != 0;
+}
+// the tuning variants exist for the full-feature step kernel only: anything else runs variant 0
+static int tma_variant_for(const lbm_ctx *ctx) {
+    int forced, les, porous;
+    feature_bits(ctx->p, &forced, &les, &porous);
+    TmaKernelInfo k;
+    return lookup_tma(forced, les, porous, 1, ctx->tma_variant, &k) ? ctx->tma_variant : 0;
+}
+// tile height of the step kernel's work list: TY of the TMA variant, or 1 for the warp-tile list
+static int pick_ty(const lbm_ctx *ctx) { return tma_eligible(ctx) ? tma_variant_ty(tma_variant_for(ctx)) : 1; }
+
+static int rebuild_lists(lbm_ctx *ctx, const uint8_t *flags, int vec, int ty, int block, cudaStream_t s) {
+    CUDA_OK(ctx, build_work_lists(ctx->g, flags, vec, ty, &ctx->d_tiles, ctx->tile_off, &ctx->d_nbr, s));
     ctx->launches += 5;
-    ctx->list_flags = flags; ctx->list_vec = vec; ctx->list_block = block; ctx->window_set = false;
+    ctx->list_flags = flags; ctx->list_vec = vec; ctx->list_ty = ty; ctx->list_block = block; ctx->window_set = false;
     ctx->slots_valid = nullptr;
+    return 0;
+}
+
+// ---- tensor maps ------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+// [comps][nzp][ny][nx] field of `elem`-byte elements, box width x ty x 1 (x 1); comps = 0: no component dimension
+static int encode_map(lbm_ctx *ctx, CUtensorMap *m, const void *base, int elem, int comps, int ty, int width = 64) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return fail(ctx, "cuTensorMapEncodeTiled is not available from this driver");
+    if (((uintptr_t)base & 15u) != 0) return fail(ctx, "field pointers must be 16-byte aligned for the TMA-staged kernel (vec = 2 selects the register-staged one)");
+    const Grid &G = ctx->g;
+    const cuuint64_t nzp = (cuuint64_t)(G.nz + 2 * G.zg);
+    cuuint64_t dims[4] = {(cuuint64_t)G.nx, (cuuint64_t)G.ny, nzp, (cuuint64_t)(comps > 0 ? comps : 1)};
+    cuuint64_t strides[3] = {(cuuint64_t)G.nx * elem, (cuuint64_t)G.plane * elem, (cuuint64_t)G.vol * elem};
+    cuuint32_t box[4] = {(cuuint32_t)width, (cuuint32_t)ty, 1u, 1u};
+    cuuint32_t es[4] = {1u, 1u, 1u, 1u};
+    const CUresult r = enc(m, elem == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, comps > 0 ? 4u : 3u,
+                           const_cast<void *>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
+    return 0;
+}
+static int tensor_maps(lbm_ctx *ctx, const StepArgs &a, int ty, const TmaMaps **out) {
+    for (const auto &e : ctx->maps)
+        if (e.pops == a.src && e.force == a.force && e.phase == a.phase && e.flags == a.flags && e.ty == ty) { *out = &e.maps; return 0; }
+    if (ctx->maps.size() >= 16) ctx->maps.clear();
+    lbm_ctx::MapEntry e;
+    memset(&e.maps, 0, sizeof e.maps);
+    e.pops = a.src; e.force = a.force; e.phase = a.phase; e.flags = a.flags; e.ty = ty;
+    if (encode_map(ctx, &e.maps.pops, a.src, 4, Q, ty)) return 1;
+    if (encode_map(ctx, &e.maps.pops_wide, a.src, 4, Q, ty, 68)) return 1;
+    if (a.force && encode_map(ctx, &e.maps.force, a.force, 4, 3, ty)) return 1;
+    if (a.phase && encode_map(ctx, &e.maps.phase, a.phase, 4, 0, ty)) return 1;
+    if (encode_map(ctx, &e.maps.flags, a.flags, 1, 0, ty)) return 1;
+    ctx->maps.push_back(e);
+    *out = &ctx->maps.back().maps;
     return 0;
 }
 
@@ -175,6 +260,9 @@ int lbm_create(lbm_ctx **out, int device, const lbm_params *p) {
     ctx->max_window = (size_t)prop.accessPolicyMaxWindowSize;
     if (make_grid(nullptr, p, &ctx->g)) { delete ctx; return 1; }
     ctx->p = *p;
+    // tuning / diagnosis knobs of the TMA-staged walls path (scripts/tune_v60.py)
+    if (const char *v = getenv("LBM_TMA_VARIANT")) ctx->tma_variant = atoi(v);
+    if (const char *v = getenv("LBM_NO_TMA")) ctx->tma_disabled = atoi(v) != 0;
     CUDA_OK(nullptr, cudaSetDevice(device));
     cudaEventCreateWithFlags(&ctx->ev_boundary, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_comm, cudaEventDisableTiming);
@@ -190,7 +278,8 @@ int lbm_set_params(lbm_ctx *ctx, const lbm_params *p) {
         if (ctx->d_nbr) { cudaFree(ctx->d_nbr); ctx->d_nbr = nullptr; }
         ctx->list_flags = nullptr;
     }
-    if (p->vec != ctx->p.vec) ctx->list_flags = nullptr;
+    if (p->vec != ctx->p.vec || p->periodic != ctx->p.periodic || p->compat != ctx->p.compat || p->features != ctx->p.features) ctx->list_flags = nullptr;
+    ctx->maps.clear();
     if (p->compat != ctx->p.compat || p->periodic != ctx->p.periodic || p->features != ctx->p.features) ctx->slots_valid = nullptr;
     ctx->g = g; ctx->p = *p;
     return 0;
@@ -250,7 +339,7 @@ int lbm_pack_flags(lbm_ctx *ctx, uint8_t *flags, const uint8_t *solid, const int
     const int vec = pick_vec(ctx);
     int block = pick_block(ctx, vec);
     lookup(ctx->p, vec, 1, &block);                 // the CTA size the step kernel will really use
-    return rebuild_lists(ctx, flags, vec, block, (cudaStream_t)stream);
+    return rebuild_lists(ctx, flags, vec, pick_ty(ctx), block, (cudaStream_t)stream);
 }
 
 }  // extern "C"
@@ -301,15 +390,27 @@ struct Launcher {
     StepKernel main = nullptr;
     int block = 0, vec = 1;
     bool walls = false;
+    bool tma = false;          // TMA-staged persistent kernel (compat = physical behind walls)
+    TmaKernelInfo tk{};
 };
 
 static int make_launcher(lbm_ctx *ctx, const lbm_params &p, const lbm_fields *f, int vec, int collide, Launcher *L) {
     L->vec = vec;
     L->walls = (p.features & LBM_FEAT_WALLS) != 0;
     L->block = pick_block(ctx, vec);
-    L->main = lookup(p, vec, collide, &L->block);      // may fall back to the default CTA size for this variant
-    if (!L->main) return fail(ctx, "no step kernel built for this feature combination");
-    if (L->walls && (ctx->list_flags != f->flags || ctx->list_vec != vec || (int)ctx->tile_off.size() != ctx->g.nz + 1 || !ctx->d_nbr))
+    const int ty = pick_ty(ctx);
+    if (ty > 1) {
+        int forced, les, porous;
+        feature_bits(p, &forced, &les, &porous);
+        if (!lookup_tma(forced, les, porous, collide, tma_variant_for(ctx), &L->tk) || L->tk.ty != ty)
+            return fail(ctx, "no TMA-staged kernel built for this feature combination");
+        CUDA_OK(ctx, cudaFuncSetAttribute((const void *)L->tk.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L->tk.smem_bytes));
+        L->tma = true;
+    } else {
+        L->main = lookup(p, vec, collide, &L->block);      // may fall back to the default CTA size for this variant
+        if (!L->main) return fail(ctx, "no step kernel built for this feature combination");
+    }
+    if (L->walls && (ctx->list_flags != f->flags || ctx->list_vec != vec || ctx->list_ty != ty || (int)ctx->tile_off.size() != ctx->g.nz + 1 || !ctx->d_nbr))
         return fail(ctx, "work lists are stale: call lbm_pack_flags on this flags field (after any geometry or vec change)");
     return 0;
 }
@@ -326,9 +427,16 @@ static int launch_planes(lbm_ctx *ctx, StepArgs &a, const Launcher &L, int z_beg
         const int t0 = ctx->tile_off[z_begin], t1 = ctx->tile_off[z_end];
         if (t1 <= t0) return 0;
         a.items = ctx->d_tiles; a.item_begin = t0; a.n_items = t1 - t0; a.nbr = ctx->d_nbr;
-        const int warps_per_cta = L.block / 32;
-        const long long grid = (t1 - t0 + warps_per_cta - 1) / warps_per_cta;
-        L.main<<<(unsigned)grid, L.block, 0, s>>>(a);
+        if (L.tma) {
+            const TmaMaps *maps = nullptr;
+            if (tensor_maps(ctx, a, L.tk.ty, &maps)) return 1;
+            const int grid = std::min(t1 - t0, ctx->sm_count * L.tk.ctas_per_sm);      // persistent CTAs, tiles strided by gridDim
+            L.tk.kernel<<<(unsigned)grid, L.tk.threads, L.tk.smem_bytes, s>>>(a, *maps);
+        } else {
+            const int warps_per_cta = L.block / 32;
+            const long long grid = (t1 - t0 + warps_per_cta - 1) / warps_per_cta;
+            L.main<<<(unsigned)grid, L.block, 0, s>>>(a);
+        }
     }
     CUDA_OK(ctx, cudaGetLastError());
     ctx->launches++;
@@ -471,7 +579,7 @@ int lbm_macroscopic(lbm_ctx *ctx, const lbm_fields *f, void *stream) {
     const int vec = phys_walls(p) ? step_vec : 1;
     const bool relist = walls && vec != step_vec;
     Launcher L;
-    if (relist && rebuild_lists(ctx, f->flags, 1, 256, (cudaStream_t)stream)) return 1;
+    if (relist && rebuild_lists(ctx, f->flags, 1, 1, 256, (cudaStream_t)stream)) return 1;
     if (make_launcher(ctx, p, f, vec, 0, &L)) return 1;
     StepArgs a;
     if (fill_args(ctx, f, &a)) return 1;
@@ -482,7 +590,7 @@ int lbm_macroscopic(lbm_ctx *ctx, const lbm_fields *f, void *stream) {
     if (relist) {      // restore the lists of the step kernel
         int block = pick_block(ctx, step_vec);
         lookup(ctx->p, step_vec, 1, &block);
-        if (rebuild_lists(ctx, f->flags, step_vec, block, (cudaStream_t)stream)) return 1;
+        if (rebuild_lists(ctx, f->flags, step_vec, pick_ty(ctx), block, (cudaStream_t)stream)) return 1;
     }
     return rc;
 }

@@ -244,19 +244,22 @@ __global__ void add_reaction_kernel(Grid G, const float *reaction, const uint8_t
 }
 
 // ---- work list + neighbour masks for the step kernel ---------------------------------------------
-// warp-tile = 32*vec x-consecutive cells of one row of an owned plane; active when at least one cell is fluid.
-// id = (z*ny + y)*segs + seg, ascending ids follow memory order.
-__global__ void tile_flags_kernel(Grid G, const uint8_t *flags, int vec, int segs, uint8_t *tile_flag) {
+// tile = 32*vec x-consecutive cells of `ty` consecutive rows of an owned plane (ty = 1: one warp-tile of the
+// register-staged kernels; ty > 1: one CTA tile of the TMA-staged kernel); active when at least one cell is fluid.
+// id = (z*rows + y/ty)*segs + seg, ascending ids follow memory order.
+__global__ void tile_flags_kernel(Grid G, const uint8_t *flags, int vec, int ty, int rows, int segs, uint8_t *tile_flag) {
     const long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const long long n = (long long)G.nz * G.ny * segs;
+    const long long n = (long long)G.nz * rows * segs;
     if (id >= n) return;
     const int seg = (int)(id % segs);
-    const long long row = id / segs;               // z*ny + y
-    const int y = (int)(row % G.ny), z = (int)(row / G.ny);
+    const long long row = id / segs;               // z*rows + y/ty
+    const int y0 = (int)(row % rows) * ty, z = (int)(row / rows);
     const int xs = seg * 32 * vec, xe = min(G.nx, xs + 32 * vec);
-    const uint8_t *f = flags + ((long long)(z + G.zg) * G.ny + y) * G.nx;
     bool fluid = false;
-    for (int x = xs; x < xe; ++x) fluid |= !(f[x] & LBM_FLAG_SOLID);
+    for (int y = y0; y < min(G.ny, y0 + ty); ++y) {
+        const uint8_t *f = flags + ((long long)(z + G.zg) * G.ny + y) * G.nx;
+        for (int x = xs; x < xe; ++x) fluid |= !(f[x] & LBM_FLAG_SOLID);
+    }
     tile_flag[id] = fluid ? 1 : 0;
 }
 
@@ -270,12 +273,12 @@ __global__ void count_flagged_per_plane_kernel(const uint8_t *tile_flag, int per
     if (threadIdx.x == 0 && z < nz) plane_count[z] = tot;
 }
 
-__global__ void expand_tiles_kernel(const int *ids, int n, int ny, int segs, unsigned *out) {
+__global__ void expand_tiles_kernel(const int *ids, int n, int rows, int ty, int segs, unsigned *out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int id = ids[i];
     const int seg = id % segs, row = id / segs;
-    out[i] = (unsigned)seg | ((unsigned)(row % ny) << 8) | ((unsigned)(row / ny) << 20);
+    out[i] = (unsigned)seg | ((unsigned)((row % rows) * ty) << 8) | ((unsigned)(row / rows) << 20);
 }
 
 // per near-wall fluid cell: bit q of the low word = the source cell x - e_q is solid (bounce-back), bit q of the high
@@ -307,12 +310,13 @@ __global__ void neighbour_mask_kernel(Grid G, const uint8_t *flags, unsigned lon
 
 // Builds the active warp-tile list (device array allocated here, owned by the caller = lbm_ctx), its per-plane
 // offsets (host vector of nz+1 entries) and the neighbour masks.  Synchronises the stream: geometry changes are rare.
-cudaError_t build_work_lists(const Grid &G, const uint8_t *flags, int vec, unsigned **d_tiles, std::vector<int> &tile_off,
+cudaError_t build_work_lists(const Grid &G, const uint8_t *flags, int vec, int ty, unsigned **d_tiles, std::vector<int> &tile_off,
                              unsigned long long **d_nbr, cudaStream_t s) {
     cudaError_t e;
     const int segs = (G.nx + 32 * vec - 1) / (32 * vec);
-    if (segs > 256 || G.ny > 4096 || G.nz > 4096) return cudaErrorInvalidValue;      // packing limits of a list entry
-    const int per_plane = G.ny * segs;
+    if (segs > 256 || G.ny > 4096 || G.nz > 4096 || ty < 1) return cudaErrorInvalidValue;      // packing limits of a list entry
+    const int rows = (G.ny + ty - 1) / ty;
+    const int per_plane = rows * segs;
     const long long ntiles = (long long)per_plane * G.nz;
     uint8_t *tile_flag = nullptr; int *d_count = nullptr, *d_num = nullptr, *d_ids = nullptr; void *tmp = nullptr; size_t tmp_bytes = 0;
     if (!*d_nbr) { if ((e = cudaMalloc(d_nbr, sizeof(unsigned long long) * (size_t)G.vol)) != cudaSuccess) return e; }
@@ -320,7 +324,7 @@ cudaError_t build_work_lists(const Grid &G, const uint8_t *flags, int vec, unsig
     if ((e = cudaMalloc(&tile_flag, (size_t)ntiles)) != cudaSuccess) return e;
     if ((e = cudaMalloc(&d_count, sizeof(int) * (size_t)G.nz)) != cudaSuccess) return e;
     if ((e = cudaMalloc(&d_num, sizeof(int))) != cudaSuccess) return e;
-    tile_flags_kernel<<<(unsigned)((ntiles + 255) / 256), 256, 0, s>>>(G, flags, vec, segs, tile_flag);
+    tile_flags_kernel<<<(unsigned)((ntiles + 255) / 256), 256, 0, s>>>(G, flags, vec, ty, rows, segs, tile_flag);
     count_flagged_per_plane_kernel<<<G.nz, 256, 0, s>>>(tile_flag, per_plane, G.nz, d_count);
     std::vector<int> counts((size_t)G.nz);
     if ((e = cudaMemcpyAsync(counts.data(), d_count, sizeof(int) * counts.size(), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
@@ -336,7 +340,7 @@ cudaError_t build_work_lists(const Grid &G, const uint8_t *flags, int vec, unsig
     if ((e = cudaMalloc(&tmp, tmp_bytes)) != cudaSuccess) return e;
     if (n_t > 0) {
         cub::DeviceSelect::Flagged(tmp, tmp_bytes, idx, tile_flag, d_ids, d_num, (int)ntiles, s);
-        expand_tiles_kernel<<<(n_t + 255) / 256, 256, 0, s>>>(d_ids, n_t, G.ny, segs, *d_tiles);
+        expand_tiles_kernel<<<(n_t + 255) / 256, 256, 0, s>>>(d_ids, n_t, rows, ty, segs, *d_tiles);
     }
     e = cudaStreamSynchronize(s);
     cudaFree(tmp); cudaFree(tile_flag); cudaFree(d_count); cudaFree(d_num); cudaFree(d_ids);

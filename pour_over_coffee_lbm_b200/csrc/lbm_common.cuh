@@ -1,5 +1,6 @@
 // Shared device-side definitions for liblbm_b200 (sm_100a).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "../../include/lbm_b200.h"
@@ -60,6 +61,15 @@ __device__ __forceinline__ float edot(float vx, float vy, float vz) {
 __device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, float by, float bz) {
     return (ax * bx + ay * by) + az * bz;
 }
+
+// tensor maps of the TMA-staged walls kernel (lbm_phys_tma.cuh), passed as a __grid_constant__ kernel parameter
+struct alignas(64) TmaMaps {
+    CUtensorMap pops;      // f32 [19][nzp][ny][nx], box 64 x TY
+    CUtensorMap pops_wide; // same tensor, box 68 x TY (populations that move in x: one 16-byte halo)
+    CUtensorMap force;     // f32 [3][nzp][ny][nx]
+    CUtensorMap phase;     // f32 [nzp][ny][nx]
+    CUtensorMap flags;     // u8  [nzp][ny][nx]
+};
 
 template <int N> struct IC { static constexpr int value = N; };
 // compile-time loop: f(IC<0>{}), f(IC<1>{}), ...

@@ -107,10 +107,11 @@ def _physical_v60_case(n, seed):
     return cfg, solid, zone, les_mask, phase, bf, u0, rho0
 
 
-@pytest.mark.parametrize("vec", [1, 2])
+@pytest.mark.parametrize("vec", [0, 1, 2])
 @pytest.mark.parametrize("strict", [True, False])
 def test_physical_v60_full_features(vec, strict):
-    """vec = 2 is the packed f32x2 kernel (two cells per thread), vec = 1 the scalar fallback for odd nx."""
+    """vec = 0 (default) is the TMA-staged persistent kernel, vec = 2 the register-staged packed f32x2 kernel (two
+    cells per thread), vec = 1 the scalar fallback for odd nx."""
     n, steps = 32, 30
     cfg, solid, zone, les_mask, phase, bf, u0, rho0 = _physical_v60_case(n, 11)
     p = R.PhysParams(nx=n, ny=n, nz=n, tau_water=0.53, tau_air=0.8, gravity_lu=1e-5, periodic=(False, False, False),
@@ -133,15 +134,18 @@ def test_physical_v60_full_features(vec, strict):
     assert np.array_equal(uu[fluid], u[fluid])
 
 
-@pytest.mark.parametrize("periodic", [(True, True, True), (True, False, True), (False, False, False)])
-@pytest.mark.parametrize("nx", [32, 27])
+@pytest.mark.parametrize("periodic", [(True, True, True), (True, False, True), (False, False, False), (False, False, True)])
+@pytest.mark.parametrize("nx", [32, 27, 80])
 def test_physical_walls_obstacles_open_and_periodic_faces(periodic, nx):
-    """Write-side bounce-back, open-face inflow (w_q) and periodic wrap of the walls kernel: random obstacles that
-    touch the faces, ragged box, odd nx (scalar kernel) and even nx (packed kernel); moments-only pass at the end."""
-    ny, nz, steps = 20, 14, 25
+    """Write-side bounce-back, open-face inflow (w_q) and periodic wrap of the walls kernels: random obstacles that
+    touch the faces, ragged box, odd nx (scalar kernel) and even nx (packed kernel; TMA-staged kernel when x and y do
+    not wrap and nx % 16 == 0 -- nx = 80 gives it a partial second tile, ny = 22 a partial tile row); moments-only
+    pass at the end."""
+    ny, nz, steps = 22, 14, 25
     rng = np.random.default_rng(5)
     solid = (rng.random((nx, ny, nz)) < 0.12).astype(np.uint8)
     solid[0:2, 3:9, :] = 1; solid[nx - 1, :, 2:5] = 1; solid[:, 0, 6:9] = 1; solid[5:9, 5:9, 0] = 1; solid[4:7, ny - 1, nz - 1] = 1
+    solid[:, 12:16, 5] = 1                              # a whole tile row without fluid
     zone = (rng.random((nx, ny, nz)) < 0.1).astype(np.int32)
     les_mask = (rng.random((nx, ny, nz)) < 0.8).astype(np.int32)
     phase = (rng.random((nx, ny, nz)) < 0.5).astype(np.float32)
@@ -189,6 +193,38 @@ def test_physical_walls_direct_population_write_needs_notification():
     eng.step(steps)
     fluid = solid == 0
     assert np.array_equal(H.from_dev_pop(eng.populations)[:, fluid], g[:, fluid])
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5])
+def test_physical_tma_tuning_variants_bit_exact(variant, monkeypatch):
+    """The other tile shapes / ring depths of the TMA-staged kernel (LBM_TMA_VARIANT: 64x4, 64x8, 64x2 tiles, 3-6
+    stages) run the same operator: bit-exact as well.  More tiles than resident CTAs, so the ring wraps."""
+    monkeypatch.setenv("LBM_TMA_VARIANT", str(variant))
+    nx, ny, nz, steps = 128, 36, 40, 6
+    rng = np.random.default_rng(21)
+    solid = (rng.random((nx, ny, nz)) < 0.1).astype(np.uint8)
+    solid[0] = 1; solid[-1] = 1; solid[:, 0] = 1; solid[:, -1] = 1; solid[:, :, 0] = 1
+    zone = (rng.random((nx, ny, nz)) < 0.1).astype(np.int32)
+    les_mask = (rng.random((nx, ny, nz)) < 0.8).astype(np.int32)
+    phase = (rng.random((nx, ny, nz)) < 0.5).astype(np.float32)
+    bf = (2e-5 * rng.standard_normal((nx, ny, nz, 3))).astype(np.float32)
+    u0 = H.smooth_velocity(nx, 0.02, 4, nz=nz, ny=ny); rho0 = H.smooth_density(nx, 0.01, 4, nz=nz, ny=ny)
+    p = R.PhysParams(nx=nx, ny=ny, nz=nz, tau_water=0.56, tau_air=0.8, gravity_lu=2e-5, periodic=(False, False, False),
+                     use_force=True, use_phase=True, les=True, porous=True, porous_darcy=0.2, porous_forch=0.5)
+    g = R.init_equilibrium_phys(rho0, u0)
+    for _ in range(steps):
+        g, rho, u = R.step_physical(g, p, solid=solid, body_force=bf, phase=phase, filter_zone=zone, les_mask=les_mask)
+    eng = _engine(nx, ny, nz, compat="physical", periodic=(False, False, False), walls=True, force=True, phase=True, les=True,
+                  porous=True, tau=0.56, tau_air=0.8, gravity_lu=2e-5, porous_darcy=0.2, porous_forch=0.5)
+    eng.solid.copy_(_torch(H.to_dev_scalar(solid))); eng.filter_zone.copy_(_torch(H.to_dev_scalar(zone)))
+    eng.les_mask.copy_(_torch(H.to_dev_scalar(les_mask))); eng.pack_flags()
+    eng.phase.copy_(_torch(H.to_dev_scalar(phase))); eng.body_force.copy_(_torch(H.to_dev_vec(bf)))
+    eng.init_equilibrium(rho=_torch(H.to_dev_scalar(rho0)), u=_torch(H.to_dev_vec(u0)))
+    eng.step(steps)
+    fluid = solid == 0
+    assert np.array_equal(H.from_dev_pop(eng.populations)[:, fluid], g[:, fluid])
+    assert np.array_equal(H.from_dev_scalar(eng.rho)[fluid], rho[fluid])
+    assert np.array_equal(H.from_dev_vec(eng.u)[fluid], u[fluid])
 
 
 def test_packed_reciprocal_and_sqrt_exhaustive():

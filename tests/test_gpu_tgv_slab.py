@@ -75,9 +75,11 @@ def test_ghost_plane_slab_equals_wrapped_single_slab(vec):
     assert torch.equal(a.rho, b.rho[1:-1]) and torch.equal(a.u, b.u[:, 1:-1])
 
 
-def test_ghost_plane_slab_with_walls_equals_wrapped_single_slab():
+@pytest.mark.parametrize("periodic", [(True, True, True), (False, False, True)])
+def test_ghost_plane_slab_with_walls_equals_wrapped_single_slab(periodic):
     """Same as above behind walls (compat = physical): obstacles straddle the slab interface, so bounce-back slots
-    that live in the ghost planes are overwritten by every exchange and must be rebuilt (refresh after the halo)."""
+    that live in the ghost planes are overwritten by every exchange and must be rebuilt (refresh after the halo).
+    x/y periodic runs the register-staged kernel, x/y open the TMA-staged one (ghost planes = tensor planes 0, nz+1)."""
     import torch
     n, steps = 32, 25
     rng = np.random.default_rng(12)
@@ -86,11 +88,11 @@ def test_ghost_plane_slab_with_walls_equals_wrapped_single_slab():
     sd = torch.from_numpy(H.to_dev_scalar(solid)).cuda()
     u0 = H.smooth_velocity(n, 0.03, 22); rho0 = H.smooth_density(n, 0.01, 22)
     ru = torch.from_numpy(H.to_dev_scalar(rho0)).cuda(); uu = torch.from_numpy(H.to_dev_vec(u0)).cuda()
-    a = _engine(n, n, n, compat="physical", walls=True, les=True, tau=0.6)
+    a = _engine(n, n, n, compat="physical", walls=True, les=True, tau=0.6, periodic=periodic)
     a.solid.copy_(sd); a.pack_flags()
     a.init_equilibrium(rho=ru, u=uu)
     a.step(steps)
-    b = _engine(n, n, n, compat="physical", walls=True, les=True, tau=0.6, zghost=1, z0=0, nz_global=n)
+    b = _engine(n, n, n, compat="physical", walls=True, les=True, tau=0.6, zghost=1, z0=0, nz_global=n, periodic=periodic)
     b.solid[1:-1].copy_(sd); b.solid[0].copy_(sd[-1]); b.solid[-1].copy_(sd[0]); b.pack_flags()
     pad = lambda t: torch.nn.functional.pad(t, (0, 0, 0, 0, 1, 1))
     b.init_equilibrium(rho=pad(ru), u=pad(uu))
