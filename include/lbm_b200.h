@@ -148,6 +148,11 @@ int  lbm_import_f(lbm_ctx *ctx, const float *f_in, const uint8_t *flags, float *
  * body_force += scale * clamp(-cs^2 grad(rho)/rho, max_force) on fluid cells. */
 int  lbm_pressure_gradient_force(lbm_ctx *ctx, const float *rho, const uint8_t *flags, float *body_force,
                                  float max_force, float scale, void *stream);
+/* Same force WRITTEN to body_force on fluid cells (solid cells untouched: the step kernel never reads them): replaces
+ * LBMSolver.clear_body_force (legacy/lbm_solver.py:656-660) + the accumulation above when the drive is the only
+ * producer of the step, and saves the full-grid clear pass. */
+int  lbm_pressure_gradient_force_set(lbm_ctx *ctx, const float *rho, const uint8_t *flags, float *body_force,
+                                     float max_force, float scale, void *stream);
 /* FilterPaperSystem.compute_forchheimer_resistance filter_paper.py:471-536: body_force += F_drag. */
 int  lbm_forchheimer_force(lbm_ctx *ctx, const float *u, const uint8_t *flags, float *body_force,
                            float fmax, void *stream);

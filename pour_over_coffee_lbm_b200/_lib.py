@@ -63,6 +63,7 @@ SIGNATURES = {
     "lbm_export_f": (C.c_int, [_P, _P, _P, _P, _P]),
     "lbm_import_f": (C.c_int, [_P, _P, _P, _P, _P]),
     "lbm_pressure_gradient_force": (C.c_int, [_P, _P, _P, _P, C.c_float, C.c_float, _P]),
+    "lbm_pressure_gradient_force_set": (C.c_int, [_P, _P, _P, _P, C.c_float, C.c_float, _P]),
     "lbm_forchheimer_force": (C.c_int, [_P, _P, _P, _P, C.c_float, _P]),
     "lbm_add_reaction_force": (C.c_int, [_P, _P, _P, _P, _P]),
     "lbm_particles_couple": (C.c_int, [_P, _P, _P, C.POINTER(LbmParticles), C.c_float, C.c_float, C.c_float, _P]),

@@ -20,10 +20,10 @@ DECL_LOOKUP(lookup_strict_g0_fn) DECL_LOOKUP(lookup_strict_g1_fn) DECL_LOOKUP(lo
 cudaError_t launch_init_equilibrium(const Grid &, int, float *, const float *, const float *, float, const float[3], cudaStream_t);
 cudaError_t launch_v60_geometry(const Grid &, uint8_t *, int32_t *, const float[5], cudaStream_t);
 cudaError_t launch_pack_flags(const Grid &, uint8_t *, const uint8_t *, const int32_t *, const int32_t *, cudaStream_t);
-cudaError_t build_work_lists(const Grid &, const uint8_t *, int, int, unsigned **, std::vector<int> &, unsigned long long **, cudaStream_t);
+cudaError_t build_work_lists(const Grid &, const uint8_t *, int, int, unsigned **, unsigned **, std::vector<int> &, unsigned long long **, cudaStream_t);
 cudaError_t launch_convert_f(const Grid &, bool, const float *, const uint8_t *, float *, cudaStream_t);
 cudaError_t launch_face_bc(const Grid &, float *, const uint8_t *, cudaStream_t, int *);
-cudaError_t launch_pressure_gradient(const Grid &, const float *, const uint8_t *, float *, float, float, cudaStream_t);
+cudaError_t launch_pressure_gradient(const Grid &, const float *, const uint8_t *, float *, float, float, int, cudaStream_t);
 cudaError_t launch_forchheimer_force(const Grid &, const float *, const uint8_t *, float *, float, float, float, float, float, cudaStream_t);
 cudaError_t launch_add_reaction(const Grid &, const float *, const uint8_t *, float *, cudaStream_t);
 cudaError_t run_selftest_math(unsigned long long[7], const StepArgs &, cudaStream_t);
@@ -88,6 +88,7 @@ struct lbm_ctx {
     cudaEvent_t ev_boundary = nullptr, ev_comm = nullptr;
     // work lists of the walls path (built by lbm_pack_flags for the flag field it packed)
     unsigned *d_tiles = nullptr;               // active warp-tiles, packed x_segment | y << 8 | z << 20
+    unsigned *d_tile_mask = nullptr;           // per warp-tile: lanes that must load (VEC = 4 walls kernel)
     cudaStream_t window_stream = nullptr; bool window_set = false;
     unsigned long long *d_nbr = nullptr;       // neighbour masks [vol]
     int list_block = 0;
@@ -101,7 +102,7 @@ struct lbm_ctx {
     // register-staged kernels), tuning variant, and the tensor maps of the field sets seen so far
     int list_ty = 1;
     int tma_variant = 0;
-    bool tma_disabled = false;
+    bool tma_enabled = false;                 // opt-in (LBM_TMA=1): measured slower than the VEC = 4 register-staged kernel
     struct MapEntry { const float *pops, *force, *phase; const uint8_t *flags; int ty; TmaMaps maps; };
     std::vector<MapEntry> maps;
 };
@@ -131,12 +132,17 @@ static int make_grid(lbm_ctx *ctx, const lbm_params *p, Grid *g) {
 
 static bool phys_walls(const lbm_params &p) { return p.compat == LBM_COMPAT_PHYSICAL && (p.features & LBM_FEAT_WALLS); }
 
+static bool tma_eligible(const lbm_ctx *ctx);
+
 static int pick_vec(const lbm_ctx *ctx) {
     int vec = ctx->p.vec;
     if (phys_walls(ctx->p)) {
-        // two cells per thread on packed f32x2 registers (lbm_phys.cuh); one when the rows are not 8-byte aligned
-        if (vec != 1) vec = 2;
-        if (ctx->g.nx % 2 != 0 || ctx->g.nx < 4) vec = 1;
+        // two cells per thread on packed f32x2 registers (lbm_phys.cuh) on 8-byte rows, else one.  vec = 4 (128-bit
+        // loads, lane masks) and the TMA-staged kernel (LBM_TMA=1) are opt-in: measured on B200 they
+        // win on all-fluid boxes (vec = 4) or by 4 % on the V60 mask (TMA) but not across the board.
+        if (vec == 0) vec = 2;      // also what the TMA-staged kernel works on (64-cell rows, two cells per lane)
+        if (vec == 4 && (ctx->g.nx % 4 != 0 || ctx->g.nx < 8)) vec = 2;
+        if (vec == 2 && (ctx->g.nx % 2 != 0 || ctx->g.nx < 4)) vec = 1;
         return vec;
     }
     // 128-bit path for dense periodic boxes (99 % of the copy bandwidth); compat = reference behind a flag field
@@ -162,7 +168,7 @@ static StepKernel lookup(const lbm_params &p, int vec, int collide, int *block);
 // for every field incl. the u8 flags, and the caller left `vec` on auto (vec = 1 / 2 select the register-staged kernels).
 static bool tma_eligible(const lbm_ctx *ctx) {
     const lbm_params &p = ctx->p;
-    return phys_walls(p) && !ctx->tma_disabled && p.vec == 0 && !(p.periodic & 3) && p.nx % 16 == 0 && p.nx >= 16;
+    return phys_walls(p) && ctx->tma_enabled && p.vec == 0 && !(p.periodic & 3) && p.nx % 16 == 0 && p.nx >= 16;
 }
 static void feature_bits(const lbm_params &p, int *forced, int *les, int *porous) {
     *forced = (p.features & (LBM_FEAT_FORCE | LBM_FEAT_PHASE)) != 0;
@@ -180,8 +186,8 @@ static int tma_variant_for(const lbm_ctx *ctx) {
 static int pick_ty(const lbm_ctx *ctx) { return tma_eligible(ctx) ? tma_variant_ty(tma_variant_for(ctx)) : 1; }
 
 static int rebuild_lists(lbm_ctx *ctx, const uint8_t *flags, int vec, int ty, int block, cudaStream_t s) {
-    CUDA_OK(ctx, build_work_lists(ctx->g, flags, vec, ty, &ctx->d_tiles, ctx->tile_off, &ctx->d_nbr, s));
-    ctx->launches += 5;
+    CUDA_OK(ctx, build_work_lists(ctx->g, flags, vec, ty, &ctx->d_tiles, &ctx->d_tile_mask, ctx->tile_off, &ctx->d_nbr, s));
+    ctx->launches += 6;
     ctx->list_flags = flags; ctx->list_vec = vec; ctx->list_ty = ty; ctx->list_block = block; ctx->window_set = false;
     ctx->slots_valid = nullptr;
     return 0;
@@ -214,7 +220,7 @@ static int encode_map(lbm_ctx *ctx, CUtensorMap *m, const void *base, int elem, 
     cuuint32_t es[4] = {1u, 1u, 1u, 1u};
     const CUresult r = enc(m, elem == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, comps > 0 ? 4u : 3u,
                            const_cast<void *>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                           width == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(ctx, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
     return 0;
 }
@@ -262,7 +268,7 @@ int lbm_create(lbm_ctx **out, int device, const lbm_params *p) {
     ctx->p = *p;
     // tuning / diagnosis knobs of the TMA-staged walls path (scripts/tune_v60.py)
     if (const char *v = getenv("LBM_TMA_VARIANT")) ctx->tma_variant = atoi(v);
-    if (const char *v = getenv("LBM_NO_TMA")) ctx->tma_disabled = atoi(v) != 0;
+    if (const char *v = getenv("LBM_TMA")) ctx->tma_enabled = atoi(v) != 0;
     CUDA_OK(nullptr, cudaSetDevice(device));
     cudaEventCreateWithFlags(&ctx->ev_boundary, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_comm, cudaEventDisableTiming);
@@ -291,6 +297,7 @@ void lbm_destroy(lbm_ctx *ctx) {
     if (ctx->ev_boundary) cudaEventDestroy(ctx->ev_boundary);
     if (ctx->ev_comm) cudaEventDestroy(ctx->ev_comm);
     if (ctx->d_tiles) cudaFree(ctx->d_tiles);
+    if (ctx->d_tile_mask) cudaFree(ctx->d_tile_mask);
     if (ctx->d_nbr) cudaFree(ctx->d_nbr);
     delete ctx;
 }
@@ -426,7 +433,7 @@ static int launch_planes(lbm_ctx *ctx, StepArgs &a, const Launcher &L, int z_beg
     } else {
         const int t0 = ctx->tile_off[z_begin], t1 = ctx->tile_off[z_end];
         if (t1 <= t0) return 0;
-        a.items = ctx->d_tiles; a.item_begin = t0; a.n_items = t1 - t0; a.nbr = ctx->d_nbr;
+        a.items = ctx->d_tiles; a.item_mask = ctx->d_tile_mask; a.item_begin = t0; a.n_items = t1 - t0; a.nbr = ctx->d_nbr;
         if (L.tma) {
             const TmaMaps *maps = nullptr;
             if (tensor_maps(ctx, a, L.tk.ty, &maps)) return 1;
@@ -620,7 +627,14 @@ int lbm_import_f(lbm_ctx *ctx, const float *f_in, const uint8_t *flags, float *g
 
 int lbm_pressure_gradient_force(lbm_ctx *ctx, const float *rho, const uint8_t *flags, float *body_force, float max_force, float scale, void *stream) {
     if (!ctx || !rho || !body_force) return fail(ctx, "null argument");
-    CUDA_OK(ctx, launch_pressure_gradient(ctx->g, rho, flags, body_force, max_force, scale, (cudaStream_t)stream));
+    CUDA_OK(ctx, launch_pressure_gradient(ctx->g, rho, flags, body_force, max_force, scale, 1, (cudaStream_t)stream));
+    ctx->launches++;
+    return 0;
+}
+
+int lbm_pressure_gradient_force_set(lbm_ctx *ctx, const float *rho, const uint8_t *flags, float *body_force, float max_force, float scale, void *stream) {
+    if (!ctx || !rho || !body_force) return fail(ctx, "null argument");
+    CUDA_OK(ctx, launch_pressure_gradient(ctx->g, rho, flags, body_force, max_force, scale, 0, (cudaStream_t)stream));
     ctx->launches++;
     return 0;
 }

@@ -40,6 +40,7 @@ struct StepArgs {
     int z_begin, z_end;    // owned planes processed by this launch (dense mode)
     const unsigned *items; // bulk mode: active warp-tiles (32*VEC x-consecutive cells): x_segment | y << 8 | z << 20
     int item_begin, n_items;
+    const unsigned *item_mask;   // VEC = 4 walls kernel: per list entry, the lanes that must load (lbm_phys.cuh)
     const unsigned long long *nbr;     // per cell (valid where NEAR): solid-source bits | out-of-box bits << 32
     int write_macro;
     float tau_water, tau_air, gravity_lu;

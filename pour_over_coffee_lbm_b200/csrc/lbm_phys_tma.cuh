@@ -8,7 +8,7 @@
 //
 //   * persistent CTAs (a few per SM); each walks the active-tile list with stride gridDim.x.  A tile is 64 x TY cells
 //     (64 x-consecutive cells of TY consecutive rows of one plane) that contains at least one fluid cell;
-//   * one PRODUCER warp per CTA (one elected lane) issues, per tile, 19 + 3 + 1 + 1 tensor-map TMA loads
+//   * NP PRODUCER warps per CTA (one elected lane each) issue, per tile, 19 + 3 + 1 + 1 tensor-map TMA loads
 //     (cp.async.bulk.tensor): population q as the box of rows (y0 - cy, z - cz) -- the y/z part of the pull shift is
 //     done by the copy engine, OUT-OF-BOX sources arrive as zeros and are replaced by the open-face rule -- then the
 //     body force, the phase field and the flag bytes.  The x part cannot be: in tiled mode the innermost start
@@ -66,19 +66,52 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
         "DONE_%=:\n"
         "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
-// streaming data: every byte is read once -> evict-first in L2 (createpolicy-equivalent constant used by CUTLASS)
-constexpr unsigned long long TMA_EVICT_FIRST = 0x12F0000000000000ull;
+// no L2 eviction hint: the 16-byte halo sectors of the 68-wide boxes are shared with the x-neighbour tile, which another
+// CTA loads at about the same time
 __device__ __forceinline__ void tma_load_4d(unsigned dst, const CUtensorMap *map, unsigned bar, int c0, int c1, int c2, int c3) {
-    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
-                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(TMA_EVICT_FIRST) : "memory");
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap *map, unsigned bar, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                  ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
-template <bool FORCED, bool LES, bool POROUS, int TY, int STAGES, bool COLLIDE, int MINB>
-__global__ void __launch_bounds__((TY + 1) * 32, MINB) phys_tma_kernel(const __grid_constant__ StepArgs P, const __grid_constant__ TmaMaps M) {
+// One producer warp's share of a tile's loads: request r (0..18 populations, 19..21 force, 22 phase, 23 flags) belongs to
+// producer r % NP.  A single warp needs ~1 us to issue all 24 (each UTMALDG drags ~12 dependent uniform-datapath
+// instructions behind it), which starved the consumers in the first version (ncu: 17 % of all stall samples on the
+// full-barrier wait); NP warps issue their shares concurrently and each arrives once on the full barrier.
+template <int TY, int NP, int PIDX>
+__device__ __forceinline__ void tma_produce(unsigned base, unsigned full, const TmaMaps &M, int x0, int y0, int zc, int zlo, int zhi,
+                                            bool use_force, bool use_phase) {
+    using S = TmaStage<TY>;
+    unsigned tx = 0;
+    static_for<0, Q>([&](auto qq) {
+        constexpr int q = decltype(qq)::value;
+        if constexpr (q % NP == PIDX) tx += cx(q) != 0 ? S::BOXW : S::BOX;
+    });
+#pragma unroll
+    for (int c = 0; c < 3; ++c) if ((Q + c) % NP == PIDX && use_force) tx += S::BOX;
+    if ((Q + 3) % NP == PIDX && use_phase) tx += S::BOX;
+    if ((Q + 4) % NP == PIDX) tx += S::FLAG_BOX;
+    mbar_expect_tx(full, tx);
+    static_for<0, Q>([&](auto qq) {
+        constexpr int q = decltype(qq)::value;
+        if constexpr (q % NP == PIDX) {
+            const int zq = cz(q) > 0 ? zlo : (cz(q) < 0 ? zhi : zc);
+            if constexpr (cx(q) == 0) tma_load_4d(base + S::off_q(q), &M.pops, full, x0, y0 - cy(q), zq, q);
+            else tma_load_4d(base + S::off_q(q), &M.pops_wide, full, cx(q) > 0 ? x0 - 4 : x0, y0 - cy(q), zq, q);
+        }
+    });
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+        if ((Q + c) % NP == PIDX && use_force) tma_load_4d(base + S::OFF_FORCE + c * S::BOX, &M.force, full, x0, y0, zc, c);
+    if ((Q + 3) % NP == PIDX && use_phase) tma_load_3d(base + S::OFF_PHASE, &M.phase, full, x0, y0, zc);
+    if ((Q + 4) % NP == PIDX) tma_load_3d(base + S::OFF_FLAGS, &M.flags, full, x0, y0, zc);
+}
+
+template <bool FORCED, bool LES, bool POROUS, int TY, int STAGES, bool COLLIDE, int MINB, int NP>
+__global__ void __launch_bounds__((TY + NP) * 32, MINB) phys_tma_kernel(const __grid_constant__ StepArgs P, const __grid_constant__ TmaMaps M) {
     using V = P2;
     using O = Ops<V>;
     using S = TmaStage<TY>;
@@ -94,7 +127,7 @@ __global__ void __launch_bounds__((TY + 1) * 32, MINB) phys_tma_kernel(const __g
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(smem_u32(bars + s), 1);                 // producer's arrive.expect_tx (+ the bytes)
+            mbar_init(smem_u32(bars + s), NP);                // each producer's arrive.expect_tx (+ the bytes)
             mbar_init(smem_u32(bars + STAGES + s), TY);       // one arrival per consumer warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -106,9 +139,9 @@ __global__ void __launch_bounds__((TY + 1) * 32, MINB) phys_tma_kernel(const __g
     const bool use_force = FORCED && P.force != nullptr;
     const bool use_phase = FORCED && P.phase != nullptr;
 
-    if (warp == TY) {
-        // ---------------- producer ----------------
-        const unsigned tx_bytes = (unsigned)(S::POP_TX_BYTES + (use_force ? 3 * S::BOX : 0) + (use_phase ? S::BOX : 0) + S::FLAG_BOX);
+    if (warp >= TY) {
+        // ---------------- producers ----------------
+        const int pidx = warp - TY;
         unsigned e_next = n_my > 0 ? __ldg(items) : 0u;
         for (int i = 0; i < n_my; ++i) {
             const int st = i % STAGES;
@@ -118,10 +151,8 @@ __global__ void __launch_bounds__((TY + 1) * 32, MINB) phys_tma_kernel(const __g
             const int x0 = (int)(e & 0xffu) * TMA_TX, y0 = (int)((e >> 8) & 0xfffu), z = (int)(e >> 20);
             const unsigned full = smem_u32(bars + st);
             const unsigned base = smem_u32(smem + st * S::BYTES);
-            // UTMALDG is a warp-uniform instruction that must be issued by ONE thread: with several active lanes (ptxas
-            // wraps divergent operands in an ELECT / R2UR.BROADCAST loop) the B200 raises "illegal instruction"
+            // UTMALDG is a warp-uniform instruction: issued by ONE thread per producer warp
             if (lane == 0) {
-                mbar_expect_tx(full, tx_bytes);
                 const int zc = z + G.zg;
                 int zlo = z - 1, zhi = z + 1;      // single slab: wrap in z, or leave the box (zero fill -> open-face rule)
                 if (!G.zg) {
@@ -129,18 +160,10 @@ __global__ void __launch_bounds__((TY + 1) * 32, MINB) phys_tma_kernel(const __g
                     if (zhi >= G.nz) zhi = G.per_z ? 0 : G.nz;
                 }
                 zlo += G.zg; zhi += G.zg;
-                static_for<0, Q>([&](auto qq) {
-                    constexpr int q = decltype(qq)::value;
-                    const int zq = cz(q) > 0 ? zlo : (cz(q) < 0 ? zhi : zc);
-                    if constexpr (cx(q) == 0) tma_load_4d(base + S::off_q(q), &M.pops, full, x0, y0 - cy(q), zq, q);
-                    else tma_load_4d(base + S::off_q(q), &M.pops_wide, full, cx(q) > 0 ? x0 - 4 : x0, y0 - cy(q), zq, q);
+                static_for<0, NP>([&](auto pp) {
+                    constexpr int PIDX = decltype(pp)::value;
+                    if (pidx == PIDX) tma_produce<TY, NP, PIDX>(base, full, M, x0, y0, zc, zlo, zhi, use_force, use_phase);
                 });
-                if (use_force) {
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) tma_load_4d(base + S::OFF_FORCE + c * S::BOX, &M.force, full, x0, y0, zc, c);
-                }
-                if (use_phase) tma_load_3d(base + S::OFF_PHASE, &M.phase, full, x0, y0, zc);
-                tma_load_3d(base + S::OFF_FLAGS, &M.flags, full, x0, y0, zc);
             }
             __syncwarp();
         }

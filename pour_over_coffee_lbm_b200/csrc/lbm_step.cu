@@ -36,7 +36,7 @@ static StepKernel pick() {
     if constexpr (POROUS && !G_WALLS) return nullptr;          // the filter zone lives in the flag byte
     else if constexpr (!COLLIDE && LES) return nullptr;
     else if constexpr (G_WALLS && G_COMPAT == LBM_COMPAT_PHYSICAL) {
-        if constexpr (VEC == 4) return nullptr;
+        if constexpr (VEC == 4) return phys_walls4_kernel<FORCED, LES, POROUS, BLOCK, COLLIDE, min_blocks<VEC, BLOCK>()>;
         else return phys_walls_kernel<FORCED, LES, POROUS, VEC, BLOCK, COLLIDE, min_blocks<VEC, BLOCK>()>;
     }
     else if constexpr (VEC == 2) return nullptr;
@@ -70,15 +70,19 @@ static StepKernel pick_feat(int forced, int les, int porous) {
 // Tuning set (physical walls group, every feature on = the V60 config): VEC x BLOCK.
 template <int VEC, int BLOCK>
 static StepKernel tuned() {
-    if constexpr (G_WALLS && G_COMPAT == LBM_COMPAT_PHYSICAL)
-        return phys_walls_kernel<true, true, true, VEC, BLOCK, true, min_blocks<VEC, BLOCK>()>;
-    else return nullptr;
+    if constexpr (G_WALLS && G_COMPAT == LBM_COMPAT_PHYSICAL) {
+        // tuning set: BLOCK = 128 / 256 run with 384 / 256 resident threads per SM (168 / 255 registers, no spills)
+        if constexpr (VEC == 4) return phys_walls4_kernel<true, true, true, BLOCK, true, (BLOCK == 128 ? 3 : (BLOCK == 256 ? 1 : min_blocks<VEC, BLOCK>()))>;
+        else return phys_walls_kernel<true, true, true, VEC, BLOCK, true, min_blocks<VEC, BLOCK>()>;
+    } else return nullptr;
 }
 static StepKernel pick_tuned(int vec, int block) {
     switch (vec * 1000 + block) {
         case 1128: return tuned<1, 128>();
         case 2128: return tuned<2, 128>();
         case 2256: return tuned<2, 256>();
+        case 4128: return tuned<4, 128>();
+        case 4256: return tuned<4, 256>();
         default: return nullptr;
     }
 }
@@ -99,7 +103,8 @@ StepKernel LBM_LOOKUP(int forced, int les, int porous, int vec, int collide, int
         else if (vec == 2) k = pick_feat<MAIN, 2, true>(forced, les, porous);
         else if (vec == 1) k = pick_feat<MAIN, 1, true>(forced, les, porous);
     } else {
-        if (vec == 2) k = pick_feat<MAIN, 2, false>(forced, false, porous);
+        if (vec == 4 && G_WALLS && G_COMPAT == LBM_COMPAT_PHYSICAL) k = pick_feat<MAIN, 4, false>(forced, false, porous);
+        else if (vec == 2) k = pick_feat<MAIN, 2, false>(forced, false, porous);
         else if (vec == 1) k = pick_feat<MAIN, 1, false>(forced, false, porous);
     }
     *block = def_block;

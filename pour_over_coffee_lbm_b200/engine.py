@@ -247,6 +247,12 @@ class D3Q19Engine:
         self._check(self.lib.lbm_pressure_gradient_force(self._ctx, _ptr(self.rho), _ptr(self.flags), _ptr(self.body_force),
                                                          float(max_force), float(scale), self.stream), "lbm_pressure_gradient_force")
 
+    def set_pressure_gradient_force(self, max_force: float = 0.12, scale: float = 1.0):
+        """clear_body_force() + add_pressure_gradient_force() on the fluid cells in one pass (solid cells keep their
+        old body_force, which no kernel reads)."""
+        self._check(self.lib.lbm_pressure_gradient_force_set(self._ctx, _ptr(self.rho), _ptr(self.flags), _ptr(self.body_force),
+                                                             float(max_force), float(scale), self.stream), "lbm_pressure_gradient_force_set")
+
     def add_forchheimer_force(self, fmax: Optional[float] = None):
         fmax = 0.01 * self.cfg.SCALE_VELOCITY / self.cfg.DT if fmax is None else fmax
         self._check(self.lib.lbm_forchheimer_force(self._ctx, _ptr(self.u), _ptr(self.flags), _ptr(self.body_force), float(fmax),

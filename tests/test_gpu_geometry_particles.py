@@ -180,6 +180,13 @@ def test_pressure_gradient_and_forchheimer_force_bit_exact():
         R.accumulate_pressure_force(st, pf, scale)
         eng.add_pressure_gradient_force(0.12, scale)
         assert np.array_equal(H.from_dev_vec(eng.body_force), st.body_force)
+        # written instead of accumulated (no clear pass): same values on fluid cells, solid cells untouched
+        keep = eng.body_force.clone()
+        eng.body_force.fill_(7.0)
+        eng.set_pressure_gradient_force(0.12, scale)
+        got = H.from_dev_vec(eng.body_force); fluid = st.solid == 0
+        assert np.array_equal(got[fluid], st.body_force[fluid]) and np.all(got[~fluid] == 7.0)
+        eng.body_force.copy_(keep)
     # FilterPaperSystem.compute_forchheimer_resistance on top
     R.compute_forchheimer_resistance(st)
     eng.add_forchheimer_force()

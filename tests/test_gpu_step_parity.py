@@ -107,11 +107,13 @@ def _physical_v60_case(n, seed):
     return cfg, solid, zone, les_mask, phase, bf, u0, rho0
 
 
-@pytest.mark.parametrize("vec", [0, 1, 2])
+@pytest.mark.parametrize("vec", [0, 1, 2, 4, "tma"])
 @pytest.mark.parametrize("strict", [True, False])
-def test_physical_v60_full_features(vec, strict):
-    """vec = 0 (default) is the TMA-staged persistent kernel, vec = 2 the register-staged packed f32x2 kernel (two
-    cells per thread), vec = 1 the scalar fallback for odd nx."""
+def test_physical_v60_full_features(vec, strict, monkeypatch):
+    """vec = 0 (default) / 2 is the two-cell packed f32x2 kernel, vec = 1 the scalar fallback for odd nx, vec = 4 the
+    four-cells-per-thread kernel (128-bit loads, lane masks), "tma" the TMA-staged persistent kernel (LBM_TMA=1)."""
+    if vec == "tma":
+        monkeypatch.setenv("LBM_TMA", "1"); vec = 0
     n, steps = 32, 30
     cfg, solid, zone, les_mask, phase, bf, u0, rho0 = _physical_v60_case(n, 11)
     p = R.PhysParams(nx=n, ny=n, nz=n, tau_water=0.53, tau_air=0.8, gravity_lu=1e-5, periodic=(False, False, False),
@@ -135,12 +137,23 @@ def test_physical_v60_full_features(vec, strict):
 
 
 @pytest.mark.parametrize("periodic", [(True, True, True), (True, False, True), (False, False, False), (False, False, True)])
-@pytest.mark.parametrize("nx", [32, 27, 80])
-def test_physical_walls_obstacles_open_and_periodic_faces(periodic, nx):
+@pytest.mark.parametrize("nx", [32, 27, 30, 80, 144])
+@pytest.mark.parametrize("path", ["auto", "vec4", "tma"])
+def test_physical_walls_obstacles_open_and_periodic_faces(periodic, nx, path, monkeypatch):
     """Write-side bounce-back, open-face inflow (w_q) and periodic wrap of the walls kernels: random obstacles that
-    touch the faces, ragged box, odd nx (scalar kernel) and even nx (packed kernel; TMA-staged kernel when x and y do
-    not wrap and nx % 16 == 0 -- nx = 80 gives it a partial second tile, ny = 22 a partial tile row); moments-only
-    pass at the end."""
+    touch the faces, ragged box.  auto: nx = 27 runs the scalar kernel, even nx two cells per thread.  vec4: the
+    four-cells-per-thread kernel with lane masks (nx = 80 / 144: partial and multiple 128-cell warp tiles).  tma: the
+    TMA-staged kernel where it applies (x and y do not wrap, nx % 16 == 0; nx = 80 gives it a partial second tile,
+    ny = 22 a partial tile row).  Moments-only pass at the end."""
+    vec = 0
+    if path == "tma":
+        if periodic[0] or periodic[1] or nx % 16:
+            pytest.skip("TMA-staged kernel not eligible")
+        monkeypatch.setenv("LBM_TMA", "1")
+    if path == "vec4":
+        if nx % 4:
+            pytest.skip("four cells per thread need nx % 4 == 0")
+        vec = 4
     ny, nz, steps = 22, 14, 25
     rng = np.random.default_rng(5)
     solid = (rng.random((nx, ny, nz)) < 0.12).astype(np.uint8)
@@ -157,7 +170,7 @@ def test_physical_walls_obstacles_open_and_periodic_faces(periodic, nx):
     for _ in range(steps):
         g, rho, u = R.step_physical(g, p, solid=solid, body_force=bf, phase=phase, filter_zone=zone, les_mask=les_mask)
     eng = _engine(nx, ny, nz, compat="physical", periodic=periodic, walls=True, force=True, phase=True, les=True,
-                  porous=True, tau=0.56, tau_air=0.8, gravity_lu=2e-5, porous_darcy=0.2, porous_forch=0.5)
+                  porous=True, tau=0.56, tau_air=0.8, gravity_lu=2e-5, porous_darcy=0.2, porous_forch=0.5, vec=vec)
     eng.solid.copy_(_torch(H.to_dev_scalar(solid))); eng.filter_zone.copy_(_torch(H.to_dev_scalar(zone)))
     eng.les_mask.copy_(_torch(H.to_dev_scalar(les_mask))); eng.pack_flags()
     eng.phase.copy_(_torch(H.to_dev_scalar(phase))); eng.body_force.copy_(_torch(H.to_dev_vec(bf)))
@@ -195,10 +208,11 @@ def test_physical_walls_direct_population_write_needs_notification():
     assert np.array_equal(H.from_dev_pop(eng.populations)[:, fluid], g[:, fluid])
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 8, 9])
 def test_physical_tma_tuning_variants_bit_exact(variant, monkeypatch):
     """The other tile shapes / ring depths of the TMA-staged kernel (LBM_TMA_VARIANT: 64x4, 64x8, 64x2 tiles, 3-6
     stages) run the same operator: bit-exact as well.  More tiles than resident CTAs, so the ring wraps."""
+    monkeypatch.setenv("LBM_TMA", "1")
     monkeypatch.setenv("LBM_TMA_VARIANT", str(variant))
     nx, ny, nz, steps = 128, 36, 40, 6
     rng = np.random.default_rng(21)

@@ -75,12 +75,17 @@ def test_ghost_plane_slab_equals_wrapped_single_slab(vec):
     assert torch.equal(a.rho, b.rho[1:-1]) and torch.equal(a.u, b.u[:, 1:-1])
 
 
+@pytest.mark.parametrize("tma", [False, True])
 @pytest.mark.parametrize("periodic", [(True, True, True), (False, False, True)])
-def test_ghost_plane_slab_with_walls_equals_wrapped_single_slab(periodic):
+def test_ghost_plane_slab_with_walls_equals_wrapped_single_slab(periodic, tma, monkeypatch):
     """Same as above behind walls (compat = physical): obstacles straddle the slab interface, so bounce-back slots
     that live in the ghost planes are overwritten by every exchange and must be rebuilt (refresh after the halo).
-    x/y periodic runs the register-staged kernel, x/y open the TMA-staged one (ghost planes = tensor planes 0, nz+1)."""
+    tma: the opt-in TMA-staged kernel (x/y open; ghost planes = tensor planes 0, nz+1)."""
     import torch
+    if tma:
+        if periodic[0]:
+            pytest.skip("TMA-staged kernel not eligible")
+        monkeypatch.setenv("LBM_TMA", "1")
     n, steps = 32, 25
     rng = np.random.default_rng(12)
     solid = (rng.random((n, n, n)) < 0.1).astype(np.uint8)
