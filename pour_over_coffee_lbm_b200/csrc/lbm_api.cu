@@ -156,7 +156,7 @@ static int pick_vec(const lbm_ctx *ctx) {
 // CTA size of the main kernel: lbm_params.block when it is one of the built sizes, else the default for `vec`
 static int pick_block(const lbm_ctx *ctx, int vec) {
     const int b = ctx->p.block;
-    if (b == 64 || b == 128 || b == 256) return b;
+    if (b == 64 || b == 128 || b == 256 || b == 65 || b == 66) return b;      // 65 / 66: occupancy tuning codes (lbm_step.cu)
     if (ctx->p.features & LBM_FEAT_WALLS) return 64;
     return vec == 1 ? 256 : 128;
 }

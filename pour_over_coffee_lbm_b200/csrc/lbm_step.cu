@@ -24,6 +24,11 @@ constexpr bool G_WALLS = (LBM_GROUP % 2) != 0;
 // resident and the headline kernel drops from 0.40 to 0.63 ms (measured).
 template <int VEC, int BLOCK>
 constexpr int min_blocks() { return (VEC == 1 ? 1024 : 512) / BLOCK; }
+// the two-cell walls kernel of compat = physical fits 96 registers (16 B of spill in the full-feature variant): 20 warps
+// per SM instead of 16 -- V60 512^3 2.22 -> 2.07 ms, all-fluid 512^3 box 4.84 -> 4.50 ms; 24 warps (80 registers, 88 B of
+// spill) gives some of it back (2.11 / 4.59 ms)
+template <int VEC, int BLOCK>
+constexpr int min_blocks_phys_walls() { return VEC == 2 ? (BLOCK == 256 ? 2 : 640 / BLOCK) : min_blocks<VEC, BLOCK>(); }
 
 // CTA size: the walls path runs best with small CTAs (near-wall warps take longer; a CTA slot is held until its
 // slowest warp retires -- V60 512^3 sweep: 64 threads 2.17 ms, 128: 2.20, 256: 2.34)
@@ -37,7 +42,7 @@ static StepKernel pick() {
     else if constexpr (!COLLIDE && LES) return nullptr;
     else if constexpr (G_WALLS && G_COMPAT == LBM_COMPAT_PHYSICAL) {
         if constexpr (VEC == 4) return phys_walls4_kernel<FORCED, LES, POROUS, BLOCK, COLLIDE, min_blocks<VEC, BLOCK>()>;
-        else return phys_walls_kernel<FORCED, LES, POROUS, VEC, BLOCK, COLLIDE, min_blocks<VEC, BLOCK>()>;
+        else return phys_walls_kernel<FORCED, LES, POROUS, VEC, BLOCK, COLLIDE, min_blocks_phys_walls<VEC, BLOCK>()>;
     }
     else if constexpr (VEC == 2) return nullptr;
     else if constexpr (!COLLIDE && VEC != 1) return nullptr;
@@ -73,11 +78,19 @@ static StepKernel tuned() {
     if constexpr (G_WALLS && G_COMPAT == LBM_COMPAT_PHYSICAL) {
         // tuning set: BLOCK = 128 / 256 run with 384 / 256 resident threads per SM (168 / 255 registers, no spills)
         if constexpr (VEC == 4) return phys_walls4_kernel<true, true, true, BLOCK, true, (BLOCK == 128 ? 3 : (BLOCK == 256 ? 1 : min_blocks<VEC, BLOCK>()))>;
-        else return phys_walls_kernel<true, true, true, VEC, BLOCK, true, min_blocks<VEC, BLOCK>()>;
+        else return phys_walls_kernel<true, true, true, VEC, BLOCK, true, min_blocks_phys_walls<VEC, BLOCK>()>;
     } else return nullptr;
+}
+// full-feature two-cell kernel at a higher occupancy cap: MINB CTAs of 64 threads per SM (10 -> 96 registers, 12 -> 80)
+template <int MINB>
+static StepKernel tuned_occ() {
+    if constexpr (G_WALLS && G_COMPAT == LBM_COMPAT_PHYSICAL) return phys_walls_kernel<true, true, true, 2, 64, true, MINB>;
+    else return nullptr;
 }
 static StepKernel pick_tuned(int vec, int block) {
     switch (vec * 1000 + block) {
+        case 2065: return tuned_occ<8>();       // block codes 65 / 66: 64-thread CTAs, 16 / 24 resident warps per SM (default 20)
+        case 2066: return tuned_occ<12>();
         case 1128: return tuned<1, 128>();
         case 2128: return tuned<2, 128>();
         case 2256: return tuned<2, 256>();
@@ -96,7 +109,7 @@ StepKernel LBM_LOOKUP(int forced, int les, int porous, int vec, int collide, int
     const int def_block = vec == 1 ? default_block<MAIN, 1>() : (vec == 2 ? default_block<MAIN, 2>() : default_block<MAIN, 4>());
     if (collide && forced && les && porous && *block && *block != def_block) {
         k = pick_tuned(vec, *block);
-        if (k) return k;
+        if (k) { if (*block == 65 || *block == 66) *block = 64; return k; }
     }
     if (collide) {
         if (vec == 4) k = pick_feat<MAIN, 4, true>(forced, les, porous);
