@@ -253,7 +253,7 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "periodic 256^3 Taylor-Green vortex, D3Q19 BGK fp32 (BASELINE configs[1])" +
                                    (f"; {world} z-slabs of 256^3, NCCL halo of 5+5 populations/interface overlapped with interior" if world > 1 else ""),
-                       "grid_per_gpu": [n, n, n], "compat": "physical", "kernel": f"step_kernel VEC={args.vec or 4} build={'strict(-fmad=false)' if not args.fast else "fast(FMA contraction)"}",
+                       "grid_per_gpu": [n, n, n], "compat": "physical", "kernel": f"step_kernel<dense> VEC={args.vec or 4}, packed f32x2 collision, explicitly rounded (one build, bit-exact vs oracle)",
                        "cache": "working set 2.55 GB per GPU >> 126 MB L2 (inputs larger than L2, no flush needed)",
                        "macro_writeout": "rho,u materialised on demand, not inside the timed steps"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

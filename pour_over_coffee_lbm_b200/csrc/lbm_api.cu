@@ -23,7 +23,7 @@ cudaError_t launch_pack_flags(const Grid &, uint8_t *, const uint8_t *, const in
 cudaError_t build_work_lists(const Grid &, const uint8_t *, int, int, unsigned **, unsigned **, std::vector<int> &, unsigned long long **, cudaStream_t);
 cudaError_t launch_convert_f(const Grid &, bool, const float *, const uint8_t *, float *, cudaStream_t);
 cudaError_t launch_face_bc(const Grid &, float *, const uint8_t *, cudaStream_t, int *);
-cudaError_t launch_pressure_gradient(const Grid &, const float *, const uint8_t *, float *, float, float, int, cudaStream_t);
+cudaError_t launch_pressure_gradient(const Grid &, const float *, const uint8_t *, float *, float, float, int, const unsigned *, int, int, cudaStream_t);
 cudaError_t launch_forchheimer_force(const Grid &, const float *, const uint8_t *, float *, float, float, float, float, float, cudaStream_t);
 cudaError_t launch_add_reaction(const Grid &, const float *, const uint8_t *, float *, cudaStream_t);
 cudaError_t run_selftest_math(unsigned long long[7], const StepArgs &, cudaStream_t);
@@ -627,14 +627,18 @@ int lbm_import_f(lbm_ctx *ctx, const float *f_in, const uint8_t *flags, float *g
 
 int lbm_pressure_gradient_force(lbm_ctx *ctx, const float *rho, const uint8_t *flags, float *body_force, float max_force, float scale, void *stream) {
     if (!ctx || !rho || !body_force) return fail(ctx, "null argument");
-    CUDA_OK(ctx, launch_pressure_gradient(ctx->g, rho, flags, body_force, max_force, scale, 1, (cudaStream_t)stream));
+    const bool listed = flags && ctx->list_flags == flags && ctx->list_ty == 1 && ctx->d_tiles && (int)ctx->tile_off.size() == ctx->g.nz + 1;
+    CUDA_OK(ctx, launch_pressure_gradient(ctx->g, rho, flags, body_force, max_force, scale, 1, listed ? ctx->d_tiles : nullptr,
+                                          listed ? ctx->tile_off[ctx->g.nz] : 0, ctx->list_vec, (cudaStream_t)stream));
     ctx->launches++;
     return 0;
 }
 
 int lbm_pressure_gradient_force_set(lbm_ctx *ctx, const float *rho, const uint8_t *flags, float *body_force, float max_force, float scale, void *stream) {
     if (!ctx || !rho || !body_force) return fail(ctx, "null argument");
-    CUDA_OK(ctx, launch_pressure_gradient(ctx->g, rho, flags, body_force, max_force, scale, 0, (cudaStream_t)stream));
+    const bool listed = flags && ctx->list_flags == flags && ctx->list_ty == 1 && ctx->d_tiles && (int)ctx->tile_off.size() == ctx->g.nz + 1;
+    CUDA_OK(ctx, launch_pressure_gradient(ctx->g, rho, flags, body_force, max_force, scale, 0, listed ? ctx->d_tiles : nullptr,
+                                          listed ? ctx->tile_off[ctx->g.nz] : 0, ctx->list_vec, (cudaStream_t)stream));
     ctx->launches++;
     return 0;
 }

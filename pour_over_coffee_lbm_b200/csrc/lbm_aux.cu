@@ -185,11 +185,9 @@ __global__ void face_bc_kernel(Grid G, float *rho, const uint8_t *flags, int pas
 // One thread per cell on a (x-chunk, y, owned z) grid: coordinates come from the block index (the first version derived
 // them from a linear index with three 64-bit divisions per thread and took 1.14 ms on a 512^3 V60 box).
 // accumulate = 0 writes body_force = F on fluid cells instead of adding to it (saves the caller's clear pass).
-__global__ void pressure_gradient_kernel(Grid G, const float *rho, const uint8_t *flags, float *bf, float max_force, float scale, int accumulate) {
+__device__ __forceinline__ void pressure_gradient_cell(const Grid &G, const float *rho, const uint8_t *flags, float *bf, float max_force,
+                                                       float scale, int accumulate, int x, int y, int z) {
     const long long n = G.vol;
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= G.nx) return;
-    const int y = blockIdx.y, z = blockIdx.z;
     const long long c = ((long long)(z + G.zg) * G.ny + y) * G.nx + x;
     if (flags && (flags[c] & LBM_FLAG_SOLID)) return;
     const int k = G.z0 + z;
@@ -208,6 +206,28 @@ __global__ void pressure_gradient_kernel(Grid G, const float *rho, const uint8_t
     if (scale != 1.0f) { fx = scale * fx; fy = scale * fy; fz = scale * fz; }
     if (accumulate) { bf[c] = bf[c] + fx; bf[n + c] = bf[n + c] + fy; bf[2 * n + c] = bf[2 * n + c] + fz; }
     else { bf[c] = fx; bf[n + c] = fy; bf[2 * n + c] = fz; }
+}
+// One thread per cell on a (x-chunk, y, owned z) grid: coordinates come from the block index (the first version derived
+// them from a linear index with three 64-bit divisions per thread and took 1.14 ms on a 512^3 V60 box).
+// accumulate = 0 writes body_force = F on fluid cells instead of adding to it (saves the caller's clear pass).
+__global__ void pressure_gradient_kernel(Grid G, const float *rho, const uint8_t *flags, float *bf, float max_force, float scale, int accumulate) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= G.nx) return;
+    pressure_gradient_cell(G, rho, flags, bf, max_force, scale, accumulate, x, blockIdx.y, blockIdx.z);
+}
+// Same over the step kernel's active warp-tile list (one warp per tile of 32*vec cells): the solid 65 % of a V60 box is
+// never visited.
+__global__ void pressure_gradient_tiles_kernel(Grid G, const float *rho, const uint8_t *flags, float *bf, float max_force, float scale,
+                                               int accumulate, const unsigned *items, int n_items, int vec) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= n_items) return;
+    const unsigned e = __ldg(items + w);
+    const int y = (int)((e >> 8) & 0xfffu), z = (int)(e >> 20);
+    const int xb = (int)(e & 0xffu) * 32 * vec + (int)(threadIdx.x & 31u);
+    for (int i = 0; i < vec; ++i) {
+        const int x = xb + 32 * i;
+        if (x < G.nx) pressure_gradient_cell(G, rho, flags, bf, max_force, scale, accumulate, x, y, z);
+    }
 }
 
 // filter_paper.py:471-536
@@ -534,7 +554,12 @@ cudaError_t launch_face_bc(const Grid &G, float *rho, const uint8_t *flags, cuda
     *count = 5;
     return cudaGetLastError();
 }
-cudaError_t launch_pressure_gradient(const Grid &G, const float *rho, const uint8_t *flags, float *bf, float max_force, float scale, int accumulate, cudaStream_t s) {
+cudaError_t launch_pressure_gradient(const Grid &G, const float *rho, const uint8_t *flags, float *bf, float max_force, float scale, int accumulate,
+                                     const unsigned *items, int n_items, int vec, cudaStream_t s) {
+    if (items) {      // the caller's tile list was built for exactly this flag field
+        if (n_items > 0) pressure_gradient_tiles_kernel<<<(n_items + 3) / 4, 128, 0, s>>>(G, rho, flags, bf, max_force, scale, accumulate, items, n_items, vec);
+        return cudaGetLastError();
+    }
     if (G.ny > 65535 || G.nz > 65535) return cudaErrorInvalidValue;
     const int b = G.nx >= 128 ? 128 : 64;
     const dim3 grid((unsigned)((G.nx + b - 1) / b), (unsigned)G.ny, (unsigned)G.nz);

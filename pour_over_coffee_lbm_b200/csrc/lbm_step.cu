@@ -77,7 +77,9 @@ template <int VEC, int BLOCK>
 static StepKernel tuned() {
     if constexpr (G_WALLS && G_COMPAT == LBM_COMPAT_PHYSICAL) {
         // tuning set: BLOCK = 128 / 256 run with 384 / 256 resident threads per SM (168 / 255 registers, no spills)
-        if constexpr (VEC == 4) return phys_walls4_kernel<true, true, true, BLOCK, true, (BLOCK == 128 ? 3 : (BLOCK == 256 ? 1 : min_blocks<VEC, BLOCK>()))>;
+        // BLOCK = 256 (tuning code): 128-thread CTAs, 3 per SM, loads NOT predicated by the lane mask
+        if constexpr (VEC == 4 && BLOCK == 256) return phys_walls4_kernel<true, true, true, 128, true, 3, false>;
+        else if constexpr (VEC == 4) return phys_walls4_kernel<true, true, true, BLOCK, true, (BLOCK == 128 ? 3 : min_blocks<VEC, BLOCK>())>;
         else return phys_walls_kernel<true, true, true, VEC, BLOCK, true, min_blocks_phys_walls<VEC, BLOCK>()>;
     } else return nullptr;
 }
@@ -109,7 +111,7 @@ StepKernel LBM_LOOKUP(int forced, int les, int porous, int vec, int collide, int
     const int def_block = vec == 1 ? default_block<MAIN, 1>() : (vec == 2 ? default_block<MAIN, 2>() : default_block<MAIN, 4>());
     if (collide && forced && les && porous && *block && *block != def_block) {
         k = pick_tuned(vec, *block);
-        if (k) { if (*block == 65 || *block == 66) *block = 64; return k; }
+        if (k) { if (*block == 65 || *block == 66) *block = 64; if (vec == 4 && *block == 256) *block = 128; return k; }
     }
     if (collide) {
         if (vec == 4) k = pick_feat<MAIN, 4, true>(forced, les, porous);
