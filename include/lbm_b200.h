@@ -143,6 +143,15 @@ int  lbm_face_bc(lbm_ctx *ctx, const lbm_fields *fields, void *stream);
 int  lbm_export_f(lbm_ctx *ctx, const float *g, const uint8_t *flags, float *f_out, void *stream);
 int  lbm_import_f(lbm_ctx *ctx, const float *f_in, const uint8_t *flags, float *g, void *stream);
 
+/* ---- observability ------------------------------------------------------- */
+/* One fused, deterministic pass over rho / u of the owned fluid cells, result left in DEVICE memory (no host sync):
+ *   out8[0] max |u|   [1] min rho   [2] max rho   [3] sum rho   [4] sum 0.5 rho |u|^2   [5] NaN count   [6] Inf count
+ *   [7] fluid cells.
+ * Replaces visualizer.compute_statistics / get_statistics (src/visualization/visualizer.py:130-183),
+ * NumericalStabilityMonitor.check_field_stability (src/core/numerical_stability.py:52-110) and the host-side
+ * reductions of main.py:907-912.  flags may be NULL (every cell is fluid). */
+int  lbm_field_statistics(lbm_ctx *ctx, const float *rho, const float *u, const uint8_t *flags, double *out8, void *stream);
+
 /* ---- neighbours that feed body_force --------------------- */
 /* PressureGradientDrive.compute_pressure_gradient + _accumulate_* pressure_gradient_drive.py:124-193,274-279:
  * body_force += scale * clamp(-cs^2 grad(rho)/rho, max_force) on fluid cells. */
@@ -179,6 +188,22 @@ int  lbm_particles_couple(lbm_ctx *ctx, const float *u, float *reaction, lbm_par
 /* CoffeeParticleSystem.apply_under_relaxation coffee_particles.py:1200-1212 as a separate call
  * (lbm_particles_couple fuses it when relax >= 0; pass relax < 0 there to skip). */
 int  lbm_particles_under_relax(lbm_ctx *ctx, lbm_particles *ps, float relax, void *stream);
+
+/* CoffeeParticleSystem.update_particle_physics coffee_particles.py:641-720 (+ validate_coordinate :75-92,
+ * validate_velocity :95-108, check_particle_boundary_violation_safe :734-778, constrain_to_boundary_safe :780-831):
+ * explicit Euler step of the active particles with the reference's clamps (dt in [1e-8, 1e-2], |a| <= 1000,
+ * |dx| <= 1 lu), the V60 cone constraint and velocity damping.  `force` is [3][n] (the reference's self.force; NULL =
+ * no force) and is zeroed for the next step.  counters (device, 2 x int32): += coordinate_errors, boundary_violations.
+ * The bounds are what FilterPaperSystem.get_coffee_bed_boundary() returns (main.py:672-679), in lattice units. */
+typedef struct {
+    float center_x, center_y, bottom_z;
+    float bottom_radius_lu, top_radius_lu;
+    float cup_height_lu;          /* config.CUP_HEIGHT / config.SCALE_LENGTH (50 if <= 0, coffee_particles.py:758-760) */
+    float max_coordinate;         /* float(max(NX, NY, NZ)), coffee_particles.py:23 */
+    float nz_minus_5;             /* float(NZ - 5), coffee_particles.py:794 */
+} lbm_particle_bounds;
+int  lbm_particles_advance(lbm_ctx *ctx, lbm_particles *ps, float *force, const lbm_particle_bounds *bounds, float dt,
+                           int32_t *counters, void *stream);
 
 /* ---- multi-GPU slabs -------------------------------------------------------------------- */
 /* Attach an NCCL communicator over the ranks of one box (z-slab chain).  unique_id is the

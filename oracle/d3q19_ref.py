@@ -651,6 +651,132 @@ def under_relax(drag_new, drag_old, active, alpha: float):
     return drag, new_old
 
 
+def _valid_coordinate(x, y, z, max_coord) -> bool:
+    """CoffeeParticleSystem.validate_coordinate, coffee_particles.py:75-92 (MIN_COORDINATE = 0, :24)."""
+    ok = not (x < 0 or x > max_coord or y < 0 or y > max_coord or z < 0 or z > max_coord)
+    if not (x == x and y == y and z == z):
+        ok = False
+    if abs(x) > F32(1e6) or abs(y) > F32(1e6) or abs(z) > F32(1e6):
+        ok = False
+    return ok
+
+
+def _valid_velocity(vx, vy, vz) -> bool:
+    """validate_velocity, coffee_particles.py:95-108 (MAX_VELOCITY = 10, :25)."""
+    s2 = (vx * vx + vy * vy) + vz * vz
+    ok = vx == vx and vy == vy and vz == vz
+    if s2 > F32(10.0) * F32(10.0):
+        ok = False
+    return bool(ok)
+
+
+def update_particle_physics(cfg: RefConfig, pos, vel, force, mass, active, dt, center_x, center_y, bottom_z,
+                            bottom_radius_lu, top_radius_lu):
+    """CoffeeParticleSystem.update_particle_physics, coffee_particles.py:641-720, with
+    check_particle_boundary_violation_safe (:734-778) and constrain_to_boundary_safe (:780-831), statement by
+    statement in f32.  Plain Python loop over the particles (test sizes only).  pos/vel/force [P,3], mass [P],
+    active [P] int32 are updated in place; returns (coordinate_errors, boundary_violations)."""
+    f = F32
+    dt_safe = max(f(1e-8), min(f(1e-2), f(dt)))
+    cx0, cy0, bz = f(center_x), f(center_y), f(bottom_z)
+    br, tr = f(bottom_radius_lu), f(top_radius_lu)
+    max_coord = f(max(cfg.NX, cfg.NY, cfg.NZ))
+    cup = f(cfg.CUP_HEIGHT / cfg.SCALE_LENGTH)      # Python-scope constant, rounded to f32 when the kernel uses it
+    if not cup > 0:
+        cup = f(50.0)
+    nz5 = f(cfg.NZ - 5)
+    coord_err = 0; viol = 0
+    norm = lambda a, b, c: np.sqrt((a * a + b * b) + c * c)
+    with np.errstate(all="ignore"):
+        for i in range(len(mass)):
+            if active[i] != 1:
+                continue
+            px, py, pz = f(pos[i, 0]), f(pos[i, 1]), f(pos[i, 2])
+            if not _valid_coordinate(px, py, pz, max_coord):
+                active[i] = 0; coord_err += 1
+                continue
+            vx, vy, vz = f(vel[i, 0]), f(vel[i, 1]), f(vel[i, 2])
+            m = f(mass[i])
+            if m > f(1e-10):
+                ax, ay, az = f(force[i, 0]) / m, f(force[i, 1]) / m, f(force[i, 2]) / m
+                amag = norm(ax, ay, az)
+                if amag > f(1000.0):
+                    sc = f(1000.0) / amag
+                    ax, ay, az = ax * sc, ay * sc, az * sc
+                nvx, nvy, nvz = vx + ax * dt_safe, vy + ay * dt_safe, vz + az * dt_safe
+                if _valid_velocity(nvx, nvy, nvz):
+                    vx, vy, vz = nvx, nvy, nvz
+                else:
+                    vx = vy = vz = f(0.0); coord_err += 1
+            dx, dy, dz = vx * dt_safe, vy * dt_safe, vz * dt_safe
+            dmag = norm(dx, dy, dz)
+            if dmag > f(1.0):
+                sc = f(1.0) / dmag
+                dx, dy, dz = dx * sc, dy * sc, dz * sc
+            nx_, ny_, nz_ = px + dx, py + dy, pz + dz
+            # check_particle_boundary_violation_safe
+            violation = False
+            if not _valid_coordinate(nx_, ny_, nz_, max_coord):
+                violation = True
+            elif nz_ < bz - f(1.0):
+                violation = True
+            else:
+                ddx, ddy = nx_ - cx0, ny_ - cy0
+                d2 = ddx * ddx + ddy * ddy
+                if d2 > f(1e6):
+                    violation = True
+                else:
+                    dist = np.sqrt(d2)
+                    hd = nz_ - bz
+                    if hd >= 0 and hd < cup:
+                        hr = max(f(0.0), min(f(1.0), hd / cup))
+                        max_r = br + (tr - br) * hr
+                        if dist > max_r * f(0.9):
+                            violation = True
+                    elif hd >= cup:
+                        if dist > tr * f(0.9):
+                            violation = True
+            if violation:
+                # constrain_to_boundary_safe
+                cx_, cy_, cz_ = nx_, ny_, nz_
+                if cz_ < bz:
+                    cz_ = bz + f(0.1)
+                max_z = min(bz + cup * f(1.5), nz5)
+                if cz_ > max_z:
+                    cz_ = max_z - f(0.1)
+                ddx, ddy = cx_ - cx0, cy_ - cy0
+                d2 = ddx * ddx + ddy * ddy
+                if d2 < f(1e6):
+                    dist = np.sqrt(d2)
+                    if dist > f(0.1):
+                        hd = max(f(0.0), cz_ - bz)
+                        max_r = tr
+                        if hd < cup:
+                            hr = max(f(0.0), min(f(1.0), hd / cup))
+                            max_r = br + (tr - br) * hr
+                        if dist > max_r * f(0.8):
+                            sf = (max_r * f(0.8)) / dist
+                            sf = max(f(0.1), min(f(1.0), sf))
+                            cx_ = cx0 + ddx * sf
+                            cy_ = cy0 + ddy * sf
+                else:
+                    cx_, cy_ = cx0, cy0
+                if _valid_coordinate(cx_, cy_, cz_, max_coord):
+                    nx_, ny_, nz_ = cx_, cy_, cz_
+                    vx, vy, vz = vx * f(0.3), vy * f(0.3), vz * f(0.3)
+                    viol += 1
+                else:
+                    nx_, ny_, nz_ = px, py, pz
+                    vx = vy = vz = f(0.0); coord_err += 1
+            if _valid_coordinate(nx_, ny_, nz_, max_coord):
+                pos[i] = (nx_, ny_, nz_)
+            else:
+                active[i] = 0; coord_err += 1
+            vel[i] = (vx, vy, vz)
+            force[i] = 0
+    return coord_err, viol
+
+
 def add_particle_reaction_forces(st: State, reaction: np.ndarray) -> None:
     """LBMSolver.add_particle_reaction_forces, legacy/lbm_solver.py:1478-1483."""
     fluid = (st.solid == 0)[..., None]

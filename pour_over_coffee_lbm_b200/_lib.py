@@ -43,6 +43,11 @@ class LbmParticles(C.Structure):
                  "u_fluid", "reynolds", "cd", "cell")] + [("n", C.c_int)]
 
 
+class LbmParticleBounds(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("center_x", "center_y", "bottom_z", "bottom_radius_lu", "top_radius_lu",
+                                         "cup_height_lu", "max_coordinate", "nz_minus_5")]
+
+
 # every symbol include/lbm_b200.h declares: (name, restype, argtypes)
 _P = C.c_void_p
 SIGNATURES = {
@@ -65,9 +70,11 @@ SIGNATURES = {
     "lbm_pressure_gradient_force": (C.c_int, [_P, _P, _P, _P, C.c_float, C.c_float, _P]),
     "lbm_pressure_gradient_force_set": (C.c_int, [_P, _P, _P, _P, C.c_float, C.c_float, _P]),
     "lbm_forchheimer_force": (C.c_int, [_P, _P, _P, _P, C.c_float, _P]),
+    "lbm_field_statistics": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "lbm_add_reaction_force": (C.c_int, [_P, _P, _P, _P, _P]),
     "lbm_particles_couple": (C.c_int, [_P, _P, _P, C.POINTER(LbmParticles), C.c_float, C.c_float, C.c_float, _P]),
     "lbm_particles_under_relax": (C.c_int, [_P, C.POINTER(LbmParticles), C.c_float, _P]),
+    "lbm_particles_advance": (C.c_int, [_P, C.POINTER(LbmParticles), _P, C.POINTER(LbmParticleBounds), C.c_float, _P, _P]),
     "lbm_nccl_unique_id": (C.c_int, [_P]),
     "lbm_attach_nccl": (C.c_int, [_P, _P, C.c_int, C.c_int]),
     "lbm_halo_exchange": (C.c_int, [_P, _P, _P, _P]),

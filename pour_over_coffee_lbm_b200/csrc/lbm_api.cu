@@ -27,9 +27,11 @@ cudaError_t launch_pressure_gradient(const Grid &, const float *, const uint8_t 
 cudaError_t launch_forchheimer_force(const Grid &, const float *, const uint8_t *, float *, float, float, float, float, float, cudaStream_t);
 cudaError_t launch_add_reaction(const Grid &, const float *, const uint8_t *, float *, cudaStream_t);
 cudaError_t run_selftest_math(unsigned long long[7], const StepArgs &, cudaStream_t);
+cudaError_t launch_field_statistics(const Grid &, const float *, const float *, const uint8_t *, void *, int, double *, cudaStream_t);
 cudaError_t launch_bounce_slots(const Grid &, float *, const uint8_t *, const unsigned long long *, int, int, cudaStream_t);
 cudaError_t launch_particles_couple(const Grid &, const float *, float *, const lbm_particles &, float, float, float, cudaStream_t);
 cudaError_t launch_particles_under_relax(const lbm_particles &, float, cudaStream_t);
+cudaError_t launch_particles_advance(const lbm_particles &, float *, const lbm_particle_bounds &, float, int *, cudaStream_t);
 // TMA-staged walls kernels of compat = physical (lbm_step_tma.cu)
 struct TmaKernelInfo {
     void (*kernel)(const StepArgs, const TmaMaps);
@@ -100,6 +102,7 @@ struct lbm_ctx {
     const float *slots_valid = nullptr;
     // TMA-staged walls path (lbm_phys_tma.cuh): tile height of the current list (1 = warp-tile list of the
     // register-staged kernels), tuning variant, and the tensor maps of the field sets seen so far
+    void *d_stat_scratch = nullptr;            // per-block partials of lbm_field_statistics
     int list_ty = 1;
     int tma_variant = 0;
     bool tma_enabled = false;                 // opt-in (LBM_TMA=1): measured slower than the VEC = 4 register-staged kernel
@@ -298,6 +301,7 @@ void lbm_destroy(lbm_ctx *ctx) {
     if (ctx->ev_comm) cudaEventDestroy(ctx->ev_comm);
     if (ctx->d_tiles) cudaFree(ctx->d_tiles);
     if (ctx->d_tile_mask) cudaFree(ctx->d_tile_mask);
+    if (ctx->d_stat_scratch) cudaFree(ctx->d_stat_scratch);
     if (ctx->d_nbr) cudaFree(ctx->d_nbr);
     delete ctx;
 }
@@ -643,6 +647,15 @@ int lbm_pressure_gradient_force_set(lbm_ctx *ctx, const float *rho, const uint8_
     return 0;
 }
 
+int lbm_field_statistics(lbm_ctx *ctx, const float *rho, const float *u, const uint8_t *flags, double *out8, void *stream) {
+    if (!ctx || !rho || !u || !out8) return fail(ctx, "null argument");
+    const int blocks = ctx->sm_count * 8;
+    if (!ctx->d_stat_scratch) CUDA_OK(ctx, cudaMalloc(&ctx->d_stat_scratch, (size_t)blocks * 8 * sizeof(double)));
+    CUDA_OK(ctx, launch_field_statistics(ctx->g, rho, u, flags, ctx->d_stat_scratch, blocks, out8, (cudaStream_t)stream));
+    ctx->launches += 2;
+    return 0;
+}
+
 int lbm_forchheimer_force(lbm_ctx *ctx, const float *u, const uint8_t *flags, float *body_force, float fmax, void *stream) {
     if (!ctx || !u || !flags || !body_force) return fail(ctx, "null argument");
     const lbm_params &p = ctx->p;
@@ -664,6 +677,14 @@ int lbm_particles_couple(lbm_ctx *ctx, const float *u, float *reaction, lbm_part
     CUDA_OK(ctx, cudaMemsetAsync(reaction, 0, (size_t)ctx->g.vol * 3 * sizeof(float), (cudaStream_t)stream));
     CUDA_OK(ctx, launch_particles_couple(ctx->g, u, reaction, *ps, water_density, water_viscosity, relax, (cudaStream_t)stream));
     ctx->launches += 1;
+    return 0;
+}
+
+int lbm_particles_advance(lbm_ctx *ctx, lbm_particles *ps, float *force, const lbm_particle_bounds *bounds, float dt, int32_t *counters, void *stream) {
+    if (!ctx || !ps || !bounds || !counters) return fail(ctx, "null argument");
+    if (!ps->pos || !ps->vel || !ps->mass || !ps->active) return fail(ctx, "particle arrays pos/vel/mass/active are required");
+    CUDA_OK(ctx, launch_particles_advance(*ps, force, *bounds, dt, counters, (cudaStream_t)stream));
+    ctx->launches++;
     return 0;
 }
 

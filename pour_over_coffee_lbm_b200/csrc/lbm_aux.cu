@@ -515,6 +515,84 @@ cudaError_t run_selftest_math(unsigned long long out[7], const StepArgs &args, c
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 
+// ---- fused field statistics -------------------------------------------------------------------------
+// One pass over rho and u of the owned fluid cells replaces the reference's statistics / stability scans:
+// visualizer.compute_statistics (visualizer.py:130-183: max / mean speed, masses), NumericalStabilityMonitor.
+// check_field_stability (numerical_stability.py:52-110: max |u|, min / max rho, NaN and Inf counts) and the
+// .to_numpy() reductions of main.py:907-912 and lbm_diagnostics.py.  Deterministic: per-block partials in a fixed
+// order, then one block folds them in index order (no float atomics).
+//   out[0] max |u| (finite values)   out[1] min rho   out[2] max rho   out[3] sum rho (mass)
+//   out[4] sum 0.5 rho |u|^2         out[5] NaN count (rho, |u|)       out[6] Inf count     out[7] fluid cells
+struct StatPartial { double v[8]; };
+__device__ __forceinline__ void stat_merge(StatPartial &a, const StatPartial &b) {
+    a.v[0] = fmax(a.v[0], b.v[0]); a.v[1] = fmin(a.v[1], b.v[1]); a.v[2] = fmax(a.v[2], b.v[2]);
+    a.v[3] += b.v[3]; a.v[4] += b.v[4]; a.v[5] += b.v[5]; a.v[6] += b.v[6]; a.v[7] += b.v[7];
+}
+__device__ __forceinline__ StatPartial stat_identity() {
+    StatPartial s; s.v[0] = 0.0; s.v[1] = 1e300; s.v[2] = -1e300; s.v[3] = s.v[4] = s.v[5] = s.v[6] = s.v[7] = 0.0; return s;
+}
+__device__ __forceinline__ StatPartial stat_block_reduce(StatPartial s) {
+    __shared__ StatPartial sh[32];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        StatPartial o;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o.v[k] = __shfl_down_sync(0xffffffffu, s.v[k], off);
+        stat_merge(s, o);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) sh[warp] = s;
+    __syncthreads();
+    if (warp == 0) {
+        s = lane < (int)(blockDim.x >> 5) ? sh[lane] : stat_identity();
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            StatPartial o;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o.v[k] = __shfl_down_sync(0xffffffffu, s.v[k], off);
+            stat_merge(s, o);
+        }
+    }
+    return s;
+}
+__global__ void __launch_bounds__(256) field_statistics_kernel(Grid G, const float *rho, const float *u, const uint8_t *flags, StatPartial *partials) {
+    StatPartial s = stat_identity();
+    const long long per = G.plane, n = per * G.nz, off = per * G.zg;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long c = off + i;
+        if (flags && (flags[c] & LBM_FLAG_SOLID)) continue;
+        const float r = rho[c], ux = u[c], uy = u[G.vol + c], uz = u[2 * G.vol + c];
+        const float um = sqrtf(dot3(ux, uy, uz, ux, uy, uz));
+        s.v[7] += 1.0;
+        if (r != r) s.v[5] += 1.0;
+        else if (isinf(r)) s.v[6] += 1.0;
+        else { s.v[1] = fmin(s.v[1], (double)r); s.v[2] = fmax(s.v[2], (double)r); s.v[3] += (double)r; }
+        if (um != um) s.v[5] += 1.0;
+        else if (isinf(um)) s.v[6] += 1.0;
+        else {
+            s.v[0] = fmax(s.v[0], (double)um);
+            if (r == r && !isinf(r)) s.v[4] += 0.5 * (double)r * ((double)ux * ux + (double)uy * uy + (double)uz * uz);
+        }
+    }
+    s = stat_block_reduce(s);
+    if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+__global__ void __launch_bounds__(256) field_statistics_fold_kernel(const StatPartial *partials, int n, double *out) {
+    // thread t folds partials t, t + 256, ... in index order; the block reduction order is fixed as well
+    StatPartial s = stat_identity();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) stat_merge(s, partials[i]);
+    s = stat_block_reduce(s);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) out[k] = s.v[k];
+    }
+}
+cudaError_t launch_field_statistics(const Grid &G, const float *rho, const float *u, const uint8_t *flags, void *scratch, int blocks, double *out, cudaStream_t s) {
+    field_statistics_kernel<<<blocks, 256, 0, s>>>(G, rho, u, flags, (StatPartial *)scratch);
+    field_statistics_fold_kernel<<<1, 256, 0, s>>>((const StatPartial *)scratch, blocks, out);
+    return cudaGetLastError();
+}
+
 // ---- host launchers (called from lbm_api.cu) -----------------------------------------------
 static inline int grid_for(long long n, int block) { long long g = (n + block - 1) / block; return (int)(g > 148LL * 32 ? 148 * 32 : g); }
 

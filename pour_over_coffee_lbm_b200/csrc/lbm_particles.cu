@@ -151,11 +151,134 @@ cudaError_t launch_particles_under_relax(const lbm_particles &ps, float relax, c
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------
+// CoffeeParticleSystem.update_particle_physics (coffee_particles.py:641-720) with its helpers validate_coordinate
+// (:75-92), validate_velocity (:95-108), check_particle_boundary_violation_safe (:734-778) and
+// constrain_to_boundary_safe (:780-831): explicit Euler with a clamped time step, acceleration and displacement caps,
+// the cone constraint (0.9 / 0.8 radius factors), velocity damping 0.3.  One thread per particle; every statement in
+// the reference's order, f32, no contraction (-fmad=false), so positions / velocities / active flags match
+// oracle/d3q19_ref.py:update_particle_physics bit for bit.  `force` ([3][n], may be NULL = no force) is zeroed like
+// the reference's self.force; counters[0] += coordinate errors, counters[1] += boundary violations.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool valid_coordinate(float x, float y, float z, float max_coord) {
+    bool ok = !(x < 0.0f || x > max_coord || y < 0.0f || y > max_coord || z < 0.0f || z > max_coord);
+    if (!(x == x && y == y && z == z)) ok = false;
+    if (fabsf(x) > 1e6f || fabsf(y) > 1e6f || fabsf(z) > 1e6f) ok = false;
+    return ok;
+}
+__device__ __forceinline__ bool valid_velocity(float vx, float vy, float vz) {
+    const float s2 = (vx * vx + vy * vy) + vz * vz;
+    bool ok = vx == vx && vy == vy && vz == vz;
+    if (s2 > 10.0f * 10.0f) ok = false;
+    return ok;
+}
+__device__ __forceinline__ float norm3(float x, float y, float z) { return sqrtf((x * x + y * y) + z * z); }
+
+__global__ void __launch_bounds__(256) particles_advance_kernel(lbm_particles P, float *force, lbm_particle_bounds B, float dt, int *counters) {
+    const int n = P.n;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n || P.active[p] != 1) return;
+    const float dt_safe = fmaxf(1e-8f, fminf(1e-2f, dt));
+    int coord_err = 0, viol = 0;
+    float px = P.pos[p], py = P.pos[n + p], pz = P.pos[2 * n + p];
+    if (!valid_coordinate(px, py, pz, B.max_coordinate)) {
+        P.active[p] = 0;
+        atomicAdd(counters, 1);
+        return;                                                    // `continue`: the force is NOT cleared on this path
+    }
+    float vx = P.vel[p], vy = P.vel[n + p], vz = P.vel[2 * n + p];
+    const float mass = P.mass[p];
+    if (mass > 1e-10f) {
+        float ax = 0.0f, ay = 0.0f, az = 0.0f;
+        if (force) { ax = force[p] / mass; ay = force[n + p] / mass; az = force[2 * n + p] / mass; }
+        const float amag = norm3(ax, ay, az);
+        if (amag > 1000.0f) { const float s = 1000.0f / amag; ax = ax * s; ay = ay * s; az = az * s; }
+        const float nvx = vx + ax * dt_safe, nvy = vy + ay * dt_safe, nvz = vz + az * dt_safe;
+        if (valid_velocity(nvx, nvy, nvz)) { vx = nvx; vy = nvy; vz = nvz; }
+        else { vx = vy = vz = 0.0f; ++coord_err; }
+    }
+    float dx = vx * dt_safe, dy = vy * dt_safe, dz = vz * dt_safe;
+    const float dmag = norm3(dx, dy, dz);
+    if (dmag > 1.0f) { const float s = 1.0f / dmag; dx = dx * s; dy = dy * s; dz = dz * s; }
+    float nx_ = px + dx, ny_ = py + dy, nz_ = pz + dz;
+
+    // check_particle_boundary_violation_safe
+    bool violation = false;
+    if (!valid_coordinate(nx_, ny_, nz_, B.max_coordinate)) violation = true;
+    else if (nz_ < B.bottom_z - 1.0f) violation = true;
+    else {
+        const float ddx = nx_ - B.center_x, ddy = ny_ - B.center_y;
+        const float d2 = ddx * ddx + ddy * ddy;
+        if (d2 > 1e6f) violation = true;
+        else {
+            const float dist = sqrtf(d2);
+            const float hd = nz_ - B.bottom_z;
+            if (hd >= 0.0f && hd < B.cup_height_lu) {
+                float hr = hd / B.cup_height_lu;
+                hr = fmaxf(0.0f, fminf(1.0f, hr));
+                const float max_r = B.bottom_radius_lu + (B.top_radius_lu - B.bottom_radius_lu) * hr;
+                if (dist > max_r * 0.9f) violation = true;
+            } else if (hd >= B.cup_height_lu) {
+                if (dist > B.top_radius_lu * 0.9f) violation = true;
+            }
+        }
+    }
+    if (violation) {
+        // constrain_to_boundary_safe
+        float cx_ = nx_, cy_ = ny_, cz_ = nz_;
+        if (cz_ < B.bottom_z) cz_ = B.bottom_z + 0.1f;
+        const float max_z = fminf(B.bottom_z + B.cup_height_lu * 1.5f, B.nz_minus_5);
+        if (cz_ > max_z) cz_ = max_z - 0.1f;
+        const float ddx = cx_ - B.center_x, ddy = cy_ - B.center_y;
+        const float d2 = ddx * ddx + ddy * ddy;
+        if (d2 < 1e6f) {
+            const float dist = sqrtf(d2);
+            if (dist > 0.1f) {
+                float hd = cz_ - B.bottom_z;
+                hd = fmaxf(0.0f, hd);
+                float max_r = B.top_radius_lu;
+                if (hd < B.cup_height_lu) {
+                    float hr = hd / B.cup_height_lu;
+                    hr = fmaxf(0.0f, fminf(1.0f, hr));
+                    max_r = B.bottom_radius_lu + (B.top_radius_lu - B.bottom_radius_lu) * hr;
+                }
+                if (dist > max_r * 0.8f) {
+                    float sf = (max_r * 0.8f) / dist;
+                    sf = fmaxf(0.1f, fminf(1.0f, sf));
+                    cx_ = B.center_x + ddx * sf;
+                    cy_ = B.center_y + ddy * sf;
+                }
+            }
+        } else { cx_ = B.center_x; cy_ = B.center_y; }
+        if (valid_coordinate(cx_, cy_, cz_, B.max_coordinate)) {
+            nx_ = cx_; ny_ = cy_; nz_ = cz_;
+            vx = vx * 0.3f; vy = vy * 0.3f; vz = vz * 0.3f;
+            ++viol;
+        } else {
+            nx_ = px; ny_ = py; nz_ = pz;
+            vx = vy = vz = 0.0f;
+            ++coord_err;
+        }
+    }
+    if (valid_coordinate(nx_, ny_, nz_, B.max_coordinate)) { P.pos[p] = nx_; P.pos[n + p] = ny_; P.pos[2 * n + p] = nz_; }
+    else { P.active[p] = 0; ++coord_err; }
+    P.vel[p] = vx; P.vel[n + p] = vy; P.vel[2 * n + p] = vz;
+    if (force) { force[p] = 0.0f; force[n + p] = 0.0f; force[2 * n + p] = 0.0f; }
+    if (coord_err) atomicAdd(counters, coord_err);
+    if (viol) atomicAdd(counters + 1, viol);
+}
+
 cudaError_t launch_particles_couple(const Grid &G, const float *u, float *reaction, const lbm_particles &ps,
                                     float rho_w, float mu_w, float relax, cudaStream_t s) {
     ParticleArgs A{G, u, reaction, ps, rho_w, mu_w, relax};
     const int b = 256, gr = (ps.n + b - 1) / b;
     if (ps.n > 0) particles_couple_kernel<<<gr, b, 0, s>>>(A);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_particles_advance(const lbm_particles &ps, float *force, const lbm_particle_bounds &b, float dt, int *counters, cudaStream_t s) {
+    if (ps.n <= 0) return cudaSuccess;
+    particles_advance_kernel<<<(ps.n + 255) / 256, 256, 0, s>>>(ps, force, b, dt, counters);
     return cudaGetLastError();
 }
 

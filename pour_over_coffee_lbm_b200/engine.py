@@ -247,6 +247,15 @@ class D3Q19Engine:
         self._check(self.lib.lbm_pressure_gradient_force(self._ctx, _ptr(self.rho), _ptr(self.flags), _ptr(self.body_force),
                                                          float(max_force), float(scale), self.stream), "lbm_pressure_gradient_force")
 
+    def field_statistics(self) -> torch.Tensor:
+        """[max|u|, min rho, max rho, sum rho, kinetic energy, NaN count, Inf count, fluid cells] of the owned slab as an
+        8-element f64 DEVICE tensor (one fused deterministic pass, no host sync; include/lbm_b200.h)."""
+        if getattr(self, "_stats", None) is None:
+            self._stats = torch.zeros(8, dtype=torch.float64, device=self.device)
+        self._check(self.lib.lbm_field_statistics(self._ctx, _ptr(self.rho), _ptr(self.u), _ptr(self.flags) if self.flags is not None else None,
+                                                  _ptr(self._stats), self.stream), "lbm_field_statistics")
+        return self._stats
+
     def set_pressure_gradient_force(self, max_force: float = 0.12, scale: float = 1.0):
         """clear_body_force() + add_pressure_gradient_force() on the fluid cells in one pass (solid cells keep their
         old body_force, which no kernel reads)."""
@@ -326,3 +335,25 @@ def particles_couple(engine: D3Q19Engine, ps: ParticleState, reaction: torch.Ten
     st = ps.struct()
     engine._check(engine.lib.lbm_particles_couple(engine._ctx, _ptr(engine.u), _ptr(reaction), C.byref(st), float(rho_w),
                                                   float(mu_w), float(relax), engine.stream), "lbm_particles_couple")
+
+
+def particles_advance(engine: D3Q19Engine, ps: ParticleState, dt: float, center_x: float, center_y: float, bottom_z: float,
+                      bottom_radius_lu: float, top_radius_lu: float, force: Optional[torch.Tensor] = None,
+                      counters: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """CoffeeParticleSystem.update_particle_physics (coffee_particles.py:641-720) on the device.  `force` is the
+    reference's self.force as a [3,n] tensor (zeroed by the call); returns the int32 counters tensor
+    [coordinate_errors, boundary_violations] (accumulated into `counters` when given)."""
+    cfg = engine.cfg
+    cup = np.float32(cfg.CUP_HEIGHT / cfg.SCALE_LENGTH)
+    if not cup > 0:
+        cup = np.float32(50.0)
+    b = L.LbmParticleBounds(center_x=float(center_x), center_y=float(center_y), bottom_z=float(bottom_z),
+                            bottom_radius_lu=float(bottom_radius_lu), top_radius_lu=float(top_radius_lu), cup_height_lu=float(cup),
+                            max_coordinate=float(max(cfg.NX, cfg.NY, cfg.NZ)), nz_minus_5=float(cfg.NZ - 5))
+    if counters is None:
+        counters = torch.zeros(2, dtype=torch.int32, device=ps.pos.device)
+    st = ps.struct()
+    engine._check(engine.lib.lbm_particles_advance(engine._ctx, C.byref(st), _ptr(force) if force is not None else None, C.byref(b),
+                                                   float(dt), _ptr(counters), engine.stream), "lbm_particles_advance")
+    return counters
+

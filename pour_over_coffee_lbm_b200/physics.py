@@ -236,6 +236,25 @@ class CoffeeParticleSystem:
         st = self.state.struct()
         e._check(e.lib.lbm_particles_under_relax(e._ctx, C.byref(st), float(relaxation_factor), e.stream), "lbm_particles_under_relax")
 
+    def update_particle_physics(self, dt: float, center_x: float, center_y: float, bottom_z: float,
+                                bottom_radius_lu: float, top_radius_lu: float) -> None:
+        """coffee_particles.py:641-720 (explicit Euler + cone constraint), called by main.py:672-679 every step."""
+        if getattr(self, "force_tensor", None) is None:
+            self.force_tensor = torch.zeros_like(self.state.pos)
+            self.error_counters = torch.zeros(2, dtype=torch.int32, device=self.state.pos.device)
+        particles_advance(self._solver.engine, self.state, dt, center_x, center_y, bottom_z, bottom_radius_lu, top_radius_lu,
+                          force=self.force_tensor, counters=self.error_counters)
+
+    def update_particles(self, dt: float) -> None:
+        """coffee_particles.py:722-732: the public wrapper with the default V60 bounds."""
+        cfg = self._solver.config
+        self.update_particle_physics(dt, cfg.NX // 2, cfg.NY // 2, cfg.NZ // 4, cfg.BOTTOM_RADIUS / cfg.SCALE_LENGTH,
+                                     cfg.TOP_RADIUS / cfg.SCALE_LENGTH)
+
+    force = property(lambda self: self._pv(self.force_tensor) if getattr(self, "force_tensor", None) is not None else None)
+    coordinate_errors = property(lambda self: int(self.error_counters[0]) if getattr(self, "error_counters", None) is not None else 0)
+    boundary_violations = property(lambda self: int(self.error_counters[1]) if getattr(self, "error_counters", None) is not None else 0)
+
     def get_coupling_diagnostics(self) -> Dict[str, Any]:
         st = self.state
         act = st.active != 0

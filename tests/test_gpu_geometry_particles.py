@@ -147,6 +147,47 @@ def test_particle_cell_indices_bit_exact_and_forces():
     np.testing.assert_array_equal(s.body_force.to_numpy(), got)
 
 
+def test_particle_integrator_bit_exact():
+    """lbm_particles_advance == CoffeeParticleSystem.update_particle_physics restated in the oracle
+    (coffee_particles.py:641-831): free flight, acceleration and displacement caps, cone / bottom / top constraints
+    with damping, invalid coordinates (deactivation), invalid velocities, massless and inactive particles; three
+    consecutive steps so constrained particles move again."""
+    import torch
+    from pour_over_coffee_lbm_b200.config import LBMConfig
+    from pour_over_coffee_lbm_b200.engine import ParticleState, particles_advance
+    n = 64
+    cfg = LBMConfig(NX=n, NY=n, NZ=n)
+    rcfg = R.RefConfig(NX=n, NY=n, NZ=n)
+    eng = _engine(n, n, n, compat="reference", periodic=(False, False, False), walls=True, config=cfg)
+    P = 1500
+    rng = np.random.default_rng(8)
+    bounds = dict(center_x=n // 2, center_y=n // 2, bottom_z=n // 4, bottom_radius_lu=rcfg.BOTTOM_RADIUS / rcfg.SCALE_LENGTH,
+                  top_radius_lu=rcfg.TOP_RADIUS / rcfg.SCALE_LENGTH)
+    pos = np.stack([rng.uniform(-2, n + 2, P), rng.uniform(-2, n + 2, P), rng.uniform(-2, n + 2, P)], 1).astype(np.float32)
+    vel = (rng.standard_normal((P, 3)) * rng.choice([0.05, 5.0, 40.0, 400.0], (P, 1))).astype(np.float32)
+    force = (rng.standard_normal((P, 3)) * rng.choice([1e-9, 1e-6, 1e-2], (P, 1))).astype(np.float32)
+    mass = rng.choice([0.0, 1e-11, 1.7e-7, 3e-7], P).astype(np.float32)
+    active = (rng.random(P) < 0.9).astype(np.int32)
+    pos[:5] = np.nan; vel[5:10, 1] = np.nan; pos[10:15, 2] = np.inf
+    ps = ParticleState(P, eng.device)
+    ps.pos.copy_(_torch(pos.T)); ps.vel.copy_(_torch(vel.T)); ps.mass.copy_(_torch(mass)); ps.active.copy_(_torch(active))
+    f_dev = _torch(force.T).contiguous()
+    counters = torch.zeros(2, dtype=torch.int32, device="cuda")
+    tot = [0, 0]
+    for step, dt in enumerate((5e-3, 1.0, 1e-12)):      # the last two exercise the dt clamp
+        ce, bv = R.update_particle_physics(rcfg, pos, vel, force, mass, active, dt, **bounds)
+        tot[0] += ce; tot[1] += bv
+        particles_advance(eng, ps, dt, force=f_dev, counters=counters, **bounds)
+        got_pos = ps.pos.cpu().numpy().T; got_vel = ps.vel.cpu().numpy().T
+        assert np.array_equal(ps.active.cpu().numpy(), active)
+        act = active == 1
+        assert np.array_equal(got_pos[act], pos[act]) and np.array_equal(got_vel[act], vel[act], equal_nan=True)   # massless particles keep a NaN velocity
+        assert np.array_equal(f_dev.cpu().numpy().T, force, equal_nan=True)
+        force[:] = (rng.standard_normal((P, 3)) * 1e-6).astype(np.float32); f_dev.copy_(_torch(force.T))
+    assert counters.cpu().tolist() == tot
+    assert tot[1] > 0 and tot[0] > 0
+
+
 def test_empty_and_single_particle():
     n = 16
     s, ps = _particle_solver(n)
@@ -194,6 +235,35 @@ def test_pressure_gradient_and_forchheimer_force_bit_exact():
     assert np.array_equal(got, st.body_force)
     zone = (st.filter_zone == 1) & (st.solid == 0)
     assert np.abs(got[zone]).max() > 0          # tests/test_forchheimer.py:31-74: non-zero in the zone
+
+
+def test_fused_field_statistics_match_numpy_and_are_deterministic():
+    """lbm_field_statistics (one pass, device result) against NumPy on a V60 mask with injected NaN / Inf."""
+    import torch
+    n = 48
+    st = H.reference_v60_state(n, seed=7)
+    rng = np.random.default_rng(2)
+    rho = (1.0 + 0.05 * rng.standard_normal(st.rho.shape)).astype(np.float32)
+    u = (0.03 * rng.standard_normal(st.u.shape)).astype(np.float32)
+    fluid = st.solid == 0
+    idx = np.argwhere(fluid)
+    rho[tuple(idx[3])] = np.nan; rho[tuple(idx[40])] = np.inf; u[tuple(idx[77])][1] = np.nan; u[tuple(idx[90])][2] = -np.inf
+    from pour_over_coffee_lbm_b200.config import LBMConfig
+    eng = _engine(n, n, n, compat="reference", periodic=(False, False, False), walls=True, config=LBMConfig(NX=n, NY=n, NZ=n))
+    eng.solid.copy_(_torch(H.to_dev_scalar(st.solid))); eng.pack_flags()
+    eng.rho.copy_(_torch(H.to_dev_scalar(rho))); eng.u.copy_(_torch(H.to_dev_vec(u)))
+    a = eng.field_statistics().clone(); b = eng.field_statistics().clone()
+    assert torch.equal(a, b)                                           # deterministic, bit for bit
+    got = a.cpu().numpy()
+    r = rho[fluid]; uf = u[fluid]
+    um = np.sqrt((uf[:, 0] * uf[:, 0] + uf[:, 1] * uf[:, 1]) + uf[:, 2] * uf[:, 2])
+    rfin = np.isfinite(r); ufin = np.isfinite(um)
+    assert got[0] == um[ufin].max() and got[1] == r[rfin].min() and got[2] == r[rfin].max()
+    assert np.isclose(got[3], r[rfin].astype(np.float64).sum(), rtol=1e-12)
+    ke = 0.5 * r.astype(np.float64) * (uf.astype(np.float64) ** 2).sum(1)
+    assert np.isclose(got[4], ke[rfin & ufin].sum(), rtol=1e-12)
+    assert got[5] == np.isnan(r).sum() + np.isnan(um).sum() and got[6] == np.isinf(r).sum() + np.isinf(um).sum()
+    assert got[7] == fluid.sum()
 
 
 # ---- facades ----------------------------------------------------------------------------------------------
