@@ -12,7 +12,7 @@ args = ap.parse_args()
 n = args.n
 # (vec, block, LBM_TMA_VARIANT): vec = 0 is the TMA-staged kernel (variants: tile 64 x TY, ring depth, CTAs per SM --
 # csrc/lbm_step_tma.cu), vec = 2 / 1 the register-staged kernels
-cases = [(2, 64, 0), (4, 128, 0), (4, 256, 0)] + ([(0, 0, v) for v in (1, 3, 6)] if os.environ.get("LBM_TMA") == "1" else [])
+cases = [(2, 64, 0), (2, 65, 0), (4, 256, 0)] + ([(0, 0, v) for v in (1, 3, 6)] if os.environ.get("LBM_TMA") == "1" else [])
 for strict in (True,):       # compat = physical has a single build
     for vec, block, variant in cases:
         os.environ["LBM_TMA_VARIANT"] = str(variant)
