@@ -305,6 +305,31 @@ class D3Q19Engine:
         return int((own == 0).sum().item())
 
 
+def v60_fluid_cells_per_plane(cfg, device=0) -> list:
+    """Fluid-cell count of every z plane of the global V60 box `cfg` (FilterPaperSystem._setup_v60_geometry,
+    filter_paper.py:206-286, evaluated by lbm_build_v60_geometry into a temporary u8 mask: 1 B per cell, no populations).
+    Input of slab.partition_z_balanced."""
+    lib = L.lib()
+    dev = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+    p = L.LbmParams(nx=cfg.NX, ny=cfg.NY, nz=cfg.NZ, nz_global=cfg.NZ, z0=0, zghost=0, periodic=0, compat=L.COMPAT_PHYSICAL,
+                    features=L.FEAT_WALLS, tau_water=0.6, tau_air=0.8, gravity_lu=0.0, cs_smag=0.18, tau_min=0.55, tau_max=1.9)
+    ctx = C.c_void_p()
+    if lib.lbm_create(C.byref(ctx), dev.index or 0, C.byref(p)) != 0:
+        raise BackendInitializationError(lib.lbm_last_error(None).decode(), "b200", "INIT_FAILED")
+    try:
+        with torch.cuda.device(dev):
+            solid = torch.zeros((cfg.NZ, cfg.NY, cfg.NX), dtype=torch.uint8, device=dev)
+            geom = (C.c_float * 5)(*cfg.v60_geometry_constants())
+            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            if lib.lbm_build_v60_geometry(ctx, _ptr(solid), None, geom, stream) != 0:
+                raise ComputeExecutionError(lib.lbm_last_error(ctx).decode(), "b200", "EXECUTION_FAILED")
+            counts = (solid == 0).sum(dim=(1, 2)).tolist()
+            del solid
+    finally:
+        lib.lbm_destroy(ctx)
+    return counts
+
+
 class ParticleState:
     """SoA particle arrays on the device (CoffeeParticleSystem fields, coffee_particles.py:30-60)."""
 

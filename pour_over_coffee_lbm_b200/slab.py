@@ -46,6 +46,30 @@ def partition_z(nz_global: int, world: int) -> List[Slab]:
     return out
 
 
+def partition_z_balanced(plane_weight, world: int, min_planes: int = 1) -> List[Slab]:
+    """Plane-aligned slabs of (nearly) equal WORK instead of equal thickness: `plane_weight[z]` is the cost
+    of plane z -- for a V60 box its fluid-cell count, which grows with z through the cone, so equal-thickness slabs leave
+    the lowest rank with a third of the mean load.  Greedy cut at the prefix-sum targets k/world, every slab keeps at
+    least `min_planes` planes; deterministic, so every rank computes the same partition from the same weights."""
+    w = [float(x) for x in plane_weight]
+    nzg = len(w)
+    if world < 1 or nzg < world * min_planes:
+        raise ValueError("need at least min_planes planes per rank")
+    total = sum(w)
+    if not total > 0:
+        return partition_z(nzg, world)
+    cuts, acc, z = [0], 0.0, 0
+    for r in range(1, world):
+        target = total * r / world
+        lo = cuts[-1] + min_planes                       # earliest admissible cut
+        hi = nzg - (world - r) * min_planes              # latest admissible cut
+        while z < hi and (z < lo or acc + 0.5 * w[z] < target):
+            acc += w[z]; z += 1
+        cuts.append(z)
+    cuts.append(nzg)
+    return [Slab(r, world, cuts[r], cuts[r + 1] - cuts[r], nzg) for r in range(world)]
+
+
 def neighbours(rank: int, world: int, periodic_z: bool) -> Tuple[Optional[int], Optional[int]]:
     """(rank below, rank above) or None at a non-periodic end of the chain."""
     down = rank - 1 if rank > 0 else (world - 1 if periodic_z else None)

@@ -65,3 +65,28 @@ def test_single_rank_periodic_self_exchange():
     for q in slab.UP_Q: assert torch.equal(g[q, 0], before[q, 4])
     for q in slab.DOWN_Q: assert torch.equal(g[q, 5], before[q, 1])
     assert torch.equal(g[:, 1:5], before[:, 1:5])
+
+
+def test_partition_z_balanced_equalises_work_and_stays_contiguous():
+    """slab.partition_z_balanced: plane-aligned, contiguous, covers the box, min_planes respected, and the
+    heaviest slab of a cone-like weight profile is within one plane of the mean (equal thickness is 1.5x off)."""
+    from pour_over_coffee_lbm_b200 import slab
+    nz = 512
+    w = [0 if z < 5 else (16 + 0.56 * (z - 5)) ** 2 for z in range(nz)]       # cone cross-section ~ r(z)^2
+    for world in (1, 2, 3, 4, 8):
+        parts = slab.partition_z_balanced(w, world, min_planes=3)
+        assert [p.rank for p in parts] == list(range(world))
+        assert parts[0].z0 == 0 and parts[-1].z0 + parts[-1].nz == nz
+        assert all(a.z0 + a.nz == b.z0 for a, b in zip(parts, parts[1:]))
+        assert all(p.nz >= 3 and p.nz_global == nz for p in parts)
+        loads = [sum(w[p.z0:p.z0 + p.nz]) for p in parts]
+        mean = sum(w) / world
+        assert max(loads) <= mean + max(w) + 1e-9
+        eq = [sum(w[p.z0:p.z0 + p.nz]) for p in slab.partition_z(nz, world)]
+        assert max(loads) <= max(eq) + 1e-9
+    # degenerate weights fall back to equal thickness; too few planes is an error
+    assert [p.nz for p in slab.partition_z_balanced([0.0] * 8, 4)] == [2, 2, 2, 2]
+    import pytest
+    with pytest.raises(ValueError):
+        slab.partition_z_balanced([1.0] * 5, 4, min_planes=2)
+
