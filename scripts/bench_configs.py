@@ -125,15 +125,17 @@ def main():
             ms_p = timed(lambda: particles_couple(eng, ps, react, relax=0.8), args.steps, args.warmup)
 
             def coupled():
-                eng.clear_body_force()
+                # step_with_two_way_coupling (legacy/lbm_solver.py:1485-1509) + the drive.  body_force = drive + reaction:
+                # the drive is WRITTEN first (no clear pass), the reaction added on top -- the same two-term f32 sum as
+                # clear -> += reaction -> += drive
+                eng.set_pressure_gradient_force(0.12, 1.0)
                 particles_couple(eng, ps, react, relax=0.8)
                 eng.add_reaction_force(react)
-                eng.add_pressure_gradient_force(0.12, 1.0)
                 eng.step(1, write_macro_every=1)
             ms = timed(coupled, args.steps, args.warmup)
             report(f"v60_{n}_particles_1M", eng, ms, 165,
                    {"particle_kernel_ms": ms_p, "particle_fraction_of_step": ms_p / ms, "particles": P,
-                    "note": "step_with_two_way_coupling sequence: clear, couple (gather+drag+scatter+relax, incl. memset of reaction), add reaction, drive, step"})
+                    "note": "step_with_two_way_coupling sequence: drive (written), couple (gather+drag+scatter+relax, incl. memset of reaction), add reaction, step"})
         del eng
 
     if want("ref_224"):
