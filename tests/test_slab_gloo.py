@@ -24,7 +24,7 @@ def _slab_step(g_loc, p_loc, solid_loc):
     return g2, rho, u
 
 
-def _worker(rank, world, port, periodic_z, out):
+def _worker(rank, world, port, periodic_z, out, balanced=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from pour_over_coffee_lbm_b200 import slab
@@ -34,7 +34,10 @@ def _worker(rank, world, port, periodic_z, out):
     if not periodic_z:
         solid[:, :, 0] = 1; solid[:, :, -1] = 1; solid[4:7, 4:7, 6:10] = 1      # walls + an obstacle across the interface
     g_glob = R.init_equilibrium_phys(rho0, u0)
-    part = slab.partition_z(nzg, world)[rank]
+    if balanced:      # unequal slab thicknesses: cuts at the prefix sums of the per-plane fluid count (slab.partition_z_balanced)
+        part = slab.partition_z_balanced([(z + 1) ** 2 * float((solid[:, :, z] == 0).sum()) for z in range(nzg)], world, min_planes=2)[rank]
+    else:
+        part = slab.partition_z(nzg, world)[rank]
     z0, nz = part.z0, part.nz
     zs = np.arange(z0 - 1, z0 + nz + 1) % nzg                                      # owned + ghost planes (wrapped indices)
     g = torch.from_numpy(H.to_dev_pop(g_glob[:, :, :, zs]))                        # device layout [q, z, y, x]
@@ -64,12 +67,14 @@ def _worker(rank, world, port, periodic_z, out):
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("balanced", [False, True])
 @pytest.mark.parametrize("periodic_z", [True, False])
-def test_two_gloo_ranks_reproduce_single_domain(periodic_z):
+def test_two_gloo_ranks_reproduce_single_domain(periodic_z, balanced):
+    """balanced: work-balanced slabs of unequal thickness (11 + 5 planes here) exchange the same 5+5 planes."""
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, periodic_z, out)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, periodic_z, out, balanced)) for r in range(2)]
     for p in procs: p.start()
     for p in procs: p.join(timeout=240)
     for p in procs:
