@@ -1,16 +1,22 @@
 """CPU ORACLE (test infrastructure, NOT product code) -- NumPy restatement of the
 reference's D3Q19 time step.
 
-PARITY STATUS: "parity unpinned" for the step trajectory.  The reference
-(latteine1217/pour-over-coffee-lbm) is pure Python + Taichi; Taichi is not
-installable in the authoring container (no wheel, no network), so the reference
-step cannot be executed here and it owns no golden trajectory.
-What IS pinned: every known-answer identity the reference's own tests hold for
-this path (lattice identities, equilibrium moments, the 10-point trilinear
-table, LES zero/mask properties, Forchheimer sign/mask) -- see
-tests/test_oracle_known_answers.py.  Everything else follows the reference
-source line by line; each function cites the file:line it restates
-(paths relative to the reference root).
+PARITY STATUS: pinned against the reference's own source code.  The reference
+(latteine1217/pour-over-coffee-lbm) is pure Python + Taichi, and Taichi is not
+installable in the authoring container (no wheel, no network) -- but its kernels are
+plain Python functions, so tests/golden/make_reference_goldens.py imports the
+UNMODIFIED reference modules from /root/reference under a small pure-Python stand-in
+for the `taichi` package (tests/golden/taichi_shim: fields = NumPy arrays, IEEE f32
+scalar arithmetic in source order, constants folded like Taichi folds them) and
+records what LBMSolver.step(), FilterPaperSystem (geometry, Forchheimer),
+PressureGradientDrive and CoffeeParticleSystem (coupling, under-relaxation,
+integrator) compute on seeded 16^3 states.  This module reproduces every recorded
+output BIT FOR BIT (tests/test_oracle_vs_reference_run.py; fixtures
+tests/golden/reference_run_*.npz).  Not covered by that pin: Taichi's own code
+generation on a real back end (fast-math reassociation / FMA contraction), which no
+source-level restatement can see.  Also pinned: every known-answer identity the
+reference's own tests hold for this path -- tests/test_oracle_known_answers.py.
+Each function cites the file:line it restates (paths relative to the reference root).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import
 this module.  The product path (pour_over_coffee_lbm_b200) never does.

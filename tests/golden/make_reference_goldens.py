@@ -1,0 +1,205 @@
+#!/usr/bin/env python
+"""Pins the oracle to the REFERENCE'S OWN SOURCE CODE (run in the authoring container, where /root/reference exists).
+
+The reference is Python + Taichi and Taichi cannot be installed here, so its kernels are executed by a small pure-Python
+stand-in for the `taichi` package (tests/golden/taichi_shim: fields = NumPy arrays, IEEE f32 scalar arithmetic in source
+order, see its docstring).  This script imports the reference's unmodified modules from /root/reference on a small grid
+(config/core.py is loaded with NX = NY = NZ patched -- the only change, done in memory), drives LBMSolver.step() and the
+neighbour kernels on seeded inputs, and writes the inputs and what the reference's code computed to
+tests/golden/reference_run_*.npz.  tests/test_oracle_vs_reference_run.py (CPU) checks oracle/ against these fixtures;
+the GPU parity tests check the CUDA kernels against the same files.  Nothing under tests/ reads /root/reference.
+"""
+import importlib.util
+import io
+import contextlib
+import os
+import re
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+
+
+def load_reference(n: int):
+    """Import the reference with the Taichi stand-in and an n^3 grid.  Returns the `config` module."""
+    sys.path.insert(0, os.path.join(HERE, "taichi_shim"))
+    sys.path.insert(1, REF)
+    src = open(os.path.join(REF, "config", "core.py")).read()
+    for name in ("NX", "NY", "NZ"):
+        src, k = re.subn(rf"^{name} = 224\s*$", f"{name} = {n}", src, flags=re.M)
+        assert k == 1, name
+
+    core = types.ModuleType("config.core"); core.__file__ = os.path.join(REF, "config", "core.py")
+    exec(compile(src, core.__file__, "exec"), core.__dict__)
+    sys.modules["config.core"] = core
+    with contextlib.redirect_stdout(io.StringIO()):
+        import config
+    assert config.NX == n and sys.modules["config.core"] is core
+    return config
+
+
+def quiet():
+    return contextlib.redirect_stdout(io.StringIO())
+
+
+def run_step_scenario(config, n, steps, seed, gravity, phase_mode):
+    """LBMSolver + FilterPaperSystem wired like main.py (main.py:560-640), seeded state, `steps` calls of step()."""
+    sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, ROOT)
+    import helpers as H
+    config.GRAVITY_LU = gravity          # an input (config/physics.py value saturates every clamp); read at kernel time
+    with quiet():
+        from src.core.legacy.lbm_solver import LBMSolver
+        from src.physics.filter_paper import FilterPaperSystem
+        s = LBMSolver()
+        s.init_fields()
+        fp = FilterPaperSystem(s)
+        fp.initialize_filter_geometry()
+        s.boundary_manager.set_filter_system(fp)
+    # the same seeded inputs tests/helpers.py:reference_v60_state builds for the oracle
+    st = H.reference_v60_state(n, seed=seed, gravity=gravity, body=1e-5, phase_mode=phase_mode)
+    inp = dict(f=st.f.copy(), phase=st.phase.copy(), body_force=st.body_force.copy())
+    s.f.from_numpy(inp["f"]); s.f_new.from_numpy(inp["f"]); s.phase.from_numpy(inp["phase"]); s.body_force.from_numpy(inp["body_force"])
+    geom = dict(solid=s.solid.to_numpy().astype(np.uint8), filter_zone=fp.filter_zone.to_numpy().astype(np.int32),
+                les_mask=s.les_mask.to_numpy().astype(np.int32))
+    with quiet():
+        for _ in range(steps):
+            s.step()
+    out = dict(rho=s.rho.to_numpy(), u=s.u.to_numpy(), f_out=s.f.to_numpy())
+    if hasattr(s, "les_model") and s.les_model is not None and hasattr(s.les_model, "nu_sgs"):
+        out["nu_sgs"] = s.les_model.nu_sgs.to_numpy()
+    return inp, geom, out, st
+
+
+def run_neighbour_scenario(config, n, seed):
+    """Body-force producers and the particle kernels of the reference on one seeded state:
+    PressureGradientDrive (force and mixed mode), FilterPaperSystem.compute_forchheimer_resistance,
+    CoffeeParticleSystem.compute_two_way_coupling_forces / apply_under_relaxation / update_particle_physics."""
+    sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, ROOT)
+    import helpers as H
+    with quiet():
+        from src.core.legacy.lbm_solver import LBMSolver
+        from src.physics.filter_paper import FilterPaperSystem
+        from src.physics.pressure_gradient_drive import PressureGradientDrive
+        from src.physics.coffee_particles import CoffeeParticleSystem
+        s = LBMSolver(); s.init_fields()
+        fp = FilterPaperSystem(s); fp.initialize_filter_geometry()
+        pg = PressureGradientDrive(s)
+    rng = np.random.default_rng(seed)
+    shp = (n, n, n)
+    rho = (1.0 + 0.05 * rng.standard_normal(shp)).astype(np.float32)
+    u = (0.02 * rng.standard_normal(shp + (3,))).astype(np.float32)
+    s.rho.from_numpy(rho); s.u.from_numpy(u)
+    res = dict(n=n, rho=rho, u=u, solid=s.solid.to_numpy().astype(np.uint8), filter_zone=fp.filter_zone.to_numpy().astype(np.int32))
+    with quiet():
+        s.body_force.fill(0.0); pg.activate_force_drive(True); pg.apply(0)
+        res["bf_force_drive"] = s.body_force.to_numpy()
+        s.body_force.fill(0.0); pg.activate_mixed_drive(True); pg.apply(0)
+        res["bf_mixed_drive"] = s.body_force.to_numpy()
+        fp.compute_forchheimer_resistance()
+        res["bf_mixed_plus_forchheimer"] = s.body_force.to_numpy()
+    # ---- particles ----
+    P = 400
+    with quiet():
+        ps = CoffeeParticleSystem(P)
+    pos = rng.uniform(-1.0, n + 1.0, (P, 3)).astype(np.float32)
+    pos[:40] = rng.uniform(3.0, n - 4.0, (40, 3)).astype(np.float32)       # some surely in the bulk
+    vel = (rng.standard_normal((P, 3)) * rng.choice([1e-3, 0.05, 5.0, 40.0], (P, 1))).astype(np.float32)
+    radius = np.clip(rng.normal(3.25e-4, 1e-4, P), 1.6e-4, 4.9e-4).astype(np.float32)
+    mass = ((np.float32(4.0 / 3.0) * np.float32(3.14159)) * (radius * radius * radius) * np.float32(config.COFFEE_BEAN_DENSITY)).astype(np.float32)
+    mass[::17] = 0.0
+    active = (rng.random(P) < 0.9).astype(np.int32)
+    ps.position.from_numpy(pos); ps.velocity.from_numpy(vel); ps.radius.from_numpy(radius); ps.mass.from_numpy(mass); ps.active.from_numpy(active)
+    old = (1e-9 * rng.standard_normal((P, 3))).astype(np.float32)
+    ps.drag_force_old.from_numpy(old)
+    with quiet():
+        ps.compute_two_way_coupling_forces(s.u)
+        res.update(p_pos=pos, p_vel=vel, p_radius=radius, p_mass=mass, p_active=active, p_drag_old_in=old,
+                   p_drag_new=ps.drag_force_new.to_numpy(), p_reaction=ps.reaction_force_field.to_numpy(),
+                   p_u_fluid=ps.fluid_velocity_at_particle.to_numpy(), p_reynolds=ps.particle_reynolds.to_numpy(),
+                   p_cd=ps.drag_coefficient.to_numpy())
+        ps.apply_under_relaxation(0.8)
+        res.update(p_drag=ps.drag_force.to_numpy(), p_drag_old_out=ps.drag_force_old.to_numpy())
+        # integrator: three calls (dt clamp on the 2nd / 3rd), forces set before each
+        b = fp.get_coffee_bed_boundary()
+        res["bounds"] = np.array([b["center_x"], b["center_y"], b["bottom_z"], b["bottom_radius_lu"], b["top_radius_lu"]], np.float64)
+        force = (rng.standard_normal((P, 3)) * rng.choice([1e-9, 1e-6, 1e-2], (P, 1))).astype(np.float32)
+        ps.force.from_numpy(force)
+        res["p_force_in"] = force
+        dts = (5e-3, 1.0, 1e-12)
+        for t, dt in enumerate(dts):
+            ps.update_particle_physics(dt, b["center_x"], b["center_y"], b["bottom_z"], b["bottom_radius_lu"], b["top_radius_lu"])
+            res[f"adv{t}_pos"] = ps.position.to_numpy(); res[f"adv{t}_vel"] = ps.velocity.to_numpy(); res[f"adv{t}_active"] = ps.active.to_numpy()
+        res["adv_dts"] = np.array(dts); res["adv_counters"] = np.array([ps.coordinate_errors[None], ps.boundary_violations[None]])
+    return res
+
+
+def check_neighbours_against_oracle(res):
+    from oracle import d3q19_ref as R
+    n = int(res["n"])
+    cfg = R.RefConfig(NX=n, NY=n, NZ=n)
+    st = R.init_fields(cfg); R.attach_filter_system(st)
+    st.rho = res["rho"].copy(); st.u = res["u"].copy()
+    ok = {}
+    ok["solid"] = np.array_equal(st.solid, res["solid"]); ok["zone"] = np.array_equal(st.filter_zone, res["filter_zone"])
+    st.body_force[:] = 0; R.accumulate_pressure_force(st, R.pressure_gradient_force(st, 0.12), 1.0)
+    ok["force_drive"] = np.array_equal(st.body_force, res["bf_force_drive"])
+    st.body_force[:] = 0; R.accumulate_pressure_force(st, R.pressure_gradient_force(st, 0.12), 0.5)
+    ok["mixed_drive"] = np.array_equal(st.body_force, res["bf_mixed_drive"])
+    R.compute_forchheimer_resistance(st)
+    ok["forchheimer"] = np.array_equal(st.body_force, res["bf_mixed_plus_forchheimer"])
+    dn, react, ufl, re_p, cd, cell = R.two_way_coupling(cfg, st.u, res["p_pos"], res["p_vel"], res["p_radius"], res["p_mass"], res["p_active"])
+    act = res["p_active"] != 0
+    ok["drag_new"] = np.array_equal(dn[act], res["p_drag_new"][act]); ok["u_fluid"] = np.array_equal(ufl[act], res["p_u_fluid"][act])
+    ok["reynolds"] = np.array_equal(re_p[act], res["p_reynolds"][act])
+    ok["cd_close"] = bool(np.allclose(cd[act], res["p_cd"][act], rtol=3e-7, atol=0))
+    ok["reaction_close"] = bool(np.allclose(react, res["p_reaction"], rtol=1e-5, atol=1e-12))
+    drag, new_old = R.under_relax(res["p_drag_new"], res["p_drag_old_in"], res["p_active"], 0.8)
+    ok["under_relax"] = np.array_equal(drag[act], res["p_drag"][act]) and np.array_equal(new_old[act], res["p_drag_old_out"][act])
+    pos = res["p_pos"].copy(); vel = res["p_vel"].copy(); force = res["p_force_in"].copy(); active = res["p_active"].copy()
+    cx, cy, bz, br, tr = [float(v) for v in res["bounds"]]
+    tot = [0, 0]; adv = True
+    for t, dt in enumerate(res["adv_dts"]):
+        ce, bv = R.update_particle_physics(cfg, pos, vel, force, res["p_mass"], active, float(dt), cx, cy, bz, br, tr)
+        tot[0] += ce; tot[1] += bv
+        a = active == 1
+        adv &= np.array_equal(active, res[f"adv{t}_active"]) and np.array_equal(pos[a], res[f"adv{t}_pos"][a]) and \
+            np.array_equal(vel[a], res[f"adv{t}_vel"][a], equal_nan=True)
+    ok["integrator"] = bool(adv); ok["integrator_counters"] = tot == [int(v) for v in res["adv_counters"]]
+    return ok
+
+
+if __name__ == "__main__":
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+    config = load_reference(n)
+    import time
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle import d3q19_ref as R
+    all_ok = True
+    default_gravity = float(config.GRAVITY_LU)
+    scenarios = [("split_phase_small_gravity", 4, 31, 2e-5, "split"), ("water_default_gravity", 3, 32, default_gravity, "water"),
+                 ("air_phase", 6, 33, 1e-4, "none")]
+    for name, steps, seed, gravity, phase_mode in scenarios:
+        t = time.time()
+        inp, geom, out, st = run_step_scenario(config, n, steps, seed=seed, gravity=gravity, phase_mode=phase_mode)
+        geo_ok = np.array_equal(geom["solid"], st.solid) and np.array_equal(geom["filter_zone"], st.filter_zone) and np.array_equal(geom["les_mask"], st.les_mask)
+        for _ in range(steps):
+            R.step(st)
+        fluid = geom["solid"] == 0
+        ok = geo_ok and np.array_equal(out["rho"][fluid], st.rho[fluid]) and np.array_equal(out["u"][fluid], st.u[fluid]) and \
+            np.array_equal(out["f_out"][:, fluid], st.f[:, fluid])
+        nu_active = int((out.get("nu_sgs", np.zeros(1)) > 0).sum())
+        print(f"[reference run] {name}: n={n} steps={steps} gravity={gravity:g}  reference {time.time() - t:.1f} s  oracle bit-exact: {ok}  (LES active cells: {nu_active})")
+        all_ok &= bool(ok)
+        np.savez_compressed(os.path.join(HERE, f"reference_run_step_{name}.npz"), n=n, steps=steps, gravity=gravity, seed=seed,
+                            phase_mode=phase_mode, **inp, **geom, **out)
+    res = run_neighbour_scenario(config, n, seed=41)
+    ok = check_neighbours_against_oracle(res)
+    print("[reference run] neighbours / particles vs oracle:", ok)
+    all_ok &= all(ok.values())
+    np.savez_compressed(os.path.join(HERE, "reference_run_neighbours.npz"), **res)
+    print("ALL OK" if all_ok else "MISMATCH")
+    sys.exit(0 if all_ok else 1)

@@ -1,0 +1,653 @@
+"""A minimal pure-Python stand-in for the `taichi` package -- TEST INFRASTRUCTURE ONLY.
+
+Purpose: the reference (pour-over-coffee-lbm) is Python + Taichi and Taichi cannot be installed in the authoring
+container.  This shim lets the reference's OWN source files import and run, statement by statement, on tiny grids, so
+that tests/golden/make_reference_goldens.py can record what the reference's code computes and pin oracle/ to it.
+
+Semantics reproduced (Taichi defaults: default_fp = f32, default_ip = i32):
+  * fields are NumPy arrays; a load yields a NumPy scalar of the field's dtype, a store casts to it;
+  * float literals and Python-scope float constants (config.X, self.x, module globals) stay Python floats while they
+    only meet each other -- Taichi folds constant sub-expressions in Python, i.e. in f64 -- and become f32 the moment they
+    meet a kernel value (NumPy's weak-scalar promotion does exactly that) or are stored: assigned to a local variable,
+    passed to / returned from a @ti.func, put into a vector or a field (AST rewrite).  Everything else is IEEE f32
+    arithmetic in source order, one rounding per operation (NumPy scalar arithmetic);
+  * kernel arguments annotated ti.f32 / ti.i32 are cast on entry; ti.cast(x, ti.i32) truncates toward zero;
+  * vectors copy on load (`a = field[i]`), component stores write through (`field[i][0] = v`, `field[i].x = v`);
+  * ti.atomic_add(field[idx], v) is a plain read-modify-write (the emulator is sequential, loops run in index order).
+Not reproduced: Taichi's code generation (fast-math reassociation / FMA contraction on a real back end), parallel order
+of atomics.  Only what the hot-path files of the reference use is implemented.
+"""
+from __future__ import annotations
+
+import ast
+import functools
+import inspect
+import itertools
+import math as _math
+import textwrap
+import types
+
+import numpy as np
+
+f32 = np.float32
+f64 = np.float64
+i32 = np.int32
+i64 = np.int64
+u8 = np.uint8
+u32 = np.uint32
+i8 = np.int8
+cpu = "cpu"; gpu = "gpu"; cuda = "cuda"; metal = "metal"; vulkan = "vulkan"; opengl = "opengl"; x64 = "x64"; arm64 = "arm64"
+__version__ = (1, 7, 3)
+
+
+class _Cfg:
+    arch = "cpu"
+    default_fp = f32
+    default_ip = i32
+
+    def __getattr__(self, k):
+        return None
+
+
+cfg = _Cfg()
+lang = types.SimpleNamespace(impl=types.SimpleNamespace(current_cfg=lambda: cfg))
+
+
+def init(*a, **k):
+    return None
+
+
+def reset():
+    return None
+
+
+def sync():
+    return None
+
+
+def template():
+    return "template"
+
+
+def loop_config(**k):
+    return None
+
+
+def static(x, *more):
+    return x
+
+
+def grouped(x):
+    return iter(x)
+
+
+def ndrange(*args):
+    rs = []
+    for a in args:
+        if isinstance(a, (tuple, list)):
+            rs.append(range(int(a[0]), int(a[1])))
+        else:
+            rs.append(range(int(a)))
+    return itertools.product(*rs)
+
+
+def _is_float(x):
+    return isinstance(x, (float, np.floating))
+
+
+def _f(x):
+    return x if isinstance(x, np.float32) else np.float32(x)
+
+
+def _const(x):
+    """Python-scope float constant read inside a kernel: an f32 value (Taichi casts compile-time constants to default_fp)."""
+    return np.float32(x) if type(x) is float else x
+
+
+# ---- scalar intrinsics --------------------------------------------------------------------------------------------
+def cast(x, dt):
+    if isinstance(x, Vec):
+        return Vec([cast(c, dt) for c in x.v])
+    if dt in (i32, i64, u8, u32, i8, int):
+        return int(x)                      # C-style truncation toward zero
+    return dt(x)
+
+
+def _promote(a, b):
+    if isinstance(a, Vec) or isinstance(b, Vec):
+        return a, b
+    if isinstance(a, np.floating) or isinstance(b, np.floating):
+        return _f(a), _f(b)
+    return a, b
+
+
+def max(a, b, *rest):  # noqa: A001
+    a, b = _promote(a, b)
+    if isinstance(a, Vec) or isinstance(b, Vec):
+        r = _vec_binop(a, b, lambda p, q: max(p, q))
+    else:
+        r = a if a >= b else b
+        if b != b: r = b
+    for c in rest:
+        r = max(r, c)
+    return r
+
+
+def min(a, b, *rest):  # noqa: A001
+    a, b = _promote(a, b)
+    if isinstance(a, Vec) or isinstance(b, Vec):
+        r = _vec_binop(a, b, lambda p, q: min(p, q))
+    else:
+        r = a if a <= b else b
+        if b != b: r = b
+    for c in rest:
+        r = min(r, c)
+    return r
+
+
+def _pyconst(*xs):
+    return all(type(x) in (float, int) for x in xs)
+
+
+def sqrt(x):
+    if _pyconst(x):
+        return _math.sqrt(x)          # constant folded in Python, like Taichi does at compile time
+    return np.sqrt(_f(x))
+
+
+def exp(x):
+    if _pyconst(x):
+        return _math.exp(x)
+    return np.exp(_f(x))
+
+
+def log(x):
+    if _pyconst(x):
+        return _math.log(x)
+    return np.log(_f(x))
+
+
+def pow(a, b):  # noqa: A001
+    if _pyconst(a, b):
+        return float(a) ** b
+    return np.power(_f(a), _f(b))
+
+
+def abs(x):  # noqa: A001
+    if isinstance(x, Vec):
+        return Vec([abs(c) for c in x.v])
+    return -x if x < 0 else x
+
+
+def floor(x):
+    return np.floor(_f(x))
+
+
+def copysign(a, b):
+    return np.copysign(_f(a), _f(b))
+
+
+def random(dt=f32):
+    raise NotImplementedError("ti.random is not emulated (not on the hot path)")
+
+
+def atomic_add(target, v):           # only reached when the AST rewrite did not apply (local accumulators)
+    return target
+
+
+math = types.SimpleNamespace(isnan=lambda x: x != x, isinf=lambda x: bool(np.isinf(x)), pi=_math.pi,
+                             sqrt=sqrt, exp=exp, pow=pow, floor=floor, min=min, max=max,
+                             clamp=lambda x, lo, hi: max(lo, min(hi, x)))
+
+
+# ---- vectors ------------------------------------------------------------------------------------------------------
+def _vec_binop(a, b, op):
+    if isinstance(a, Vec) and isinstance(b, Vec):
+        return Vec([op(p, q) for p, q in zip(a.v, b.v)])
+    if isinstance(a, Vec):
+        return Vec([op(p, b) for p in a.v])
+    return Vec([op(a, q) for q in b.v])
+
+
+class Vec:
+    """A small value-type vector: element-wise IEEE arithmetic on NumPy scalars, left-to-right reductions."""
+    __slots__ = ("v",)
+    __array_ufunc__ = None           # NumPy scalars defer to the reflected operators below
+    __array_priority__ = 1000
+
+    def __init__(self, vals, dt=None):
+        vals = list(vals.v) if isinstance(vals, Vec) else list(vals)
+        if dt is not None:
+            vals = [cast(x, dt) if dt in (i32, i64) else dt(x) for x in vals]
+        else:
+            vals = [np.float32(x) if type(x) is float else x for x in vals]
+        self.v = vals
+
+    n = property(lambda self: len(self.v))
+
+    def __len__(self): return len(self.v)
+    def __iter__(self): return iter(self.v)
+    def __getitem__(self, i): return self.v[int(i)]
+    def __setitem__(self, i, x): self.v[int(i)] = x
+    x = property(lambda s: s.v[0], lambda s, val: s.v.__setitem__(0, val))
+    y = property(lambda s: s.v[1], lambda s, val: s.v.__setitem__(1, val))
+    z = property(lambda s: s.v[2], lambda s, val: s.v.__setitem__(2, val))
+
+    def _f32(self):
+        return [_f(c) for c in self.v]
+
+    def __add__(s, o): return _vec_binop(s, o, lambda p, q: _arith(p, q, "+"))
+    def __radd__(s, o): return _vec_binop(o, s, lambda p, q: _arith(p, q, "+"))
+    def __sub__(s, o): return _vec_binop(s, o, lambda p, q: _arith(p, q, "-"))
+    def __rsub__(s, o): return _vec_binop(o, s, lambda p, q: _arith(p, q, "-"))
+    def __mul__(s, o): return _vec_binop(s, o, lambda p, q: _arith(p, q, "*"))
+    def __rmul__(s, o): return _vec_binop(o, s, lambda p, q: _arith(p, q, "*"))
+    def __truediv__(s, o): return _vec_binop(s, o, lambda p, q: _arith(p, q, "/"))
+    def __rtruediv__(s, o): return _vec_binop(o, s, lambda p, q: _arith(p, q, "/"))
+    def __neg__(s): return Vec([-c for c in s.v])
+
+    def dot(s, o):
+        acc = None
+        for p, q in zip(s.v, o.v):
+            t = _arith(p, q, "*")
+            acc = t if acc is None else _arith(acc, t, "+")
+        return acc
+
+    def norm_sqr(s):
+        return s.dot(s)
+
+    def norm(s, eps=None):
+        r = s.norm_sqr()
+        if eps is not None:
+            r = _arith(r, eps, "+")
+        return sqrt(r)
+
+    def normalized(s, eps=0):
+        return s / s.norm(eps if eps else None)
+
+    def cast(s, dt):
+        return Vec([cast(c, dt) for c in s.v])
+
+    def to_numpy(s):
+        return np.array(s.v)
+
+    def __repr__(s):
+        return f"Vec({s.v})"
+
+
+def _arith(p, q, op):
+    if type(p) is float: p = np.float32(p)
+    if type(q) is float: q = np.float32(q)
+    with np.errstate(all="ignore"):
+        if op == "+": return p + q
+        if op == "-": return p - q
+        if op == "*": return p * q
+        return _f(p) / _f(q) if not (_is_float(p) or _is_float(q)) else p / q
+
+
+class _VectorFactory:
+    def __call__(self, vals, dt=None):
+        return Vec(vals, dt)
+
+    @staticmethod
+    def field(n, dtype, shape=(), **kw):
+        return VectorField(n, dtype, shape)
+
+    @staticmethod
+    def zero(dt, n):
+        return Vec([dt(0)] * n)
+
+    @staticmethod
+    def one(dt, n):
+        return Vec([dt(1)] * n)
+
+
+Vector = _VectorFactory()
+
+
+class Mat:
+    """Row-major small matrix, indexed m[i, j]."""
+    __slots__ = ("rows",)
+    __array_ufunc__ = None
+
+    def __init__(self, rows, dt=None):
+        self.rows = [Vec(r, dt) for r in rows]
+
+    def __getitem__(self, ij):
+        i, j = ij
+        return self.rows[int(i)].v[int(j)]
+
+    def __setitem__(self, ij, x):
+        i, j = ij
+        self.rows[int(i)].v[int(j)] = x
+
+
+class _MatrixFactory:
+    def __call__(self, rows, dt=None):
+        return Mat(rows, dt)
+
+    @staticmethod
+    def field(n, m, dtype, shape=(), **kw):
+        raise NotImplementedError("ti.Matrix.field is not emulated")
+
+
+Matrix = _MatrixFactory()
+
+
+# ---- fields -------------------------------------------------------------------------------------------------------
+def _shape(shape):
+    if shape is None:
+        return ()
+    if isinstance(shape, (int, np.integer)):
+        return (int(shape),)
+    return tuple(int(s) for s in shape)
+
+
+def _idx(idx):
+    if idx is None:
+        return ()
+    if isinstance(idx, Vec):
+        return tuple(int(c) for c in idx.v)
+    if isinstance(idx, tuple):
+        return tuple(int(i) for i in idx)
+    return (int(idx),)
+
+
+class Field:
+    def __init__(self, dtype, shape=()):
+        self.dtype = dtype
+        self.a = np.zeros(_shape(shape), dtype)
+
+    shape = property(lambda s: s.a.shape)
+
+    def __getitem__(self, idx):
+        return self.a[_idx(idx)]
+
+    def __setitem__(self, idx, v):
+        with np.errstate(all="ignore"):
+            if np.issubdtype(self.a.dtype, np.integer) and _is_float(v):
+                v = int(v)
+            self.a[_idx(idx)] = v
+
+    def _atomic_add(self, idx, v):
+        old = self[idx]
+        with np.errstate(all="ignore"):
+            self[idx] = old + (np.float32(v) if type(v) is float else v)
+        return old
+
+    def fill(self, v):
+        self.a[...] = v
+
+    def to_numpy(self):
+        return self.a.copy()
+
+    def from_numpy(self, arr):
+        self.a[...] = np.asarray(arr).astype(self.a.dtype)
+
+    def copy_from(self, other):
+        self.a[...] = other.a
+
+    def __iter__(self):
+        return iter(np.ndindex(*self.a.shape))
+
+
+class VectorField:
+    def __init__(self, n, dtype, shape=()):
+        self.n = n
+        self.dtype = dtype
+        self.a = np.zeros(_shape(shape) + (n,), dtype)
+
+    shape = property(lambda s: s.a.shape[:-1])
+
+    def __getitem__(self, idx):
+        return Vec(list(self.a[_idx(idx)]))          # value copy
+
+    def __setitem__(self, idx, v):
+        with np.errstate(all="ignore"):
+            self.a[_idx(idx)] = v.v if isinstance(v, Vec) else v
+
+    def _set_component(self, idx, k, v):
+        with np.errstate(all="ignore"):
+            self.a[_idx(idx) + (int(k),)] = v
+
+    def _atomic_add(self, idx, v):
+        old = self[idx]
+        self[idx] = old + v
+        return old
+
+    def fill(self, v):
+        self.a[...] = v.v if isinstance(v, Vec) else v
+
+    def to_numpy(self):
+        return self.a.copy()
+
+    def from_numpy(self, arr):
+        self.a[...] = np.asarray(arr).astype(self.a.dtype)
+
+    def copy_from(self, other):
+        self.a[...] = other.a
+
+    def __iter__(self):
+        return iter(np.ndindex(*self.a.shape[:-1]))
+
+
+def field(dtype, shape=(), **kw):
+    return Field(dtype, shape)
+
+
+# ---- kernel / func: AST rewrite -----------------------------------------------------------------------------------
+_COMP = {"x": 0, "y": 1, "z": 2, "w": 3}
+
+
+class _Rewrite(ast.NodeTransformer):
+    """ti.atomic_add(F[idx], v) -> F._atomic_add(idx, v); F[idx][k] = v and F[idx].x = v -> F._set_component(idx, k, v);
+    every stored / returned value goes through __ti_val (Python float -> f32, vectors copied)."""
+
+    def __init__(self, global_floats=None):
+        pass
+
+    @staticmethod
+    def _val(node):
+        return ast.Call(ast.Name("__ti_val", ast.Load()), [node], [])
+
+    def visit_BinOp(self, node):
+        self.generic_visit(node)
+        if isinstance(node.op, ast.Pow):
+            return ast.copy_location(ast.Call(ast.Name("__ti_pow", ast.Load()), [node.left, node.right], []), node)
+        return node
+
+    def visit_Return(self, node):
+        self.generic_visit(node)
+        if node.value is not None:
+            node.value = self._val(node.value)
+        return node
+
+    def visit_Call(self, node):
+        self.generic_visit(node)
+        f = node.func
+        if (isinstance(f, ast.Attribute) and f.attr == "atomic_add" and len(node.args) == 2 and isinstance(node.args[0], ast.Subscript)):
+            tgt = node.args[0]
+            base = _unwrap(tgt.value)
+            return ast.copy_location(ast.Call(ast.Attribute(base, "_atomic_add", ast.Load()), [tgt.slice, node.args[1]], []), node)
+        return node
+
+    def _component_store(self, target, value, node):
+        # F[idx][k] = v      /      F[idx].x = v
+        if isinstance(target, ast.Subscript) and isinstance(_unwrap(target.value), ast.Subscript):
+            inner = _unwrap(target.value)
+            return ast.Expr(ast.Call(ast.Attribute(_unwrap(inner.value), "_set_component", ast.Load()), [inner.slice, target.slice, value], []))
+        if isinstance(target, ast.Attribute) and target.attr in _COMP and isinstance(_unwrap(target.value), ast.Subscript):
+            inner = _unwrap(target.value)
+            return ast.Expr(ast.Call(ast.Attribute(_unwrap(inner.value), "_set_component", ast.Load()),
+                                     [inner.slice, ast.Constant(_COMP[target.attr]), value], []))
+        return None
+
+    def visit_Assign(self, node):
+        node.value = self._val(self.visit(node.value))
+        if len(node.targets) == 1:
+            t = node.targets[0]
+            t2 = self._visit_target(t)
+            r = self._component_store(t2, node.value, node)
+            if r is not None:
+                return ast.copy_location(r, node)
+            node.targets = [t2]
+            return node
+        node.targets = [self._visit_target(t) for t in node.targets]
+        return node
+
+    def visit_AugAssign(self, node):
+        node.value = self._val(self.visit(node.value))
+        t2 = self._visit_target(node.target)
+        load = _as_load(t2)
+        r = self._component_store(t2, ast.BinOp(load, node.op, node.value), node)
+        if r is not None:
+            return ast.copy_location(r, node)
+        node.target = t2
+        return node
+
+    def _visit_target(self, t):
+        # visit index expressions inside a store target, but never wrap the target itself
+        if isinstance(t, ast.Subscript):
+            t.value = self._visit_target(t.value) if isinstance(t.value, (ast.Subscript, ast.Attribute)) else self.visit(t.value)
+            t.slice = self.visit(t.slice)
+        elif isinstance(t, ast.Attribute):
+            t.value = self._visit_target(t.value) if isinstance(t.value, (ast.Subscript, ast.Attribute)) else self.visit(t.value)
+        elif isinstance(t, (ast.Tuple, ast.List)):
+            t.elts = [self._visit_target(e) for e in t.elts]
+        return t
+
+
+def _unwrap(n):
+    while isinstance(n, ast.Call) and isinstance(n.func, ast.Name) and n.func.id == "__ti_const" and len(n.args) == 1:
+        n = n.args[0]
+    return n
+
+
+class _ToLoad(ast.NodeTransformer):
+    def visit_Subscript(self, n):
+        self.generic_visit(n); n.ctx = ast.Load(); return n
+
+    def visit_Attribute(self, n):
+        self.generic_visit(n); n.ctx = ast.Load(); return n
+
+    def visit_Name(self, n):
+        n.ctx = ast.Load(); return n
+
+
+def _as_load(t):
+    import copy
+    return _ToLoad().visit(copy.deepcopy(t))
+
+
+_ANN_CAST = {"f32": np.float32, "f64": np.float64, "i32": int, "i64": int, "u8": int}
+np.seterr(all="ignore")          # f32 overflow / invalid are values, not events, in a kernel
+
+
+def _powop(a, b):
+    """`a ** b` inside a kernel.  Constants fold in Python.  An integer exponent is expanded into multiplications by
+    squaring (Taichi's alg_simp pass / LLVM powi: r = 1; while b: if b & 1: r *= a; a *= a; b >>= 1), so x**2 = x*x and
+    x**3 = x*(x*x) with f32 roundings; anything else is powf."""
+    if _pyconst(a, b):
+        return a ** b
+    if isinstance(a, Vec):
+        return Vec([_powop(c, b) for c in a.v])
+    if isinstance(b, (int, np.integer)) and not isinstance(b, bool):
+        n = int(b)
+        neg = n < 0
+        n = -n if neg else n
+        base = _f(a) if _is_float(a) else a
+        r = None
+        while n:
+            if n & 1:
+                r = base if r is None else r * base
+            n >>= 1
+            if n:
+                base = base * base
+        if r is None:
+            r = np.float32(1.0)
+        return np.float32(1.0) / r if neg else r
+    return np.power(_f(a), _f(b))
+
+
+def _val(x):
+    """A value entering kernel storage (local variable, argument, return value): Python floats become f32, vectors are
+    copied (Taichi vectors are values: `a = b` and argument passing copy)."""
+    if type(x) is float:
+        return np.float32(x)
+    return Vec(list(x.v)) if isinstance(x, Vec) else x
+
+
+def _rewrite(fn):
+    """Re-compile `fn` with the kernel-scope semantics described in the module docstring.  The new function shares the
+    defining module's globals (late-bound names stay visible)."""
+    try:
+        src = textwrap.dedent(inspect.getsource(fn))
+    except (OSError, TypeError):
+        return fn, {}
+    tree = ast.parse(src)
+    fdef = tree.body[0]
+    fdef.decorator_list = []
+    casts = {}
+    for a in fdef.args.args:
+        ann = a.annotation
+        if isinstance(ann, ast.Attribute) and ann.attr in _ANN_CAST:
+            casts[a.arg] = _ANN_CAST[ann.attr]
+        a.annotation = None
+    fdef.returns = None
+    gl = fn.__globals__
+    global_floats = {k for k, v in gl.items() if type(v) is float}
+    body = [_Rewrite(global_floats).visit(s) for s in fdef.body]
+    # arguments are passed by value
+    pre = [ast.Assign([ast.Name(a.arg, ast.Store())], ast.Call(ast.Name("__ti_val", ast.Load()), [ast.Name(a.arg, ast.Load())], []))
+           for a in fdef.args.args if a.arg != "self"]
+    doc = []
+    if body and isinstance(body[0], ast.Expr) and isinstance(getattr(body[0], "value", None), ast.Constant) and isinstance(body[0].value.value, str):
+        doc, body = [body[0]], body[1:]
+    fdef.body = doc + pre + body
+    ast.fix_missing_locations(tree)
+    gl.setdefault("__ti_val", _val)
+    gl.setdefault("__ti_pow", _powop)
+    if fn.__closure__:
+        for name, cell in zip(fn.__code__.co_freevars, fn.__closure__):
+            try:
+                gl.setdefault(name, cell.cell_contents)
+            except ValueError:
+                pass
+    ns = {}
+    code = compile(tree, filename=f"<taichi_shim:{fn.__module__}.{fn.__qualname__}>", mode="exec")
+    exec(code, gl, ns)
+    new = ns[fdef.name]
+    new.__ti_emulated__ = True
+    return new, casts
+
+
+def kernel(fn):
+    new, casts = _rewrite(fn)
+    if not casts:
+        return new
+    names = list(inspect.signature(fn).parameters)
+
+    @functools.wraps(fn)
+    def call(*args, **kwargs):
+        args = list(args)
+        for i, nme in enumerate(names[:len(args)]):
+            if nme in casts and not isinstance(args[i], (Field, VectorField, Vec)):
+                args[i] = casts[nme](args[i])
+        for k in list(kwargs):
+            if k in casts:
+                kwargs[k] = casts[k](kwargs[k])
+        return new(*args, **kwargs)
+    call.__ti_emulated__ = True
+    return call
+
+
+def func(fn):
+    return _rewrite(fn)[0]
+
+
+def pyfunc(fn):
+    return fn
+
+
+def data_oriented(cls):
+    return cls
