@@ -9,10 +9,11 @@
  * "C restatement of the Taichi ti.cpu kernels" baseline of bench.py
  * (cpu_baseline.kind = "port"; Taichi is not installable here).
  *
- * PARITY STATUS: "parity unpinned" for the step trajectory -- see the header of
- * oracle/d3q19_ref.py.  This file is validated against that NumPy restatement
- * bit-for-bit (tests/test_oracle_c_vs_numpy.py) and through it against the
- * reference's known-answer identities.
+ * PARITY STATUS: pinned against the reference's own source code -- recorded runs of
+ * the unmodified reference modules under a pure-Python Taichi stand-in
+ * (tests/golden/reference_run_step_*.npz, see the header of oracle/d3q19_ref.py); this
+ * file reproduces their rho, u and f bit for bit (tests/test_oracle_vs_reference_run.py)
+ * and agrees bit for bit with the NumPy restatement (tests/test_oracle_c_vs_numpy.py).
  *
  * Layout: the reference's Taichi dense layout, f[q][i][j][k] with k (z) fastest,
  * u[i][j][k][3] AoS.  All arithmetic f32, left-to-right as written in the

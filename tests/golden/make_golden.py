@@ -4,9 +4,9 @@
 1. reference_config.json  -- constants read by IMPORTING the reference's own `config` package (it imports without
    Taichi) and by parsing the literal lattice table of src/core/lbm_algorithms.py:158-164 (that module needs Taichi,
    so its table is read from the source text).  These pin the oracle's and the product's constants to the reference.
-2. step_reference_24.npz / step_physical_24.npz -- seeded inputs -> outputs of the CPU oracle after 10 steps.  The
-   reference cannot be executed here (no Taichi wheel), so these pin the ORACLE (regression) and give the GPU tests a
-   fixture that does not need the oracle at run time.
+2. step_reference_24.npz / step_physical_24.npz -- seeded inputs -> outputs of the CPU oracle after 10 steps: regression
+   fixtures of the ORACLE (the recordings of the reference's own code live in reference_run_*.npz, written by
+   make_reference_goldens.py) that also give the GPU tests a fixture which does not need the oracle at run time.
 Nothing under tests/ reads /root/reference at test time.
 """
 import io
