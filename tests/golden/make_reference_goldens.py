@@ -74,6 +74,52 @@ def run_step_scenario(config, n, steps, seed, gravity, phase_mode):
     return inp, geom, out, st
 
 
+def run_open_box_scenario(config, n, steps, seed, gravity):
+    """The first 30 steps of main.py: LBMSolver in its init_fields geometry (no V60 mask, no filter system) -- every face
+    is an open face: populations that would enter from outside keep their stale w_q (quirk Q6), the boundary manager's
+    top / bottom / outlet strategies write rho on the fluid faces (quirk Q5).  A solid obstacle is added so bounce-back
+    next to open faces is covered as well."""
+    sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, ROOT)
+    import helpers as H
+    from oracle import d3q19_ref as R
+    config.GRAVITY_LU = gravity
+    with quiet():
+        from src.core.legacy.lbm_solver import LBMSolver
+        s = LBMSolver()
+        s.init_fields()
+    rng = np.random.default_rng(seed)
+    solid = np.zeros((n, n, n), np.uint8)
+    solid[5:9, 4:8, 0:3] = 1; solid[n - 1, 3:7, 6:10] = 1; solid[6:10, 6:10, 7:11] = 1
+    phase = rng.uniform(0.0, 1.0, (n, n, n)).astype(np.float32)
+    bf = (1e-5 * rng.standard_normal((n, n, n, 3))).astype(np.float32)
+    u0 = H.smooth_velocity(n, 0.02, seed); rho0 = H.smooth_density(n, 0.01, seed)
+    f0 = np.stack([R.equilibrium_ref(rho0, u0[..., 0], u0[..., 1], u0[..., 2], q, "config") for q in range(19)]).astype(np.float32)
+    # a state reachable from init_fields (f = f_new = w_q): populations that would have entered through a face were never
+    # written by any step, so those slots still hold w_q in both buffers
+    for q in range(19):
+        for ax, e in enumerate((int(R.CX[q]), int(R.CY[q]), int(R.CZ[q]))):
+            if e != 0:
+                sl = [slice(None)] * 3; sl[ax] = 0 if e > 0 else -1
+                f0[q][tuple(sl)] = R.W[q]
+    s.solid.from_numpy(solid); s.phase.from_numpy(phase); s.body_force.from_numpy(bf); s.f.from_numpy(f0); s.f_new.from_numpy(f0)
+    with quiet():
+        for _ in range(steps):
+            s.step()
+    inp = dict(f=f0, phase=phase, body_force=bf, solid=solid, les_mask=s.les_mask.to_numpy().astype(np.int32))
+    out = dict(rho=s.rho.to_numpy(), u=s.u.to_numpy(), f_out=s.f.to_numpy())
+    return inp, out
+
+
+def oracle_open_box(inp, n, steps, gravity):
+    from oracle import d3q19_ref as R
+    st = R.init_fields(R.RefConfig(NX=n, NY=n, NZ=n, GRAVITY_LU=gravity))
+    st.solid = inp["solid"].copy(); st.phase = inp["phase"].copy(); st.body_force = inp["body_force"].copy()
+    st.f = inp["f"].copy(); st.f_new = inp["f"].copy(); st.les_mask = inp["les_mask"].copy()
+    for _ in range(steps):
+        R.step(st)
+    return st
+
+
 def run_neighbour_scenario(config, n, seed):
     """Body-force producers and the particle kernels of the reference on one seeded state:
     PressureGradientDrive (force and mixed mode), FilterPaperSystem.compute_forchheimer_resistance,
@@ -196,6 +242,16 @@ if __name__ == "__main__":
         all_ok &= bool(ok)
         np.savez_compressed(os.path.join(HERE, f"reference_run_step_{name}.npz"), n=n, steps=steps, gravity=gravity, seed=seed,
                             phase_mode=phase_mode, **inp, **geom, **out)
+    steps, gravity = 5, 3e-5
+    t = time.time()
+    inp, out = run_open_box_scenario(config, n, steps, seed=35, gravity=gravity)
+    st = oracle_open_box(inp, n, steps, gravity)
+    fluid = inp["solid"] == 0
+    ok = np.array_equal(out["rho"][fluid], st.rho[fluid]) and np.array_equal(out["u"][fluid], st.u[fluid]) and \
+        np.array_equal(out["f_out"][:, fluid], st.f[:, fluid])
+    print(f"[reference run] open_box_no_filter: n={n} steps={steps}  reference {time.time() - t:.1f} s  oracle bit-exact: {ok}")
+    all_ok &= bool(ok)
+    np.savez_compressed(os.path.join(HERE, "reference_run_openbox.npz"), n=n, steps=steps, gravity=gravity, **inp, **out)
     res = run_neighbour_scenario(config, n, seed=41)
     ok = check_neighbours_against_oracle(res)
     print("[reference run] neighbours / particles vs oracle:", ok)
