@@ -22,6 +22,11 @@
  * The populations stored are POST-COLLISION values; streaming happens on read
  * (pull scheme).  lbm_export_f / lbm_import_f convert to/from the reference's
  * pre-collision `f[q,i,j,k]` view exactly (pure data movement).
+ *
+ * Environment (read by lbm_create; diagnosis / tuning only, results are bit-identical):
+ *   LBM_TMA=1            compat = physical behind walls: use the TMA-staged persistent kernel (csrc/lbm_phys_tma.cuh)
+ *                        when the box does not wrap in x or y and nx % 16 == 0
+ *   LBM_TMA_VARIANT=0..9 its tile height / ring depth / producer-warp count (csrc/lbm_step_tma.cu)
  */
 #ifndef LBM_B200_H
 #define LBM_B200_H
@@ -70,8 +75,10 @@ typedef struct {
     float porous_forch;       /* physical: F_eps/sqrt(K) [1/lu] */
     float K_lu, beta_lu;      /* reference: filter_paper.py:423-469 */
     float c_darcy, c_forch;   /* reference: constant folds of filter_paper.py:578-586 */
-    int vec;                  /* tuning: cells per thread along x (1, 2 or 4; 0 = auto) */
-    int block;                /* tuning: threads per CTA (0 = auto) */
+    int vec;                  /* tuning: cells per thread along x (1, 2 or 4; 0 = auto: 4 in periodic boxes, 2 behind walls in
+                                 compat = physical, 1 behind walls in compat = reference) */
+    int block;                /* tuning: threads per CTA (0 = auto; 64 / 128 / 256; behind walls in compat = physical the
+                                 codes 65 / 66 select 64-thread CTAs at 16 / 24 resident warps per SM, default 20) */
 } lbm_params;
 
 typedef struct {

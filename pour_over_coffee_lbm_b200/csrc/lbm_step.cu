@@ -76,8 +76,8 @@ static StepKernel pick_feat(int forced, int les, int porous) {
 template <int VEC, int BLOCK>
 static StepKernel tuned() {
     if constexpr (G_WALLS && G_COMPAT == LBM_COMPAT_PHYSICAL) {
-        // tuning set: BLOCK = 128 / 256 run with 384 / 256 resident threads per SM (168 / 255 registers, no spills)
-        // BLOCK = 256 (tuning code): 128-thread CTAs, 3 per SM, loads NOT predicated by the lane mask
+        // VEC = 4: BLOCK = 128 runs 3 CTAs per SM (168 registers, no spills); BLOCK = 256 is a tuning CODE for the same
+        // 128-thread CTAs with plain (not lane-mask predicated) loads
         if constexpr (VEC == 4 && BLOCK == 256) return phys_walls4_kernel<true, true, true, 128, true, 3, false>;
         else if constexpr (VEC == 4) return phys_walls4_kernel<true, true, true, BLOCK, true, (BLOCK == 128 ? 3 : min_blocks<VEC, BLOCK>())>;
         else return phys_walls_kernel<true, true, true, VEC, BLOCK, true, min_blocks_phys_walls<VEC, BLOCK>()>;
