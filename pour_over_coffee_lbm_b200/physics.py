@@ -15,7 +15,7 @@ from typing import Any, Dict, Optional
 import numpy as np
 import torch
 
-from .engine import ParticleState, particles_couple, _ptr
+from .engine import ParticleState, particles_advance, particles_couple, _ptr
 from .fields import ScalarField, VectorField
 
 
@@ -131,6 +131,49 @@ class FilterPaperSystem:
         z = self.lbm.engine.filter_zone
         return {"total_filter_nodes": int((z == 1).sum()), "filter_fraction": float((z == 1).float().mean())}
 
+    def get_filter_inner_radius_at_height(self, z: float) -> float:
+        """filter_paper.py:840-854: inner radius of the cone at height z (lattice units), f32 like the kernel."""
+        cfg = self.lbm.config
+        f = np.float32
+        cup = f(cfg.CUP_HEIGHT / cfg.SCALE_LENGTH)
+        top, bot = f(cfg.TOP_RADIUS / cfg.SCALE_LENGTH), f(cfg.BOTTOM_RADIUS / cfg.SCALE_LENGTH)
+        h = (f(z) - f(self.filter_bottom_z if self.filter_bottom_z is not None else 5.0)) / cup
+        h = max(f(0.0), min(f(1.0), h))
+        return float(bot + (top - bot) * h)
+
+    def get_coffee_bed_boundary(self) -> Dict[str, Any]:
+        """filter_paper.py:856-900: the cone the coffee bed lives in (main.py:672-679 feeds it to the particle integrator)."""
+        cfg = self.lbm.config
+        bottom = self.filter_bottom_z if self.filter_bottom_z is not None else 5.0
+        return {"center_x": cfg.NX * 0.5, "center_y": cfg.NY * 0.5, "bottom_z": bottom,
+                "top_z": bottom + cfg.CUP_HEIGHT / cfg.SCALE_LENGTH,
+                "top_radius_lu": cfg.TOP_RADIUS / cfg.SCALE_LENGTH, "bottom_radius_lu": cfg.BOTTOM_RADIUS / cfg.SCALE_LENGTH,
+                "get_radius_at_height": self.get_filter_inner_radius_at_height}
+
+    def update_dynamic_resistance(self) -> None:
+        """filter_paper.py:703-746: blockage <- 0.95 blockage + 0.05 * 0.9 (1 - exp(-0.1 accumulated)); accumulated *= 0.999,
+        in the filter zone.  (Element-wise torch ops on the device fields; the blockage field feeds the step kernel.)"""
+        if self._blockage is None:
+            return
+        if getattr(self, "_accumulated", None) is None:
+            self._accumulated = torch.zeros_like(self._blockage)
+            self.accumulated_particles = ScalarField(lambda: self._accumulated, self.lbm.engine.zghost)
+        zone = self.lbm.engine.filter_zone == 1
+        new = 0.9 * (1.0 - torch.exp(-0.1 * self._accumulated))
+        self._blockage.copy_(torch.where(zone, 0.95 * self._blockage + 0.05 * new, self._blockage))
+        self._accumulated.copy_(torch.where(zone, self._accumulated * 0.999, self._accumulated))
+
+    def step(self, particle_system: Optional[Any] = None) -> None:
+        """filter_paper.py:748-790: one filter time step.  The drag on the fluid is inside the fused step kernel
+        (apply_filter_effects); what remains is the blockage update."""
+        self.apply_filter_effects()
+        self.update_dynamic_resistance()
+
+    def print_status(self) -> None:
+        st = self.get_filter_statistics()
+        print(f"FilterPaperSystem: {st['total_filter_nodes']:,} filter nodes ({100 * st['filter_fraction']:.2f} % of the box), "
+              f"bottom z = {self.filter_bottom_z}, thickness = {self.filter_thickness_lu} lu")
+
 
 # ----------------------------------------------------------------------------------------------------
 class PressureGradientDrive:
@@ -142,27 +185,84 @@ class PressureGradientDrive:
         self.density_drive_active = False
 
     def activate_force_drive(self, active: bool = True):
-        self.force_drive_active = bool(active)
-        if active: self.mixed_drive_active = False
+        """pressure_gradient_drive.py:81-86: switching one mode on (or off) clears the other two."""
+        self.force_drive_active = bool(active); self.mixed_drive_active = False; self.density_drive_active = False
 
     def activate_mixed_drive(self, active: bool = True):
-        self.mixed_drive_active = bool(active)
-        if active: self.force_drive_active = False
+        self.mixed_drive_active = bool(active); self.force_drive_active = False; self.density_drive_active = False
 
     def activate_density_drive(self, active: bool = True):
         # method A writes rho, which the next macroscopic pass overwrites: inert in LBMSolver (SURVEY a20)
-        self.density_drive_active = bool(active)
+        self.density_drive_active = bool(active); self.force_drive_active = False; self.mixed_drive_active = False
 
     def apply_force_drive(self):
         if self.force_drive_active:
             self.lbm.engine.add_pressure_gradient_force(self.MAX_PRESSURE_FORCE, 1.0)
 
+    def apply_mixed_drive(self):
+        if self.mixed_drive_active:
+            self.lbm.engine.add_pressure_gradient_force(self.MAX_PRESSURE_FORCE, 0.5)
+
+    def compute_pressure_gradient(self):
+        """pressure_gradient_drive.py:124-177: the clamped acceleration field -cs^2 grad(rho)/rho, kept in
+        `pressure_force` ([3, z, y, x] device tensor; zero on solid cells) without touching body_force."""
+        e = self.lbm.engine
+        if getattr(self, "_pressure_force", None) is None:
+            self._pressure_force = torch.zeros_like(e.u)
+            self.pressure_force = VectorField(lambda: self._pressure_force, e.zghost)
+        self._pressure_force.zero_()
+        e._check(e.lib.lbm_pressure_gradient_force_set(e._ctx, _ptr(e.rho), _ptr(e.flags), _ptr(self._pressure_force),
+                                                       float(self.MAX_PRESSURE_FORCE), 1.0, e.stream), "lbm_pressure_gradient_force_set")
+
+    def initialize_target_density(self):
+        """pressure_gradient_drive.py:54-72: z profile 0.4 -> 1 over the bottom 20 %, 1 in the middle, 1 -> 1.8 over the top
+        20 % (global z)."""
+        e = self.lbm.engine
+        f = np.float32
+        k = np.arange(e.z0 - e.zghost, e.z0 + e.nz + e.zghost, dtype=np.float32)
+        zr = k / f(e.nz_global)
+        hi = f(1.0) + ((zr - f(0.8)) / (f(1.0) - f(0.8))) * (f(1.8) - f(1.0))
+        lo = f(0.4) + (zr / f(0.2)) * (f(1.0) - f(0.4))
+        prof = np.where(zr >= f(0.8), hi, np.where(zr <= f(0.2), lo, f(1.0))).astype(np.float32)
+        self._target_density = torch.from_numpy(prof).to(e.device)[:, None, None].expand(-1, e.ny, e.nx)
+
+    def apply_density_drive(self):
+        """pressure_gradient_drive.py:95-122 (method A): nudges rho toward the target profile by at most 0.001 per call,
+        clamped to [0.5, 2].  LBMSolver recomputes rho from f before it is used, so this is cosmetic there."""
+        if not self.density_drive_active:
+            return
+        e = self.lbm.engine
+        if getattr(self, "_target_density", None) is None:
+            self.initialize_target_density()
+        adj = torch.clamp((self._target_density - e.rho) * 0.025, -0.001, 0.001)
+        new = torch.clamp(e.rho + adj, 0.5, 2.0)
+        e.rho.copy_(torch.where(e.solid == 0, new, e.rho) if e.solid is not None else new)
+
     def apply(self, step: int = 0):
         """pressure_gradient_drive.py:257-272"""
+        if self.density_drive_active:
+            self.apply_density_drive()
         if self.force_drive_active:
             self.lbm.engine.add_pressure_gradient_force(self.MAX_PRESSURE_FORCE, 1.0)
         elif self.mixed_drive_active:
             self.lbm.engine.add_pressure_gradient_force(self.MAX_PRESSURE_FORCE, 0.5)
+
+    def get_status(self) -> Dict[str, Any]:
+        return {"density_drive": bool(self.density_drive_active), "force_drive": bool(self.force_drive_active),
+                "mixed_drive": bool(self.mixed_drive_active), "max_pressure_force": float(self.MAX_PRESSURE_FORCE)}
+
+    def get_statistics(self) -> Dict[str, Any]:
+        """pressure_gradient_drive.py:281-330: extrema of the fields the drive acts on (from the fused statistics pass)."""
+        s = self.lbm.engine.field_statistics().tolist()
+        return {"max_pressure": s[2], "min_pressure": s[1], "pressure_drop": s[2] - s[1], "max_velocity": s[0],
+                "mean_density": s[3] / max(1.0, s[7] - s[5] - s[6])}
+
+    get_enhanced_diagnostics = get_statistics
+    compute_statistics = get_statistics
+
+    def check_enhanced_stability(self) -> bool:
+        s = self.lbm.engine.field_statistics().tolist()
+        return bool(s[5] == 0 and s[6] == 0 and s[0] < 0.3 and s[1] > 0.1 and s[2] < 5.0)
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -223,6 +323,135 @@ class CoffeeParticleSystem:
         st.mass[:n] = torch.as_tensor(np.asarray(mass, np.float32)).to(dev)
         st.active.zero_(); st.active[:n] = 1
         self.particle_count = n
+
+    # ---- validation helpers (coffee_particles.py:75-117) ----
+    MIN_COORDINATE, MAX_VELOCITY, MAX_RADIUS, MIN_RADIUS = 0.0, 10.0, 0.01, 1e-5
+
+    @property
+    def MAX_COORDINATE(self) -> float:
+        c = self._solver.config
+        return float(max(c.NX, c.NY, c.NZ))
+
+    def validate_coordinate(self, x, y, z) -> bool:
+        m = self.MAX_COORDINATE
+        return bool(all(np.isfinite(v) and 0.0 <= v <= m and abs(v) <= 1e6 for v in (x, y, z)))
+
+    def validate_velocity(self, vx, vy, vz) -> bool:
+        return bool(all(v == v for v in (vx, vy, vz)) and vx * vx + vy * vy + vz * vz <= self.MAX_VELOCITY ** 2)
+
+    def validate_radius(self, radius) -> bool:
+        return bool(radius == radius and self.MIN_RADIUS <= radius <= self.MAX_RADIUS)
+
+    # ---- creation (host side, like the reference: these run once, in Python) ----
+    def clear_all_particles(self) -> None:
+        """coffee_particles.py:119-144"""
+        st = self.state
+        for t in (st.pos, st.vel, st.radius, st.mass, st.drag, st.drag_new, st.drag_old, st.u_fluid, st.reynolds, st.cd):
+            t.zero_()
+        st.active.zero_()
+        if self.reaction_force_tensor is not None:
+            self.reaction_force_tensor.zero_()
+        if getattr(self, "error_counters", None) is not None:
+            self.error_counters.zero_()
+        self.particle_count = 0
+
+    def generate_gaussian_particle_radius(self, mean_radius=None, std_dev_ratio: float = 0.3, rng=None) -> float:
+        """coffee_particles.py:146-182: N(mean, 30 %) clipped to [0.5, 1.5] x mean."""
+        cfg = self._solver.config
+        mean = cfg.COFFEE_PARTICLE_RADIUS if mean_radius is None else mean_radius
+        mean = max(self.MIN_RADIUS, min(self.MAX_RADIUS, mean))
+        rng = rng if rng is not None else np.random
+        r = rng.normal(mean, mean * std_dev_ratio)
+        return float(np.clip(r, max(self.MIN_RADIUS, 0.5 * mean), min(self.MAX_RADIUS, 1.5 * mean)))
+
+    def create_particle_with_physics(self, idx: int, px, py, pz, radius, vx=0.0, vy=0.0, vz=0.0) -> int:
+        """coffee_particles.py:184-218: one particle with mass = (4/3) 3.14159 r^3 rho_coffee (f32); 1 on success."""
+        if not (0 <= idx < self.max_particles and self.validate_coordinate(px, py, pz) and self.validate_velocity(vx, vy, vz)
+                and self.validate_radius(radius)):
+            return 0
+        f = np.float32
+        r = f(radius)
+        mass = ((f(4.0) / f(3.0)) * f(3.14159)) * (r * (r * r)) * f(self.coffee_density)
+        if not (mass == mass and mass > 0):
+            return 0
+        st = self.state
+        st.pos[:, idx] = torch.tensor([px, py, pz], dtype=torch.float32)
+        st.vel[:, idx] = torch.tensor([vx, vy, vz], dtype=torch.float32)
+        st.radius[idx] = float(r); st.mass[idx] = float(mass); st.active[idx] = 1
+        self.particle_count = max(self.particle_count, idx + 1)
+        return 1
+
+    def initialize_coffee_bed_confined(self, filter_paper_system, seed: Optional[int] = None) -> int:
+        """coffee_particles.py:220-412: the coffee bed as layered discs above the filter surface inside the V60 cone
+        (up to 2000 particles, 10-30 layers, radius concentrated toward the axis, Gaussian grain sizes).  The reference
+        draws with the unseeded global NumPy generator one particle at a time; here each layer is drawn in one
+        vectorised batch from `seed` (same distributions and acceptance tests), then uploaded once."""
+        cfg = self._solver.config
+        rng = np.random.default_rng(seed)
+        self.clear_all_particles()
+        b = filter_paper_system.get_coffee_bed_boundary()
+        cx, cy, bz = float(b["center_x"]), float(b["center_y"]), float(b["bottom_z"])
+        top_r, bot_r = float(b["top_radius_lu"]), float(b["bottom_radius_lu"])
+        if not all(np.isfinite([cx, cy, bz, top_r, bot_r])) or not (0 <= cx <= cfg.NX and 0 <= cy <= cfg.NY and 0 <= bz <= cfg.NZ):
+            return 0
+        bed_bottom = bz + 2.0
+        bed_h = max(5.0, min(30.0, max(0.005, min(0.05, getattr(cfg, "COFFEE_BED_HEIGHT_PHYS", 0.015))) / cfg.SCALE_LENGTH))
+        bed_top = bed_bottom + bed_h
+        if bed_top >= cfg.NZ - 5:
+            bed_top = cfg.NZ - 5; bed_h = bed_top - bed_bottom
+        target = min(2000, self.max_particles - 100)
+        if target <= 0 or bed_h <= 0:
+            return 0
+        layers = max(10, min(int(bed_h / 2), 30))
+        if target < layers:
+            layers = max(1, target)
+        per_layer = max(1, target // layers)
+        cup_h = max(10.0, cfg.CUP_HEIGHT / cfg.SCALE_LENGTH)
+        bed_r = getattr(cfg, "COFFEE_BED_TOP_RADIUS", top_r * 0.8) / cfg.SCALE_LENGTH
+        pos = []
+        for layer in range(layers):
+            if len(pos) >= target:
+                break
+            z = bed_bottom + (layer / layers) * bed_h
+            if z > bed_top:
+                break
+            ratio = min(1.0, max(0.0, (z - bz) / cup_h))
+            layer_r = max(1.0, min(top_r * 1.5, bot_r + (top_r - bot_r) * ratio))
+            bed_ratio = max(0.1, min(1.0, (bed_h - (z - bed_bottom)) / bed_h))
+            eff_r = max(2.0, min(min(layer_r * 0.85, bed_r * (0.3 + 0.7 * bed_ratio)), 50.0))
+            n_try = per_layer * 5
+            ang = rng.uniform(0, 2 * np.pi, n_try)
+            r = np.clip(rng.uniform(0, 1, n_try) ** 1.5 * eff_r * 0.9, 0.0, eff_r * 0.9)
+            x = cx + r * np.cos(ang); y = cy + r * np.sin(ang); zf = z + rng.uniform(-0.5, 0.5, n_try)
+            ok = (x >= 5.0) & (x <= cfg.NX - 5.0) & (y >= 5.0) & (y <= cfg.NY - 5.0) & (zf >= bed_bottom) & (zf <= bed_top)
+            # _safe_cone_boundary_check (coffee_particles.py:414-440): inside 0.9 x the cone radius at that height
+            hr = np.clip((zf - bz) / cup_h, 0.0, 1.0)
+            ok &= np.hypot(x - cx, y - cy) <= (bot_r + (top_r - bot_r) * hr) * 0.9
+            take = np.flatnonzero(ok)[:min(per_layer, target - len(pos))]
+            pos.extend(np.stack([x[take], y[take], zf[take]], 1))
+        n = len(pos)
+        if n == 0:
+            return 0
+        mean = max(self.MIN_RADIUS, min(self.MAX_RADIUS, cfg.COFFEE_PARTICLE_RADIUS))
+        radius = np.clip(rng.normal(mean, 0.3 * mean, n), max(self.MIN_RADIUS, 0.5 * mean), min(self.MAX_RADIUS, 1.5 * mean))
+        self.set_particles(np.asarray(pos, np.float32), radius=radius.astype(np.float32))
+        return n
+
+    def get_particle_statistics(self) -> Dict[str, Any]:
+        """coffee_particles.py:833-900: radius / position statistics of the valid active particles."""
+        st = self.state
+        cfg = self._solver.config
+        n = self.particle_count
+        act = (st.active[:n] == 1).cpu().numpy()
+        r = st.radius[:n].cpu().numpy(); p = st.pos[:, :n].cpu().numpy().T
+        ok = act & np.isfinite(r) & np.isfinite(p).all(1) & (r >= self.MIN_RADIUS) & (r <= self.MAX_RADIUS) & \
+            (p[:, 0] >= 0) & (p[:, 0] <= cfg.NX) & (p[:, 1] >= 0) & (p[:, 1] <= cfg.NY) & (p[:, 2] >= 0) & (p[:, 2] <= cfg.NZ)
+        rr = r[ok]
+        out = {"count": int(ok.sum()), "invalid_particles": int((act & ~ok).sum()), "mean_radius": float(rr.mean()) if rr.size else 0.0,
+               "std_radius": float(rr.std()) if rr.size else 0.0, "min_radius": float(rr.min()) if rr.size else 0.0,
+               "max_radius": float(rr.max()) if rr.size else 0.0, "radii": rr, "positions": p[ok],
+               "coordinate_errors": self.coordinate_errors, "boundary_violations": self.boundary_violations}
+        return out
 
     def compute_two_way_coupling_forces(self, fluid_u=None, relax: float = -1.0):
         """coffee_particles.py:1107-1154; relax >= 0 also applies the under-relaxation in the same kernel."""

@@ -205,6 +205,34 @@ class LBMSolver:
     def get_velocity_vector_field(self):
         return self.u
 
+    # velocity-layout helpers of the legacy class (legacy/lbm_solver.py:1114-1232): one device layout here, both views live
+    def get_velocity_vector(self):
+        return self.u
+
+    def get_velocity_components(self):
+        return self.ux, self.uy, self.uz
+
+    def set_velocity_vector(self, u_field) -> None:
+        self.u.from_numpy(u_field.to_numpy() if hasattr(u_field, "to_numpy") else np.asarray(u_field, np.float32))
+
+    def has_soa_velocity_layout(self) -> bool:
+        return True
+
+    def sync_soa_to_vector_velocity(self) -> None:      # ux/uy/uz and u are views of the same tensor
+        pass
+
+    sync_vector_to_soa_velocity = sync_soa_to_vector_velocity
+
+    def get_solver_type(self) -> str:
+        return "b200"
+
+    # main.py:735-790 probes these names before falling back to step()
+    def step_ultra_optimized(self) -> None:
+        self.step()
+
+    def step_with_cfl_control(self) -> None:
+        self.step()
+
     get_velocity_field_for_thermal_coupling = get_velocity_vector_field
 
     def field_statistics(self) -> torch.Tensor:

@@ -304,6 +304,46 @@ def test_solver_facade_surface_and_protocol():
     assert m["throughput_mlups"] > 0 and us.backend.validate_platform()
 
 
+def test_main_py_orchestration_surface_on_the_device():
+    """The calls main.py makes around the step (main.py:560-700, 735-935): filter geometry -> coffee bed creation ->
+    pre-stabilisation loop (step + particle integrator with the filter's bounds) -> drive + coupled step, statistics."""
+    from pour_over_coffee_lbm_b200.solver import LBMSolver
+    from pour_over_coffee_lbm_b200.physics import CoffeeParticleSystem, FilterPaperSystem, PressureGradientDrive
+    n = 64
+    s = LBMSolver(nx=n, ny=n, nz=n); s.init_fields()
+    fp = FilterPaperSystem(s); fp.initialize_filter_geometry()
+    b = fp.get_coffee_bed_boundary()
+    assert b["center_x"] == n * 0.5 and b["bottom_z"] == 5.0 and b["top_radius_lu"] > b["bottom_radius_lu"] > 0
+    assert abs(b["get_radius_at_height"](b["top_z"]) - b["top_radius_lu"]) < 1e-4
+    ps = CoffeeParticleSystem(3000, solver=s)
+    created = ps.initialize_coffee_bed_confined(fp, seed=3)
+    assert 500 < created <= 2000
+    st = ps.get_particle_statistics()
+    assert st["count"] == created and 0.5 * 3.25e-4 <= st["min_radius"] <= st["max_radius"] <= 1.5 * 3.25e-4
+    pos0 = st["positions"]
+    # every grain starts inside the cone, above the filter surface
+    r = np.hypot(pos0[:, 0] - b["center_x"], pos0[:, 1] - b["center_y"])
+    assert (pos0[:, 2] >= b["bottom_z"] + 2.0).all() and (r <= [b["get_radius_at_height"](z) for z in pos0[:, 2]]).all()
+    cfg = s.config
+    for _ in range(5):                                                     # main.py:667-679
+        s.step()
+        ps.update_particle_physics(cfg.DT * cfg.SCALE_TIME * 0.1, b["center_x"], b["center_y"], b["bottom_z"], b["bottom_radius_lu"],
+                                   b["top_radius_lu"])
+    assert int((ps.active == 1).sum()) == created and ps.coordinate_errors == 0
+    drive = PressureGradientDrive(s); drive.activate_force_drive(True)
+    assert drive.get_status()["force_drive"] and not drive.get_status()["density_drive"]
+    for _ in range(3):
+        s.clear_body_force(); drive.apply(); s.step_with_two_way_coupling(ps, 1.0, 0.8); fp.step(ps)
+    drive.compute_pressure_gradient()
+    assert float(drive._pressure_force.abs().max()) <= 0.12 * 1.0001
+    stats = drive.get_statistics()
+    assert np.isfinite(list(stats.values())).all() and s.check_stability() and drive.check_enhanced_stability()
+    ux, uy, uz = s.get_velocity_components()
+    assert ux.shape == (n, n, n) and s.has_soa_velocity_layout() and s.get_solver_type() == "b200"
+    drive.activate_density_drive(True); drive.apply()                       # method A: nudges rho (cosmetic, SURVEY a20)
+    assert not drive.force_drive_active and np.isfinite(s.rho.to_numpy()).all()
+
+
 def test_body_force_accumulation_fluid_only():
     """tests/test_lbm_body_force.py:77-100,218-239 of the reference: body_force += semantics, fluid cells only."""
     from pour_over_coffee_lbm_b200.solver import LBMSolver
