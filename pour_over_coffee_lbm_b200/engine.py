@@ -225,6 +225,40 @@ class D3Q19Engine:
         f = self._fields()
         self._check(self.lib.lbm_face_bc(self._ctx, C.byref(f), self.stream), "lbm_face_bc")
 
+    # ---- restart checkpoint (absent in the reference) ------------------------------------
+    _CKPT_FIELDS = ("rho", "body_force", "phase", "solid", "filter_zone", "les_mask", "blockage")
+
+    def save_checkpoint(self, path: str) -> None:
+        """Everything a bit-exact restart needs: the current population buffer, the macroscopic fields the kernels read
+        back (rho; both u buffers of the reference-mode LES), the inputs (force, phase, geometry) and the step count.
+        One file per slab (torch.save); geometry and parameters are checked on load."""
+        torch.cuda.synchronize(self.device)
+        blob = {"version": 1, "shape": (self.nx, self.ny, self.nz, self.zghost, self.z0, self.nz_global), "compat": self.compat,
+                "features": self.features, "steps_done": self.steps_done, "g": self.g[self.cur].cpu(),
+                "u": [u.cpu() for u in self.u_buf], "u_cur": self.u_cur}
+        for name in self._CKPT_FIELDS:
+            t = getattr(self, name, None)
+            blob[name] = t.cpu() if t is not None else None
+        torch.save(blob, path)
+
+    def load_checkpoint(self, path: str) -> None:
+        blob = torch.load(path, map_location="cpu", weights_only=False)
+        if tuple(blob["shape"]) != (self.nx, self.ny, self.nz, self.zghost, self.z0, self.nz_global) or blob["compat"] != self.compat \
+                or blob["features"] != self.features:
+            raise ValueError("checkpoint was written for a different slab geometry, compat mode or feature set")
+        for name in self._CKPT_FIELDS:
+            t = getattr(self, name, None)
+            if blob[name] is not None and t is not None:
+                t.copy_(blob[name])
+        if self.flags is not None:
+            self.pack_flags()                      # flags, work lists, neighbour masks from solid / filter_zone / les_mask
+        self.g[self.cur].copy_(blob["g"]); self.g[1 - self.cur].copy_(blob["g"])
+        for dst, src in zip(self.u_buf, blob["u"]):
+            dst.copy_(src)
+        self.u_cur = blob["u_cur"] if len(self.u_buf) == 2 else 0
+        self.steps_done = int(blob["steps_done"])
+        self.populations_changed()
+
     # ---- reference `f` view ------------------------------------------------------------------
     def export_f(self) -> torch.Tensor:
         """The reference's pre-collision f in device layout [19, nzp, ny, nx] (exact data movement)."""
