@@ -175,6 +175,49 @@ int  lbm_forchheimer_force(lbm_ctx *ctx, const float *u, const uint8_t *flags, f
 /* LBMSolver.add_particle_reaction_forces legacy/lbm_solver.py:1478-1483: body_force += reaction on fluid. */
 int  lbm_add_reaction_force(lbm_ctx *ctx, const float *reaction, const uint8_t *flags, float *body_force, void *stream);
 
+/* ---- producers next to the step: surface tension, phase field, pouring nozzle ---------------- */
+/* MultiphaseFlow3D.accumulate_surface_tension_pre_collision src/core/multiphase_3d.py:409-418 in two launches:
+ * compute_gradients :111-132 (grad_phi, normal; grad_mu when mu and grad_mu are given), then compute_curvature :134-149 +
+ * compute_surface_tension_force :313-332 (the live definition) + apply_surface_tension :354-363
+ * (body_force += surface_force / rho on fluid cells with rho > 1e-10; body_force = NULL computes the fields only, as the
+ * first three kernels of MultiphaseFlow3D.step :396-398 do).  Scalars are [zp][y][x], vectors [3][zp][y][x]; the outer
+ * cell layer of every output keeps what it held (the reference never writes it).  Single slab (zghost = 0). */
+int  lbm_surface_tension(lbm_ctx *ctx, const float *phi, const float *mu_or_null, const float *rho, const uint8_t *flags,
+                         float *grad_phi, float *grad_mu_or_null, float *normal, float *curvature, float *surface_force,
+                         float *body_force_or_null, float sigma, void *stream);
+/* MultiphaseFlow3D.compute_chemical_potential multiphase_3d.py:80-109: laplacian_phi (optional output) and
+ * mu = phi^3 - phi - kappa * lap(phi) on interior cells; kappa = 3 * sigma * W / 8 folded by the caller.  The reference
+ * calls it once, from standardize_initial_state :542-571.  Single slab. */
+int  lbm_chemical_potential(lbm_ctx *ctx, const float *phi, float *laplacian_phi_or_null, float *mu, float kappa, void *stream);
+/* MultiphaseFlow3D.apply_surface_tension multiphase_3d.py:354-363 alone (step() with precollision_applied = False). */
+int  lbm_apply_surface_tension(lbm_ctx *ctx, const float *surface_force, const float *rho, const uint8_t *flags,
+                               float *body_force, void *stream);
+/* The phase-field half of MultiphaseFlow3D.step multiphase_3d.py:404-407 in two launches:
+ * update_phase_field_cahn_hilliard :151-197 + apply_phase_separation :334-352 (phi -> phi_new, interior cells), then
+ * copy_phase_field :383-387 + update_density_from_phase :365-381 (phi = phi_new, rho, phase on every cell).
+ * mu = NULL is the all-zero chemical potential the live step() leaves behind.  rho_water / rho_air are doubles because
+ * the reference folds (RHO_WATER - RHO_AIR) in f64 before it meets an f32 value.  Single slab (zghost = 0). */
+int  lbm_phase_field_step(lbm_ctx *ctx, float *phi, float *phi_new, const float *mu_or_null, const float *u, float *rho,
+                          float *phase, float mobility, float dt, double rho_water, double rho_air, void *stream);
+/* MultiphaseFlow3D.update_density_from_phase multiphase_3d.py:365-381 alone (main.py:624). */
+int  lbm_density_from_phase(lbm_ctx *ctx, const float *phi, float *rho, float *phase, double rho_water, double rho_air,
+                            void *stream);
+/* PrecisePouringSystem (src/physics/precise_pouring.py).  The host advances pour_time and evaluates
+ * _get_current_pour_position :81-97 (centre or spiral); the kernels visit the nozzle's bounding box only. */
+typedef struct {
+    float pour_x, pour_y;         /* current nozzle centre, lattice units */
+    float radius;                 /* POUR_DIAMETER_GRID / 2 */
+    int   pour_z;                 /* POUR_HEIGHT (global plane index); the stream reaches 4 planes below it */
+    float velocity;               /* POUR_VELOCITY, lu/ts */
+    float flow_rate;              /* pour_flow_rate[None] */
+    float dt;
+} lbm_pour;
+/* apply_pouring_force precise_pouring.py:131-163: body_force.z -= min(velocity * intensity * flow_rate / dt, 10) on the
+ * fluid cells under the nozzle (Gaussian radial profile x exponential vertical decay, _is_in_pouring_region :99-129). */
+int  lbm_pouring_force(lbm_ctx *ctx, const lbm_pour *pour, const uint8_t *flags, float *body_force, void *stream);
+/* apply_gradual_phase_change precise_pouring.py:165-196: phi relaxes toward +1 under the nozzle (rate limited). */
+int  lbm_pouring_phase_change(lbm_ctx *ctx, const lbm_pour *pour, const uint8_t *flags, float *phi, void *stream);
+
 /* ---- coffee particles (src/physics/coffee_particles.py) ------------------------------- */
 typedef struct {
     float *pos, *vel;             /* [3][n] SoA, lattice units */

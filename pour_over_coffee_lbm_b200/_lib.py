@@ -43,6 +43,11 @@ class LbmParticles(C.Structure):
                  "u_fluid", "reynolds", "cd", "cell")] + [("n", C.c_int)]
 
 
+class LbmPour(C.Structure):
+    _fields_ = [("pour_x", C.c_float), ("pour_y", C.c_float), ("radius", C.c_float), ("pour_z", C.c_int),
+                ("velocity", C.c_float), ("flow_rate", C.c_float), ("dt", C.c_float)]
+
+
 class LbmParticleBounds(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("center_x", "center_y", "bottom_z", "bottom_radius_lu", "top_radius_lu",
                                          "cup_height_lu", "max_coordinate", "nz_minus_5")]
@@ -72,6 +77,13 @@ SIGNATURES = {
     "lbm_forchheimer_force": (C.c_int, [_P, _P, _P, _P, C.c_float, _P]),
     "lbm_field_statistics": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "lbm_add_reaction_force": (C.c_int, [_P, _P, _P, _P, _P]),
+    "lbm_surface_tension": (C.c_int, [_P] * 11 + [C.c_float, _P]),
+    "lbm_chemical_potential": (C.c_int, [_P, _P, _P, _P, C.c_float, _P]),
+    "lbm_apply_surface_tension": (C.c_int, [_P, _P, _P, _P, _P, _P]),
+    "lbm_phase_field_step": (C.c_int, [_P] * 7 + [C.c_float, C.c_float, C.c_double, C.c_double, _P]),
+    "lbm_density_from_phase": (C.c_int, [_P, _P, _P, _P, C.c_double, C.c_double, _P]),
+    "lbm_pouring_force": (C.c_int, [_P, C.POINTER(LbmPour), _P, _P, _P]),
+    "lbm_pouring_phase_change": (C.c_int, [_P, C.POINTER(LbmPour), _P, _P, _P]),
     "lbm_particles_couple": (C.c_int, [_P, _P, _P, C.POINTER(LbmParticles), C.c_float, C.c_float, C.c_float, _P]),
     "lbm_particles_under_relax": (C.c_int, [_P, C.POINTER(LbmParticles), C.c_float, _P]),
     "lbm_particles_advance": (C.c_int, [_P, C.POINTER(LbmParticles), _P, C.POINTER(LbmParticleBounds), C.c_float, _P, _P]),

@@ -7,6 +7,7 @@ V60 geometry and the particle coupling read is kept.
 """
 from __future__ import annotations
 
+import math
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -52,6 +53,14 @@ class LBMConfig:
     U_CHAR: float = 0.02
     PAPER_THICKNESS: float = 0.0001          # filter_paper.py:106
     PAPER_POROSITY: float = 0.85             # filter_paper.py:107
+    AIR_DENSITY_20C: float = 1.204           # config/physics.py:50
+    RHO_WATER: float = 1.0                   # config/physics.py:114
+    WEBER_NUMBER: float = 1.0                # config/physics.py:180
+    POUR_RATE_ML_S: float = 4.0              # config/physics.py:81
+    POUR_HEIGHT_CM: float = 12.5             # config/physics.py:87
+    INLET_DIAMETER_M: float = 0.005          # config/physics.py:88
+    NOZZLE_DIAMETER_M: float = 0.005         # config/physics.py:89
+    GRAVITY_CORRECTION: float = 0.05         # config/physics.py:92
     SCALE_LENGTH: float = field(default=0.0)
     SCALE_TIME: float = field(default=0.0)
     GRAVITY_LU: float = field(default=-1.0)
@@ -67,6 +76,18 @@ class LBMConfig:
     TAU_WATER = property(lambda self: self.TAU_FLUID)            # config/__init__.py:285
     RE_CHAR = property(lambda self: self.U_CHAR * self.CUP_HEIGHT / self.WATER_VISCOSITY_90C)
     use_les = property(lambda self: self.ENABLE_LES and self.RE_CHAR > self.LES_REYNOLDS_THRESHOLD)
+
+    # multiphase / pouring constants (config/physics.py:95-101, 115, 181, 254-273; config/core.py:84)
+    RHO_AIR = property(lambda self: self.AIR_DENSITY_20C / self.WATER_DENSITY_90C)
+    SURFACE_TENSION_LU = property(lambda self: (self.RHO_WATER * (self.U_CHAR * self.SCALE_TIME / self.SCALE_LENGTH) ** 2 * self.SCALE_LENGTH)
+                                  / self.WEBER_NUMBER)
+    GRID_SIZE_CM = property(lambda self: self.SCALE_LENGTH * 100)
+    INLET_AREA = property(lambda self: math.pi * (min(self.INLET_DIAMETER_M, self.NOZZLE_DIAMETER_M) / 2.0) ** 2)
+
+    @property
+    def INLET_VELOCITY(self) -> float:
+        base = (self.POUR_RATE_ML_S * 1e-6) / (math.pi * (self.INLET_DIAMETER_M / 2.0) ** 2)
+        return min(0.05, base * (1.0 + self.GRAVITY_CORRECTION) * self.SCALE_TIME / self.SCALE_LENGTH)
 
     # --- f32 constants exactly as the reference's kernels see them --------------------------
     def v60_geometry_constants(self):

@@ -32,6 +32,14 @@ cudaError_t launch_bounce_slots(const Grid &, float *, const uint8_t *, const un
 cudaError_t launch_particles_couple(const Grid &, const float *, float *, const lbm_particles &, float, float, float, cudaStream_t);
 cudaError_t launch_particles_under_relax(const lbm_particles &, float, cudaStream_t);
 cudaError_t launch_particles_advance(const lbm_particles &, float *, const lbm_particle_bounds &, float, int *, cudaStream_t);
+cudaError_t launch_surface_tension(const Grid &, const float *, const float *, const float *, const uint8_t *, float *, float *, float *, float *,
+                                   float *, float *, float, cudaStream_t);
+cudaError_t launch_apply_surface_tension(const Grid &, const float *, const float *, const uint8_t *, float *, cudaStream_t);
+cudaError_t launch_chemical_potential(const Grid &, const float *, float *, float *, float, cudaStream_t);
+cudaError_t launch_phase_field_step(const Grid &, float *, float *, const float *, const float *, float *, float *, float, float, float, float,
+                                    cudaStream_t);
+cudaError_t launch_density_from_phase(const Grid &, const float *, float *, float *, float, float, cudaStream_t);
+cudaError_t launch_pour(const Grid &, const lbm_pour &, const float[5], int, const uint8_t *, float *, cudaStream_t, int *);
 // TMA-staged walls kernels of compat = physical (lbm_step_tma.cu)
 struct TmaKernelInfo {
     void (*kernel)(const StepArgs, const TmaMaps);
@@ -669,6 +677,73 @@ int lbm_add_reaction_force(lbm_ctx *ctx, const float *reaction, const uint8_t *f
     CUDA_OK(ctx, launch_add_reaction(ctx->g, reaction, flags, body_force, (cudaStream_t)stream));
     ctx->launches++;
     return 0;
+}
+
+// ---- producers next to the step: surface tension, phase-field step, pouring nozzle (lbm_producers.cu) ----
+static int single_slab_only(lbm_ctx *ctx, const char *what) {
+    if (ctx->g.zg != 0) { ctx->error = std::string(what) + ": 7-point stencils over phi / normal are implemented for a single slab (zghost = 0)"; return 1; }
+    return 0;
+}
+
+int lbm_surface_tension(lbm_ctx *ctx, const float *phi, const float *mu, const float *rho, const uint8_t *flags, float *grad_phi, float *grad_mu,
+                        float *normal, float *curvature, float *surface_force, float *body_force, float sigma, void *stream) {
+    if (!ctx || !phi || !grad_phi || !normal || !curvature || !surface_force) return fail(ctx, "null argument");
+    if (body_force && (!rho || !flags)) return fail(ctx, "lbm_surface_tension: body_force needs rho and flags");
+    if (single_slab_only(ctx, "lbm_surface_tension")) return 1;
+    CUDA_OK(ctx, launch_surface_tension(ctx->g, phi, mu, rho, flags, grad_phi, grad_mu, normal, curvature, surface_force, body_force, sigma,
+                                        (cudaStream_t)stream));
+    ctx->launches += 2;
+    return 0;
+}
+
+int lbm_chemical_potential(lbm_ctx *ctx, const float *phi, float *laplacian_phi, float *mu, float kappa, void *stream) {
+    if (!ctx || !phi || !mu) return fail(ctx, "null argument");
+    if (single_slab_only(ctx, "lbm_chemical_potential")) return 1;
+    CUDA_OK(ctx, launch_chemical_potential(ctx->g, phi, laplacian_phi, mu, kappa, (cudaStream_t)stream));
+    ctx->launches++;
+    return 0;
+}
+
+int lbm_apply_surface_tension(lbm_ctx *ctx, const float *surface_force, const float *rho, const uint8_t *flags, float *body_force, void *stream) {
+    if (!ctx || !surface_force || !rho || !flags || !body_force) return fail(ctx, "null argument");
+    CUDA_OK(ctx, launch_apply_surface_tension(ctx->g, surface_force, rho, flags, body_force, (cudaStream_t)stream));
+    ctx->launches++;
+    return 0;
+}
+
+int lbm_phase_field_step(lbm_ctx *ctx, float *phi, float *phi_new, const float *mu, const float *u, float *rho, float *phase, float mobility,
+                         float dt, double rho_water, double rho_air, void *stream) {
+    if (!ctx || !phi || !phi_new || !u || !rho || !phase) return fail(ctx, "null argument");
+    if (phi == phi_new) return fail(ctx, "lbm_phase_field_step: phi and phi_new must be distinct buffers");
+    if (single_slab_only(ctx, "lbm_phase_field_step")) return 1;
+    CUDA_OK(ctx, launch_phase_field_step(ctx->g, phi, phi_new, mu, u, rho, phase, mobility, dt, (float)rho_air, (float)(rho_water - rho_air),
+                                         (cudaStream_t)stream));
+    ctx->launches += 2;
+    return 0;
+}
+
+int lbm_density_from_phase(lbm_ctx *ctx, const float *phi, float *rho, float *phase, double rho_water, double rho_air, void *stream) {
+    if (!ctx || !phi || !rho || !phase) return fail(ctx, "null argument");
+    CUDA_OK(ctx, launch_density_from_phase(ctx->g, phi, rho, phase, (float)rho_air, (float)(rho_water - rho_air), (cudaStream_t)stream));
+    ctx->launches++;
+    return 0;
+}
+
+static int pour_common(lbm_ctx *ctx, const lbm_pour *pour, int mode, const uint8_t *flags, float *field, void *stream) {
+    if (!ctx || !pour || !flags || !field) return fail(ctx, "null argument");
+    if (!(pour->radius > 0.0f)) return fail(ctx, "lbm_pour: radius must be positive");
+    float decay[5];
+    for (int d = 0; d < 5; ++d) decay[d] = (float)exp(-(double)d / 2.0);     // the reference folds this constant expression in f64
+    int launched = 0;
+    CUDA_OK(ctx, launch_pour(ctx->g, *pour, decay, mode, flags, field, (cudaStream_t)stream, &launched));
+    ctx->launches += launched;
+    return 0;
+}
+int lbm_pouring_force(lbm_ctx *ctx, const lbm_pour *pour, const uint8_t *flags, float *body_force, void *stream) {
+    return pour_common(ctx, pour, 0, flags, body_force, stream);
+}
+int lbm_pouring_phase_change(lbm_ctx *ctx, const lbm_pour *pour, const uint8_t *flags, float *phi, void *stream) {
+    return pour_common(ctx, pour, 1, flags, phi, stream);
 }
 
 int lbm_particles_couple(lbm_ctx *ctx, const float *u, float *reaction, lbm_particles *ps, float water_density,

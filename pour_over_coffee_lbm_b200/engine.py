@@ -305,6 +305,37 @@ class D3Q19Engine:
         self._check(self.lib.lbm_add_reaction_force(self._ctx, _ptr(reaction), _ptr(self.flags), _ptr(self.body_force), self.stream),
                     "lbm_add_reaction_force")
 
+    # ---- multiphase / pouring producers (csrc/lbm_producers.cu) -----------------------------------
+    def chemical_potential(self, phi, laplacian_phi, mu, kappa: float):
+        self._check(self.lib.lbm_chemical_potential(self._ctx, _ptr(phi), _ptr(laplacian_phi), _ptr(mu), float(kappa), self.stream),
+                    "lbm_chemical_potential")
+
+    def surface_tension(self, phi, mu, grad_phi, grad_mu, normal, curvature, surface_force, sigma: float, apply: bool = True):
+        """compute_gradients + compute_curvature + compute_surface_tension_force (+ apply_surface_tension when `apply`)."""
+        self._check(self.lib.lbm_surface_tension(self._ctx, _ptr(phi), _ptr(mu), _ptr(self.rho), _ptr(self.flags), _ptr(grad_phi), _ptr(grad_mu),
+                                                 _ptr(normal), _ptr(curvature), _ptr(surface_force),
+                                                 _ptr(self.body_force) if apply else None, float(sigma), self.stream), "lbm_surface_tension")
+
+    def apply_surface_tension(self, surface_force):
+        self._check(self.lib.lbm_apply_surface_tension(self._ctx, _ptr(surface_force), _ptr(self.rho), _ptr(self.flags), _ptr(self.body_force),
+                                                       self.stream), "lbm_apply_surface_tension")
+
+    def phase_field_step(self, phi, phi_new, mu, mobility: float, dt: float, rho_water: float, rho_air: float):
+        self._check(self.lib.lbm_phase_field_step(self._ctx, _ptr(phi), _ptr(phi_new), _ptr(mu), _ptr(self.u), _ptr(self.rho), _ptr(self.phase),
+                                                  float(mobility), float(dt), float(rho_water), float(rho_air), self.stream),
+                    "lbm_phase_field_step")
+
+    def density_from_phase(self, phi, rho_water: float, rho_air: float):
+        self._check(self.lib.lbm_density_from_phase(self._ctx, _ptr(phi), _ptr(self.rho), _ptr(self.phase), float(rho_water), float(rho_air),
+                                                    self.stream), "lbm_density_from_phase")
+
+    def pouring_force(self, pour: "L.LbmPour", body_force=None):
+        bf = self.body_force if body_force is None else body_force
+        self._check(self.lib.lbm_pouring_force(self._ctx, pour, _ptr(self.flags), _ptr(bf), self.stream), "lbm_pouring_force")
+
+    def pouring_phase_change(self, pour: "L.LbmPour", phi):
+        self._check(self.lib.lbm_pouring_phase_change(self._ctx, pour, _ptr(self.flags), _ptr(phi), self.stream), "lbm_pouring_phase_change")
+
     # ---- slabs ----------------------------------------------------------------------------------
     def attach_process_group(self, group=None):
         """Create the NCCL communicator of the z-slab chain; the unique id travels through

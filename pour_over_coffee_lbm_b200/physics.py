@@ -6,6 +6,8 @@ Names and call signatures follow the reference so main.py-style orchestration ke
   FilterPaperSystem          src/physics/filter_paper.py:47-926          (geometry + drag only)
   PressureGradientDrive      src/physics/pressure_gradient_drive.py:14-397 (force mode B / mixed)
   CoffeeParticleSystem       src/physics/coffee_particles.py:14-1245      (two-way coupling only)
+  MultiphaseFlow3D           src/core/multiphase_3d.py:12-579             (surface tension + phase-field step)
+  PrecisePouringSystem       src/physics/precise_pouring.py:12-404        (nozzle force + gradual phase change)
 All device work goes through the C ABI; nothing here computes on the CPU.
 """
 from __future__ import annotations
@@ -15,6 +17,7 @@ from typing import Any, Dict, Optional
 import numpy as np
 import torch
 
+from . import _lib as L
 from .engine import ParticleState, particles_advance, particles_couple, _ptr
 from .fields import ScalarField, VectorField
 
@@ -495,3 +498,276 @@ class CoffeeParticleSystem:
         return {"active_particles": n, "avg_reynolds": float(st.reynolds[act].mean()), "max_reynolds": float(st.reynolds[act].max()),
                 "avg_drag_coeff": float(st.cd[act].mean()), "max_reaction_force": float(torch.sqrt((r * r).sum(0)).max()),
                 "coupling_quality": "active"}
+
+
+# ----------------------------------------------------------------------------------------------------
+class MultiphaseFlow3D:
+    """src/core/multiphase_3d.py:12-579 -- the phase-field system as main.py drives it (main.py:622-631, 795-800, 839):
+    `accumulate_surface_tension_pre_collision()` before the collision and `step()` after it, plus the initial-state
+    helpers.  Device work: lbm_surface_tension (2 launches for the reference's 4 kernels), lbm_phase_field_step
+    (2 launches for 4 kernels), lbm_density_from_phase, lbm_chemical_potential.  The live `step()` of the reference is
+    the second definition (:389-407); the Cahn-Hilliard `step()` at :246-270 is shadowed by it and never runs."""
+
+    def __init__(self, lbm_solver: Any):
+        self.lbm = lbm_solver
+        e = lbm_solver.engine
+        cfg = lbm_solver.config
+        if e.zghost:
+            raise NotImplementedError("MultiphaseFlow3D: single slab only (the phi / normal stencils have no halo exchange yet)")
+        if e.body_force is None or e.phase is None or e.flags is None:
+            raise ValueError("MultiphaseFlow3D needs a solver with body_force, phase and a flag field (force=True, phase=True, walls=True)")
+        sc = lambda: torch.zeros_like(e.rho)
+        vc = lambda: torch.zeros_like(e.body_force)
+        self._phi, self._phi_new, self._mu, self._curv, self._lap = sc(), sc(), sc(), sc(), sc()
+        self._normal, self._grad_phi, self._grad_mu, self._sf = vc(), vc(), vc(), vc()
+        self.phi = ScalarField(lambda: self._phi); self.phi_new = ScalarField(lambda: self._phi_new)
+        self.mu = ScalarField(lambda: self._mu); self.curvature = ScalarField(lambda: self._curv)
+        self.laplacian_phi = ScalarField(lambda: self._lap)
+        self.normal = VectorField(lambda: self._normal); self.grad_phi = VectorField(lambda: self._grad_phi)
+        self.grad_mu = VectorField(lambda: self._grad_mu); self.surface_force = VectorField(lambda: self._sf)
+        # multiphase_3d.py:40-47
+        self.INTERFACE_WIDTH = 2.0
+        self.MOBILITY = 0.001
+        self.SURFACE_TENSION_COEFF = cfg.SURFACE_TENSION_LU
+        self.CAHN_NUMBER = 0.005
+        self.BETA = 12.0 * self.SURFACE_TENSION_COEFF / self.INTERFACE_WIDTH
+        self.KAPPA = 1.5 * self.SURFACE_TENSION_COEFF * self.INTERFACE_WIDTH
+
+    def _ready(self):
+        self.lbm._sync_flags()
+        return self.lbm.engine
+
+    # ---- kernels of the reference, same names ----------------------------------------------------------------
+    def init_phase_field(self) -> None:
+        """multiphase_3d.py:55-78: a dry dripper, phi = -1 everywhere."""
+        self._phi.fill_(-1.0)
+
+    def compute_chemical_potential(self) -> None:
+        """multiphase_3d.py:80-109."""
+        kappa = 3.0 * self.SURFACE_TENSION_COEFF * self.INTERFACE_WIDTH / 8.0
+        self._ready().chemical_potential(self._phi, self._lap, self._mu, kappa)
+
+    def _surface_tension_fields(self, apply: bool) -> None:
+        self._ready().surface_tension(self._phi, self._mu, self._grad_phi, self._grad_mu, self._normal, self._curv, self._sf,
+                                      self.SURFACE_TENSION_COEFF, apply=apply)
+
+    def compute_gradients(self) -> None:
+        """multiphase_3d.py:111-132.  The device pass also refreshes curvature and surface_force (one fused chain)."""
+        self._surface_tension_fields(False)
+
+    compute_curvature = compute_gradients                   # :134-149, same fused pass
+    compute_surface_tension_force = compute_gradients       # :313-332, same fused pass
+
+    def apply_surface_tension(self) -> None:
+        """multiphase_3d.py:354-363."""
+        self._ready().apply_surface_tension(self._sf)
+
+    def accumulate_surface_tension_pre_collision(self) -> None:
+        """multiphase_3d.py:409-418."""
+        self._surface_tension_fields(True)
+
+    def update_density_from_phase(self) -> None:
+        """multiphase_3d.py:365-381."""
+        cfg = self.lbm.config
+        self._ready().density_from_phase(self._phi, cfg.RHO_WATER, cfg.RHO_AIR)
+
+    def copy_phase_field(self) -> None:
+        self._phi.copy_(self._phi_new)
+
+    def step(self, step_count: int = 0, precollision_applied: bool = False) -> None:
+        """multiphase_3d.py:389-407."""
+        cfg = self.lbm.config
+        self._surface_tension_fields((not precollision_applied) and step_count > 10)
+        self.lbm.engine.phase_field_step(self._phi, self._phi_new, self._mu, self.MOBILITY, cfg.DT, cfg.RHO_WATER, cfg.RHO_AIR)
+
+    # ---- initial state (multiphase_3d.py:420-579) --------------------------------------------------------------
+    def _set_dry_initial_state(self) -> None:
+        fluid = self._ready().solid == 0
+        self._phi[fluid] = -1.0
+        self._phi_new[fluid] = -1.0
+
+    def validate_initial_phase_consistency(self) -> None:
+        phi = self._phi
+        bad = int(((phi < -1.1) | (phi > 1.1)).sum().item())
+        if bad > 0:
+            raise ValueError(f"{bad} phase-field values outside [-1, 1]")
+
+    def standardize_initial_state(self, force_dry_state: bool = True) -> None:
+        if force_dry_state:
+            self._set_dry_initial_state()
+        self.update_density_from_phase()
+        self.compute_chemical_potential()
+        self.compute_gradients()
+        self.validate_initial_phase_consistency()
+
+    def get_interface_statistics(self) -> Dict[str, Any]:
+        """multiphase_3d.py:290-311."""
+        cfg = self.lbm.config
+        phi = self._phi
+        interface = phi.abs() < 0.9
+        gmag = torch.linalg.vector_norm(self._grad_phi, dim=0)
+        thick = (1.0 / (gmag + 1e-10))[interface]
+        return {"interface_volume": float(interface.sum().item()) * cfg.SCALE_LENGTH ** 3,
+                "water_fraction": float((phi > 0).sum().item()) / phi.numel(),
+                "interface_thickness": (float(thick.mean().item()) if thick.numel() else float("nan")) * cfg.SCALE_LENGTH,
+                "max_curvature": float(self._curv.abs().max().item()),
+                "surface_tension_magnitude": float(torch.linalg.vector_norm(self._sf, dim=0).max().item())}
+
+
+# ----------------------------------------------------------------------------------------------------
+class _Scalar0D:
+    """ti.field(dtype, shape=()) surface: value[None] get / set."""
+
+    def __init__(self, dtype):
+        self._dt, self._v = dtype, dtype(0)
+
+    def __getitem__(self, _):
+        return self._v
+
+    def __setitem__(self, _, value):
+        self._v = self._dt(value)
+
+
+class PrecisePouringSystem:
+    """src/physics/precise_pouring.py:12-404.  The nozzle state lives on the host (a handful of scalars, as in the
+    reference); the two kernels run over the nozzle's bounding box on the device.  `solver` (or `bind`) names the solver
+    whose engine executes them: the reference passes the fields to each call, and the fields of this framework belong to
+    an engine."""
+
+    def __init__(self, solver: Any = None, config: Any = None):
+        self.lbm = solver
+        cfg = config if config is not None else (solver.config if solver is not None else None)
+        if cfg is None:
+            raise ValueError("PrecisePouringSystem needs a solver or a config")
+        self.config = cfg
+        self.POUR_DIAMETER_CM = 0.5
+        self.POUR_DIAMETER_GRID = self.POUR_DIAMETER_CM / cfg.GRID_SIZE_CM
+        self.POUR_HEIGHT_CM = cfg.POUR_HEIGHT_CM
+        self.POUR_VELOCITY = cfg.INLET_VELOCITY
+        v60_top_z = int(5.0 + int(cfg.CUP_HEIGHT / cfg.SCALE_LENGTH))
+        self.POUR_HEIGHT = max(8, min(int(v60_top_z + 2), cfg.NZ - 6))
+        f32, i32 = np.float32, np.int32
+        self.pouring_active, self.pour_pattern = _Scalar0D(i32), _Scalar0D(i32)
+        self.pour_center_x, self.pour_center_y, self.pour_flow_rate, self.pour_time = (_Scalar0D(f32) for _ in range(4))
+        self.spiral_radius, self.spiral_speed, self.spiral_center_x, self.spiral_center_y = (_Scalar0D(f32) for _ in range(4))
+
+    def bind(self, solver) -> None:
+        self.lbm = solver
+
+    def start_pouring(self, center_x=None, center_y=None, flow_rate=1.0, pattern="center") -> None:
+        """precise_pouring.py:49-74."""
+        cfg = self.config
+        center_x = cfg.NX // 2 if center_x is None else center_x
+        center_y = cfg.NY // 2 if center_y is None else center_y
+        self.pour_center_x[None] = center_x; self.pour_center_y[None] = center_y
+        self.pour_flow_rate[None] = flow_rate
+        self.pouring_active[None] = 1
+        self.pour_time[None] = 0.0
+        if pattern == "center":
+            self.pour_pattern[None] = 0
+        elif pattern == "spiral":
+            self.pour_pattern[None] = 1
+            self.spiral_center_x[None] = center_x; self.spiral_center_y[None] = center_y
+            self.spiral_radius[None] = 5.0; self.spiral_speed[None] = 1.0
+
+    def stop_pouring(self) -> None:
+        self.pouring_active[None] = 0
+
+    def _get_current_pour_position(self):
+        """precise_pouring.py:81-97, f32 like the kernel-scope original."""
+        f = np.float32
+        x, y = self.pour_center_x[None], self.pour_center_y[None]
+        if self.pour_pattern[None] == 1:
+            t = self.pour_time[None] * self.spiral_speed[None]
+            r = self.spiral_radius[None] * (f(1.0) + f(0.1) * t)
+            x = self.spiral_center_x[None] + r * np.cos(t)
+            y = self.spiral_center_y[None] + r * np.sin(t)
+            d = self.POUR_DIAMETER_GRID
+            x = max(f(d), min(f(self.config.NX - d), x))
+            y = max(f(d), min(f(self.config.NY - d), y))
+        return f(x), f(y)
+
+    def _pour_struct(self, dt: float) -> "L.LbmPour":
+        x, y = self._get_current_pour_position()
+        return L.LbmPour(pour_x=float(x), pour_y=float(y), radius=float(np.float32(self.POUR_DIAMETER_GRID / 2.0)),
+                         pour_z=int(self.POUR_HEIGHT), velocity=float(np.float32(self.POUR_VELOCITY)),
+                         flow_rate=float(self.pour_flow_rate[None]), dt=float(np.float32(dt)))
+
+    @staticmethod
+    def _tensor(field_or_tensor):
+        return field_or_tensor._get() if hasattr(field_or_tensor, "_get") else field_or_tensor
+
+    def _engine(self):
+        if self.lbm is None:
+            raise ValueError("PrecisePouringSystem is not bound to a solver (pass solver= or call bind())")
+        self.lbm._sync_flags()
+        return self.lbm.engine
+
+    def apply_pouring_force(self, lbm_body_force, solid, dt: float) -> None:
+        """precise_pouring.py:131-163.  `solid` is accepted for signature parity; the kernel reads the engine's packed flags
+        (same mask).  main.py:778 passes four arguments, which raises TypeError there as well and is swallowed by its
+        try/except."""
+        if self.pouring_active[None] != 1:
+            return
+        self.pour_time[None] = self.pour_time[None] + np.float32(dt)
+        self._engine().pouring_force(self._pour_struct(dt), self._tensor(lbm_body_force))
+
+    def apply_gradual_phase_change(self, multiphase_phi, solid, dt: float) -> None:
+        """precise_pouring.py:165-196."""
+        if self.pouring_active[None] != 1:
+            return
+        self._engine().pouring_phase_change(self._pour_struct(dt), self._tensor(multiphase_phi))
+
+    def create_water_impact_force(self, particle_system, max_force: float, dt: float) -> None:
+        raise NotImplementedError("create_water_impact_force (precise_pouring.py:196-233) is not on main.py's step path and is not built")
+
+    def adjust_flow_rate(self, new_rate) -> None:
+        self.pour_flow_rate[None] = max(0.1, min(3.0, new_rate))
+
+    def switch_to_spiral_pour(self, radius=10.0, speed=1.0) -> None:
+        if self.pouring_active[None]:
+            self.pour_pattern[None] = 1
+            self.spiral_radius[None] = radius; self.spiral_speed[None] = speed
+
+    def move_pour_center(self, new_x, new_y) -> None:
+        self.pour_center_x[None] = max(5, min(self.config.NX - 5, new_x))
+        self.pour_center_y[None] = max(5, min(self.config.NY - 5, new_y))
+
+    def get_pouring_info(self) -> Dict[str, Any]:
+        """precise_pouring.py:235-274."""
+        if self.pouring_active[None] != 1:
+            return {"active": False, "position": (0, 0), "diameter_grid": 0, "diameter_cm": 0, "velocity": 0, "flow_rate": 0,
+                    "pour_time": 0, "pattern": 0}
+        x, y = self._get_current_pour_position()
+        return {"active": True, "position": (float(x), float(y)), "diameter_grid": float(self.POUR_DIAMETER_GRID),
+                "diameter_cm": float(self.POUR_DIAMETER_CM), "velocity": float(self.POUR_VELOCITY),
+                "flow_rate": float(self.pour_flow_rate[None]), "pour_time": float(self.pour_time[None]),
+                "pattern": int(self.pour_pattern[None])}
+
+    def get_current_flow_rate(self) -> float:
+        if self.pouring_active[None] == 0:
+            return 0.0
+        cfg = self.config
+        return float(self.pour_flow_rate[None] * cfg.INLET_VELOCITY * (cfg.INLET_AREA / cfg.SCALE_LENGTH ** 2))
+
+    def get_current_flow_rate_ml_s(self) -> float:
+        return float(self.config.POUR_RATE_ML_S * max(0.0, self.pour_flow_rate[None]))
+
+    def _check_pouring_conditions(self) -> Dict[str, Any]:
+        """precise_pouring.py:314-349."""
+        cfg = self.config
+        r, pz, h = self.POUR_DIAMETER_GRID / 2.0, self.POUR_HEIGHT, 4.0
+        cx, cy = cfg.NX // 2, cfg.NY // 2
+        ii = np.arange(max(0, int(cx - r)), min(cfg.NX, int(cx + r + 1)))
+        jj = np.arange(max(0, int(cy - r)), min(cfg.NY, int(cy + r + 1)))
+        kk = np.arange(max(0, int(pz - h)), min(cfg.NZ, int(pz + 1)))
+        d = np.sqrt((ii[:, None] - cx) ** 2.0 + (jj[None, :] - cy) ** 2.0)
+        inside = int((d <= r).sum()) * int(((kk <= pz) & (kk >= pz - h)).sum())
+        total = ii.size * jj.size * kk.size
+        return {"center_position": (cx, cy), "pour_radius": r, "z_range": [pz - h, pz], "affected_cells": inside,
+                "total_checked": total, "effectiveness": inside / max(1, total)}
+
+    def get_pouring_diagnostics(self) -> Dict[str, Any]:
+        return {"configuration": {"diameter_cm": self.POUR_DIAMETER_CM, "diameter_grid": self.POUR_DIAMETER_GRID,
+                                  "height": self.POUR_HEIGHT, "velocity": self.POUR_VELOCITY, "grid_size_cm": self.config.GRID_SIZE_CM},
+                "current_state": self.get_pouring_info(), "conditions_check": self._check_pouring_conditions()}

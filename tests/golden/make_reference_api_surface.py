@@ -28,6 +28,8 @@ if __name__ == "__main__":
         from src.physics.coffee_particles import CoffeeParticleSystem
         from src.physics.boundary_conditions import BoundaryConditionManager
         from src.physics.les_turbulence import LESTurbulenceModel
+        from src.core.multiphase_3d import MultiphaseFlow3D
+        from src.physics.precise_pouring import PrecisePouringSystem
         s = LBMSolver()
     proto = sorted(getattr(LBMSolverProtocol, "__protocol_attrs__", set()))
     out = {
@@ -42,6 +44,8 @@ if __name__ == "__main__":
         "CoffeeParticleSystem.methods": public_methods(CoffeeParticleSystem),
         "BoundaryConditionManager.methods": public_methods(BoundaryConditionManager),
         "LESTurbulenceModel.methods": public_methods(LESTurbulenceModel),
+        "MultiphaseFlow3D.methods": public_methods(MultiphaseFlow3D),
+        "PrecisePouringSystem.methods": public_methods(PrecisePouringSystem),
     }
     with open(os.path.join(HERE, "reference_api_surface.json"), "w") as fh:
         json.dump(out, fh, indent=1, sort_keys=True)

@@ -60,7 +60,11 @@ def run_step_scenario(config, n, steps, seed, gravity, phase_mode):
         fp.initialize_filter_geometry()
         s.boundary_manager.set_filter_system(fp)
     # the same seeded inputs tests/helpers.py:reference_v60_state builds for the oracle
-    st = H.reference_v60_state(n, seed=seed, gravity=gravity, body=1e-5, phase_mode=phase_mode)
+    if phase_mode == "air_random":      # tau_air everywhere (the stable regime of the legacy solver), gravity*phase active
+        st = H.reference_v60_state(n, seed=seed, gravity=gravity, body=1e-5, phase_mode="none")
+        st.phase[:] = np.random.default_rng(seed + 1000).uniform(0.0, 0.5, size=st.phase.shape).astype(np.float32)
+    else:
+        st = H.reference_v60_state(n, seed=seed, gravity=gravity, body=1e-5, phase_mode=phase_mode)
     inp = dict(f=st.f.copy(), phase=st.phase.copy(), body_force=st.body_force.copy())
     s.f.from_numpy(inp["f"]); s.f_new.from_numpy(inp["f"]); s.phase.from_numpy(inp["phase"]); s.body_force.from_numpy(inp["body_force"])
     geom = dict(solid=s.solid.to_numpy().astype(np.uint8), filter_zone=fp.filter_zone.to_numpy().astype(np.int32),
@@ -218,6 +222,114 @@ def check_neighbours_against_oracle(res):
     return ok
 
 
+def run_multiphase_scenario(config, n, seed):
+    """The per-step producers next to the LBM step in main.py (main.py:770-800, 839): MultiphaseFlow3D's surface-tension
+    chain and phase-field step, PrecisePouringSystem's nozzle force and gradual phase change, on one seeded state with
+    the V60 mask.  (main.py itself calls apply_pouring_force with four arguments, which raises and is swallowed by its
+    try/except, main.py:778-783; the method is driven here with its declared signature.)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, ROOT)
+    import helpers as H
+    with quiet():
+        from src.core.legacy.lbm_solver import LBMSolver
+        from src.physics.filter_paper import FilterPaperSystem
+        from src.core.multiphase_3d import MultiphaseFlow3D
+        from src.physics.precise_pouring import PrecisePouringSystem
+        s = LBMSolver(); s.init_fields()
+        fp = FilterPaperSystem(s); fp.initialize_filter_geometry()
+        mp = MultiphaseFlow3D(s)
+        pp = PrecisePouringSystem()
+    rng = np.random.default_rng(seed)
+    x = np.arange(n, dtype=np.float32)
+    X, Y, Z = np.meshgrid(x, x, x, indexing="ij")
+    # a wavy free surface through the cone, some noise, saturated cells on both sides, a flat patch (zero gradient)
+    phi = np.tanh((6.5 - Z + 0.8 * np.sin(0.7 * X) + 0.5 * np.cos(0.9 * Y)) / 1.5).astype(np.float32)
+    phi += (0.03 * rng.standard_normal(phi.shape)).astype(np.float32)
+    phi = np.clip(phi, -1.0, 1.0).astype(np.float32)
+    phi[2:6, 2:6, 2:5] = 0.25
+    u = H.smooth_velocity(n, 0.05, seed) + (0.01 * rng.standard_normal((n, n, n, 3))).astype(np.float32)
+    u = u.astype(np.float32); u[3, 4, 5] = 0.0
+    rho = (1.0 + 0.05 * rng.standard_normal((n, n, n))).astype(np.float32)
+    rho[7, 7, 7] = 0.0; rho[8, 7, 6] = 5e-11                    # the rho > 1e-10 guard of apply_surface_tension
+    bf = (1e-4 * rng.standard_normal((n, n, n, 3))).astype(np.float32)
+    phi_new0 = (0.1 * rng.standard_normal((n, n, n))).astype(np.float32)   # the outer layer of phi_new is never written by the update
+    mp.phi.from_numpy(phi); mp.phi_new.from_numpy(phi_new0); s.u.from_numpy(u); s.rho.from_numpy(rho); s.body_force.from_numpy(bf)
+    with quiet():
+        mp.compute_chemical_potential()                         # a non-zero mu for the diffusion term (an input here)
+    res = dict(n=n, solid=s.solid.to_numpy().astype(np.uint8), phi=phi, phi_new_in=phi_new0, mu=mp.mu.to_numpy(),
+               laplacian_phi=mp.laplacian_phi.to_numpy(), interface_width=float(mp.INTERFACE_WIDTH), u=u, rho=rho, body_force=bf,
+               cfg_pour_diameter_grid=float(pp.POUR_DIAMETER_GRID), cfg_pour_height=int(pp.POUR_HEIGHT),
+               sigma=float(mp.SURFACE_TENSION_COEFF), mobility=float(mp.MOBILITY), dt=float(config.DT),
+               rho_water=float(config.RHO_WATER), rho_air=float(config.RHO_AIR))
+    with quiet():
+        mp.accumulate_surface_tension_pre_collision()
+    res.update(st_grad_phi=mp.grad_phi.to_numpy(), st_grad_mu=mp.grad_mu.to_numpy(), st_normal=mp.normal.to_numpy(),
+               st_curvature=mp.curvature.to_numpy(), st_surface_force=mp.surface_force.to_numpy(), st_body_force=s.body_force.to_numpy())
+    with quiet():
+        mp.step(20, precollision_applied=True)
+    res.update(s1_phi=mp.phi.to_numpy(), s1_phi_new=mp.phi_new.to_numpy(), s1_rho=s.rho.to_numpy(), s1_phase=s.phase.to_numpy(),
+               s1_body_force=s.body_force.to_numpy())
+    with quiet():
+        mp.step(21, precollision_applied=False)
+    res.update(s2_phi=mp.phi.to_numpy(), s2_rho=s.rho.to_numpy(), s2_phase=s.phase.to_numpy(), s2_body_force=s.body_force.to_numpy(),
+               s2_surface_force=mp.surface_force.to_numpy(), s2_curvature=mp.curvature.to_numpy())
+    # ---- pouring: a nozzle that covers a few cells of the 16^3 box (diameter and height are plain attributes) ----
+    pp.POUR_DIAMETER_GRID = 5.0
+    pp.POUR_HEIGHT = 10
+    res.update(pour_diameter=float(pp.POUR_DIAMETER_GRID), pour_height=int(pp.POUR_HEIGHT), pour_velocity=float(pp.POUR_VELOCITY))
+    calls = []
+    with quiet():
+        pp.start_pouring(pattern="center", flow_rate=0.3)
+        pp.apply_pouring_force(s.body_force, s.solid, 0.1); calls.append(("center", 0.3, 0.1))
+        pp.apply_gradual_phase_change(mp.phi, s.solid, 0.1)
+        res.update(p1_body_force=s.body_force.to_numpy(), p1_phi=mp.phi.to_numpy())
+        pp.start_pouring(pattern="spiral", flow_rate=1.0)
+        for dt in (0.5, 1e-3, 1e-9):            # plain; acceleration capped at 10; dt below the 1e-8 guard
+            pp.apply_pouring_force(s.body_force, s.solid, dt)
+            pp.apply_gradual_phase_change(mp.phi, s.solid, dt)
+        res.update(p2_body_force=s.body_force.to_numpy(), p2_phi=mp.phi.to_numpy(), p2_pour_time=float(pp.pour_time[None]),
+                   p2_dts=np.array([0.5, 1e-3, 1e-9]))
+        pp.stop_pouring()
+        pp.apply_pouring_force(s.body_force, s.solid, 1.0)
+        res.update(p3_body_force=s.body_force.to_numpy())
+    return res
+
+
+def check_multiphase_against_oracle(res):
+    from oracle import producers_ref as P
+    n = int(res["n"])
+    m = P.MultiphaseState(n)
+    m.phi = res["phi"].copy(); m.phi_new = res["phi_new_in"].copy()
+    u = res["u"]; rho = res["rho"].copy(); bf = res["body_force"].copy(); solid = res["solid"]; phase = np.zeros_like(rho)
+    sig, mob, dt, rw, ra = (float(res[k]) for k in ("sigma", "mobility", "dt", "rho_water", "rho_air"))
+    ok = {}
+    lap = P.compute_chemical_potential(m, sig, float(res["interface_width"]))
+    ok["chemical_potential"] = np.array_equal(m.mu, res["mu"]) and np.array_equal(lap, res["laplacian_phi"])
+    P.accumulate_surface_tension_pre_collision(m, rho, solid, bf, sig)
+    for k, a in (("grad_phi", m.grad_phi), ("grad_mu", m.grad_mu), ("normal", m.normal), ("curvature", m.curvature),
+                 ("surface_force", m.surface_force), ("body_force", bf)):
+        ok["st_" + k] = np.array_equal(a, res["st_" + k])
+    P.multiphase_step(m, u, rho, phase, solid, bf, sig, mob, dt, rw, ra, 20, True)
+    ok["s1"] = all(np.array_equal(a, res[k]) for k, a in (("s1_phi", m.phi), ("s1_phi_new", m.phi_new), ("s1_rho", rho), ("s1_phase", phase),
+                                                         ("s1_body_force", bf)))
+    P.multiphase_step(m, u, rho, phase, solid, bf, sig, mob, dt, rw, ra, 21, False)
+    ok["s2"] = all(np.array_equal(a, res[k]) for k, a in (("s2_phi", m.phi), ("s2_rho", rho), ("s2_phase", phase), ("s2_body_force", bf),
+                                                         ("s2_surface_force", m.surface_force), ("s2_curvature", m.curvature)))
+    p = P.PourState(n, float(res["pour_diameter"]), int(res["pour_height"]), float(res["pour_velocity"]))
+    p.start_pouring(pattern="center", flow_rate=0.3)
+    P.apply_pouring_force(p, bf, solid, 0.1); P.apply_gradual_phase_change(p, m.phi, solid, 0.1)
+    ok["pour_center"] = np.array_equal(bf, res["p1_body_force"]) and np.array_equal(m.phi, res["p1_phi"])
+    p.start_pouring(pattern="spiral", flow_rate=1.0)
+    for d in res["p2_dts"]:
+        P.apply_pouring_force(p, bf, solid, float(d)); P.apply_gradual_phase_change(p, m.phi, solid, float(d))
+    ok["pour_spiral"] = np.array_equal(bf, res["p2_body_force"]) and np.array_equal(m.phi, res["p2_phi"]) and \
+        float(p.pour_time) == float(res["p2_pour_time"])
+    p.active = 0
+    P.apply_pouring_force(p, bf, solid, 1.0)
+    ok["pour_stopped"] = np.array_equal(bf, res["p3_body_force"])
+    ok["nozzle_cells"] = int((res["p1_body_force"] != res["s2_body_force"]).any(-1).sum()) > 10
+    return ok
+
+
 if __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 16
     config = load_reference(n)
@@ -225,6 +337,26 @@ if __name__ == "__main__":
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle import d3q19_ref as R
     all_ok = True
+    if len(sys.argv) > 2 and sys.argv[2] == "long":
+        # BASELINE's "rho and u after 1000 steps" criterion against the reference's own code: ~50 min of emulation at 16^3
+        steps = int(sys.argv[3]) if len(sys.argv) > 3 else 1000
+        t = time.time()
+        inp, geom, out, st = run_step_scenario(config, n, steps, seed=36, gravity=2e-5, phase_mode="air_random")
+        from oracle import ref_cpu as RC
+        cs = RC.CState(st); cs.step(steps)
+        fluid = geom["solid"] == 0
+        ok = np.array_equal(out["rho"][fluid], cs.rho[fluid]) and np.array_equal(out["u"][fluid], cs.u[fluid]) and \
+            np.array_equal(out["f_out"][:, fluid], cs.f[:, fluid])
+        print(f"[reference run] air_random_{steps}: n={n} reference {time.time() - t:.0f} s  C oracle bit-exact: {ok}  max|u| {np.abs(out['u'][fluid]).max():.3e}")
+        np.savez_compressed(os.path.join(HERE, f"reference_run_long_air_{steps}.npz"), n=n, steps=steps, gravity=2e-5, seed=36,
+                            phase_mode="air_random", **inp, **geom, **out)
+        sys.exit(0 if ok else 1)
+    if len(sys.argv) > 2 and sys.argv[2] == "producers":
+        res = run_multiphase_scenario(config, n, seed=43)
+        ok = check_multiphase_against_oracle(res)
+        print("[reference run] multiphase / pouring producers vs oracle:", ok)
+        np.savez_compressed(os.path.join(HERE, "reference_run_multiphase.npz"), **res)
+        sys.exit(0 if all(ok.values()) else 1)
     default_gravity = float(config.GRAVITY_LU)
     scenarios = [("split_phase_small_gravity", 4, 31, 2e-5, "split"), ("water_default_gravity", 3, 32, default_gravity, "water"),
                  ("air_phase", 6, 33, 1e-4, "none")]
@@ -257,5 +389,10 @@ if __name__ == "__main__":
     print("[reference run] neighbours / particles vs oracle:", ok)
     all_ok &= all(ok.values())
     np.savez_compressed(os.path.join(HERE, "reference_run_neighbours.npz"), **res)
+    res = run_multiphase_scenario(config, n, seed=43)
+    ok = check_multiphase_against_oracle(res)
+    print("[reference run] multiphase / pouring producers vs oracle:", ok)
+    all_ok &= all(ok.values())
+    np.savez_compressed(os.path.join(HERE, "reference_run_multiphase.npz"), **res)
     print("ALL OK" if all_ok else "MISMATCH")
     sys.exit(0 if all_ok else 1)

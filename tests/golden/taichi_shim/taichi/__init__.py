@@ -167,6 +167,18 @@ def log(x):
     return np.log(_f(x))
 
 
+def cos(x):
+    if _pyconst(x):
+        return _math.cos(x)
+    return np.cos(_f(x))
+
+
+def sin(x):
+    if _pyconst(x):
+        return _math.sin(x)
+    return np.sin(_f(x))
+
+
 def pow(a, b):  # noqa: A001
     if _pyconst(a, b):
         return float(a) ** b

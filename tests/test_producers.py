@@ -1,0 +1,210 @@
+"""Per-step producers next to the LBM step: MultiphaseFlow3D's surface-tension chain and phase-field
+step, PrecisePouringSystem's nozzle force and gradual phase change.
+
+tests/golden/reference_run_multiphase.npz was recorded by running the UNMODIFIED reference modules
+(src/core/multiphase_3d.py, src/physics/precise_pouring.py) under the pure-Python Taichi stand-in
+(tests/golden/make_reference_goldens.py).  CPU: oracle/producers_ref.py reproduces it bit for bit.  GPU: the CUDA
+kernels, driven through the facade classes and the C ABI, reproduce it bit for bit -- except the nozzle's Gaussian, which
+goes through expf on the device (<= 2 ulp, CUDA math library) and NumPy's exp in the recording.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import helpers as H
+from oracle import producers_ref as P
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_run_multiphase.npz")
+
+
+@pytest.fixture(scope="module")
+def z():
+    return np.load(GOLD)
+
+
+def _consts(z):
+    return tuple(float(z[k]) for k in ("sigma", "mobility", "dt", "rho_water", "rho_air"))
+
+
+# ---- CPU: oracle == recorded reference run ------------------------------------------------------------------------------
+def test_oracle_surface_tension_chain_reproduces_the_reference_run(z):
+    n = int(z["n"]); sig = _consts(z)[0]
+    m = P.MultiphaseState(n); m.phi = z["phi"].copy()
+    lap = P.compute_chemical_potential(m, sig, float(z["interface_width"]))
+    assert np.array_equal(m.mu, z["mu"]) and np.array_equal(lap, z["laplacian_phi"])
+    bf = z["body_force"].copy()
+    P.accumulate_surface_tension_pre_collision(m, z["rho"], z["solid"], bf, sig)
+    for name, got in (("grad_phi", m.grad_phi), ("grad_mu", m.grad_mu), ("normal", m.normal), ("curvature", m.curvature),
+                      ("surface_force", m.surface_force), ("body_force", bf)):
+        assert np.array_equal(got, z["st_" + name]), name
+    # the scenario exercises every branch: flat patches without a normal, saturated cells, the rho guard
+    c = (slice(1, -1),) * 3
+    assert (np.linalg.norm(z["st_normal"][c], axis=-1) == 0).sum() > 0
+    assert (np.abs(z["phi"][c]) >= 0.9).sum() > 100 and (np.abs(z["st_surface_force"]).sum(-1) > 0).sum() > 100
+    assert (z["st_body_force"] != z["body_force"]).any(-1).sum() > 100
+
+
+def test_oracle_phase_field_step_reproduces_the_reference_run(z):
+    n = int(z["n"]); sig, mob, dt, rw, ra = _consts(z)
+    m = P.MultiphaseState(n); m.phi = z["phi"].copy(); m.phi_new = z["phi_new_in"].copy(); m.mu = z["mu"].copy()
+    rho = z["rho"].copy(); bf = z["st_body_force"].copy(); phase = np.zeros_like(rho)
+    P.multiphase_step(m, z["u"], rho, phase, z["solid"], bf, sig, mob, dt, rw, ra, 20, True)
+    for name, got in (("phi", m.phi), ("phi_new", m.phi_new), ("rho", rho), ("phase", phase), ("body_force", bf)):
+        assert np.array_equal(got, z["s1_" + name]), name
+    # the outer layer of phi comes from phi_new's (never written) outer layer: copy_phase_field copies everything
+    assert np.array_equal(m.phi[0], z["phi_new_in"][0]) and not np.array_equal(z["phi"][0], z["phi_new_in"][0])
+    P.multiphase_step(m, z["u"], rho, phase, z["solid"], bf, sig, mob, dt, rw, ra, 21, False)
+    for name, got in (("phi", m.phi), ("rho", rho), ("phase", phase), ("body_force", bf), ("surface_force", m.surface_force),
+                      ("curvature", m.curvature)):
+        assert np.array_equal(got, z["s2_" + name]), name
+    assert (z["s2_body_force"] != z["s1_body_force"]).any()          # step_count > 10 and not precollision_applied: force re-applied
+
+
+def test_oracle_pouring_reproduces_the_reference_run(z):
+    n = int(z["n"])
+    bf = z["s2_body_force"].copy(); phi = z["s2_phi"].copy(); solid = z["solid"]
+    p = P.PourState(n, float(z["pour_diameter"]), int(z["pour_height"]), float(z["pour_velocity"]))
+    P.apply_pouring_force(p, bf, solid, 1.0)                         # not started: nothing happens
+    assert np.array_equal(bf, z["s2_body_force"])
+    p.start_pouring(pattern="center", flow_rate=0.3)
+    P.apply_pouring_force(p, bf, solid, 0.1); P.apply_gradual_phase_change(p, phi, solid, 0.1)
+    assert np.array_equal(bf, z["p1_body_force"]) and np.array_equal(phi, z["p1_phi"])
+    assert (z["p1_body_force"] != z["s2_body_force"]).any(-1).sum() > 50
+    p.start_pouring(pattern="spiral", flow_rate=1.0)
+    for dt in z["p2_dts"]:
+        P.apply_pouring_force(p, bf, solid, float(dt)); P.apply_gradual_phase_change(p, phi, solid, float(dt))
+    assert np.array_equal(bf, z["p2_body_force"]) and np.array_equal(phi, z["p2_phi"])
+    assert float(p.pour_time) == float(z["p2_pour_time"])
+    assert np.abs(z["p2_body_force"] - z["p1_body_force"]).max() == pytest.approx(10.0, rel=0.02)    # the 10 lu/ts^2 cap was hit
+    p.active = 0
+    P.apply_pouring_force(p, bf, solid, 1.0)
+    assert np.array_equal(bf, z["p3_body_force"])
+
+
+def test_facade_constants_match_the_reference_run(z):
+    """SURFACE_TENSION_LU, RHO_AIR, INLET_VELOCITY, the nozzle diameter and height the reference derived at 16^3."""
+    from pour_over_coffee_lbm_b200.config import LBMConfig
+    n = int(z["n"])
+    c = LBMConfig(NX=n, NY=n, NZ=n)
+    assert c.SURFACE_TENSION_LU == float(z["sigma"]) and c.RHO_AIR == float(z["rho_air"]) and c.RHO_WATER == float(z["rho_water"])
+    assert c.INLET_VELOCITY == float(z["pour_velocity"]) and c.DT == float(z["dt"])
+    assert 0.5 / c.GRID_SIZE_CM == float(z["cfg_pour_diameter_grid"])
+    assert max(8, min(int(int(5.0 + int(c.CUP_HEIGHT / c.SCALE_LENGTH)) + 2), c.NZ - 6)) == int(z["cfg_pour_height"])
+
+
+# ---- GPU: CUDA kernels through the facades == recorded reference run ---------------------------------------------------
+def _torch(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _solver(z, **kw):
+    from pour_over_coffee_lbm_b200.physics import FilterPaperSystem, MultiphaseFlow3D
+    from pour_over_coffee_lbm_b200.solver import LBMSolver
+    n = int(z["n"])
+    s = LBMSolver(nx=n, ny=n, nz=n, compat="reference", strict=True, **kw)
+    s.init_fields()
+    FilterPaperSystem(s).initialize_filter_geometry()
+    assert np.array_equal(H.from_dev_scalar(s.engine.solid), z["solid"])
+    mp = MultiphaseFlow3D(s)
+    assert mp.SURFACE_TENSION_COEFF == float(z["sigma"]) and mp.MOBILITY == float(z["mobility"])
+    mp.phi.from_numpy(z["phi"]); mp.phi_new.from_numpy(z["phi_new_in"])
+    s.rho.from_numpy(z["rho"]); s.u.from_numpy(z["u"]); s.body_force.from_numpy(z["body_force"])
+    return s, mp
+
+
+@pytest.mark.gpu
+def test_gpu_multiphase_chain_reproduces_the_reference_run(z):
+    s, mp = _solver(z)
+    mp.compute_chemical_potential()
+    assert np.array_equal(mp.mu.to_numpy(), z["mu"]) and np.array_equal(mp.laplacian_phi.to_numpy(), z["laplacian_phi"])
+    launches = s.engine.launch_count()
+    mp.accumulate_surface_tension_pre_collision()
+    assert s.engine.launch_count() - launches == 2                  # 4 Taichi kernels of the reference in 2 launches
+    for name, field in (("grad_phi", mp.grad_phi), ("grad_mu", mp.grad_mu), ("normal", mp.normal), ("curvature", mp.curvature),
+                        ("surface_force", mp.surface_force), ("body_force", s.body_force)):
+        assert np.array_equal(field.to_numpy(), z["st_" + name]), name
+    mp.step(20, precollision_applied=True)
+    for name, field in (("phi", mp.phi), ("phi_new", mp.phi_new), ("rho", s.rho), ("phase", s.phase), ("body_force", s.body_force)):
+        assert np.array_equal(field.to_numpy(), z["s1_" + name]), name
+    mp.step(21, precollision_applied=False)
+    for name, field in (("phi", mp.phi), ("rho", s.rho), ("phase", s.phase), ("body_force", s.body_force),
+                        ("surface_force", mp.surface_force), ("curvature", mp.curvature)):
+        assert np.array_equal(field.to_numpy(), z["s2_" + name]), name
+    # the stand-alone entry points
+    s.body_force.from_numpy(z["s1_body_force"]); s.rho.from_numpy(z["s1_rho"])
+    mp.apply_surface_tension()
+    assert np.array_equal(s.body_force.to_numpy(), z["s2_body_force"])
+    mp.update_density_from_phase()
+    assert np.array_equal(s.rho.to_numpy(), z["s2_rho"]) and np.array_equal(s.phase.to_numpy(), z["s2_phase"])
+    st = mp.get_interface_statistics()
+    assert st["max_curvature"] == pytest.approx(float(np.abs(z["s2_curvature"]).max()), rel=1e-6)
+
+
+@pytest.mark.gpu
+def test_gpu_pouring_reproduces_the_reference_run(z):
+    from pour_over_coffee_lbm_b200.physics import PrecisePouringSystem
+    s, mp = _solver(z)
+    pp = PrecisePouringSystem(s)
+    assert pp.POUR_DIAMETER_GRID == float(z["cfg_pour_diameter_grid"]) and pp.POUR_HEIGHT == int(z["cfg_pour_height"])
+    assert pp.POUR_VELOCITY == float(z["pour_velocity"])
+    pp.POUR_DIAMETER_GRID = float(z["pour_diameter"]); pp.POUR_HEIGHT = int(z["pour_height"])
+    s.body_force.from_numpy(z["s2_body_force"]); mp.phi.from_numpy(z["s2_phi"])
+    pp.apply_pouring_force(s.body_force, s.solid, 1.0)              # not started
+    assert np.array_equal(s.body_force.to_numpy(), z["s2_body_force"])
+
+    def close(got, want, base, what):
+        # untouched cells are bit-identical; nozzle cells carry expf's <= 2 ulp on the increment
+        touched = want != base
+        assert np.array_equal(got[~touched], want[~touched]), what
+        inc = np.abs(want - base)[touched]
+        assert np.all(np.abs(got - want)[touched] <= 8 * np.finfo(np.float32).eps * np.maximum(inc, np.abs(want[touched]))), what
+
+    pp.start_pouring(pattern="center", flow_rate=0.3)
+    pp.apply_pouring_force(s.body_force, s.solid, 0.1); pp.apply_gradual_phase_change(mp.phi, s.solid, 0.1)
+    close(s.body_force.to_numpy(), z["p1_body_force"], z["s2_body_force"], "centre force")
+    close(mp.phi.to_numpy(), z["p1_phi"], z["s2_phi"], "centre phase change")
+    s.body_force.from_numpy(z["p1_body_force"]); mp.phi.from_numpy(z["p1_phi"])
+    pp.start_pouring(pattern="spiral", flow_rate=1.0)
+    for dt in z["p2_dts"]:
+        pp.apply_pouring_force(s.body_force, s.solid, float(dt)); pp.apply_gradual_phase_change(mp.phi, s.solid, float(dt))
+    assert float(pp.pour_time[None]) == float(z["p2_pour_time"])
+    bf = s.body_force.to_numpy(); phi = mp.phi.to_numpy()
+    assert np.allclose(bf, z["p2_body_force"], rtol=1e-6, atol=1e-9) and np.array_equal(bf[z["p2_body_force"] == z["p1_body_force"]],
+                                                                                         z["p1_body_force"][z["p2_body_force"] == z["p1_body_force"]])
+    assert np.allclose(phi, z["p2_phi"], rtol=1e-6, atol=1e-7)
+    info = pp.get_pouring_info()
+    assert info["active"] and info["pattern"] == 1
+    pp.stop_pouring()
+    before = s.body_force.to_numpy()
+    pp.apply_pouring_force(s.body_force, s.solid, 1.0)
+    assert np.array_equal(s.body_force.to_numpy(), before)
+
+
+@pytest.mark.gpu
+def test_gpu_main_py_step_order_with_producers_runs(z):
+    """main.py:770-839 on the device: clear -> pouring force + phase change -> pressure drive -> surface tension ->
+    step -> multiphase step, a few iterations on the V60 box; fields stay finite and the phase field stays in [-1, 1]."""
+    import torch
+    from pour_over_coffee_lbm_b200.physics import PrecisePouringSystem, PressureGradientDrive
+    s, mp = _solver(z, gravity_lu=1e-5)          # the default GRAVITY_LU of a 16^3 box (618 lu/ts^2) saturates everything
+    s.init_fields()
+    mp.standardize_initial_state(force_dry_state=True)
+    pp = PrecisePouringSystem(s); pp.POUR_DIAMETER_GRID = 5.0; pp.POUR_HEIGHT = 10
+    pd = PressureGradientDrive(s); pd.activate_force_drive(True)
+    pp.start_pouring(pattern="center"); pp.adjust_flow_rate(0.3)
+    for it in range(1, 14):
+        s.clear_body_force()
+        pp.apply_pouring_force(s.body_force, s.solid, 1.0)
+        pp.apply_gradual_phase_change(mp.phi, s.solid, 1.0)
+        pd.apply(it)
+        if it > 10:
+            mp.accumulate_surface_tension_pre_collision()
+        s.step()
+        mp.step(it, precollision_applied=True)
+    phi = mp._phi
+    assert torch.isfinite(phi).all() and float(phi.abs().max()) <= 1.0 + 1e-3
+    assert float((phi > -1.0).sum()) > 0                            # water arrived under the nozzle
+    assert torch.isfinite(s.engine.rho).all() and torch.isfinite(s.engine.u).all()
+    assert float(s.engine.body_force[2].min()) < 0.0                # the nozzle pushed down this step
