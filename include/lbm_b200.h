@@ -255,6 +255,17 @@ typedef struct {
 int  lbm_particles_advance(lbm_ctx *ctx, lbm_particles *ps, float *force, const lbm_particle_bounds *bounds, float dt,
                            int32_t *counters, void *stream);
 
+/* FilterPaperSystem.block_particles_at_filter src/physics/filter_paper.py:616-700: active particles above a filter-zone
+ * cell (flags bit LBM_FLAG_FILTER; the particle's own plane and two either side, first hit wins) that move down bounce
+ * (v_z <- -0.3 v_z), get a horizontal kick (uniform - 0.5) * noise (reference: noise = 0.01) and add 0.01 to
+ * `accumulated` ([zp][y][x], atomics).  The cell index is int(pos / scale_length) as in the reference (quirk Q9).  The
+ * reference's kick comes from Taichi's unseeded generator; here it is a pure function of (seed, particle, draw). */
+int  lbm_particles_block_at_filter(lbm_ctx *ctx, lbm_particles *ps, const uint8_t *flags, float *accumulated,
+                                   float scale_length, float noise, unsigned seed, void *stream);
+/* FilterPaperSystem.update_dynamic_resistance filter_paper.py:703-746 on filter-zone cells:
+ * blockage <- 0.95 blockage + 0.05 * 0.9 (1 - exp(-0.1 accumulated)); accumulated *= 0.999. */
+int  lbm_filter_dynamic_resistance(lbm_ctx *ctx, const uint8_t *flags, float *blockage, float *accumulated, void *stream);
+
 /* ---- multi-GPU slabs -------------------------------------------------------------------- */
 /* Attach an NCCL communicator over the ranks of one box (z-slab chain).  unique_id is the
  * 128-byte ncclUniqueId produced by lbm_nccl_unique_id on rank 0 and broadcast by the host

@@ -249,3 +249,42 @@ def apply_gradual_phase_change(p: PourState, phi, solid, dt: float) -> None:
     change = ((rate * tot) * dt) * p.flow_rate
     new = np.maximum(F32(-1.0), np.minimum(F32(1.0), phi + change))
     phi[...] = np.where(sel, new, phi)
+
+
+# ---- FilterPaperSystem: particle interception and dynamic resistance (src/physics/filter_paper.py) -------------------
+def update_dynamic_resistance(filter_zone, blockage, accumulated) -> None:
+    """filter_paper.py:703-746 (filter-zone cells, in place)."""
+    z = filter_zone == 1
+    nb = F32(0.9) * (F32(1.0) - np.exp(F32(-0.1) * accumulated).astype(F32))
+    blockage[...] = np.where(z, F32(0.95) * blockage + F32(0.05) * nb, blockage)
+    accumulated[...] = np.where(z, accumulated * F32(0.999), accumulated)
+
+
+def uniform01(seed: int, p: int, d: int) -> np.float32:
+    """The device's counter-based draw (csrc/lbm_producers.cu:uniform01, lowbias32 hash): the reference's ti.random() is an
+    unseeded per-thread stream, so the kick is OUR definition -- a pure function of (seed, particle, draw)."""
+    m = 0xFFFFFFFF
+    h = (seed ^ ((p * 0x9E3779B9) & m) ^ ((d * 0x85EBCA6B) & m)) & m
+    h ^= h >> 16; h = (h * 0x7FEB352D) & m; h ^= h >> 15; h = (h * 0x846CA68B) & m; h ^= h >> 16
+    return F32(h >> 8) * F32(1.0 / 16777216.0)
+
+
+def block_particles_at_filter(filter_zone, pos, vel, active, accumulated, scale_length: float, noise: float = 0.01, seed: int = 0) -> None:
+    """filter_paper.py:616-700; pos / vel [P,3] in place.  noise = 0 is the reference with ti.random() == 0.5."""
+    nx, ny, nz = filter_zone.shape
+    sl = F32(scale_length)
+    for p in range(pos.shape[0]):
+        if active[p] == 0:
+            continue
+        g = [int(np.trunc(np.clip(pos[p, c] / sl, -2.0e9, 2.0e9))) for c in range(3)]
+        if not (0 <= g[0] < nx and 0 <= g[1] < ny and 0 <= g[2] < nz):
+            continue
+        for off in range(-2, 3):
+            k = g[2] + off
+            if 0 <= k < nz and filter_zone[g[0], g[1], k] == 1:
+                if vel[p, 2] < 0:
+                    vel[p, 2] = (-vel[p, 2]) * F32(0.3)
+                    vel[p, 0] = vel[p, 0] + (uniform01(seed, p, 0) - F32(0.5)) * F32(noise)
+                    vel[p, 1] = vel[p, 1] + (uniform01(seed, p, 1) - F32(0.5)) * F32(noise)
+                    accumulated[g[0], g[1], k] = accumulated[g[0], g[1], k] + F32(0.01)
+                break

@@ -35,6 +35,8 @@ cudaError_t launch_particles_advance(const lbm_particles &, float *, const lbm_p
 cudaError_t launch_surface_tension(const Grid &, const float *, const float *, const float *, const uint8_t *, float *, float *, float *, float *,
                                    float *, float *, float, cudaStream_t);
 cudaError_t launch_apply_surface_tension(const Grid &, const float *, const float *, const uint8_t *, float *, cudaStream_t);
+cudaError_t launch_dynamic_resistance(const Grid &, const uint8_t *, float *, float *, cudaStream_t);
+cudaError_t launch_particles_block_at_filter(const Grid &, const lbm_particles &, const uint8_t *, float *, float, float, unsigned, cudaStream_t);
 cudaError_t launch_chemical_potential(const Grid &, const float *, float *, float *, float, cudaStream_t);
 cudaError_t launch_phase_field_step(const Grid &, float *, float *, const float *, const float *, float *, float *, float, float, float, float,
                                     cudaStream_t);
@@ -726,6 +728,22 @@ int lbm_density_from_phase(lbm_ctx *ctx, const float *phi, float *rho, float *ph
     if (!ctx || !phi || !rho || !phase) return fail(ctx, "null argument");
     CUDA_OK(ctx, launch_density_from_phase(ctx->g, phi, rho, phase, (float)rho_air, (float)(rho_water - rho_air), (cudaStream_t)stream));
     ctx->launches++;
+    return 0;
+}
+
+int lbm_filter_dynamic_resistance(lbm_ctx *ctx, const uint8_t *flags, float *blockage, float *accumulated, void *stream) {
+    if (!ctx || !flags || !blockage || !accumulated) return fail(ctx, "null argument");
+    CUDA_OK(ctx, launch_dynamic_resistance(ctx->g, flags, blockage, accumulated, (cudaStream_t)stream));
+    ctx->launches++;
+    return 0;
+}
+
+int lbm_particles_block_at_filter(lbm_ctx *ctx, lbm_particles *ps, const uint8_t *flags, float *accumulated, float scale_length, float noise,
+                                  unsigned seed, void *stream) {
+    if (!ctx || !ps || !flags || !accumulated) return fail(ctx, "null argument");
+    if (!(scale_length > 0.0f)) return fail(ctx, "lbm_particles_block_at_filter: scale_length must be positive");
+    CUDA_OK(ctx, launch_particles_block_at_filter(ctx->g, *ps, flags, accumulated, scale_length, noise, seed, (cudaStream_t)stream));
+    ctx->launches += ps->n > 0 ? 1 : 0;
     return 0;
 }
 

@@ -193,6 +193,55 @@ __global__ void pour_kernel(Grid G, PourArgs P, const uint8_t *__restrict__ flag
     }
 }
 
+// FilterPaperSystem.update_dynamic_resistance, filter_paper.py:703-746 (filter-zone cells):
+// blockage <- 0.95 blockage + 0.05 * 0.9 (1 - exp(-0.1 accumulated)); accumulated *= 0.999.  The blockage field is an
+// input of the step kernel's filter damping (apply_filter_effects :578-586).
+__global__ void dynamic_resistance_kernel(Grid G, const uint8_t *__restrict__ flags, float *__restrict__ blockage, float *__restrict__ accumulated) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, zp = blockIdx.z + G.zg;
+    if (x >= G.nx) return;
+    const long long c = ((long long)zp * G.ny + y) * G.nx + x;
+    if (!(flags[c] & LBM_FLAG_FILTER)) return;
+    const float acc = accumulated[c];
+    const float nb = 0.9f * (1.0f - expf(-0.1f * acc));
+    blockage[c] = 0.95f * blockage[c] + 0.05f * nb;
+    accumulated[c] = acc * 0.999f;
+}
+
+// Counter-based uniform [0, 1): the reference draws ti.random() from Taichi's unseeded per-thread generator, which no
+// implementation can reproduce; here a draw is a pure function of (seed, particle, draw index) -- lowbias32 hash.
+__device__ __forceinline__ float uniform01(unsigned seed, unsigned p, unsigned d) {
+    unsigned h = seed ^ (p * 0x9E3779B9u) ^ (d * 0x85EBCA6Bu);
+    h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+    return (float)(h >> 8) * (1.0f / 16777216.0f);
+}
+// FilterPaperSystem.block_particles_at_filter, filter_paper.py:616-700: a particle over a filter-zone cell (5 planes
+// around its own) that moves down bounces with restitution 0.3, gets a small horizontal kick, and leaves 0.01 in
+// accumulated_particles.  The reference divides the (lattice-unit) position by SCALE_LENGTH here (quirk Q9: mixed
+// units) -- reproduced, the caller passes the divisor.
+__global__ void particles_block_at_filter_kernel(Grid G, lbm_particles P, const uint8_t *__restrict__ flags, float *__restrict__ accumulated,
+                                                 float scale_length, float noise, unsigned seed) {
+    const int n = P.n, p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n || P.active[p] == 0) return;
+    const int gx = (int)(P.pos[p] / scale_length), gy = (int)(P.pos[n + p] / scale_length), gz = (int)(P.pos[2 * n + p] / scale_length);
+    if (gx < 0 || gx >= G.nx || gy < 0 || gy >= G.ny || gz < 0 || gz >= G.nz_global) return;
+    for (int off = -2; off <= 2; ++off) {
+        const int k = gz + off;
+        if (k < 0 || k >= G.nz_global) continue;
+        const int zp = k - G.z0 + G.zg;
+        if (zp < 0 || zp >= G.nz + 2 * G.zg) continue;                 // beyond this slab's planes
+        const long long c = ((long long)zp * G.ny + gy) * G.nx + gx;
+        if (!(flags[c] & LBM_FLAG_FILTER)) continue;
+        const float vz = P.vel[2 * n + p];
+        if (vz < 0.0f) {
+            P.vel[2 * n + p] = (-vz) * 0.3f;
+            P.vel[p] = P.vel[p] + (uniform01(seed, (unsigned)p, 0u) - 0.5f) * noise;
+            P.vel[n + p] = P.vel[n + p] + (uniform01(seed, (unsigned)p, 1u) - 0.5f) * noise;
+            atomicAdd(accumulated + c, 0.01f);
+        }
+        break;
+    }
+}
+
 inline dim3 cell_grid(const Grid &G, int b) { return dim3((unsigned)((G.nx + b - 1) / b), (unsigned)G.ny, (unsigned)G.nz); }
 inline int cell_block(const Grid &G) { return G.nx >= 128 ? 128 : 64; }
 
@@ -232,6 +281,18 @@ cudaError_t launch_density_from_phase(const Grid &G, const float *phi, float *rh
     if (G.ny > 65535 || G.nz > 65535) return cudaErrorInvalidValue;
     const int b = cell_block(G);
     mp_copy_density_kernel<<<cell_grid(G, b), b, 0, s>>>(G, phi, const_cast<float *>(phi), rho, phase, rho_air, drho);
+    return cudaGetLastError();
+}
+cudaError_t launch_dynamic_resistance(const Grid &G, const uint8_t *flags, float *blockage, float *accumulated, cudaStream_t s) {
+    if (G.ny > 65535 || G.nz > 65535) return cudaErrorInvalidValue;
+    const int b = cell_block(G);
+    dynamic_resistance_kernel<<<cell_grid(G, b), b, 0, s>>>(G, flags, blockage, accumulated);
+    return cudaGetLastError();
+}
+cudaError_t launch_particles_block_at_filter(const Grid &G, const lbm_particles &ps, const uint8_t *flags, float *accumulated, float scale_length,
+                                             float noise, unsigned seed, cudaStream_t s) {
+    const int b = 256, gr = (ps.n + b - 1) / b;
+    if (ps.n > 0) particles_block_at_filter_kernel<<<gr, b, 0, s>>>(G, ps, flags, accumulated, scale_length, noise, seed);
     return cudaGetLastError();
 }
 // mode 0: body_force (3 components), mode 1: phi.  *launched = 0 when the nozzle's box misses this slab.

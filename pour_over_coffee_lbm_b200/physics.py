@@ -153,23 +153,50 @@ class FilterPaperSystem:
                 "top_radius_lu": cfg.TOP_RADIUS / cfg.SCALE_LENGTH, "bottom_radius_lu": cfg.BOTTOM_RADIUS / cfg.SCALE_LENGTH,
                 "get_radius_at_height": self.get_filter_inner_radius_at_height}
 
-    def update_dynamic_resistance(self) -> None:
-        """filter_paper.py:703-746: blockage <- 0.95 blockage + 0.05 * 0.9 (1 - exp(-0.1 accumulated)); accumulated *= 0.999,
-        in the filter zone.  (Element-wise torch ops on the device fields; the blockage field feeds the step kernel.)"""
+    def _ensure_accumulated(self):
         if self._blockage is None:
-            return
+            raise RuntimeError("FilterPaperSystem: call initialize_filter_geometry() first")
         if getattr(self, "_accumulated", None) is None:
             self._accumulated = torch.zeros_like(self._blockage)
             self.accumulated_particles = ScalarField(lambda: self._accumulated, self.lbm.engine.zghost)
-        zone = self.lbm.engine.filter_zone == 1
-        new = 0.9 * (1.0 - torch.exp(-0.1 * self._accumulated))
-        self._blockage.copy_(torch.where(zone, 0.95 * self._blockage + 0.05 * new, self._blockage))
-        self._accumulated.copy_(torch.where(zone, self._accumulated * 0.999, self._accumulated))
+
+    def update_dynamic_resistance(self) -> None:
+        """filter_paper.py:703-746: blockage <- 0.95 blockage + 0.05 * 0.9 (1 - exp(-0.1 accumulated)); accumulated *= 0.999 in
+        the filter zone (lbm_filter_dynamic_resistance).  The blockage field feeds the step kernel's filter damping."""
+        if self._blockage is None:
+            return
+        self._ensure_accumulated()
+        self.lbm._sync_flags()
+        e = self.lbm.engine
+        e._check(e.lib.lbm_filter_dynamic_resistance(e._ctx, _ptr(e.flags), _ptr(self._blockage), _ptr(self._accumulated), e.stream),
+                 "lbm_filter_dynamic_resistance")
+
+    def block_particles_at_filter(self, particle_positions=None, particle_velocities=None, particle_radii=None, particle_active=None,
+                                  particle_count=None, particle_system=None, noise: float = 0.01, seed: Optional[int] = None) -> None:
+        """filter_paper.py:616-700 (lbm_particles_block_at_filter).  The reference passes the five Taichi fields of the particle
+        system; here the particle arrays belong to a `CoffeeParticleSystem`, so pass it as `particle_system` (or as the first
+        positional argument).  The horizontal kick of the reference comes from Taichi's unseeded ti.random(); here it is a
+        counter-based draw from (seed, particle) -- `seed` defaults to a per-call counter."""
+        ps = particle_system if particle_system is not None else particle_positions
+        if not hasattr(ps, "state"):
+            raise TypeError("block_particles_at_filter needs the CoffeeParticleSystem that owns the particle arrays")
+        self._ensure_accumulated()
+        self.lbm._sync_flags()
+        self._block_calls = getattr(self, "_block_calls", 0) + 1
+        e = self.lbm.engine
+        st = ps.state.struct()
+        import ctypes as C
+        e._check(e.lib.lbm_particles_block_at_filter(e._ctx, C.byref(st), _ptr(e.flags), _ptr(self._accumulated),
+                                                     float(np.float32(self.lbm.config.SCALE_LENGTH)), float(noise),
+                                                     int(self._block_calls if seed is None else seed) & 0xFFFFFFFF, e.stream),
+                 "lbm_particles_block_at_filter")
 
     def step(self, particle_system: Optional[Any] = None) -> None:
         """filter_paper.py:748-790: one filter time step.  The drag on the fluid is inside the fused step kernel
-        (apply_filter_effects); what remains is the blockage update."""
+        (apply_filter_effects); then particle interception and the blockage update."""
         self.apply_filter_effects()
+        if particle_system is not None:
+            self.block_particles_at_filter(particle_system=particle_system)
         self.update_dynamic_resistance()
 
     def print_status(self) -> None:

@@ -330,6 +330,65 @@ def check_multiphase_against_oracle(res):
     return ok
 
 
+def run_filter_particle_scenario(config, n, seed):
+    """FilterPaperSystem.block_particles_at_filter + update_dynamic_resistance (filter_paper.py:616-746; the particle half of
+    FilterPaperSystem.step :748-790).  ti.random() -- an unseeded stream in Taichi -- is pinned to 0.5 for the recording, so the
+    horizontal kick is zero and everything recorded is deterministic.  The method divides positions by SCALE_LENGTH, so the
+    scenario places the particles at (lattice coordinate x SCALE_LENGTH) to reach the filter zone at all."""
+    import taichi
+    taichi.random = lambda dt=None: np.float32(0.5)
+    with quiet():
+        from src.core.legacy.lbm_solver import LBMSolver
+        from src.physics.filter_paper import FilterPaperSystem
+        from src.physics.coffee_particles import CoffeeParticleSystem
+        s = LBMSolver(); s.init_fields()
+        fp = FilterPaperSystem(s); fp.initialize_filter_geometry()
+        P = 300
+        ps = CoffeeParticleSystem(P)
+    rng = np.random.default_rng(seed)
+    zone = fp.filter_zone.to_numpy().astype(np.int32)
+    cells = np.argwhere(zone == 1)
+    pick = cells[rng.integers(0, len(cells), 200)].astype(np.float64)
+    pick[:, 2] += rng.integers(-3, 4, 200)                                   # within / beyond the 5-plane search window
+    rest = rng.uniform(-2.0, n + 2.0, (P - 200, 3))
+    lat = np.concatenate([pick + rng.uniform(0.05, 0.95, pick.shape), rest])
+    pos = (lat * config.SCALE_LENGTH).astype(np.float32)
+    pos[-5:] = rng.uniform(0.0, n, (5, 3)).astype(np.float32)                # lattice-unit positions, as main.py feeds them: far outside
+    vel = (0.05 * rng.standard_normal((P, 3))).astype(np.float32)
+    active = (rng.random(P) < 0.9).astype(np.int32)
+    radius = np.full(P, 3.25e-4, np.float32)
+    ps.position.from_numpy(pos); ps.velocity.from_numpy(vel); ps.radius.from_numpy(radius); ps.active.from_numpy(active)
+    ps.particle_count[None] = P
+    acc0 = np.where(zone == 1, rng.uniform(0.0, 30.0, zone.shape), 0.0).astype(np.float32)
+    blk0 = np.where(zone == 1, rng.uniform(0.0, 0.5, zone.shape), 0.0).astype(np.float32)
+    fp.accumulated_particles.from_numpy(acc0); fp.filter_blockage.from_numpy(blk0)
+    res = dict(n=n, scale_length=float(config.SCALE_LENGTH), filter_zone=zone, p_pos=pos, p_vel=vel, p_active=active, p_radius=radius,
+               accumulated_in=acc0, blockage_in=blk0)
+    with quiet():
+        for t in range(2):
+            fp.block_particles_at_filter(ps.position, ps.velocity, ps.radius, ps.active, ps.particle_count)
+            res[f"b{t}_vel"] = ps.velocity.to_numpy(); res[f"b{t}_accumulated"] = fp.accumulated_particles.to_numpy()
+        for t in range(2):
+            fp.update_dynamic_resistance()
+            res[f"r{t}_blockage"] = fp.filter_blockage.to_numpy(); res[f"r{t}_accumulated"] = fp.accumulated_particles.to_numpy()
+    return res
+
+
+def check_filter_particles_against_oracle(res):
+    from oracle import producers_ref as P
+    vel = res["p_vel"].copy(); acc = res["accumulated_in"].copy(); blk = res["blockage_in"].copy()
+    ok = {}
+    for t in range(2):
+        P.block_particles_at_filter(res["filter_zone"], res["p_pos"], vel, res["p_active"], acc, float(res["scale_length"]), noise=0.0)
+        ok[f"block{t}"] = np.array_equal(vel, res[f"b{t}_vel"]) and np.array_equal(acc, res[f"b{t}_accumulated"])
+    for t in range(2):
+        P.update_dynamic_resistance(res["filter_zone"], blk, acc)
+        ok[f"resist{t}"] = np.array_equal(blk, res[f"r{t}_blockage"]) and np.array_equal(acc, res[f"r{t}_accumulated"])
+    ok["bounced"] = int((res["b0_vel"][:, 2] != res["p_vel"][:, 2]).sum()) > 20
+    ok["second_pass_quiet"] = np.array_equal(res["b0_vel"], res["b1_vel"])      # after the bounce v_z > 0: nothing more happens
+    return ok
+
+
 if __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 16
     config = load_reference(n)
@@ -356,7 +415,11 @@ if __name__ == "__main__":
         ok = check_multiphase_against_oracle(res)
         print("[reference run] multiphase / pouring producers vs oracle:", ok)
         np.savez_compressed(os.path.join(HERE, "reference_run_multiphase.npz"), **res)
-        sys.exit(0 if all(ok.values()) else 1)
+        res2 = run_filter_particle_scenario(config, n, seed=47)
+        ok2 = check_filter_particles_against_oracle(res2)
+        print("[reference run] filter / particle interception vs oracle:", ok2)
+        np.savez_compressed(os.path.join(HERE, "reference_run_filter_particles.npz"), **res2)
+        sys.exit(0 if all(ok.values()) and all(ok2.values()) else 1)
     default_gravity = float(config.GRAVITY_LU)
     scenarios = [("split_phase_small_gravity", 4, 31, 2e-5, "split"), ("water_default_gravity", 3, 32, default_gravity, "water"),
                  ("air_phase", 6, 33, 1e-4, "none")]
@@ -394,5 +457,10 @@ if __name__ == "__main__":
     print("[reference run] multiphase / pouring producers vs oracle:", ok)
     all_ok &= all(ok.values())
     np.savez_compressed(os.path.join(HERE, "reference_run_multiphase.npz"), **res)
+    res = run_filter_particle_scenario(config, n, seed=47)
+    ok = check_filter_particles_against_oracle(res)
+    print("[reference run] filter / particle interception vs oracle:", ok)
+    all_ok &= all(ok.values())
+    np.savez_compressed(os.path.join(HERE, "reference_run_filter_particles.npz"), **res)
     print("ALL OK" if all_ok else "MISMATCH")
     sys.exit(0 if all_ok else 1)

@@ -16,6 +16,7 @@ import helpers as H
 from oracle import producers_ref as P
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_run_multiphase.npz")
+GOLD_FP = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_run_filter_particles.npz")
 
 
 @pytest.fixture(scope="module")
@@ -91,6 +92,31 @@ def test_facade_constants_match_the_reference_run(z):
     assert c.INLET_VELOCITY == float(z["pour_velocity"]) and c.DT == float(z["dt"])
     assert 0.5 / c.GRID_SIZE_CM == float(z["cfg_pour_diameter_grid"])
     assert max(8, min(int(int(5.0 + int(c.CUP_HEIGHT / c.SCALE_LENGTH)) + 2), c.NZ - 6)) == int(z["cfg_pour_height"])
+
+
+def test_oracle_filter_particle_interception_reproduces_the_reference_run():
+    """FilterPaperSystem.block_particles_at_filter + update_dynamic_resistance, recorded with ti.random() pinned to 0.5
+    (Taichi's stream is unseeded), i.e. without the horizontal kick: noise = 0 here."""
+    z = np.load(GOLD_FP)
+    vel = z["p_vel"].copy(); acc = z["accumulated_in"].copy(); blk = z["blockage_in"].copy()
+    for t in range(2):
+        P.block_particles_at_filter(z["filter_zone"], z["p_pos"], vel, z["p_active"], acc, float(z["scale_length"]), noise=0.0)
+        assert np.array_equal(vel, z[f"b{t}_vel"]) and np.array_equal(acc, z[f"b{t}_accumulated"])
+    assert (z["b0_vel"][:, 2] != z["p_vel"][:, 2]).sum() > 20 and np.array_equal(z["b0_vel"][:, :2], z["p_vel"][:, :2])
+    assert (z["b0_accumulated"] != z["accumulated_in"]).sum() > 10
+    for t in range(2):
+        P.update_dynamic_resistance(z["filter_zone"], blk, acc)
+        assert np.array_equal(blk, z[f"r{t}_blockage"]) and np.array_equal(acc, z[f"r{t}_accumulated"])
+    # the kick of the product path: bounded by noise / 2, a pure function of (seed, particle)
+    v1 = z["p_vel"].copy(); v2 = z["p_vel"].copy(); v3 = z["p_vel"].copy()
+    a = z["accumulated_in"].copy()
+    P.block_particles_at_filter(z["filter_zone"], z["p_pos"], v1, z["p_active"], a.copy(), float(z["scale_length"]), 0.01, seed=7)
+    P.block_particles_at_filter(z["filter_zone"], z["p_pos"], v2, z["p_active"], a.copy(), float(z["scale_length"]), 0.01, seed=7)
+    P.block_particles_at_filter(z["filter_zone"], z["p_pos"], v3, z["p_active"], a.copy(), float(z["scale_length"]), 0.01, seed=8)
+    hit = z["b0_vel"][:, 2] != z["p_vel"][:, 2]
+    assert np.array_equal(v1, v2) and not np.array_equal(v1, v3) and np.array_equal(v1[:, 2], z["b0_vel"][:, 2])
+    assert np.abs(v1[:, :2] - z["p_vel"][:, :2]).max() <= 0.005 + 1e-9 and np.array_equal(v1[~hit], z["p_vel"][~hit])
+    assert 0.2 < np.mean([float(P.uniform01(3, p, 0)) for p in range(2000)]) - 0.0 < 0.8
 
 
 # ---- GPU: CUDA kernels through the facades == recorded reference run ---------------------------------------------------
@@ -208,3 +234,40 @@ def test_gpu_main_py_step_order_with_producers_runs(z):
     assert float((phi > -1.0).sum()) > 0                            # water arrived under the nozzle
     assert torch.isfinite(s.engine.rho).all() and torch.isfinite(s.engine.u).all()
     assert float(s.engine.body_force[2].min()) < 0.0                # the nozzle pushed down this step
+
+
+@pytest.mark.gpu
+def test_gpu_filter_particle_interception_reproduces_the_reference_run():
+    """lbm_particles_block_at_filter / lbm_filter_dynamic_resistance through FilterPaperSystem: bounce, accumulation (atomics of
+    one constant: order-free) bit-exact with noise = 0; the blockage update within expf's 2 ulp; the kick equals the oracle's
+    counter-based draw bit for bit."""
+    import torch
+    from pour_over_coffee_lbm_b200.physics import CoffeeParticleSystem, FilterPaperSystem
+    from pour_over_coffee_lbm_b200.solver import LBMSolver
+    z = np.load(GOLD_FP)
+    n = int(z["n"]); npart = z["p_pos"].shape[0]
+    s = LBMSolver(nx=n, ny=n, nz=n, compat="reference", strict=True); s.init_fields()
+    fp = FilterPaperSystem(s); fp.initialize_filter_geometry()
+    assert np.array_equal(H.from_dev_scalar(s.engine.filter_zone), z["filter_zone"])
+    assert float(np.float32(s.config.SCALE_LENGTH)) == float(np.float32(z["scale_length"]))
+    ps = CoffeeParticleSystem(npart, solver=s)
+
+    def load():
+        ps.set_particles(z["p_pos"], z["p_vel"], z["p_radius"])
+        ps.state.active.copy_(torch.from_numpy(z["p_active"]).cuda())
+        fp._ensure_accumulated()
+        fp.accumulated_particles.from_numpy(z["accumulated_in"]); fp.filter_blockage.from_numpy(z["blockage_in"])
+    load()
+    for t in range(2):
+        fp.block_particles_at_filter(particle_system=ps, noise=0.0)
+        assert np.array_equal(ps.velocity.cpu().numpy(), z[f"b{t}_vel"])
+        assert np.array_equal(fp.accumulated_particles.to_numpy(), z[f"b{t}_accumulated"])
+    for t in range(2):
+        fp.update_dynamic_resistance()
+        assert np.array_equal(fp.accumulated_particles.to_numpy(), z[f"r{t}_accumulated"])
+        assert np.allclose(fp.filter_blockage.to_numpy(), z[f"r{t}_blockage"], rtol=1e-6, atol=1e-8)
+    load()
+    fp.block_particles_at_filter(particle_system=ps, noise=0.01, seed=7)
+    want = z["p_vel"].copy(); acc = z["accumulated_in"].copy()
+    P.block_particles_at_filter(z["filter_zone"], z["p_pos"], want, z["p_active"], acc, float(z["scale_length"]), 0.01, seed=7)
+    assert np.array_equal(ps.velocity.cpu().numpy(), want) and np.array_equal(fp.accumulated_particles.to_numpy(), acc)
