@@ -255,6 +255,13 @@ typedef struct {
 int  lbm_particles_advance(lbm_ctx *ctx, lbm_particles *ps, float *force, const lbm_particle_bounds *bounds, float dt,
                            int32_t *counters, void *stream);
 
+/* CoffeeParticleSystem.apply_fluid_forces coffee_particles.py:547-639: force[p] = clamped Stokes drag (nearest-cell fluid
+ * velocity) + buoyancy + gravity for every active particle that passes the reference's guards; others keep their force;
+ * invalid positions deactivate the particle and count into counters[0] (may be NULL).  `force` is the [3][n] array
+ * lbm_particles_advance consumes.  water_viscosity is the dynamic viscosity the reference stores
+ * (WATER_VISCOSITY_90C * WATER_DENSITY_90C); doubles because the reference folds max(1e-8, mu) in f64. */
+int  lbm_particles_fluid_forces(lbm_ctx *ctx, const float *u, lbm_particles *ps, float *force, double water_density,
+                                double water_viscosity, double gravity, int32_t *counters, void *stream);
 /* FilterPaperSystem.block_particles_at_filter src/physics/filter_paper.py:616-700: active particles above a filter-zone
  * cell (flags bit LBM_FLAG_FILTER; the particle's own plane and two either side, first hit wins) that move down bounce
  * (v_z <- -0.3 v_z), get a horizontal kick (uniform - 0.5) * noise (reference: noise = 0.01) and add 0.01 to

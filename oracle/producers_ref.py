@@ -288,3 +288,63 @@ def block_particles_at_filter(filter_zone, pos, vel, active, accumulated, scale_
                     vel[p, 1] = vel[p, 1] + (uniform01(seed, p, 1) - F32(0.5)) * F32(noise)
                     accumulated[g[0], g[1], k] = accumulated[g[0], g[1], k] + F32(0.01)
                 break
+
+
+# ---- CoffeeParticleSystem.apply_fluid_forces (src/physics/coffee_particles.py:547-639) ------------------------------
+def _valid_coordinate(x, y, z, max_coord):
+    ok = not (x < 0 or x > max_coord or y < 0 or y > max_coord or z < 0 or z > max_coord)
+    if not (x == x and y == y and z == z):
+        ok = False
+    if abs(x) > 1e6 or abs(y) > 1e6 or abs(z) > 1e6:
+        ok = False
+    return ok
+
+
+def apply_fluid_forces(u, pos, vel, radius, mass, active, force, water_density, water_viscosity, gravity=9.81) -> int:
+    """coffee_particles.py:547-639, in place on vel / active / force ([P,3]); returns the coordinate-error count.
+    u is the LBM vector field [NX,NY,NZ,3]; water_viscosity = WATER_VISCOSITY_90C * WATER_DENSITY_90C (:70)."""
+    nx, ny, nz = u.shape[:3]
+    max_coord = F32(max(nx, ny, nz))
+    rho_w = F32(water_density); mu_safe = F32(max(1e-8, water_viscosity)); g = F32(gravity)
+    vol_k = F32((4.0 / 3.0) * 3.14159)
+    errors = 0
+    fmax, fmin = (lambda a, b: a if a >= b else b), (lambda a, b: a if a <= b else b)
+    for p in range(pos.shape[0]):
+        if active[p] != 1:
+            continue
+        x, y, z = pos[p]
+        if not _valid_coordinate(x, y, z, max_coord):
+            active[p] = 0; errors += 1
+            continue
+        gi = int(fmax(F32(0), fmin(F32(nx - 2), x))); gj = int(fmax(F32(0), fmin(F32(ny - 2), y))); gk = int(fmax(F32(0), fmin(F32(nz - 2), z)))
+        f = u[gi, gj, gk]
+        fs = np.sqrt((f[0] * f[0] + f[1] * f[1]) + f[2] * f[2])
+        if not (fs == fs and fs <= F32(100.0)):
+            continue
+        v = vel[p].copy()
+        s2 = (v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]
+        if not (v[0] == v[0] and v[1] == v[1] and v[2] == v[2]) or s2 > F32(100.0):
+            vel[p] = 0; v = vel[p].copy()
+        r = f - v
+        rs = np.sqrt((r[0] * r[0] + r[1] * r[1]) + r[2] * r[2])
+        if not (rs > F32(1e-6) and rs < F32(10.0)):
+            continue
+        rad, m = radius[p], mass[p]
+        if (rad < F32(1e-5) or rad > F32(0.01) or rad != rad) or not (m == m and m > 0):
+            continue
+        re = (((rs * F32(2.0)) * rad) * rho_w) / mu_safe
+        re = fmax(F32(0.01), fmin(F32(1000.0), re))
+        cd = F32(24.0) / fmax(F32(0.1), re)
+        cd = fmax(F32(0.1), fmin(F32(10.0), cd))
+        dm = ((((F32(0.5) * cd) * F32(3.14159)) * (rad * rad)) * rho_w) * rs
+        dm = fmin(dm, m * F32(100.0))
+        drag = dm * (r / rs) if rs > 0 else np.zeros(3, F32)
+        volume = vol_k * ((rad * rad) * rad)
+        bm = fmin((volume * rho_w) * g, m * F32(20.0))
+        gm = m * g
+        buoy = np.array([bm * F32(0), bm * F32(0), bm * F32(1)], F32)
+        grav = np.array([gm * F32(0), gm * F32(0), gm * F32(-1)], F32)
+        total = (drag + buoy) + grav
+        fm = np.sqrt((total[0] * total[0] + total[1] * total[1]) + total[2] * total[2])
+        force[p] = total if (fm == fm and fm < m * F32(1000.0)) else grav
+    return errors

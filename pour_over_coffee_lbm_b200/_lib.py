@@ -87,6 +87,7 @@ SIGNATURES = {
     "lbm_particles_couple": (C.c_int, [_P, _P, _P, C.POINTER(LbmParticles), C.c_float, C.c_float, C.c_float, _P]),
     "lbm_particles_under_relax": (C.c_int, [_P, C.POINTER(LbmParticles), C.c_float, _P]),
     "lbm_particles_advance": (C.c_int, [_P, C.POINTER(LbmParticles), _P, C.POINTER(LbmParticleBounds), C.c_float, _P, _P]),
+    "lbm_particles_fluid_forces": (C.c_int, [_P, _P, C.POINTER(LbmParticles), _P, C.c_double, C.c_double, C.c_double, _P, _P]),
     "lbm_particles_block_at_filter": (C.c_int, [_P, C.POINTER(LbmParticles), _P, _P, C.c_float, C.c_float, C.c_uint, _P]),
     "lbm_filter_dynamic_resistance": (C.c_int, [_P, _P, _P, _P, _P]),
     "lbm_nccl_unique_id": (C.c_int, [_P]),

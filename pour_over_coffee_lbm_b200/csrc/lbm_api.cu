@@ -35,6 +35,8 @@ cudaError_t launch_particles_advance(const lbm_particles &, float *, const lbm_p
 cudaError_t launch_surface_tension(const Grid &, const float *, const float *, const float *, const uint8_t *, float *, float *, float *, float *,
                                    float *, float *, float, cudaStream_t);
 cudaError_t launch_apply_surface_tension(const Grid &, const float *, const float *, const uint8_t *, float *, cudaStream_t);
+cudaError_t launch_particles_fluid_forces(const Grid &, const float *, const lbm_particles &, float *, float, float, float, float, float, int *,
+                                          cudaStream_t);
 cudaError_t launch_dynamic_resistance(const Grid &, const uint8_t *, float *, float *, cudaStream_t);
 cudaError_t launch_particles_block_at_filter(const Grid &, const lbm_particles &, const uint8_t *, float *, float, float, unsigned, cudaStream_t);
 cudaError_t launch_chemical_potential(const Grid &, const float *, float *, float *, float, cudaStream_t);
@@ -728,6 +730,19 @@ int lbm_density_from_phase(lbm_ctx *ctx, const float *phi, float *rho, float *ph
     if (!ctx || !phi || !rho || !phase) return fail(ctx, "null argument");
     CUDA_OK(ctx, launch_density_from_phase(ctx->g, phi, rho, phase, (float)rho_air, (float)(rho_water - rho_air), (cudaStream_t)stream));
     ctx->launches++;
+    return 0;
+}
+
+int lbm_particles_fluid_forces(lbm_ctx *ctx, const float *u, lbm_particles *ps, float *force, double water_density, double water_viscosity,
+                               double gravity, int32_t *counters, void *stream) {
+    if (!ctx || !u || !ps || !force) return fail(ctx, "null argument");
+    const Grid &g = ctx->g;
+    const float max_coord = (float)std::max(g.nx, std::max(g.ny, g.nz_global));
+    const float mu_safe = (float)std::max(1e-8, water_viscosity);             // ti.max(1e-8, self.water_viscosity): folded in f64
+    const float vol_k = (float)((4.0 / 3.0) * 3.14159);                        // (4.0/3.0) * 3.14159: folded in f64
+    CUDA_OK(ctx, launch_particles_fluid_forces(g, u, *ps, force, (float)water_density, mu_safe, (float)gravity, vol_k, max_coord, counters,
+                                               (cudaStream_t)stream));
+    ctx->launches += ps->n > 0 ? 1 : 0;
     return 0;
 }
 

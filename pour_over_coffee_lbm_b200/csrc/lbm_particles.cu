@@ -268,6 +268,65 @@ __global__ void __launch_bounds__(256) particles_advance_kernel(lbm_particles P,
     if (viol) atomicAdd(counters + 1, viol);
 }
 
+// ---------------------------------------------------------------------------------------------
+// CoffeeParticleSystem.apply_fluid_forces (coffee_particles.py:547-639): the producer of the integrator's `force`:
+// nearest-cell fluid velocity, clamped Stokes drag, buoyancy and gravity, each with the reference's guards; a particle
+// that fails a guard keeps the force it had.  One thread per particle, reference statement order, -fmad=false.
+// vol_k = f32((4/3) * 3.14159), mu_safe = f32(max(1e-8, water_viscosity)): constant expressions the reference folds in f64.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) particles_fluid_forces_kernel(Grid G, const float *__restrict__ u, lbm_particles P, float *__restrict__ force,
+                                                                     float rho_w, float mu_safe, float gravity, float vol_k, float max_coord,
+                                                                     int *counters) {
+    const int n = P.n;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n || P.active[p] != 1) return;
+    const float px = P.pos[p], py = P.pos[n + p], pz = P.pos[2 * n + p];
+    if (!valid_coordinate(px, py, pz, max_coord)) {
+        P.active[p] = 0;
+        if (counters) atomicAdd(counters, 1);
+        return;
+    }
+    const int gi = (int)fmaxf(0.0f, fminf((float)(G.nx - 2), px));
+    const int gj = (int)fmaxf(0.0f, fminf((float)(G.ny - 2), py));
+    const int gk = (int)fmaxf(0.0f, fminf((float)(G.nz_global - 2), pz));
+    const int kl = gk - G.z0;
+    if (kl < -G.zg || kl >= G.nz + G.zg) return;                     // another slab's cell
+    const long long vol = G.vol, c = ((long long)(kl + G.zg) * G.ny + gj) * G.nx + gi;
+    const float fx = u[c], fy = u[vol + c], fz = u[2 * vol + c];
+    const float fspeed = norm3(fx, fy, fz);
+    if (!(fspeed == fspeed && fspeed <= 100.0f)) return;
+    float vx = P.vel[p], vy = P.vel[n + p], vz = P.vel[2 * n + p];
+    if (!valid_velocity(vx, vy, vz)) { P.vel[p] = 0.0f; P.vel[n + p] = 0.0f; P.vel[2 * n + p] = 0.0f; vx = vy = vz = 0.0f; }
+    const float rx = fx - vx, ry = fy - vy, rz = fz - vz;
+    const float rs = norm3(rx, ry, rz);
+    if (!(rs > 1e-6f && rs < 10.0f)) return;
+    const float radius = P.radius[p], mass = P.mass[p];
+    const bool radius_ok = !(radius < 1e-5f || radius > 0.01f || radius != radius);
+    if (!(radius_ok && mass == mass && mass > 0.0f)) return;
+    float re = (((rs * 2.0f) * radius) * rho_w) / mu_safe;
+    re = fmaxf(0.01f, fminf(1000.0f, re));
+    float cd = 24.0f / fmaxf(0.1f, re);
+    cd = fmaxf(0.1f, fminf(10.0f, cd));
+    float dm = ((((0.5f * cd) * 3.14159f) * (radius * radius)) * rho_w) * rs;
+    dm = fminf(dm, mass * 100.0f);
+    float dx = 0.0f, dy = 0.0f, dz = 0.0f;
+    if (rs > 0.0f) { dx = dm * (rx / rs); dy = dm * (ry / rs); dz = dm * (rz / rs); }
+    const float volume = vol_k * ((radius * radius) * radius);
+    const float bm = fminf((volume * rho_w) * gravity, mass * 20.0f);
+    const float gm = mass * gravity;
+    const float tx = (dx + bm * 0.0f) + gm * 0.0f, ty = (dy + bm * 0.0f) + gm * 0.0f, tz = (dz + bm) + (-gm);
+    const float fm = norm3(tx, ty, tz);
+    if (fm == fm && fm < mass * 1000.0f) { force[p] = tx; force[n + p] = ty; force[2 * n + p] = tz; }
+    else { force[p] = gm * 0.0f; force[n + p] = gm * 0.0f; force[2 * n + p] = -gm; }
+}
+
+cudaError_t launch_particles_fluid_forces(const Grid &G, const float *u, const lbm_particles &ps, float *force, float rho_w, float mu_safe,
+                                          float gravity, float vol_k, float max_coord, int *counters, cudaStream_t s) {
+    if (ps.n <= 0) return cudaSuccess;
+    particles_fluid_forces_kernel<<<(ps.n + 255) / 256, 256, 0, s>>>(G, u, ps, force, rho_w, mu_safe, gravity, vol_k, max_coord, counters);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_particles_couple(const Grid &G, const float *u, float *reaction, const lbm_particles &ps,
                                     float rho_w, float mu_w, float relax, cudaStream_t s) {
     ParticleArgs A{G, u, reaction, ps, rho_w, mu_w, relax};

@@ -504,6 +504,20 @@ class CoffeeParticleSystem:
         particles_advance(self._solver.engine, self.state, dt, center_x, center_y, bottom_z, bottom_radius_lu, top_radius_lu,
                           force=self.force_tensor, counters=self.error_counters)
 
+    def apply_fluid_forces(self, fluid_u=None, fluid_v=None, fluid_w=None, fluid_density=None, pressure=None, dt: float = 0.0) -> None:
+        """coffee_particles.py:547-639 (lbm_particles_fluid_forces): fills the integrator's force from the solver's velocity
+        field.  The reference reads only `fluid_u` (the LBM vector field) of its six arguments; here the field is the bound
+        solver's `u`."""
+        import ctypes as C
+        if getattr(self, "force_tensor", None) is None:
+            self.force_tensor = torch.zeros_like(self.state.pos)
+            self.error_counters = torch.zeros(2, dtype=torch.int32, device=self.state.pos.device)
+        e = self._solver.engine
+        st = self.state.struct()
+        e._check(e.lib.lbm_particles_fluid_forces(e._ctx, _ptr(e.u), C.byref(st), _ptr(self.force_tensor), float(self.water_density),
+                                                  float(self.water_viscosity), float(self.gravity), _ptr(self.error_counters), e.stream),
+                 "lbm_particles_fluid_forces")
+
     def update_particles(self, dt: float) -> None:
         """coffee_particles.py:722-732: the public wrapper with the default V60 bounds."""
         cfg = self._solver.config

@@ -371,6 +371,29 @@ def run_filter_particle_scenario(config, n, seed):
         for t in range(2):
             fp.update_dynamic_resistance()
             res[f"r{t}_blockage"] = fp.filter_blockage.to_numpy(); res[f"r{t}_accumulated"] = fp.accumulated_particles.to_numpy()
+    # ---- CoffeeParticleSystem.apply_fluid_forces (coffee_particles.py:547-639): the producer of the integrator's force ----
+    P2 = 400
+    with quiet():
+        ps2 = CoffeeParticleSystem(P2)
+    u = (rng.standard_normal((n, n, n, 3)) * rng.choice([1e-7, 0.02, 0.5, 30.0, 200.0], (n, n, n, 1), p=[0.1, 0.5, 0.3, 0.05, 0.05])).astype(np.float32)
+    pos2 = rng.uniform(-1.0, n + 1.0, (P2, 3)).astype(np.float32)
+    pos2[:150] = rng.uniform(0.5, n - 1.5, (150, 3)).astype(np.float32)
+    vel2 = (rng.standard_normal((P2, 3)) * rng.choice([1e-3, 0.05, 3.0, 40.0], (P2, 1))).astype(np.float32)
+    rad2 = np.clip(rng.normal(3.25e-4, 1e-4, P2), 1.6e-4, 4.9e-4).astype(np.float32)
+    rad2[::23] = 0.02; rad2[5::29] = 1e-6                                       # validate_radius rejects both
+    mass2 = ((np.float32(4.0 / 3.0) * np.float32(3.14159)) * (rad2 * rad2 * rad2) * np.float32(config.COFFEE_BEAN_DENSITY)).astype(np.float32)
+    mass2[::17] = 0.0; mass2[3::31] = 1e-12                                     # mass guard; tiny mass -> the force caps
+    act2 = (rng.random(P2) < 0.9).astype(np.int32)
+    force0 = (1e-7 * rng.standard_normal((P2, 3))).astype(np.float32)
+    s.u.from_numpy(u)
+    ps2.position.from_numpy(pos2); ps2.velocity.from_numpy(vel2); ps2.radius.from_numpy(rad2); ps2.mass.from_numpy(mass2)
+    ps2.active.from_numpy(act2); ps2.force.from_numpy(force0)
+    with quiet():
+        ps2.apply_fluid_forces(s.u, s.u, s.u, s.rho, s.rho, 0.01)
+    res.update(ff_u=u, ff_pos=pos2, ff_vel=vel2, ff_radius=rad2, ff_mass=mass2, ff_active=act2, ff_force_in=force0,
+               ff_force=ps2.force.to_numpy(), ff_vel_out=ps2.velocity.to_numpy(), ff_active_out=ps2.active.to_numpy(),
+               ff_errors=int(ps2.coordinate_errors[None]), water_density=float(ps2.water_density), water_viscosity=float(ps2.water_viscosity),
+               particle_gravity=float(ps2.gravity))
     return res
 
 
@@ -384,6 +407,12 @@ def check_filter_particles_against_oracle(res):
     for t in range(2):
         P.update_dynamic_resistance(res["filter_zone"], blk, acc)
         ok[f"resist{t}"] = np.array_equal(blk, res[f"r{t}_blockage"]) and np.array_equal(acc, res[f"r{t}_accumulated"])
+    vel = res["ff_vel"].copy(); act = res["ff_active"].copy(); force = res["ff_force_in"].copy()
+    err = P.apply_fluid_forces(res["ff_u"], res["ff_pos"], vel, res["ff_radius"], res["ff_mass"], act, force, float(res["water_density"]),
+                               float(res["water_viscosity"]), float(res["particle_gravity"]))
+    ok["fluid_forces"] = np.array_equal(force, res["ff_force"]) and np.array_equal(vel, res["ff_vel_out"]) and \
+        np.array_equal(act, res["ff_active_out"]) and err == int(res["ff_errors"])
+    ok["fluid_forces_cover"] = int((res["ff_force"] != res["ff_force_in"]).any(-1).sum()) > 50 and err > 10
     ok["bounced"] = int((res["b0_vel"][:, 2] != res["p_vel"][:, 2]).sum()) > 20
     ok["second_pass_quiet"] = np.array_equal(res["b0_vel"], res["b1_vel"])      # after the bounce v_z > 0: nothing more happens
     return ok

@@ -57,6 +57,26 @@ def test_step_kernel_reproduces_the_reference_run(path, vec):
 
 
 @pytest.mark.parametrize("vec", [1, 4])
+def test_step_kernel_reproduces_1000_steps_of_the_reference_run(vec):
+    """BASELINE: "rho and u must agree within 1e-5 relative (fp32) after 1000 steps" -- against 1000 recorded calls of the
+    reference's own LBMSolver.step() (tests/golden/reference_run_long_air_1000.npz): the strict build agrees bit for bit."""
+    z = np.load(os.path.join(GOLD, "reference_run_long_air_1000.npz"))
+    n, steps, gravity = int(z["n"]), int(z["steps"]), float(z["gravity"])
+    assert steps == 1000
+    eng = _engine(n, n, n, compat="reference", periodic=(False, False, False), walls=True, force=True, phase=True, les=True,
+                  porous=True, strict=True, vec=vec, config=_cfg(n, gravity), gravity_lu=gravity)
+    eng.build_v60_geometry()
+    assert np.array_equal(H.from_dev_scalar(eng.solid), z["solid"])
+    eng.phase.copy_(_torch(H.to_dev_scalar(z["phase"]))); eng.body_force.copy_(_torch(H.to_dev_vec(z["body_force"])))
+    eng.import_f(_torch(H.to_dev_pop(z["f"])))
+    eng.step(steps)
+    fluid = z["solid"] == 0
+    assert np.array_equal(H.from_dev_scalar(eng.rho)[fluid], z["rho"][fluid])
+    assert np.array_equal(H.from_dev_vec(eng.u)[fluid], z["u"][fluid])
+    assert np.array_equal(H.from_dev_pop(eng.export_f())[:, fluid], z["f_out"][:, fluid])
+
+
+@pytest.mark.parametrize("vec", [1, 4])
 def test_open_box_step_and_face_bc_reproduce_the_reference_run(vec):
     """No V60 mask, no filter system: open faces (stale w_q inflow), boundary-manager face writes (lbm_face_bc), obstacles
     touching the faces -- the first 30 steps of main.py."""

@@ -112,7 +112,7 @@ def test_facade_classes_cover_the_recorded_reference_api_surface():
     skip = {"LBMSolver.methods": {"enable_temperature_dependent_properties", "enable_thermal_coupling_output", "equilibrium_3d",
                                   "get_temperature_coupling_diagnostics", "step_with_temperature_coupling", "streaming_3d",
                                   "update_properties_from_temperature"},
-            "CoffeeParticleSystem.methods": {"apply_fluid_forces", "check_particle_boundary_violation_safe", "clear_reaction_forces",
+            "CoffeeParticleSystem.methods": {"check_particle_boundary_violation_safe", "clear_reaction_forces",
                                              "compute_drag_coefficient", "constrain_to_boundary_safe", "distribute_force_to_grid",
                                              "emergency_cleanup", "enforce_filter_boundary", "interpolate_fluid_velocity_from_field",
                                              "interpolate_fluid_velocity_trilinear", "validate_system_integrity"},

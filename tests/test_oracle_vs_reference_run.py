@@ -30,6 +30,7 @@ def oracle_state_from_fixture(z):
 def test_fixtures_present():
     assert len(STEP_FILES) == 3 and os.path.exists(os.path.join(GOLD, "reference_run_neighbours.npz"))
     assert os.path.exists(os.path.join(GOLD, "reference_run_openbox.npz"))
+    assert os.path.exists(os.path.join(GOLD, "reference_run_long_air_1000.npz"))
 
 
 @pytest.mark.parametrize("path", STEP_FILES, ids=[os.path.basename(p)[19:-4] for p in STEP_FILES])
@@ -54,6 +55,28 @@ def test_oracle_step_reproduces_the_reference_run(path):
     cs.step(int(z["steps"]))
     assert np.array_equal(cs.rho[fluid], z["rho"][fluid]) and np.array_equal(cs.u[fluid], z["u"][fluid])
     assert np.array_equal(cs.f[:, fluid], z["f_out"][:, fluid])
+
+
+def test_oracle_reproduces_1000_steps_of_the_reference_run():
+    """BASELINE's criterion "rho and u after 1000 steps" against the reference's own code: 1000 calls of LBMSolver.step()
+    (V60 16^3, tau_air relaxation -- the stable regime of the legacy solver --, random phase in [0, 0.5] so gravity acts,
+    seeded state; ~50 min under the Taichi stand-in, recorded once).  The C oracle (all 1000 steps) and the NumPy oracle
+    (its own 1000 steps) land on the recorded rho, u, f bit for bit."""
+    z = np.load(os.path.join(GOLD, "reference_run_long_air_1000.npz"))
+    steps = int(z["steps"])
+    assert steps == 1000
+    fluid = z["solid"] == 0
+    from oracle import ref_cpu as RC
+    cs = RC.CState(oracle_state_from_fixture(z))
+    cs.step(steps)
+    assert np.array_equal(cs.rho[fluid], z["rho"][fluid]) and np.array_equal(cs.u[fluid], z["u"][fluid])
+    assert np.array_equal(cs.f[:, fluid], z["f_out"][:, fluid])
+    assert np.isfinite(z["u"]).all() and np.abs(z["u"][fluid]).max() > 1e-6 and abs(float(z["rho"][fluid].mean()) - 1.0) < 0.05
+    st = oracle_state_from_fixture(z)
+    for _ in range(steps):
+        R.step(st)
+    assert np.array_equal(st.rho[fluid], z["rho"][fluid]) and np.array_equal(st.u[fluid], z["u"][fluid])
+    assert np.array_equal(st.f[:, fluid], z["f_out"][:, fluid])
 
 
 def test_oracle_open_box_reproduces_the_reference_run():

@@ -107,6 +107,12 @@ def test_oracle_filter_particle_interception_reproduces_the_reference_run():
     for t in range(2):
         P.update_dynamic_resistance(z["filter_zone"], blk, acc)
         assert np.array_equal(blk, z[f"r{t}_blockage"]) and np.array_equal(acc, z[f"r{t}_accumulated"])
+    # CoffeeParticleSystem.apply_fluid_forces: drag + buoyancy + gravity with every guard of the reference
+    vel = z["ff_vel"].copy(); act = z["ff_active"].copy(); force = z["ff_force_in"].copy()
+    err = P.apply_fluid_forces(z["ff_u"], z["ff_pos"], vel, z["ff_radius"], z["ff_mass"], act, force, float(z["water_density"]),
+                               float(z["water_viscosity"]), float(z["particle_gravity"]))
+    assert np.array_equal(force, z["ff_force"]) and np.array_equal(vel, z["ff_vel_out"]) and np.array_equal(act, z["ff_active_out"])
+    assert err == int(z["ff_errors"]) > 10 and (z["ff_force"] != z["ff_force_in"]).any(-1).sum() > 50
     # the kick of the product path: bounded by noise / 2, a pure function of (seed, particle)
     v1 = z["p_vel"].copy(); v2 = z["p_vel"].copy(); v3 = z["p_vel"].copy()
     a = z["accumulated_in"].copy()
@@ -117,6 +123,40 @@ def test_oracle_filter_particle_interception_reproduces_the_reference_run():
     assert np.array_equal(v1, v2) and not np.array_equal(v1, v3) and np.array_equal(v1[:, 2], z["b0_vel"][:, 2])
     assert np.abs(v1[:, :2] - z["p_vel"][:, :2]).max() <= 0.005 + 1e-9 and np.array_equal(v1[~hit], z["p_vel"][~hit])
     assert 0.2 < np.mean([float(P.uniform01(3, p, 0)) for p in range(2000)]) - 0.0 < 0.8
+
+
+def test_pouring_facade_host_state_follows_the_oracle(z):
+    """The host half of PrecisePouringSystem (no device needed): pour_time accumulation, centre / spiral nozzle position,
+    the struct handed to lbm_pouring_force, flow-rate limits, diagnostics."""
+    from pour_over_coffee_lbm_b200.config import LBMConfig
+    from pour_over_coffee_lbm_b200.physics import PrecisePouringSystem
+    n = int(z["n"])
+    pp = PrecisePouringSystem(config=LBMConfig(NX=n, NY=n, NZ=n))
+    pp.POUR_DIAMETER_GRID = float(z["pour_diameter"]); pp.POUR_HEIGHT = int(z["pour_height"])
+    ref = P.PourState(n, float(z["pour_diameter"]), int(z["pour_height"]), float(z["pour_velocity"]))
+    assert pp.get_pouring_info()["active"] is False and pp.get_current_flow_rate() == 0.0
+    pp.start_pouring(pattern="spiral", flow_rate=1.0); ref.start_pouring(pattern="spiral", flow_rate=1.0)
+    for dt in (0.5, 1e-3, 0.25, 2.0):
+        pp.pour_time[None] = pp.pour_time[None] + np.float32(dt)          # what apply_pouring_force does before the launch
+        ref.pour_time = np.float32(ref.pour_time + np.float32(dt))
+        x, y = pp._get_current_pour_position(); rx, ry = ref.position()
+        assert x == rx and y == ry and x.dtype == np.float32
+        st = pp._pour_struct(dt)
+        assert st.pour_x == float(rx) and st.pour_y == float(ry) and st.pour_z == int(z["pour_height"])
+        assert st.radius == float(np.float32(float(z["pour_diameter"]) / 2.0)) and st.dt == float(np.float32(dt))
+    assert float(pp.pour_time[None]) == float(ref.pour_time)
+    info = pp.get_pouring_info()
+    assert info["active"] and info["pattern"] == 1 and info["position"] == (float(x), float(y))
+    pp.adjust_flow_rate(7.0); assert float(pp.pour_flow_rate[None]) == 3.0
+    pp.adjust_flow_rate(0.0); assert float(pp.pour_flow_rate[None]) == np.float32(0.1)
+    pp.move_pour_center(-3, 100); assert (float(pp.pour_center_x[None]), float(pp.pour_center_y[None])) == (5.0, n - 5.0)
+    chk = pp._check_pouring_conditions()
+    assert chk["affected_cells"] > 0 and 0 < chk["effectiveness"] <= 1 and chk["z_range"] == [pp.POUR_HEIGHT - 4.0, pp.POUR_HEIGHT]
+    assert pp.get_current_flow_rate_ml_s() == pytest.approx(0.4) and pp.get_pouring_diagnostics()["configuration"]["height"] == pp.POUR_HEIGHT
+    with pytest.raises(ValueError):
+        pp.apply_pouring_force(None, None, 0.1)                              # not bound to a solver: refuses, never a CPU path
+    pp.stop_pouring()
+    pp.apply_pouring_force(None, None, 0.1)                                  # inactive: returns before touching anything
 
 
 # ---- GPU: CUDA kernels through the facades == recorded reference run ---------------------------------------------------
@@ -271,3 +311,26 @@ def test_gpu_filter_particle_interception_reproduces_the_reference_run():
     want = z["p_vel"].copy(); acc = z["accumulated_in"].copy()
     P.block_particles_at_filter(z["filter_zone"], z["p_pos"], want, z["p_active"], acc, float(z["scale_length"]), 0.01, seed=7)
     assert np.array_equal(ps.velocity.cpu().numpy(), want) and np.array_equal(fp.accumulated_particles.to_numpy(), acc)
+
+
+@pytest.mark.gpu
+def test_gpu_apply_fluid_forces_reproduces_the_reference_run():
+    """lbm_particles_fluid_forces through CoffeeParticleSystem.apply_fluid_forces: force, reset velocities, deactivated
+    particles and the error counter equal the recorded run of the reference's kernel bit for bit."""
+    import torch
+    from pour_over_coffee_lbm_b200.physics import CoffeeParticleSystem
+    from pour_over_coffee_lbm_b200.solver import LBMSolver
+    z = np.load(GOLD_FP)
+    n = int(z["n"]); npart = z["ff_pos"].shape[0]
+    s = LBMSolver(nx=n, ny=n, nz=n, compat="reference", strict=True); s.init_fields()
+    s.u.from_numpy(z["ff_u"])
+    ps = CoffeeParticleSystem(npart, solver=s)
+    assert ps.water_density == float(z["water_density"]) and ps.water_viscosity == float(z["water_viscosity"]) and ps.gravity == float(z["particle_gravity"])
+    ps.set_particles(z["ff_pos"], z["ff_vel"], z["ff_radius"], z["ff_mass"])
+    ps.state.active.copy_(torch.from_numpy(z["ff_active"]).cuda())
+    ps.force_tensor = torch.from_numpy(np.ascontiguousarray(z["ff_force_in"].T)).cuda()
+    ps.error_counters = torch.zeros(2, dtype=torch.int32, device="cuda")
+    ps.apply_fluid_forces(s.u, s.u, s.u, s.rho, s.rho, 0.01)
+    assert np.array_equal(ps.force.cpu().numpy(), z["ff_force"])
+    assert np.array_equal(ps.velocity.cpu().numpy(), z["ff_vel_out"]) and np.array_equal(ps.active.cpu().numpy(), z["ff_active_out"])
+    assert ps.coordinate_errors == int(z["ff_errors"])

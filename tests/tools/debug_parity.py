@@ -1,7 +1,8 @@
-"""Ad-hoc parity diagnostics (prints error magnitudes / mismatch locations)."""
+"""Ad-hoc parity diagnostics (prints error magnitudes / mismatch locations).  Test infrastructure: lives under tests/ because it
+calls the CPU oracle (only tests/, smoke() and bench.py's cpu_baseline leg may)."""
 import sys, os
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import helpers as H
 from oracle import d3q19_ref as R, ref_cpu as RC
