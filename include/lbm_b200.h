@@ -185,6 +185,15 @@ int  lbm_add_reaction_force(lbm_ctx *ctx, const float *reaction, const uint8_t *
 int  lbm_surface_tension(lbm_ctx *ctx, const float *phi, const float *mu_or_null, const float *rho, const uint8_t *flags,
                          float *grad_phi, float *grad_mu_or_null, float *normal, float *curvature, float *surface_force,
                          float *body_force_or_null, float sigma, void *stream);
+/* The same chain when only body_force is wanted (what main.py:795-800 needs from accumulate_surface_tension_pre_collision):
+ * ONE launch, no intermediate fields.  surface_force vanishes outside the interface band |phi| < 0.9, so a thread reads its
+ * cells' phi and flags and leaves unless a fluid cell is in the band; band cells rebuild their neighbours' normals from a
+ * 25-point stencil of phi with the statements of the two-launch version: body_force comes out bit-identical to
+ * lbm_surface_tension(..., body_force, ...).  The reference never writes the outer cell layer of `normal` and
+ * `surface_force`; pass the arrays that hold those layers (read there only) or NULL for zeros.  Single slab. */
+int  lbm_surface_tension_body_force(lbm_ctx *ctx, const float *phi, const float *rho, const uint8_t *flags,
+                                    const float *normal_outer_or_null, const float *surface_force_outer_or_null,
+                                    float *body_force, float sigma, void *stream);
 /* MultiphaseFlow3D.compute_chemical_potential multiphase_3d.py:80-109: laplacian_phi (optional output) and
  * mu = phi^3 - phi - kappa * lap(phi) on interior cells; kappa = 3 * sigma * W / 8 folded by the caller.  The reference
  * calls it once, from standardize_initial_state :542-571.  Single slab. */

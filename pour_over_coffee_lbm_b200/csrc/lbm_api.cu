@@ -35,6 +35,8 @@ cudaError_t launch_particles_advance(const lbm_particles &, float *, const lbm_p
 cudaError_t launch_surface_tension(const Grid &, const float *, const float *, const float *, const uint8_t *, float *, float *, float *, float *,
                                    float *, float *, float, cudaStream_t);
 cudaError_t launch_apply_surface_tension(const Grid &, const float *, const float *, const uint8_t *, float *, cudaStream_t);
+cudaError_t launch_surface_tension_lean(const Grid &, const float *, const float *, const uint8_t *, const float *, const float *, float *, float,
+                                        cudaStream_t);
 cudaError_t launch_particles_fluid_forces(const Grid &, const float *, const lbm_particles &, float *, float, float, float, float, float, int *,
                                           cudaStream_t);
 cudaError_t launch_dynamic_resistance(const Grid &, const uint8_t *, float *, float *, cudaStream_t);
@@ -697,6 +699,15 @@ int lbm_surface_tension(lbm_ctx *ctx, const float *phi, const float *mu, const f
     CUDA_OK(ctx, launch_surface_tension(ctx->g, phi, mu, rho, flags, grad_phi, grad_mu, normal, curvature, surface_force, body_force, sigma,
                                         (cudaStream_t)stream));
     ctx->launches += 2;
+    return 0;
+}
+
+int lbm_surface_tension_body_force(lbm_ctx *ctx, const float *phi, const float *rho, const uint8_t *flags, const float *normal_outer,
+                                   const float *surface_force_outer, float *body_force, float sigma, void *stream) {
+    if (!ctx || !phi || !rho || !flags || !body_force) return fail(ctx, "null argument");
+    if (single_slab_only(ctx, "lbm_surface_tension_body_force")) return 1;
+    CUDA_OK(ctx, launch_surface_tension_lean(ctx->g, phi, rho, flags, normal_outer, surface_force_outer, body_force, sigma, (cudaStream_t)stream));
+    ctx->launches++;
     return 0;
 }
 

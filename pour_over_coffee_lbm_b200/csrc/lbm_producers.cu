@@ -213,6 +213,113 @@ __global__ void mp_curvature_force_kernel(Grid G, const float *__restrict__ phi,
     apply_lanes<VEC>(G, c, rho, flags, body_force, sx, sy, sz);
 }
 
+// ---- the same chain WITHOUT materialising grad_phi / normal / curvature / surface_force ---------------------------------
+// What main.py needs from accumulate_surface_tension_pre_collision is body_force; the four fields are diagnostics
+// (get_interface_statistics).  surface_force is zero outside the interface band |phi| < 0.9, so a thread first looks at its
+// own 4 cells (one 128-bit load of phi, one flag word) and leaves unless a fluid cell lies in the band; a band cell then
+// evaluates its own gradient and the gradients of its six neighbours from a 25-point stencil of phi (the neighbours'
+// normals are recomputed instead of read back) with exactly the statements of the two-launch version, so body_force is
+// bit-identical.  Traffic: 5 B/cell + the stencil around the band instead of 117 B/cell.
+// Cells of the outer layer never get a normal / surface_force from the reference's kernels; whatever those arrays hold
+// there is used when the caller passes them (normal_outer / force_outer, read on the outer layer only), else zero.
+__device__ __forceinline__ float unit_component(float gx, float gy, float gz, int comp) {
+    const float mag = norm3(gx, gy, gz);
+    const float g = comp == 0 ? gx : (comp == 1 ? gy : gz);
+    return mag > 1e-10f ? g / mag : 0.0f;
+}
+template <int VEC>
+__global__ void mp_surface_tension_lean_kernel(Grid G, const float *__restrict__ phi, const float *__restrict__ rho, const uint8_t *__restrict__ flags,
+                                               const float *__restrict__ normal_outer, const float *__restrict__ force_outer,
+                                               float *__restrict__ body_force, float sigma) {
+    CellPos P;
+    if (!cell_pos<VEC>(G, P)) return;
+    const long long n = G.vol, c = P.c;
+    const int nx = G.nx;
+    const long long pl = G.plane;
+    bool in[VEC];
+    lanes_interior<VEC>(G, P.x0, in);
+    const unsigned fw = Vec<VEC>::ldflags(flags + c);
+    bool fluid[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) fluid[i] = !((fw >> (8 * i)) & LBM_FLAG_SOLID);
+    float sx[VEC], sy[VEC], sz[VEC];
+    bool work[VEC], any = false;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) { sx[i] = sy[i] = sz[i] = 0.0f; work[i] = false; }
+    // outer layer: the stored force, if the caller keeps one
+    if (force_outer) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i)
+            if (fluid[i] && !(P.row_interior && in[i])) {
+                sx[i] = force_outer[c + i]; sy[i] = force_outer[n + c + i]; sz[i] = force_outer[2 * n + c + i];
+                work[i] = true; any = true;
+            }
+    }
+    if (P.row_interior) {
+        float p0[VEC];
+        Vec<VEC>::ld(phi + c, p0);
+        bool band[VEC], any_band = false;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) { band[i] = in[i] && fluid[i] && fabsf(p0[i]) < 0.9f; any_band |= band[i]; }
+        if (any_band) {
+            const int y = P.y, k = P.k;
+            const bool ym_in = y - 1 >= 1, yp_in = y + 1 <= G.ny - 2, km_in = k - 1 >= 1, kp_in = k + 1 <= G.nz_global - 2;
+            // value of phi at (x0 + dx, y + dy, k + dk); 0 beyond the row ends (only cells whose result is unused read those)
+            auto at = [&](int dx, int dy, int dk) -> float {
+                const int x = P.x0 + dx;
+                return (x >= 0 && x < nx) ? phi[c + dx + (long long)dy * nx + (long long)dk * pl] : 0.0f;
+            };
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                if (!band[i]) continue;
+                const int x = P.x0 + i;
+                const float gx = (at(i + 1, 0, 0) - at(i - 1, 0, 0)) * 0.5f, gy = (at(i, 1, 0) - at(i, -1, 0)) * 0.5f,
+                            gz = (at(i, 0, 1) - at(i, 0, -1)) * 0.5f;
+                const float mag = norm3(gx, gy, gz);
+                if (!(mag > 1e-10f)) continue;                                    // normal = 0: no curvature, no force
+                const float n0x = gx / mag, n0y = gy / mag, n0z = gz / mag;
+                float curv = 0.0f;
+                if (norm3(n0x, n0y, n0z) > 1e-10f) {
+                    float nxp, nxm, nyp, nym, nzp, nzm;
+                    if (x + 1 <= nx - 2) nxp = unit_component((at(i + 2, 0, 0) - at(i, 0, 0)) * 0.5f, (at(i + 1, 1, 0) - at(i + 1, -1, 0)) * 0.5f,
+                                                              (at(i + 1, 0, 1) - at(i + 1, 0, -1)) * 0.5f, 0);
+                    else nxp = normal_outer ? normal_outer[c + i + 1] : 0.0f;
+                    if (x - 1 >= 1) nxm = unit_component((at(i, 0, 0) - at(i - 2, 0, 0)) * 0.5f, (at(i - 1, 1, 0) - at(i - 1, -1, 0)) * 0.5f,
+                                                         (at(i - 1, 0, 1) - at(i - 1, 0, -1)) * 0.5f, 0);
+                    else nxm = normal_outer ? normal_outer[c + i - 1] : 0.0f;
+                    if (yp_in) nyp = unit_component((at(i + 1, 1, 0) - at(i - 1, 1, 0)) * 0.5f, (at(i, 2, 0) - at(i, 0, 0)) * 0.5f,
+                                                    (at(i, 1, 1) - at(i, 1, -1)) * 0.5f, 1);
+                    else nyp = normal_outer ? normal_outer[n + c + i + nx] : 0.0f;
+                    if (ym_in) nym = unit_component((at(i + 1, -1, 0) - at(i - 1, -1, 0)) * 0.5f, (at(i, 0, 0) - at(i, -2, 0)) * 0.5f,
+                                                    (at(i, -1, 1) - at(i, -1, -1)) * 0.5f, 1);
+                    else nym = normal_outer ? normal_outer[n + c + i - nx] : 0.0f;
+                    if (kp_in) nzp = unit_component((at(i + 1, 0, 1) - at(i - 1, 0, 1)) * 0.5f, (at(i, 1, 1) - at(i, -1, 1)) * 0.5f,
+                                                    (at(i, 0, 2) - at(i, 0, 0)) * 0.5f, 2);
+                    else nzp = normal_outer ? normal_outer[2 * n + c + i + pl] : 0.0f;
+                    if (km_in) nzm = unit_component((at(i + 1, 0, -1) - at(i - 1, 0, -1)) * 0.5f, (at(i, 1, -1) - at(i, -1, -1)) * 0.5f,
+                                                    (at(i, 0, 0) - at(i, 0, -2)) * 0.5f, 2);
+                    else nzm = normal_outer ? normal_outer[2 * n + c + i - pl] : 0.0f;
+                    const float dnx = (nxp - nxm) * 0.5f, dny = (nyp - nym) * 0.5f, dnz = (nzp - nzm) * 0.5f;
+                    curv = (dnx + dny) + dnz;
+                }
+                const float fm = (sigma * curv) * mag;
+                sx[i] = fm * n0x; sy[i] = fm * n0y; sz[i] = fm * n0z;
+                work[i] = true; any = true;
+            }
+        }
+    }
+    if (!any) return;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        if (!work[i]) continue;
+        const float r = rho[c + i];
+        if (r > 1e-10f) {
+            body_force[c + i] = body_force[c + i] + sx[i] / r; body_force[n + c + i] = body_force[n + c + i] + sy[i] / r;
+            body_force[2 * n + c + i] = body_force[2 * n + c + i] + sz[i] / r;
+        }
+    }
+}
+
 // apply_surface_tension :354-363 alone (MultiphaseFlow3D.step with precollision_applied = False re-applies a stored force)
 template <int VEC>
 __global__ void mp_apply_surface_tension_kernel(Grid G, const float *__restrict__ surface_force, const float *__restrict__ rho,
@@ -432,6 +539,13 @@ cudaError_t launch_surface_tension(const Grid &G, const float *phi, const float 
     const int vec = pick_vec(G, aligned16(phi, mu, rho, grad_phi, grad_mu, normal, curvature, surface_force, body_force) && ((uintptr_t)flags & 3u) == 0);
     LAUNCH_CELLS(mp_gradients_kernel, vec, s, G, phi, mu, grad_phi, grad_mu, normal);
     LAUNCH_CELLS(mp_curvature_force_kernel, vec, s, G, phi, rho, flags, grad_phi, normal, curvature, surface_force, body_force, sigma);
+    return cudaGetLastError();
+}
+cudaError_t launch_surface_tension_lean(const Grid &G, const float *phi, const float *rho, const uint8_t *flags, const float *normal_outer,
+                                        const float *force_outer, float *body_force, float sigma, cudaStream_t s) {
+    if (!grid_ok(G)) return cudaErrorInvalidValue;
+    const int vec = pick_vec(G, aligned16(phi) && ((uintptr_t)flags & 3u) == 0);
+    LAUNCH_CELLS(mp_surface_tension_lean_kernel, vec, s, G, phi, rho, flags, normal_outer, force_outer, body_force, sigma);
     return cudaGetLastError();
 }
 cudaError_t launch_apply_surface_tension(const Grid &G, const float *surface_force, const float *rho, const uint8_t *flags, float *body_force,

@@ -316,6 +316,12 @@ class D3Q19Engine:
                                                  _ptr(normal), _ptr(curvature), _ptr(surface_force),
                                                  _ptr(self.body_force) if apply else None, float(sigma), self.stream), "lbm_surface_tension")
 
+    def surface_tension_body_force(self, phi, sigma: float, normal_outer=None, surface_force_outer=None):
+        """body_force += surface tension / rho in ONE launch, no intermediate fields (bit-identical to surface_tension(apply=True))."""
+        self._check(self.lib.lbm_surface_tension_body_force(self._ctx, _ptr(phi), _ptr(self.rho), _ptr(self.flags), _ptr(normal_outer),
+                                                            _ptr(surface_force_outer), _ptr(self.body_force), float(sigma), self.stream),
+                    "lbm_surface_tension_body_force")
+
     def apply_surface_tension(self, surface_force):
         self._check(self.lib.lbm_apply_surface_tension(self._ctx, _ptr(surface_force), _ptr(self.rho), _ptr(self.flags), _ptr(self.body_force),
                                                        self.stream), "lbm_apply_surface_tension")

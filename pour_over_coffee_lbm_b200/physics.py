@@ -549,8 +549,15 @@ class MultiphaseFlow3D:
     (2 launches for 4 kernels), lbm_density_from_phase, lbm_chemical_potential.  The live `step()` of the reference is
     the second definition (:389-407); the Cahn-Hilliard `step()` at :246-270 is shadowed by it and never runs."""
 
-    def __init__(self, lbm_solver: Any):
+    def __init__(self, lbm_solver: Any, lazy_fields: bool = False):
+        """lazy_fields = False: every call materialises grad_phi / normal / curvature / surface_force exactly when the reference
+        does.  lazy_fields = True: the hot calls (accumulate_surface_tension_pre_collision, step) only update body_force -- one
+        launch that touches the interface band, bit-identical body_force -- and the four diagnostic fields are computed when
+        somebody reads them, from the phase field as it is at that moment (after a step() the reference's copies still
+        reflect phi before the step's update)."""
         self.lbm = lbm_solver
+        self.lazy_fields = bool(lazy_fields)
+        self._stale = False
         e = lbm_solver.engine
         cfg = lbm_solver.config
         if e.zghost:
@@ -562,10 +569,12 @@ class MultiphaseFlow3D:
         self._phi, self._phi_new, self._mu, self._curv, self._lap = sc(), sc(), sc(), sc(), sc()
         self._normal, self._grad_phi, self._grad_mu, self._sf = vc(), vc(), vc(), vc()
         self.phi = ScalarField(lambda: self._phi); self.phi_new = ScalarField(lambda: self._phi_new)
-        self.mu = ScalarField(lambda: self._mu); self.curvature = ScalarField(lambda: self._curv)
+        self.mu = ScalarField(lambda: self._mu)
         self.laplacian_phi = ScalarField(lambda: self._lap)
-        self.normal = VectorField(lambda: self._normal); self.grad_phi = VectorField(lambda: self._grad_phi)
-        self.grad_mu = VectorField(lambda: self._grad_mu); self.surface_force = VectorField(lambda: self._sf)
+        fresh = self._fresh
+        self.curvature = ScalarField(lambda: fresh(self._curv))
+        self.normal = VectorField(lambda: fresh(self._normal)); self.grad_phi = VectorField(lambda: fresh(self._grad_phi))
+        self.grad_mu = VectorField(lambda: fresh(self._grad_mu)); self.surface_force = VectorField(lambda: fresh(self._sf))
         # multiphase_3d.py:40-47
         self.INTERFACE_WIDTH = 2.0
         self.MOBILITY = 0.001
@@ -578,6 +587,19 @@ class MultiphaseFlow3D:
         self.lbm._sync_flags()
         return self.lbm.engine
 
+    def _fresh(self, tensor):
+        """Field access: materialise the diagnostic fields first if a lazy call skipped them."""
+        if self._stale:
+            self._surface_tension_fields(False)
+        return tensor
+
+    def _surface_tension_to_body_force(self) -> None:
+        if self.lazy_fields:
+            self._ready().surface_tension_body_force(self._phi, self.SURFACE_TENSION_COEFF, self._normal, self._sf)
+            self._stale = True
+        else:
+            self._surface_tension_fields(True)
+
     # ---- kernels of the reference, same names ----------------------------------------------------------------
     def init_phase_field(self) -> None:
         """multiphase_3d.py:55-78: a dry dripper, phi = -1 everywhere."""
@@ -589,6 +611,7 @@ class MultiphaseFlow3D:
         self._ready().chemical_potential(self._phi, self._lap, self._mu, kappa)
 
     def _surface_tension_fields(self, apply: bool) -> None:
+        self._stale = False
         self._ready().surface_tension(self._phi, self._mu, self._grad_phi, self._grad_mu, self._normal, self._curv, self._sf,
                                       self.SURFACE_TENSION_COEFF, apply=apply)
 
@@ -601,11 +624,11 @@ class MultiphaseFlow3D:
 
     def apply_surface_tension(self) -> None:
         """multiphase_3d.py:354-363."""
-        self._ready().apply_surface_tension(self._sf)
+        self._ready().apply_surface_tension(self._fresh(self._sf))
 
     def accumulate_surface_tension_pre_collision(self) -> None:
         """multiphase_3d.py:409-418."""
-        self._surface_tension_fields(True)
+        self._surface_tension_to_body_force()
 
     def update_density_from_phase(self) -> None:
         """multiphase_3d.py:365-381."""
@@ -618,7 +641,12 @@ class MultiphaseFlow3D:
     def step(self, step_count: int = 0, precollision_applied: bool = False) -> None:
         """multiphase_3d.py:389-407."""
         cfg = self.lbm.config
-        self._surface_tension_fields((not precollision_applied) and step_count > 10)
+        if (not precollision_applied) and step_count > 10:
+            self._surface_tension_to_body_force()
+        elif self.lazy_fields:
+            self._ready(); self._stale = True          # the three field kernels of :396-398 are deferred until somebody reads them
+        else:
+            self._surface_tension_fields(False)
         self.lbm.engine.phase_field_step(self._phi, self._phi_new, self._mu, self.MOBILITY, cfg.DT, cfg.RHO_WATER, cfg.RHO_AIR)
 
     # ---- initial state (multiphase_3d.py:420-579) --------------------------------------------------------------
@@ -646,7 +674,7 @@ class MultiphaseFlow3D:
         cfg = self.lbm.config
         phi = self._phi
         interface = phi.abs() < 0.9
-        gmag = torch.linalg.vector_norm(self._grad_phi, dim=0)
+        gmag = torch.linalg.vector_norm(self._fresh(self._grad_phi), dim=0)
         thick = (1.0 / (gmag + 1e-10))[interface]
         return {"interface_volume": float(interface.sum().item()) * cfg.SCALE_LENGTH ** 3,
                 "water_fraction": float((phi > 0).sum().item()) / phi.numel(),

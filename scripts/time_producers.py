@@ -56,6 +56,8 @@ parts = {
         (lambda: eng.surface_tension(phi, mu, grad_phi, grad_mu, normal, curv, sf, sigma, apply=True), 117 * cells),
     "lbm_surface_tension (no mu / grad_mu)":
         (lambda: eng.surface_tension(phi, None, grad_phi, None, normal, curv, sf, sigma, apply=True), 101 * cells),
+    "lbm_surface_tension_body_force (one launch, interface band only, no intermediate fields)":
+        (lambda: eng.surface_tension_body_force(phi, sigma, normal, sf), 5 * cells),
     "lbm_apply_surface_tension": (lambda: eng.apply_surface_tension(sf), 41 * cells),
     "lbm_phase_field_step": (lambda: eng.phase_field_step(phi, phi_new, mu, 0.001, 1.0, cfg.RHO_WATER, cfg.RHO_AIR), 40 * cells),
     "lbm_density_from_phase": (lambda: eng.density_from_phase(phi, cfg.RHO_WATER, cfg.RHO_AIR), 12 * cells),

@@ -59,6 +59,12 @@ int emu_surface_tension(int vec, int nx, int ny, int nz, const float *phi, const
     RUN_CELLS(mp_curvature_force_kernel, vec, G, phi, rho, flags, grad_phi, normal, curvature, surface_force, body_force, sigma);
     return 0;
 }
+int emu_surface_tension_lean(int vec, int nx, int ny, int nz, const float *phi, const float *rho, const uint8_t *flags, const float *normal_outer,
+                             const float *force_outer, float *body_force, float sigma) {
+    const Grid G = make_grid(nx, ny, nz);
+    RUN_CELLS(mp_surface_tension_lean_kernel, vec, G, phi, rho, flags, normal_outer, force_outer, body_force, sigma);
+    return 0;
+}
 int emu_apply_surface_tension(int vec, int nx, int ny, int nz, const float *surface_force, const float *rho, const uint8_t *flags, float *body_force) {
     const Grid G = make_grid(nx, ny, nz);
     RUN_CELLS(mp_apply_surface_tension_kernel, vec, G, surface_force, rho, flags, body_force);

@@ -369,3 +369,28 @@ def test_gpu_multiphase_kernels_on_a_non_cubic_box_match_the_oracle(nx):
     assert np.array_equal(H.from_dev_vec(eng.body_force), bf) and np.array_equal(H.from_dev_vec(d_sf), m.surface_force)
     assert np.array_equal(H.from_dev_scalar(d_curv), m.curvature) and np.array_equal(H.from_dev_vec(d_n), m.normal)
     assert np.array_equal(H.from_dev_vec(d_g), m.grad_phi) and np.array_equal(H.from_dev_vec(d_gm), m.grad_mu)
+
+
+@pytest.mark.gpu
+def test_gpu_lazy_fields_same_body_force_in_one_launch(z):
+    """MultiphaseFlow3D(lazy_fields=True): lbm_surface_tension_body_force (one launch over the interface band, no intermediate
+    fields) gives the recorded body_force bit for bit; the diagnostic fields appear, exact, when they are read."""
+    from pour_over_coffee_lbm_b200.physics import MultiphaseFlow3D
+    s, _ = _solver(z)
+    mp = MultiphaseFlow3D(s, lazy_fields=True)
+    mp.phi.from_numpy(z["phi"]); mp.phi_new.from_numpy(z["phi_new_in"])
+    mp.compute_chemical_potential()
+    launches = s.engine.launch_count()
+    mp.accumulate_surface_tension_pre_collision()
+    assert s.engine.launch_count() - launches == 1
+    assert np.array_equal(s.body_force.to_numpy(), z["st_body_force"])
+    assert np.array_equal(mp.curvature.to_numpy(), z["st_curvature"]) and np.array_equal(mp.surface_force.to_numpy(), z["st_surface_force"])
+    assert np.array_equal(mp.normal.to_numpy(), z["st_normal"]) and np.array_equal(s.body_force.to_numpy(), z["st_body_force"])
+    launches = s.engine.launch_count()
+    mp.step(20, precollision_applied=True)
+    assert s.engine.launch_count() - launches == 2                  # only the phase-field update: the field kernels were deferred
+    for name, field in (("phi", mp.phi), ("phi_new", mp.phi_new), ("rho", s.rho), ("phase", s.phase), ("body_force", s.body_force)):
+        assert np.array_equal(field.to_numpy(), z["s1_" + name]), name
+    mp.step(21, precollision_applied=False)
+    for name, field in (("phi", mp.phi), ("rho", s.rho), ("phase", s.phase), ("body_force", s.body_force)):
+        assert np.array_equal(field.to_numpy(), z["s2_" + name]), name

@@ -60,6 +60,9 @@ def test_emulated_multiphase_kernels_reproduce_the_reference_run(emu, vec):
 
     def chain(body_force):
         emu.emu_surface_tension(*dims, _p(phi), _p(mu), _p(rho), _p(flags), _p(gphi), _p(gmu), _p(nrm), _p(curv), _p(sf), _p(body_force), _f(sigma))
+    bf_lean = H.to_dev_vec(z["body_force"])                             # the field-free kernel: body_force only, same bits
+    emu.emu_surface_tension_lean(*dims, _p(phi), _p(rho), _p(flags), None, None, _p(bf_lean), _f(sigma))
+    assert np.array_equal(bf_lean, H.to_dev_vec(z["st_body_force"]))
     chain(bf)
     for name, got in (("grad_phi", gphi), ("grad_mu", gmu), ("normal", nrm), ("surface_force", sf), ("body_force", bf)):
         assert np.array_equal(got, H.to_dev_vec(z["st_" + name])), name
@@ -151,20 +154,25 @@ def test_emulated_vec4_equals_vec1_on_a_non_cubic_box(emu):
     rho = (1 + 0.1 * rng.standard_normal(sh)).astype(np.float32); rho[3, 4, 2] = 0.0
     bf0 = (1e-3 * rng.standard_normal(sh + (3,))).astype(np.float32); sf0 = (1e-3 * rng.standard_normal(sh + (3,))).astype(np.float32)
     solid = (rng.random(sh) < 0.4).astype(np.uint8)
+    nrm0 = rng.normal(0, 0.5, sh + (3,)).astype(np.float32)              # what the never-written outer layer of `normal` holds
     outs = []
     for vec in (4, 1):
         dims = (C.c_int(vec), C.c_int(nx), C.c_int(ny), C.c_int(nz))
         d_phi, d_new, d_mu, d_u = H.to_dev_scalar(phi), H.to_dev_scalar(phi_new0), H.to_dev_scalar(mu0), H.to_dev_vec(u)
         d_rho, d_bf, d_sf, d_flags = H.to_dev_scalar(rho), H.to_dev_vec(bf0), H.to_dev_vec(sf0), H.to_dev_scalar(solid)
         d_phase = np.zeros_like(d_rho); d_curv = np.zeros_like(d_rho)
-        d_g, d_gm, d_n = np.zeros_like(d_bf), np.zeros_like(d_bf), np.zeros_like(d_bf)
+        d_g, d_gm, d_n = np.zeros_like(d_bf), np.zeros_like(d_bf), H.to_dev_vec(nrm0)
+        d_bf_lean = H.to_dev_vec(bf0)
+        emu.emu_surface_tension_lean(*dims, _p(d_phi), _p(d_rho), _p(d_flags), _p(H.to_dev_vec(nrm0)), _p(H.to_dev_vec(sf0)), _p(d_bf_lean), _f(0.05))
         emu.emu_surface_tension(*dims, _p(d_phi), _p(d_mu), _p(d_rho), _p(d_flags), _p(d_g), _p(d_gm), _p(d_n), _p(d_curv), _p(d_sf), _p(d_bf), _f(0.05))
+        assert np.array_equal(d_bf_lean, d_bf)
         emu.emu_phase_field_step(*dims, _p(d_phi), _p(d_new), _p(d_mu), _p(d_u), _p(d_rho), _p(d_phase), _f(0.001), _f(1.0), C.c_double(1.0),
                                  C.c_double(0.00125))
         outs.append([a.copy() for a in (d_phi, d_new, d_rho, d_phase, d_bf, d_sf, d_curv, d_g, d_gm, d_n)])
     for a, b in zip(*outs):
         assert np.array_equal(a, b)
     m = P.MultiphaseState(sh); m.phi = phi.copy(); m.phi_new = phi_new0.copy(); m.mu = mu0.copy(); m.surface_force = sf0.copy()
+    m.normal = nrm0.copy()
     bf = bf0.copy(); r = rho.copy(); ph = np.zeros_like(r)
     P.accumulate_surface_tension_pre_collision(m, r, solid, bf, 0.05)
     P.update_phase_field_cahn_hilliard(m, u, 0.001, 1.0); P.apply_phase_separation(m, 1.0); m.phi[...] = m.phi_new
