@@ -16,6 +16,7 @@ static EmuIdx emu_block_idx, emu_thread_idx, emu_block_dim;
 #define blockDim emu_block_dim
 static inline float atomicAdd(float *p, float v) { const float o = *p; *p = o + v; return o; }
 
+#define __launch_bounds__(...)
 #define LBM_EMULATE_ON_HOST 1
 #include "../../pour_over_coffee_lbm_b200/csrc/lbm_producers.cu"
 
@@ -84,12 +85,14 @@ int emu_density_from_phase(int vec, int nx, int ny, int nz, const float *phi, fl
 }
 int emu_dynamic_resistance(int cells, int nx, int ny, int nz, const uint8_t *flags, float *blockage, float *accumulated) {
     const Grid G = make_grid(nx, ny, nz);
-    const int t = (nx + cells - 1) / cells, b = 32;
-    const dim3 grid((unsigned)((t + b - 1) / b), (unsigned)ny, (unsigned)nz);
-    if (cells == 16) run(grid, b, [&] { dynamic_resistance_kernel<16>(G, flags, blockage, accumulated); });
-    else if (cells == 4) run(grid, b, [&] { dynamic_resistance_kernel<4>(G, flags, blockage, accumulated); });
-    else run(grid, b, [&] { dynamic_resistance_kernel<1>(G, flags, blockage, accumulated); });
-    return 0;
+    const long long begin = (long long)G.zg * G.plane, count = (long long)G.nz * G.plane;
+    if (cells == 0) cells = dynamic_resistance_cells(begin, count, flags, false);      // what the launcher would pick
+    const long long threads = (count + cells - 1) / cells;
+    const dim3 grid((unsigned)((threads + 255) / 256), 1, 1);
+    if (cells == 16) run(grid, 256, [&] { dynamic_resistance_kernel<16>(begin, count, flags, blockage, accumulated); });
+    else if (cells == 4) run(grid, 256, [&] { dynamic_resistance_kernel<4>(begin, count, flags, blockage, accumulated); });
+    else run(grid, 256, [&] { dynamic_resistance_kernel<1>(begin, count, flags, blockage, accumulated); });
+    return cells;
 }
 int emu_particles_block_at_filter(int nx, int ny, int nz, int n, float *pos, float *vel, int32_t *active, const uint8_t *flags, float *accumulated,
                                   float scale_length, float noise, unsigned seed) {
