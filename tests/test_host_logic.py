@@ -131,3 +131,48 @@ def test_facade_classes_cover_the_recorded_reference_api_surface():
         missing = [m for m in ref[key] if m not in skip.get(key, set()) and not hasattr(cls, m)]
         assert not missing, (key, missing)
 
+
+
+def test_multiphase_facade_call_sequence_and_lazy_fields():
+    """MultiphaseFlow3D's host logic on a stub engine (CPU tensors, recorded calls): the exact mode issues the reference's
+    kernels where the reference does; lazy_fields=True issues the one-launch body-force kernel in the hot calls and
+    materialises the diagnostic fields on first read."""
+    import torch
+    from pour_over_coffee_lbm_b200.config import LBMConfig
+    from pour_over_coffee_lbm_b200.physics import MultiphaseFlow3D
+
+    class Engine:
+        zghost = 0
+        def __init__(self):
+            self.rho = torch.ones(4, 4, 4); self.body_force = torch.zeros(3, 4, 4, 4); self.phase = torch.zeros(4, 4, 4)
+            self.flags = torch.zeros(4, 4, 4, dtype=torch.uint8); self.solid = torch.zeros(4, 4, 4, dtype=torch.uint8)
+            self.calls = []
+        def surface_tension(self, *a, apply=True, **k): self.calls.append(("fields", apply))
+        def surface_tension_body_force(self, *a, **k): self.calls.append(("body_force_only",))
+        def apply_surface_tension(self, sf): self.calls.append(("apply",))
+        def phase_field_step(self, *a, **k): self.calls.append(("phase_step",))
+        def density_from_phase(self, *a, **k): self.calls.append(("density",))
+        def chemical_potential(self, *a, **k): self.calls.append(("mu",))
+
+    class Solver:
+        def __init__(self):
+            self.engine = Engine(); self.config = LBMConfig(NX=4, NY=4, NZ=4); self.synced = 0
+        def _sync_flags(self): self.synced += 1
+
+    s = Solver(); mp = MultiphaseFlow3D(s)                       # exact mode: the reference's kernel sequence
+    mp.accumulate_surface_tension_pre_collision(); mp.step(5, precollision_applied=True); mp.step(20, precollision_applied=False)
+    mp.step(5, precollision_applied=False)                       # step_count <= 10: no force yet (multiphase_3d.py:401)
+    assert s.engine.calls == [("fields", True), ("fields", False), ("phase_step",), ("fields", True), ("phase_step",),
+                              ("fields", False), ("phase_step",)]
+    assert s.synced >= 4                                          # flags are re-packed (if dirty) before every launch that reads them
+    s = Solver(); mp = MultiphaseFlow3D(s, lazy_fields=True)
+    mp.accumulate_surface_tension_pre_collision(); mp.step(11, precollision_applied=True)
+    assert s.engine.calls == [("body_force_only",), ("phase_step",)]
+    mp.curvature.to_numpy(); mp.normal.to_numpy()                 # first read materialises once
+    assert s.engine.calls[2:] == [("fields", False)]
+    mp.step(12, precollision_applied=False); mp.apply_surface_tension()
+    assert s.engine.calls[3:] == [("body_force_only",), ("phase_step",), ("fields", False), ("apply",)]
+    mp.standardize_initial_state(force_dry_state=True)
+    assert s.engine.calls[7:] == [("density",), ("mu",), ("fields", False)] and float(mp.phi.to_numpy().max()) == -1.0
+    with pytest.raises(NotImplementedError):
+        s.engine.zghost = 1; MultiphaseFlow3D(s)
