@@ -394,3 +394,35 @@ def test_gpu_lazy_fields_same_body_force_in_one_launch(z):
     mp.step(21, precollision_applied=False)
     for name, field in (("phi", mp.phi), ("rho", s.rho), ("phase", s.phase), ("body_force", s.body_force)):
         assert np.array_equal(field.to_numpy(), z["s2_" + name]), name
+
+
+@pytest.mark.gpu
+def test_gpu_one_launch_surface_tension_equals_the_chain_at_scale():
+    """Size-independent property at 128^3 with the V60 mask: body_force from lbm_surface_tension_body_force (one launch, interface
+    band only) is bit-identical to the four-kernel chain's, for a wavy noisy interface that crosses the cone."""
+    import torch
+    from pour_over_coffee_lbm_b200.physics import FilterPaperSystem
+    from pour_over_coffee_lbm_b200.solver import LBMSolver
+    n = 128
+    s = LBMSolver(nx=n, ny=n, nz=n, compat="reference", strict=True); s.init_fields()
+    FilterPaperSystem(s).initialize_filter_geometry()
+    e = s.engine
+    g = torch.Generator(device="cuda"); g.manual_seed(11)
+    zc = torch.arange(n, device="cuda", dtype=torch.float32)[:, None, None]
+    xc = torch.arange(n, device="cuda", dtype=torch.float32)[None, None, :]
+    phi = torch.tanh((0.5 * n + 4.0 * torch.sin(0.2 * xc) - zc) / 2.0).expand(n, n, n).contiguous()
+    phi = (phi + 0.02 * torch.randn((n, n, n), device="cuda", generator=g)).clamp_(-1.0, 1.0)
+    e.rho.copy_(1.0 + 0.05 * torch.randn((n, n, n), device="cuda", generator=g))
+    bf0 = 1e-4 * torch.randn((3, n, n, n), device="cuda", generator=g)
+    sc = lambda: torch.zeros_like(e.rho)
+    vc = lambda: torch.zeros_like(e.body_force)
+    gphi, nrm, sf, curv = vc(), vc(), vc(), sc()
+    e.body_force.copy_(bf0)
+    e.surface_tension(phi, None, gphi, None, nrm, curv, sf, 0.05, apply=True)
+    chain = e.body_force.clone()
+    e.body_force.copy_(bf0)
+    e.surface_tension_body_force(phi, 0.05)
+    assert torch.equal(e.body_force, chain)
+    changed = int((chain != bf0).any(0).sum())
+    assert changed > 10_000 and changed < 0.2 * n ** 3              # the band is thin: most of the box is never touched
+    assert float(curv.abs().max()) > 0 and torch.isfinite(chain).all()
