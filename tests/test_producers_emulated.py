@@ -181,3 +181,28 @@ def test_emulated_vec4_equals_vec1_on_a_non_cubic_box(emu):
     assert np.array_equal(got[0], H.to_dev_scalar(m.phi)) and np.array_equal(got[2], H.to_dev_scalar(r)) and np.array_equal(got[3], H.to_dev_scalar(ph))
     assert np.array_equal(got[4], H.to_dev_vec(bf)) and np.array_equal(got[5], H.to_dev_vec(m.surface_force))
     assert np.array_equal(got[6], H.to_dev_scalar(m.curvature)) and np.array_equal(got[9], H.to_dev_vec(m.normal))
+
+
+def test_emulated_one_launch_surface_tension_equals_the_chain_on_a_v60_box(emu):
+    """48^3 with the V60 mask and a wavy, noisy interface through the cone: the one-launch kernel's body_force is bit-identical
+    to the four-kernel chain's, and only the interface band is touched."""
+    from oracle import d3q19_ref as R
+    n = 48
+    solid = R.v60_solid(R.RefConfig(NX=n, NY=n, NZ=n))
+    rng = np.random.default_rng(11)
+    x = np.arange(n, dtype=np.float32)
+    X, Y, Z = np.meshgrid(x, x, x, indexing="ij")
+    phi = np.tanh((0.5 * n + 3.0 * np.sin(0.3 * X) + 2.0 * np.cos(0.25 * Y) - Z) / 2.0) + 0.02 * rng.standard_normal((n, n, n))
+    phi = np.clip(phi, -1, 1).astype(np.float32)
+    rho = (1 + 0.05 * rng.standard_normal((n, n, n))).astype(np.float32)
+    bf0 = (1e-4 * rng.standard_normal((n, n, n, 3))).astype(np.float32)
+    dims = (C.c_int(4), C.c_int(n), C.c_int(n), C.c_int(n))
+    d_phi, d_rho, d_flags = H.to_dev_scalar(phi), H.to_dev_scalar(rho), H.to_dev_scalar(solid).astype(np.uint8)
+    chain, lean = H.to_dev_vec(bf0), H.to_dev_vec(bf0)
+    z3 = lambda: np.zeros_like(chain)
+    emu.emu_surface_tension(*dims, _p(d_phi), None, _p(d_rho), _p(d_flags), _p(z3()), None, _p(z3()), _p(np.zeros_like(d_rho)), _p(z3()), _p(chain),
+                            _f(0.05))
+    emu.emu_surface_tension_lean(*dims, _p(d_phi), _p(d_rho), _p(d_flags), None, None, _p(lean), _f(0.05))
+    assert np.array_equal(chain, lean)
+    changed = (chain != H.to_dev_vec(bf0)).any(0).sum()
+    assert 500 < changed < 0.2 * n ** 3
