@@ -145,11 +145,13 @@ __global__ void particles_under_relax_kernel(lbm_particles P, float relax) {
     }
 }
 
+#ifndef LBM_EMULATE_ON_HOST      /* tests/emu compiles the kernels with g++ and runs them thread by thread */
 cudaError_t launch_particles_under_relax(const lbm_particles &ps, float relax, cudaStream_t s) {
     const int b = 256, gr = (ps.n + b - 1) / b;
     if (ps.n > 0) particles_under_relax_kernel<<<gr, b, 0, s>>>(ps, relax);
     return cudaGetLastError();
 }
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // CoffeeParticleSystem.update_particle_physics (coffee_particles.py:641-720) with its helpers validate_coordinate
@@ -320,6 +322,7 @@ __global__ void __launch_bounds__(256) particles_fluid_forces_kernel(Grid G, con
     else { force[p] = gm * 0.0f; force[n + p] = gm * 0.0f; force[2 * n + p] = -gm; }
 }
 
+#ifndef LBM_EMULATE_ON_HOST      /* tests/emu compiles the kernels with g++ and runs them thread by thread */
 cudaError_t launch_particles_fluid_forces(const Grid &G, const float *u, const lbm_particles &ps, float *force, float rho_w, float mu_safe,
                                           float gravity, float vol_k, float max_coord, int *counters, cudaStream_t s) {
     if (ps.n <= 0) return cudaSuccess;
@@ -340,5 +343,6 @@ cudaError_t launch_particles_advance(const lbm_particles &ps, float *force, cons
     particles_advance_kernel<<<(ps.n + 255) / 256, 256, 0, s>>>(ps, force, b, dt, counters);
     return cudaGetLastError();
 }
+#endif
 
 }  // namespace lbm
