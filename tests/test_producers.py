@@ -424,5 +424,5 @@ def test_gpu_one_launch_surface_tension_equals_the_chain_at_scale():
     e.surface_tension_body_force(phi, 0.05)
     assert torch.equal(e.body_force, chain)
     changed = int((chain != bf0).any(0).sum())
-    assert changed > 10_000 and changed < 0.2 * n ** 3              # the band is thin: most of the box is never touched
+    assert 2_000 < changed < 0.2 * n ** 3                           # the band is thin: most of the box is never touched
     assert float(curv.abs().max()) > 0 and torch.isfinite(chain).all()
