@@ -185,6 +185,14 @@ int  lbm_add_reaction_force(lbm_ctx *ctx, const float *reaction, const uint8_t *
 int  lbm_surface_tension(lbm_ctx *ctx, const float *phi, const float *mu_or_null, const float *rho, const uint8_t *flags,
                          float *grad_phi, float *grad_mu_or_null, float *normal, float *curvature, float *surface_force,
                          float *body_force_or_null, float sigma, void *stream);
+/* The two launches of lbm_surface_tension as separate calls, for z-slabs: the stencils read the ghost planes of `phi`
+ * (and `mu`) in the first call and of `normal` in the second, so a slab refreshes `normal`'s ghost planes between them
+ * (slab.exchange_planes over torch.distributed / NCCL; MultiphaseFlow3D does it).  Any zghost. */
+int  lbm_surface_tension_gradients(lbm_ctx *ctx, const float *phi, const float *mu_or_null, float *grad_phi,
+                                   float *grad_mu_or_null, float *normal, void *stream);
+int  lbm_surface_tension_curvature_force(lbm_ctx *ctx, const float *phi, const float *rho, const uint8_t *flags,
+                                         const float *grad_phi, const float *normal, float *curvature, float *surface_force,
+                                         float *body_force_or_null, float sigma, void *stream);
 /* The same chain when only body_force is wanted (what main.py:795-800 needs from accumulate_surface_tension_pre_collision):
  * ONE launch, no intermediate fields.  surface_force vanishes outside the interface band |phi| < 0.9, so a thread reads its
  * cells' phi and flags and leaves unless a fluid cell is in the band; band cells rebuild their neighbours' normals from a
@@ -196,7 +204,7 @@ int  lbm_surface_tension_body_force(lbm_ctx *ctx, const float *phi, const float 
                                     float *body_force, float sigma, void *stream);
 /* MultiphaseFlow3D.compute_chemical_potential multiphase_3d.py:80-109: laplacian_phi (optional output) and
  * mu = phi^3 - phi - kappa * lap(phi) on interior cells; kappa = 3 * sigma * W / 8 folded by the caller.  The reference
- * calls it once, from standardize_initial_state :542-571.  Single slab. */
+ * calls it once, from standardize_initial_state :542-571.  On z-slabs the ghost planes of phi must be current. */
 int  lbm_chemical_potential(lbm_ctx *ctx, const float *phi, float *laplacian_phi_or_null, float *mu, float kappa, void *stream);
 /* MultiphaseFlow3D.apply_surface_tension multiphase_3d.py:354-363 alone (step() with precollision_applied = False). */
 int  lbm_apply_surface_tension(lbm_ctx *ctx, const float *surface_force, const float *rho, const uint8_t *flags,
@@ -205,7 +213,8 @@ int  lbm_apply_surface_tension(lbm_ctx *ctx, const float *surface_force, const f
  * update_phase_field_cahn_hilliard :151-197 + apply_phase_separation :334-352 (phi -> phi_new, interior cells), then
  * copy_phase_field :383-387 + update_density_from_phase :365-381 (phi = phi_new, rho, phase on every cell).
  * mu = NULL is the all-zero chemical potential the live step() leaves behind.  rho_water / rho_air are doubles because
- * the reference folds (RHO_WATER - RHO_AIR) in f64 before it meets an f32 value.  Single slab (zghost = 0). */
+ * the reference folds (RHO_WATER - RHO_AIR) in f64 before it meets an f32 value.  On z-slabs the ghost planes of phi (and
+ * mu) must be current; the owned planes are written. */
 int  lbm_phase_field_step(lbm_ctx *ctx, float *phi, float *phi_new, const float *mu_or_null, const float *u, float *rho,
                           float *phase, float mobility, float dt, double rho_water, double rho_air, void *stream);
 /* MultiphaseFlow3D.update_density_from_phase multiphase_3d.py:365-381 alone (main.py:624). */

@@ -78,6 +78,8 @@ SIGNATURES = {
     "lbm_field_statistics": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "lbm_add_reaction_force": (C.c_int, [_P, _P, _P, _P, _P]),
     "lbm_surface_tension": (C.c_int, [_P] * 11 + [C.c_float, _P]),
+    "lbm_surface_tension_gradients": (C.c_int, [_P] * 7),
+    "lbm_surface_tension_curvature_force": (C.c_int, [_P] * 9 + [C.c_float, _P]),
     "lbm_surface_tension_body_force": (C.c_int, [_P] * 7 + [C.c_float, _P]),
     "lbm_chemical_potential": (C.c_int, [_P, _P, _P, _P, C.c_float, _P]),
     "lbm_apply_surface_tension": (C.c_int, [_P, _P, _P, _P, _P, _P]),

@@ -32,7 +32,7 @@ cudaError_t launch_bounce_slots(const Grid &, float *, const uint8_t *, const un
 cudaError_t launch_particles_couple(const Grid &, const float *, float *, const lbm_particles &, float, float, float, cudaStream_t);
 cudaError_t launch_particles_under_relax(const lbm_particles &, float, cudaStream_t);
 cudaError_t launch_particles_advance(const lbm_particles &, float *, const lbm_particle_bounds &, float, int *, cudaStream_t);
-cudaError_t launch_surface_tension(const Grid &, const float *, const float *, const float *, const uint8_t *, float *, float *, float *, float *,
+cudaError_t launch_surface_tension(const Grid &, int, const float *, const float *, const float *, const uint8_t *, float *, float *, float *, float *,
                                    float *, float *, float, cudaStream_t);
 cudaError_t launch_apply_surface_tension(const Grid &, const float *, const float *, const uint8_t *, float *, cudaStream_t);
 cudaError_t launch_surface_tension_lean(const Grid &, const float *, const float *, const uint8_t *, const float *, const float *, float *, float,
@@ -695,10 +695,28 @@ int lbm_surface_tension(lbm_ctx *ctx, const float *phi, const float *mu, const f
                         float *normal, float *curvature, float *surface_force, float *body_force, float sigma, void *stream) {
     if (!ctx || !phi || !grad_phi || !normal || !curvature || !surface_force) return fail(ctx, "null argument");
     if (body_force && (!rho || !flags)) return fail(ctx, "lbm_surface_tension: body_force needs rho and flags");
-    if (single_slab_only(ctx, "lbm_surface_tension")) return 1;
-    CUDA_OK(ctx, launch_surface_tension(ctx->g, phi, mu, rho, flags, grad_phi, grad_mu, normal, curvature, surface_force, body_force, sigma,
+    if (single_slab_only(ctx, "lbm_surface_tension (use the _gradients / _curvature_force pair with a ghost-plane refresh of `normal` between them)")) return 1;
+    CUDA_OK(ctx, launch_surface_tension(ctx->g, 3, phi, mu, rho, flags, grad_phi, grad_mu, normal, curvature, surface_force, body_force, sigma,
                                         (cudaStream_t)stream));
     ctx->launches += 2;
+    return 0;
+}
+
+int lbm_surface_tension_gradients(lbm_ctx *ctx, const float *phi, const float *mu, float *grad_phi, float *grad_mu, float *normal, void *stream) {
+    if (!ctx || !phi || !grad_phi || !normal) return fail(ctx, "null argument");
+    CUDA_OK(ctx, launch_surface_tension(ctx->g, 1, phi, mu, nullptr, nullptr, grad_phi, grad_mu, normal, nullptr, nullptr, nullptr, 0.0f,
+                                        (cudaStream_t)stream));
+    ctx->launches++;
+    return 0;
+}
+
+int lbm_surface_tension_curvature_force(lbm_ctx *ctx, const float *phi, const float *rho, const uint8_t *flags, const float *grad_phi,
+                                        const float *normal, float *curvature, float *surface_force, float *body_force, float sigma, void *stream) {
+    if (!ctx || !phi || !grad_phi || !normal || !curvature || !surface_force) return fail(ctx, "null argument");
+    if (body_force && (!rho || !flags)) return fail(ctx, "lbm_surface_tension_curvature_force: body_force needs rho and flags");
+    CUDA_OK(ctx, launch_surface_tension(ctx->g, 2, phi, nullptr, rho, flags, const_cast<float *>(grad_phi), nullptr, const_cast<float *>(normal),
+                                        curvature, surface_force, body_force, sigma, (cudaStream_t)stream));
+    ctx->launches++;
     return 0;
 }
 
@@ -713,7 +731,6 @@ int lbm_surface_tension_body_force(lbm_ctx *ctx, const float *phi, const float *
 
 int lbm_chemical_potential(lbm_ctx *ctx, const float *phi, float *laplacian_phi, float *mu, float kappa, void *stream) {
     if (!ctx || !phi || !mu) return fail(ctx, "null argument");
-    if (single_slab_only(ctx, "lbm_chemical_potential")) return 1;
     CUDA_OK(ctx, launch_chemical_potential(ctx->g, phi, laplacian_phi, mu, kappa, (cudaStream_t)stream));
     ctx->launches++;
     return 0;
@@ -730,7 +747,6 @@ int lbm_phase_field_step(lbm_ctx *ctx, float *phi, float *phi_new, const float *
                          float dt, double rho_water, double rho_air, void *stream) {
     if (!ctx || !phi || !phi_new || !u || !rho || !phase) return fail(ctx, "null argument");
     if (phi == phi_new) return fail(ctx, "lbm_phase_field_step: phi and phi_new must be distinct buffers");
-    if (single_slab_only(ctx, "lbm_phase_field_step")) return 1;
     CUDA_OK(ctx, launch_phase_field_step(ctx->g, phi, phi_new, mu, u, rho, phase, mobility, dt, (float)rho_air, (float)(rho_water - rho_air),
                                          (cudaStream_t)stream));
     ctx->launches += 2;

@@ -542,13 +542,15 @@ cudaError_t launch_chemical_potential(const Grid &G, const float *phi, float *la
     LAUNCH_CELLS(mp_chemical_potential_kernel, vec, s, G, phi, laplacian, mu, kappa);
     return cudaGetLastError();
 }
-cudaError_t launch_surface_tension(const Grid &G, const float *phi, const float *mu, const float *rho, const uint8_t *flags, float *grad_phi,
-                                   float *grad_mu, float *normal, float *curvature, float *surface_force, float *body_force, float sigma,
-                                   cudaStream_t s) {
+// stage bit 0: compute_gradients, bit 1: curvature + force + apply.  On z-slabs the caller refreshes the ghost planes of
+// `normal` between the two stages (the curvature stencil reads n_z at k -+ 1).
+cudaError_t launch_surface_tension(const Grid &G, int stages, const float *phi, const float *mu, const float *rho, const uint8_t *flags,
+                                   float *grad_phi, float *grad_mu, float *normal, float *curvature, float *surface_force, float *body_force,
+                                   float sigma, cudaStream_t s) {
     if (!grid_ok(G)) return cudaErrorInvalidValue;
     const int vec = pick_vec(G, aligned16(phi, mu, rho, grad_phi, grad_mu, normal, curvature, surface_force, body_force) && ((uintptr_t)flags & 3u) == 0);
-    LAUNCH_CELLS(mp_gradients_kernel, vec, s, G, phi, mu, grad_phi, grad_mu, normal);
-    LAUNCH_CELLS(mp_curvature_force_kernel, vec, s, G, phi, rho, flags, grad_phi, normal, curvature, surface_force, body_force, sigma);
+    if (stages & 1) LAUNCH_CELLS(mp_gradients_kernel, vec, s, G, phi, mu, grad_phi, grad_mu, normal);
+    if (stages & 2) LAUNCH_CELLS(mp_curvature_force_kernel, vec, s, G, phi, rho, flags, grad_phi, normal, curvature, surface_force, body_force, sigma);
     return cudaGetLastError();
 }
 cudaError_t launch_surface_tension_lean(const Grid &G, const float *phi, const float *rho, const uint8_t *flags, const float *normal_outer,

@@ -316,6 +316,17 @@ class D3Q19Engine:
                                                  _ptr(normal), _ptr(curvature), _ptr(surface_force),
                                                  _ptr(self.body_force) if apply else None, float(sigma), self.stream), "lbm_surface_tension")
 
+    def surface_tension_gradients(self, phi, mu, grad_phi, grad_mu, normal):
+        """First launch of the chain (any zghost): compute_gradients."""
+        self._check(self.lib.lbm_surface_tension_gradients(self._ctx, _ptr(phi), _ptr(mu), _ptr(grad_phi), _ptr(grad_mu), _ptr(normal), self.stream),
+                    "lbm_surface_tension_gradients")
+
+    def surface_tension_curvature_force(self, phi, grad_phi, normal, curvature, surface_force, sigma: float, apply: bool = True):
+        """Second launch of the chain (any zghost; `normal`'s ghost planes must be current): curvature, force, body_force."""
+        self._check(self.lib.lbm_surface_tension_curvature_force(self._ctx, _ptr(phi), _ptr(self.rho), _ptr(self.flags), _ptr(grad_phi), _ptr(normal),
+                                                                 _ptr(curvature), _ptr(surface_force), _ptr(self.body_force) if apply else None,
+                                                                 float(sigma), self.stream), "lbm_surface_tension_curvature_force")
+
     def surface_tension_body_force(self, phi, sigma: float, normal_outer=None, surface_force_outer=None):
         """body_force += surface tension / rho in ONE launch, no intermediate fields (bit-identical to surface_tension(apply=True))."""
         self._check(self.lib.lbm_surface_tension_body_force(self._ctx, _ptr(phi), _ptr(self.rho), _ptr(self.flags), _ptr(normal_outer),

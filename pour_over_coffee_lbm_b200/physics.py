@@ -556,25 +556,26 @@ class MultiphaseFlow3D:
         somebody reads them, from the phase field as it is at that moment (after a step() the reference's copies still
         reflect phi before the step's update)."""
         self.lbm = lbm_solver
-        self.lazy_fields = bool(lazy_fields)
-        self._stale = False
         e = lbm_solver.engine
         cfg = lbm_solver.config
-        if e.zghost:
-            raise NotImplementedError("MultiphaseFlow3D: single slab only (the phi / normal stencils have no halo exchange yet)")
+        # z-slabs: the chain runs as two calls with ghost-plane refreshes of phi / mu / normal (slab.exchange_planes); the
+        # one-launch kernel reaches k -+ 2 and is single-slab only
+        self.lazy_fields = bool(lazy_fields) and not e.zghost
+        self._stale = False
         if e.body_force is None or e.phase is None or e.flags is None:
             raise ValueError("MultiphaseFlow3D needs a solver with body_force, phase and a flag field (force=True, phase=True, walls=True)")
         sc = lambda: torch.zeros_like(e.rho)
         vc = lambda: torch.zeros_like(e.body_force)
         self._phi, self._phi_new, self._mu, self._curv, self._lap = sc(), sc(), sc(), sc(), sc()
         self._normal, self._grad_phi, self._grad_mu, self._sf = vc(), vc(), vc(), vc()
-        self.phi = ScalarField(lambda: self._phi); self.phi_new = ScalarField(lambda: self._phi_new)
-        self.mu = ScalarField(lambda: self._mu)
-        self.laplacian_phi = ScalarField(lambda: self._lap)
+        zg = e.zghost
+        self.phi = ScalarField(lambda: self._phi, zg); self.phi_new = ScalarField(lambda: self._phi_new, zg)
+        self.mu = ScalarField(lambda: self._mu, zg)
+        self.laplacian_phi = ScalarField(lambda: self._lap, zg)
         fresh = self._fresh
-        self.curvature = ScalarField(lambda: fresh(self._curv))
-        self.normal = VectorField(lambda: fresh(self._normal)); self.grad_phi = VectorField(lambda: fresh(self._grad_phi))
-        self.grad_mu = VectorField(lambda: fresh(self._grad_mu)); self.surface_force = VectorField(lambda: fresh(self._sf))
+        self.curvature = ScalarField(lambda: fresh(self._curv), zg)
+        self.normal = VectorField(lambda: fresh(self._normal), zg); self.grad_phi = VectorField(lambda: fresh(self._grad_phi), zg)
+        self.grad_mu = VectorField(lambda: fresh(self._grad_mu), zg); self.surface_force = VectorField(lambda: fresh(self._sf), zg)
         # multiphase_3d.py:40-47
         self.INTERFACE_WIDTH = 2.0
         self.MOBILITY = 0.001
@@ -586,6 +587,15 @@ class MultiphaseFlow3D:
     def _ready(self):
         self.lbm._sync_flags()
         return self.lbm.engine
+
+    def _ghosts(self, *tensors) -> None:
+        """z-slabs: fill the ghost planes of whole-plane fields from the neighbours (no-op on a single slab)."""
+        e = self.lbm.engine
+        if not e.zghost:
+            return
+        from . import slab
+        for t in tensors:
+            slab.exchange_planes(t, e.rank, e.nranks, e.periodic[2])
 
     def _fresh(self, tensor):
         """Field access: materialise the diagnostic fields first if a lazy call skipped them."""
@@ -608,12 +618,21 @@ class MultiphaseFlow3D:
     def compute_chemical_potential(self) -> None:
         """multiphase_3d.py:80-109."""
         kappa = 3.0 * self.SURFACE_TENSION_COEFF * self.INTERFACE_WIDTH / 8.0
+        self._ghosts(self._phi)
         self._ready().chemical_potential(self._phi, self._lap, self._mu, kappa)
+        self._ghosts(self._mu)
 
     def _surface_tension_fields(self, apply: bool) -> None:
         self._stale = False
-        self._ready().surface_tension(self._phi, self._mu, self._grad_phi, self._grad_mu, self._normal, self._curv, self._sf,
-                                      self.SURFACE_TENSION_COEFF, apply=apply)
+        e = self._ready()
+        if not e.zghost:
+            e.surface_tension(self._phi, self._mu, self._grad_phi, self._grad_mu, self._normal, self._curv, self._sf,
+                              self.SURFACE_TENSION_COEFF, apply=apply)
+            return
+        self._ghosts(self._phi)
+        e.surface_tension_gradients(self._phi, self._mu, self._grad_phi, self._grad_mu, self._normal)
+        self._ghosts(self._normal)
+        e.surface_tension_curvature_force(self._phi, self._grad_phi, self._normal, self._curv, self._sf, self.SURFACE_TENSION_COEFF, apply=apply)
 
     def compute_gradients(self) -> None:
         """multiphase_3d.py:111-132.  The device pass also refreshes curvature and surface_force (one fused chain)."""
@@ -647,6 +666,7 @@ class MultiphaseFlow3D:
             self._ready(); self._stale = True          # the three field kernels of :396-398 are deferred until somebody reads them
         else:
             self._surface_tension_fields(False)
+        self._ghosts(self._phi)
         self.lbm.engine.phase_field_step(self._phi, self._phi_new, self._mu, self.MOBILITY, cfg.DT, cfg.RHO_WATER, cfg.RHO_AIR)
 
     # ---- initial state (multiphase_3d.py:420-579) --------------------------------------------------------------

@@ -132,6 +132,34 @@ def exchange_halo(g: torch.Tensor, rank: int, world: int, periodic_z: bool, grou
         else: vec3[:, 0].copy_(buf)
 
 
+def exchange_planes(field: torch.Tensor, rank: int, world: int, periodic_z: bool, group=None) -> None:
+    """Fill the two ghost planes of a scalar [nz+2, ny, nx] or vector [C, nz+2, ny, nx] field from the z neighbours' boundary
+    planes (whole planes: phi, mu, normal of the multiphase producers -- their 7-point stencils read k -+ 1).  torch.distributed
+    point-to-point: NCCL on device tensors, gloo on the CPU tests.  A slab at a non-periodic end keeps its outer ghost plane."""
+    import torch.distributed as dist
+    zdim = field.dim() - 3
+    nzp = field.shape[zdim]
+    plane = lambda k: field.select(zdim, k)
+    down, up = neighbours(rank, world, periodic_z)
+    if world == 1:
+        if periodic_z:
+            plane(0).copy_(plane(nzp - 2)); plane(nzp - 1).copy_(plane(1))
+        return
+    ops, bufs = [], []
+    for peer, send_k, recv_k in ((up, nzp - 2, nzp - 1), (down, 1, 0)):
+        if peer is None:
+            continue
+        send = plane(send_k).contiguous(); recv = torch.empty_like(send)
+        ops += [dist.P2POp(dist.isend, send, peer, group), dist.P2POp(dist.irecv, recv, peer, group)]
+        bufs.append((recv_k, recv))
+    if world == 2 and periodic_z and rank == 1:
+        ops = [ops[i] for i in _swap_pairs(len(ops))]
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    for k, buf in bufs:
+        plane(k).copy_(buf)
+
+
 def _swap_pairs(n: int) -> List[int]:
     """rank 1 of a 2-rank periodic ring posts its (send,recv) pairs in the opposite neighbour order so that
     message k of rank 0 meets message k of rank 1."""

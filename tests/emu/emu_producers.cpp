@@ -34,10 +34,10 @@ static void run(dim3 grid, unsigned block, F &&kernel) {
                     kernel();
                 }
 }
-static Grid make_grid(int nx, int ny, int nz) {
+static Grid make_grid(int nx, int ny, int nz, int zg = 0, int z0 = 0, int nz_global = 0) {
     Grid G{};
-    G.nx = nx; G.ny = ny; G.nz = nz; G.zg = 0; G.nz_global = nz; G.z0 = 0;
-    G.plane = (long long)nx * ny; G.vol = G.plane * nz;
+    G.nx = nx; G.ny = ny; G.nz = nz; G.zg = zg; G.nz_global = nz_global > 0 ? nz_global : nz; G.z0 = z0;
+    G.plane = (long long)nx * ny; G.vol = G.plane * (nz + 2 * zg);
     return G;
 }
 #define RUN_CELLS(kernel, vec, ...)                                                                          \
@@ -58,6 +58,26 @@ int emu_surface_tension(int vec, int nx, int ny, int nz, const float *phi, const
     const Grid G = make_grid(nx, ny, nz);
     RUN_CELLS(mp_gradients_kernel, vec, G, phi, mu, grad_phi, grad_mu, normal);
     RUN_CELLS(mp_curvature_force_kernel, vec, G, phi, rho, flags, grad_phi, normal, curvature, surface_force, body_force, sigma);
+    return 0;
+}
+// z-slab variants: nz owned planes starting at global plane z0, one ghost plane per side (fields are [nz + 2][ny][nx])
+int emu_slab_gradients(int vec, int nx, int ny, int nz, int z0, int nz_global, const float *phi, const float *mu, float *grad_phi, float *grad_mu,
+                       float *normal) {
+    const Grid G = make_grid(nx, ny, nz, 1, z0, nz_global);
+    RUN_CELLS(mp_gradients_kernel, vec, G, phi, mu, grad_phi, grad_mu, normal);
+    return 0;
+}
+int emu_slab_curvature_force(int vec, int nx, int ny, int nz, int z0, int nz_global, const float *phi, const float *rho, const uint8_t *flags,
+                             const float *grad_phi, const float *normal, float *curvature, float *surface_force, float *body_force, float sigma) {
+    const Grid G = make_grid(nx, ny, nz, 1, z0, nz_global);
+    RUN_CELLS(mp_curvature_force_kernel, vec, G, phi, rho, flags, grad_phi, normal, curvature, surface_force, body_force, sigma);
+    return 0;
+}
+int emu_slab_phase_field_step(int vec, int nx, int ny, int nz, int z0, int nz_global, float *phi, float *phi_new, const float *mu, const float *u,
+                              float *rho, float *phase, float mobility, float dt, double rho_water, double rho_air) {
+    const Grid G = make_grid(nx, ny, nz, 1, z0, nz_global);
+    RUN_CELLS(mp_phase_update_kernel, vec, G, phi, mu, u, phi_new, mobility, dt);
+    RUN_CELLS(mp_copy_density_kernel, vec, G, phi_new, phi, rho, phase, (float)rho_air, (float)(rho_water - rho_air));
     return 0;
 }
 int emu_surface_tension_lean(int vec, int nx, int ny, int nz, const float *phi, const float *rho, const uint8_t *flags, const float *normal_outer,

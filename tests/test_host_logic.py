@@ -174,5 +174,22 @@ def test_multiphase_facade_call_sequence_and_lazy_fields():
     assert s.engine.calls[3:] == [("body_force_only",), ("phase_step",), ("fields", False), ("apply",)]
     mp.standardize_initial_state(force_dry_state=True)
     assert s.engine.calls[7:] == [("density",), ("mu",), ("fields", False)] and float(mp.phi.to_numpy().max()) == -1.0
-    with pytest.raises(NotImplementedError):
-        s.engine.zghost = 1; MultiphaseFlow3D(s)
+    # z-slab: two calls with ghost-plane refreshes (phi before the gradients, normal between the launches); never the one-launch
+    # kernel (its stencil reaches k -+ 2)
+    from pour_over_coffee_lbm_b200 import slab
+    s = Solver(); e = s.engine
+    e.zghost, e.rank, e.nranks, e.periodic = 1, 0, 2, (False, False, False)
+    e.rho = torch.ones(6, 4, 4); e.body_force = torch.zeros(3, 6, 4, 4)
+    e.surface_tension_gradients = lambda *a, **k: e.calls.append(("gradients",))
+    e.surface_tension_curvature_force = lambda *a, apply=True, **k: e.calls.append(("curvature_force", apply))
+    real = slab.exchange_planes
+    try:
+        slab.exchange_planes = lambda t, rank, world, per, group=None: e.calls.append(("ghosts", tuple(t.shape)))
+        mp = MultiphaseFlow3D(s, lazy_fields=True)
+        assert mp.lazy_fields is False and mp.phi.shape == (4, 4, 4)          # ghost planes hidden from the field surface
+        mp.accumulate_surface_tension_pre_collision(); mp.step(3, precollision_applied=True)
+    finally:
+        slab.exchange_planes = real
+    assert e.calls == [("ghosts", (6, 4, 4)), ("gradients",), ("ghosts", (3, 6, 4, 4)), ("curvature_force", True),
+                       ("ghosts", (6, 4, 4)), ("gradients",), ("ghosts", (3, 6, 4, 4)), ("curvature_force", False),
+                       ("ghosts", (6, 4, 4)), ("phase_step",)]

@@ -80,3 +80,91 @@ def test_two_gloo_ranks_reproduce_single_domain(periodic_z, balanced):
     for p in procs:
         assert p.exitcode == 0
     assert out.get(timeout=5) is True
+
+
+# ---- multiphase producers on z-slabs: device kernel source (CPU-emulated) + slab.exchange_planes over gloo ----------------
+def _mp_worker(rank, world, port, out, cuts):
+    import ctypes as C
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pour_over_coffee_lbm_b200 import slab
+    here = os.path.dirname(os.path.abspath(__file__))
+    emu = C.CDLL(os.path.join(here, "emu", "_build", "libemu_producers.so"))
+    z = np.load(os.path.join(here, "golden", "reference_run_multiphase.npz"))
+    n = int(z["n"]); z0, nz = cuts[rank]
+    P = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+    F = lambda v: C.c_float(float(v))
+
+    def local(dev, ghost_from_neighbours=False):
+        """[.., z, y, x] global array -> this slab's [.., nz + 2, y, x]; ghost planes start as zeros (the exchange must fill them)."""
+        zax = dev.ndim - 3
+        sl = [slice(None)] * dev.ndim; sl[zax] = slice(z0, z0 + nz)
+        own = dev[tuple(sl)]
+        pad = [(0, 0)] * dev.ndim; pad[zax] = (1, 1)
+        return np.ascontiguousarray(np.pad(own, pad))
+
+    phi, phi_new, mu = local(H.to_dev_scalar(z["phi"])), local(H.to_dev_scalar(z["phi_new_in"])), local(H.to_dev_scalar(z["mu"]))
+    u, rho, bf = local(H.to_dev_vec(z["u"])), local(H.to_dev_scalar(z["rho"])), local(H.to_dev_vec(z["body_force"]))
+    flags = local(H.to_dev_scalar(z["solid"]).astype(np.uint8))
+    phase, curv = np.zeros_like(rho), np.zeros_like(rho)
+    gphi, gmu, nrm, sf = (np.zeros_like(bf) for _ in range(4))
+    dims = (C.c_int(4), C.c_int(n), C.c_int(n), C.c_int(nz), C.c_int(z0), C.c_int(n))
+    tt = torch.from_numpy                                   # shares memory with the NumPy array: the exchange writes in place
+    sigma, mob, dt = float(z["sigma"]), float(z["mobility"]), float(z["dt"])
+    rw, ra = C.c_double(float(z["rho_water"])), C.c_double(float(z["rho_air"]))
+
+    def chain(body_force):
+        slab.exchange_planes(tt(phi), rank, world, False); slab.exchange_planes(tt(mu), rank, world, False)
+        emu.emu_slab_gradients(*dims, P(phi), P(mu), P(gphi), P(gmu), P(nrm))
+        slab.exchange_planes(tt(nrm), rank, world, False)
+        emu.emu_slab_curvature_force(*dims, P(phi), P(rho), P(flags), P(gphi), P(nrm), P(curv), P(sf), P(body_force), F(sigma))
+
+    def phase_step():
+        emu.emu_slab_phase_field_step(*dims, P(phi), P(phi_new), P(mu), P(u), P(rho), P(phase), F(mob), F(dt), rw, ra)
+
+    own = lambda a: a[..., 1:-1, :, :].copy()
+    snaps = {}
+    chain(bf)
+    snaps["st"] = dict(grad_phi=own(gphi), grad_mu=own(gmu), normal=own(nrm), curvature=own(curv), surface_force=own(sf), body_force=own(bf))
+    chain(None); phase_step()
+    snaps["s1"] = dict(phi=own(phi), phi_new=own(phi_new), rho=own(rho), phase=own(phase), body_force=own(bf))
+    chain(bf); phase_step()
+    snaps["s2"] = dict(phi=own(phi), rho=own(rho), phase=own(phase), body_force=own(bf), surface_force=own(sf), curvature=own(curv))
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (z0, snaps))
+    if rank == 0:
+        parts = [s for _, s in sorted(gathered, key=lambda t: t[0])]
+        ok = True
+        for stage in ("st", "s1", "s2"):
+            for name in parts[0][stage]:
+                full = np.concatenate([p[stage][name] for p in parts], axis=-3)
+                want = z[f"{stage}_{name}"]
+                want = H.to_dev_vec(want) if want.ndim == 4 else H.to_dev_scalar(want)
+                ok &= bool(np.array_equal(full, want))
+        out.put(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("cuts", [((0, 8), (8, 8)), ((0, 5), (5, 11))], ids=["equal", "unequal"])
+def test_two_gloo_ranks_multiphase_producers_reproduce_the_reference_run(cuts):
+    """The surface-tension chain and the phase-field step on two z-slabs (ghost planes of phi, mu and -- between the two
+    launches -- normal filled by slab.exchange_planes over gloo): the gathered slabs equal the recorded single-domain run of
+    the reference bit for bit.  The device kernels run as CPU-emulated source (tests/emu)."""
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    lib = os.path.join(here, "emu", "_build", "libemu_producers.so"); src = os.path.join(here, "emu", "emu_producers.cpp")
+    kern = os.path.join(os.path.dirname(here), "pour_over_coffee_lbm_b200", "csrc", "lbm_producers.cu")
+    os.makedirs(os.path.dirname(lib), exist_ok=True)
+    if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(src), os.path.getmtime(kern)):
+        subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-w", "-shared", "-fPIC", "-I/usr/local/cuda/include",
+                        "-include", "algorithm", src, "-o", lib], check=True)
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_mp_worker, args=(r, 2, port, out, cuts)) for r in range(2)]
+    for p in procs: p.start()
+    for p in procs: p.join(timeout=240)
+    for p in procs:
+        assert p.exitcode == 0
+    assert out.get(timeout=5) is True
