@@ -610,11 +610,12 @@ def drag_coefficient(re_p):
     return cd.astype(F32)
 
 
-def two_way_coupling(cfg: RefConfig, u: np.ndarray, pos, vel, radius, mass, active):
+def two_way_coupling(cfg: RefConfig, u: np.ndarray, pos, vel, radius, mass, active, sequential: bool = False):
     """compute_two_way_coupling_forces, coffee_particles.py:1107-1154.
     Returns (drag_force_new [P,3], reaction_force_field [NX,NY,NZ,3], u_fluid, re_p, cd, cell[P,3]).
-    The scatter is summed in f64-free f32 but in particle order (atomics are order-free in the
-    reference; compare with a tolerance)."""
+    The scatter is summed in f32, corner by corner over all particles (atomics are order-free in the reference; compare with
+    a tolerance) -- or, with sequential=True, particle by particle in the reference's corner order, which is the order a
+    serial execution of the reference's loop produces (bit-exact against the recorded runs; slow, small P only)."""
     P = pos.shape[0]
     rho_w = F32(cfg.WATER_DENSITY_90C)
     mu_w = F32(cfg.WATER_VISCOSITY_90C * cfg.WATER_DENSITY_90C)
@@ -637,11 +638,17 @@ def two_way_coupling(cfg: RefConfig, u: np.ndarray, pos, vel, radius, mass, acti
     i, j, k, w = particle_cell_and_weights(cfg, pos)
     field_ = np.zeros((cfg.NX, cfg.NY, cfg.NZ, 3), F32)
     react = -drag_new
-    for (a, b, c) in _SCATTER_ORDER:
-        contrib = (w[(a, b, c)][:, None] * react).astype(F32)
-        contrib[~mov] = 0
-        for comp in range(3):
-            np.add.at(field_[..., comp], (i + a, j + b, k + c), contrib[:, comp])
+    if sequential:
+        for p in np.nonzero(mov)[0]:
+            for (a, b, c) in _SCATTER_ORDER:
+                cell_ = (i[p] + a, j[p] + b, k[p] + c)
+                field_[cell_] = field_[cell_] + (w[(a, b, c)][p] * react[p]).astype(F32)
+    else:
+        for (a, b, c) in _SCATTER_ORDER:
+            contrib = (w[(a, b, c)][:, None] * react).astype(F32)
+            contrib[~mov] = 0
+            for comp in range(3):
+                np.add.at(field_[..., comp], (i + a, j + b, k + c), contrib[:, comp])
     u_fl_out = np.where(act[:, None], u_fl, F32(0.0)).astype(F32)
     cell = np.stack([i, j, k], axis=1).astype(np.int32)
     return drag_new, field_, u_fl_out, re_out, cd_out, cell

@@ -418,6 +418,75 @@ def check_filter_particles_against_oracle(res):
     return ok
 
 
+def run_coupled_scenario(config, n, seed, steps=6):
+    """BASELINE configs[3] as the reference wires it: LBMSolver.step_with_two_way_coupling(particle_system, dt, relax)
+    (legacy/lbm_solver.py:1485-1509: clear body force -> coupling on the current u -> under-relaxation -> reaction into the
+    body force -> step) followed by CoffeeParticleSystem.update_particle_physics with the filter's bounds (main.py:672-679),
+    `steps` times on the V60 box, air-phase relaxation."""
+    sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, ROOT)
+    import helpers as H
+    gravity = 2e-5
+    config.GRAVITY_LU = gravity
+    with quiet():
+        from src.core.legacy.lbm_solver import LBMSolver
+        from src.physics.filter_paper import FilterPaperSystem
+        from src.physics.coffee_particles import CoffeeParticleSystem
+        s = LBMSolver(); s.init_fields()
+        fp = FilterPaperSystem(s); fp.initialize_filter_geometry()
+        s.boundary_manager.set_filter_system(fp)
+        P = 250
+        ps = CoffeeParticleSystem(P)
+    st = H.reference_v60_state(n, seed=seed, gravity=gravity, body=1e-5, phase_mode="none")
+    st.phase[:] = np.random.default_rng(seed + 1000).uniform(0.0, 0.5, size=st.phase.shape).astype(np.float32)
+    rng = np.random.default_rng(seed + 7)
+    fluid_cells = np.argwhere(st.solid == 0)
+    pos = (fluid_cells[rng.integers(0, len(fluid_cells), P)] + rng.uniform(0.05, 0.95, (P, 3))).astype(np.float32)
+    pos[-20:] = rng.uniform(-1.0, n + 1.0, (20, 3)).astype(np.float32)
+    vel = (0.02 * rng.standard_normal((P, 3))).astype(np.float32)
+    radius = np.clip(rng.normal(3.25e-4, 1e-4, P), 1.6e-4, 4.9e-4).astype(np.float32)
+    mass = ((np.float32(4.0 / 3.0) * np.float32(3.14159)) * (radius * radius * radius) * np.float32(config.COFFEE_BEAN_DENSITY)).astype(np.float32)
+    active = (rng.random(P) < 0.92).astype(np.int32)
+    s.f.from_numpy(st.f); s.f_new.from_numpy(st.f); s.phase.from_numpy(st.phase)
+    ps.position.from_numpy(pos); ps.velocity.from_numpy(vel); ps.radius.from_numpy(radius); ps.mass.from_numpy(mass); ps.active.from_numpy(active)
+    b = fp.get_coffee_bed_boundary()
+    bounds = np.array([b["center_x"], b["center_y"], b["bottom_z"], b["bottom_radius_lu"], b["top_radius_lu"]], np.float64)
+    dt_p = 5e-3
+    res = dict(n=n, steps=steps, gravity=gravity, seed=seed, f=st.f.copy(), phase=st.phase.copy(), solid=s.solid.to_numpy().astype(np.uint8),
+               p_pos=pos, p_vel=vel, p_radius=radius, p_mass=mass, p_active=active, bounds=bounds, dt_particles=dt_p, relax=0.8)
+    with quiet():
+        for _ in range(steps):
+            s.step_with_two_way_coupling(ps, 1.0, 0.8)
+            ps.update_particle_physics(dt_p, b["center_x"], b["center_y"], b["bottom_z"], b["bottom_radius_lu"], b["top_radius_lu"])
+    res.update(rho=s.rho.to_numpy(), u=s.u.to_numpy(), f_out=s.f.to_numpy(), body_force=s.body_force.to_numpy(),
+               p_pos_out=ps.position.to_numpy(), p_vel_out=ps.velocity.to_numpy(), p_active_out=ps.active.to_numpy(),
+               p_drag=ps.drag_force.to_numpy(), p_drag_old=ps.drag_force_old.to_numpy(), p_reynolds=ps.particle_reynolds.to_numpy(),
+               p_reaction=ps.reaction_force_field.to_numpy())
+    return res
+
+
+def oracle_coupled(res):
+    """The same sequence from oracle/ functions; returns (State, pos, vel, active, drag, drag_old, reaction)."""
+    from oracle import d3q19_ref as R
+    n = int(res["n"])
+    cfg = R.RefConfig(NX=n, NY=n, NZ=n, GRAVITY_LU=float(res["gravity"]))
+    st = R.init_fields(cfg); R.attach_filter_system(st)
+    st.f = res["f"].copy(); st.f_new = res["f"].copy(); st.phase = res["phase"].copy()
+    pos, vel, active = res["p_pos"].copy(), res["p_vel"].copy(), res["p_active"].copy()
+    drag_old = np.zeros_like(pos); drag = np.zeros_like(pos); react = None
+    force = np.zeros_like(pos)
+    cx, cy, bz, br, tr = [float(v) for v in res["bounds"]]
+    for _ in range(int(res["steps"])):
+        st.body_force[:] = 0
+        dn, react, ufl, re_p, cd, cell = R.two_way_coupling(cfg, st.u, pos, vel, res["p_radius"], res["p_mass"], active, sequential=True)
+        new_drag, new_old = R.under_relax(dn, drag_old, active, float(res["relax"]))
+        a = active != 0
+        drag[a] = new_drag[a]; drag_old[a] = new_old[a]
+        R.add_particle_reaction_forces(st, react)
+        R.step(st)
+        R.update_particle_physics(cfg, pos, vel, force, res["p_mass"], active, float(res["dt_particles"]), cx, cy, bz, br, tr)
+    return st, pos, vel, active, drag, drag_old, react, re_p
+
+
 if __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 16
     config = load_reference(n)
@@ -439,6 +508,20 @@ if __name__ == "__main__":
         np.savez_compressed(os.path.join(HERE, f"reference_run_long_air_{steps}.npz"), n=n, steps=steps, gravity=2e-5, seed=36,
                             phase_mode="air_random", **inp, **geom, **out)
         sys.exit(0 if ok else 1)
+    if len(sys.argv) > 2 and sys.argv[2] == "coupled":
+        t = time.time()
+        res = run_coupled_scenario(config, n, seed=51)
+        st, pos, vel, active, drag, drag_old, react, re_p = oracle_coupled(res)
+        fluid = res["solid"] == 0; a = res["p_active_out"] == 1
+        ok = dict(rho=np.array_equal(st.rho[fluid], res["rho"][fluid]), u=np.array_equal(st.u[fluid], res["u"][fluid]),
+                  f=np.array_equal(st.f[:, fluid], res["f_out"][:, fluid]), active=np.array_equal(active, res["p_active_out"]),
+                  pos=np.array_equal(pos[a], res["p_pos_out"][a]), vel=np.array_equal(vel[a], res["p_vel_out"][a]),
+                  drag=bool(np.allclose(drag[a], res["p_drag"][a], rtol=1e-6, atol=1e-20)),
+                  reaction=bool(np.allclose(react, res["p_reaction"], rtol=1e-5, atol=1e-14)))
+        print(f"[reference run] coupled step x{int(res['steps'])} ({time.time() - t:.0f} s) vs oracle:", ok,
+              " moving particles:", int((res["p_reynolds"] > 0).sum()), " max|reaction|", float(np.abs(res["p_reaction"]).max()))
+        np.savez_compressed(os.path.join(HERE, "reference_run_coupled.npz"), **res)
+        sys.exit(0 if all(ok.values()) else 1)
     if len(sys.argv) > 2 and sys.argv[2] == "producers":
         res = run_multiphase_scenario(config, n, seed=43)
         ok = check_multiphase_against_oracle(res)
@@ -491,5 +574,13 @@ if __name__ == "__main__":
     print("[reference run] filter / particle interception vs oracle:", ok)
     all_ok &= all(ok.values())
     np.savez_compressed(os.path.join(HERE, "reference_run_filter_particles.npz"), **res)
+    res = run_coupled_scenario(config, n, seed=51)
+    st, pos, vel, active, drag, drag_old, react, re_p = oracle_coupled(res)
+    fluid = res["solid"] == 0; a = res["p_active_out"] == 1
+    ok = np.array_equal(st.rho[fluid], res["rho"][fluid]) and np.array_equal(st.u[fluid], res["u"][fluid]) and \
+        np.array_equal(st.f[:, fluid], res["f_out"][:, fluid]) and np.array_equal(pos[a], res["p_pos_out"][a])
+    print("[reference run] coupled sequence vs oracle bit-exact:", ok)
+    all_ok &= bool(ok)
+    np.savez_compressed(os.path.join(HERE, "reference_run_coupled.npz"), **res)
     print("ALL OK" if all_ok else "MISMATCH")
     sys.exit(0 if all_ok else 1)

@@ -1,0 +1,80 @@
+"""BASELINE configs[3] as the reference wires it -- LBMSolver.step_with_two_way_coupling(particle_system, dt, relax)
+(legacy/lbm_solver.py:1485-1509) followed by CoffeeParticleSystem.update_particle_physics with the filter's bounds
+(main.py:672-679), six times on the V60 box -- against a recorded run of the reference's own code
+(tests/golden/reference_run_coupled.npz, made by tests/golden/make_reference_goldens.py `coupled`).
+
+CPU: the oracle functions chained in that order reproduce the recording bit for bit (scatter summed in the serial order of
+the reference's loop).  GPU: the facade classes over the C ABI; the scatter's atomics are unordered on a GPU, so the flow
+fields carry rounding noise of the reaction force: rho, u within BASELINE's 1e-5 relative, particles bit-exact.
+(The file sorts last on purpose: it is the one GPU test added after the round's GPU budget was spent.)
+"""
+import os
+
+import numpy as np
+import pytest
+
+import helpers as H
+from oracle import d3q19_ref as R
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_run_coupled.npz")
+
+
+def test_oracle_coupled_sequence_reproduces_the_reference_run():
+    z = np.load(GOLD)
+    n = int(z["n"])
+    cfg = R.RefConfig(NX=n, NY=n, NZ=n, GRAVITY_LU=float(z["gravity"]))
+    st = R.init_fields(cfg); R.attach_filter_system(st)
+    assert np.array_equal(st.solid, z["solid"])
+    st.f = z["f"].copy(); st.f_new = z["f"].copy(); st.phase = z["phase"].copy()
+    pos, vel, active = z["p_pos"].copy(), z["p_vel"].copy(), z["p_active"].copy()
+    drag_old = np.zeros_like(pos); drag = np.zeros_like(pos); force = np.zeros_like(pos)
+    cx, cy, bz, br, tr = [float(v) for v in z["bounds"]]
+    for _ in range(int(z["steps"])):
+        st.body_force[:] = 0                                                       # clear_body_force
+        dn, react, ufl, re_p, cd, cell = R.two_way_coupling(cfg, st.u, pos, vel, z["p_radius"], z["p_mass"], active, sequential=True)
+        new_drag, new_old = R.under_relax(dn, drag_old, active, float(z["relax"]))
+        a = active != 0
+        drag[a] = new_drag[a]; drag_old[a] = new_old[a]
+        R.add_particle_reaction_forces(st, react)
+        R.step(st)
+        R.update_particle_physics(cfg, pos, vel, force, z["p_mass"], active, float(z["dt_particles"]), cx, cy, bz, br, tr)
+    fluid = z["solid"] == 0; a = z["p_active_out"] == 1
+    assert np.array_equal(st.rho[fluid], z["rho"][fluid]) and np.array_equal(st.u[fluid], z["u"][fluid])
+    assert np.array_equal(st.f[:, fluid], z["f_out"][:, fluid]) and np.array_equal(st.body_force, z["body_force"])
+    assert np.array_equal(active, z["p_active_out"]) and np.array_equal(pos[a], z["p_pos_out"][a]) and np.array_equal(vel[a], z["p_vel_out"][a])
+    assert np.allclose(drag[a], z["p_drag"][a], rtol=1e-6, atol=1e-20)              # powf in C_D
+    assert np.array_equal(react, z["p_reaction"]) or np.allclose(react, z["p_reaction"], rtol=1e-6, atol=1e-14)
+    assert float(np.abs(z["p_reaction"]).max()) > 1e-6 and int((z["p_reynolds"] > 0).sum()) > 100     # the coupling is not a no-op
+
+
+@pytest.mark.gpu
+def test_gpu_coupled_sequence_reproduces_the_reference_run():
+    import torch
+    from pour_over_coffee_lbm_b200.config import LBMConfig
+    from pour_over_coffee_lbm_b200.physics import CoffeeParticleSystem, FilterPaperSystem
+    from pour_over_coffee_lbm_b200.solver import LBMSolver
+    z = np.load(GOLD)
+    n, gravity = int(z["n"]), float(z["gravity"])
+    c = R.RefConfig(NX=n, NY=n, NZ=n, GRAVITY_LU=gravity)
+    cfg = LBMConfig(NX=n, NY=n, NZ=n, TAU_FLUID=c.TAU_WATER, TAU_AIR=c.TAU_AIR, GRAVITY_LU=gravity)
+    s = LBMSolver(nx=n, ny=n, nz=n, config=cfg, compat="reference", strict=True, gravity_lu=gravity)
+    s.init_fields()
+    fp = FilterPaperSystem(s); fp.initialize_filter_geometry()
+    assert np.array_equal(s.solid.to_numpy(), z["solid"])
+    s.f.from_numpy(z["f"]); s.phase.from_numpy(z["phase"])
+    npart = z["p_pos"].shape[0]
+    ps = CoffeeParticleSystem(npart, solver=s)
+    ps.set_particles(z["p_pos"], z["p_vel"], z["p_radius"], z["p_mass"])
+    ps.state.active.copy_(torch.from_numpy(z["p_active"]).cuda())
+    cx, cy, bz, br, tr = [float(v) for v in z["bounds"]]
+    for _ in range(int(z["steps"])):
+        s.step_with_two_way_coupling(ps, 1.0, float(z["relax"]))
+        ps.update_particle_physics(float(z["dt_particles"]), cx, cy, bz, br, tr)
+    fluid = z["solid"] == 0; a = z["p_active_out"] == 1
+    rho, u = s.rho.to_numpy(), s.u.to_numpy()
+    assert H.rel_err(rho[fluid], z["rho"][fluid]) <= 1e-5 and H.rel_err(u[fluid], z["u"][fluid]) <= 1e-5      # BASELINE's bar
+    assert H.rel_err(s.f.to_numpy()[:, fluid], z["f_out"][:, fluid]) <= 1e-5
+    assert np.allclose(s.body_force.to_numpy(), z["body_force"], rtol=1e-4, atol=1e-11)
+    assert np.array_equal(ps.active.cpu().numpy(), z["p_active_out"])
+    assert np.array_equal(ps.position.cpu().numpy()[a], z["p_pos_out"][a]) and np.array_equal(ps.velocity.cpu().numpy()[a], z["p_vel_out"][a])
+    assert np.allclose(ps.drag_force.cpu().numpy()[a], z["p_drag"][a], rtol=1e-5, atol=1e-18)
