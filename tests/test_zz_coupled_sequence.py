@@ -6,7 +6,6 @@
 CPU: the oracle functions chained in that order reproduce the recording bit for bit (scatter summed in the serial order of
 the reference's loop).  GPU: the facade classes over the C ABI; the scatter's atomics are unordered on a GPU, so the flow
 fields carry rounding noise of the reaction force: rho, u within BASELINE's 1e-5 relative, particles bit-exact.
-(The file sorts last on purpose: it is the one GPU test added after the round's GPU budget was spent.)
 """
 import os
 
