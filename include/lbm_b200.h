@@ -27,6 +27,8 @@
  *   LBM_TMA=1            compat = physical behind walls: use the TMA-staged persistent kernel (csrc/lbm_phys_tma.cuh)
  *                        when the box does not wrap in x or y and nx % 16 == 0
  *   LBM_TMA_VARIANT=0..9 its tile height / ring depth / producer-warp count (csrc/lbm_step_tma.cu)
+ *   LBM_PRODUCERS_VEC=1  multiphase / filter producers (csrc/lbm_producers.cu): one cell per thread instead of four
+ *                        (read at the first launch; the four-cell path needs nx % 4 == 0 and 16-byte aligned fields anyway)
  */
 #ifndef LBM_B200_H
 #define LBM_B200_H
