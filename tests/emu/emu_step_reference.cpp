@@ -59,3 +59,32 @@ extern "C" int emu_step_reference(int nx, int ny, int nz, const float *src, floa
     else run<false, false>(P);
     return 0;
 }
+
+// compat = physical, fully periodic box (the headline configuration): step_cells<LBM_COMPAT_PHYSICAL, MODE_DENSE, ..., VEC = 1>
+// -- pull with in-kernel wrap, collide_phys<float>, write-back.  The GPU runs the VEC = 4 instantiation of the same function
+// (128-bit loads, shuffles, packed f32x2 collision); the arithmetic contract makes both produce the same bits.
+template <bool LES>
+static void run_dense(const StepArgs &P) {
+    const Grid &G = P.g;
+    for (int z = 0; z < G.nz; ++z)
+        for (int y = 0; y < G.ny; ++y)
+            for (int x = 0; x < G.nx; ++x)
+                step_cells<LBM_COMPAT_PHYSICAL, MODE_DENSE, false, LES, false, 1, true>(P, x, y, z, true, (unsigned)(x & 31));
+}
+extern "C" int emu_step_physical_dense(int nx, int ny, int nz, int steps, float *g0, float *g1, float *rho, float *u, int les, float tau,
+                                       float cs_smag, float tau_min, float tau_max, int write_macro_last_only) {
+    StepArgs P{};
+    P.g.nx = nx; P.g.ny = ny; P.g.nz = nz; P.g.zg = 0; P.g.nz_global = nz; P.g.z0 = 0;
+    P.g.per_x = P.g.per_y = P.g.per_z = 1;
+    P.g.plane = (long long)nx * ny; P.g.vol = P.g.plane * nz;
+    P.rho = rho; P.u_dst = u; P.u_src = u;
+    P.tau_water = tau; P.tau_air = tau; P.tau_min = tau_min; P.tau_max = tau_max;
+    P.les_k = (float)(18.0 * sqrt(2.0) * (double)cs_smag * (double)cs_smag);
+    float *buf[2] = {g0, g1};
+    for (int s = 0; s < steps; ++s) {
+        P.src = buf[s & 1]; P.dst = buf[(s + 1) & 1];
+        P.write_macro = (!write_macro_last_only || s == steps - 1) ? 1 : 0;
+        if (les) run_dense<true>(P); else run_dense<false>(P);
+    }
+    return steps & 1;      // index of the buffer that holds the newest populations
+}

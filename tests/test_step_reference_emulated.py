@@ -147,3 +147,55 @@ def test_emulated_reference_step_kernel_on_the_open_box_recording(emu):
     assert np.array_equal(u[fluid], z["u"][fluid]) and np.array_equal(f_out[:, fluid], z["f_out"][:, fluid])
     inner = fluid.copy(); inner[[0, -1]] = False; inner[:, [0, -1]] = False; inner[:, :, [0, -1]] = False
     assert np.array_equal(rho[inner], z["rho"][inner])
+
+
+# ---- compat = physical, the headline configuration: step_cells<PHYSICAL, DENSE, ..., VEC = 1> ---------------------------
+@pytest.mark.parametrize("les", [False, True])
+def test_emulated_dense_physical_step_kernel_matches_the_oracle_and_its_golden(emu, les):
+    """pull with in-kernel periodic wrap + collide_phys<float> + write-back, 10 steps at 24^3 from the committed fixture's
+    initial state: bit-exact against oracle.step_physical (and, with LES, against tests/golden/step_physical_24.npz)."""
+    z = np.load(os.path.join(GOLD, "step_physical_24.npz"))
+    n, steps = int(z["n"]), int(z["steps"])
+    p = R.PhysParams(nx=n, ny=n, nz=n, tau_water=float(z["tau"]), les=les)
+    g = R.init_equilibrium_phys(z["rho0"], z["u0"])
+    b0 = H.to_dev_pop(g); b1 = np.empty_like(b0)
+    rho = np.empty((n, n, n), np.float32); u = np.empty((3, n, n, n), np.float32)
+    for _ in range(steps):
+        g, rho_o, u_o = R.step_physical(g, p)
+    f32 = lambda v: C.c_float(float(v))
+    cur = emu.emu_step_physical_dense(C.c_int(n), C.c_int(n), C.c_int(n), C.c_int(steps), _p(b0), _p(b1), _p(rho), _p(u), C.c_int(int(les)),
+                                      f32(p.tau_water), f32(p.cs_smag), f32(p.tau_min), f32(p.tau_max), C.c_int(1))
+    got = np.transpose((b0, b1)[cur], (0, 3, 2, 1))
+    assert np.array_equal(got, g) and np.array_equal(np.transpose(rho, (2, 1, 0)), rho_o) and np.array_equal(np.transpose(u, (3, 2, 1, 0)), u_o)
+    if les:
+        assert np.array_equal(got, z["g"]) and np.array_equal(np.transpose(rho, (2, 1, 0)), z["rho"])
+
+
+@pytest.mark.parametrize("tau", [0.53, 0.8])
+def test_emulated_taylor_green_decay_rate(emu, tau):
+    """BASELINE's third criterion on the CPU, with the product's kernel source: the z-invariant Taylor-Green vortex (exact
+    Navier-Stokes solution) on a periodic 128 x 128 x 2 box, u0 = 0.01, 1000 steps; ln E fitted over steps 200..1000 against
+    -4 nu k^2, nu = (tau - 1/2)/3, within 0.5 %.  (The GPU test does the same at 256^3.)"""
+    n, nz, u0, steps, every = 128, 2, 0.01, 1000, 50
+    k = 2 * np.pi / n
+    x = np.arange(n)[:, None, None] * k; y = np.arange(n)[None, :, None] * k
+    ux = (u0 * np.sin(x) * np.cos(y) * np.ones((1, 1, nz))).astype(np.float32)
+    uy = (-u0 * np.cos(x) * np.sin(y) * np.ones((1, 1, nz))).astype(np.float32)
+    rho0 = (1.0 - (3.0 * u0 * u0 / 4.0) * (np.cos(2 * x) + np.cos(2 * y)) * np.ones((1, 1, nz))).astype(np.float32)
+    uinit = np.stack([ux, uy, np.zeros_like(ux)], -1)
+    g = R.init_equilibrium_phys(rho0, uinit)
+    bufs = [H.to_dev_pop(g), None]; bufs[1] = np.empty_like(bufs[0])
+    rho = np.empty((nz, n, n), np.float32); u = np.empty((3, nz, n, n), np.float32)
+    f32 = lambda v: C.c_float(float(v))
+    ts, es, cur = [], [], 0
+    for s in range(0, steps, every):
+        r = emu.emu_step_physical_dense(C.c_int(n), C.c_int(n), C.c_int(nz), C.c_int(every), _p(bufs[cur]), _p(bufs[1 - cur]), _p(rho), _p(u),
+                                        C.c_int(0), f32(tau), f32(0.18), f32(0.55), f32(1.90), C.c_int(1))
+        cur = cur if r == 0 else 1 - cur
+        ts.append(s + every - 1); es.append(float((0.5 * rho.astype(np.float64) * (u.astype(np.float64) ** 2).sum(0)).sum()))
+    ts, es = np.array(ts, float), np.array(es, float)
+    sel = ts >= 200
+    slope = np.polyfit(ts[sel], np.log(es[sel]), 1)[0]
+    expected = -4.0 * ((tau - 0.5) / 3.0) * k * k
+    assert abs(slope / expected - 1.0) <= 5e-3, (slope, expected)
+    assert float(np.abs(u[2]).max()) < 1e-4 * u0 and float(np.abs(u[0][0] - u[0][1]).max()) == 0.0
