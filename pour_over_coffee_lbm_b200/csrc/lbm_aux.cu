@@ -1,8 +1,10 @@
 // Initialisation, geometry, flag packing, f<->g conversion, face BCs and the small
 // stencil kernels that feed body_force.  Compiled with -fmad=false so that every value is
 // bit-identical to oracle/d3q19_ref.py (these kernels are not on the roofline path).
+#ifndef LBM_EMULATE_ON_HOST   /* tests/emu compiles the plain kernels of this file with the host compiler */
 #include <cub/cub.cuh>
 #include <thrust/iterator/counting_iterator.h>
+#endif
 
 #include <vector>
 
@@ -283,6 +285,7 @@ __global__ void tile_flags_kernel(Grid G, const uint8_t *flags, int vec, int ty,
     }
     tile_flag[id] = fluid ? 1 : 0;
 }
+#ifndef LBM_EMULATE_ON_HOST   /* tests/emu compiles the plain kernels of this file with the host compiler */
 
 __global__ void count_flagged_per_plane_kernel(const uint8_t *tile_flag, int per_plane, int nz, int *plane_count) {
     const int z = blockIdx.x;
@@ -293,6 +296,7 @@ __global__ void count_flagged_per_plane_kernel(const uint8_t *tile_flag, int per
     const int tot = BR(tmp).Sum(n);
     if (threadIdx.x == 0 && z < nz) plane_count[z] = tot;
 }
+#endif
 
 __global__ void expand_tiles_kernel(const int *ids, int n, int rows, int ty, int segs, unsigned *out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -350,6 +354,7 @@ __global__ void neighbour_mask_kernel(Grid G, const uint8_t *flags, unsigned lon
 
 // Builds the active warp-tile list (device array allocated here, owned by the caller = lbm_ctx), its per-plane
 // offsets (host vector of nz+1 entries) and the neighbour masks.  Synchronises the stream: geometry changes are rare.
+#ifndef LBM_EMULATE_ON_HOST   /* tests/emu compiles the plain kernels of this file with the host compiler */
 cudaError_t build_work_lists(const Grid &G, const uint8_t *flags, int vec, int ty, unsigned **d_tiles, unsigned **d_tile_mask,
                              std::vector<int> &tile_off, unsigned long long **d_nbr, cudaStream_t s) {
     cudaError_t e;
@@ -390,6 +395,7 @@ cudaError_t build_work_lists(const Grid &G, const uint8_t *flags, int vec, int t
     if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }
+#endif
 
 // ---- write-side bounce-back slots (compat = physical, walls path; see lbm_phys.cuh) ---------------------
 // Re-creates the bounce-back slots of a population buffer from the cells' own values:
@@ -423,6 +429,7 @@ __global__ void bounce_slots_kernel(Grid G, float *g, const uint8_t *flags, cons
 }
 
 
+#ifndef LBM_EMULATE_ON_HOST   /* tests/emu compiles the plain kernels of this file with the host compiler */
 // ---- self-test of the packed reciprocal / square root (lbm_phys.cuh) -----------------------------------
 // Every f32 bit pattern goes through both lanes of Ops<P2>::rcp / ::sqrt and is compared, bit for bit, with the
 // correctly rounded scalar intrinsics.  counts[0] = reciprocal mismatches, counts[1] = square-root mismatches.
@@ -662,4 +669,5 @@ cudaError_t launch_add_reaction(const Grid &G, const float *reaction, const uint
     return cudaGetLastError();
 }
 
+#endif
 }  // namespace lbm

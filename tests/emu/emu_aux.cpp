@@ -1,0 +1,103 @@
+// TEST INFRASTRUCTURE -- not product code.  The plain kernels of pour_over_coffee_lbm_b200/csrc/lbm_aux.cu (V60 geometry,
+// flag packing, neighbour masks, exact f <-> g conversion, face density writes, pressure-gradient and Forchheimer forces,
+// reaction accumulation, equilibrium initialisation) compiled by the HOST compiler and executed thread by thread (see
+// emu_producers.cpp).  Grid-stride kernels run as one block of one thread.  The cub-based work-list builder, the packed-math
+// self-test and the shuffle-based statistics stay GPU-only.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+
+struct EmuIdx { unsigned x, y, z; };
+static EmuIdx emu_block_idx, emu_thread_idx, emu_block_dim, emu_grid_dim;
+#define blockIdx emu_block_idx
+#define threadIdx emu_thread_idx
+#define blockDim emu_block_dim
+#define gridDim emu_grid_dim
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+static inline float __frcp_rn(float a) { return 1.0f / a; }
+static inline float __fsqrt_rn(float a) { return sqrtf(a); }
+static inline unsigned __float_as_uint(float a) { unsigned u; __builtin_memcpy(&u, &a, 4); return u; }
+template <class T> static inline T __ldg(const T *p) { return *p; }
+template <class T> static inline T __ldcs(const T *p) { return *p; }
+template <class T> static inline void __stcs(T *p, T v) { *p = v; }
+static inline float atomicAdd(float *p, float v) { const float o = *p; *p = o + v; return o; }
+static inline int min(int a, int b) { return a < b ? a : b; }               // CUDA's integer min / max device functions
+static inline int max(int a, int b) { return a > b ? a : b; }
+#define __launch_bounds__(...)
+#define LBM_EMULATE_ON_HOST 1
+#define LBM_PHYS_COLLISION_ONLY 1
+#include "../../pour_over_coffee_lbm_b200/csrc/lbm_aux.cu"
+
+using namespace lbm;
+
+template <class F>
+static void run(dim3 grid, unsigned block, F &&kernel) {
+    emu_block_dim = {block, 1, 1}; emu_grid_dim = {grid.x, grid.y, grid.z};
+    for (unsigned bz = 0; bz < grid.z; ++bz)
+        for (unsigned by = 0; by < grid.y; ++by)
+            for (unsigned bx = 0; bx < grid.x; ++bx)
+                for (unsigned t = 0; t < block; ++t) { emu_block_idx = {bx, by, bz}; emu_thread_idx = {t, 0, 0}; kernel(); }
+}
+template <class F> static void run_stride(F &&kernel) { run(dim3(1, 1, 1), 1, kernel); }     // grid-stride loop: one thread walks everything
+static Grid make_grid(int nx, int ny, int nz, int periodic = 0) {
+    Grid G{};
+    G.nx = nx; G.ny = ny; G.nz = nz; G.zg = 0; G.nz_global = nz; G.z0 = 0;
+    G.per_x = periodic & 1; G.per_y = (periodic >> 1) & 1; G.per_z = (periodic >> 2) & 1;
+    G.plane = (long long)nx * ny; G.vol = G.plane * nz;
+    return G;
+}
+
+extern "C" {
+int emu_v60_geometry(int nx, int ny, int nz, uint8_t *solid, int32_t *zone, const float *geom5) {
+    const Grid G = make_grid(nx, ny, nz);
+    run_stride([&] { v60_geometry_kernel(G, solid, zone, geom5[0], geom5[1], geom5[2], geom5[3], geom5[4]); });
+    return 0;
+}
+int emu_pack_flags_and_masks(int nx, int ny, int nz, int periodic, uint8_t *flags, const uint8_t *solid, const int32_t *zone, const int32_t *les,
+                             unsigned long long *nbr) {
+    const Grid G = make_grid(nx, ny, nz, periodic);
+    run_stride([&] { pack_flags_kernel(G, flags, solid, zone, les); });
+    run_stride([&] { neighbour_mask_kernel(G, flags, nbr); });
+    return 0;
+}
+int emu_convert_f(int nx, int ny, int nz, int to_reference_f, const float *in, const uint8_t *flags, float *out) {
+    const Grid G = make_grid(nx, ny, nz);
+    if (to_reference_f) run_stride([&] { convert_f_kernel<true>(G, in, flags, out); });
+    else run_stride([&] { convert_f_kernel<false>(G, in, flags, out); });
+    return 0;
+}
+int emu_face_bc(int nx, int ny, int nz, float *rho, const uint8_t *flags) {
+    const Grid G = make_grid(nx, ny, nz);
+    const unsigned b = 128;
+    for (int pass = 0; pass < 5; ++pass) {                                    // launch geometry of launch_face_bc
+        dim3 grid;
+        if (pass == 0 || pass == 1 || pass == 4) grid = dim3((nx + b - 1) / b, ny);
+        else if (pass == 2) grid = dim3((ny + b - 1) / b, nz);
+        else grid = dim3((nx + b - 1) / b, nz);
+        run(grid, b, [&] { face_bc_kernel(G, rho, flags, pass); });
+    }
+    return 0;
+}
+int emu_pressure_gradient(int nx, int ny, int nz, const float *rho, const uint8_t *flags, float *bf, float max_force, float scale, int accumulate) {
+    const Grid G = make_grid(nx, ny, nz);
+    const unsigned b = nx >= 128 ? 128 : 64;
+    run(dim3((nx + b - 1) / b, ny, nz), b, [&] { pressure_gradient_kernel(G, rho, flags, bf, max_force, scale, accumulate); });
+    return 0;
+}
+int emu_forchheimer(int nx, int ny, int nz, const float *u, const uint8_t *flags, float *bf, float K, float beta, float c_darcy, float c_forch,
+                    float fmax) {
+    const Grid G = make_grid(nx, ny, nz);
+    const unsigned b = 256;
+    run(dim3((unsigned)((G.vol + b - 1) / b), 1, 1), b, [&] { forchheimer_force_kernel(G, u, flags, bf, K, beta, c_darcy, c_forch, fmax); });
+    return 0;
+}
+int emu_add_reaction(int nx, int ny, int nz, const float *reaction, const uint8_t *flags, float *bf) {
+    const Grid G = make_grid(nx, ny, nz);
+    run_stride([&] { add_reaction_kernel(G, reaction, flags, bf); });
+    return 0;
+}
+}  // extern "C"

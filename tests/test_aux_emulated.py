@@ -1,0 +1,131 @@
+"""The plain kernels of csrc/lbm_aux.cu -- V60 geometry, flag packing, neighbour masks, exact f <-> g conversion, face density
+writes, pressure-gradient and Forchheimer forces -- compiled by g++ and executed thread by thread on the CPU
+(tests/emu/emu_aux.cpp), against the recorded runs of the reference and the oracle.  Includes BASELINE's first criterion
+(solid / fluid flags bit-exact) at the reference's own 224^3 on product kernel source, and the whole legacy-compatible
+pipeline lbm_pack_flags -> lbm_import_f -> lbm_step x N -> lbm_export_f as emulated product kernels against the 1000-step
+recording.  Test infrastructure only."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import helpers as H
+from oracle import d3q19_ref as R
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden")
+CSRC = os.path.join(os.path.dirname(HERE), "pour_over_coffee_lbm_b200", "csrc")
+
+
+def _build(name, deps):
+    src = os.path.join(HERE, "emu", name + ".cpp"); lib = os.path.join(HERE, "emu", "_build", "lib" + name + ".so")
+    os.makedirs(os.path.dirname(lib), exist_ok=True)
+    deps = [src] + [os.path.join(CSRC, d) for d in deps]
+    if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(d) for d in deps):
+        subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-w", "-shared", "-fPIC", "-I/usr/local/cuda/include",
+                        "-include", "algorithm", src, "-o", lib], check=True)
+    return C.CDLL(lib)
+
+
+@pytest.fixture(scope="module")
+def aux():
+    return _build("emu_aux", ["lbm_aux.cu", "lbm_phys.cuh", "lbm_common.cuh"])
+
+
+@pytest.fixture(scope="module")
+def stepper():
+    return _build("emu_step_reference", ["lbm_step_kernel.cuh", "lbm_phys.cuh", "lbm_common.cuh"])
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _dims(n):
+    return C.c_int(n), C.c_int(n), C.c_int(n)
+
+
+def _geometry(aux, n):
+    from pour_over_coffee_lbm_b200.config import LBMConfig
+    cfg = LBMConfig(NX=n, NY=n, NZ=n)
+    solid = np.zeros((n, n, n), np.uint8); zone = np.zeros((n, n, n), np.int32)
+    geom = np.array(cfg.v60_geometry_constants(), np.float32)
+    aux.emu_v60_geometry(*_dims(n), _p(solid), _p(zone), _p(geom))
+    return np.transpose(solid, (2, 1, 0)), np.transpose(zone, (2, 1, 0))
+
+
+@pytest.mark.parametrize("n", [16, 64, 224])
+def test_emulated_v60_geometry_flags_bit_exact(aux, n):
+    """BASELINE: "solid/fluid flags ... must match bit-exactly" -- v60_geometry_kernel against the recorded reference run
+    (16^3) and the oracle's restatement of FilterPaperSystem._setup_v60_geometry / _setup_filter_zones (64^3, 224^3)."""
+    solid, zone = _geometry(aux, n)
+    cfg = R.RefConfig(NX=n, NY=n, NZ=n)
+    assert np.array_equal(solid, R.v60_solid(cfg)) and np.array_equal(zone, R.filter_zones(cfg))
+    if n == 16:
+        z = np.load(os.path.join(GOLD, "reference_run_neighbours.npz"))
+        assert np.array_equal(solid, z["solid"]) and np.array_equal(zone, z["filter_zone"])
+    if n == 224:
+        assert 0.30 < float((solid == 0).mean()) < 0.40
+
+
+def test_emulated_force_producers_reproduce_the_reference_run(aux):
+    """pressure_gradient_kernel (force and mixed drive) and forchheimer_force_kernel against the recorded
+    PressureGradientDrive / FilterPaperSystem.compute_forchheimer_resistance run."""
+    from pour_over_coffee_lbm_b200.config import LBMConfig
+    z = np.load(os.path.join(GOLD, "reference_run_neighbours.npz"))
+    n = int(z["n"]); cfg = LBMConfig(NX=n, NY=n, NZ=n)
+    flags = H.to_dev_scalar((z["solid"] | (2 * (z["filter_zone"] != 0))).astype(np.uint8))
+    rho, u = H.to_dev_scalar(z["rho"]), H.to_dev_vec(z["u"])
+    bf = np.zeros_like(u)
+    aux.emu_pressure_gradient(*_dims(n), _p(rho), _p(flags), _p(bf), C.c_float(0.12), C.c_float(1.0), C.c_int(1))
+    assert np.array_equal(np.transpose(bf, (3, 2, 1, 0)), z["bf_force_drive"])
+    bf[:] = 0
+    aux.emu_pressure_gradient(*_dims(n), _p(rho), _p(flags), _p(bf), C.c_float(0.12), C.c_float(0.5), C.c_int(1))
+    assert np.array_equal(np.transpose(bf, (3, 2, 1, 0)), z["bf_mixed_drive"])
+    k_lu, beta = cfg.forchheimer_parameters(); c_darcy, c_forch = cfg.filter_constants()
+    aux.emu_forchheimer(*_dims(n), _p(u), _p(flags), _p(bf), C.c_float(k_lu), C.c_float(beta), C.c_float(c_darcy), C.c_float(c_forch),
+                        C.c_float(0.01 * cfg.SCALE_VELOCITY / cfg.DT))
+    assert np.array_equal(np.transpose(bf, (3, 2, 1, 0)), z["bf_mixed_plus_forchheimer"])
+
+
+@pytest.mark.parametrize("name", ["reference_run_long_air_1000", "reference_run_step_water_default_gravity", "reference_run_openbox"])
+def test_emulated_pipeline_pack_import_step_export(aux, stepper, name):
+    """lbm_pack_flags (+ neighbour masks) -> lbm_import_f -> lbm_step x N (-> lbm_face_bc) -> lbm_export_f, every stage the product's
+    kernel source, against the reference's recorded runs -- 1000 steps, the default-gravity scenario with all clamps
+    saturated, and the open box with the boundary manager's face writes."""
+    from pour_over_coffee_lbm_b200.config import LBMConfig
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    n, steps, gravity = int(z["n"]), int(z["steps"]), float(z["gravity"])
+    open_box = "filter_zone" not in z.files
+    c = R.RefConfig(NX=n, NY=n, NZ=n, GRAVITY_LU=gravity)
+    cfg = LBMConfig(NX=n, NY=n, NZ=n, TAU_FLUID=c.TAU_WATER, TAU_AIR=c.TAU_AIR, GRAVITY_LU=gravity)
+    k_lu, beta_lu = cfg.forchheimer_parameters(); c_darcy, c_forch = cfg.filter_constants()
+    solid = H.to_dev_scalar(z["solid"]).astype(np.uint8)
+    zone = H.to_dev_scalar(z["filter_zone"]).astype(np.int32) if not open_box else np.zeros((n, n, n), np.int32)
+    les = H.to_dev_scalar(z["les_mask"]).astype(np.int32)
+    flags = np.zeros((n, n, n), np.uint8); nbr = np.zeros((n, n, n), np.uint64)
+    aux.emu_pack_flags_and_masks(*_dims(n), C.c_int(0), _p(flags), _p(solid), _p(zone), _p(les), _p(nbr))
+    g = [np.empty((19, n, n, n), np.float32), np.empty((19, n, n, n), np.float32)]
+    f_in = H.to_dev_pop(z["f"])
+    aux.emu_convert_f(*_dims(n), C.c_int(0), _p(f_in), _p(flags), _p(g[0]))
+    g[1][:] = g[0]
+    force, phase = H.to_dev_vec(z["body_force"]), H.to_dev_scalar(z["phase"])
+    rho = np.ones((n, n, n), np.float32); u = [np.zeros((3, n, n, n), np.float32), np.zeros((3, n, n, n), np.float32)]
+    blockage = np.zeros((n, n, n), np.float32)
+    f32 = lambda v: C.c_float(float(v))
+    cur = 0
+    for _ in range(steps):
+        stepper.emu_step_reference(*_dims(n), _p(g[cur]), _p(g[1 - cur]), _p(rho), _p(u[cur]), _p(u[1 - cur]), _p(force), _p(phase), _p(blockage),
+                                   _p(flags), _p(nbr), C.c_int(1), C.c_int(0 if open_box else 1), f32(cfg.TAU_WATER), f32(cfg.TAU_AIR), f32(gravity),
+                                   f32(cfg.LES_CS), f32(0.55), f32(1.90), f32(k_lu), f32(beta_lu), f32(c_darcy), f32(c_forch))
+        cur = 1 - cur
+        if open_box:
+            aux.emu_face_bc(*_dims(n), _p(rho), _p(flags))
+    f_out = np.empty_like(g[cur])
+    aux.emu_convert_f(*_dims(n), C.c_int(1), _p(g[cur]), _p(flags), _p(f_out))
+    fluid = z["solid"] == 0
+    assert np.array_equal(np.transpose(rho, (2, 1, 0))[fluid], z["rho"][fluid])
+    assert np.array_equal(np.transpose(u[cur], (3, 2, 1, 0))[fluid], z["u"][fluid])
+    assert np.array_equal(np.transpose(f_out, (0, 3, 2, 1))[:, fluid], z["f_out"][:, fluid])
