@@ -484,9 +484,36 @@ class CoffeeParticleSystem:
         return out
 
     def compute_two_way_coupling_forces(self, fluid_u=None, relax: float = -1.0):
-        """coffee_particles.py:1107-1154; relax >= 0 also applies the under-relaxation in the same kernel."""
-        particles_couple(self._solver.engine, self.state, self.reaction_force_tensor, relax=relax,
+        """coffee_particles.py:1107-1154; relax >= 0 also applies the under-relaxation in the same kernel.
+        On z-slabs the particle arrays are replicated on every rank and the owner computes (`_couple_on_slab`)."""
+        e = self._solver.engine
+        if e.zghost:
+            self._couple_on_slab(relax)
+            return
+        particles_couple(e, self.state, self.reaction_force_tensor, relax=relax,
                          water_density=self.water_density, water_viscosity=self.water_viscosity)
+
+    def _couple_on_slab(self, relax: float) -> None:
+        """z-slabs: every rank holds all particles; a particle is computed by the rank whose slab holds its base cell.  The
+        kernel is the single-GPU one -- it is handed an `active` array masked to the owned particles.  Around it: ghost planes
+        of u in (trilinear gather reaches one plane up), the top ghost plane of the reaction field out and added to the rank
+        above (scatter reaches one plane up), then one all-reduce per output array so the replicated state stays identical
+        (torch.distributed: NCCL on the device, gloo in tests/test_slab_gloo.py, where the kernel source runs CPU-emulated)."""
+        from . import slab
+        e, st = self._solver.engine, self.state
+        per_z = e.periodic[2]
+        slab.exchange_planes(e.u, e.rank, e.nranks, per_z)
+        active_all = st.active
+        owned = slab.particle_owner_mask(st.pos[2], active_all, e.z0, e.nz, e.nz_global)
+        st.active = owned
+        try:
+            particles_couple(e, st, self.reaction_force_tensor, relax=relax, water_density=self.water_density,
+                             water_viscosity=self.water_viscosity)
+        finally:
+            st.active = active_all
+        slab.reduce_ghost_up(self.reaction_force_tensor, e.rank, e.nranks, per_z)
+        outs = [st.drag_new, st.u_fluid, st.reynolds, st.cd, st.cell] + ([st.drag, st.drag_old] if relax >= 0.0 else [])
+        slab.allreduce_owned(outs, owned, active_all)
 
     def apply_under_relaxation(self, relaxation_factor: float):
         """coffee_particles.py:1200-1212"""

@@ -160,6 +160,54 @@ def exchange_planes(field: torch.Tensor, rank: int, world: int, periodic_z: bool
         plane(k).copy_(buf)
 
 
+def reduce_ghost_up(field: torch.Tensor, rank: int, world: int, periodic_z: bool, group=None) -> None:
+    """Reverse halo for scattered quantities (the particles' reaction force): what a rank deposited in its TOP ghost plane
+    belongs to the first owned plane of the rank above -- send it up, add what arrives from below to plane 1, clear the ghost.
+    (A particle is owned by the slab that holds its base cell, so its eight corners reach one plane up, never down.)"""
+    import torch.distributed as dist
+    zdim = field.dim() - 3
+    nzp = field.shape[zdim]
+    plane = lambda k: field.select(zdim, k)
+    down, up = neighbours(rank, world, periodic_z)
+    if world == 1:
+        if periodic_z:
+            plane(1).add_(plane(nzp - 1))
+        plane(nzp - 1).zero_()
+        return
+    ops, recv = [], None
+    if up is not None:
+        ops.append(dist.P2POp(dist.isend, plane(nzp - 1).contiguous(), up, group))
+    if down is not None:
+        recv = torch.empty_like(plane(1).contiguous())
+        ops.append(dist.P2POp(dist.irecv, recv, down, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    if recv is not None:
+        plane(1).add_(recv)
+    plane(nzp - 1).zero_()
+
+
+def particle_owner_mask(pos_z: torch.Tensor, active: torch.Tensor, z0: int, nz: int, nz_global: int) -> torch.Tensor:
+    """Replicated particles, owner computes: a particle belongs to the slab that holds its base cell
+    k = int(max(0, min(NZ - 2, z))) (coffee_particles.py:1054-1056, the kernel's own formula).  int32 mask: active AND owned."""
+    k = pos_z.clamp(0.0, float(nz_global - 2)).to(torch.int32)
+    owned = (k >= z0) & (k < z0 + nz)
+    return torch.where(owned, active, torch.zeros_like(active))
+
+
+def allreduce_owned(tensors, owned_active: torch.Tensor, active: torch.Tensor, group=None) -> None:
+    """Make the per-particle outputs of the coupling kernel identical on every rank: the owner's value wins (sum over ranks of
+    values masked to the owners), inactive particles keep what they had.  tensors: [n] or [C, n], any dtype all_reduce takes."""
+    import torch.distributed as dist
+    own = owned_active != 0
+    act = active != 0
+    for t in tensors:
+        tmp = torch.where(own, t, torch.zeros_like(t))
+        dist.all_reduce(tmp, op=dist.ReduceOp.SUM, group=group)
+        t.copy_(torch.where(act, tmp, t))
+
+
 def _swap_pairs(n: int) -> List[int]:
     """rank 1 of a 2-rank periodic ring posts its (send,recv) pairs in the opposite neighbour order so that
     message k of rank 0 meets message k of rank 1."""

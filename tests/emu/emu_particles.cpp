@@ -30,10 +30,10 @@ static void run(unsigned n, unsigned block, F &&kernel) {
     for (unsigned b = 0; b < (n + block - 1) / block; ++b)
         for (unsigned t = 0; t < block; ++t) { emu_block_idx = {b, 0, 0}; emu_thread_idx = {t, 0, 0}; kernel(); }
 }
-static Grid make_grid(int nx, int ny, int nz) {
+static Grid make_grid(int nx, int ny, int nz, int zg = 0, int z0 = 0, int nz_global = 0) {
     Grid G{};
-    G.nx = nx; G.ny = ny; G.nz = nz; G.zg = 0; G.nz_global = nz; G.z0 = 0;
-    G.plane = (long long)nx * ny; G.vol = G.plane * nz;
+    G.nx = nx; G.ny = ny; G.nz = nz; G.zg = zg; G.nz_global = nz_global > 0 ? nz_global : nz; G.z0 = z0;
+    G.plane = (long long)nx * ny; G.vol = G.plane * (nz + 2 * zg);
     return G;
 }
 
@@ -41,6 +41,14 @@ extern "C" {
 int emu_particles_couple(int nx, int ny, int nz, const float *u, float *reaction, lbm_particles *ps, float rho_w, float mu_w, float relax) {
     ParticleArgs A{make_grid(nx, ny, nz), u, reaction, *ps, rho_w, mu_w, relax};
     for (long long i = 0; i < A.g.vol * 3; ++i) reaction[i] = 0.0f;          // lbm_particles_couple clears the field first (lbm_api.cu)
+    run((unsigned)ps->n, 256, [&] { particles_couple_kernel(A); });
+    return 0;
+}
+// z-slab: nz owned planes from global plane z0, one ghost plane per side (u and reaction are [3][nz + 2][ny][nx])
+int emu_particles_couple_slab(int nx, int ny, int nz, int z0, int nz_global, const float *u, float *reaction, lbm_particles *ps, float rho_w,
+                              float mu_w, float relax) {
+    ParticleArgs A{make_grid(nx, ny, nz, 1, z0, nz_global), u, reaction, *ps, rho_w, mu_w, relax};
+    for (long long i = 0; i < A.g.vol * 3; ++i) reaction[i] = 0.0f;
     run((unsigned)ps->n, 256, [&] { particles_couple_kernel(A); });
     return 0;
 }

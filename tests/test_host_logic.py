@@ -193,3 +193,33 @@ def test_multiphase_facade_call_sequence_and_lazy_fields():
     assert e.calls == [("ghosts", (6, 4, 4)), ("gradients",), ("ghosts", (3, 6, 4, 4)), ("curvature_force", True),
                        ("ghosts", (6, 4, 4)), ("gradients",), ("ghosts", (3, 6, 4, 4)), ("curvature_force", False),
                        ("ghosts", (6, 4, 4)), ("phase_step",)]
+
+
+def test_particle_coupling_on_a_slab_masks_ownership_and_exchanges(monkeypatch):
+    """CoffeeParticleSystem._couple_on_slab (host logic, stubbed engine): ghost planes of u in, the single-GPU kernel on an
+    `active` array masked to the particles whose base cell lies in the slab, reaction ghost plane up, outputs all-reduced; the
+    replicated `active` array is restored."""
+    import torch
+    from pour_over_coffee_lbm_b200 import physics, slab
+    calls = []
+
+    class Engine:
+        zghost, rank, nranks, z0, nz, nz_global, periodic = 1, 1, 2, 8, 8, 16, (False, False, False)
+        u = torch.zeros(3, 10, 4, 4)
+    class State:
+        pos = torch.tensor([[1.0, 2.0, 3.0, 1.0], [1.0, 2.0, 3.0, 1.0], [2.5, 8.0, 14.9, 15.7]])      # base planes 2, 8, 14, 14 (clamped)
+        active = torch.tensor([1, 1, 0, 1], dtype=torch.int32)
+        drag_new = drag = drag_old = u_fluid = torch.zeros(3, 4); reynolds = cd = torch.zeros(4); cell = torch.zeros(3, 4, dtype=torch.int32)
+    class Solver:
+        engine = Engine()
+
+    ps = object.__new__(physics.CoffeeParticleSystem)
+    ps._solver, ps.state, ps.reaction_force_tensor, ps.water_density, ps.water_viscosity = Solver(), State(), torch.zeros(3, 10, 4, 4), 965.3, 3e-4
+    monkeypatch.setattr(slab, "exchange_planes", lambda t, r, w, p, group=None: calls.append(("ghosts_in", tuple(t.shape))))
+    monkeypatch.setattr(slab, "reduce_ghost_up", lambda t, r, w, p, group=None: calls.append(("ghost_up", tuple(t.shape))))
+    monkeypatch.setattr(slab, "allreduce_owned", lambda ts, own, act, group=None: calls.append(("allreduce", len(ts), own.tolist(), act.tolist())))
+    monkeypatch.setattr(physics, "particles_couple", lambda e, st, react, **kw: calls.append(("kernel", st.active.tolist(), kw["relax"])))
+    ps.compute_two_way_coupling_forces(None, relax=0.8)
+    assert calls == [("ghosts_in", (3, 10, 4, 4)), ("kernel", [0, 1, 0, 1], 0.8), ("ghost_up", (3, 10, 4, 4)),
+                     ("allreduce", 7, [0, 1, 0, 1], [1, 1, 0, 1])]
+    assert ps.state.active.tolist() == [1, 1, 0, 1]

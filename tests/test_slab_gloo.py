@@ -168,3 +168,87 @@ def test_two_gloo_ranks_multiphase_producers_reproduce_the_reference_run(cuts):
     for p in procs:
         assert p.exitcode == 0
     assert out.get(timeout=5) is True
+
+
+# ---- particle coupling on z-slabs: replicated particles, owner computes (emulated kernel source + slab helpers over gloo) ----
+def _particle_worker(rank, world, port, out, cuts):
+    import ctypes as C
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pour_over_coffee_lbm_b200 import slab
+    here = os.path.dirname(os.path.abspath(__file__))
+    emu = C.CDLL(os.path.join(here, "emu", "_build", "libemu_particles.so"))
+    z = np.load(os.path.join(here, "golden", "reference_run_neighbours.npz"))
+    n = int(z["n"]); z0, nz = cuts[rank]
+    cfg = R.RefConfig(NX=n, NY=n, NZ=n)
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+
+    class Particles(C.Structure):
+        _fields_ = [(k, C.c_void_p) for k in ("pos", "vel", "radius", "mass", "active", "drag_new", "drag_old", "drag", "u_fluid", "reynolds", "cd",
+                                              "cell")] + [("n", C.c_int)]
+    npart = z["p_pos"].shape[0]
+    t = lambda a: np.ascontiguousarray(a.T.astype(np.float32))
+    st = dict(pos=t(z["p_pos"]), vel=t(z["p_vel"]), radius=z["p_radius"].copy(), mass=z["p_mass"].copy(), active=z["p_active"].astype(np.int32).copy(),
+              drag_new=np.zeros((3, npart), np.float32), drag_old=t(z["p_drag_old_in"]), drag=np.zeros((3, npart), np.float32),
+              u_fluid=np.zeros((3, npart), np.float32), reynolds=np.zeros(npart, np.float32), cd=np.zeros(npart, np.float32),
+              cell=np.zeros((3, npart), np.int32))
+    # this slab's u with one ghost plane per side: owned planes from the global field, ghosts filled by the exchange
+    u_glob = H.to_dev_vec(z["u"])
+    u = np.ascontiguousarray(np.pad(u_glob[:, z0:z0 + nz], ((0, 0), (1, 1), (0, 0), (0, 0))))
+    slab.exchange_planes(torch.from_numpy(u), rank, world, False)
+    # owner computes: the kernel sees the other slabs' particles as inactive
+    owned = slab.particle_owner_mask(torch.from_numpy(st["pos"][2]), torch.from_numpy(st["active"]), z0, nz, n)
+    masked = owned.numpy().copy()
+    s = Particles(*[P(masked if k == "active" else st[k]) for k in ("pos", "vel", "radius", "mass", "active", "drag_new", "drag_old", "drag", "u_fluid",
+                                                                      "reynolds", "cd", "cell")], npart)
+    react = np.zeros_like(u)
+    emu.emu_particles_couple_slab(C.c_int(n), C.c_int(n), C.c_int(nz), C.c_int(z0), C.c_int(n), P(u), P(react), C.byref(s),
+                                  C.c_float(np.float32(cfg.WATER_DENSITY_90C)), C.c_float(np.float32(cfg.WATER_VISCOSITY_90C * cfg.WATER_DENSITY_90C)),
+                                  C.c_float(0.8))
+    slab.reduce_ghost_up(torch.from_numpy(react), rank, world, False)
+    outs = [torch.from_numpy(st[k]) for k in ("drag_new", "drag_old", "drag", "u_fluid", "reynolds", "cd", "cell")]
+    slab.allreduce_owned(outs, owned, torch.from_numpy(st["active"]))
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (z0, react[:, 1:-1].copy(), {k: st[k].copy() for k in ("drag_new", "drag_old", "drag", "u_fluid", "reynolds", "cd", "cell")},
+                                      int((masked != 0).sum())))
+    if rank == 0:
+        parts = sorted(gathered, key=lambda g: g[0])
+        react_full = np.transpose(np.concatenate([p[1] for p in parts], axis=1), (3, 2, 1, 0))
+        act = z["p_active"] != 0
+        ok = all(all(np.array_equal(p[2][k], parts[0][2][k]) for k in parts[0][2]) for p in parts)            # replicated state is consistent
+        o = parts[0][2]
+        ok &= np.array_equal(o["u_fluid"].T[act], z["p_u_fluid"][act]) and np.array_equal(o["reynolds"][act], z["p_reynolds"][act])
+        ok &= bool(np.allclose(o["drag_new"].T[act], z["p_drag_new"][act], rtol=1e-6, atol=0))
+        ok &= bool(np.allclose(o["drag"].T[act], z["p_drag"][act], rtol=1e-6, atol=1e-16) and np.allclose(o["drag_old"].T[act], z["p_drag_old_out"][act], rtol=1e-6, atol=1e-16))
+        ok &= np.array_equal(o["cell"].T[act], np.stack(R.particle_cell_and_weights(cfg, z["p_pos"])[:3], 1)[act])
+        ok &= bool(np.allclose(react_full, z["p_reaction"], rtol=1e-5, atol=1e-12))
+        ok &= sum(p[3] for p in parts) == int(act.sum()) and all(p[3] > 0 for p in parts)                       # every active particle has exactly one owner
+        out.put(bool(ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("cuts", [((0, 8), (8, 8)), ((0, 11), (11, 5))], ids=["equal", "unequal"])
+def test_two_gloo_ranks_particle_coupling_reproduces_the_reference_run(cuts):
+    """Two-way coupling on two z-slabs with replicated particles: each rank runs the coupling kernel (CPU-emulated source) on
+    the particles whose base cell it owns (slab.particle_owner_mask hands the kernel a masked `active` array -- the kernel is
+    unchanged), gathers u through a ghost plane, deposits reaction into its top ghost plane; slab.reduce_ghost_up moves that
+    plane to the rank above, slab.allreduce_owned makes the per-particle outputs identical everywhere.  Result = the recorded
+    single-domain run of the reference (scatter sums within rounding)."""
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    lib = os.path.join(here, "emu", "_build", "libemu_particles.so"); src = os.path.join(here, "emu", "emu_particles.cpp")
+    kern = os.path.join(os.path.dirname(here), "pour_over_coffee_lbm_b200", "csrc", "lbm_particles.cu")
+    os.makedirs(os.path.dirname(lib), exist_ok=True)
+    if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(src), os.path.getmtime(kern)):
+        subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-w", "-shared", "-fPIC", "-I/usr/local/cuda/include",
+                        "-include", "algorithm", src, "-o", lib], check=True)
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_particle_worker, args=(r, 2, port, out, cuts)) for r in range(2)]
+    for p in procs: p.start()
+    for p in procs: p.join(timeout=240)
+    for p in procs:
+        assert p.exitcode == 0
+    assert out.get(timeout=5) is True
