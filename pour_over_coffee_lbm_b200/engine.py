@@ -444,6 +444,29 @@ def particles_couple(engine: D3Q19Engine, ps: ParticleState, reaction: torch.Ten
                                                   float(mu_w), float(relax), engine.stream), "lbm_particles_couple")
 
 
+def particles_couple_slab(engine: D3Q19Engine, ps: ParticleState, reaction: torch.Tensor, relax: float = 0.8,
+                          water_density: Optional[float] = None, water_viscosity: Optional[float] = None):
+    """Two-way coupling on a z-slab engine: every rank holds all particles; a particle is computed by the rank whose slab holds
+    its base cell.  The kernel is the single-GPU one -- it is handed an `active` array masked to the owned particles.  Around
+    it: ghost planes of u in (the trilinear gather reaches one plane up), the top ghost plane of the reaction field out and
+    added to the rank above (the scatter reaches one plane up), then one all-reduce per output array so that the replicated
+    state stays identical (torch.distributed: NCCL on the device, gloo in tests/test_slab_gloo.py, where the kernel source runs
+    CPU-emulated)."""
+    from . import slab
+    per_z = engine.periodic[2]
+    slab.exchange_planes(engine.u, engine.rank, engine.nranks, per_z)
+    active_all = ps.active
+    owned = slab.particle_owner_mask(ps.pos[2], active_all, engine.z0, engine.nz, engine.nz_global)
+    ps.active = owned
+    try:
+        particles_couple(engine, ps, reaction, relax=relax, water_density=water_density, water_viscosity=water_viscosity)
+    finally:
+        ps.active = active_all
+    slab.reduce_ghost_up(reaction, engine.rank, engine.nranks, per_z)
+    outs = [ps.drag_new, ps.u_fluid, ps.reynolds, ps.cd, ps.cell] + ([ps.drag, ps.drag_old] if relax >= 0.0 else [])
+    slab.allreduce_owned(outs, owned, active_all)
+
+
 def particles_advance(engine: D3Q19Engine, ps: ParticleState, dt: float, center_x: float, center_y: float, bottom_z: float,
                       bottom_radius_lu: float, top_radius_lu: float, force: Optional[torch.Tensor] = None,
                       counters: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -497,26 +497,10 @@ class CoffeeParticleSystem:
                          water_density=self.water_density, water_viscosity=self.water_viscosity)
 
     def _couple_on_slab(self, relax: float) -> None:
-        """z-slabs: every rank holds all particles; a particle is computed by the rank whose slab holds its base cell.  The
-        kernel is the single-GPU one -- it is handed an `active` array masked to the owned particles.  Around it: ghost planes
-        of u in (trilinear gather reaches one plane up), the top ghost plane of the reaction field out and added to the rank
-        above (scatter reaches one plane up), then one all-reduce per output array so the replicated state stays identical
-        (torch.distributed: NCCL on the device, gloo in tests/test_slab_gloo.py, where the kernel source runs CPU-emulated)."""
-        from . import slab
-        e, st = self._solver.engine, self.state
-        per_z = e.periodic[2]
-        slab.exchange_planes(e.u, e.rank, e.nranks, per_z)
-        active_all = st.active
-        owned = slab.particle_owner_mask(st.pos[2], active_all, e.z0, e.nz, e.nz_global)
-        st.active = owned
-        try:
-            particles_couple(e, st, self.reaction_force_tensor, relax=relax, water_density=self.water_density,
-                             water_viscosity=self.water_viscosity)
-        finally:
-            st.active = active_all
-        slab.reduce_ghost_up(self.reaction_force_tensor, e.rank, e.nranks, per_z)
-        outs = [st.drag_new, st.u_fluid, st.reynolds, st.cd, st.cell] + ([st.drag, st.drag_old] if relax >= 0.0 else [])
-        slab.allreduce_owned(outs, owned, active_all)
+        """z-slabs: replicated particles, owner computes (engine.particles_couple_slab)."""
+        from .engine import particles_couple_slab
+        particles_couple_slab(self._solver.engine, self.state, self.reaction_force_tensor, relax=relax, water_density=self.water_density,
+                              water_viscosity=self.water_viscosity)
 
     def apply_under_relaxation(self, relaxation_factor: float):
         """coffee_particles.py:1200-1212"""

@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--size", dest="n", type=int, default=1024); ap.add_argument("--size-z", dest="nz", type=int, default=0)
     ap.add_argument("--steps", type=int, default=30); ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--equal", action="store_true", help="equal-thickness slabs instead of fluid-balanced ones")
+    ap.add_argument("--particles", type=int, default=0, help="BASELINE configs[4]: N coffee particles, two-way coupled every step (replicated "
+                    "on every rank, owner computes; engine.particles_couple_slab -- written at the end of round 1, first GPU run is round 2's)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -52,12 +54,32 @@ def main():
         eng.halo_exchange()
     fluid = eng.fluid_cells()
 
+    ps = react = None
+    if args.particles > 0:
+        from pour_over_coffee_lbm_b200.engine import ParticleState, particles_couple, particles_couple_slab
+        ps = ParticleState(args.particles, eng.device)
+        gp = torch.Generator(device="cuda"); gp.manual_seed(42)                      # the same particles on every rank
+        ps.pos[0].uniform_(0.35 * n, 0.65 * n, generator=gp); ps.pos[1].uniform_(0.35 * n, 0.65 * n, generator=gp)
+        ps.pos[2].uniform_(6.0, 0.45 * nzg, generator=gp)
+        ps.radius.fill_(3.25e-4); ps.mass.fill_(float(4.0 / 3.0 * 3.14159 * 3.25e-4 ** 3 * 1200.0)); ps.active.fill_(1)
+        react = torch.zeros_like(eng.u)
+
+    def coupled_step():
+        eng.clear_body_force()
+        if world > 1: particles_couple_slab(eng, ps, react, relax=0.8)
+        else: particles_couple(eng, ps, react, relax=0.8)
+        eng.add_reaction_force(react)
+        eng.step(1, write_macro_every=1)                                             # the coupling reads this step's u
+
     def timed(steps):
         if world > 1: dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        eng.step(steps, write_macro_every=0)
+        if ps is None:
+            eng.step(steps, write_macro_every=0)
+        else:
+            for _ in range(steps): coupled_step()
         e1.record()
         torch.cuda.synchronize()
         if world > 1: dist.barrier()
@@ -81,7 +103,8 @@ def main():
         except Exception:
             pass
         bytes_ = tot_fluid * 165 + (cells - tot_fluid)
-        print(json.dumps({"config": f"V60 {n}x{n}x{nzg}, all features, z-slabs", "n_gpus": world, "ms_per_step": ms_max,
+        print(json.dumps({"config": f"V60 {n}x{n}x{nzg}, all features, z-slabs" + (f", {args.particles} particles two-way coupled" if args.particles else ""),
+                          "n_gpus": world, "ms_per_step": ms_max,
                           "MLUPS": cells / ms_max / 1e3, "MFLUPS": tot_fluid / ms_max / 1e3, "fluid_fraction": tot_fluid / cells,
                           "partition": "equal thickness" if (args.equal or world == 1) else "fluid-balanced", "per_rank_ms": [round(x, 4) for x in per_ms], "per_rank_fluid_Mcells": [round(x / 1e6, 2) for x in per_fluid],
                           "slab_imbalance_max_over_mean": max(per_fluid) / (tot_fluid / world),

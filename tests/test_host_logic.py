@@ -200,7 +200,7 @@ def test_particle_coupling_on_a_slab_masks_ownership_and_exchanges(monkeypatch):
     `active` array masked to the particles whose base cell lies in the slab, reaction ghost plane up, outputs all-reduced; the
     replicated `active` array is restored."""
     import torch
-    from pour_over_coffee_lbm_b200 import physics, slab
+    from pour_over_coffee_lbm_b200 import engine as engine_mod, physics, slab
     calls = []
 
     class Engine:
@@ -218,7 +218,7 @@ def test_particle_coupling_on_a_slab_masks_ownership_and_exchanges(monkeypatch):
     monkeypatch.setattr(slab, "exchange_planes", lambda t, r, w, p, group=None: calls.append(("ghosts_in", tuple(t.shape))))
     monkeypatch.setattr(slab, "reduce_ghost_up", lambda t, r, w, p, group=None: calls.append(("ghost_up", tuple(t.shape))))
     monkeypatch.setattr(slab, "allreduce_owned", lambda ts, own, act, group=None: calls.append(("allreduce", len(ts), own.tolist(), act.tolist())))
-    monkeypatch.setattr(physics, "particles_couple", lambda e, st, react, **kw: calls.append(("kernel", st.active.tolist(), kw["relax"])))
+    monkeypatch.setattr(engine_mod, "particles_couple", lambda e, st, react, **kw: calls.append(("kernel", st.active.tolist(), kw["relax"])))
     ps.compute_two_way_coupling_forces(None, relax=0.8)
     assert calls == [("ghosts_in", (3, 10, 4, 4)), ("kernel", [0, 1, 0, 1], 0.8), ("ghost_up", (3, 10, 4, 4)),
                      ("allreduce", 7, [0, 1, 0, 1], [1, 1, 0, 1])]
