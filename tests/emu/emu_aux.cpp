@@ -95,6 +95,11 @@ int emu_forchheimer(int nx, int ny, int nz, const float *u, const uint8_t *flags
     run(dim3((unsigned)((G.vol + b - 1) / b), 1, 1), b, [&] { forchheimer_force_kernel(G, u, flags, bf, K, beta, c_darcy, c_forch, fmax); });
     return 0;
 }
+int emu_bounce_slots(int nx, int ny, int nz, int periodic, float *g, const uint8_t *flags, const unsigned long long *nbr) {
+    const Grid G = make_grid(nx, ny, nz, periodic);
+    run_stride([&] { bounce_slots_kernel(G, g, flags, nbr, 0, nz); });
+    return 0;
+}
 int emu_add_reaction(int nx, int ny, int nz, const float *reaction, const uint8_t *flags, float *bf) {
     const Grid G = make_grid(nx, ny, nz);
     run_stride([&] { add_reaction_kernel(G, reaction, flags, bf); });

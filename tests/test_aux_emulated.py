@@ -188,3 +188,63 @@ def test_emulated_pipeline_on_random_ragged_boxes_matches_the_oracle(aux, steppe
     assert np.array_equal(np.transpose(rho, (2, 1, 0))[fluid], st.rho[fluid], equal_nan=True)
     assert np.array_equal(np.transpose(f_out, (0, 3, 2, 1))[:, fluid], st.f[:, fluid], equal_nan=True)
     assert np.isfinite(st.u[fluid]).all() and (st.filter_zone == 1).sum() > 20
+
+
+# ---- compat = physical behind walls: phys_walls_kernel<VEC = 1> + phys_finish (write-side bounce-back) ------------------------
+@pytest.fixture(scope="module")
+def walls():
+    return _build("emu_step_walls_physical", ["lbm_phys.cuh", "lbm_common.cuh"])
+
+
+def _walls_case(aux, walls, shape, periodic, solid, zone, les_mask, phase, bf, rho0, u0, steps, p):
+    nx, ny, nz = shape
+    dims = (C.c_int(nx), C.c_int(ny), C.c_int(nz))
+    per = (1 if periodic[0] else 0) | (2 if periodic[1] else 0) | (4 if periodic[2] else 0)
+    g = R.init_equilibrium_phys(rho0, u0)
+    d_solid = H.to_dev_scalar(solid); d_zone = H.to_dev_scalar(zone.astype(np.int32)); d_les = H.to_dev_scalar(les_mask.astype(np.int32))
+    flags = np.zeros((nz, ny, nx), np.uint8); nbr = np.zeros((nz, ny, nx), np.uint64)
+    aux.emu_pack_flags_and_masks(*dims, C.c_int(per), _p(flags), _p(d_solid), _p(d_zone), _p(d_les), _p(nbr))
+    b = [H.to_dev_pop(g), None]
+    aux.emu_bounce_slots(*dims, C.c_int(per), _p(b[0]), _p(flags), _p(nbr))          # what the engine does before the first step
+    b[1] = b[0].copy()
+    rho = np.zeros((nz, ny, nx), np.float32); u = np.zeros((3, nz, ny, nx), np.float32)
+    f32 = lambda v: C.c_float(float(v))
+    cur = walls.emu_step_walls_physical(*dims, C.c_int(per), C.c_int(steps), _p(b[0]), _p(b[1]), _p(rho), _p(u),
+                                        _p(H.to_dev_vec(bf)) if bf is not None else None, _p(H.to_dev_scalar(phase)) if phase is not None else None,
+                                        _p(flags), _p(nbr), C.c_int(int(p.les)), C.c_int(int(p.porous)), f32(p.tau_water), f32(p.tau_air),
+                                        f32(p.gravity_lu), f32(p.cs_smag), f32(p.tau_min), f32(p.tau_max), f32(p.porous_darcy), f32(p.porous_forch))
+    for _ in range(steps):
+        g, rho_o, u_o = R.step_physical(g, p, solid=solid, body_force=bf, phase=phase, filter_zone=zone, les_mask=les_mask)
+    fluid = solid == 0
+    assert np.array_equal(np.transpose(b[cur], (0, 3, 2, 1))[:, fluid], g[:, fluid])
+    assert np.array_equal(np.transpose(rho, (2, 1, 0))[fluid], rho_o[fluid]) and np.array_equal(np.transpose(u, (3, 2, 1, 0))[fluid], u_o[fluid])
+
+
+def test_emulated_physical_walls_kernel_v60_all_features(aux, walls):
+    """The BASELINE configs[2] family at 32^3: V60 mask, force, phase, local-stress LES, Guo-Zhao drag in the filter zone; the
+    emulated one-cell walls kernel (pull + write-side bounce-back) against oracle.step_physical, bit for bit, 12 steps."""
+    n, steps = 32, 12
+    cfg = R.RefConfig(NX=n, NY=n, NZ=n)
+    solid = R.v60_solid(cfg); zone = R.filter_zones(cfg); les_mask = np.where(zone == 1, 0, 1).astype(np.int32)
+    rng = np.random.default_rng(11)
+    phase = np.zeros((n, n, n), np.float32); phase[:, :, : int(0.6 * n)] = 1.0
+    bf = (2e-5 * rng.standard_normal((n, n, n, 3))).astype(np.float32)
+    u0 = H.smooth_velocity(n, 0.02, 11); rho0 = H.smooth_density(n, 0.01, 11)
+    p = R.PhysParams(nx=n, ny=n, nz=n, tau_water=0.53, tau_air=0.8, gravity_lu=1e-5, periodic=(False, False, False), use_force=True,
+                     use_phase=True, les=True, porous=True, porous_darcy=0.37, porous_forch=0.9)
+    _walls_case(aux, walls, (n, n, n), (False, False, False), solid, zone, les_mask, phase, bf, rho0, u0, steps, p)
+
+
+@pytest.mark.parametrize("periodic", [(True, True, True), (True, False, True), (False, False, False)])
+def test_emulated_physical_walls_kernel_obstacles_on_open_and_periodic_faces(aux, walls, periodic):
+    """Obstacles touching open and periodic faces of a ragged box (nx = 27: a partial warp-tile): wrap in the pull, wrap of the
+    write-side bounce-back targets, w_q inflow on open faces."""
+    nx, ny, nz, steps = 27, 10, 12, 8
+    rng = np.random.default_rng(5)
+    solid = np.zeros((nx, ny, nz), np.uint8)
+    solid[0:3, 2:5, 3:6] = 1; solid[nx - 2:, 6:9, 0:2] = 1; solid[10:14, 0:2, nz - 2:] = 1; solid[12:15, 4:7, 5:8] = 1
+    solid |= (rng.random((nx, ny, nz)) < 0.05).astype(np.uint8)
+    zone = np.zeros((nx, ny, nz), np.int32); les_mask = np.ones((nx, ny, nz), np.int32)
+    u0 = H.smooth_velocity(nx, 0.03, 8, nz=nz, ny=ny); rho0 = H.smooth_density(nx, 0.01, 8, nz=nz, ny=ny)
+    p = R.PhysParams(nx=nx, ny=ny, nz=nz, tau_water=0.6, periodic=periodic, les=True)
+    _walls_case(aux, walls, (nx, ny, nz), periodic, solid, zone, les_mask, None, None, rho0, u0, steps, p)
