@@ -103,3 +103,30 @@ def assert_fast_build_close(got, ref, scale, tol=1e-5, what=""):
     got = np.asarray(got, np.float64); ref = np.asarray(ref, np.float64)
     err = float(np.abs(got - ref).max()) / scale
     assert err <= tol, f"{what}: max|d|/scale = {err:.3e} > {tol}"
+
+
+# ---- CPU emulation of product kernel source (tests/emu) ---------------------------------------------------------------
+def build_emu(name, kernel_files):
+    """Compile tests/emu/<name>.cpp -- a harness that #includes product CUDA source and runs it thread by thread -- with the
+    host compiler and return the ctypes handle.  Rebuilt when the harness or any of `kernel_files` (under csrc/) is newer.
+    Skips the calling test when there is no g++ or no CUDA headers (the emulation is extra coverage, not the parity proof)."""
+    import ctypes
+    import os
+    import shutil
+    import subprocess
+    import pytest
+    here = os.path.dirname(os.path.abspath(__file__))
+    csrc = os.path.join(os.path.dirname(here), "pour_over_coffee_lbm_b200", "csrc")
+    src = os.path.join(here, "emu", name + ".cpp")
+    lib = os.path.join(here, "emu", "_build", "lib" + name + ".so")
+    inc = os.environ.get("CUDA_HOME", "/usr/local/cuda") + "/include"
+    if shutil.which("g++") is None or not os.path.exists(os.path.join(inc, "cuda_runtime.h")):
+        pytest.skip("kernel-source emulation needs g++ and the CUDA headers")
+    os.makedirs(os.path.dirname(lib), exist_ok=True)
+    deps = [src] + [os.path.join(csrc, f) for f in kernel_files]
+    if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(d) for d in deps):
+        tmp = lib + f".{os.getpid()}.tmp"
+        subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-w", "-shared", "-fPIC", "-I" + inc, "-include", "algorithm",
+                        src, "-o", tmp], check=True)
+        os.replace(tmp, lib)
+    return ctypes.CDLL(lib)

@@ -20,13 +20,7 @@ CSRC = os.path.join(os.path.dirname(HERE), "pour_over_coffee_lbm_b200", "csrc")
 
 
 def _build(name, deps):
-    src = os.path.join(HERE, "emu", name + ".cpp"); lib = os.path.join(HERE, "emu", "_build", "lib" + name + ".so")
-    os.makedirs(os.path.dirname(lib), exist_ok=True)
-    deps = [src] + [os.path.join(CSRC, d) for d in deps]
-    if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(d) for d in deps):
-        subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-w", "-shared", "-fPIC", "-I/usr/local/cuda/include",
-                        "-include", "algorithm", src, "-o", lib], check=True)
-    return C.CDLL(lib)
+    return H.build_emu(name, deps)
 
 
 @pytest.fixture(scope="module")

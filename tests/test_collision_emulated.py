@@ -21,12 +21,7 @@ CSRC = os.path.join(os.path.dirname(HERE), "pour_over_coffee_lbm_b200", "csrc")
 
 @pytest.fixture(scope="module")
 def emu():
-    os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    deps = [SRC, os.path.join(CSRC, "lbm_phys.cuh"), os.path.join(CSRC, "lbm_common.cuh")]
-    if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(d) for d in deps):
-        subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-w", "-shared", "-fPIC", "-I/usr/local/cuda/include",
-                        "-include", "algorithm", SRC, "-o", LIB], check=True)
-    return C.CDLL(LIB)
+    return H.build_emu("emu_collision", ['lbm_phys.cuh', 'lbm_common.cuh'])
 
 
 def _p(a):

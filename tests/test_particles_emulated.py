@@ -30,11 +30,7 @@ class Bounds(C.Structure):             # include/lbm_b200.h: lbm_particle_bounds
 
 @pytest.fixture(scope="module")
 def emu():
-    os.makedirs(os.path.dirname(EMU_LIB), exist_ok=True)
-    if not os.path.exists(EMU_LIB) or os.path.getmtime(EMU_LIB) < max(os.path.getmtime(EMU_SRC), os.path.getmtime(KERNELS)):
-        subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-w", "-shared", "-fPIC", "-I/usr/local/cuda/include",
-                        "-include", "algorithm", EMU_SRC, "-o", EMU_LIB], check=True)
-    return C.CDLL(EMU_LIB)
+    return H.build_emu("emu_particles", ['lbm_particles.cu', 'lbm_common.cuh'])
 
 
 def _p(a):

@@ -25,12 +25,7 @@ KERNELS = os.path.join(os.path.dirname(HERE), "pour_over_coffee_lbm_b200", "csrc
 
 @pytest.fixture(scope="module")
 def emu():
-    os.makedirs(os.path.dirname(EMU_LIB), exist_ok=True)
-    stale = not os.path.exists(EMU_LIB) or os.path.getmtime(EMU_LIB) < max(os.path.getmtime(EMU_SRC), os.path.getmtime(KERNELS))
-    if stale:
-        subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-w", "-shared", "-fPIC", "-I/usr/local/cuda/include",
-                        "-include", "algorithm", EMU_SRC, "-o", EMU_LIB], check=True)
-    return C.CDLL(EMU_LIB)
+    return H.build_emu("emu_producers", ['lbm_producers.cu', 'lbm_common.cuh'])
 
 
 def _p(a):

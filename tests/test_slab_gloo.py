@@ -151,14 +151,7 @@ def test_two_gloo_ranks_multiphase_producers_reproduce_the_reference_run(cuts):
     """The surface-tension chain and the phase-field step on two z-slabs (ghost planes of phi, mu and -- between the two
     launches -- normal filled by slab.exchange_planes over gloo): the gathered slabs equal the recorded single-domain run of
     the reference bit for bit.  The device kernels run as CPU-emulated source (tests/emu)."""
-    import subprocess
-    here = os.path.dirname(os.path.abspath(__file__))
-    lib = os.path.join(here, "emu", "_build", "libemu_producers.so"); src = os.path.join(here, "emu", "emu_producers.cpp")
-    kern = os.path.join(os.path.dirname(here), "pour_over_coffee_lbm_b200", "csrc", "lbm_producers.cu")
-    os.makedirs(os.path.dirname(lib), exist_ok=True)
-    if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(src), os.path.getmtime(kern)):
-        subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-w", "-shared", "-fPIC", "-I/usr/local/cuda/include",
-                        "-include", "algorithm", src, "-o", lib], check=True)
+    H.build_emu("emu_producers", ["lbm_producers.cu", "lbm_common.cuh"])
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
@@ -235,14 +228,7 @@ def test_two_gloo_ranks_particle_coupling_reproduces_the_reference_run(cuts):
     unchanged), gathers u through a ghost plane, deposits reaction into its top ghost plane; slab.reduce_ghost_up moves that
     plane to the rank above, slab.allreduce_owned makes the per-particle outputs identical everywhere.  Result = the recorded
     single-domain run of the reference (scatter sums within rounding)."""
-    import subprocess
-    here = os.path.dirname(os.path.abspath(__file__))
-    lib = os.path.join(here, "emu", "_build", "libemu_particles.so"); src = os.path.join(here, "emu", "emu_particles.cpp")
-    kern = os.path.join(os.path.dirname(here), "pour_over_coffee_lbm_b200", "csrc", "lbm_particles.cu")
-    os.makedirs(os.path.dirname(lib), exist_ok=True)
-    if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(src), os.path.getmtime(kern)):
-        subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-w", "-shared", "-fPIC", "-I/usr/local/cuda/include",
-                        "-include", "algorithm", src, "-o", lib], check=True)
+    H.build_emu("emu_particles", ["lbm_particles.cu", "lbm_common.cuh"])
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()

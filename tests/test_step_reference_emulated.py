@@ -29,12 +29,7 @@ FILES = sorted(glob.glob(os.path.join(GOLD, "reference_run_step_*.npz"))) + [os.
 
 @pytest.fixture(scope="module")
 def emu():
-    os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("lbm_step_kernel.cuh", "lbm_phys.cuh", "lbm_common.cuh")]
-    if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(d) for d in deps):
-        subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-w", "-shared", "-fPIC", "-I/usr/local/cuda/include",
-                        "-include", "algorithm", SRC, "-o", LIB], check=True)
-    return C.CDLL(LIB)
+    return H.build_emu("emu_step_reference", ['lbm_step_kernel.cuh', 'lbm_phys.cuh', 'lbm_common.cuh'])
 
 
 def _p(a):
