@@ -6,7 +6,6 @@ pipeline lbm_pack_flags -> lbm_import_f -> lbm_step x N -> lbm_export_f as emula
 recording.  Test infrastructure only."""
 import ctypes as C
 import os
-import subprocess
 
 import numpy as np
 import pytest
@@ -16,7 +15,6 @@ from oracle import d3q19_ref as R
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = os.path.join(HERE, "golden")
-CSRC = os.path.join(os.path.dirname(HERE), "pour_over_coffee_lbm_b200", "csrc")
 
 
 def _build(name, deps):

@@ -5,7 +5,6 @@ oracle/d3q19_ref.py:step_physical.  Bit for bit, several steps, every feature co
 device.)  Test infrastructure only."""
 import ctypes as C
 import os
-import subprocess
 
 import numpy as np
 import pytest
@@ -14,9 +13,6 @@ import helpers as H
 from oracle import d3q19_ref as R
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = os.path.join(HERE, "emu", "emu_collision.cpp")
-LIB = os.path.join(HERE, "emu", "_build", "libemu_collision.so")
-CSRC = os.path.join(os.path.dirname(HERE), "pour_over_coffee_lbm_b200", "csrc")
 
 
 @pytest.fixture(scope="module")

@@ -3,7 +3,6 @@
 use.  See tests/test_producers_emulated.py for why.  Test infrastructure only."""
 import ctypes as C
 import os
-import subprocess
 
 import numpy as np
 import pytest
@@ -13,9 +12,6 @@ from oracle import d3q19_ref as R
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = os.path.join(HERE, "golden")
-EMU_SRC = os.path.join(HERE, "emu", "emu_particles.cpp")
-EMU_LIB = os.path.join(HERE, "emu", "_build", "libemu_particles.so")
-KERNELS = os.path.join(os.path.dirname(HERE), "pour_over_coffee_lbm_b200", "csrc", "lbm_particles.cu")
 
 
 class Particles(C.Structure):          # include/lbm_b200.h: lbm_particles

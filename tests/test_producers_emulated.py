@@ -8,7 +8,6 @@ emulation library is never on the product path.
 """
 import ctypes as C
 import os
-import subprocess
 
 import numpy as np
 import pytest
@@ -18,9 +17,6 @@ import helpers as H
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = os.path.join(HERE, "golden", "reference_run_multiphase.npz")
 GOLD_FP = os.path.join(HERE, "golden", "reference_run_filter_particles.npz")
-EMU_SRC = os.path.join(HERE, "emu", "emu_producers.cpp")
-EMU_LIB = os.path.join(HERE, "emu", "_build", "libemu_producers.so")
-KERNELS = os.path.join(os.path.dirname(HERE), "pour_over_coffee_lbm_b200", "csrc", "lbm_producers.cu")
 
 
 @pytest.fixture(scope="module")

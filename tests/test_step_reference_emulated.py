@@ -11,7 +11,6 @@ between the loads and the stores is the product's statement sequence.  Test infr
 import ctypes as C
 import glob
 import os
-import subprocess
 
 import numpy as np
 import pytest
@@ -21,9 +20,6 @@ from oracle import d3q19_ref as R
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = os.path.join(HERE, "golden")
-SRC = os.path.join(HERE, "emu", "emu_step_reference.cpp")
-LIB = os.path.join(HERE, "emu", "_build", "libemu_step_reference.so")
-CSRC = os.path.join(os.path.dirname(HERE), "pour_over_coffee_lbm_b200", "csrc")
 FILES = sorted(glob.glob(os.path.join(GOLD, "reference_run_step_*.npz"))) + [os.path.join(GOLD, "reference_run_long_air_1000.npz")]
 
 
