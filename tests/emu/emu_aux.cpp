@@ -43,11 +43,11 @@ static void run(dim3 grid, unsigned block, F &&kernel) {
                 for (unsigned t = 0; t < block; ++t) { emu_block_idx = {bx, by, bz}; emu_thread_idx = {t, 0, 0}; kernel(); }
 }
 template <class F> static void run_stride(F &&kernel) { run(dim3(1, 1, 1), 1, kernel); }     // grid-stride loop: one thread walks everything
-static Grid make_grid(int nx, int ny, int nz, int periodic = 0) {
+static Grid make_grid(int nx, int ny, int nz, int periodic = 0, int zg = 0, int z0 = 0, int nz_global = 0) {
     Grid G{};
-    G.nx = nx; G.ny = ny; G.nz = nz; G.zg = 0; G.nz_global = nz; G.z0 = 0;
+    G.nx = nx; G.ny = ny; G.nz = nz; G.zg = zg; G.nz_global = nz_global > 0 ? nz_global : nz; G.z0 = z0;
     G.per_x = periodic & 1; G.per_y = (periodic >> 1) & 1; G.per_z = (periodic >> 2) & 1;
-    G.plane = (long long)nx * ny; G.vol = G.plane * nz;
+    G.plane = (long long)nx * ny; G.vol = G.plane * (nz + 2 * zg);
     return G;
 }
 
@@ -66,6 +66,20 @@ int emu_pack_flags_and_masks(int nx, int ny, int nz, int periodic, uint8_t *flag
 }
 int emu_convert_f(int nx, int ny, int nz, int to_reference_f, const float *in, const uint8_t *flags, float *out) {
     const Grid G = make_grid(nx, ny, nz);
+    if (to_reference_f) run_stride([&] { convert_f_kernel<true>(G, in, flags, out); });
+    else run_stride([&] { convert_f_kernel<false>(G, in, flags, out); });
+    return 0;
+}
+// z-slab variants (one ghost plane per side; fields are [nz + 2][ny][nx]; the ghost planes of `solid` hold the neighbours' mask)
+int emu_slab_pack_flags_and_masks(int nx, int ny, int nz, int z0, int nz_global, uint8_t *flags, const uint8_t *solid, const int32_t *zone,
+                                  const int32_t *les, unsigned long long *nbr) {
+    const Grid G = make_grid(nx, ny, nz, 0, 1, z0, nz_global);
+    run_stride([&] { pack_flags_kernel(G, flags, solid, zone, les); });
+    run_stride([&] { neighbour_mask_kernel(G, flags, nbr); });
+    return 0;
+}
+int emu_slab_convert_f(int nx, int ny, int nz, int z0, int nz_global, int to_reference_f, const float *in, const uint8_t *flags, float *out) {
+    const Grid G = make_grid(nx, ny, nz, 0, 1, z0, nz_global);
     if (to_reference_f) run_stride([&] { convert_f_kernel<true>(G, in, flags, out); });
     else run_stride([&] { convert_f_kernel<false>(G, in, flags, out); });
     return 0;

@@ -40,6 +40,26 @@ static void run(const StepArgs &P) {
                 step_cells<LBM_COMPAT_REFERENCE, MODE_BULK, true, LES, POROUS, 1, true>(P, x, y, z, true, (unsigned)(x & 31));
 }
 
+extern "C" int emu_step_reference_slab(int nx, int ny, int nz, int z0, int nz_global, const float *src, float *dst, float *rho, const float *u_src,
+                                       float *u_dst, const float *force, const float *phase, const float *blockage, const uint8_t *flags,
+                                       const unsigned long long *nbr, int les, int porous, float tau_water, float tau_air, float gravity_lu,
+                                       float cs_smag, float tau_min, float tau_max, float K_lu, float beta_lu, float c_darcy, float c_forch) {
+    StepArgs P{};
+    P.g.nx = nx; P.g.ny = ny; P.g.nz = nz; P.g.zg = 1; P.g.nz_global = nz_global; P.g.z0 = z0;
+    P.g.per_x = P.g.per_y = P.g.per_z = 0;
+    P.g.plane = (long long)nx * ny; P.g.vol = P.g.plane * (nz + 2);
+    P.src = src; P.dst = dst; P.rho = rho; P.u_src = u_src; P.u_dst = u_dst; P.force = force; P.phase = phase; P.blockage = blockage;
+    P.flags = flags; P.nbr = nbr; P.write_macro = 1;
+    P.tau_water = tau_water; P.tau_air = tau_air; P.gravity_lu = gravity_lu; P.tau_min = tau_min; P.tau_max = tau_max;
+    P.les_k = (cs_smag * 1.0f) * (cs_smag * 1.0f);
+    P.K_lu = K_lu; P.beta_lu = beta_lu; P.c_darcy = c_darcy; P.c_forch = c_forch;
+    if (les && porous) run<true, true>(P);
+    else if (les) run<true, false>(P);
+    else if (porous) run<false, true>(P);
+    else run<false, false>(P);
+    return 0;
+}
+
 extern "C" int emu_step_reference(int nx, int ny, int nz, const float *src, float *dst, float *rho, const float *u_src, float *u_dst,
                                   const float *force, const float *phase, const float *blockage, const uint8_t *flags,
                                   const unsigned long long *nbr, int les, int porous, float tau_water, float tau_air, float gravity_lu,

@@ -238,3 +238,84 @@ def test_two_gloo_ranks_particle_coupling_reproduces_the_reference_run(cuts):
     for p in procs:
         assert p.exitcode == 0
     assert out.get(timeout=5) is True
+
+
+# ---- the legacy-compatible step on z-slabs: product kernel source (CPU-emulated) + slab.exchange_halo over gloo ---------------
+def _step_worker(rank, world, port, out, cuts, fixture):
+    import ctypes as C
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pour_over_coffee_lbm_b200 import slab
+    from pour_over_coffee_lbm_b200.config import LBMConfig
+    here = os.path.dirname(os.path.abspath(__file__))
+    aux = C.CDLL(os.path.join(here, "emu", "_build", "libemu_aux.so")); stepper = C.CDLL(os.path.join(here, "emu", "_build", "libemu_step_reference.so"))
+    z = np.load(os.path.join(here, "golden", fixture))
+    n, steps, gravity = int(z["n"]), int(z["steps"]), float(z["gravity"])
+    z0, nz = cuts[rank]
+    c = R.RefConfig(NX=n, NY=n, NZ=n, GRAVITY_LU=gravity)
+    cfg = LBMConfig(NX=n, NY=n, NZ=n, TAU_FLUID=c.TAU_WATER, TAU_AIR=c.TAU_AIR, GRAVITY_LU=gravity)
+    k_lu, beta_lu = cfg.forchheimer_parameters(); c_darcy, c_forch = cfg.filter_constants()
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    f32 = lambda v: C.c_float(float(v))
+
+    def local(dev):
+        """global [.., z, y, x] -> this slab's [.., nz + 2, y, x] with the neighbours' planes as ghosts (zeros outside the box)"""
+        zax = dev.ndim - 3
+        pad = [(0, 0)] * dev.ndim; pad[zax] = (1, 1)
+        full = np.pad(dev, pad)
+        sl = [slice(None)] * dev.ndim; sl[zax] = slice(z0, z0 + nz + 2)
+        return np.ascontiguousarray(full[tuple(sl)])
+
+    solid = local(H.to_dev_scalar(z["solid"]).astype(np.uint8)); zone = local(H.to_dev_scalar(z["filter_zone"]).astype(np.int32))
+    les = local(H.to_dev_scalar(z["les_mask"]).astype(np.int32))
+    dims = (C.c_int(n), C.c_int(n), C.c_int(nz), C.c_int(z0), C.c_int(n))
+    flags = np.zeros_like(solid); nbr = np.zeros(solid.shape, np.uint64)
+    aux.emu_slab_pack_flags_and_masks(*dims, P(flags), P(solid), P(zone), P(les), P(nbr))
+    g = [np.empty((19, nz + 2, n, n), np.float32), None]
+    aux.emu_slab_convert_f(*dims, C.c_int(0), P(local(H.to_dev_pop(z["f"]))), P(flags), P(g[0])); g[1] = g[0].copy()
+    force, phase = local(H.to_dev_vec(z["body_force"])), local(H.to_dev_scalar(z["phase"]))
+    rho = np.ones((nz + 2, n, n), np.float32); u = [np.zeros((3, nz + 2, n, n), np.float32), np.zeros((3, nz + 2, n, n), np.float32)]
+    blockage = np.zeros((nz + 2, n, n), np.float32)
+    cur = 0
+    for _ in range(steps):
+        slab.exchange_halo(torch.from_numpy(g[cur]), rank, world, False, vec3=torch.from_numpy(u[cur]))   # 5 + 5 populations, u for the FD-LES
+        stepper.emu_step_reference_slab(*dims, P(g[cur]), P(g[1 - cur]), P(rho), P(u[cur]), P(u[1 - cur]), P(force), P(phase), P(blockage), P(flags),
+                                        P(nbr), C.c_int(1), C.c_int(1), f32(cfg.TAU_WATER), f32(cfg.TAU_AIR), f32(gravity), f32(cfg.LES_CS), f32(0.55),
+                                        f32(1.90), f32(k_lu), f32(beta_lu), f32(c_darcy), f32(c_forch))
+        cur = 1 - cur
+    slab.exchange_halo(torch.from_numpy(g[cur]), rank, world, False)
+    f_out = np.empty_like(g[cur])
+    aux.emu_slab_convert_f(*dims, C.c_int(1), P(g[cur]), P(flags), P(f_out))
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (z0, rho[1:-1].copy(), u[cur][:, 1:-1].copy(), f_out[:, 1:-1].copy()))
+    if rank == 0:
+        parts = sorted(gathered, key=lambda t: t[0])
+        rho_f = np.transpose(np.concatenate([p[1] for p in parts], 0), (2, 1, 0))
+        u_f = np.transpose(np.concatenate([p[2] for p in parts], 1), (3, 2, 1, 0))
+        f_f = np.transpose(np.concatenate([p[3] for p in parts], 1), (0, 3, 2, 1))
+        fluid = z["solid"] == 0
+        out.put(bool(np.array_equal(rho_f[fluid], z["rho"][fluid]) and np.array_equal(u_f[fluid], z["u"][fluid]) and
+                     np.array_equal(f_f[:, fluid], z["f_out"][:, fluid])))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fixture,cuts", [("reference_run_step_split_phase_small_gravity.npz", ((0, 8), (8, 8))),
+                                          ("reference_run_step_water_default_gravity.npz", ((0, 5), (5, 11))),
+                                          ("reference_run_long_air_1000.npz", ((0, 9), (9, 7)))],
+                         ids=["les_active_equal", "default_gravity_unequal", "1000_steps_unequal"])
+def test_two_gloo_ranks_legacy_step_kernel_reproduces_the_reference_run(fixture, cuts):
+    """The product's legacy-compatible step kernel source (CPU-emulated, slab geometry: one ghost plane per side, global-z tests)
+    on two z-slabs with slab.exchange_halo (5 + 5 outgoing populations per interface, u planes for the lagged FD-LES) over gloo:
+    the gathered result equals the reference's own recorded single-domain runs -- 1000 steps included -- bit for bit."""
+    H.build_emu("emu_aux", ["lbm_aux.cu", "lbm_phys.cuh", "lbm_common.cuh"])
+    H.build_emu("emu_step_reference", ["lbm_step_kernel.cuh", "lbm_phys.cuh", "lbm_common.cuh"])
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_step_worker, args=(r, 2, port, out, cuts, fixture)) for r in range(2)]
+    for p in procs: p.start()
+    for p in procs: p.join(timeout=600)
+    for p in procs:
+        assert p.exitcode == 0
+    assert out.get(timeout=5) is True
