@@ -7,6 +7,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <vector>
 
 struct EmuIdx { unsigned x, y, z; };
 static EmuIdx emu_block_idx, emu_thread_idx, emu_block_dim, emu_grid_dim;
@@ -101,6 +102,24 @@ int emu_pressure_gradient(int nx, int ny, int nz, const float *rho, const uint8_
     const unsigned b = nx >= 128 ? 128 : 64;
     run(dim3((nx + b - 1) / b, ny, nz), b, [&] { pressure_gradient_kernel(G, rho, flags, bf, max_force, scale, accumulate); });
     return 0;
+}
+// the tile-list variant the library uses when the caller's flag field is the one its work lists were built for: one warp per
+// active warp-tile (32 * vec x-consecutive cells of a row holding at least one fluid cell)
+int emu_pressure_gradient_tiles(int nx, int ny, int nz, int vec, const float *rho, const uint8_t *flags, float *bf, float max_force, float scale,
+                                int accumulate) {
+    const Grid G = make_grid(nx, ny, nz);
+    std::vector<unsigned> items;
+    const int span = 32 * vec, segs = (nx + span - 1) / span;
+    for (int z = 0; z < nz; ++z)
+        for (int y = 0; y < ny; ++y)
+            for (int sgm = 0; sgm < segs; ++sgm) {
+                bool any = false;
+                for (int x = span * sgm; x < nx && x < span * (sgm + 1); ++x) any |= !(flags[((long long)z * ny + y) * nx + x] & LBM_FLAG_SOLID);
+                if (any) items.push_back((unsigned)sgm | ((unsigned)y << 8) | ((unsigned)z << 20));
+            }
+    const int n_items = (int)items.size();
+    run(dim3((n_items + 3) / 4, 1, 1), 128, [&] { pressure_gradient_tiles_kernel(G, rho, flags, bf, max_force, scale, accumulate, items.data(), n_items, vec); });
+    return n_items;
 }
 int emu_forchheimer(int nx, int ny, int nz, const float *u, const uint8_t *flags, float *bf, float K, float beta, float c_darcy, float c_forch,
                     float fmax) {

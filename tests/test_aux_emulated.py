@@ -76,6 +76,11 @@ def test_emulated_force_producers_reproduce_the_reference_run(aux):
     bf[:] = 0
     aux.emu_pressure_gradient(*_dims(n), _p(rho), _p(flags), _p(bf), C.c_float(0.12), C.c_float(0.5), C.c_int(1))
     assert np.array_equal(np.transpose(bf, (3, 2, 1, 0)), z["bf_mixed_drive"])
+    for vec in (1, 2, 4):                                        # the tile-list variant (what a V60 run uses): same values, "set" mode included
+        bt = np.full_like(u, 7.0)
+        n_items = aux.emu_pressure_gradient_tiles(*_dims(n), C.c_int(vec), _p(rho), _p(flags), _p(bt), C.c_float(0.12), C.c_float(0.5), C.c_int(0))
+        fluid_dev = H.to_dev_scalar(z["solid"]) == 0
+        assert n_items > 0 and np.array_equal(bt[:, fluid_dev], bf[:, fluid_dev]) and np.all(bt[:, ~fluid_dev] == 7.0)
     k_lu, beta = cfg.forchheimer_parameters(); c_darcy, c_forch = cfg.filter_constants()
     aux.emu_forchheimer(*_dims(n), _p(u), _p(flags), _p(bf), C.c_float(k_lu), C.c_float(beta), C.c_float(c_darcy), C.c_float(c_forch),
                         C.c_float(0.01 * cfg.SCALE_VELOCITY / cfg.DT))
