@@ -51,6 +51,10 @@ extern "C" {
 #define LBM_FEAT_PHASE   4    /* phase field read: tau by phase, gravity*phase */
 #define LBM_FEAT_LES     8    /* Smagorinsky eddy viscosity (physical: local Pi^neq; reference: FD on lagged u) */
 #define LBM_FEAT_POROUS  16   /* filter-zone drag (physical: force; reference: post-step u damping) */
+#define LBM_FEAT_DRIVE   32   /* compat=physical behind walls, four-cell kernel: the pressure-gradient drive
+                                 (PressureGradientDrive, pressure_gradient_drive.py:124-193) is evaluated inside the step kernel from
+                                 the previous step's rho (lbm_fields.rho_src) and added to body_force: same bits as
+                                 lbm_pressure_gradient_force + lbm_step, one pass less */
 #define LBM_FEAT_STRICT  64   /* compat=reference: use the -fmad=false build, bit-exact against the CPU oracle
                                  (compat=physical rounds every operation explicitly: one build, always bit-exact) */
 
@@ -81,6 +85,8 @@ typedef struct {
                                  compat = physical, 1 behind walls in compat = reference) */
     int block;                /* tuning: threads per CTA (0 = auto; 64 / 128 / 256; behind walls in compat = physical the
                                  codes 65 / 66 select 64-thread CTAs at 16 / 24 resident warps per SM, default 20) */
+    float drive_max_force;    /* LBM_FEAT_DRIVE: clamp on |F| (PressureGradientDrive.MAX_PRESSURE_FORCE) ... */
+    float drive_scale;        /* ... and the factor of the accumulation (1 in force mode, 0.5 in mixed mode) */
 } lbm_params;
 
 typedef struct {
@@ -91,6 +97,7 @@ typedef struct {
     float *phase;             /* may be NULL unless LBM_FEAT_PHASE */
     float *blockage;          /* FilterPaperSystem.filter_blockage, may be NULL */
     uint8_t *flags;           /* may be NULL unless LBM_FEAT_WALLS */
+    float *rho_src;           /* LBM_FEAT_DRIVE: rho of the previous step (read); lbm_step swaps rho / rho_src every step */
 } lbm_fields;
 
 /* ---- life cycle -------------------------------------------------------------------------- */

@@ -17,7 +17,7 @@ CSRC = os.path.join(_HERE, "csrc")
 # ---- constants mirrored from include/lbm_b200.h -------------------------------------------
 Q = 19
 COMPAT_PHYSICAL, COMPAT_REFERENCE = 0, 1
-FEAT_WALLS, FEAT_FORCE, FEAT_PHASE, FEAT_LES, FEAT_POROUS, FEAT_STRICT = 1, 2, 4, 8, 16, 64
+FEAT_WALLS, FEAT_FORCE, FEAT_PHASE, FEAT_LES, FEAT_POROUS, FEAT_DRIVE, FEAT_STRICT = 1, 2, 4, 8, 16, 32, 64
 FLAG_SOLID, FLAG_FILTER, FLAG_LES, FLAG_NEAR = 1, 2, 4, 8
 
 
@@ -29,12 +29,12 @@ class LbmParams(C.Structure):
                 ("cs_smag", C.c_float), ("tau_min", C.c_float), ("tau_max", C.c_float),
                 ("porous_darcy", C.c_float), ("porous_forch", C.c_float),
                 ("K_lu", C.c_float), ("beta_lu", C.c_float), ("c_darcy", C.c_float), ("c_forch", C.c_float),
-                ("vec", C.c_int), ("block", C.c_int)]
+                ("vec", C.c_int), ("block", C.c_int), ("drive_max_force", C.c_float), ("drive_scale", C.c_float)]
 
 
 class LbmFields(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
-                ("f_src", "f_dst", "rho", "u_src", "u_dst", "body_force", "phase", "blockage", "flags")]
+                ("f_src", "f_dst", "rho", "u_src", "u_dst", "body_force", "phase", "blockage", "flags", "rho_src")]
 
 
 class LbmParticles(C.Structure):

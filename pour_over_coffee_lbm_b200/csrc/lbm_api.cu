@@ -21,9 +21,10 @@ cudaError_t launch_init_equilibrium(const Grid &, int, float *, const float *, c
 cudaError_t launch_v60_geometry(const Grid &, uint8_t *, int32_t *, const float[5], cudaStream_t);
 cudaError_t launch_pack_flags(const Grid &, uint8_t *, const uint8_t *, const int32_t *, const int32_t *, cudaStream_t);
 cudaError_t build_work_lists(const Grid &, const uint8_t *, int, int, unsigned **, unsigned **, std::vector<int> &, unsigned long long **, cudaStream_t);
+cudaError_t build_chord_lists(const Grid &, const uint8_t *, uint4 **, unsigned **, std::vector<int> &, unsigned long long **, long long *, cudaStream_t);
 cudaError_t launch_convert_f(const Grid &, bool, const float *, const uint8_t *, float *, cudaStream_t);
 cudaError_t launch_face_bc(const Grid &, float *, const uint8_t *, cudaStream_t, int *);
-cudaError_t launch_pressure_gradient(const Grid &, const float *, const uint8_t *, float *, float, float, int, const unsigned *, int, int, cudaStream_t);
+cudaError_t launch_pressure_gradient(const Grid &, const float *, const uint8_t *, float *, float, float, int, const unsigned *, const uint4 *, int, int, cudaStream_t);
 cudaError_t launch_forchheimer_force(const Grid &, const float *, const uint8_t *, float *, float, float, float, float, float, cudaStream_t);
 cudaError_t launch_add_reaction(const Grid &, const float *, const uint8_t *, float *, cudaStream_t);
 cudaError_t run_selftest_math(unsigned long long[7], const StepArgs &, cudaStream_t);
@@ -104,7 +105,10 @@ struct lbm_ctx {
     cudaEvent_t ev_boundary = nullptr, ev_comm = nullptr;
     // work lists of the walls path (built by lbm_pack_flags for the flag field it packed)
     unsigned *d_tiles = nullptr;               // active warp-tiles, packed x_segment | y << 8 | z << 20
-    unsigned *d_tile_mask = nullptr;           // per warp-tile: lanes that must load (VEC = 4 walls kernel)
+    unsigned *d_tile_mask = nullptr;           // per warp-tile: lanes that must load (unused by the current kernels)
+    uint4 *d_ctiles = nullptr;                 // vec = 4: chord-fitted tiles (lbm_phys_chord.cuh) ...
+    unsigned *d_links = nullptr;               // ... and their wall links
+    long long n_links = 0;
     cudaStream_t window_stream = nullptr; bool window_set = false;
     unsigned long long *d_nbr = nullptr;       // neighbour masks [vol]
     int list_block = 0;
@@ -158,7 +162,7 @@ static int pick_vec(const lbm_ctx *ctx) {
         // loads, lane masks) and the TMA-staged kernel (LBM_TMA=1) are opt-in: measured on B200 they
         // win on all-fluid boxes (vec = 4) or by 4 % on the V60 mask (TMA) but not across the board.
         if (vec == 0) vec = 2;      // also what the TMA-staged kernel works on (64-cell rows, two cells per lane)
-        if (vec == 4 && (ctx->g.nx % 4 != 0 || ctx->g.nx < 8)) vec = 2;
+        if (vec == 4 && (ctx->g.nx % 4 != 0 || ctx->g.nx < 8 || ctx->g.nx > 2048 || ctx->g.ny > 65535 || ctx->g.nz > 65535)) vec = 2;
         if (vec == 2 && (ctx->g.nx % 2 != 0 || ctx->g.nx < 4)) vec = 1;
         return vec;
     }
@@ -188,7 +192,7 @@ static bool tma_eligible(const lbm_ctx *ctx) {
     return phys_walls(p) && ctx->tma_enabled && p.vec == 0 && !(p.periodic & 3) && p.nx % 16 == 0 && p.nx >= 16;
 }
 static void feature_bits(const lbm_params &p, int *forced, int *les, int *porous) {
-    *forced = (p.features & (LBM_FEAT_FORCE | LBM_FEAT_PHASE)) != 0;
+    *forced = ((p.features & (LBM_FEAT_FORCE | LBM_FEAT_PHASE)) != 0 ? 1 : 0) | ((p.features & LBM_FEAT_DRIVE) ? 2 : 0);
     *les = (p.features & LBM_FEAT_LES) != 0;
     *porous = (p.features & LBM_FEAT_POROUS) != 0;
 }
@@ -202,9 +206,16 @@ static int tma_variant_for(const lbm_ctx *ctx) {
 // tile height of the step kernel's work list: TY of the TMA variant, or 1 for the warp-tile list
 static int pick_ty(const lbm_ctx *ctx) { return tma_eligible(ctx) ? tma_variant_ty(tma_variant_for(ctx)) : 1; }
 
+static bool chord_lists(const lbm_ctx *ctx, int vec) { return phys_walls(ctx->p) && vec == 4; }
+
 static int rebuild_lists(lbm_ctx *ctx, const uint8_t *flags, int vec, int ty, int block, cudaStream_t s) {
-    CUDA_OK(ctx, build_work_lists(ctx->g, flags, vec, ty, &ctx->d_tiles, &ctx->d_tile_mask, ctx->tile_off, &ctx->d_nbr, s));
-    ctx->launches += 6;
+    if (chord_lists(ctx, vec) && ty == 1) {
+        CUDA_OK(ctx, build_chord_lists(ctx->g, flags, &ctx->d_ctiles, &ctx->d_links, ctx->tile_off, &ctx->d_nbr, &ctx->n_links, s));
+        ctx->launches += 6;
+    } else {
+        CUDA_OK(ctx, build_work_lists(ctx->g, flags, vec, ty, &ctx->d_tiles, &ctx->d_tile_mask, ctx->tile_off, &ctx->d_nbr, s));
+        ctx->launches += 6;
+    }
     ctx->list_flags = flags; ctx->list_vec = vec; ctx->list_ty = ty; ctx->list_block = block; ctx->window_set = false;
     ctx->slots_valid = nullptr;
     return 0;
@@ -315,6 +326,8 @@ void lbm_destroy(lbm_ctx *ctx) {
     if (ctx->ev_comm) cudaEventDestroy(ctx->ev_comm);
     if (ctx->d_tiles) cudaFree(ctx->d_tiles);
     if (ctx->d_tile_mask) cudaFree(ctx->d_tile_mask);
+    if (ctx->d_ctiles) cudaFree(ctx->d_ctiles);
+    if (ctx->d_links) cudaFree(ctx->d_links);
     if (ctx->d_stat_scratch) cudaFree(ctx->d_stat_scratch);
     if (ctx->d_nbr) cudaFree(ctx->d_nbr);
     delete ctx;
@@ -372,9 +385,9 @@ int lbm_pack_flags(lbm_ctx *ctx, uint8_t *flags, const uint8_t *solid, const int
 // ---- step ---------------------------------------------------------------------------------------
 static StepKernel lookup(const lbm_params &p, int vec, int collide, int *block) {
     const int walls = (p.features & LBM_FEAT_WALLS) != 0;
-    const int forced = (p.features & (LBM_FEAT_FORCE | LBM_FEAT_PHASE)) != 0;
-    const int les = (p.features & LBM_FEAT_LES) != 0;
-    const int porous = (p.features & LBM_FEAT_POROUS) != 0;
+    int forced, les, porous;
+    feature_bits(p, &forced, &les, &porous);
+    if (!collide) forced &= 1;                       // moments only: the drive does not enter
     const int group = p.compat * 2 + walls;
     const bool strict = (p.features & LBM_FEAT_STRICT) != 0;
 #define LBM_PICK(g) (strict ? lookup_strict_g##g##_fn(forced, les, porous, vec, collide, block) \
@@ -397,6 +410,7 @@ static int fill_args(lbm_ctx *ctx, const lbm_fields *f, StepArgs *a) {
     a->force = (p.features & LBM_FEAT_FORCE) ? f->body_force : nullptr;
     a->phase = (p.features & LBM_FEAT_PHASE) ? f->phase : nullptr;
     a->blockage = f->blockage; a->flags = f->flags;
+    a->rho_src = f->rho_src; a->drive_max_force = p.drive_max_force; a->drive_scale = p.drive_scale;
     a->tau_water = p.tau_water; a->tau_air = p.tau_air; a->gravity_lu = p.gravity_lu;
     a->tau_min = p.tau_min; a->tau_max = p.tau_max;
     if (p.compat == LBM_COMPAT_REFERENCE) a->les_k = (p.cs_smag * 1.0f) * (p.cs_smag * 1.0f);     // les_turbulence.py:369
@@ -452,6 +466,18 @@ static int launch_planes(lbm_ctx *ctx, StepArgs &a, const Launcher &L, int z_beg
         const int t0 = ctx->tile_off[z_begin], t1 = ctx->tile_off[z_end];
         if (t1 <= t0) return 0;
         a.items = ctx->d_tiles; a.item_mask = ctx->d_tile_mask; a.item_begin = t0; a.n_items = t1 - t0; a.nbr = ctx->d_nbr;
+        a.ctiles = ctx->d_ctiles; a.links = ctx->d_links;
+        a.regular = (getenv("LBM_REGULAR") && atoi(getenv("LBM_REGULAR"))) ? 1 : 0;
+        if (getenv("LBM_L2_WINDOW") && atoi(getenv("LBM_L2_WINDOW")) && ctx->d_ctiles && ctx->window_stream != s) {
+            // experiment: keep the tile list L2-resident (persisting access-policy window on the launching stream)
+            const size_t bytes = std::min((size_t)ctx->tile_off[ctx->g.nz] * sizeof(uint4), ctx->max_window);
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min(bytes, (size_t)64 << 20));
+            cudaStreamAttrValue v; memset(&v, 0, sizeof v);
+            v.accessPolicyWindow.base_ptr = ctx->d_ctiles; v.accessPolicyWindow.num_bytes = bytes; v.accessPolicyWindow.hitRatio = 1.0f;
+            v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting; v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &v);
+            ctx->window_stream = s;
+        }
         if (L.tma) {
             const TmaMaps *maps = nullptr;
             if (tensor_maps(ctx, a, L.tk.ty, &maps)) return 1;
@@ -472,7 +498,7 @@ static int launch_planes(lbm_ctx *ctx, StepArgs &a, const Launcher &L, int z_beg
 static const int UP_Q[5] = {5, 11, 12, 15, 16};
 static const int DOWN_Q[5] = {6, 13, 14, 17, 18};
 
-static int exchange(lbm_ctx *ctx, float *g, float *vec3, cudaStream_t s) {
+static int exchange(lbm_ctx *ctx, float *g, float *vec3, float *scalar, cudaStream_t s) {
     const Grid &G = ctx->g;
     if (!G.zg) return 0;
     const size_t plane = (size_t)G.plane;
@@ -493,6 +519,10 @@ static int exchange(lbm_ctx *ctx, float *g, float *vec3, cudaStream_t s) {
             float *v = vec3 + (size_t)d * G.vol;
             CUDA_OK(ctx, cudaMemcpyAsync(v, v + (size_t)G.nz * plane, plane * 4, cudaMemcpyDeviceToDevice, s));
             CUDA_OK(ctx, cudaMemcpyAsync(v + (size_t)(G.nz + 1) * plane, v + plane, plane * 4, cudaMemcpyDeviceToDevice, s));
+        }
+        if (scalar) {
+            CUDA_OK(ctx, cudaMemcpyAsync(scalar, scalar + (size_t)G.nz * plane, plane * 4, cudaMemcpyDeviceToDevice, s));
+            CUDA_OK(ctx, cudaMemcpyAsync(scalar + (size_t)(G.nz + 1) * plane, scalar + plane, plane * 4, cudaMemcpyDeviceToDevice, s));
         }
         return 0;
     }
@@ -521,6 +551,13 @@ static int exchange(lbm_ctx *ctx, float *g, float *vec3, cudaStream_t s) {
             const bool upward = (pass == 0) != swap_order;
             if (upward && has_up) bad |= post(true, v + (size_t)G.nz * plane, v + (size_t)(G.nz + 1) * plane);
             if (!upward && has_down) bad |= post(false, v + plane, v);
+        }
+    }
+    if (scalar) {
+        for (int pass = 0; pass < 2; ++pass) {
+            const bool upward = (pass == 0) != swap_order;
+            if (upward && has_up) bad |= post(true, scalar + (size_t)G.nz * plane, scalar + (size_t)(G.nz + 1) * plane);
+            if (!upward && has_down) bad |= post(false, scalar + plane, scalar);
         }
     }
     NCCL_OK(ctx, g_nccl.GroupEnd());
@@ -560,6 +597,10 @@ int lbm_step(lbm_ctx *ctx, lbm_fields *f, int nsteps, int write_macro_every, voi
     const bool ref_les = p.compat == LBM_COMPAT_REFERENCE && (p.features & LBM_FEAT_LES);
     if (ref_les && write_macro_every != 1) return fail(ctx, "compat=reference with LES needs u every step (write_macro_every must be 1)");
     if (ref_les && (!f->u_src || !f->u_dst || f->u_src == f->u_dst)) return fail(ctx, "compat=reference with LES needs distinct u_src/u_dst");
+    const bool drive = (p.features & LBM_FEAT_DRIVE) != 0;
+    if (drive && !(phys_walls(p) && vec == 4)) return fail(ctx, "LBM_FEAT_DRIVE is fused into the four-cell walls kernel of compat=physical (LBM_FEAT_WALLS, nx % 4 == 0, vec = 0 or 4)");
+    if (drive && write_macro_every != 1) return fail(ctx, "LBM_FEAT_DRIVE reads the previous step's rho (write_macro_every must be 1)");
+    if (drive && (!f->rho || !f->rho_src || f->rho == f->rho_src)) return fail(ctx, "LBM_FEAT_DRIVE needs distinct rho (written) and rho_src (previous step) fields");
     cudaStream_t cs = (cudaStream_t)compute_stream, ms = (cudaStream_t)comm_stream;
     const bool slabs = ctx->g.zg == 1;
     const bool overlap = slabs && ctx->nranks > 1 && ms != nullptr && ms != cs && ctx->g.nz >= 3;
@@ -577,17 +618,18 @@ int lbm_step(lbm_ctx *ctx, lbm_fields *f, int nsteps, int write_macro_every, voi
             CUDA_OK(ctx, cudaEventRecord(ctx->ev_boundary, cs));
             CUDA_OK(ctx, cudaStreamWaitEvent(ms, ctx->ev_boundary, 0));
             if (launch_planes(ctx, a, L, 1, ctx->g.nz - 1, cs)) return 1;
-            if (exchange(ctx, f->f_dst, (ref_les && a.write_macro) ? f->u_dst : nullptr, ms)) return 1;
+            if (exchange(ctx, f->f_dst, (ref_les && a.write_macro) ? f->u_dst : nullptr, drive ? f->rho : nullptr, ms)) return 1;
             CUDA_OK(ctx, cudaEventRecord(ctx->ev_comm, ms));
             CUDA_OK(ctx, cudaStreamWaitEvent(cs, ctx->ev_comm, 0));
         } else {
             if (launch_planes(ctx, a, L, 0, ctx->g.nz, cs)) return 1;
-            if (slabs && exchange(ctx, f->f_dst, (ref_les && a.write_macro) ? f->u_dst : nullptr, cs)) return 1;
+            if (slabs && exchange(ctx, f->f_dst, (ref_les && a.write_macro) ? f->u_dst : nullptr, drive ? f->rho : nullptr, cs)) return 1;
         }
         if (slabs && L.walls && refresh_boundary_slots(ctx, f->f_dst, f->flags, cs)) return 1;
         if (phys_walls(p)) ctx->slots_valid = f->f_dst;
         float *t = f->f_src; f->f_src = f->f_dst; f->f_dst = t;
         if (a.write_macro && f->u_src && f->u_src != f->u_dst) { t = f->u_src; f->u_src = f->u_dst; f->u_dst = t; }
+        if (drive) { t = f->rho; f->rho = f->rho_src; f->rho_src = t; }      // rho_src = the density this step wrote
     }
     return 0;
 }
@@ -645,18 +687,24 @@ int lbm_import_f(lbm_ctx *ctx, const float *f_in, const uint8_t *flags, float *g
 
 int lbm_pressure_gradient_force(lbm_ctx *ctx, const float *rho, const uint8_t *flags, float *body_force, float max_force, float scale, void *stream) {
     if (!ctx || !rho || !body_force) return fail(ctx, "null argument");
-    const bool listed = flags && ctx->list_flags == flags && ctx->list_ty == 1 && ctx->d_tiles && (int)ctx->tile_off.size() == ctx->g.nz + 1;
-    CUDA_OK(ctx, launch_pressure_gradient(ctx->g, rho, flags, body_force, max_force, scale, 1, listed ? ctx->d_tiles : nullptr,
-                                          listed ? ctx->tile_off[ctx->g.nz] : 0, ctx->list_vec, (cudaStream_t)stream));
+    const bool chord = chord_lists(ctx, ctx->list_vec);
+    const bool listed = flags && ctx->list_flags == flags && ctx->list_ty == 1 && (chord ? ctx->d_ctiles != nullptr : ctx->d_tiles != nullptr) &&
+                        (int)ctx->tile_off.size() == ctx->g.nz + 1;
+    CUDA_OK(ctx, launch_pressure_gradient(ctx->g, rho, flags, body_force, max_force, scale, 1, listed && !chord ? ctx->d_tiles : nullptr,
+                                          listed && chord ? ctx->d_ctiles : nullptr, listed ? ctx->tile_off[ctx->g.nz] : 0, ctx->list_vec,
+                                          (cudaStream_t)stream));
     ctx->launches++;
     return 0;
 }
 
 int lbm_pressure_gradient_force_set(lbm_ctx *ctx, const float *rho, const uint8_t *flags, float *body_force, float max_force, float scale, void *stream) {
     if (!ctx || !rho || !body_force) return fail(ctx, "null argument");
-    const bool listed = flags && ctx->list_flags == flags && ctx->list_ty == 1 && ctx->d_tiles && (int)ctx->tile_off.size() == ctx->g.nz + 1;
-    CUDA_OK(ctx, launch_pressure_gradient(ctx->g, rho, flags, body_force, max_force, scale, 0, listed ? ctx->d_tiles : nullptr,
-                                          listed ? ctx->tile_off[ctx->g.nz] : 0, ctx->list_vec, (cudaStream_t)stream));
+    const bool chord = chord_lists(ctx, ctx->list_vec);
+    const bool listed = flags && ctx->list_flags == flags && ctx->list_ty == 1 && (chord ? ctx->d_ctiles != nullptr : ctx->d_tiles != nullptr) &&
+                        (int)ctx->tile_off.size() == ctx->g.nz + 1;
+    CUDA_OK(ctx, launch_pressure_gradient(ctx->g, rho, flags, body_force, max_force, scale, 0, listed && !chord ? ctx->d_tiles : nullptr,
+                                          listed && chord ? ctx->d_ctiles : nullptr, listed ? ctx->tile_off[ctx->g.nz] : 0, ctx->list_vec,
+                                          (cudaStream_t)stream));
     ctx->launches++;
     return 0;
 }
@@ -855,7 +903,7 @@ int lbm_attach_nccl(lbm_ctx *ctx, const void *unique_id128, int rank, int nranks
 int lbm_halo_exchange(lbm_ctx *ctx, float *g, float *vec3_or_null, void *stream) {
     if (!ctx || !g) return fail(ctx, "null argument");
     ctx->slots_valid = nullptr;      // the incoming ghost planes overwrite the bounce-back slots that live in them
-    return exchange(ctx, g, vec3_or_null, (cudaStream_t)stream);
+    return exchange(ctx, g, vec3_or_null, nullptr, (cudaStream_t)stream);
 }
 
 }  // extern "C"

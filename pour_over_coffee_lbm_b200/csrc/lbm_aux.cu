@@ -194,18 +194,12 @@ __device__ __forceinline__ void pressure_gradient_cell(const Grid &G, const floa
     if (flags && (flags[c] & LBM_FLAG_SOLID)) return;
     const int k = G.z0 + z;
     const float r0 = rho[c];
-    float gx, gy, gz;
-    if (x > 0 && x < G.nx - 1) gx = (rho[c + 1] - rho[c - 1]) * 0.5f; else if (x == 0) gx = rho[c + 1] - r0; else gx = r0 - rho[c - 1];
-    if (y > 0 && y < G.ny - 1) gy = (rho[c + G.nx] - rho[c - G.nx]) * 0.5f; else if (y == 0) gy = rho[c + G.nx] - r0; else gy = r0 - rho[c - G.nx];
-    if (k > 0 && k < G.nz_global - 1) gz = (rho[c + G.plane] - rho[c - G.plane]) * 0.5f; else if (k == 0) gz = rho[c + G.plane] - r0; else gz = r0 - rho[c - G.plane];
-    const float cs2 = (float)(1.0 / 3.0);
-    float fx = 0.0f, fy = 0.0f, fz = 0.0f;
-    if (r0 > 1e-12f) {
-        fx = -(gx * cs2) / r0; fy = -(gy * cs2) / r0; fz = -(gz * cs2) / r0;
-        const float mag = sqrtf(dot3(fx, fy, fz, fx, fy, fz));
-        if (mag > max_force) { const float s = max_force / mag; fx = fx * s; fy = fy * s; fz = fz * s; }
-    }
-    if (scale != 1.0f) { fx = scale * fx; fy = scale * fy; fz = scale * fz; }
+    const float gx = pressure_gradient_diff(r0, x > 0 ? rho[c - 1] : r0, x < G.nx - 1 ? rho[c + 1] : r0, x == 0 ? -1 : (x == G.nx - 1 ? 1 : 0));
+    const float gy = pressure_gradient_diff(r0, y > 0 ? rho[c - G.nx] : r0, y < G.ny - 1 ? rho[c + G.nx] : r0, y == 0 ? -1 : (y == G.ny - 1 ? 1 : 0));
+    const float gz = pressure_gradient_diff(r0, k > 0 ? rho[c - G.plane] : r0, k < G.nz_global - 1 ? rho[c + G.plane] : r0,
+                                            k == 0 ? -1 : (k == G.nz_global - 1 ? 1 : 0));
+    float fx, fy, fz;
+    pressure_gradient_value(r0, gx, gy, gz, max_force, scale, fx, fy, fz);
     if (accumulate) { bf[c] = bf[c] + fx; bf[n + c] = bf[n + c] + fy; bf[2 * n + c] = bf[2 * n + c] + fz; }
     else { bf[c] = fx; bf[n + c] = fy; bf[2 * n + c] = fz; }
 }
@@ -230,6 +224,18 @@ __global__ void pressure_gradient_tiles_kernel(Grid G, const float *rho, const u
         const int x = xb + 32 * i;
         if (x < G.nx) pressure_gradient_cell(G, rho, flags, bf, max_force, scale, accumulate, x, y, z);
     }
+}
+
+// Same over the chord-fitted tiles of the four-cell walls kernel (one lane per active quad).
+__global__ void pressure_gradient_chord_kernel(Grid G, const float *rho, const uint8_t *flags, float *bf, float max_force, float scale,
+                                               int accumulate, const uint4 *tiles, int n_items) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= n_items) return;
+    const uint4 e = tiles[w];
+    const unsigned lane = threadIdx.x & 31u;
+    if (!((e.z >> lane) & 1u)) return;
+    const int xb = ((int)(e.x & 0xfffu) + (int)lane) * 4;
+    for (int i = 0; i < 4; ++i) pressure_gradient_cell(G, rho, flags, bf, max_force, scale, accumulate, xb + i, (int)(e.y & 0xffffu), (int)(e.y >> 16));
 }
 
 // filter_paper.py:471-536
@@ -392,6 +398,147 @@ cudaError_t build_work_lists(const Grid &G, const uint8_t *flags, int vec, int t
     }
     e = cudaStreamSynchronize(s);
     cudaFree(tmp); cudaFree(tile_flag); cudaFree(d_count); cudaFree(d_num); cudaFree(d_ids);
+    if (e != cudaSuccess) return e;
+    return cudaGetLastError();
+}
+#endif
+
+// ---- chord-fitted tiles and wall links of the four-cell walls kernel (lbm_phys_chord.cuh) ------------------------
+// A "quad" is 4 x-consecutive cells on a 16-byte boundary; it is active when it holds a fluid cell.  A tile is up to 32
+// consecutive quads of one row, STARTING at an active quad (greedy cover of the row from the left), so a tile begins
+// within 3 cells of a chord's first fluid cell and only the last tile of a chord is partly empty -- against x-aligned
+// 128-cell tiles, which make every tile of a V60 row a chord end.  Tile entry (uint4):
+//   .x = first quad | n_links << 12     .y = y | z << 16     .z = lane mask (bit l: quad first + l is active)
+//   .w = index of the tile's first wall link
+// Link (u32) = one 4-byte store the kernel does cooperatively after the collision: value = post-collision population q of
+// cell c of lane l, target = population plane qd of the cell (target x, y + dy, z + dz):
+//   bits 0-4 source lane, 5-6 cell of the quad, 7-11 q, 12-16 qd, 17-18 dy+1, 19-20 dz+1, 21-31 target x.
+// Two kinds: WALL links -- (fluid cell, q) whose target x + e_q is solid: f_q goes to the solid cell's slot of opp(q)
+// (halfway bounce-back on the write side, lbm_phys.cuh) -- and SELF links -- the 19 populations of a fluid cell of a quad
+// that also holds solid cells (a chord end): such a quad cannot be stored as one 128-bit vector.
+// The kernels below are plain (one thread per row / per tile) so that tests/emu can run them on the CPU; they run once
+// per geometry change.
+__device__ __forceinline__ bool quad_active(const uint8_t *row, int q) {
+    return !((row[4 * q] & row[4 * q + 1] & row[4 * q + 2] & row[4 * q + 3]) & LBM_FLAG_SOLID);
+}
+__global__ void chord_count_kernel(Grid G, const uint8_t *flags, int *row_tiles) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= G.nz * G.ny) return;
+    const int z = r / G.ny, y = r - z * G.ny;
+    const uint8_t *row = flags + ((long long)(z + G.zg) * G.ny + y) * G.nx;
+    const int nq = G.nx / 4;
+    int n = 0;
+    for (int q = 0; q < nq;) {
+        if (quad_active(row, q)) { ++n; q += 32; } else ++q;
+    }
+    row_tiles[r] = n;
+}
+__global__ void chord_fill_kernel(Grid G, const uint8_t *flags, const unsigned long long *nbr, const int *row_off, uint4 *tiles, int *tile_links) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= G.nz * G.ny) return;
+    const int z = r / G.ny, y = r - z * G.ny;
+    const long long base = ((long long)(z + G.zg) * G.ny + y) * G.nx;
+    const uint8_t *row = flags + base;
+    const int nq = G.nx / 4;
+    int t = row_off[r];
+    for (int q = 0; q < nq;) {
+        if (!quad_active(row, q)) { ++q; continue; }
+        unsigned mask = 0; int nl = 0;
+        for (int l = 0; l < 32 && q + l < nq; ++l) {
+            if (!quad_active(row, q + l)) continue;
+            mask |= 1u << l;
+            int n_fluid = 0;
+            for (int c = 0; c < 4; ++c) {
+                const int x = 4 * (q + l) + c;
+                const unsigned fl = row[x];
+                if (fl & LBM_FLAG_SOLID) continue;
+                ++n_fluid;
+                if (fl & LBM_FLAG_NEAR) nl += __popc((unsigned)nbr[base + x] & 0x7fffeu);
+            }
+            if (n_fluid < 4) nl += Q * n_fluid;                   // a quad the chord ends in: its fluid cells are stored through self links
+        }
+        tiles[t] = make_uint4((unsigned)q, (unsigned)y | ((unsigned)z << 16), mask, 0u);
+        tile_links[t] = nl;
+        ++t; q += 32;
+    }
+}
+__global__ void chord_links_kernel(Grid G, const uint8_t *flags, const unsigned long long *nbr, uint4 *tiles, const int *link_off, int n_tiles,
+                                   unsigned *links) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    const uint4 e = tiles[t];
+    const int q0 = (int)e.x, y = (int)(e.y & 0xffffu), z = (int)(e.y >> 16);
+    const long long base = ((long long)(z + G.zg) * G.ny + y) * G.nx;
+    const uint8_t *row = flags + base;
+    const unsigned begin = (unsigned)link_off[t];
+    unsigned o = begin;
+    for (int l = 0; l < 32; ++l) {
+        if (!((e.z >> l) & 1u)) continue;
+        const bool mixed = ((row[4 * (q0 + l)] | row[4 * (q0 + l) + 1] | row[4 * (q0 + l) + 2] | row[4 * (q0 + l) + 3]) & LBM_FLAG_SOLID) != 0;
+        for (int c = 0; c < 4; ++c) {
+            const int x = 4 * (q0 + l) + c;
+            const unsigned fl = row[x];
+            if (fl & LBM_FLAG_SOLID) continue;
+            if (mixed)                                            // self links: population q of this cell -> its own slot
+                for (int q = 0; q < Q; ++q)
+                    links[o++] = (unsigned)l | ((unsigned)c << 5) | ((unsigned)q << 7) | ((unsigned)q << 12) | (1u << 17) | (1u << 19) | ((unsigned)x << 21);
+            if (!(fl & LBM_FLAG_NEAR)) continue;
+            const unsigned m = (unsigned)nbr[base + x];
+            for (int q = 1; q < Q; ++q) {
+                if (!((m >> opp(q)) & 1u)) continue;
+                int xt = x + cx(q);
+                if (xt < 0) xt = G.nx - 1; else if (xt >= G.nx) xt = 0;          // periodic wrap (an open face is never "solid")
+                links[o++] = (unsigned)l | ((unsigned)c << 5) | ((unsigned)q << 7) | ((unsigned)opp(q) << 12) | ((unsigned)(cy(q) + 1) << 17) |
+                             ((unsigned)(cz(q) + 1) << 19) | ((unsigned)xt << 21);
+            }
+        }
+    }
+    tiles[t].x = (unsigned)q0 | ((o - begin) << 12);
+    tiles[t].w = begin;
+}
+#ifndef LBM_EMULATE_ON_HOST
+// Builds the chord-fitted tile list, its per-plane offsets (host vector of nz + 1 entries), the wall links and the
+// neighbour masks.  Synchronises the stream: geometry changes are rare.
+cudaError_t build_chord_lists(const Grid &G, const uint8_t *flags, uint4 **d_ctiles, unsigned **d_links, std::vector<int> &tile_off,
+                              unsigned long long **d_nbr, long long *n_links_out, cudaStream_t s) {
+    cudaError_t e;
+    if (G.nx % 4 != 0 || G.nx > 2048 || G.ny > 65535 || G.nz > 65535) return cudaErrorInvalidValue;      // packing limits of a tile entry / link
+    const int rows = G.nz * G.ny;
+    int *row_cnt = nullptr, *row_off = nullptr, *tile_links = nullptr, *link_off = nullptr; void *tmp = nullptr; size_t tmp_bytes = 0;
+    if (!*d_nbr) { if ((e = cudaMalloc(d_nbr, sizeof(unsigned long long) * (size_t)G.vol)) != cudaSuccess) return e; }
+    neighbour_mask_kernel<<<148 * 16, 256, 0, s>>>(G, flags, *d_nbr);
+    if ((e = cudaMalloc(&row_cnt, sizeof(int) * (size_t)(rows + 1))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&row_off, sizeof(int) * (size_t)(rows + 1))) != cudaSuccess) return e;
+    cudaMemsetAsync(row_cnt + rows, 0, sizeof(int), s);
+    chord_count_kernel<<<(rows + 127) / 128, 128, 0, s>>>(G, flags, row_cnt);
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, row_cnt, row_off, rows + 1, s);
+    if ((e = cudaMalloc(&tmp, tmp_bytes)) != cudaSuccess) return e;
+    cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, row_cnt, row_off, rows + 1, s);
+    tile_off.assign(G.nz + 1, 0);
+    if ((e = cudaMemcpy2DAsync(tile_off.data(), sizeof(int), row_off, sizeof(int) * (size_t)G.ny, sizeof(int), (size_t)G.nz + 1, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+    cudaFree(tmp); tmp = nullptr;
+    const int n_t = tile_off[G.nz];
+    if (*d_ctiles) { cudaFree(*d_ctiles); *d_ctiles = nullptr; }
+    if (*d_links) { cudaFree(*d_links); *d_links = nullptr; }
+    if ((e = cudaMalloc(d_ctiles, sizeof(uint4) * (size_t)(n_t > 0 ? n_t : 1))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&tile_links, sizeof(int) * (size_t)(n_t + 1))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&link_off, sizeof(int) * (size_t)(n_t + 1))) != cudaSuccess) return e;
+    cudaMemsetAsync(tile_links + n_t, 0, sizeof(int), s);
+    int n_l = 0;
+    if (n_t > 0) {
+        chord_fill_kernel<<<(rows + 127) / 128, 128, 0, s>>>(G, flags, *d_nbr, row_off, *d_ctiles, tile_links);
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, tile_links, link_off, n_t + 1, s);
+        if ((e = cudaMalloc(&tmp, tmp_bytes)) != cudaSuccess) return e;
+        cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, tile_links, link_off, n_t + 1, s);
+        if ((e = cudaMemcpyAsync(&n_l, link_off + n_t, sizeof(int), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+        if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+    }
+    if ((e = cudaMalloc(d_links, sizeof(unsigned) * (size_t)(n_l > 0 ? n_l : 1))) != cudaSuccess) return e;
+    if (n_t > 0) chord_links_kernel<<<(n_t + 127) / 128, 128, 0, s>>>(G, flags, *d_nbr, *d_ctiles, link_off, n_t, *d_links);
+    e = cudaStreamSynchronize(s);
+    if (n_links_out) *n_links_out = n_l;
+    cudaFree(tmp); cudaFree(row_cnt); cudaFree(row_off); cudaFree(tile_links); cudaFree(link_off);
     if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }
@@ -640,7 +787,11 @@ cudaError_t launch_face_bc(const Grid &G, float *rho, const uint8_t *flags, cuda
     return cudaGetLastError();
 }
 cudaError_t launch_pressure_gradient(const Grid &G, const float *rho, const uint8_t *flags, float *bf, float max_force, float scale, int accumulate,
-                                     const unsigned *items, int n_items, int vec, cudaStream_t s) {
+                                     const unsigned *items, const uint4 *ctiles, int n_items, int vec, cudaStream_t s) {
+    if (ctiles) {     // chord-fitted tiles of the four-cell walls kernel
+        if (n_items > 0) pressure_gradient_chord_kernel<<<(n_items + 3) / 4, 128, 0, s>>>(G, rho, flags, bf, max_force, scale, accumulate, ctiles, n_items);
+        return cudaGetLastError();
+    }
     if (items) {      // the caller's tile list was built for exactly this flag field
         if (n_items > 0) pressure_gradient_tiles_kernel<<<(n_items + 3) / 4, 128, 0, s>>>(G, rho, flags, bf, max_force, scale, accumulate, items, n_items, vec);
         return cudaGetLastError();

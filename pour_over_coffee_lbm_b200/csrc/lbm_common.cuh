@@ -42,6 +42,11 @@ struct StepArgs {
     int item_begin, n_items;
     const unsigned *item_mask;   // VEC = 4 walls kernel: per list entry, the lanes that must load (lbm_phys.cuh)
     const unsigned long long *nbr;     // per cell (valid where NEAR): solid-source bits | out-of-box bits << 32
+    // chord-fitted tiles of the four-cell walls kernel (lbm_phys_chord.cuh): one uint4 per tile, one u32 per wall link
+    const uint4 *ctiles; const unsigned *links;
+    int regular;           // experiment (LBM_REGULAR=1, all-fluid box with solid faces only): tile coordinates computed, not loaded
+    // fused pressure-gradient drive (LBM_FEAT_DRIVE): rho of the previous step, clamp and scale of the force
+    const float *rho_src; float drive_max_force, drive_scale;
     int write_macro;
     float tau_water, tau_air, gravity_lu;
     float tau_min, tau_max;
@@ -61,6 +66,25 @@ __device__ __forceinline__ float edot(float vx, float vy, float vz) {
 }
 __device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, float by, float bz) {
     return (ax * bx + ay * by) + az * bz;
+}
+
+// PressureGradientDrive.compute_pressure_gradient + the force it accumulates (pressure_gradient_drive.py:124-193, 274-279),
+// shared by the stand-alone producer (lbm_aux.cu) and the step kernel that fuses it (lbm_phys_chord.cuh, LBM_FEAT_DRIVE);
+// both translation units are compiled with -fmad=false, so the two give the same bits.
+// pos: -1 = first cell of the axis (one-sided forward difference), +1 = last cell (backward), 0 = interior (central).
+__device__ __forceinline__ float pressure_gradient_diff(float r0, float lo, float hi, int pos) {
+    return pos == 0 ? (hi - lo) * 0.5f : (pos < 0 ? hi - r0 : r0 - lo);
+}
+__device__ __forceinline__ void pressure_gradient_value(float r0, float gx, float gy, float gz, float max_force, float scale,
+                                                        float &fx, float &fy, float &fz) {
+    const float cs2 = (float)(1.0 / 3.0);
+    fx = 0.0f; fy = 0.0f; fz = 0.0f;
+    if (r0 > 1e-12f) {
+        fx = -(gx * cs2) / r0; fy = -(gy * cs2) / r0; fz = -(gz * cs2) / r0;
+        const float mag = sqrtf(dot3(fx, fy, fz, fx, fy, fz));
+        if (mag > max_force) { const float s = max_force / mag; fx = fx * s; fy = fy * s; fz = fz * s; }
+    }
+    if (scale != 1.0f) { fx = scale * fx; fy = scale * fy; fz = scale * fz; }
 }
 
 // tensor maps of the TMA-staged walls kernel (lbm_phys_tma.cuh), passed as a __grid_constant__ kernel parameter

@@ -30,28 +30,51 @@ constexpr int min_blocks() { return (VEC == 1 ? 1024 : 512) / BLOCK; }
 template <int VEC, int BLOCK>
 constexpr int min_blocks_phys_walls() { return VEC == 2 ? (BLOCK == 256 ? 2 : 640 / BLOCK) : min_blocks<VEC, BLOCK>(); }
 
+// chord kernel (lbm_phys_chord.cuh): 10.1 KB of shared memory per warp; 16 warps per SM = 128 registers, no spills.
+// Measured on B200, V60 512^3: 16 warps 1.82 ms, 18 / 20 warps (112 / 96 registers, ~90 B of spills) 1.99 ms.
+template <int BLOCK>
+constexpr int chord_blocks() { return 512 / BLOCK; }
+
 // CTA size: the walls path runs best with small CTAs (near-wall warps take longer; a CTA slot is held until its
 // slowest warp retires -- V60 512^3 sweep: 64 threads 2.17 ms, 128: 2.20, 256: 2.34)
 template <int MODE, int VEC>
 constexpr int default_block() { return MODE == MODE_BULK ? 64 : (VEC == 1 ? 256 : 128); }
 
-template <int MODE, bool FORCED, bool LES, bool POROUS, int VEC, bool COLLIDE>
+template <int MODE, bool FORCED, bool LES, bool POROUS, int VEC, bool COLLIDE, bool DRIVE = false>
 static StepKernel pick() {
     constexpr int BLOCK = default_block<MODE, VEC>();
     if constexpr (POROUS && !G_WALLS) return nullptr;          // the filter zone lives in the flag byte
     else if constexpr (!COLLIDE && LES) return nullptr;
     else if constexpr (G_WALLS && G_COMPAT == LBM_COMPAT_PHYSICAL) {
-        if constexpr (VEC == 4) return phys_walls4_kernel<FORCED, LES, POROUS, BLOCK, COLLIDE, min_blocks<VEC, BLOCK>()>;
+        // VEC = 4: chord-fitted tiles + wall links (lbm_phys_chord.cuh), the only kernel that fuses the pressure drive
+        if constexpr (VEC == 4) return phys_chord_kernel<FORCED, LES, POROUS, DRIVE, BLOCK, COLLIDE, chord_blocks<BLOCK>()>;
+        else if constexpr (DRIVE) return nullptr;
         else return phys_walls_kernel<FORCED, LES, POROUS, VEC, BLOCK, COLLIDE, min_blocks_phys_walls<VEC, BLOCK>()>;
     }
+    else if constexpr (DRIVE) return nullptr;
     else if constexpr (VEC == 2) return nullptr;
     else if constexpr (!COLLIDE && VEC != 1) return nullptr;
     else return step_kernel<LBM_STRICT_BUILD, G_COMPAT, MODE, FORCED, LES, POROUS, VEC, BLOCK, COLLIDE, min_blocks<VEC, BLOCK>()>;
 }
 
+// `forced`: bit 0 = body_force / phase inputs, bit 1 = fused pressure-gradient drive (LBM_FEAT_DRIVE)
 template <int MODE, int VEC, bool COLLIDE>
 static StepKernel pick_feat(int forced, int les, int porous) {
-    const int key = (forced ? 4 : 0) | (les ? 2 : 0) | (porous ? 1 : 0);
+    const int key = ((forced & 1) ? 4 : 0) | (les ? 2 : 0) | (porous ? 1 : 0);
+    if (forced & 2) {
+        if constexpr (COLLIDE && VEC == 4) {
+            switch (key) {
+                case 0: return pick<MODE, false, false, false, VEC, COLLIDE, true>();
+                case 1: return pick<MODE, false, false, true, VEC, COLLIDE, true>();
+                case 2: return pick<MODE, false, true, false, VEC, COLLIDE, true>();
+                case 3: return pick<MODE, false, true, true, VEC, COLLIDE, true>();
+                case 4: return pick<MODE, true, false, false, VEC, COLLIDE, true>();
+                case 5: return pick<MODE, true, false, true, VEC, COLLIDE, true>();
+                case 6: return pick<MODE, true, true, false, VEC, COLLIDE, true>();
+                default: return pick<MODE, true, true, true, VEC, COLLIDE, true>();
+            }
+        } else return nullptr;
+    }
     switch (key) {
         case 0: return pick<MODE, false, false, false, VEC, COLLIDE>();
         case 1: return pick<MODE, false, false, true, VEC, COLLIDE>();
@@ -78,8 +101,12 @@ static StepKernel tuned() {
     if constexpr (G_WALLS && G_COMPAT == LBM_COMPAT_PHYSICAL) {
         // VEC = 4: BLOCK = 128 runs 3 CTAs per SM (168 registers, no spills); BLOCK = 256 is a tuning CODE for the same
         // 128-thread CTAs with plain (not lane-mask predicated) loads
-        if constexpr (VEC == 4 && BLOCK == 256) return phys_walls4_kernel<true, true, true, 128, true, 3, false>;
-        else if constexpr (VEC == 4) return phys_walls4_kernel<true, true, true, BLOCK, true, (BLOCK == 128 ? 3 : min_blocks<VEC, BLOCK>())>;
+        // VEC = 4 (chord kernel): BLOCK = 128 -> 4 CTAs of 128 threads (16 warps, 128 registers); the code 256 selects
+        // 64-thread CTAs at 6 per SM (12 warps, 168 registers, no spills)
+        // VEC = 4 (chord kernel), 64-thread CTAs: default 8 CTAs per SM (16 warps, 128 registers); block code 128 -> 9 CTAs (18 warps,
+        // 112 registers), 256 -> 128-thread CTAs, 4 per SM
+        if constexpr (VEC == 4 && BLOCK == 256) return phys_chord_kernel<true, true, true, false, 128, true, 4>;
+        else if constexpr (VEC == 4) return phys_chord_kernel<true, true, true, false, 64, true, 9>;
         else return phys_walls_kernel<true, true, true, VEC, BLOCK, true, min_blocks_phys_walls<VEC, BLOCK>()>;
     } else return nullptr;
 }
@@ -109,9 +136,9 @@ StepKernel LBM_LOOKUP(int forced, int les, int porous, int vec, int collide, int
     StepKernel k = nullptr;
     constexpr int MAIN = G_WALLS ? MODE_BULK : MODE_DENSE;
     const int def_block = vec == 1 ? default_block<MAIN, 1>() : (vec == 2 ? default_block<MAIN, 2>() : default_block<MAIN, 4>());
-    if (collide && forced && les && porous && *block && *block != def_block) {
+    if (collide && forced == 1 && les && porous && *block && *block != def_block) {
         k = pick_tuned(vec, *block);
-        if (k) { if (*block == 65 || *block == 66) *block = 64; if (vec == 4 && *block == 256) *block = 128; return k; }
+        if (k) { if (*block == 65 || *block == 66) *block = 64; if (vec == 4) *block = (*block == 256 ? 128 : 64); return k; }
     }
     if (collide) {
         if (vec == 4) k = pick_feat<MAIN, 4, true>(forced, les, porous);

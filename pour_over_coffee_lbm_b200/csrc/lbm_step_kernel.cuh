@@ -22,6 +22,7 @@
 #pragma once
 #include "lbm_common.cuh"
 #include "lbm_phys.cuh"
+#include "lbm_phys_chord.cuh"
 
 namespace lbm {
 

@@ -37,7 +37,7 @@ class D3Q19Engine:
                  nz_global: Optional[int] = None, tau: Optional[float] = None, tau_air: Optional[float] = None,
                  gravity_lu: Optional[float] = None, cs_smag: Optional[float] = None,
                  porous_darcy: float = 0.0, porous_forch: float = 0.0, vec: int = 0, block: int = 0,
-                 macro_fields: bool = True):
+                 macro_fields: bool = True, drive: bool = False, drive_max_force: float = 0.12, drive_scale: float = 1.0):
         if not torch.cuda.is_available():
             raise BackendInitializationError(
                 "no CUDA device visible: pour_over_coffee_lbm_b200 runs on B200 (sm_100a) only, there is no CPU fallback",
@@ -60,6 +60,8 @@ class D3Q19Engine:
         if les: feats |= L.FEAT_LES
         if porous: feats |= L.FEAT_POROUS
         if strict: feats |= L.FEAT_STRICT
+        if drive: feats |= L.FEAT_DRIVE          # pressure-gradient drive fused into the step kernel (include/lbm_b200.h)
+        self.drive = bool(drive)
         self.features = feats
         k_lu, beta_lu = self.cfg.forchheimer_parameters()
         c_darcy, c_forch = self.cfg.filter_constants()
@@ -72,7 +74,8 @@ class D3Q19Engine:
             gravity_lu=self.cfg.GRAVITY_LU if gravity_lu is None else gravity_lu,
             cs_smag=self.cfg.LES_CS if cs_smag is None else cs_smag, tau_min=0.55, tau_max=1.90,
             porous_darcy=porous_darcy, porous_forch=porous_forch,
-            K_lu=k_lu, beta_lu=beta_lu, c_darcy=c_darcy, c_forch=c_forch, vec=vec, block=block)
+            K_lu=k_lu, beta_lu=beta_lu, c_darcy=c_darcy, c_forch=c_forch, vec=vec, block=block,
+            drive_max_force=drive_max_force, drive_scale=drive_scale)
         self._ctx = C.c_void_p()
         rc = self.lib.lbm_create(C.byref(self._ctx), device, C.byref(self.params))
         if rc != 0:
@@ -83,7 +86,9 @@ class D3Q19Engine:
         with torch.cuda.device(dev):
             self.g = [torch.empty((L.Q,) + shp, dtype=torch.float32, device=dev) for _ in range(2)]
             self.cur = 0                      # index of the buffer holding the newest populations
-            self.rho = torch.ones(shp, dtype=torch.float32, device=dev) if macro_fields else None
+            # rho: one buffer; a ping-pong pair when the fused drive reads the previous step's density while this step's is written
+            self.rho_buf = [torch.ones(shp, dtype=torch.float32, device=dev) for _ in range(2 if drive else 1)] if macro_fields else []
+            self.rho_cur = 0
             self.ref_les = self.compat == L.COMPAT_REFERENCE and les
             nu = 2 if self.ref_les else 1
             self.u_buf = [torch.zeros((3,) + shp, dtype=torch.float32, device=dev) for _ in range(nu)] if macro_fields else []
@@ -114,6 +119,11 @@ class D3Q19Engine:
     @property
     def u(self) -> torch.Tensor:
         return self.u_buf[self.u_cur]
+
+    @property
+    def rho(self) -> Optional[torch.Tensor]:
+        """the newest density field (None when the engine was built without macroscopic fields)"""
+        return self.rho_buf[self.rho_cur] if self.rho_buf else None
 
     @property
     def populations(self) -> torch.Tensor:
@@ -158,8 +168,9 @@ class D3Q19Engine:
             self._check(self.lib.lbm_init_equilibrium(self._ctx, _ptr(buf), _ptr(rho), _ptr(u), float(rho0), arr, self.stream),
                         "lbm_init_equilibrium")
         if self.rho is not None:
-            if rho is None: self.rho.fill_(rho0)
-            else: self.rho.copy_(rho)
+            for rb in self.rho_buf:
+                if rho is None: rb.fill_(rho0)
+                else: rb.copy_(rho)
             for ub in self.u_buf:
                 if u is None:
                     for c in range(3): ub[c].fill_(float(u0[c]))
@@ -181,6 +192,8 @@ class D3Q19Engine:
                                             _ptr(self.les_mask), self.stream), "lbm_pack_flags")
         if len(self.u_buf) == 2:      # keep the u ping-pong pair identical on cells the kernel never writes
             self.u_buf[1 - self.u_cur].copy_(self.u_buf[self.u_cur])
+        if len(self.rho_buf) == 2:
+            self.rho_buf[1 - self.rho_cur].copy_(self.rho_buf[self.rho_cur])
 
     def set_geometry_preserving_f(self, mutate):
         """Change the solid mask exactly as the reference would see it: the reference streams with the
@@ -198,9 +211,13 @@ class D3Q19Engine:
             u_src, u_dst = self.u_buf[self.u_cur], self.u_buf[1 - self.u_cur]
         else:
             u_src, u_dst = None, (self.u_buf[0] if self.u_buf else None)
-        return L.LbmFields(f_src=_ptr(self.g[self.cur]), f_dst=_ptr(self.g[1 - self.cur]), rho=_ptr(self.rho),
+        if len(self.rho_buf) == 2:    # fused drive: this step writes the other buffer and reads the newest one
+            rho, rho_src = self.rho_buf[1 - self.rho_cur], self.rho_buf[self.rho_cur]
+        else:
+            rho, rho_src = self.rho, None
+        return L.LbmFields(f_src=_ptr(self.g[self.cur]), f_dst=_ptr(self.g[1 - self.cur]), rho=_ptr(rho),
                            u_src=_ptr(u_src), u_dst=_ptr(u_dst), body_force=_ptr(self.body_force),
-                           phase=_ptr(self.phase), blockage=_ptr(self.blockage), flags=_ptr(self.flags))
+                           phase=_ptr(self.phase), blockage=_ptr(self.blockage), flags=_ptr(self.flags), rho_src=_ptr(rho_src))
 
     def step(self, nsteps: int = 1, write_macro_every: int = 1):
         """nsteps fused collide-stream updates (one kernel launch each)."""
@@ -213,16 +230,20 @@ class D3Q19Engine:
             self.cur = 1 - self.cur
         if self.ref_les and write_macro_every == 1 and nsteps % 2 == 1:
             self.u_cur = 1 - self.u_cur
+        if len(self.rho_buf) == 2 and nsteps % 2 == 1:
+            self.rho_cur = 1 - self.rho_cur
         self.steps_done += nsteps
 
     def macroscopic(self):
         f = self._fields()
         if self.ref_les:
             f.u_dst = _ptr(self.u_buf[self.u_cur])
+        f.rho = _ptr(self.rho)
         self._check(self.lib.lbm_macroscopic(self._ctx, C.byref(f), self.stream), "lbm_macroscopic")
 
     def face_bc(self):
         f = self._fields()
+        f.rho = _ptr(self.rho)
         self._check(self.lib.lbm_face_bc(self._ctx, C.byref(f), self.stream), "lbm_face_bc")
 
     # ---- restart checkpoint (absent in the reference) ------------------------------------

@@ -26,6 +26,7 @@ template <class T> static inline T __ldg(const T *p) { return *p; }
 template <class T> static inline T __ldcs(const T *p) { return *p; }
 template <class T> static inline void __stcs(T *p, T v) { *p = v; }
 static inline float atomicAdd(float *p, float v) { const float o = *p; *p = o + v; return o; }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int min(int a, int b) { return a < b ? a : b; }               // CUDA's integer min / max device functions
 static inline int max(int a, int b) { return a > b ? a : b; }
 #define __launch_bounds__(...)
@@ -131,6 +132,34 @@ int emu_forchheimer(int nx, int ny, int nz, const float *u, const uint8_t *flags
 int emu_bounce_slots(int nx, int ny, int nz, int periodic, float *g, const uint8_t *flags, const unsigned long long *nbr) {
     const Grid G = make_grid(nx, ny, nz, periodic);
     run_stride([&] { bounce_slots_kernel(G, g, flags, nbr, 0, nz); });
+    return 0;
+}
+// chord-fitted tiles + wall links of the four-cell walls kernel (build_chord_lists without cub: the two exclusive sums run
+// here on the host).  Returns the number of tiles; tiles = [n][4] u32, links_out holds up to max_links entries.
+int emu_chord_lists(int nx, int ny, int nz, int periodic, const uint8_t *flags, const unsigned long long *nbr, unsigned *tiles_out, int max_tiles,
+                    unsigned *links_out, int max_links, int *n_links_out) {
+    const Grid G = make_grid(nx, ny, nz, periodic);
+    const int rows = nz * ny;
+    std::vector<int> cnt(rows + 1, 0), off(rows + 1, 0);
+    run(dim3((rows + 127) / 128, 1, 1), 128, [&] { chord_count_kernel(G, flags, cnt.data()); });
+    for (int r = 0; r < rows; ++r) off[r + 1] = off[r] + cnt[r];
+    const int n_t = off[rows];
+    if (n_t > max_tiles) return -1;
+    std::vector<uint4> tiles(n_t > 0 ? n_t : 1);
+    std::vector<int> tl(n_t + 1, 0), lo(n_t + 1, 0);
+    run(dim3((rows + 127) / 128, 1, 1), 128, [&] { chord_fill_kernel(G, flags, nbr, off.data(), tiles.data(), tl.data()); });
+    for (int t = 0; t < n_t; ++t) lo[t + 1] = lo[t] + tl[t];
+    if (lo[n_t] > max_links) return -2;
+    run(dim3((n_t + 127) / 128, 1, 1), 128, [&] { chord_links_kernel(G, flags, nbr, tiles.data(), lo.data(), n_t, links_out); });
+    for (int t = 0; t < n_t; ++t) { tiles_out[4 * t] = tiles[t].x; tiles_out[4 * t + 1] = tiles[t].y; tiles_out[4 * t + 2] = tiles[t].z; tiles_out[4 * t + 3] = tiles[t].w; }
+    *n_links_out = lo[n_t];
+    return n_t;
+}
+// pressure-gradient producer over the chord-fitted tiles
+int emu_pressure_gradient_chord(int nx, int ny, int nz, const float *rho, const uint8_t *flags, float *bf, float max_force, float scale, int accumulate,
+                                const unsigned *tiles, int n_tiles) {
+    const Grid G = make_grid(nx, ny, nz);
+    run(dim3((n_tiles + 3) / 4, 1, 1), 128, [&] { pressure_gradient_chord_kernel(G, rho, flags, bf, max_force, scale, accumulate, reinterpret_cast<const uint4 *>(tiles), n_tiles); });
     return 0;
 }
 int emu_add_reaction(int nx, int ny, int nz, const float *reaction, const uint8_t *flags, float *bf) {

@@ -40,7 +40,10 @@ def test_struct_layouts_match_header_field_order():
         fields += [f.strip() for f in parts[1].split(",")]
     assert fields == [f[0] for f in _lib.LbmParams._fields_]
     assert C.sizeof(_lib.LbmParams) == 4 * len(fields)
-    assert C.sizeof(_lib.LbmFields) == 8 * 9 and C.sizeof(_lib.LbmParticles) == 8 * 12 + 8
+    fbody = re.sub(r"/\*.*?\*/", "", src[src.index("typedef struct {\n    float *f_src"):src.index("} lbm_fields;")], flags=re.S)
+    ffields = [n.strip().lstrip("*") for decl in fbody.replace("typedef struct {", "").split(";") if decl.strip() for n in decl.strip().split(None, 1)[1].split(",")]
+    assert ffields == [f[0] for f in _lib.LbmFields._fields_]
+    assert C.sizeof(_lib.LbmFields) == 8 * len(ffields) and C.sizeof(_lib.LbmParticles) == 8 * 12 + 8
 
 
 def test_no_cpu_fallback():

@@ -245,3 +245,97 @@ def test_emulated_physical_walls_kernel_obstacles_on_open_and_periodic_faces(aux
     u0 = H.smooth_velocity(nx, 0.03, 8, nz=nz, ny=ny); rho0 = H.smooth_density(nx, 0.01, 8, nz=nz, ny=ny)
     p = R.PhysParams(nx=nx, ny=ny, nz=nz, tau_water=0.6, periodic=periodic, les=True)
     _walls_case(aux, walls, (nx, ny, nz), periodic, solid, zone, les_mask, None, None, rho0, u0, steps, p)
+
+
+# ---- chord-fitted tiles + wall links of the four-cell walls kernel (csrc/lbm_phys_chord.cuh) ---------------------------------------
+_CX = [0, 1, -1, 0, 0, 0, 0, 1, -1, 1, -1, 1, -1, 1, -1, 0, 0, 0, 0]
+_CY = [0, 0, 0, 1, -1, 0, 0, 1, 1, -1, -1, 0, 0, 0, 0, 1, -1, 1, -1]
+_CZ = [0, 0, 0, 0, 0, 1, -1, 0, 0, 0, 0, 1, 1, -1, -1, 1, 1, -1, -1]
+_OPP = [0, 2, 1, 4, 3, 6, 5, 10, 9, 8, 7, 14, 13, 12, 11, 18, 17, 16, 15]
+
+
+def _chord_lists(aux, solid_zyx, periodic):
+    nz, ny, nx = solid_zyx.shape
+    flags = np.zeros_like(solid_zyx); nbr = np.zeros(solid_zyx.shape, np.uint64)
+    aux.emu_pack_flags_and_masks(C.c_int(nx), C.c_int(ny), C.c_int(nz), C.c_int(periodic), _p(flags), _p(np.ascontiguousarray(solid_zyx)), None, None, _p(nbr))
+    max_t, max_l = nz * ny * (nx // 4 + 1), 18 * solid_zyx.size
+    tiles = np.zeros((max_t, 4), np.uint32); links = np.zeros(max_l, np.uint32); nl = C.c_int(0)
+    nt = aux.emu_chord_lists(C.c_int(nx), C.c_int(ny), C.c_int(nz), C.c_int(periodic), _p(flags), _p(nbr), _p(tiles), C.c_int(max_t), _p(links),
+                             C.c_int(max_l), C.byref(nl))
+    assert nt >= 0
+    return flags, nbr, tiles[:nt], links[:nl.value]
+
+
+@pytest.mark.parametrize("case", ["v60_64", "random_40x12x9", "random_periodic_24x10x8", "two_chords_136x6x5"])
+def test_emulated_chord_tiles_cover_the_fluid_quads_once_and_links_are_the_wall_links(aux, case):
+    """build_chord_lists (lbm_aux.cu): every quad holding a fluid cell belongs to exactly one (tile, lane); tiles start at an active
+    quad, are sorted in memory order and never cross a row; the links of a tile are exactly the (fluid cell, q) pairs whose
+    target x + e_q is a solid cell inside the box, with the target coordinates and opp(q) packed as the kernel expects, plus
+    the 19 self links of every fluid cell of a quad that also holds solid cells."""
+    rng = np.random.default_rng(5)
+    periodic = 0
+    if case == "v60_64":
+        solid = np.ascontiguousarray(np.transpose(R.v60_solid(R.RefConfig(NX=64, NY=64, NZ=64)), (2, 1, 0)))
+    elif case == "random_40x12x9":
+        solid = (rng.random((9, 12, 40)) < 0.35).astype(np.uint8)
+    elif case == "random_periodic_24x10x8":
+        solid = (rng.random((8, 10, 24)) < 0.3).astype(np.uint8); periodic = 7
+    else:      # a row longer than one tile with a solid gap wider than a tile between two chords
+        solid = np.ones((5, 6, 136 * 2), np.uint8); solid[:, :, 3:50] = 0; solid[:, :, 200:269] = 0; solid[2, 3, 120] = 0
+    nz, ny, nx = solid.shape
+    flags, nbr, tiles, links = _chord_lists(aux, solid, periodic)
+    fluid = solid == 0
+    quad_active = fluid.reshape(nz, ny, nx // 4, 4).any(-1)
+    seen = np.zeros_like(quad_active, dtype=np.int32)
+    prev_key = -1
+    want_links = set(); got_links = set(); got_self = set()
+    for t in range(len(tiles)):
+        q0 = int(tiles[t, 0] & 0xfff); nl = int(tiles[t, 0] >> 12); y = int(tiles[t, 1] & 0xffff); z = int(tiles[t, 1] >> 16)
+        mask = int(tiles[t, 2]); lb = int(tiles[t, 3])
+        assert mask & 1 and quad_active[z, y, q0]
+        key = (z * ny + y) * (nx // 4) + q0
+        assert key > prev_key; prev_key = key
+        for l in range(32):
+            if (mask >> l) & 1:
+                assert q0 + l < nx // 4 and quad_active[z, y, q0 + l]
+                seen[z, y, q0 + l] += 1
+            elif q0 + l < nx // 4:
+                assert not quad_active[z, y, q0 + l]
+        for L in links[lb:lb + nl]:
+            L = int(L)
+            l, c, q, qd, dy, dz, xt = L & 31, (L >> 5) & 3, (L >> 7) & 31, (L >> 12) & 31, ((L >> 17) & 3) - 1, ((L >> 19) & 3) - 1, L >> 21
+            assert (mask >> l) & 1
+            x = 4 * (q0 + l) + c
+            if qd == q and dy == 0 and dz == 0 and xt == x and (q == 0 or qd != _OPP[q]):      # self link (a quad the chord ends in)
+                assert not fluid[z, y, 4 * (q0 + l):4 * (q0 + l) + 4].all() and fluid[z, y, x]
+                got_self.add((z, y, x, q))
+                continue
+            assert qd == _OPP[q] and dy == _CY[q] and dz == _CZ[q]
+            assert xt == (x + _CX[q]) % nx
+            got_links.add((z, y, x, q))
+    assert np.array_equal(seen, quad_active.astype(np.int32))
+    per = [(periodic >> d) & 1 for d in range(3)]
+    for z, y, x in zip(*np.nonzero(fluid)):
+        for q in range(1, 19):
+            xt, yt, zt = x + _CX[q], y + _CY[q], z + _CZ[q]
+            if not per[0] and not 0 <= xt < nx or not per[1] and not 0 <= yt < ny or not per[2] and not 0 <= zt < nz:
+                continue
+            if solid[zt % nz, yt % ny, xt % nx]:
+                want_links.add((int(z), int(y), int(x), q))
+    quad_mixed = quad_active & ~fluid.reshape(nz, ny, nx // 4, 4).all(-1)
+    want_self = {(int(z), int(y), int(x), q) for z, y, x in zip(*np.nonzero(fluid & np.repeat(quad_mixed, 4, axis=2))) for q in range(19)}
+    assert got_links == want_links and got_self == want_self and len(links) == len(want_links) + len(want_self)
+
+
+def test_emulated_chord_tile_pressure_gradient_equals_the_grid_kernel(aux):
+    """pressure_gradient_chord_kernel (the producer over the four-cell kernel's tiles) against the recorded drive run."""
+    z = np.load(os.path.join(GOLD, "reference_run_neighbours.npz"))
+    n = int(z["n"])
+    solid = np.ascontiguousarray(H.to_dev_scalar(z["solid"]).astype(np.uint8))
+    flags, nbr, tiles, links = _chord_lists(aux, solid, 0)
+    rho, u = H.to_dev_scalar(z["rho"]), H.to_dev_vec(z["u"])
+    for scale, key in ((1.0, "bf_force_drive"), (0.5, "bf_mixed_drive")):
+        bf = np.zeros_like(u)
+        aux.emu_pressure_gradient_chord(*_dims(n), _p(rho), _p(flags), _p(bf), C.c_float(0.12), C.c_float(scale), C.c_int(1), _p(np.ascontiguousarray(tiles)),
+                                        C.c_int(len(tiles)))
+        assert np.array_equal(np.transpose(bf, (3, 2, 1, 0)), z[key])
