@@ -81,10 +81,11 @@ typedef struct {
     float porous_forch;       /* physical: F_eps/sqrt(K) [1/lu] */
     float K_lu, beta_lu;      /* reference: filter_paper.py:423-469 */
     float c_darcy, c_forch;   /* reference: constant folds of filter_paper.py:578-586 */
-    int vec;                  /* tuning: cells per thread along x (1, 2 or 4; 0 = auto: 4 in periodic boxes, 2 behind walls in
-                                 compat = physical, 1 behind walls in compat = reference) */
-    int block;                /* tuning: threads per CTA (0 = auto; 64 / 128 / 256; behind walls in compat = physical the
-                                 codes 65 / 66 select 64-thread CTAs at 16 / 24 resident warps per SM, default 20) */
+    int vec;                  /* tuning: cells per thread along x (1, 2 or 4; 0 = auto: 4 in periodic boxes and behind walls in
+                                 compat = physical -- chord-fitted tiles, csrc/lbm_phys_chord.cuh -- when nx % 4 == 0 and
+                                 nx <= 2048, else 2 / 1; 1 behind walls in compat = reference) */
+    int block;                /* tuning: threads per CTA (0 = auto; 64 / 128 / 256; behind walls in compat = physical these are
+                                 occupancy codes of the kernel `vec` selects, see csrc/lbm_step.cu) */
     float drive_max_force;    /* LBM_FEAT_DRIVE: clamp on |F| (PressureGradientDrive.MAX_PRESSURE_FORCE) ... */
     float drive_scale;        /* ... and the factor of the accumulation (1 in force mode, 0.5 in mixed mode) */
 } lbm_params;

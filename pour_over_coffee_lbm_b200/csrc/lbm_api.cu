@@ -154,14 +154,18 @@ static int make_grid(lbm_ctx *ctx, const lbm_params *p, Grid *g) {
 static bool phys_walls(const lbm_params &p) { return p.compat == LBM_COMPAT_PHYSICAL && (p.features & LBM_FEAT_WALLS); }
 
 static bool tma_eligible(const lbm_ctx *ctx);
+static bool tma_eligible_params(const lbm_ctx *ctx) {
+    const lbm_params &p = ctx->p;
+    return phys_walls(p) && ctx->tma_enabled && p.vec == 0 && !(p.periodic & 3) && p.nx % 16 == 0 && p.nx >= 16;
+}
 
 static int pick_vec(const lbm_ctx *ctx) {
     int vec = ctx->p.vec;
     if (phys_walls(ctx->p)) {
-        // two cells per thread on packed f32x2 registers (lbm_phys.cuh) on 8-byte rows, else one.  vec = 4 (128-bit
-        // loads, lane masks) and the TMA-staged kernel (LBM_TMA=1) are opt-in: measured on B200 they
-        // win on all-fluid boxes (vec = 4) or by 4 % on the V60 mask (TMA) but not across the board.
-        if (vec == 0) vec = 2;      // also what the TMA-staged kernel works on (64-cell rows, two cells per lane)
+        // four cells per thread on chord-fitted tiles (lbm_phys_chord.cuh) when rows are 16-byte multiples, else two cells per
+        // thread on packed f32x2 registers (lbm_phys.cuh) on 8-byte rows, else one.  The TMA-staged kernel (LBM_TMA=1, works on
+        // the two-cell lists) is opt-in.
+        if (vec == 0) vec = tma_eligible_params(ctx) ? 2 : 4;
         if (vec == 4 && (ctx->g.nx % 4 != 0 || ctx->g.nx < 8 || ctx->g.nx > 2048 || ctx->g.ny > 65535 || ctx->g.nz > 65535)) vec = 2;
         if (vec == 2 && (ctx->g.nx % 2 != 0 || ctx->g.nx < 4)) vec = 1;
         return vec;
@@ -297,6 +301,7 @@ int lbm_create(lbm_ctx **out, int device, const lbm_params *p) {
     // tuning / diagnosis knobs of the TMA-staged walls path (scripts/tune_v60.py)
     if (const char *v = getenv("LBM_TMA_VARIANT")) ctx->tma_variant = atoi(v);
     if (const char *v = getenv("LBM_TMA")) ctx->tma_enabled = atoi(v) != 0;
+
     CUDA_OK(nullptr, cudaSetDevice(device));
     cudaEventCreateWithFlags(&ctx->ev_boundary, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_comm, cudaEventDisableTiming);
@@ -448,6 +453,8 @@ static int make_launcher(lbm_ctx *ctx, const lbm_params &p, const lbm_fields *f,
     } else {
         L->main = lookup(p, vec, collide, &L->block);      // may fall back to the default CTA size for this variant
         if (!L->main) return fail(ctx, "no step kernel built for this feature combination");
+        if (chord_lists(ctx, vec))      // the chord kernels live on shared memory: take the largest carve-out
+            cudaFuncSetAttribute((const void *)L->main, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     }
     if (L->walls && (ctx->list_flags != f->flags || ctx->list_vec != vec || ctx->list_ty != ty || (int)ctx->tile_off.size() != ctx->g.nz + 1 || !ctx->d_nbr))
         return fail(ctx, "work lists are stale: call lbm_pack_flags on this flags field (after any geometry or vec change)");
@@ -467,17 +474,6 @@ static int launch_planes(lbm_ctx *ctx, StepArgs &a, const Launcher &L, int z_beg
         if (t1 <= t0) return 0;
         a.items = ctx->d_tiles; a.item_mask = ctx->d_tile_mask; a.item_begin = t0; a.n_items = t1 - t0; a.nbr = ctx->d_nbr;
         a.ctiles = ctx->d_ctiles; a.links = ctx->d_links;
-        a.regular = (getenv("LBM_REGULAR") && atoi(getenv("LBM_REGULAR"))) ? 1 : 0;
-        if (getenv("LBM_L2_WINDOW") && atoi(getenv("LBM_L2_WINDOW")) && ctx->d_ctiles && ctx->window_stream != s) {
-            // experiment: keep the tile list L2-resident (persisting access-policy window on the launching stream)
-            const size_t bytes = std::min((size_t)ctx->tile_off[ctx->g.nz] * sizeof(uint4), ctx->max_window);
-            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min(bytes, (size_t)64 << 20));
-            cudaStreamAttrValue v; memset(&v, 0, sizeof v);
-            v.accessPolicyWindow.base_ptr = ctx->d_ctiles; v.accessPolicyWindow.num_bytes = bytes; v.accessPolicyWindow.hitRatio = 1.0f;
-            v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting; v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-            cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &v);
-            ctx->window_stream = s;
-        }
         if (L.tma) {
             const TmaMaps *maps = nullptr;
             if (tensor_maps(ctx, a, L.tk.ty, &maps)) return 1;

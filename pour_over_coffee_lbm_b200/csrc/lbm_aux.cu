@@ -410,12 +410,9 @@ cudaError_t build_work_lists(const Grid &G, const uint8_t *flags, int vec, int t
 // 128-cell tiles, which make every tile of a V60 row a chord end.  Tile entry (uint4):
 //   .x = first quad | n_links << 12     .y = y | z << 16     .z = lane mask (bit l: quad first + l is active)
 //   .w = index of the tile's first wall link
-// Link (u32) = one 4-byte store the kernel does cooperatively after the collision: value = post-collision population q of
-// cell c of lane l, target = population plane qd of the cell (target x, y + dy, z + dz):
-//   bits 0-4 source lane, 5-6 cell of the quad, 7-11 q, 12-16 qd, 17-18 dy+1, 19-20 dz+1, 21-31 target x.
-// Two kinds: WALL links -- (fluid cell, q) whose target x + e_q is solid: f_q goes to the solid cell's slot of opp(q)
-// (halfway bounce-back on the write side, lbm_phys.cuh) -- and SELF links -- the 19 populations of a fluid cell of a quad
-// that also holds solid cells (a chord end): such a quad cannot be stored as one 128-bit vector.
+// Wall link (u32) = one (fluid cell, direction q) pair whose target x + e_q is solid: the post-collision f_q goes to the
+// solid cell's slot of opp(q) (halfway bounce-back on the write side, lbm_phys.cuh):
+//   bits 0-4 source lane, 5-6 cell of the quad, 7-11 q, 12-16 opp(q), 17-18 cy(q)+1, 19-20 cz(q)+1, 21-31 target x.
 // The kernels below are plain (one thread per row / per tile) so that tests/emu can run them on the CPU; they run once
 // per geometry change.
 __device__ __forceinline__ bool quad_active(const uint8_t *row, int q) {
@@ -447,15 +444,11 @@ __global__ void chord_fill_kernel(Grid G, const uint8_t *flags, const unsigned l
         for (int l = 0; l < 32 && q + l < nq; ++l) {
             if (!quad_active(row, q + l)) continue;
             mask |= 1u << l;
-            int n_fluid = 0;
             for (int c = 0; c < 4; ++c) {
                 const int x = 4 * (q + l) + c;
                 const unsigned fl = row[x];
-                if (fl & LBM_FLAG_SOLID) continue;
-                ++n_fluid;
-                if (fl & LBM_FLAG_NEAR) nl += __popc((unsigned)nbr[base + x] & 0x7fffeu);
+                if (!(fl & LBM_FLAG_SOLID) && (fl & LBM_FLAG_NEAR)) nl += __popc((unsigned)nbr[base + x] & 0x7fffeu);
             }
-            if (n_fluid < 4) nl += Q * n_fluid;                   // a quad the chord ends in: its fluid cells are stored through self links
         }
         tiles[t] = make_uint4((unsigned)q, (unsigned)y | ((unsigned)z << 16), mask, 0u);
         tile_links[t] = nl;
@@ -474,15 +467,10 @@ __global__ void chord_links_kernel(Grid G, const uint8_t *flags, const unsigned 
     unsigned o = begin;
     for (int l = 0; l < 32; ++l) {
         if (!((e.z >> l) & 1u)) continue;
-        const bool mixed = ((row[4 * (q0 + l)] | row[4 * (q0 + l) + 1] | row[4 * (q0 + l) + 2] | row[4 * (q0 + l) + 3]) & LBM_FLAG_SOLID) != 0;
         for (int c = 0; c < 4; ++c) {
             const int x = 4 * (q0 + l) + c;
             const unsigned fl = row[x];
-            if (fl & LBM_FLAG_SOLID) continue;
-            if (mixed)                                            // self links: population q of this cell -> its own slot
-                for (int q = 0; q < Q; ++q)
-                    links[o++] = (unsigned)l | ((unsigned)c << 5) | ((unsigned)q << 7) | ((unsigned)q << 12) | (1u << 17) | (1u << 19) | ((unsigned)x << 21);
-            if (!(fl & LBM_FLAG_NEAR)) continue;
+            if ((fl & LBM_FLAG_SOLID) || !(fl & LBM_FLAG_NEAR)) continue;
             const unsigned m = (unsigned)nbr[base + x];
             for (int q = 1; q < Q; ++q) {
                 if (!((m >> opp(q)) & 1u)) continue;

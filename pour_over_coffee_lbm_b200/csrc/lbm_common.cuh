@@ -44,7 +44,6 @@ struct StepArgs {
     const unsigned long long *nbr;     // per cell (valid where NEAR): solid-source bits | out-of-box bits << 32
     // chord-fitted tiles of the four-cell walls kernel (lbm_phys_chord.cuh): one uint4 per tile, one u32 per wall link
     const uint4 *ctiles; const unsigned *links;
-    int regular;           // experiment (LBM_REGULAR=1, all-fluid box with solid faces only): tile coordinates computed, not loaded
     // fused pressure-gradient drive (LBM_FEAT_DRIVE): rho of the previous step, clamp and scale of the force
     const float *rho_src; float drive_max_force, drive_scale;
     int write_macro;

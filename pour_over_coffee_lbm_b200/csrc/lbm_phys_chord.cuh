@@ -19,12 +19,18 @@
 //   * the two cell pairs of a thread are collided one after the other (packed f32x2); each pair reads its 19 inputs from the
 //     row (LDS.64, or two LDS.32 for the shifted ones) directly into register pairs and writes its results back into the
 //     lane's own words (STS.64), so only one pair is in registers at a time;
-//   * write-back: LDS.128 + 128-bit streaming store per population for all-fluid quads.  Everything irregular is a
-//     precomputed LINK of the tile (one u32 per (cell, population)): the wall links of halfway bounce-back on the write side
-//     (post-collision f_q of a fluid cell -> slot opp(q) of its solid neighbour, lbm_phys.cuh) and the "self" links of the
-//     fluid cells of a quad a chord ends in (19 each).  All 32 lanes walk the link list together, one link per lane and
-//     round (LDS + one 4-byte store); a tile without links skips it on a warp-uniform branch.  The neighbour masks are not
-//     read by this kernel, the flag word only for the solid / filter / LES bits;
+//   * write-back: LDS.128 + 128-bit streaming store per population for all-fluid quads; the fluid cells of a quad a chord
+//     ends in go out one cell at a time with lane q < 19 storing population q (warp-uniform loop over a ballot).  Halfway
+//     bounce-back stays on the write side (post-collision f_q of a fluid cell -> slot opp(q) of its solid neighbour,
+//     lbm_phys.cuh) but is a precomputed WALL LINK list of the tile (one u32 per (cell, q)): all 32 lanes walk it together,
+//     one link per lane and round (LDS + one 4-byte store), the first round prefetched with the tile.  The neighbour masks
+//     are not read by this kernel, the flag word only for the solid / filter / LES bits;
+//   * tried on top of this and rejected, with numbers (profiles/r02_tune_chord_pipelined.log, r02_exp_l2_prefetch.log,
+//     r02_exp_entry_load.log; V60 512^3, same box): a persistent launch with two stages per warp and the next tile's loads in
+//     flight during the collision (8 warps per SM 1.92 ms, 10 warps 2.20 ms, against 1.87 ms for one tile per warp at 16 warps:
+//     half the warps do hide the memory latency, but then the ~6 cycles between two issues of one warp are the limit);
+//     prefetching the inputs of the tile 256 .. 16384 places ahead into L2 (1.78 .. 2.19 ms against 1.79 ms); a persisting
+//     L2 window over the tile list and tile coordinates computed instead of loaded (no change);
 //   * LBM_FEAT_DRIVE: the pressure-gradient drive (pressure_gradient_drive.py:124-193) is evaluated from the PREVIOUS
 //     step's rho inside this kernel (same statements as the stand-alone producer, lbm_common.cuh) while the populations
 //     are still in flight, and added to the body force: the separate producer pass and its 12 B force round trip disappear.
@@ -48,125 +54,159 @@ __device__ __forceinline__ float4 lds128(unsigned a) {
 }
 
 constexpr int CHORD_ROW = 4 + 128 + 4;                // floats per staged population row: left edge | 32 lanes x 4 | right edge
-constexpr int CHORD_WARP_BYTES = Q * CHORD_ROW * 4;   // 10336 B per warp
+constexpr unsigned CHORD_ROWB = CHORD_ROW * 4;        // bytes per row
+constexpr int CHORD_STAGE = Q * CHORD_ROW;            // floats per stage (one tile): 10336 B
 
-template <bool FORCED, bool LES, bool POROUS, bool DRIVE, int BLOCK, bool COLLIDE, int MINB>
-__global__ void __launch_bounds__(BLOCK, MINB) phys_chord_kernel(const __grid_constant__ StepArgs P) {
-    constexpr bool HAS_F = FORCED || DRIVE;
-    __shared__ __align__(16) float stage[BLOCK / 32][Q][CHORD_ROW];
-    const Grid &G = P.g;
-    const unsigned lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
-    const int w = (blockIdx.x * BLOCK + threadIdx.x) >> 5;
-    if (w >= P.n_items) return;                                          // warp-uniform
-    const uint4 e = __ldg(P.ctiles + P.item_begin + w);
-    const unsigned lmask = e.z, n_links = e.x >> 12;
-    const bool live = ((lmask >> lane) & 1u) != 0;
-    const int x0 = ((int)(e.x & 0xfffu) + (live ? (int)lane : 0)) * 4;  // dead lanes shadow lane 0 (always live) for their addresses
-    const int y = (int)(e.y & 0xffffu), z = (int)(e.y >> 16);
-    const int zp = z + G.zg;
-    const unsigned row0 = ((unsigned)zp * (unsigned)G.ny + (unsigned)y) * (unsigned)G.nx;
-    const unsigned own = row0 + (unsigned)x0;
-    const unsigned vol = (unsigned)G.vol;
-
-    // neighbour rows as 32-bit index deltas: periodic wrap, else clamp (a clamped source lies outside an open face and is
-    // replaced by w_q below)
+// what a lane knows about its tile from the entry (recomputed where needed: ~25 integer instructions)
+struct ChordGeom {
+    bool live;
+    int x0, y, z;
+    unsigned lmask, own, row0;
+    int dym, dyq, dzm, dzq;          // neighbour rows as 32-bit index deltas: periodic wrap, else clamp (a clamped source lies
+};                                   // outside an open face and is replaced by w_q)
+__device__ __forceinline__ ChordGeom chord_decode(const uint4 e, const unsigned lane, const Grid &G) {
+    ChordGeom t;
+    t.lmask = e.z;
+    t.live = ((e.z >> lane) & 1u) != 0;
+    t.x0 = ((int)(e.x & 0xfffu) + (t.live ? (int)lane : 0)) * 4;      // dead lanes shadow lane 0 (always live) for their addresses
+    t.y = (int)(e.y & 0xffffu); t.z = (int)(e.y >> 16);
+    t.row0 = ((unsigned)(t.z + G.zg) * (unsigned)G.ny + (unsigned)t.y) * (unsigned)G.nx;
+    t.own = t.row0 + (unsigned)t.x0;
     const int nxi = G.nx, plane = (int)G.plane;
-    int dym = -nxi; if (y == 0) dym = G.per_y ? (G.ny - 1) * nxi : 0;
-    int dyq = nxi; if (y == G.ny - 1) dyq = G.per_y ? -(G.ny - 1) * nxi : 0;
-    int dzm = -plane, dzq = plane;
+    t.dym = -nxi; if (t.y == 0) t.dym = G.per_y ? (G.ny - 1) * nxi : 0;
+    t.dyq = nxi; if (t.y == G.ny - 1) t.dyq = G.per_y ? -(G.ny - 1) * nxi : 0;
+    t.dzm = -plane; t.dzq = plane;
     if (!G.zg) {
-        if (z == 0) dzm = G.per_z ? (G.nz - 1) * plane : 0;
-        if (z == G.nz - 1) dzq = G.per_z ? -(G.nz - 1) * plane : 0;
+        if (t.z == 0) t.dzm = G.per_z ? (G.nz - 1) * plane : 0;
+        if (t.z == G.nz - 1) t.dzq = G.per_z ? -(G.nz - 1) * plane : 0;
     }
-    // shared-window address of this lane's words of row 0; row q is q * CHORD_ROW * 4 bytes further
-    // (dead lanes read lane 0's words -- benign values for the arithmetic they run along with the warp -- and write nothing)
-    const unsigned s_own = (unsigned)__cvta_generic_to_shared(&stage[wib][0][4 + 4 * (live ? lane : 0u)]);
-    constexpr unsigned ROWB = CHORD_ROW * 4;
+    return t;
+}
 
-    // (1) populations: global -> shared, nothing held in registers while in flight
-    if (live) {
+// (1) populations: global -> shared, nothing held in registers while in flight.  s_own = shared-window address of this lane's
+// words of row 0 of the stage.
+__device__ __forceinline__ void chord_issue_loads(const StepArgs &P, const ChordGeom &t, const unsigned lane, const unsigned s_own) {
+    const Grid &G = P.g;
+    const unsigned vol = (unsigned)G.vol;
+    if (t.live) {
         const float *rowp[3][3];
 #pragma unroll
         for (int dz = -1; dz <= 1; ++dz)
 #pragma unroll
             for (int dy = -1; dy <= 1; ++dy)
-                rowp[dz + 1][dy + 1] = P.src + (own + (unsigned)(dy < 0 ? dym : (dy > 0 ? dyq : 0)) + (unsigned)(dz < 0 ? dzm : (dz > 0 ? dzq : 0)));
+                rowp[dz + 1][dy + 1] = P.src + (t.own + (unsigned)(dy < 0 ? t.dym : (dy > 0 ? t.dyq : 0)) + (unsigned)(dz < 0 ? t.dzm : (dz > 0 ? t.dzq : 0)));
         static_for<0, Q>([&](auto qq) {
             constexpr int q = decltype(qq)::value;
-            cp_async16(s_own + q * ROWB, plane_of(rowp[1 - cz(q)][1 - cy(q)], vol, q));
+            cp_async16(s_own + q * CHORD_ROWB, plane_of(rowp[1 - cz(q)][1 - cy(q)], vol, q));
         });
         // x-1 / x+4 neighbour of the quad when no live lane brings it: first / last lane, a gap in the lane mask, row ends
-        if (lane == 0 || !((lmask >> (lane - 1)) & 1u)) {
-            int dxm = -1; if (x0 == 0) dxm = G.per_x ? G.nx - 1 : 0;
+        if (lane == 0 || !((t.lmask >> (lane - 1)) & 1u)) {
+            int dxm = -1; if (t.x0 == 0) dxm = G.per_x ? G.nx - 1 : 0;
             static_for<0, Q>([&](auto qq) {
                 constexpr int q = decltype(qq)::value;
-                if constexpr (cx(q) > 0) cp_async4(s_own + q * ROWB - 4, plane_of(rowp[1 - cz(q)][1 - cy(q)], vol, q) + dxm);
+                if constexpr (cx(q) > 0) cp_async4(s_own + q * CHORD_ROWB - 4, plane_of(rowp[1 - cz(q)][1 - cy(q)], vol, q) + dxm);
             });
         }
-        if (lane == 31 || !((lmask >> (lane + 1)) & 1u)) {
-            int dxq = 4; if (x0 == G.nx - 4) dxq = G.per_x ? -(G.nx - 4) : 3;
+        if (lane == 31 || !((t.lmask >> (lane + 1)) & 1u)) {
+            int dxq = 4; if (t.x0 == G.nx - 4) dxq = G.per_x ? -(G.nx - 4) : 3;
             static_for<0, Q>([&](auto qq) {
                 constexpr int q = decltype(qq)::value;
-                if constexpr (cx(q) < 0) cp_async4(s_own + q * ROWB + 16, plane_of(rowp[1 - cz(q)][1 - cy(q)], vol, q) + dxq);
+                if constexpr (cx(q) < 0) cp_async4(s_own + q * CHORD_ROWB + 16, plane_of(rowp[1 - cz(q)][1 - cy(q)], vol, q) + dxq);
             });
         }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
+}
 
-    // (2) flags, body force, phase, rho stencil of the fused drive: plain loads (registers are free while the populations travel)
-    const unsigned flag_word = __ldg(reinterpret_cast<const unsigned *>(P.flags + own));
-    bool has_force = false, has_phase = false;
-    float F[3][4], ph[4];
+// (2) flags, body force, phase, rho stencil of the fused drive, first round of wall links: plain loads into registers
+struct ChordAux {
+    unsigned flag_word, link0;
+    float4 bf[3], ph;
+    float4 r, rym, ryp, rzm, rzp;
+    float rxm, rxp;
+};
+template <bool FORCED, bool DRIVE>
+__device__ __forceinline__ void chord_load_aux(const StepArgs &P, const ChordGeom &t, const uint4 e, const unsigned lane, ChordAux &a) {
+    const Grid &G = P.g;
+    const unsigned vol = (unsigned)G.vol;
+    a.flag_word = __ldg(reinterpret_cast<const unsigned *>(P.flags + t.own));
+    a.link0 = 0;
+    if (lane < (e.x >> 12)) a.link0 = __ldg(P.links + e.w + lane);
+    if constexpr (FORCED) {
+        if (P.force != nullptr) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) a.bf[d] = __ldg(reinterpret_cast<const float4 *>(plane_of(P.force + t.own, vol, d)));
+        }
+        if (P.phase != nullptr) a.ph = __ldg(reinterpret_cast<const float4 *>(P.phase + t.own));
+    }
+    if constexpr (DRIVE) {
+        const float *pr = P.rho_src + t.own;
+        a.r = __ldg(reinterpret_cast<const float4 *>(pr));
+        a.rym = __ldg(reinterpret_cast<const float4 *>(pr + t.dym)); a.ryp = __ldg(reinterpret_cast<const float4 *>(pr + t.dyq));
+        a.rzm = __ldg(reinterpret_cast<const float4 *>(pr + t.dzm)); a.rzp = __ldg(reinterpret_cast<const float4 *>(pr + t.dzq));
+        a.rxm = __ldg(pr - (t.x0 > 0 ? 1 : 0)); a.rxp = __ldg(pr + (t.x0 + 4 < G.nx ? 4 : 3));
+    }
+}
+
+// body force of the lane's four cells: the fused pressure-gradient drive (from the previous step's rho) + the body_force field.
+// Runs BEFORE the populations have landed, i.e. inside the memory wait.
+template <bool FORCED, bool DRIVE>
+__device__ __forceinline__ void chord_force(const StepArgs &P, const ChordGeom &t, const ChordAux &a, float (&F)[3][4], float (&ph)[4]) {
+    const Grid &G = P.g;
 #pragma unroll
     for (int c = 0; c < 4; ++c) { F[0][c] = F[1][c] = F[2][c] = 0.0f; ph[c] = 0.0f; }
-    if constexpr (HAS_F) {
-        has_phase = FORCED && P.phase != nullptr;
-        has_force = DRIVE || (FORCED && (P.force != nullptr || (has_phase && P.gravity_lu != 0.0f)));
-        float4 bf[3];
-        bool have_bf = false;
-        if constexpr (FORCED) {
-            have_bf = P.force != nullptr;
-            if (have_bf) {
+    if constexpr (DRIVE) {
+        const float r0[4] = {a.r.x, a.r.y, a.r.z, a.r.w}, lo[4] = {a.rxm, a.r.x, a.r.y, a.r.z}, hi[4] = {a.r.y, a.r.z, a.r.w, a.rxp};
+        const float ym[4] = {a.rym.x, a.rym.y, a.rym.z, a.rym.w}, yq[4] = {a.ryp.x, a.ryp.y, a.ryp.z, a.ryp.w};
+        const float zm[4] = {a.rzm.x, a.rzm.y, a.rzm.z, a.rzm.w}, zq[4] = {a.rzp.x, a.rzp.y, a.rzp.z, a.rzp.w};
+        const int kg = G.z0 + t.z;
+        const int ypos = t.y == 0 ? -1 : (t.y == G.ny - 1 ? 1 : 0), zpos = kg == 0 ? -1 : (kg == G.nz_global - 1 ? 1 : 0);
 #pragma unroll
-                for (int d = 0; d < 3; ++d) bf[d] = __ldg(reinterpret_cast<const float4 *>(plane_of(P.force + own, vol, d)));
-            }
-            if (has_phase) { const float4 t = __ldg(reinterpret_cast<const float4 *>(P.phase + own)); ph[0] = t.x; ph[1] = t.y; ph[2] = t.z; ph[3] = t.w; }
+        for (int c = 0; c < 4; ++c) {
+            const int x = t.x0 + c;
+            const float gx = pressure_gradient_diff(r0[c], lo[c], hi[c], x == 0 ? -1 : (x == G.nx - 1 ? 1 : 0));
+            const float gy = pressure_gradient_diff(r0[c], ym[c], yq[c], ypos);
+            const float gz = pressure_gradient_diff(r0[c], zm[c], zq[c], zpos);
+            pressure_gradient_value(r0[c], gx, gy, gz, P.drive_max_force, P.drive_scale, F[0][c], F[1][c], F[2][c]);
         }
-        if constexpr (DRIVE) {
-            const float *pr = P.rho_src + own;
-            const float4 r = __ldg(reinterpret_cast<const float4 *>(pr));
-            const float4 rym = __ldg(reinterpret_cast<const float4 *>(pr + dym)), ryp = __ldg(reinterpret_cast<const float4 *>(pr + dyq));
-            const float4 rzm = __ldg(reinterpret_cast<const float4 *>(pr + dzm)), rzp = __ldg(reinterpret_cast<const float4 *>(pr + dzq));
-            const float rxm = __ldg(pr - (x0 > 0 ? 1 : 0)), rxp = __ldg(pr + (x0 + 4 < nxi ? 4 : 3));
-            const float r0[4] = {r.x, r.y, r.z, r.w}, lo[4] = {rxm, r.x, r.y, r.z}, hi[4] = {r.y, r.z, r.w, rxp};
-            const float ym[4] = {rym.x, rym.y, rym.z, rym.w}, yq[4] = {ryp.x, ryp.y, ryp.z, ryp.w};
-            const float zm[4] = {rzm.x, rzm.y, rzm.z, rzm.w}, zq[4] = {rzp.x, rzp.y, rzp.z, rzp.w};
-            const int kg = G.z0 + z;
-            const int ypos = y == 0 ? -1 : (y == G.ny - 1 ? 1 : 0), zpos = kg == 0 ? -1 : (kg == G.nz_global - 1 ? 1 : 0);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int x = x0 + c;
-                const float gx = pressure_gradient_diff(r0[c], lo[c], hi[c], x == 0 ? -1 : (x == nxi - 1 ? 1 : 0));
-                const float gy = pressure_gradient_diff(r0[c], ym[c], yq[c], ypos);
-                const float gz = pressure_gradient_diff(r0[c], zm[c], zq[c], zpos);
-                pressure_gradient_value(r0[c], gx, gy, gz, P.drive_max_force, P.drive_scale, F[0][c], F[1][c], F[2][c]);
-            }
-        }
-        if (have_bf) {      // body_force (+ drive: the sum the producer leaves in body_force in accumulate mode)
-            const float b[3][4] = {{bf[0].x, bf[0].y, bf[0].z, bf[0].w}, {bf[1].x, bf[1].y, bf[1].z, bf[1].w}, {bf[2].x, bf[2].y, bf[2].z, bf[2].w}};
+    }
+    if constexpr (FORCED) {
+        if (P.force != nullptr) {      // body_force (+ drive: the sum the producer leaves in body_force in accumulate mode)
+            const float b[3][4] = {{a.bf[0].x, a.bf[0].y, a.bf[0].z, a.bf[0].w}, {a.bf[1].x, a.bf[1].y, a.bf[1].z, a.bf[1].w},
+                                   {a.bf[2].x, a.bf[2].y, a.bf[2].z, a.bf[2].w}};
 #pragma unroll
             for (int d = 0; d < 3; ++d)
 #pragma unroll
                 for (int c = 0; c < 4; ++c) F[d][c] = DRIVE ? b[d][c] + F[d][c] : b[d][c];
         }
+        if (P.phase != nullptr) { ph[0] = a.ph.x; ph[1] = a.ph.y; ph[2] = a.ph.z; ph[3] = a.ph.w; }
     }
-    unsigned fl[4];
+}
+
+// (3) + (4): collide the tile staged at s_own (after its cp.async group has landed and the warp has synchronised), write back.
+// s_row0 = shared-window address of word 0 of lane 0 in row 0 of the stage, s_park = of this lane's 8 bytes in the warp's
+// 4 x 256 B parking area for the first pair's rho, u.
+template <bool FORCED, bool LES, bool POROUS, bool DRIVE, bool COLLIDE>
+__device__ __forceinline__ void chord_compute_store(const StepArgs &P, const ChordGeom &t, const uint4 e, const ChordAux &a, const float (&F)[3][4],
+                                                    const float (&ph)[4], const unsigned lane, const unsigned s_own, const unsigned s_row0,
+                                                    const unsigned s_park) {
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr bool HAS_F = FORCED || DRIVE;
+    constexpr unsigned ROWB = CHORD_ROWB;
+    const Grid &G = P.g;
+    const unsigned vol = (unsigned)G.vol, own = t.own, n_links = e.x >> 12;
+    const int x0 = t.x0, y = t.y, z = t.z;
+    const bool live = t.live;
+    const bool has_phase = FORCED && P.phase != nullptr;
+    const bool has_force = DRIVE || (FORCED && (P.force != nullptr || (has_phase && P.gravity_lu != 0.0f)));
+    unsigned fl[4], mine_bits = 0;
     bool mine[4], all_mine = true;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        fl[c] = (flag_word >> (8 * c)) & 0xffu;
+        fl[c] = (a.flag_word >> (8 * c)) & 0xffu;
         mine[c] = live && !(fl[c] & LBM_FLAG_SOLID);
         all_mine &= mine[c];
+        mine_bits |= mine[c] ? (1u << c) : 0u;
     }
     // open faces: sources outside the box deliver w_q
     bool ylo = false, yhi = false, zlo = false, zhi = false, xlo = false, xhi = false;
@@ -178,13 +218,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) phys_chord_kernel(const __grid_co
     }
     const bool on_face = ylo || yhi || zlo || zhi || xlo || xhi;
 
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    __syncwarp();
-
-    // (3) the two cell pairs, one after the other.  Pair h = cells 2h, 2h + 1 of the quad; population q of those cells:
-    //     cx = 0: words 2h, 2h + 1 of the lane; cx > 0 (source x - 1): words 2h - 1, 2h; cx < 0 (source x + 1): words 2h + 1, 2h + 2.
-    //     Before pair 0 writes its results into words 0, 1, every word of pair 1 that a result could overwrite is taken:
-    //     the lane's own word 1 (cx > 0) and the next lane's word 0 (cx < 0).
+    // The two cell pairs, one after the other.  Pair h = cells 2h, 2h + 1 of the quad; population q of those cells:
+    //   cx = 0: words 2h, 2h + 1 of the lane; cx > 0 (source x - 1): words 2h - 1, 2h; cx < 0 (source x + 1): words 2h + 1, 2h + 2.
+    // Before pair 0 writes its results into words 0, 1, every word of pair 1 that a result could overwrite is taken:
+    // the lane's own word 1 (cx > 0) and the next lane's word 0 (cx < 0).
     float keep[Q];
     static_for<0, Q>([&](auto qq) {
         constexpr int q = decltype(qq)::value;
@@ -196,10 +233,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) phys_chord_kernel(const __grid_co
         P2 fp[Q];
         static_for<0, Q>([&](auto qq) {
             constexpr int q = decltype(qq)::value;
-            const unsigned a = s_own + q * ROWB + 8 * h;
-            if constexpr (cx(q) == 0) fp[q] = lds64(a);
-            else if constexpr (cx(q) > 0) fp[q] = h == 0 ? p2_make(lds32(a - 4), lds32(a)) : p2_make(keep[q], lds32(a));
-            else fp[q] = h == 0 ? p2_make(lds32(a + 4), lds32(a + 8)) : p2_make(lds32(a + 4), keep[q]);
+            const unsigned sa = s_own + q * ROWB + 8 * h;
+            if constexpr (cx(q) == 0) fp[q] = lds64(sa);
+            else if constexpr (cx(q) > 0) fp[q] = h == 0 ? p2_make(lds32(sa - 4), lds32(sa)) : p2_make(keep[q], lds32(sa));
+            else fp[q] = h == 0 ? p2_make(lds32(sa + 4), lds32(sa + 8)) : p2_make(lds32(sa + 4), keep[q]);
         });
         if (on_face) {
             static_for<1, Q>([&](auto qq) {
@@ -224,15 +261,20 @@ __global__ void __launch_bounds__(BLOCK, MINB) phys_chord_kernel(const __grid_co
                 });
             }
         }
-        // rho, u of this pair: 64-bit stores now (default cache policy: the two halves of a sector meet in L2) instead of eight
-        // more registers held through the second collision
+        // rho, u: all-fluid quads go out as 128-bit vectors after the second pair (a sector written in two halves costs a fill
+        // from HBM: measured +0.23 ms per step at V60 512^3); the first pair's four values wait in shared memory, not in registers
         if (P.write_macro) {
-            if (mine[2 * h] && mine[2 * h + 1]) {
-                float *pu = P.u_dst + own + 2 * h;
-                *reinterpret_cast<unsigned long long *>(P.rho + own + 2 * h) = mac.rho.v;
-                *reinterpret_cast<unsigned long long *>(pu) = mac.ux.v;
-                *reinterpret_cast<unsigned long long *>(plane_of(pu, vol, 1)) = mac.uy.v;
-                *reinterpret_cast<unsigned long long *>(plane_of(pu, vol, 2)) = mac.uz.v;
+            if (all_mine) {
+                if (h == 0) {
+                    sts64(s_park, mac.rho); sts64(s_park + 256u, mac.ux); sts64(s_park + 512u, mac.uy); sts64(s_park + 768u, mac.uz);
+                } else {
+                    const P2 r0 = lds64(s_park), x0p = lds64(s_park + 256u), y0p = lds64(s_park + 512u), z0p = lds64(s_park + 768u);
+                    float *pu = P.u_dst + own;
+                    __stcs(reinterpret_cast<float4 *>(P.rho + own), make_float4(p2_lo(r0), p2_hi(r0), p2_lo(mac.rho), p2_hi(mac.rho)));
+                    __stcs(reinterpret_cast<float4 *>(pu), make_float4(p2_lo(x0p), p2_hi(x0p), p2_lo(mac.ux), p2_hi(mac.ux)));
+                    __stcs(reinterpret_cast<float4 *>(plane_of(pu, vol, 1)), make_float4(p2_lo(y0p), p2_hi(y0p), p2_lo(mac.uy), p2_hi(mac.uy)));
+                    __stcs(reinterpret_cast<float4 *>(plane_of(pu, vol, 2)), make_float4(p2_lo(z0p), p2_hi(z0p), p2_lo(mac.uz), p2_hi(mac.uz)));
+                }
             } else {
 #pragma unroll
                 for (int l = 0; l < 2; ++l)
@@ -247,7 +289,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) phys_chord_kernel(const __grid_co
         }
     }
 
-    // (4) write-back
+    // write-back
     if constexpr (COLLIDE) {
         if (all_mine) {
             float *pd = P.dst + own;
@@ -256,19 +298,53 @@ __global__ void __launch_bounds__(BLOCK, MINB) phys_chord_kernel(const __grid_co
                 __stcs(reinterpret_cast<float4 *>(plane_of(pd, vol, q)), lds128(s_own + q * ROWB));
             });
         }
-        // the tile's links: wall links (halfway bounce-back, write side) and the cells of quads a chord ends in
-        if (n_links) {                                                   // warp-uniform
-            __syncwarp();
-            const unsigned s_row = (unsigned)__cvta_generic_to_shared(&stage[wib][0][4]);
-            for (unsigned i = lane; i < n_links; i += 32u) {
-                const unsigned L = __ldg(P.links + e.w + i);
-                const float v = lds32(s_row + ((L >> 7) & 31u) * ROWB + (((L & 31u) << 2) + ((L >> 5) & 3u)) * 4u);
-                const unsigned cyl = (L >> 17) & 3u, czl = (L >> 19) & 3u;
-                const unsigned t = row0 + (L >> 21) + (unsigned)(cyl == 0 ? dym : (cyl == 2 ? dyq : 0)) + (unsigned)(czl == 0 ? dzm : (czl == 2 ? dzq : 0));
-                *plane_of(P.dst + t, vol, (int)((L >> 12) & 31u)) = v;
+        // quads a chord ends in (fluid and solid cells): their fluid cells go out one cell at a time, lane q < 19 storing population q
+        const unsigned mixed = __ballot_sync(FULL, live && !all_mine);
+        if (mixed | n_links) __syncwarp();                               // results of every lane are in the stage
+        for (unsigned m = mixed; m; m &= m - 1) {                        // warp-uniform
+            const int ls = __ffs(m) - 1;
+            const unsigned bits = __shfl_sync(FULL, mine_bits, ls), cell0 = __shfl_sync(FULL, own, ls);
+            if (lane < Q) {
+                float *pq = plane_of(P.dst + cell0, vol, (int)lane);
+                const unsigned sa = s_row0 + lane * ROWB + (unsigned)ls * 16u;
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if ((bits >> c) & 1u) pq[c] = lds32(sa + 4u * c);
             }
         }
+        // wall links (halfway bounce-back, write side): one link per lane and round, the first round was loaded with the tile
+        for (unsigned i = lane; i < n_links; i += 32u) {
+            const unsigned L = i < 32u ? a.link0 : __ldg(P.links + e.w + i);
+            const float v = lds32(s_row0 + ((L >> 7) & 31u) * ROWB + (((L & 31u) << 2) + ((L >> 5) & 3u)) * 4u);
+            const unsigned cyl = (L >> 17) & 3u, czl = (L >> 19) & 3u;
+            const unsigned tg = t.row0 + (L >> 21) + (unsigned)(cyl == 0 ? t.dym : (cyl == 2 ? t.dyq : 0)) + (unsigned)(czl == 0 ? t.dzm : (czl == 2 ? t.dzq : 0));
+            *plane_of(P.dst + tg, vol, (int)((L >> 12) & 31u)) = v;
+        }
     }
+}
+
+// One tile per warp (one launch of ceil(tiles / warps per CTA) CTAs).
+template <bool FORCED, bool LES, bool POROUS, bool DRIVE, int BLOCK, bool COLLIDE, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) phys_chord_kernel(const __grid_constant__ StepArgs P) {
+    __shared__ __align__(16) float stage[BLOCK / 32][CHORD_STAGE];
+    __shared__ __align__(8) float park[BLOCK / 32][4][64];
+    const unsigned lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+    const int w = (blockIdx.x * BLOCK + threadIdx.x) >> 5;
+    if (w >= P.n_items) return;                                          // warp-uniform
+    const uint4 e = __ldg(P.ctiles + P.item_begin + w);
+    const ChordGeom t = chord_decode(e, lane, P.g);
+    // dead lanes read lane 0's words -- benign values for the arithmetic they run along with the warp -- and write nothing
+    const unsigned s_row0 = (unsigned)__cvta_generic_to_shared(&stage[wib][4]);
+    const unsigned s_own = s_row0 + 16u * (t.live ? lane : 0u);
+    chord_issue_loads(P, t, lane, s_own);
+    ChordAux a{};
+    chord_load_aux<FORCED, DRIVE>(P, t, e, lane, a);
+    float F[3][4], ph[4];
+    chord_force<FORCED, DRIVE>(P, t, a, F, ph);
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
+    chord_compute_store<FORCED, LES, POROUS, DRIVE, COLLIDE>(P, t, e, a, F, ph, lane, s_own, s_row0,
+                                                             (unsigned)__cvta_generic_to_shared(&park[wib][0][2 * lane]));
 }
 
 #endif  // LBM_EMULATE_ON_HOST

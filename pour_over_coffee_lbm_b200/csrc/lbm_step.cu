@@ -30,8 +30,8 @@ constexpr int min_blocks() { return (VEC == 1 ? 1024 : 512) / BLOCK; }
 template <int VEC, int BLOCK>
 constexpr int min_blocks_phys_walls() { return VEC == 2 ? (BLOCK == 256 ? 2 : 640 / BLOCK) : min_blocks<VEC, BLOCK>(); }
 
-// chord kernel (lbm_phys_chord.cuh): 10.1 KB of shared memory per warp; 16 warps per SM = 128 registers, no spills.
-// Measured on B200, V60 512^3: 16 warps 1.82 ms, 18 / 20 warps (112 / 96 registers, ~90 B of spills) 1.99 ms.
+// chord kernel (lbm_phys_chord.cuh), 64-thread CTAs, one tile per warp: 10.1 KB of shared memory per warp, 8 CTAs per SM = 16
+// warps at 128 registers, no spills (measured on B200, V60 512^3: 16 warps 1.82 ms, 18 / 20 warps with ~90 B of spills 1.99 ms).
 template <int BLOCK>
 constexpr int chord_blocks() { return 512 / BLOCK; }
 
@@ -103,8 +103,8 @@ static StepKernel tuned() {
         // 128-thread CTAs with plain (not lane-mask predicated) loads
         // VEC = 4 (chord kernel): BLOCK = 128 -> 4 CTAs of 128 threads (16 warps, 128 registers); the code 256 selects
         // 64-thread CTAs at 6 per SM (12 warps, 168 registers, no spills)
-        // VEC = 4 (chord kernel), 64-thread CTAs: default 8 CTAs per SM (16 warps, 128 registers); block code 128 -> 9 CTAs (18 warps,
-        // 112 registers), 256 -> 128-thread CTAs, 4 per SM
+        // VEC = 4 (chord kernel, default 64-thread CTAs, 8 per SM): block code 128 -> 9 CTAs per SM (112 registers), 256 -> 128-thread
+        // CTAs, 4 per SM
         if constexpr (VEC == 4 && BLOCK == 256) return phys_chord_kernel<true, true, true, false, 128, true, 4>;
         else if constexpr (VEC == 4) return phys_chord_kernel<true, true, true, false, 64, true, 9>;
         else return phys_walls_kernel<true, true, true, VEC, BLOCK, true, min_blocks_phys_walls<VEC, BLOCK>()>;

@@ -485,7 +485,7 @@ def particles_couple_slab(engine: D3Q19Engine, ps: ParticleState, reaction: torc
         ps.active = active_all
     slab.reduce_ghost_up(reaction, engine.rank, engine.nranks, per_z)
     outs = [ps.drag_new, ps.u_fluid, ps.reynolds, ps.cd, ps.cell] + ([ps.drag, ps.drag_old] if relax >= 0.0 else [])
-    slab.allreduce_owned(outs, owned, active_all)
+    slab.allreduce_owned_packed(outs, owned, active_all)
 
 
 def particles_advance(engine: D3Q19Engine, ps: ParticleState, dt: float, center_x: float, center_y: float, bottom_z: float,

@@ -270,8 +270,7 @@ def _chord_lists(aux, solid_zyx, periodic):
 def test_emulated_chord_tiles_cover_the_fluid_quads_once_and_links_are_the_wall_links(aux, case):
     """build_chord_lists (lbm_aux.cu): every quad holding a fluid cell belongs to exactly one (tile, lane); tiles start at an active
     quad, are sorted in memory order and never cross a row; the links of a tile are exactly the (fluid cell, q) pairs whose
-    target x + e_q is a solid cell inside the box, with the target coordinates and opp(q) packed as the kernel expects, plus
-    the 19 self links of every fluid cell of a quad that also holds solid cells."""
+    target x + e_q is a solid cell inside the box, with the target coordinates and opp(q) packed as the kernel expects."""
     rng = np.random.default_rng(5)
     periodic = 0
     if case == "v60_64":
@@ -288,7 +287,7 @@ def test_emulated_chord_tiles_cover_the_fluid_quads_once_and_links_are_the_wall_
     quad_active = fluid.reshape(nz, ny, nx // 4, 4).any(-1)
     seen = np.zeros_like(quad_active, dtype=np.int32)
     prev_key = -1
-    want_links = set(); got_links = set(); got_self = set()
+    want_links = set(); got_links = set()
     for t in range(len(tiles)):
         q0 = int(tiles[t, 0] & 0xfff); nl = int(tiles[t, 0] >> 12); y = int(tiles[t, 1] & 0xffff); z = int(tiles[t, 1] >> 16)
         mask = int(tiles[t, 2]); lb = int(tiles[t, 3])
@@ -306,10 +305,6 @@ def test_emulated_chord_tiles_cover_the_fluid_quads_once_and_links_are_the_wall_
             l, c, q, qd, dy, dz, xt = L & 31, (L >> 5) & 3, (L >> 7) & 31, (L >> 12) & 31, ((L >> 17) & 3) - 1, ((L >> 19) & 3) - 1, L >> 21
             assert (mask >> l) & 1
             x = 4 * (q0 + l) + c
-            if qd == q and dy == 0 and dz == 0 and xt == x and (q == 0 or qd != _OPP[q]):      # self link (a quad the chord ends in)
-                assert not fluid[z, y, 4 * (q0 + l):4 * (q0 + l) + 4].all() and fluid[z, y, x]
-                got_self.add((z, y, x, q))
-                continue
             assert qd == _OPP[q] and dy == _CY[q] and dz == _CZ[q]
             assert xt == (x + _CX[q]) % nx
             got_links.add((z, y, x, q))
@@ -322,9 +317,7 @@ def test_emulated_chord_tiles_cover_the_fluid_quads_once_and_links_are_the_wall_
                 continue
             if solid[zt % nz, yt % ny, xt % nx]:
                 want_links.add((int(z), int(y), int(x), q))
-    quad_mixed = quad_active & ~fluid.reshape(nz, ny, nx // 4, 4).all(-1)
-    want_self = {(int(z), int(y), int(x), q) for z, y, x in zip(*np.nonzero(fluid & np.repeat(quad_mixed, 4, axis=2))) for q in range(19)}
-    assert got_links == want_links and got_self == want_self and len(links) == len(want_links) + len(want_self)
+    assert got_links == want_links and len(links) == len(want_links)
 
 
 def test_emulated_chord_tile_pressure_gradient_equals_the_grid_kernel(aux):

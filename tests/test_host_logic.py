@@ -217,7 +217,7 @@ def test_particle_coupling_on_a_slab_masks_ownership_and_exchanges(monkeypatch):
     ps._solver, ps.state, ps.reaction_force_tensor, ps.water_density, ps.water_viscosity = Solver(), State(), torch.zeros(3, 10, 4, 4), 965.3, 3e-4
     monkeypatch.setattr(slab, "exchange_planes", lambda t, r, w, p, group=None: calls.append(("ghosts_in", tuple(t.shape))))
     monkeypatch.setattr(slab, "reduce_ghost_up", lambda t, r, w, p, group=None: calls.append(("ghost_up", tuple(t.shape))))
-    monkeypatch.setattr(slab, "allreduce_owned", lambda ts, own, act, group=None: calls.append(("allreduce", len(ts), own.tolist(), act.tolist())))
+    monkeypatch.setattr(slab, "allreduce_owned_packed", lambda ts, own, act, group=None: calls.append(("allreduce", len(ts), own.tolist(), act.tolist())))
     monkeypatch.setattr(engine_mod, "particles_couple", lambda e, st, react, **kw: calls.append(("kernel", st.active.tolist(), kw["relax"])))
     ps.compute_two_way_coupling_forces(None, relax=0.8)
     assert calls == [("ghosts_in", (3, 10, 4, 4)), ("kernel", [0, 1, 0, 1], 0.8), ("ghost_up", (3, 10, 4, 4)),

@@ -200,7 +200,10 @@ def _particle_worker(rank, world, port, out, cuts):
                                   C.c_float(0.8))
     slab.reduce_ghost_up(torch.from_numpy(react), rank, world, False)
     outs = [torch.from_numpy(st[k]) for k in ("drag_new", "drag_old", "drag", "u_fluid", "reynolds", "cd", "cell")]
+    packed = [o.clone() for o in outs]
     slab.allreduce_owned(outs, owned, torch.from_numpy(st["active"]))
+    slab.allreduce_owned_packed(packed, owned, torch.from_numpy(st["active"]))        # one collective instead of seven: same bits
+    assert all(torch.equal(a, b) for a, b in zip(outs, packed))      # (the float sum turns the owner's -0.0 into +0.0, the packed one keeps its bits)
     gathered = [None] * world
     dist.all_gather_object(gathered, (z0, react[:, 1:-1].copy(), {k: st[k].copy() for k in ("drag_new", "drag_old", "drag", "u_fluid", "reynolds", "cd", "cell")},
                                       int((masked != 0).sum())))
