@@ -311,6 +311,10 @@ int  lbm_attach_nccl(lbm_ctx *ctx, const void *unique_id128, int rank, int nrank
 /* exchange the 5+5 outgoing populations of the slab's boundary planes of g (and optionally the
  * ghost planes of a 3-component vector field) with the z neighbours. */
 int  lbm_halo_exchange(lbm_ctx *ctx, float *g, float *vec3_or_null, void *stream);
+/* The same exchange for whole ghost planes of a scalar ([zp][y][x]) and / or a 3-component vector field: rho before the
+ * pressure-gradient producers read it across a slab interface (pressure_gradient_drive.py:124-177 reads rho[k -+ 1]), u before the
+ * particle gather.  lbm_step keeps rho's ghost planes current by itself when LBM_FEAT_DRIVE is on. */
+int  lbm_halo_exchange_field(lbm_ctx *ctx, float *scalar_or_null, float *vec3_or_null, void *stream);
 
 #ifdef __cplusplus
 }

@@ -96,6 +96,7 @@ SIGNATURES = {
     "lbm_nccl_unique_id": (C.c_int, [_P]),
     "lbm_attach_nccl": (C.c_int, [_P, _P, C.c_int, C.c_int]),
     "lbm_halo_exchange": (C.c_int, [_P, _P, _P, _P]),
+    "lbm_halo_exchange_field": (C.c_int, [_P, _P, _P, _P]),
 }
 
 

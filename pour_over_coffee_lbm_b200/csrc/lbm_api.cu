@@ -342,6 +342,7 @@ long long lbm_launch_count(lbm_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 int lbm_selftest_math(lbm_ctx *ctx, unsigned long long mismatches[7], void *stream) {
     if (!ctx || !mismatches) return fail(ctx, "null argument");
+    cudaSetDevice(ctx->device);      // launches follow the context's device, whatever the caller's current device is
     StepArgs a;
     memset(&a, 0, sizeof a);
     a.g = ctx->g;
@@ -360,6 +361,7 @@ int lbm_populations_changed(lbm_ctx *ctx) {
 
 int lbm_init_equilibrium(lbm_ctx *ctx, float *g, const float *rho, const float *u, float rho0, const float u0[3], void *stream) {
     if (!ctx || !g) return fail(ctx, "null argument");
+    cudaSetDevice(ctx->device);      // launches follow the context's device, whatever the caller's current device is
     const float z[3] = {0, 0, 0};
     CUDA_OK(ctx, launch_init_equilibrium(ctx->g, ctx->p.compat, g, rho, u, rho0, u0 ? u0 : z, (cudaStream_t)stream));
     ctx->launches++;
@@ -369,6 +371,7 @@ int lbm_init_equilibrium(lbm_ctx *ctx, float *g, const float *rho, const float *
 
 int lbm_build_v60_geometry(lbm_ctx *ctx, uint8_t *solid, int32_t *filter_zone, const float geom[5], void *stream) {
     if (!ctx || !geom) return fail(ctx, "null argument");
+    cudaSetDevice(ctx->device);      // launches follow the context's device, whatever the caller's current device is
     CUDA_OK(ctx, launch_v60_geometry(ctx->g, solid, filter_zone, geom, (cudaStream_t)stream));
     ctx->launches++;
     return 0;
@@ -376,6 +379,7 @@ int lbm_build_v60_geometry(lbm_ctx *ctx, uint8_t *solid, int32_t *filter_zone, c
 
 int lbm_pack_flags(lbm_ctx *ctx, uint8_t *flags, const uint8_t *solid, const int32_t *filter_zone, const int32_t *les_mask, void *stream) {
     if (!ctx || !flags || !solid) return fail(ctx, "null argument");
+    cudaSetDevice(ctx->device);      // launches follow the context's device, whatever the caller's current device is
     CUDA_OK(ctx, launch_pack_flags(ctx->g, flags, solid, filter_zone, les_mask, (cudaStream_t)stream));
     ctx->launches++;
     // active-tile list for the bulk kernel and the compact list of near-wall cells (synchronises the stream)
@@ -461,16 +465,20 @@ static int make_launcher(lbm_ctx *ctx, const lbm_params &p, const lbm_fields *f,
     return 0;
 }
 
-// launch one step on owned planes [z_begin, z_end)
+// launch one step on owned planes [z_begin, z_end); z_begin < 0: the two boundary planes 0 and nz - 1 of a slab in ONE launch
+// (dense: blockIdx.y strides by nz - 1; walls: the copy of the two planes' list entries behind the list, see build_work_lists)
 static int launch_planes(lbm_ctx *ctx, StepArgs &a, const Launcher &L, int z_begin, int z_end, cudaStream_t s) {
-    if (z_end <= z_begin) return 0;
+    const bool both = z_begin < 0;
+    if (!both && z_end <= z_begin) return 0;
     if (!L.walls) {
-        a.z_begin = z_begin; a.z_end = z_end;
+        a.z_begin = both ? 0 : z_begin; a.z_end = both ? ctx->g.nz : z_end; a.z_stride = both ? ctx->g.nz - 1 : 1;
         const long long per_plane = (long long)(ctx->g.nx / L.vec) * ctx->g.ny;
-        dim3 grid((unsigned)((per_plane + L.block - 1) / L.block), (unsigned)(z_end - z_begin));
+        dim3 grid((unsigned)((per_plane + L.block - 1) / L.block), (unsigned)(both ? 2 : z_end - z_begin));
         L.main<<<grid, L.block, 0, s>>>(a);
     } else {
-        const int t0 = ctx->tile_off[z_begin], t1 = ctx->tile_off[z_end];
+        const int nz = ctx->g.nz, n_t = ctx->tile_off[nz];
+        const int t0 = both ? n_t : ctx->tile_off[z_begin];
+        const int t1 = both ? n_t + (ctx->tile_off[1] - ctx->tile_off[0]) + (ctx->tile_off[nz] - ctx->tile_off[nz - 1]) : ctx->tile_off[z_end];
         if (t1 <= t0) return 0;
         a.items = ctx->d_tiles; a.item_mask = ctx->d_tile_mask; a.item_begin = t0; a.n_items = t1 - t0; a.nbr = ctx->d_nbr;
         a.ctiles = ctx->d_ctiles; a.links = ctx->d_links;
@@ -498,6 +506,7 @@ static int exchange(lbm_ctx *ctx, float *g, float *vec3, float *scalar, cudaStre
     const Grid &G = ctx->g;
     if (!G.zg) return 0;
     const size_t plane = (size_t)G.plane;
+    const int nq = g ? 5 : 0;                               // g == NULL: only the whole-plane fields travel
     float *top_owned = g + (size_t)(G.nz) * plane;          // physical plane nz   (last owned)
     float *bot_owned = g + (size_t)1 * plane;               // physical plane 1    (first owned)
     float *ghost_lo = g;                                    // physical plane 0
@@ -507,7 +516,7 @@ static int exchange(lbm_ctx *ctx, float *g, float *vec3, float *scalar, cudaStre
     const int up_r = (up % ctx->nranks + ctx->nranks) % ctx->nranks, down_r = (down % ctx->nranks + ctx->nranks) % ctx->nranks;
     if (ctx->nranks == 1) {     // single slab with ghosts ("virtual slab" test mode): periodic wrap onto itself
         if (!G.per_z) return 0;
-        for (int i = 0; i < 5; ++i) {
+        for (int i = 0; i < nq; ++i) {
             CUDA_OK(ctx, cudaMemcpyAsync(ghost_lo + (size_t)UP_Q[i] * G.vol, top_owned + (size_t)UP_Q[i] * G.vol, plane * 4, cudaMemcpyDeviceToDevice, s));
             CUDA_OK(ctx, cudaMemcpyAsync(ghost_hi + (size_t)DOWN_Q[i] * G.vol, bot_owned + (size_t)DOWN_Q[i] * G.vol, plane * 4, cudaMemcpyDeviceToDevice, s));
         }
@@ -534,7 +543,7 @@ static int exchange(lbm_ctx *ctx, float *g, float *vec3, float *scalar, cudaStre
     };
     int bad = 0;
     NCCL_OK(ctx, g_nccl.GroupStart());
-    for (int i = 0; i < 5; ++i) {
+    for (int i = 0; i < nq; ++i) {
         for (int pass = 0; pass < 2; ++pass) {
             const bool upward = (pass == 0) != swap_order;
             if (upward && has_up) bad |= post(true, top_owned + (size_t)UP_Q[i] * G.vol, ghost_hi + (size_t)DOWN_Q[i] * G.vol);
@@ -585,6 +594,7 @@ extern "C" {
 
 int lbm_step(lbm_ctx *ctx, lbm_fields *f, int nsteps, int write_macro_every, void *compute_stream, void *comm_stream) {
     if (!ctx || !f) return fail(ctx, "null argument");
+    cudaSetDevice(ctx->device);      // launches follow the context's device, whatever the caller's current device is
     if (!f->f_dst) return fail(ctx, "f_dst is NULL");
     const lbm_params &p = ctx->p;
     const int vec = pick_vec(ctx);
@@ -609,8 +619,10 @@ int lbm_step(lbm_ctx *ctx, lbm_fields *f, int nsteps, int write_macro_every, voi
         if (a.write_macro && (!f->rho || !f->u_dst)) return fail(ctx, "write_macro requested but rho/u_dst is NULL");
         if (overlap) {
             // boundary planes first, then the halo travels on the comm stream while the interior runs
-            if (launch_planes(ctx, a, L, 0, 1, cs)) return 1;
-            if (launch_planes(ctx, a, L, ctx->g.nz - 1, ctx->g.nz, cs)) return 1;
+            if (L.tma) {      // the TMA-staged kernel addresses tile rows, not list copies: one launch per boundary plane
+                if (launch_planes(ctx, a, L, 0, 1, cs)) return 1;
+                if (launch_planes(ctx, a, L, ctx->g.nz - 1, ctx->g.nz, cs)) return 1;
+            } else if (launch_planes(ctx, a, L, -1, -1, cs)) return 1;
             CUDA_OK(ctx, cudaEventRecord(ctx->ev_boundary, cs));
             CUDA_OK(ctx, cudaStreamWaitEvent(ms, ctx->ev_boundary, 0));
             if (launch_planes(ctx, a, L, 1, ctx->g.nz - 1, cs)) return 1;
@@ -632,6 +644,7 @@ int lbm_step(lbm_ctx *ctx, lbm_fields *f, int nsteps, int write_macro_every, voi
 
 int lbm_macroscopic(lbm_ctx *ctx, const lbm_fields *f, void *stream) {
     if (!ctx || !f) return fail(ctx, "null argument");
+    cudaSetDevice(ctx->device);      // launches follow the context's device, whatever the caller's current device is
     lbm_params p = ctx->p;
     p.features &= ~LBM_FEAT_LES;
     if (p.compat == LBM_COMPAT_REFERENCE) p.features &= ~LBM_FEAT_POROUS;
@@ -660,6 +673,7 @@ int lbm_macroscopic(lbm_ctx *ctx, const lbm_fields *f, void *stream) {
 
 int lbm_face_bc(lbm_ctx *ctx, const lbm_fields *f, void *stream) {
     if (!ctx || !f || !f->rho) return fail(ctx, "null argument");
+    cudaSetDevice(ctx->device);      // launches follow the context's device, whatever the caller's current device is
     int n = 0;
     CUDA_OK(ctx, launch_face_bc(ctx->g, f->rho, f->flags, (cudaStream_t)stream, &n));
     ctx->launches += n;
@@ -668,6 +682,7 @@ int lbm_face_bc(lbm_ctx *ctx, const lbm_fields *f, void *stream) {
 
 int lbm_export_f(lbm_ctx *ctx, const float *g, const uint8_t *flags, float *f_out, void *stream) {
     if (!ctx || !g || !f_out || g == f_out) return fail(ctx, "bad argument");
+    cudaSetDevice(ctx->device);      // launches follow the context's device, whatever the caller's current device is
     CUDA_OK(ctx, launch_convert_f(ctx->g, true, g, flags, f_out, (cudaStream_t)stream));
     ctx->launches++;
     return 0;
@@ -675,6 +690,7 @@ int lbm_export_f(lbm_ctx *ctx, const float *g, const uint8_t *flags, float *f_ou
 
 int lbm_import_f(lbm_ctx *ctx, const float *f_in, const uint8_t *flags, float *g, void *stream) {
     if (!ctx || !g || !f_in || g == f_in) return fail(ctx, "bad argument");
+    cudaSetDevice(ctx->device);      // launches follow the context's device, whatever the caller's current device is
     CUDA_OK(ctx, launch_convert_f(ctx->g, false, f_in, flags, g, (cudaStream_t)stream));
     ctx->launches++;
     ctx->slots_valid = nullptr;
@@ -683,6 +699,7 @@ int lbm_import_f(lbm_ctx *ctx, const float *f_in, const uint8_t *flags, float *g
 
 int lbm_pressure_gradient_force(lbm_ctx *ctx, const float *rho, const uint8_t *flags, float *body_force, float max_force, float scale, void *stream) {
     if (!ctx || !rho || !body_force) return fail(ctx, "null argument");
+    cudaSetDevice(ctx->device);      // launches follow the context's device, whatever the caller's current device is
     const bool chord = chord_lists(ctx, ctx->list_vec);
     const bool listed = flags && ctx->list_flags == flags && ctx->list_ty == 1 && (chord ? ctx->d_ctiles != nullptr : ctx->d_tiles != nullptr) &&
                         (int)ctx->tile_off.size() == ctx->g.nz + 1;
@@ -695,6 +712,7 @@ int lbm_pressure_gradient_force(lbm_ctx *ctx, const float *rho, const uint8_t *f
 
 int lbm_pressure_gradient_force_set(lbm_ctx *ctx, const float *rho, const uint8_t *flags, float *body_force, float max_force, float scale, void *stream) {
     if (!ctx || !rho || !body_force) return fail(ctx, "null argument");
+    cudaSetDevice(ctx->device);      // launches follow the context's device, whatever the caller's current device is
     const bool chord = chord_lists(ctx, ctx->list_vec);
     const bool listed = flags && ctx->list_flags == flags && ctx->list_ty == 1 && (chord ? ctx->d_ctiles != nullptr : ctx->d_tiles != nullptr) &&
                         (int)ctx->tile_off.size() == ctx->g.nz + 1;
@@ -707,6 +725,7 @@ int lbm_pressure_gradient_force_set(lbm_ctx *ctx, const float *rho, const uint8_
 
 int lbm_field_statistics(lbm_ctx *ctx, const float *rho, const float *u, const uint8_t *flags, double *out8, void *stream) {
     if (!ctx || !rho || !u || !out8) return fail(ctx, "null argument");
+    cudaSetDevice(ctx->device);      // launches follow the context's device, whatever the caller's current device is
     const int blocks = ctx->sm_count * 8;
     if (!ctx->d_stat_scratch) CUDA_OK(ctx, cudaMalloc(&ctx->d_stat_scratch, (size_t)blocks * 8 * sizeof(double)));
     CUDA_OK(ctx, launch_field_statistics(ctx->g, rho, u, flags, ctx->d_stat_scratch, blocks, out8, (cudaStream_t)stream));
@@ -716,6 +735,7 @@ int lbm_field_statistics(lbm_ctx *ctx, const float *rho, const float *u, const u
 
 int lbm_forchheimer_force(lbm_ctx *ctx, const float *u, const uint8_t *flags, float *body_force, float fmax, void *stream) {
     if (!ctx || !u || !flags || !body_force) return fail(ctx, "null argument");
+    cudaSetDevice(ctx->device);      // launches follow the context's device, whatever the caller's current device is
     const lbm_params &p = ctx->p;
     CUDA_OK(ctx, launch_forchheimer_force(ctx->g, u, flags, body_force, p.K_lu, p.beta_lu, p.c_darcy, p.c_forch, fmax, (cudaStream_t)stream));
     ctx->launches++;
@@ -724,6 +744,7 @@ int lbm_forchheimer_force(lbm_ctx *ctx, const float *u, const uint8_t *flags, fl
 
 int lbm_add_reaction_force(lbm_ctx *ctx, const float *reaction, const uint8_t *flags, float *body_force, void *stream) {
     if (!ctx || !reaction || !body_force) return fail(ctx, "null argument");
+    cudaSetDevice(ctx->device);      // launches follow the context's device, whatever the caller's current device is
     CUDA_OK(ctx, launch_add_reaction(ctx->g, reaction, flags, body_force, (cudaStream_t)stream));
     ctx->launches++;
     return 0;
@@ -738,6 +759,7 @@ static int single_slab_only(lbm_ctx *ctx, const char *what) {
 int lbm_surface_tension(lbm_ctx *ctx, const float *phi, const float *mu, const float *rho, const uint8_t *flags, float *grad_phi, float *grad_mu,
                         float *normal, float *curvature, float *surface_force, float *body_force, float sigma, void *stream) {
     if (!ctx || !phi || !grad_phi || !normal || !curvature || !surface_force) return fail(ctx, "null argument");
+    cudaSetDevice(ctx->device);      // launches follow the context's device, whatever the caller's current device is
     if (body_force && (!rho || !flags)) return fail(ctx, "lbm_surface_tension: body_force needs rho and flags");
     if (single_slab_only(ctx, "lbm_surface_tension (use the _gradients / _curvature_force pair with a ghost-plane refresh of `normal` between them)")) return 1;
     CUDA_OK(ctx, launch_surface_tension(ctx->g, 3, phi, mu, rho, flags, grad_phi, grad_mu, normal, curvature, surface_force, body_force, sigma,
@@ -748,6 +770,7 @@ int lbm_surface_tension(lbm_ctx *ctx, const float *phi, const float *mu, const f
 
 int lbm_surface_tension_gradients(lbm_ctx *ctx, const float *phi, const float *mu, float *grad_phi, float *grad_mu, float *normal, void *stream) {
     if (!ctx || !phi || !grad_phi || !normal) return fail(ctx, "null argument");
+    cudaSetDevice(ctx->device);      // launches follow the context's device, whatever the caller's current device is
     CUDA_OK(ctx, launch_surface_tension(ctx->g, 1, phi, mu, nullptr, nullptr, grad_phi, grad_mu, normal, nullptr, nullptr, nullptr, 0.0f,
                                         (cudaStream_t)stream));
     ctx->launches++;
@@ -757,6 +780,7 @@ int lbm_surface_tension_gradients(lbm_ctx *ctx, const float *phi, const float *m
 int lbm_surface_tension_curvature_force(lbm_ctx *ctx, const float *phi, const float *rho, const uint8_t *flags, const float *grad_phi,
                                         const float *normal, float *curvature, float *surface_force, float *body_force, float sigma, void *stream) {
     if (!ctx || !phi || !grad_phi || !normal || !curvature || !surface_force) return fail(ctx, "null argument");
+    cudaSetDevice(ctx->device);      // launches follow the context's device, whatever the caller's current device is
     if (body_force && (!rho || !flags)) return fail(ctx, "lbm_surface_tension_curvature_force: body_force needs rho and flags");
     CUDA_OK(ctx, launch_surface_tension(ctx->g, 2, phi, nullptr, rho, flags, const_cast<float *>(grad_phi), nullptr, const_cast<float *>(normal),
                                         curvature, surface_force, body_force, sigma, (cudaStream_t)stream));
@@ -767,6 +791,7 @@ int lbm_surface_tension_curvature_force(lbm_ctx *ctx, const float *phi, const fl
 int lbm_surface_tension_body_force(lbm_ctx *ctx, const float *phi, const float *rho, const uint8_t *flags, const float *normal_outer,
                                    const float *surface_force_outer, float *body_force, float sigma, void *stream) {
     if (!ctx || !phi || !rho || !flags || !body_force) return fail(ctx, "null argument");
+    cudaSetDevice(ctx->device);      // launches follow the context's device, whatever the caller's current device is
     if (single_slab_only(ctx, "lbm_surface_tension_body_force")) return 1;
     CUDA_OK(ctx, launch_surface_tension_lean(ctx->g, phi, rho, flags, normal_outer, surface_force_outer, body_force, sigma, (cudaStream_t)stream));
     ctx->launches++;
@@ -775,6 +800,7 @@ int lbm_surface_tension_body_force(lbm_ctx *ctx, const float *phi, const float *
 
 int lbm_chemical_potential(lbm_ctx *ctx, const float *phi, float *laplacian_phi, float *mu, float kappa, void *stream) {
     if (!ctx || !phi || !mu) return fail(ctx, "null argument");
+    cudaSetDevice(ctx->device);      // launches follow the context's device, whatever the caller's current device is
     CUDA_OK(ctx, launch_chemical_potential(ctx->g, phi, laplacian_phi, mu, kappa, (cudaStream_t)stream));
     ctx->launches++;
     return 0;
@@ -782,6 +808,7 @@ int lbm_chemical_potential(lbm_ctx *ctx, const float *phi, float *laplacian_phi,
 
 int lbm_apply_surface_tension(lbm_ctx *ctx, const float *surface_force, const float *rho, const uint8_t *flags, float *body_force, void *stream) {
     if (!ctx || !surface_force || !rho || !flags || !body_force) return fail(ctx, "null argument");
+    cudaSetDevice(ctx->device);      // launches follow the context's device, whatever the caller's current device is
     CUDA_OK(ctx, launch_apply_surface_tension(ctx->g, surface_force, rho, flags, body_force, (cudaStream_t)stream));
     ctx->launches++;
     return 0;
@@ -790,6 +817,7 @@ int lbm_apply_surface_tension(lbm_ctx *ctx, const float *surface_force, const fl
 int lbm_phase_field_step(lbm_ctx *ctx, float *phi, float *phi_new, const float *mu, const float *u, float *rho, float *phase, float mobility,
                          float dt, double rho_water, double rho_air, void *stream) {
     if (!ctx || !phi || !phi_new || !u || !rho || !phase) return fail(ctx, "null argument");
+    cudaSetDevice(ctx->device);      // launches follow the context's device, whatever the caller's current device is
     if (phi == phi_new) return fail(ctx, "lbm_phase_field_step: phi and phi_new must be distinct buffers");
     CUDA_OK(ctx, launch_phase_field_step(ctx->g, phi, phi_new, mu, u, rho, phase, mobility, dt, (float)rho_air, (float)(rho_water - rho_air),
                                          (cudaStream_t)stream));
@@ -799,6 +827,7 @@ int lbm_phase_field_step(lbm_ctx *ctx, float *phi, float *phi_new, const float *
 
 int lbm_density_from_phase(lbm_ctx *ctx, const float *phi, float *rho, float *phase, double rho_water, double rho_air, void *stream) {
     if (!ctx || !phi || !rho || !phase) return fail(ctx, "null argument");
+    cudaSetDevice(ctx->device);      // launches follow the context's device, whatever the caller's current device is
     CUDA_OK(ctx, launch_density_from_phase(ctx->g, phi, rho, phase, (float)rho_air, (float)(rho_water - rho_air), (cudaStream_t)stream));
     ctx->launches++;
     return 0;
@@ -807,6 +836,7 @@ int lbm_density_from_phase(lbm_ctx *ctx, const float *phi, float *rho, float *ph
 int lbm_particles_fluid_forces(lbm_ctx *ctx, const float *u, lbm_particles *ps, float *force, double water_density, double water_viscosity,
                                double gravity, int32_t *counters, void *stream) {
     if (!ctx || !u || !ps || !force) return fail(ctx, "null argument");
+    cudaSetDevice(ctx->device);      // launches follow the context's device, whatever the caller's current device is
     const Grid &g = ctx->g;
     const float max_coord = (float)std::max(g.nx, std::max(g.ny, g.nz_global));
     const float mu_safe = (float)std::max(1e-8, water_viscosity);             // ti.max(1e-8, self.water_viscosity): folded in f64
@@ -819,6 +849,7 @@ int lbm_particles_fluid_forces(lbm_ctx *ctx, const float *u, lbm_particles *ps, 
 
 int lbm_filter_dynamic_resistance(lbm_ctx *ctx, const uint8_t *flags, float *blockage, float *accumulated, void *stream) {
     if (!ctx || !flags || !blockage || !accumulated) return fail(ctx, "null argument");
+    cudaSetDevice(ctx->device);      // launches follow the context's device, whatever the caller's current device is
     CUDA_OK(ctx, launch_dynamic_resistance(ctx->g, flags, blockage, accumulated, (cudaStream_t)stream));
     ctx->launches++;
     return 0;
@@ -827,6 +858,7 @@ int lbm_filter_dynamic_resistance(lbm_ctx *ctx, const uint8_t *flags, float *blo
 int lbm_particles_block_at_filter(lbm_ctx *ctx, lbm_particles *ps, const uint8_t *flags, float *accumulated, float scale_length, float noise,
                                   unsigned seed, void *stream) {
     if (!ctx || !ps || !flags || !accumulated) return fail(ctx, "null argument");
+    cudaSetDevice(ctx->device);      // launches follow the context's device, whatever the caller's current device is
     if (!(scale_length > 0.0f)) return fail(ctx, "lbm_particles_block_at_filter: scale_length must be positive");
     CUDA_OK(ctx, launch_particles_block_at_filter(ctx->g, *ps, flags, accumulated, scale_length, noise, seed, (cudaStream_t)stream));
     ctx->launches += ps->n > 0 ? 1 : 0;
@@ -835,6 +867,7 @@ int lbm_particles_block_at_filter(lbm_ctx *ctx, lbm_particles *ps, const uint8_t
 
 static int pour_common(lbm_ctx *ctx, const lbm_pour *pour, int mode, const uint8_t *flags, float *field, void *stream) {
     if (!ctx || !pour || !flags || !field) return fail(ctx, "null argument");
+    cudaSetDevice(ctx->device);
     if (!(pour->radius > 0.0f)) return fail(ctx, "lbm_pour: radius must be positive");
     float decay[5];
     for (int d = 0; d < 5; ++d) decay[d] = (float)exp(-(double)d / 2.0);     // the reference folds this constant expression in f64
@@ -853,6 +886,7 @@ int lbm_pouring_phase_change(lbm_ctx *ctx, const lbm_pour *pour, const uint8_t *
 int lbm_particles_couple(lbm_ctx *ctx, const float *u, float *reaction, lbm_particles *ps, float water_density,
                          float water_viscosity, float relax, void *stream) {
     if (!ctx || !u || !reaction || !ps) return fail(ctx, "null argument");
+    cudaSetDevice(ctx->device);      // launches follow the context's device, whatever the caller's current device is
     CUDA_OK(ctx, cudaMemsetAsync(reaction, 0, (size_t)ctx->g.vol * 3 * sizeof(float), (cudaStream_t)stream));
     CUDA_OK(ctx, launch_particles_couple(ctx->g, u, reaction, *ps, water_density, water_viscosity, relax, (cudaStream_t)stream));
     ctx->launches += 1;
@@ -861,6 +895,7 @@ int lbm_particles_couple(lbm_ctx *ctx, const float *u, float *reaction, lbm_part
 
 int lbm_particles_advance(lbm_ctx *ctx, lbm_particles *ps, float *force, const lbm_particle_bounds *bounds, float dt, int32_t *counters, void *stream) {
     if (!ctx || !ps || !bounds || !counters) return fail(ctx, "null argument");
+    cudaSetDevice(ctx->device);      // launches follow the context's device, whatever the caller's current device is
     if (!ps->pos || !ps->vel || !ps->mass || !ps->active) return fail(ctx, "particle arrays pos/vel/mass/active are required");
     CUDA_OK(ctx, launch_particles_advance(*ps, force, *bounds, dt, counters, (cudaStream_t)stream));
     ctx->launches++;
@@ -869,6 +904,7 @@ int lbm_particles_advance(lbm_ctx *ctx, lbm_particles *ps, float *force, const l
 
 int lbm_particles_under_relax(lbm_ctx *ctx, lbm_particles *ps, float relax, void *stream) {
     if (!ctx || !ps) return fail(ctx, "null argument");
+    cudaSetDevice(ctx->device);      // launches follow the context's device, whatever the caller's current device is
     CUDA_OK(ctx, launch_particles_under_relax(*ps, relax, (cudaStream_t)stream));
     ctx->launches += 1;
     return 0;
@@ -898,8 +934,15 @@ int lbm_attach_nccl(lbm_ctx *ctx, const void *unique_id128, int rank, int nranks
 
 int lbm_halo_exchange(lbm_ctx *ctx, float *g, float *vec3_or_null, void *stream) {
     if (!ctx || !g) return fail(ctx, "null argument");
+    cudaSetDevice(ctx->device);      // launches follow the context's device, whatever the caller's current device is
     ctx->slots_valid = nullptr;      // the incoming ghost planes overwrite the bounce-back slots that live in them
     return exchange(ctx, g, vec3_or_null, nullptr, (cudaStream_t)stream);
+}
+
+int lbm_halo_exchange_field(lbm_ctx *ctx, float *scalar_or_null, float *vec3_or_null, void *stream) {
+    if (!ctx || (!scalar_or_null && !vec3_or_null)) return fail(ctx, "null argument");
+    cudaSetDevice(ctx->device);      // launches follow the context's device, whatever the caller's current device is
+    return exchange(ctx, nullptr, vec3_or_null, scalar_or_null, (cudaStream_t)stream);
 }
 
 }  // extern "C"

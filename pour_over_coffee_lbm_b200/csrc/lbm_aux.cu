@@ -385,8 +385,10 @@ cudaError_t build_work_lists(const Grid &G, const uint8_t *flags, int vec, int t
     if (*d_tiles) { cudaFree(*d_tiles); *d_tiles = nullptr; }
     if (*d_tile_mask) { cudaFree(*d_tile_mask); *d_tile_mask = nullptr; }
     const int n_t = tile_off[G.nz];
-    if ((e = cudaMalloc(d_tiles, sizeof(unsigned) * (size_t)(n_t > 0 ? n_t : 1))) != cudaSuccess) return e;
-    if ((e = cudaMalloc(d_tile_mask, sizeof(unsigned) * (size_t)(n_t > 0 ? n_t : 1))) != cudaSuccess) return e;
+    // slabs: room for a copy of the first and the last owned plane's entries behind the list (one launch for both, lbm_api.cu)
+    const int n_b = (G.zg && G.nz >= 2) ? (tile_off[1] - tile_off[0]) + (tile_off[G.nz] - tile_off[G.nz - 1]) : 0;
+    if ((e = cudaMalloc(d_tiles, sizeof(unsigned) * (size_t)(n_t + n_b > 0 ? n_t + n_b : 1))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(d_tile_mask, sizeof(unsigned) * (size_t)(n_t + n_b > 0 ? n_t + n_b : 1))) != cudaSuccess) return e;
     if ((e = cudaMalloc(&d_ids, sizeof(int) * (size_t)(n_t > 0 ? n_t : 1))) != cudaSuccess) return e;
     thrust::counting_iterator<int> idx(0);
     cub::DeviceSelect::Flagged(nullptr, tmp_bytes, idx, tile_flag, d_ids, d_num, (int)ntiles, s);
@@ -395,6 +397,13 @@ cudaError_t build_work_lists(const Grid &G, const uint8_t *flags, int vec, int t
         cub::DeviceSelect::Flagged(tmp, tmp_bytes, idx, tile_flag, d_ids, d_num, (int)ntiles, s);
         expand_tiles_kernel<<<(n_t + 255) / 256, 256, 0, s>>>(d_ids, n_t, rows, ty, segs, *d_tiles);
         if (ty == 1) tile_lane_mask_kernel<<<(n_t + 127) / 128, 128, 0, s>>>(G, flags, vec, *d_tiles, n_t, *d_tile_mask);
+        if (n_b > 0) {
+            const int n0 = tile_off[1] - tile_off[0], n1 = tile_off[G.nz] - tile_off[G.nz - 1];
+            cudaMemcpyAsync(*d_tiles + n_t, *d_tiles + tile_off[0], sizeof(unsigned) * (size_t)n0, cudaMemcpyDeviceToDevice, s);
+            cudaMemcpyAsync(*d_tiles + n_t + n0, *d_tiles + tile_off[G.nz - 1], sizeof(unsigned) * (size_t)n1, cudaMemcpyDeviceToDevice, s);
+            cudaMemcpyAsync(*d_tile_mask + n_t, *d_tile_mask + tile_off[0], sizeof(unsigned) * (size_t)n0, cudaMemcpyDeviceToDevice, s);
+            cudaMemcpyAsync(*d_tile_mask + n_t + n0, *d_tile_mask + tile_off[G.nz - 1], sizeof(unsigned) * (size_t)n1, cudaMemcpyDeviceToDevice, s);
+        }
     }
     e = cudaStreamSynchronize(s);
     cudaFree(tmp); cudaFree(tile_flag); cudaFree(d_count); cudaFree(d_num); cudaFree(d_ids);
@@ -509,7 +518,8 @@ cudaError_t build_chord_lists(const Grid &G, const uint8_t *flags, uint4 **d_cti
     const int n_t = tile_off[G.nz];
     if (*d_ctiles) { cudaFree(*d_ctiles); *d_ctiles = nullptr; }
     if (*d_links) { cudaFree(*d_links); *d_links = nullptr; }
-    if ((e = cudaMalloc(d_ctiles, sizeof(uint4) * (size_t)(n_t > 0 ? n_t : 1))) != cudaSuccess) return e;
+    const int n_b = (G.zg && G.nz >= 2) ? (tile_off[1] - tile_off[0]) + (tile_off[G.nz] - tile_off[G.nz - 1]) : 0;      // see build_work_lists
+    if ((e = cudaMalloc(d_ctiles, sizeof(uint4) * (size_t)(n_t + n_b > 0 ? n_t + n_b : 1))) != cudaSuccess) return e;
     if ((e = cudaMalloc(&tile_links, sizeof(int) * (size_t)(n_t + 1))) != cudaSuccess) return e;
     if ((e = cudaMalloc(&link_off, sizeof(int) * (size_t)(n_t + 1))) != cudaSuccess) return e;
     cudaMemsetAsync(tile_links + n_t, 0, sizeof(int), s);
@@ -524,6 +534,11 @@ cudaError_t build_chord_lists(const Grid &G, const uint8_t *flags, uint4 **d_cti
     }
     if ((e = cudaMalloc(d_links, sizeof(unsigned) * (size_t)(n_l > 0 ? n_l : 1))) != cudaSuccess) return e;
     if (n_t > 0) chord_links_kernel<<<(n_t + 127) / 128, 128, 0, s>>>(G, flags, *d_nbr, *d_ctiles, link_off, n_t, *d_links);
+    if (n_b > 0) {      // the finished entries (link counts and offsets included) of the two boundary planes, once more, contiguous
+        const int n0 = tile_off[1] - tile_off[0], n1 = tile_off[G.nz] - tile_off[G.nz - 1];
+        cudaMemcpyAsync(*d_ctiles + n_t, *d_ctiles + tile_off[0], sizeof(uint4) * (size_t)n0, cudaMemcpyDeviceToDevice, s);
+        cudaMemcpyAsync(*d_ctiles + n_t + n0, *d_ctiles + tile_off[G.nz - 1], sizeof(uint4) * (size_t)n1, cudaMemcpyDeviceToDevice, s);
+    }
     e = cudaStreamSynchronize(s);
     if (n_links_out) *n_links_out = n_l;
     cudaFree(tmp); cudaFree(row_cnt); cudaFree(row_off); cudaFree(tile_links); cudaFree(link_off);

@@ -37,7 +37,8 @@ struct StepArgs {
     float *rho; const float *u_src; float *u_dst;
     const float *force; const float *phase; const float *blockage;
     const uint8_t *flags;
-    int z_begin, z_end;    // owned planes processed by this launch (dense mode)
+    int z_begin, z_end;    // owned planes processed by this launch (dense mode): z = z_begin + blockIdx.y * z_stride
+    int z_stride;          // 1, or nz - 1 for the launch that takes the two boundary planes of a slab together
     const unsigned *items; // bulk mode: active warp-tiles (32*VEC x-consecutive cells): x_segment | y << 8 | z << 20
     int item_begin, n_items;
     const unsigned *item_mask;   // VEC = 4 walls kernel: per list entry, the lanes that must load (lbm_phys.cuh)

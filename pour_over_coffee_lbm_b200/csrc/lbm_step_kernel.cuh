@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) step_kernel(const __grid_constant
         const int nxv = G.nx / VEC;
         const int per_plane = nxv * G.ny;
         int t = blockIdx.x * BLOCK + threadIdx.x;
-        const int z = P.z_begin + blockIdx.y;
+        const int z = P.z_begin + (int)blockIdx.y * P.z_stride;
         const bool active = t < per_plane;
         if (!active) t = per_plane - 1;
         const int y = t / nxv;

@@ -103,6 +103,7 @@ class D3Q19Engine:
         self.comm_stream = None
         self.rank, self.nranks = 0, 1
         self.steps_done = 0
+        self.populations_generation = 0       # bumped by everything that rewrites g (fields.PopulationField keys its cache on it)
         if walls:
             self.pack_flags()          # all-fluid box: NEAR on open faces, work lists for the step kernels
         self.init_equilibrium(1.0, (0.0, 0.0, 0.0))
@@ -144,6 +145,7 @@ class D3Q19Engine:
     def populations_changed(self):
         """Call after writing `populations` / `g[...]` directly (torch ops): compat = physical behind walls keeps
         bounce-back copies in the solid cells' slots and must rebuild them (include/lbm_b200.h)."""
+        self.populations_generation += 1
         self._check(self.lib.lbm_populations_changed(self._ctx), "lbm_populations_changed")
 
     def selftest_math(self):
@@ -164,6 +166,7 @@ class D3Q19Engine:
                          u: Optional[torch.Tensor] = None):
         """g <- f_eq(rho, u); both ping-pong buffers (LBMSolver.init_fields sets f and f_new)."""
         arr = (C.c_float * 3)(*[float(x) for x in u0])
+        self.populations_generation += 1
         for buf in self.g:
             self._check(self.lib.lbm_init_equilibrium(self._ctx, _ptr(buf), _ptr(rho), _ptr(u), float(rho0), arr, self.stream),
                         "lbm_init_equilibrium")
@@ -188,6 +191,7 @@ class D3Q19Engine:
         self.pack_flags()
 
     def pack_flags(self):
+        self.populations_generation += 1      # the exported f depends on the mask (bounce-back, inflow)
         self._check(self.lib.lbm_pack_flags(self._ctx, _ptr(self.flags), _ptr(self.solid), _ptr(self.filter_zone),
                                             _ptr(self.les_mask), self.stream), "lbm_pack_flags")
         if len(self.u_buf) == 2:      # keep the u ping-pong pair identical on cells the kernel never writes
@@ -204,6 +208,9 @@ class D3Q19Engine:
         self.pack_flags()
         self._check(self.lib.lbm_import_f(self._ctx, _ptr(f), _ptr(self.flags), _ptr(self.g[self.cur]), self.stream), "lbm_import_f")
         self.g[1 - self.cur].copy_(self.g[self.cur])
+        self.populations_generation += 1
+        if self.zghost:
+            self.halo_exchange()              # the ghost planes' populations were converted with the old mask
 
     # ---- the hot path --------------------------------------------------------------------------
     def _fields(self) -> L.LbmFields:
@@ -233,6 +240,7 @@ class D3Q19Engine:
         if len(self.rho_buf) == 2 and nsteps % 2 == 1:
             self.rho_cur = 1 - self.rho_cur
         self.steps_done += nsteps
+        self.populations_generation += 1
 
     def macroscopic(self):
         f = self._fields()
@@ -263,13 +271,17 @@ class D3Q19Engine:
         torch.save(blob, path)
 
     def load_checkpoint(self, path: str) -> None:
-        blob = torch.load(path, map_location="cpu", weights_only=False)
+        blob = torch.load(path, map_location="cpu", weights_only=True)      # tensors, ints, lists and tuples only
         if tuple(blob["shape"]) != (self.nx, self.ny, self.nz, self.zghost, self.z0, self.nz_global) or blob["compat"] != self.compat \
                 or blob["features"] != self.features:
             raise ValueError("checkpoint was written for a different slab geometry, compat mode or feature set")
         for name in self._CKPT_FIELDS:
             t = getattr(self, name, None)
-            if blob[name] is not None and t is not None:
+            if blob[name] is not None and t is None:
+                if name != "blockage":
+                    raise ValueError(f"checkpoint holds a '{name}' field this engine was built without")
+                self.blockage = t = torch.zeros_like(self.rho)        # FilterPaperSystem's blockage, not allocated yet
+            if blob[name] is not None:
                 t.copy_(blob[name])
         if self.flags is not None:
             self.pack_flags()                      # flags, work lists, neighbour masks from solid / filter_zone / les_mask
@@ -279,6 +291,8 @@ class D3Q19Engine:
         self.u_cur = blob["u_cur"] if len(self.u_buf) == 2 else 0
         self.steps_done = int(blob["steps_done"])
         self.populations_changed()
+        if self.zghost:
+            self.halo_exchange()
 
     # ---- reference `f` view ------------------------------------------------------------------
     def export_f(self) -> torch.Tensor:
@@ -289,6 +303,7 @@ class D3Q19Engine:
 
     def import_f(self, f: torch.Tensor):
         f = f.to(self.device, torch.float32).contiguous()
+        self.populations_generation += 1
         self._check(self.lib.lbm_import_f(self._ctx, _ptr(f), _ptr(self.flags), _ptr(self.g[self.cur]), self.stream), "lbm_import_f")
         self.g[1 - self.cur].copy_(self.g[self.cur])
         if self.zghost:
@@ -299,6 +314,7 @@ class D3Q19Engine:
         self.body_force.zero_()
 
     def add_pressure_gradient_force(self, max_force: float = 0.12, scale: float = 1.0):
+        self.exchange_field(scalar=self.rho)      # the gradient reads rho[k -+ 1] across a slab interface
         self._check(self.lib.lbm_pressure_gradient_force(self._ctx, _ptr(self.rho), _ptr(self.flags), _ptr(self.body_force),
                                                          float(max_force), float(scale), self.stream), "lbm_pressure_gradient_force")
 
@@ -314,6 +330,7 @@ class D3Q19Engine:
     def set_pressure_gradient_force(self, max_force: float = 0.12, scale: float = 1.0):
         """clear_body_force() + add_pressure_gradient_force() on the fluid cells in one pass (solid cells keep their
         old body_force, which no kernel reads)."""
+        self.exchange_field(scalar=self.rho)
         self._check(self.lib.lbm_pressure_gradient_force_set(self._ctx, _ptr(self.rho), _ptr(self.flags), _ptr(self.body_force),
                                                              float(max_force), float(scale), self.stream), "lbm_pressure_gradient_force_set")
 
@@ -396,6 +413,14 @@ class D3Q19Engine:
     def halo_exchange(self, with_u: bool = False):
         v = _ptr(self.u) if (with_u and self.u_buf) else None
         self._check(self.lib.lbm_halo_exchange(self._ctx, _ptr(self.g[self.cur]), v, self.stream), "lbm_halo_exchange")
+        if self.drive:          # the fused drive reads the previous step's rho across the interface
+            for rb in self.rho_buf:
+                self.exchange_field(scalar=rb)
+
+    def exchange_field(self, scalar: Optional[torch.Tensor] = None, vec3: Optional[torch.Tensor] = None):
+        """Refresh the ghost planes of a scalar and / or 3-vector field from the z neighbours (NCCL inside the library)."""
+        if self.zghost:
+            self._check(self.lib.lbm_halo_exchange_field(self._ctx, _ptr(scalar), _ptr(vec3), self.stream), "lbm_halo_exchange_field")
 
     # ---- sizes ---------------------------------------------------------------------------------
     def cells(self) -> int:

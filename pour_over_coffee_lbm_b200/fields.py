@@ -128,19 +128,24 @@ class PopulationField(_FieldBase):
 
     The device stores post-collision populations (pull scheme); this field materialises the
     reference view on demand with lbm_export_f and writes through lbm_import_f -- both are exact
-    data movement.  Reads are cached until the next step.
+    data movement.  Reads are cached until the populations change: the engine bumps `populations_generation` in every call
+    that rewrites g (step, init_equilibrium, import_f, load_checkpoint, a geometry change, pack_flags, populations_changed), so a
+    reset or a restart can never hand back -- or write through -- the populations of before.
     """
 
     def __init__(self, engine, on_write=None):
         super().__init__(on_write)
         self._eng = engine
         self._cache = None
-        self._cache_step = -1
+        self._cache_gen = -1
+
+    def invalidate(self) -> None:
+        self._cache, self._cache_gen = None, -1
 
     def _materialise(self) -> torch.Tensor:
-        if self._cache is None or self._cache_step != self._eng.steps_done:
+        if self._cache is None or self._cache_gen != self._eng.populations_generation:
             self._cache = self._eng.export_f()
-            self._cache_step = self._eng.steps_done
+            self._cache_gen = self._eng.populations_generation
         return self._cache
 
     def view(self):
@@ -152,7 +157,7 @@ class PopulationField(_FieldBase):
 
     def _flush(self):
         self._eng.import_f(self._cache)
-        self._cache_step = self._eng.steps_done
+        self._cache_gen = self._eng.populations_generation        # the cache IS what was just imported
 
     def from_numpy(self, arr) -> None:
         super().from_numpy(arr); self._flush()

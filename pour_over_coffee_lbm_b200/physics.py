@@ -244,6 +244,7 @@ class PressureGradientDrive:
             self._pressure_force = torch.zeros_like(e.u)
             self.pressure_force = VectorField(lambda: self._pressure_force, e.zghost)
         self._pressure_force.zero_()
+        e.exchange_field(scalar=e.rho)        # z-slabs: the gradient reads rho[k -+ 1] across the interface
         e._check(e.lib.lbm_pressure_gradient_force_set(e._ctx, _ptr(e.rho), _ptr(e.flags), _ptr(self._pressure_force),
                                                        float(self.MAX_PRESSURE_FORCE), 1.0, e.stream), "lbm_pressure_gradient_force_set")
 

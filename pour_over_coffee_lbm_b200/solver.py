@@ -78,6 +78,12 @@ class LBMSolver:
             return
         self._flags_dirty = False
         e = self.engine
+        if e.zghost and e.nranks > 1:
+            # the field surface writes owned planes only: the neighbours' boundary planes of the masks belong in the ghost planes
+            # before NEAR flags, neighbour masks and wall links are derived from them
+            from . import slab
+            for t in (e.solid, e.filter_zone, e.les_mask):
+                slab.exchange_planes(t, e.rank, e.nranks, e.periodic[2])
         if e.steps_done > 0 and e.compat_name == "reference":
             e.set_geometry_preserving_f(lambda: None)
         else:

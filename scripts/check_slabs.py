@@ -60,6 +60,68 @@ def run_case(name, rank, world, local, nx, nzg, steps, make_engine, setup):
     return bool(flag.item())
 
 
+def run_particles(rank, world, local, nx, nzg, make_engine, setup, cfg, n_part=20000, steps=6):
+    """Two-way coupling on slabs (replicated particles, owner computes, engine.particles_couple_slab over NCCL) against the single-GPU
+    coupling: base-cell indices, fluid velocity at the particle and Reynolds number bit for bit; drag within 1e-6 (powf); the reaction
+    field and the flow after `steps` coupled steps within 1e-5 of the field scale (a GPU's scatter atomics are unordered)."""
+    from pour_over_coffee_lbm_b200.engine import ParticleState, particles_couple, particles_couple_slab
+
+    def particles(dev):
+        rng = np.random.default_rng(11)
+        ps = ParticleState(n_part, dev)
+        pos = np.stack([rng.uniform(0.3 * nx, 0.7 * nx, n_part), rng.uniform(0.3 * nx, 0.7 * nx, n_part), rng.uniform(4.0, nzg - 4.0, n_part)])
+        ps.pos.copy_(torch.from_numpy(pos.astype(np.float32)))
+        ps.vel.copy_(torch.from_numpy((1e-3 * rng.standard_normal((3, n_part))).astype(np.float32)))
+        rad = np.clip(rng.normal(3.25e-4, 1e-4, n_part), 1.6e-4, 4.9e-4).astype(np.float32)
+        ps.radius.copy_(torch.from_numpy(rad))
+        ps.mass.copy_(torch.from_numpy(((np.float32(4 / 3) * np.float32(3.14159)) * rad ** 3 * np.float32(1200.0)).astype(np.float32)))
+        ps.active.fill_(1); ps.active[::17] = 0
+        return ps
+
+    part = slab.partition_z(nzg, world)[rank]
+    eng = make_engine(nz=part.nz, zghost=1, z0=part.z0, nz_global=nzg, device=local)
+    eng.attach_process_group()
+    setup(eng, part.z0, part.nz, True)
+    eng.halo_exchange(with_u=True)
+    ps = particles(eng.device)
+    eng.step(3)
+    for _ in range(steps):
+        particles_couple_slab(eng, ps, eng.body_force, relax=0.8)
+        eng.step(1)
+    torch.cuda.synchronize()
+    mine = (eng.rho[1:-1].cpu(), eng.u[:, 1:-1].cpu(), eng.body_force[:, 1:-1].cpu())
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (part.z0, mine))
+    ok = True
+    if rank == 0:
+        gathered.sort(key=lambda t: t[0])
+        rho = torch.cat([m[0] for _, m in gathered], dim=0); u = torch.cat([m[1] for _, m in gathered], dim=1)
+        react = torch.cat([m[2] for _, m in gathered], dim=1)
+        ref = make_engine(nz=nzg, zghost=0, z0=0, nz_global=nzg, device=local)
+        setup(ref, 0, nzg, False)
+        pr = particles(ref.device)
+        ref.step(3)
+        for _ in range(steps):
+            particles_couple(ref, pr, ref.body_force, relax=0.8)
+            ref.step(1)
+        torch.cuda.synchronize()
+        act = (pr.active != 0).cpu()
+        e_cell = torch.equal(ps.cell.cpu()[:, act], pr.cell.cpu()[:, act])
+        fluid = (ref.solid == 0).cpu()
+        close = lambda a, b, tol: bool(((a - b).abs().max() <= tol * max(float(b.abs().max()), 1e-30)).item())
+        e_uf = close(ps.u_fluid.cpu()[:, act], pr.u_fluid.cpu()[:, act], 1e-5)
+        e_drag = close(ps.drag.cpu()[:, act], pr.drag.cpu()[:, act], 1e-5)
+        e_react = close(react[:, fluid], ref.body_force.cpu()[:, fluid], 1e-5)
+        e_rho = close(rho[fluid], ref.rho.cpu()[fluid], 1e-5)
+        e_u = close(u[:, fluid], ref.u.cpu()[:, fluid], 1e-5)
+        ok = e_cell and e_uf and e_drag and e_react and e_rho and e_u
+        print(f"[check_slabs] particles on slabs: world={world} particles={n_part} coupled steps={steps} cell indices (bit-exact)={e_cell} u_fluid={e_uf} "
+              f"drag={e_drag} reaction field={e_react} rho={e_rho} u={e_u}", flush=True)
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    return bool(flag.item())
+
+
 def main():
     rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -85,10 +147,11 @@ def main():
     cfg = LBMConfig(NX=nx, NY=nx, NZ=nzg, GRAVITY_LU=1e-5)
     bf = torch.from_numpy(H.to_dev_vec((2e-5 * np.random.default_rng(3).standard_normal((nx, nx, nzg, 3))).astype(np.float32)))
 
-    def mk2(nz, zghost, z0, nz_global, device, compat="physical"):
+    def mk2(nz, zghost, z0, nz_global, device, compat="physical", drive=False):
         kw = dict(porous_darcy=0.37, porous_forch=0.9) if compat == "physical" else {}
         return D3Q19Engine(nx, nx, nz, compat=compat, periodic=(False, False, False), walls=True, force=True, phase=True, les=True,
-                           porous=True, config=cfg, gravity_lu=1e-5, zghost=zghost, z0=z0, nz_global=nz_global, device=device, **kw)
+                           porous=True, config=cfg, gravity_lu=1e-5, zghost=zghost, z0=z0, nz_global=nz_global, device=device, drive=drive,
+                           drive_scale=0.5, **kw)
 
     def setup2(eng, z0, nz, ghost, phase_scale=1.0):
         eng.build_v60_geometry()
@@ -100,6 +163,9 @@ def main():
         eng.body_force.copy_(b.cuda())
         eng.init_equilibrium(rho=r.cuda(), u=v.cuda())
     ok &= run_case("V60 all features physical", rank, world, local, nx, nzg, 25, mk2, setup2)
+    # the pressure-gradient drive fused into the step kernel reads rho across the interface (rho planes travel with the halo)
+    ok &= run_case("V60 physical + fused pressure-gradient drive", rank, world, local, nx, nzg, 25, lambda **k: mk2(drive=True, **k), setup2)
+    ok &= run_particles(rank, world, local, nx, nzg, mk2, setup2, cfg)
 
     # ---- legacy solver (reference): FD-LES reads u across the interface ----------------------------------
     ok &= run_case("V60 compat=reference (water phase, FD-LES active)", rank, world, local, nx, nzg, 10,

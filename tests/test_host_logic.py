@@ -223,3 +223,34 @@ def test_particle_coupling_on_a_slab_masks_ownership_and_exchanges(monkeypatch):
     assert calls == [("ghosts_in", (3, 10, 4, 4)), ("kernel", [0, 1, 0, 1], 0.8), ("ghost_up", (3, 10, 4, 4)),
                      ("allreduce", 7, [0, 1, 0, 1], [1, 1, 0, 1])]
     assert ps.state.active.tolist() == [1, 1, 0, 1]
+
+
+def test_population_field_cache_follows_the_engine_generation_counter():
+    """the f view was cached on steps_done alone, so init_fields / import_f / load_checkpoint / a geometry change handed
+    back -- and wrote through -- the populations of before.  The cache is now keyed on a counter the engine bumps in every call that
+    rewrites g."""
+    import torch
+    from pour_over_coffee_lbm_b200.fields import PopulationField
+
+    class Engine:
+        zghost, steps_done, populations_generation = 0, 0, 0
+
+        def __init__(self):
+            self.state = torch.zeros(19, 2, 2, 2); self.imported = []
+
+        def export_f(self):
+            return self.state.clone()
+
+        def import_f(self, t):
+            self.populations_generation += 1
+            self.imported.append(t.clone()); self.state = t.clone()
+
+    e = Engine()
+    f = PopulationField(e)
+    assert float(f.to_numpy().sum()) == 0.0
+    e.state += 1.0; e.populations_generation += 1                        # init_equilibrium / load_checkpoint: steps_done unchanged
+    assert float(f.to_numpy()[0, 0, 0, 0]) == 1.0
+    e.state += 1.0; e.populations_generation += 1
+    f[3, 0, 0, 0] = 7.0                                                  # write-through starts from the CURRENT populations
+    assert float(e.imported[-1][0, 0, 0, 0]) == 2.0 and float(e.imported[-1][3, 0, 0, 0]) == 7.0
+    assert float(f.to_numpy()[3, 0, 0, 0]) == 7.0 and len(e.imported) == 1      # and the cache is what was imported: no re-export
