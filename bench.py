@@ -219,7 +219,8 @@ def v60_engine(n, *, nz_global=None, z0=0, nz=None, zghost=0, device=0, drive=Fa
 
 def bed_particles(eng, count, seed=42):
     """`count` particles uniform in the coffee-bed frustum (bottom 30 % of the cone, 80 % of the local
-    radius), radius N(3.25e-4, 30 %) clipped to [0.5, 1.5] x mean, at rest.  Same particles on every rank."""
+    radius), radius N(3.25e-4, 30 %) clipped to [0.5, 1.5] x mean, at rest, stored in cell order (z slowest).  Same particles on every
+    rank."""
     import torch
     from pour_over_coffee_lbm_b200.engine import ParticleState
     cfg = eng.cfg
@@ -236,6 +237,7 @@ def bed_particles(eng, count, seed=42):
     ps.radius.copy_(torch.from_numpy(rad))
     ps.mass.copy_(torch.from_numpy(((np.float32(4 / 3) * np.float32(3.14159)) * rad ** 3 * np.float32(1200.0)).astype(np.float32)))
     ps.active.fill_(1)
+    ps.sort_by_cell(eng.nx, eng.ny)     # layer by layer, as the reference creates its bed (coffee_particles.py:220-412)
     return ps
 
 
@@ -386,13 +388,13 @@ def run_single(args, local):
 
         def coupled(k):
             # LBMSolver.step_with_two_way_coupling (legacy/lbm_solver.py:1485-1509) + the drive: clear -> coupling on the current u ->
-            # under-relaxation -> reaction into body_force -> step.  The coupling kernel zeroes and scatters straight into body_force
-            # (clear + "+= reaction" in one), the drive is added inside the step kernel.
+            # under-relaxation -> reaction into body_force -> step.  The coupling scatters straight into body_force (clear + "+= reaction"
+            # in one; the clear is sparse: last step's deposits, cell by cell), the drive is added inside the step kernel.
             for _ in range(k):
-                particles_couple(eng, ps, eng.body_force, relax=0.8)
+                particles_couple(eng, ps, eng.body_force, relax=0.8, sparse_clear=True)
                 eng.step(1, write_macro_every=1)
         tm = timer.measure(coupled, args.steps, args.warmup)
-        tp = timer.measure(lambda k: [particles_couple(eng, ps, eng.body_force, relax=0.8) for _ in range(k)], args.steps, args.warmup)
+        tp = timer.measure(lambda k: [particles_couple(eng, ps, eng.body_force, relax=0.8, sparse_clear=True) for _ in range(k)], args.steps, args.warmup)
         subs.append(record(f"v60_{n}_particles_{args.particles}", cells, fluid, B_V60, tm, peak, launches_per_step=2,
                            note="configs[3]: + two-way coupled particles (trilinear gather, Schiller-Naumann drag, warp-aggregated atomic scatter, "
                                 "under-relaxation) every step",
@@ -605,7 +607,7 @@ def run_multi(args, world, rank, local):
 
     def coupled(k):
         for _ in range(k):
-            particles_couple_slab(eng, ps, eng.body_force, relax=0.8)
+            particles_couple_slab(eng, ps, eng.body_force, relax=0.8, sparse_clear=True, sync="state")
             eng.step(1, write_macro_every=1)
     l0 = eng.launch_count()
     head = timer.measure(coupled, args.steps, args.warmup)

@@ -32,6 +32,7 @@ cudaError_t launch_field_statistics(const Grid &, const float *, const float *, 
 cudaError_t launch_bounce_slots(const Grid &, float *, const uint8_t *, const unsigned long long *, int, int, cudaStream_t);
 cudaError_t launch_particles_couple(const Grid &, const float *, float *, const lbm_particles &, float, float, float, cudaStream_t);
 cudaError_t launch_particles_under_relax(const lbm_particles &, float, cudaStream_t);
+cudaError_t launch_particles_clear_deposits(const Grid &, float *, const lbm_particles &, cudaStream_t);
 cudaError_t launch_particles_advance(const lbm_particles &, float *, const lbm_particle_bounds &, float, int *, cudaStream_t);
 cudaError_t launch_surface_tension(const Grid &, int, const float *, const float *, const float *, const uint8_t *, float *, float *, float *, float *,
                                    float *, float *, float, cudaStream_t);
@@ -890,6 +891,25 @@ int lbm_particles_couple(lbm_ctx *ctx, const float *u, float *reaction, lbm_part
     CUDA_OK(ctx, cudaMemsetAsync(reaction, 0, (size_t)ctx->g.vol * 3 * sizeof(float), (cudaStream_t)stream));
     CUDA_OK(ctx, launch_particles_couple(ctx->g, u, reaction, *ps, water_density, water_viscosity, relax, (cudaStream_t)stream));
     ctx->launches += 1;
+    return 0;
+}
+
+int lbm_particles_couple_sparse(lbm_ctx *ctx, const float *u, float *reaction, lbm_particles *ps, float water_density,
+                                float water_viscosity, float relax, void *stream) {
+    if (!ctx || !u || !reaction || !ps || !ps->cell) return fail(ctx, "null argument");
+    cudaSetDevice(ctx->device);
+    const Grid &G = ctx->g;
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_OK(ctx, launch_particles_clear_deposits(G, reaction, *ps, s));
+    if (G.zg) {      // slabs: what the neighbours' particles left in the interface planes (slab.reduce_ghost_up) is not in this rank's cell list
+        for (int d = 0; d < 3; ++d) {
+            float *r = reaction + (size_t)d * G.vol;
+            CUDA_OK(ctx, cudaMemsetAsync(r, 0, (size_t)G.plane * 2 * sizeof(float), s));
+            CUDA_OK(ctx, cudaMemsetAsync(r + (size_t)(G.nz + 1) * G.plane, 0, (size_t)G.plane * sizeof(float), s));
+        }
+    }
+    CUDA_OK(ctx, launch_particles_couple(G, u, reaction, *ps, water_density, water_viscosity, relax, s));
+    ctx->launches += ps->n > 0 ? 2 : 0;
     return 0;
 }
 

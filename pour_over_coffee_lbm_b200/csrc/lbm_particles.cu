@@ -132,6 +132,29 @@ __global__ void __launch_bounds__(256) particles_couple_kernel(const ParticleArg
     }
 }
 
+// Sparse clear of the reaction field: zero the 8 corners (x 3 components) of every particle's RECORDED base cell, i.e. exactly
+// what the previous coupling call deposited (it wrote P.cell).  1 M particles: 24 M four-byte stores instead of a memset of the
+// whole field (1.6 GB at 512^3: 0.27 of the coupling's 0.37 ms; 7 GB on a 1024^2 x 600 slab).  Corners outside the slab's planes
+// (ghost planes included) are skipped.
+__global__ void __launch_bounds__(256) particles_clear_deposits_kernel(Grid G, float *reaction, const int *cell, int n) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int i = cell[p], j = cell[n + p], kl = cell[2 * n + p] - G.z0 + G.zg;
+    if (i < 0 || i > G.nx - 2 || j < 0 || j > G.ny - 2) return;
+    const int nzp = G.nz + 2 * G.zg;
+#pragma unroll
+    for (int dz = 0; dz < 2; ++dz) {
+        const int kk = kl + dz;
+        if (kk < 0 || kk >= nzp) continue;
+        const long long b = ((long long)kk * G.ny + j) * G.nx + i;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            float *r = reaction + (long long)d * G.vol + b;
+            r[0] = 0.0f; r[1] = 0.0f; r[G.nx] = 0.0f; r[G.nx + 1] = 0.0f;
+        }
+    }
+}
+
 // CoffeeParticleSystem.apply_under_relaxation as a stand-alone call (coffee_particles.py:1200-1212)
 __global__ void particles_under_relax_kernel(lbm_particles P, float relax) {
     const int n = P.n;
@@ -146,6 +169,11 @@ __global__ void particles_under_relax_kernel(lbm_particles P, float relax) {
 }
 
 #ifndef LBM_EMULATE_ON_HOST      /* tests/emu compiles the kernels with g++ and runs them thread by thread */
+cudaError_t launch_particles_clear_deposits(const Grid &G, float *reaction, const lbm_particles &ps, cudaStream_t s) {
+    const int b = 256, gr = (ps.n + b - 1) / b;
+    if (ps.n > 0) particles_clear_deposits_kernel<<<gr, b, 0, s>>>(G, reaction, ps.cell, ps.n);
+    return cudaGetLastError();
+}
 cudaError_t launch_particles_under_relax(const lbm_particles &ps, float relax, cudaStream_t s) {
     const int b = 256, gr = (ps.n + b - 1) / b;
     if (ps.n > 0) particles_under_relax_kernel<<<gr, b, 0, s>>>(ps, relax);

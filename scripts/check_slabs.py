@@ -84,9 +84,10 @@ def run_particles(rank, world, local, nx, nzg, make_engine, setup, cfg, n_part=2
     setup(eng, part.z0, part.nz, True)
     eng.halo_exchange(with_u=True)
     ps = particles(eng.device)
+    eng.body_force.zero_()          # sparse clear: the reaction target starts at zero and only the coupling writes it
     eng.step(3)
     for _ in range(steps):
-        particles_couple_slab(eng, ps, eng.body_force, relax=0.8)
+        particles_couple_slab(eng, ps, eng.body_force, relax=0.8, sparse_clear=True)
         eng.step(1)
     torch.cuda.synchronize()
     mine = (eng.rho[1:-1].cpu(), eng.u[:, 1:-1].cpu(), eng.body_force[:, 1:-1].cpu())
@@ -100,6 +101,7 @@ def run_particles(rank, world, local, nx, nzg, make_engine, setup, cfg, n_part=2
         ref = make_engine(nz=nzg, zghost=0, z0=0, nz_global=nzg, device=local)
         setup(ref, 0, nzg, False)
         pr = particles(ref.device)
+        ref.body_force.zero_()
         ref.step(3)
         for _ in range(steps):
             particles_couple(ref, pr, ref.body_force, relax=0.8)

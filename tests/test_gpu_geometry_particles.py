@@ -357,3 +357,56 @@ def test_body_force_accumulation_fluid_only():
     s.add_particle_reaction_forces(ps); s.add_particle_reaction_forces(ps)
     bf = s.body_force.to_numpy(); solid = s.solid.to_numpy()
     assert np.allclose(bf[solid == 0], 2e-3) and np.all(bf[solid != 0] == 0)
+
+
+def test_sparse_clear_of_the_reaction_field_equals_the_dense_clear():
+    """lbm_particles_couple_sparse (the previous call's deposits cleared cell by cell from ps.cell) against lbm_particles_couple
+    (memset of the whole field) over several calls with moving particles, some of them switched off in between: same reaction
+    field (the scatter atomics are unordered: 1e-6 of the field scale), identical per-particle outputs."""
+    import torch
+    from pour_over_coffee_lbm_b200.engine import ParticleState, particles_couple
+    n, P = 48, 5000
+    rng = np.random.default_rng(3)
+    eng = _engine(n, n, n, compat="physical", periodic=(False, False, False), walls=True, force=True)
+    eng.u.copy_(_torch((0.02 * rng.standard_normal((3, n, n, n))).astype(np.float32)))
+
+    def particles():
+        ps = ParticleState(P, eng.device)
+        r = np.random.default_rng(9)
+        ps.pos.copy_(_torch(r.uniform(2.0, n - 3.0, (3, P)).astype(np.float32)))
+        ps.vel.copy_(_torch((1e-3 * r.standard_normal((3, P))).astype(np.float32)))
+        ps.radius.fill_(3.25e-4); ps.mass.fill_(float(4.0 / 3.0 * 3.14159 * 3.25e-4 ** 3 * 1200.0)); ps.active.fill_(1)
+        return ps
+    a, b = particles(), particles()
+    dense = torch.zeros_like(eng.u); sparse = torch.zeros_like(eng.u)
+    for it in range(4):
+        particles_couple(eng, a, dense, relax=0.8)
+        particles_couple(eng, b, sparse, relax=0.8, sparse_clear=True)
+        scale = float(dense.abs().max())
+        assert scale > 0 and float((dense - sparse).abs().max()) <= 1e-6 * scale
+        assert int((sparse != 0).sum()) <= 24 * P                           # nothing of the earlier positions is left behind
+        for x, y in ((a.cell, b.cell), (a.drag, b.drag), (a.u_fluid, b.u_fluid)):
+            assert torch.equal(x, y)
+        step = _torch((0.9 * rng.standard_normal((3, P))).astype(np.float32))
+        for ps in (a, b):
+            ps.pos.add_(step).clamp_(1.0, n - 2.5)
+            ps.active[it::7] = 0
+
+
+def test_particle_cell_indices_bit_exact_at_one_million_particles():
+    """BASELINE: "particle cell indices must match bit-exactly" at the particle count of configs[3]: 10^6 particles in the V60 bed
+    of a 512-wide box (positions only -- no 512^3 populations needed: u is a thin synthetic slab), kernel against the oracle's
+    f32 clamp + truncation (coffee_particles.py:1054-1056), including positions outside the box and exactly on cell faces."""
+    import torch
+    from pour_over_coffee_lbm_b200.engine import ParticleState, particles_couple
+    nx, nz, P = 512, 16, 1_000_000
+    rng = np.random.default_rng(42)
+    eng = _engine(nx, nx, nz, compat="physical", periodic=(False, False, False), walls=True, force=True)
+    pos = np.stack([rng.uniform(-3.0, nx + 3.0, P), rng.uniform(-3.0, nx + 3.0, P), rng.uniform(-2.0, nz + 2.0, P)]).astype(np.float32)
+    pos[:, ::1000] = np.round(pos[:, ::1000])                                # exactly on cell faces
+    ps = ParticleState(P, eng.device)
+    ps.pos.copy_(_torch(pos)); ps.radius.fill_(3.25e-4); ps.mass.fill_(1e-7); ps.active.fill_(1)
+    particles_couple(eng, ps, torch.zeros_like(eng.u), relax=0.8)
+    cfg = R.RefConfig(NX=nx, NY=nx, NZ=nz)
+    i, j, k, _ = R.particle_cell_and_weights(cfg, pos.T.copy())
+    assert np.array_equal(ps.cell.cpu().numpy(), np.stack([i, j, k]))
