@@ -21,10 +21,12 @@ cudaError_t launch_init_equilibrium(const Grid &, int, float *, const float *, c
 cudaError_t launch_v60_geometry(const Grid &, uint8_t *, int32_t *, const float[5], cudaStream_t);
 cudaError_t launch_pack_flags(const Grid &, uint8_t *, const uint8_t *, const int32_t *, const int32_t *, cudaStream_t);
 cudaError_t build_work_lists(const Grid &, const uint8_t *, int, int, unsigned **, unsigned **, std::vector<int> &, unsigned long long **, cudaStream_t);
-cudaError_t build_chord_lists(const Grid &, const uint8_t *, uint4 **, unsigned **, std::vector<int> &, unsigned long long **, long long *, cudaStream_t);
+cudaError_t build_chord_lists(const Grid &, const uint8_t *, unsigned long long **, uint2 **, unsigned long long **, std::vector<int> &, unsigned long long **, long long *,
+                              cudaStream_t);
 cudaError_t launch_convert_f(const Grid &, bool, const float *, const uint8_t *, float *, cudaStream_t);
 cudaError_t launch_face_bc(const Grid &, float *, const uint8_t *, cudaStream_t, int *);
-cudaError_t launch_pressure_gradient(const Grid &, const float *, const uint8_t *, float *, float, float, int, const unsigned *, const uint4 *, int, int, cudaStream_t);
+cudaError_t launch_pressure_gradient(const Grid &, const float *, const uint8_t *, float *, float, float, int, const unsigned *, const unsigned long long *, int, int,
+                                     cudaStream_t);
 cudaError_t launch_forchheimer_force(const Grid &, const float *, const uint8_t *, float *, float, float, float, float, float, cudaStream_t);
 cudaError_t launch_add_reaction(const Grid &, const float *, const uint8_t *, float *, cudaStream_t);
 cudaError_t run_selftest_math(unsigned long long[7], const StepArgs &, cudaStream_t);
@@ -107,8 +109,9 @@ struct lbm_ctx {
     // work lists of the walls path (built by lbm_pack_flags for the flag field it packed)
     unsigned *d_tiles = nullptr;               // active warp-tiles, packed x_segment | y << 8 | z << 20
     unsigned *d_tile_mask = nullptr;           // per warp-tile: lanes that must load (unused by the current kernels)
-    uint4 *d_ctiles = nullptr;                 // vec = 4: chord-fitted tiles (lbm_phys_chord.cuh) ...
-    unsigned *d_links = nullptr;               // ... and their wall links
+    unsigned long long *d_ctiles = nullptr;    // vec = 4: packed quad list (lbm_phys_chord.cuh), one u64 per lane slot ...
+    uint2 *d_tile_links = nullptr;             // ... per tile: first wall link, number of links ...
+    unsigned long long *d_links = nullptr;     // ... and the wall links
     long long n_links = 0;
     cudaStream_t window_stream = nullptr; bool window_set = false;
     unsigned long long *d_nbr = nullptr;       // neighbour masks [vol]
@@ -167,7 +170,8 @@ static int pick_vec(const lbm_ctx *ctx) {
         // thread on packed f32x2 registers (lbm_phys.cuh) on 8-byte rows, else one.  The TMA-staged kernel (LBM_TMA=1, works on
         // the two-cell lists) is opt-in.
         if (vec == 0) vec = tma_eligible_params(ctx) ? 2 : 4;
-        if (vec == 4 && (ctx->g.nx % 4 != 0 || ctx->g.nx < 8 || ctx->g.nx > 2048 || ctx->g.ny > 65535 || ctx->g.nz > 65535)) vec = 2;
+        if (vec == 4 && (ctx->g.nx % 4 != 0 || ctx->g.nx < 8 || ctx->g.nx > 16384 || ctx->g.ny > 65535 || ctx->g.nz + 2 * ctx->g.zg > 65535 ||
+                         ctx->g.vol >= (1ll << 32))) vec = 2;
         if (vec == 2 && (ctx->g.nx % 2 != 0 || ctx->g.nx < 4)) vec = 1;
         return vec;
     }
@@ -215,7 +219,7 @@ static bool chord_lists(const lbm_ctx *ctx, int vec) { return phys_walls(ctx->p)
 
 static int rebuild_lists(lbm_ctx *ctx, const uint8_t *flags, int vec, int ty, int block, cudaStream_t s) {
     if (chord_lists(ctx, vec) && ty == 1) {
-        CUDA_OK(ctx, build_chord_lists(ctx->g, flags, &ctx->d_ctiles, &ctx->d_links, ctx->tile_off, &ctx->d_nbr, &ctx->n_links, s));
+        CUDA_OK(ctx, build_chord_lists(ctx->g, flags, &ctx->d_ctiles, &ctx->d_tile_links, &ctx->d_links, ctx->tile_off, &ctx->d_nbr, &ctx->n_links, s));
         ctx->launches += 6;
     } else {
         CUDA_OK(ctx, build_work_lists(ctx->g, flags, vec, ty, &ctx->d_tiles, &ctx->d_tile_mask, ctx->tile_off, &ctx->d_nbr, s));
@@ -334,6 +338,7 @@ void lbm_destroy(lbm_ctx *ctx) {
     if (ctx->d_tile_mask) cudaFree(ctx->d_tile_mask);
     if (ctx->d_ctiles) cudaFree(ctx->d_ctiles);
     if (ctx->d_links) cudaFree(ctx->d_links);
+    if (ctx->d_tile_links) cudaFree(ctx->d_tile_links);
     if (ctx->d_stat_scratch) cudaFree(ctx->d_stat_scratch);
     if (ctx->d_nbr) cudaFree(ctx->d_nbr);
     delete ctx;
@@ -482,7 +487,7 @@ static int launch_planes(lbm_ctx *ctx, StepArgs &a, const Launcher &L, int z_beg
         const int t1 = both ? n_t + (ctx->tile_off[1] - ctx->tile_off[0]) + (ctx->tile_off[nz] - ctx->tile_off[nz - 1]) : ctx->tile_off[z_end];
         if (t1 <= t0) return 0;
         a.items = ctx->d_tiles; a.item_mask = ctx->d_tile_mask; a.item_begin = t0; a.n_items = t1 - t0; a.nbr = ctx->d_nbr;
-        a.ctiles = ctx->d_ctiles; a.links = ctx->d_links;
+        a.quads = ctx->d_ctiles; a.tile_links = ctx->d_tile_links; a.links = ctx->d_links;
         if (L.tma) {
             const TmaMaps *maps = nullptr;
             if (tensor_maps(ctx, a, L.tk.ty, &maps)) return 1;

@@ -226,16 +226,15 @@ __global__ void pressure_gradient_tiles_kernel(Grid G, const float *rho, const u
     }
 }
 
-// Same over the chord-fitted tiles of the four-cell walls kernel (one lane per active quad).
+// Same over the packed quad list of the four-cell walls kernel (one thread per lane slot).
 __global__ void pressure_gradient_chord_kernel(Grid G, const float *rho, const uint8_t *flags, float *bf, float max_force, float scale,
-                                               int accumulate, const uint4 *tiles, int n_items) {
-    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (w >= n_items) return;
-    const uint4 e = tiles[w];
-    const unsigned lane = threadIdx.x & 31u;
-    if (!((e.z >> lane) & 1u)) return;
-    const int xb = ((int)(e.x & 0xfffu) + (int)lane) * 4;
-    for (int i = 0; i < 4; ++i) pressure_gradient_cell(G, rho, flags, bf, max_force, scale, accumulate, xb + i, (int)(e.y & 0xffffu), (int)(e.y >> 16));
+                                               int accumulate, const unsigned long long *quads, int n_items) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= (long long)n_items * 32) return;
+    const unsigned long long e = quads[i];
+    if (!(e & (1ull << 44))) return;
+    const int xb = (int)(e & 0xfffu) * 4;
+    for (int k = 0; k < 4; ++k) pressure_gradient_cell(G, rho, flags, bf, max_force, scale, accumulate, xb + k, (int)((e >> 12) & 0xffffu), (int)((e >> 28) & 0xffffu));
 }
 
 // filter_paper.py:471-536
@@ -412,136 +411,153 @@ cudaError_t build_work_lists(const Grid &G, const uint8_t *flags, int vec, int t
 }
 #endif
 
-// ---- chord-fitted tiles and wall links of the four-cell walls kernel (lbm_phys_chord.cuh) ------------------------
-// A "quad" is 4 x-consecutive cells on a 16-byte boundary; it is active when it holds a fluid cell.  A tile is up to 32
-// consecutive quads of one row, STARTING at an active quad (greedy cover of the row from the left), so a tile begins
-// within 3 cells of a chord's first fluid cell and only the last tile of a chord is partly empty -- against x-aligned
-// 128-cell tiles, which make every tile of a V60 row a chord end.  Tile entry (uint4):
-//   .x = first quad | n_links << 12     .y = y | z << 16     .z = lane mask (bit l: quad first + l is active)
-//   .w = index of the tile's first wall link
-// Wall link (u32) = one (fluid cell, direction q) pair whose target x + e_q is solid: the post-collision f_q goes to the
-// solid cell's slot of opp(q) (halfway bounce-back on the write side, lbm_phys.cuh):
-//   bits 0-4 source lane, 5-6 cell of the quad, 7-11 q, 12-16 opp(q), 17-18 cy(q)+1, 19-20 cz(q)+1, 21-31 target x.
-// The kernels below are plain (one thread per row / per tile) so that tests/emu can run them on the CPU; they run once
-// per geometry change.
+// ---- packed quad list and wall links of the four-cell walls kernel (lbm_phys_chord.cuh) --------------------------
+// A "quad" is 4 x-consecutive cells on a 16-byte boundary; it is active when it holds a fluid cell.  The kernel's work list is
+// the sequence of ALL active quads of a plane in memory order (y, then x), cut into tiles of 32 -- one warp per tile, one lane
+// per quad, tiles run across row ends.  A first version cut tiles per chord (<= 32 quads of ONE row): on the V60 512^3 mask
+// that launched 14.77 M lane slots for 12.05 M active quads (82 % of the lanes alive), and since a warp costs the same
+// whether 11 or 32 of its lanes work, the step ran at 0.67 of the HBM peak where a periodic box (every lane alive) runs at
+// 0.86 (profiles/r02_exp_structure_cost_periodic_box.log).  Only the last tile of a plane is padded (slab launches address plane
+// ranges).  Per lane slot (u64): bits 0-11 quad index in the row, 12-27 y, 28-43 z, 44 live, 45 / 46 the previous / next lane
+// of the SAME tile holds the quad to the left / right in the same row (else the lane fetches that neighbour itself).
+// Wall link (u64) = one (fluid cell, direction q) pair whose target x + e_q is solid: the post-collision f_q goes to the solid
+// cell's slot of opp(q) (halfway bounce-back on the write side, lbm_phys.cuh): bits 0-31 target cell index in a scalar volume,
+// 32-36 source lane, 37-38 cell of the quad, 39-43 q, 44-48 opp(q).  Per tile (uint2): first link, number of links.
+// The kernels below are plain (one thread per row / per tile) so that tests/emu can run them on the CPU; they run once per
+// geometry change.
+#define LBM_QUAD_LIVE (1ull << 44)
+#define LBM_QUAD_LEFT (1ull << 45)
+#define LBM_QUAD_RIGHT (1ull << 46)
 __device__ __forceinline__ bool quad_active(const uint8_t *row, int q) {
     return !((row[4 * q] & row[4 * q + 1] & row[4 * q + 2] & row[4 * q + 3]) & LBM_FLAG_SOLID);
 }
-__global__ void chord_count_kernel(Grid G, const uint8_t *flags, int *row_tiles) {
+__global__ void quad_count_kernel(Grid G, const uint8_t *flags, int *row_quads) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= G.nz * G.ny) return;
     const int z = r / G.ny, y = r - z * G.ny;
     const uint8_t *row = flags + ((long long)(z + G.zg) * G.ny + y) * G.nx;
-    const int nq = G.nx / 4;
     int n = 0;
-    for (int q = 0; q < nq;) {
-        if (quad_active(row, q)) { ++n; q += 32; } else ++q;
-    }
-    row_tiles[r] = n;
+    for (int q = 0; q < G.nx / 4; ++q) n += quad_active(row, q) ? 1 : 0;
+    row_quads[r] = n;
 }
-__global__ void chord_fill_kernel(Grid G, const uint8_t *flags, const unsigned long long *nbr, const int *row_off, uint4 *tiles, int *tile_links) {
+// row_off: exclusive prefix of row_quads over all rows; plane_base[z]: first lane slot of plane z (a multiple of 32)
+__global__ void quad_fill_kernel(Grid G, const uint8_t *flags, const int *row_off, const int *plane_base, unsigned long long *quads) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= G.nz * G.ny) return;
     const int z = r / G.ny, y = r - z * G.ny;
-    const long long base = ((long long)(z + G.zg) * G.ny + y) * G.nx;
-    const uint8_t *row = flags + base;
-    const int nq = G.nx / 4;
-    int t = row_off[r];
-    for (int q = 0; q < nq;) {
-        if (!quad_active(row, q)) { ++q; continue; }
-        unsigned mask = 0; int nl = 0;
-        for (int l = 0; l < 32 && q + l < nq; ++l) {
-            if (!quad_active(row, q + l)) continue;
-            mask |= 1u << l;
-            for (int c = 0; c < 4; ++c) {
-                const int x = 4 * (q + l) + c;
-                const unsigned fl = row[x];
-                if (!(fl & LBM_FLAG_SOLID) && (fl & LBM_FLAG_NEAR)) nl += __popc((unsigned)nbr[base + x] & 0x7fffeu);
-            }
-        }
-        tiles[t] = make_uint4((unsigned)q, (unsigned)y | ((unsigned)z << 16), mask, 0u);
-        tile_links[t] = nl;
-        ++t; q += 32;
+    const uint8_t *row = flags + ((long long)(z + G.zg) * G.ny + y) * G.nx;
+    int slot = plane_base[z] + (row_off[r] - row_off[z * G.ny]);
+    int prev = -2;
+    for (int q = 0; q < G.nx / 4; ++q) {
+        if (!quad_active(row, q)) continue;
+        unsigned long long e = (unsigned long long)q | ((unsigned long long)y << 12) | ((unsigned long long)z << 28) | LBM_QUAD_LIVE;
+        if (prev == q - 1 && (slot & 31) != 0) e |= LBM_QUAD_LEFT;
+        if (q + 1 < G.nx / 4 && quad_active(row, q + 1) && ((slot + 1) & 31) != 0) e |= LBM_QUAD_RIGHT;
+        quads[slot++] = e;
+        prev = q;
     }
 }
-__global__ void chord_links_kernel(Grid G, const uint8_t *flags, const unsigned long long *nbr, uint4 *tiles, const int *link_off, int n_tiles,
-                                   unsigned *links) {
+// one thread per tile: number of wall links (fill == 0) or the links themselves
+__global__ void quad_links_kernel(Grid G, const uint8_t *flags, const unsigned long long *nbr, const unsigned long long *quads, int n_tiles,
+                                  int fill, int *tile_count, const int *link_off, uint2 *tile_links, unsigned long long *links) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tiles) return;
-    const uint4 e = tiles[t];
-    const int q0 = (int)e.x, y = (int)(e.y & 0xffffu), z = (int)(e.y >> 16);
-    const long long base = ((long long)(z + G.zg) * G.ny + y) * G.nx;
-    const uint8_t *row = flags + base;
-    const unsigned begin = (unsigned)link_off[t];
-    unsigned o = begin;
+    unsigned n = 0;
+    const unsigned begin = fill ? (unsigned)link_off[t] : 0u;
     for (int l = 0; l < 32; ++l) {
-        if (!((e.z >> l) & 1u)) continue;
+        const unsigned long long e = quads[(long long)t * 32 + l];
+        if (!(e & LBM_QUAD_LIVE)) continue;
+        const int q0 = (int)(e & 0xfffu), y = (int)((e >> 12) & 0xffffu), z = (int)((e >> 28) & 0xffffu);
+        const long long base = ((long long)(z + G.zg) * G.ny + y) * G.nx;
         for (int c = 0; c < 4; ++c) {
-            const int x = 4 * (q0 + l) + c;
-            const unsigned fl = row[x];
+            const int x = 4 * q0 + c;
+            const unsigned fl = flags[base + x];
             if ((fl & LBM_FLAG_SOLID) || !(fl & LBM_FLAG_NEAR)) continue;
             const unsigned m = (unsigned)nbr[base + x];
             for (int q = 1; q < Q; ++q) {
                 if (!((m >> opp(q)) & 1u)) continue;
-                int xt = x + cx(q);
-                if (xt < 0) xt = G.nx - 1; else if (xt >= G.nx) xt = 0;          // periodic wrap (an open face is never "solid")
-                links[o++] = (unsigned)l | ((unsigned)c << 5) | ((unsigned)q << 7) | ((unsigned)opp(q) << 12) | ((unsigned)(cy(q) + 1) << 17) |
-                             ((unsigned)(cz(q) + 1) << 19) | ((unsigned)xt << 21);
+                if (fill) {
+                    int xt = x + cx(q), yt = y + cy(q), zt = z + G.zg + cz(q);          // periodic wrap (an open face is never "solid")
+                    if (xt < 0) xt = G.nx - 1; else if (xt >= G.nx) xt = 0;
+                    if (yt < 0) yt = G.ny - 1; else if (yt >= G.ny) yt = 0;
+                    if (!G.zg) { if (zt < 0) zt = G.nz - 1; else if (zt >= G.nz) zt = 0; }
+                    const unsigned long long target = (unsigned long long)(((long long)zt * G.ny + yt) * G.nx + xt);
+                    links[begin + n] = target | ((unsigned long long)l << 32) | ((unsigned long long)c << 37) | ((unsigned long long)q << 39) |
+                                       ((unsigned long long)opp(q) << 44);
+                }
+                ++n;
             }
         }
     }
-    tiles[t].x = (unsigned)q0 | ((o - begin) << 12);
-    tiles[t].w = begin;
+    if (fill) tile_links[t] = make_uint2(begin, n);
+    else tile_count[t] = (int)n;
 }
 #ifndef LBM_EMULATE_ON_HOST
-// Builds the chord-fitted tile list, its per-plane offsets (host vector of nz + 1 entries), the wall links and the
-// neighbour masks.  Synchronises the stream: geometry changes are rare.
-cudaError_t build_chord_lists(const Grid &G, const uint8_t *flags, uint4 **d_ctiles, unsigned **d_links, std::vector<int> &tile_off,
-                              unsigned long long **d_nbr, long long *n_links_out, cudaStream_t s) {
+// Builds the packed quad list, its per-plane TILE offsets (host vector of nz + 1 entries), the wall links and the neighbour
+// masks.  Synchronises the stream: geometry changes are rare.
+cudaError_t build_chord_lists(const Grid &G, const uint8_t *flags, unsigned long long **d_quads, uint2 **d_tile_links, unsigned long long **d_links,
+                              std::vector<int> &tile_off, unsigned long long **d_nbr, long long *n_links_out, cudaStream_t s) {
     cudaError_t e;
-    if (G.nx % 4 != 0 || G.nx > 2048 || G.ny > 65535 || G.nz > 65535) return cudaErrorInvalidValue;      // packing limits of a tile entry / link
+    if (G.nx % 4 != 0 || G.nx > 16384 || G.ny > 65535 || G.nz + 2 * G.zg > 65535 || G.vol >= (1ll << 32)) return cudaErrorInvalidValue;   // packing limits
     const int rows = G.nz * G.ny;
-    int *row_cnt = nullptr, *row_off = nullptr, *tile_links = nullptr, *link_off = nullptr; void *tmp = nullptr; size_t tmp_bytes = 0;
+    int *row_cnt = nullptr, *row_off = nullptr, *d_plane_base = nullptr, *tile_cnt = nullptr, *link_off = nullptr; void *tmp = nullptr; size_t tmp_bytes = 0;
     if (!*d_nbr) { if ((e = cudaMalloc(d_nbr, sizeof(unsigned long long) * (size_t)G.vol)) != cudaSuccess) return e; }
     neighbour_mask_kernel<<<148 * 16, 256, 0, s>>>(G, flags, *d_nbr);
     if ((e = cudaMalloc(&row_cnt, sizeof(int) * (size_t)(rows + 1))) != cudaSuccess) return e;
     if ((e = cudaMalloc(&row_off, sizeof(int) * (size_t)(rows + 1))) != cudaSuccess) return e;
     cudaMemsetAsync(row_cnt + rows, 0, sizeof(int), s);
-    chord_count_kernel<<<(rows + 127) / 128, 128, 0, s>>>(G, flags, row_cnt);
+    quad_count_kernel<<<(rows + 127) / 128, 128, 0, s>>>(G, flags, row_cnt);
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, row_cnt, row_off, rows + 1, s);
     if ((e = cudaMalloc(&tmp, tmp_bytes)) != cudaSuccess) return e;
     cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, row_cnt, row_off, rows + 1, s);
-    tile_off.assign(G.nz + 1, 0);
-    if ((e = cudaMemcpy2DAsync(tile_off.data(), sizeof(int), row_off, sizeof(int) * (size_t)G.ny, sizeof(int), (size_t)G.nz + 1, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+    std::vector<int> plane_start((size_t)G.nz + 1), plane_base((size_t)G.nz + 1, 0);
+    if ((e = cudaMemcpy2DAsync(plane_start.data(), sizeof(int), row_off, sizeof(int) * (size_t)G.ny, sizeof(int), (size_t)G.nz + 1, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
     if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
     cudaFree(tmp); tmp = nullptr;
+    tile_off.assign(G.nz + 1, 0);
+    for (int z = 0; z < G.nz; ++z) {
+        const int nq = plane_start[z + 1] - plane_start[z];
+        tile_off[z + 1] = tile_off[z] + (nq + 31) / 32;            // the last tile of a plane is padded with dead lanes
+        plane_base[z + 1] = tile_off[z + 1] * 32;
+    }
     const int n_t = tile_off[G.nz];
-    if (*d_ctiles) { cudaFree(*d_ctiles); *d_ctiles = nullptr; }
+    // slabs: room for a copy of the first and the last owned plane's tiles behind the list (one launch for both, lbm_api.cu)
+    const int n_b = (G.zg && G.nz >= 2) ? (tile_off[1] - tile_off[0]) + (tile_off[G.nz] - tile_off[G.nz - 1]) : 0;
+    if (*d_quads) { cudaFree(*d_quads); *d_quads = nullptr; }
+    if (*d_tile_links) { cudaFree(*d_tile_links); *d_tile_links = nullptr; }
     if (*d_links) { cudaFree(*d_links); *d_links = nullptr; }
-    const int n_b = (G.zg && G.nz >= 2) ? (tile_off[1] - tile_off[0]) + (tile_off[G.nz] - tile_off[G.nz - 1]) : 0;      // see build_work_lists
-    if ((e = cudaMalloc(d_ctiles, sizeof(uint4) * (size_t)(n_t + n_b > 0 ? n_t + n_b : 1))) != cudaSuccess) return e;
-    if ((e = cudaMalloc(&tile_links, sizeof(int) * (size_t)(n_t + 1))) != cudaSuccess) return e;
+    const size_t nt_alloc = (size_t)(n_t + n_b > 0 ? n_t + n_b : 1);
+    if ((e = cudaMalloc(d_quads, sizeof(unsigned long long) * 32 * nt_alloc)) != cudaSuccess) return e;
+    if ((e = cudaMalloc(d_tile_links, sizeof(uint2) * nt_alloc)) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&d_plane_base, sizeof(int) * (size_t)(G.nz + 1))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&tile_cnt, sizeof(int) * (size_t)(n_t + 1))) != cudaSuccess) return e;
     if ((e = cudaMalloc(&link_off, sizeof(int) * (size_t)(n_t + 1))) != cudaSuccess) return e;
-    cudaMemsetAsync(tile_links + n_t, 0, sizeof(int), s);
+    cudaMemsetAsync(*d_quads, 0, sizeof(unsigned long long) * 32 * nt_alloc, s);      // dead lanes: cell (0, 0, 0), never stored
+    cudaMemsetAsync(*d_tile_links, 0, sizeof(uint2) * nt_alloc, s);
+    cudaMemsetAsync(tile_cnt + n_t, 0, sizeof(int), s);
+    cudaMemcpyAsync(d_plane_base, plane_base.data(), sizeof(int) * (size_t)(G.nz + 1), cudaMemcpyHostToDevice, s);
     int n_l = 0;
     if (n_t > 0) {
-        chord_fill_kernel<<<(rows + 127) / 128, 128, 0, s>>>(G, flags, *d_nbr, row_off, *d_ctiles, tile_links);
-        cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, tile_links, link_off, n_t + 1, s);
+        quad_fill_kernel<<<(rows + 127) / 128, 128, 0, s>>>(G, flags, row_off, d_plane_base, *d_quads);
+        quad_links_kernel<<<(n_t + 127) / 128, 128, 0, s>>>(G, flags, *d_nbr, *d_quads, n_t, 0, tile_cnt, nullptr, nullptr, nullptr);
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, tile_cnt, link_off, n_t + 1, s);
         if ((e = cudaMalloc(&tmp, tmp_bytes)) != cudaSuccess) return e;
-        cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, tile_links, link_off, n_t + 1, s);
+        cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, tile_cnt, link_off, n_t + 1, s);
         if ((e = cudaMemcpyAsync(&n_l, link_off + n_t, sizeof(int), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
         if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
     }
-    if ((e = cudaMalloc(d_links, sizeof(unsigned) * (size_t)(n_l > 0 ? n_l : 1))) != cudaSuccess) return e;
-    if (n_t > 0) chord_links_kernel<<<(n_t + 127) / 128, 128, 0, s>>>(G, flags, *d_nbr, *d_ctiles, link_off, n_t, *d_links);
-    if (n_b > 0) {      // the finished entries (link counts and offsets included) of the two boundary planes, once more, contiguous
+    if ((e = cudaMalloc(d_links, sizeof(unsigned long long) * (size_t)(n_l > 0 ? n_l : 1))) != cudaSuccess) return e;
+    if (n_t > 0) quad_links_kernel<<<(n_t + 127) / 128, 128, 0, s>>>(G, flags, *d_nbr, *d_quads, n_t, 1, nullptr, link_off, *d_tile_links, *d_links);
+    if (n_b > 0) {      // the finished entries of the two boundary planes, once more, contiguous
         const int n0 = tile_off[1] - tile_off[0], n1 = tile_off[G.nz] - tile_off[G.nz - 1];
-        cudaMemcpyAsync(*d_ctiles + n_t, *d_ctiles + tile_off[0], sizeof(uint4) * (size_t)n0, cudaMemcpyDeviceToDevice, s);
-        cudaMemcpyAsync(*d_ctiles + n_t + n0, *d_ctiles + tile_off[G.nz - 1], sizeof(uint4) * (size_t)n1, cudaMemcpyDeviceToDevice, s);
+        cudaMemcpyAsync(*d_quads + (size_t)n_t * 32, *d_quads + (size_t)tile_off[0] * 32, sizeof(unsigned long long) * 32 * (size_t)n0, cudaMemcpyDeviceToDevice, s);
+        cudaMemcpyAsync(*d_quads + (size_t)(n_t + n0) * 32, *d_quads + (size_t)tile_off[G.nz - 1] * 32, sizeof(unsigned long long) * 32 * (size_t)n1, cudaMemcpyDeviceToDevice, s);
+        cudaMemcpyAsync(*d_tile_links + n_t, *d_tile_links + tile_off[0], sizeof(uint2) * (size_t)n0, cudaMemcpyDeviceToDevice, s);
+        cudaMemcpyAsync(*d_tile_links + n_t + n0, *d_tile_links + tile_off[G.nz - 1], sizeof(uint2) * (size_t)n1, cudaMemcpyDeviceToDevice, s);
     }
     e = cudaStreamSynchronize(s);
     if (n_links_out) *n_links_out = n_l;
-    cudaFree(tmp); cudaFree(row_cnt); cudaFree(row_off); cudaFree(tile_links); cudaFree(link_off);
+    cudaFree(tmp); cudaFree(row_cnt); cudaFree(row_off); cudaFree(d_plane_base); cudaFree(tile_cnt); cudaFree(link_off);
     if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }
@@ -790,8 +806,8 @@ cudaError_t launch_face_bc(const Grid &G, float *rho, const uint8_t *flags, cuda
     return cudaGetLastError();
 }
 cudaError_t launch_pressure_gradient(const Grid &G, const float *rho, const uint8_t *flags, float *bf, float max_force, float scale, int accumulate,
-                                     const unsigned *items, const uint4 *ctiles, int n_items, int vec, cudaStream_t s) {
-    if (ctiles) {     // chord-fitted tiles of the four-cell walls kernel
+                                     const unsigned *items, const unsigned long long *ctiles, int n_items, int vec, cudaStream_t s) {
+    if (ctiles) {     // packed quad list of the four-cell walls kernel
         if (n_items > 0) pressure_gradient_chord_kernel<<<(n_items + 3) / 4, 128, 0, s>>>(G, rho, flags, bf, max_force, scale, accumulate, ctiles, n_items);
         return cudaGetLastError();
     }

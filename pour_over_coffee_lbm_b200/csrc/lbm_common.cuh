@@ -43,8 +43,9 @@ struct StepArgs {
     int item_begin, n_items;
     const unsigned *item_mask;   // VEC = 4 walls kernel: per list entry, the lanes that must load (lbm_phys.cuh)
     const unsigned long long *nbr;     // per cell (valid where NEAR): solid-source bits | out-of-box bits << 32
-    // chord-fitted tiles of the four-cell walls kernel (lbm_phys_chord.cuh): one uint4 per tile, one u32 per wall link
-    const uint4 *ctiles; const unsigned *links;
+    // packed quad list of the four-cell walls kernel (lbm_phys_chord.cuh, lbm_aux.cu): one u64 per lane slot, one uint2 (first link,
+    // links) per tile, one u64 per wall link
+    const unsigned long long *quads; const uint2 *tile_links; const unsigned long long *links;
     // fused pressure-gradient drive (LBM_FEAT_DRIVE): rho of the previous step, clamp and scale of the force
     const float *rho_src; float drive_max_force, drive_scale;
     int write_macro;

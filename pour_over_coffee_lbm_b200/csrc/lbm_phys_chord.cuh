@@ -1,4 +1,4 @@
-// compat = physical behind walls, four cells per thread on chord-fitted tiles, populations staged in shared memory
+// compat = physical behind walls, four cells per thread on a packed list of active quads, populations staged in shared memory
 // (sm_100a) -- the default walls kernel.
 //
 // Why (ncu, V60 512^3, B200).  The two-cell register-staged kernel (lbm_phys.cuh) ran at 57 % of DRAM peak with 927
@@ -8,29 +8,34 @@
 // spill instructions -- and 19 % of all stall samples sat on two spill STOREs inside the load phase: a loaded value has to
 // arrive before it can be spilled, so the warp's loads went out in two or three serialised round trips
 // (profiles/r02_chord_v1_*).  This version takes the populations out of the register file while they are in flight:
-//   * tiles are CHORD-FITTED (lbm_aux.cu, build_chord_lists): up to 32 consecutive quads (4 cells, 16-byte aligned) of one
-//     row starting at the chord's first active quad, with a 32-bit lane mask; 48.2 M cell slots are launched for the 47.7 M
-//     fluid cells of the V60 512^3 mask (x-aligned 64-cell tiles: 58.9 M).  Lanes outside the mask load and store nothing;
-//   * every live lane issues 19 cp.async of 16 bytes (global -> shared, no register, L1 bypassed) into the warp's private
+//   * the work list is the sequence of ALL active quads (4 cells, 16-byte aligned, at least one fluid) of a plane in memory
+//     order, cut into tiles of 32: one warp per tile, one lane per quad, tiles run across row ends (lbm_aux.cu,
+//     build_chord_lists).  A warp costs the same whether 11 or 32 of its lanes work: tiles cut per chord left 18 % of the lanes
+//     of a V60 512^3 step idle (0.67 of the HBM peak against 0.86 on a box where every lane is alive); the packed list launches
+//     12.05 M lane slots for 12.05 M active quads.  Each lane reads its own (quad, y, z) entry;
+//   * every lane issues 19 cp.async of 16 bytes (global -> shared, no register, L1 bypassed) into the warp's private
 //     staging rows, one row of 4 + 128 + 4 floats per population: lane l owns words [4 + 4l, 8 + 4l).  The one-cell shift in
 //     x of the 10 moving populations is an ADDRESS offset when the row is read back (cells x-1 .. x+2 are words 3 + 4l ..),
-//     so there are no shuffles and no register moves; the x-1 / x+4 neighbour that no live lane brings (first / last lane of
-//     a chord, row ends, periodic wrap) arrives by a 4-byte cp.async in the word next to the lane's own;
+//     so there are no shuffles and no register moves; where the neighbouring lane does not hold the neighbouring quad
+//     (chord ends, row changes inside a tile, row ends, periodic wrap) the lane fetches the one word itself by a 4-byte
+//     cp.async into a small per-warp edge array;
 //   * the two cell pairs of a thread are collided one after the other (packed f32x2); each pair reads its 19 inputs from the
 //     row (LDS.64, or two LDS.32 for the shifted ones) directly into register pairs and writes its results back into the
 //     lane's own words (STS.64), so only one pair is in registers at a time;
 //   * write-back: LDS.128 + 128-bit streaming store per population for all-fluid quads; the fluid cells of a quad a chord
 //     ends in go out one cell at a time with lane q < 19 storing population q (warp-uniform loop over a ballot).  Halfway
 //     bounce-back stays on the write side (post-collision f_q of a fluid cell -> slot opp(q) of its solid neighbour,
-//     lbm_phys.cuh) but is a precomputed WALL LINK list of the tile (one u32 per (cell, q)): all 32 lanes walk it together,
+//     lbm_phys.cuh) but is a precomputed WALL LINK list of the tile (one u64 per (cell, q)): all 32 lanes walk it together,
 //     one link per lane and round (LDS + one 4-byte store), the first round prefetched with the tile.  The neighbour masks
 //     are not read by this kernel, the flag word only for the solid / filter / LES bits;
 //   * tried on top of this and rejected, with numbers (profiles/r02_tune_chord_pipelined.log, r02_exp_l2_prefetch.log,
-//     r02_exp_entry_load.log; V60 512^3, same box): a persistent launch with two stages per warp and the next tile's loads in
-//     flight during the collision (8 warps per SM 1.92 ms, 10 warps 2.20 ms, against 1.87 ms for one tile per warp at 16 warps:
-//     half the warps do hide the memory latency, but then the ~6 cycles between two issues of one warp are the limit);
-//     prefetching the inputs of the tile 256 .. 16384 places ahead into L2 (1.78 .. 2.19 ms against 1.79 ms); a persisting
-//     L2 window over the tile list and tile coordinates computed instead of loaded (no change);
+//     r02_exp_entry_load.log, r02_exp_bulk_store.log, r02_exp_even_quad_alignment.log; V60 512^3, same box): a persistent launch
+//     with two stages per warp and the next tile's loads in flight during the collision (8 warps per SM 1.92 ms, 10 warps
+//     2.20 ms, against 1.87 ms for one tile per warp at 16 warps: half the warps do hide the memory latency, but then the ~6
+//     cycles between two issues of one warp are the limit); prefetching the inputs of the tile 256 .. 16384 places ahead into
+//     L2 (1.78 .. 2.19 ms against 1.79 ms); a persisting L2 window over the tile list and tile coordinates computed instead
+//     of loaded (no change); write-back through cp.async.bulk (each UBLKCP drags ~19 uniform-datapath instructions: +1 %);
+//     tiles starting on 32-byte boundaries (+2 %);
 //   * LBM_FEAT_DRIVE: the pressure-gradient drive (pressure_gradient_drive.py:124-193) is evaluated from the PREVIOUS
 //     step's rho inside this kernel (same statements as the stand-alone producer, lbm_common.cuh) while the populations
 //     are still in flight, and added to the body force: the separate producer pass and its 12 B force round trip disappear.
@@ -57,19 +62,19 @@ constexpr int CHORD_ROW = 4 + 128 + 4;                // floats per staged popul
 constexpr unsigned CHORD_ROWB = CHORD_ROW * 4;        // bytes per row
 constexpr int CHORD_STAGE = Q * CHORD_ROW;            // floats per stage (one tile): 10336 B
 
-// what a lane knows about its tile from the entry (recomputed where needed: ~25 integer instructions)
+// what a lane knows about its quad from its list entry (lbm_aux.cu: bits 0-11 quad, 12-27 y, 28-43 z, 44 live, 45 / 46 the
+// neighbouring lane holds the neighbouring quad)
 struct ChordGeom {
-    bool live;
+    bool live, left_adj, right_adj;
     int x0, y, z;
-    unsigned lmask, own, row0;
+    unsigned own, row0;
     int dym, dyq, dzm, dzq;          // neighbour rows as 32-bit index deltas: periodic wrap, else clamp (a clamped source lies
 };                                   // outside an open face and is replaced by w_q)
-__device__ __forceinline__ ChordGeom chord_decode(const uint4 e, const unsigned lane, const Grid &G) {
+__device__ __forceinline__ ChordGeom chord_decode(const unsigned long long e, const Grid &G) {
     ChordGeom t;
-    t.lmask = e.z;
-    t.live = ((e.z >> lane) & 1u) != 0;
-    t.x0 = ((int)(e.x & 0xfffu) + (t.live ? (int)lane : 0)) * 4;      // dead lanes shadow lane 0 (always live) for their addresses
-    t.y = (int)(e.y & 0xffffu); t.z = (int)(e.y >> 16);
+    t.live = ((e >> 44) & 1ull) != 0; t.left_adj = ((e >> 45) & 1ull) != 0; t.right_adj = ((e >> 46) & 1ull) != 0;
+    t.x0 = (int)(e & 0xfffull) * 4;         // dead lanes (padding of a plane's last tile) sit on cell (0, 0, 0): loaded, never stored
+    t.y = (int)((e >> 12) & 0xffffull); t.z = (int)((e >> 28) & 0xffffull);
     t.row0 = ((unsigned)(t.z + G.zg) * (unsigned)G.ny + (unsigned)t.y) * (unsigned)G.nx;
     t.own = t.row0 + (unsigned)t.x0;
     const int nxi = G.nx, plane = (int)G.plane;
@@ -82,56 +87,58 @@ __device__ __forceinline__ ChordGeom chord_decode(const uint4 e, const unsigned 
     }
     return t;
 }
+// index of a moving population in the per-warp edge array: cx > 0 (1, 7, 9, 11, 13) -> 0..4, cx < 0 (2, 8, 10, 12, 14) -> 5..9
+__host__ __device__ constexpr int edge_slot(int q) { return q == 1 ? 0 : q == 2 ? 5 : (cx(q) > 0 ? (q - 7) / 2 + 1 : (q - 8) / 2 + 6); }
+constexpr unsigned CHORD_EDGEB = 32 * 4;              // bytes per population in the edge array
 
 // (1) populations: global -> shared, nothing held in registers while in flight.  s_own = shared-window address of this lane's
-// words of row 0 of the stage.
-__device__ __forceinline__ void chord_issue_loads(const StepArgs &P, const ChordGeom &t, const unsigned lane, const unsigned s_own) {
+// words of row 0 of the stage, s_edge = of this lane's word of population slot 0 in the edge array.
+__device__ __forceinline__ void chord_issue_loads(const StepArgs &P, const ChordGeom &t, const unsigned s_own, const unsigned s_edge) {
     const Grid &G = P.g;
     const unsigned vol = (unsigned)G.vol;
-    if (t.live) {
-        const float *rowp[3][3];
+    const float *rowp[3][3];
 #pragma unroll
-        for (int dz = -1; dz <= 1; ++dz)
+    for (int dz = -1; dz <= 1; ++dz)
 #pragma unroll
-            for (int dy = -1; dy <= 1; ++dy)
-                rowp[dz + 1][dy + 1] = P.src + (t.own + (unsigned)(dy < 0 ? t.dym : (dy > 0 ? t.dyq : 0)) + (unsigned)(dz < 0 ? t.dzm : (dz > 0 ? t.dzq : 0)));
+        for (int dy = -1; dy <= 1; ++dy)
+            rowp[dz + 1][dy + 1] = P.src + (t.own + (unsigned)(dy < 0 ? t.dym : (dy > 0 ? t.dyq : 0)) + (unsigned)(dz < 0 ? t.dzm : (dz > 0 ? t.dzq : 0)));
+    static_for<0, Q>([&](auto qq) {
+        constexpr int q = decltype(qq)::value;
+        cp_async16(s_own + q * CHORD_ROWB, plane_of(rowp[1 - cz(q)][1 - cy(q)], vol, q));
+    });
+    // x-1 / x+4 neighbour of the quad when the neighbouring lane does not bring it
+    if (!t.left_adj) {
+        int dxm = -1; if (t.x0 == 0) dxm = G.per_x ? G.nx - 1 : 0;
         static_for<0, Q>([&](auto qq) {
             constexpr int q = decltype(qq)::value;
-            cp_async16(s_own + q * CHORD_ROWB, plane_of(rowp[1 - cz(q)][1 - cy(q)], vol, q));
+            if constexpr (cx(q) > 0) cp_async4(s_edge + edge_slot(q) * CHORD_EDGEB, plane_of(rowp[1 - cz(q)][1 - cy(q)], vol, q) + dxm);
         });
-        // x-1 / x+4 neighbour of the quad when no live lane brings it: first / last lane, a gap in the lane mask, row ends
-        if (lane == 0 || !((t.lmask >> (lane - 1)) & 1u)) {
-            int dxm = -1; if (t.x0 == 0) dxm = G.per_x ? G.nx - 1 : 0;
-            static_for<0, Q>([&](auto qq) {
-                constexpr int q = decltype(qq)::value;
-                if constexpr (cx(q) > 0) cp_async4(s_own + q * CHORD_ROWB - 4, plane_of(rowp[1 - cz(q)][1 - cy(q)], vol, q) + dxm);
-            });
-        }
-        if (lane == 31 || !((t.lmask >> (lane + 1)) & 1u)) {
-            int dxq = 4; if (t.x0 == G.nx - 4) dxq = G.per_x ? -(G.nx - 4) : 3;
-            static_for<0, Q>([&](auto qq) {
-                constexpr int q = decltype(qq)::value;
-                if constexpr (cx(q) < 0) cp_async4(s_own + q * CHORD_ROWB + 16, plane_of(rowp[1 - cz(q)][1 - cy(q)], vol, q) + dxq);
-            });
-        }
+    }
+    if (!t.right_adj) {
+        int dxq = 4; if (t.x0 == G.nx - 4) dxq = G.per_x ? -(G.nx - 4) : 3;
+        static_for<0, Q>([&](auto qq) {
+            constexpr int q = decltype(qq)::value;
+            if constexpr (cx(q) < 0) cp_async4(s_edge + edge_slot(q) * CHORD_EDGEB, plane_of(rowp[1 - cz(q)][1 - cy(q)], vol, q) + dxq);
+        });
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
 // (2) flags, body force, phase, rho stencil of the fused drive, first round of wall links: plain loads into registers
 struct ChordAux {
-    unsigned flag_word, link0;
+    unsigned flag_word;
+    unsigned long long link0;
     float4 bf[3], ph;
     float4 r, rym, ryp, rzm, rzp;
     float rxm, rxp;
 };
 template <bool FORCED, bool DRIVE>
-__device__ __forceinline__ void chord_load_aux(const StepArgs &P, const ChordGeom &t, const uint4 e, const unsigned lane, ChordAux &a) {
+__device__ __forceinline__ void chord_load_aux(const StepArgs &P, const ChordGeom &t, const uint2 tl, const unsigned lane, ChordAux &a) {
     const Grid &G = P.g;
     const unsigned vol = (unsigned)G.vol;
     a.flag_word = __ldg(reinterpret_cast<const unsigned *>(P.flags + t.own));
     a.link0 = 0;
-    if (lane < (e.x >> 12)) a.link0 = __ldg(P.links + e.w + lane);
+    if (lane < tl.y) a.link0 = __ldg(P.links + tl.x + lane);
     if constexpr (FORCED) {
         if (P.force != nullptr) {
 #pragma unroll
@@ -187,14 +194,14 @@ __device__ __forceinline__ void chord_force(const StepArgs &P, const ChordGeom &
 // s_row0 = shared-window address of word 0 of lane 0 in row 0 of the stage, s_park = of this lane's 8 bytes in the warp's
 // 4 x 256 B parking area for the first pair's rho, u.
 template <bool FORCED, bool LES, bool POROUS, bool DRIVE, bool COLLIDE>
-__device__ __forceinline__ void chord_compute_store(const StepArgs &P, const ChordGeom &t, const uint4 e, const ChordAux &a, const float (&F)[3][4],
+__device__ __forceinline__ void chord_compute_store(const StepArgs &P, const ChordGeom &t, const uint2 tl, const ChordAux &a, const float (&F)[3][4],
                                                     const float (&ph)[4], const unsigned lane, const unsigned s_own, const unsigned s_row0,
-                                                    const unsigned s_park) {
+                                                    const unsigned s_edge, const unsigned s_park) {
     constexpr unsigned FULL = 0xffffffffu;
     constexpr bool HAS_F = FORCED || DRIVE;
     constexpr unsigned ROWB = CHORD_ROWB;
     const Grid &G = P.g;
-    const unsigned vol = (unsigned)G.vol, own = t.own, n_links = e.x >> 12;
+    const unsigned vol = (unsigned)G.vol, own = t.own, n_links = tl.y;
     const int x0 = t.x0, y = t.y, z = t.z;
     const bool live = t.live;
     const bool has_phase = FORCED && P.phase != nullptr;
@@ -221,12 +228,12 @@ __device__ __forceinline__ void chord_compute_store(const StepArgs &P, const Cho
     // The two cell pairs, one after the other.  Pair h = cells 2h, 2h + 1 of the quad; population q of those cells:
     //   cx = 0: words 2h, 2h + 1 of the lane; cx > 0 (source x - 1): words 2h - 1, 2h; cx < 0 (source x + 1): words 2h + 1, 2h + 2.
     // Before pair 0 writes its results into words 0, 1, every word of pair 1 that a result could overwrite is taken:
-    // the lane's own word 1 (cx > 0) and the next lane's word 0 (cx < 0).
+    // the lane's own word 1 (cx > 0) and the next lane's word 0 (cx < 0; from the edge array where that lane holds another quad).
     float keep[Q];
     static_for<0, Q>([&](auto qq) {
         constexpr int q = decltype(qq)::value;
         if constexpr (cx(q) > 0) keep[q] = lds32(s_own + q * ROWB + 4);
-        if constexpr (cx(q) < 0) keep[q] = lds32(s_own + q * ROWB + 16);
+        if constexpr (cx(q) < 0) keep[q] = lds32(t.right_adj ? s_own + q * ROWB + 16 : s_edge + edge_slot(q) * CHORD_EDGEB);
     });
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -235,7 +242,8 @@ __device__ __forceinline__ void chord_compute_store(const StepArgs &P, const Cho
             constexpr int q = decltype(qq)::value;
             const unsigned sa = s_own + q * ROWB + 8 * h;
             if constexpr (cx(q) == 0) fp[q] = lds64(sa);
-            else if constexpr (cx(q) > 0) fp[q] = h == 0 ? p2_make(lds32(sa - 4), lds32(sa)) : p2_make(keep[q], lds32(sa));
+            else if constexpr (cx(q) > 0)
+                fp[q] = h == 0 ? p2_make(lds32(t.left_adj ? sa - 4 : s_edge + edge_slot(q) * CHORD_EDGEB), lds32(sa)) : p2_make(keep[q], lds32(sa));
             else fp[q] = h == 0 ? p2_make(lds32(sa + 4), lds32(sa + 8)) : p2_make(lds32(sa + 4), keep[q]);
         });
         if (on_face) {
@@ -314,36 +322,38 @@ __device__ __forceinline__ void chord_compute_store(const StepArgs &P, const Cho
         }
         // wall links (halfway bounce-back, write side): one link per lane and round, the first round was loaded with the tile
         for (unsigned i = lane; i < n_links; i += 32u) {
-            const unsigned L = i < 32u ? a.link0 : __ldg(P.links + e.w + i);
-            const float v = lds32(s_row0 + ((L >> 7) & 31u) * ROWB + (((L & 31u) << 2) + ((L >> 5) & 3u)) * 4u);
-            const unsigned cyl = (L >> 17) & 3u, czl = (L >> 19) & 3u;
-            const unsigned tg = t.row0 + (L >> 21) + (unsigned)(cyl == 0 ? t.dym : (cyl == 2 ? t.dyq : 0)) + (unsigned)(czl == 0 ? t.dzm : (czl == 2 ? t.dzq : 0));
-            *plane_of(P.dst + tg, vol, (int)((L >> 12) & 31u)) = v;
+            const unsigned long long L = i < 32u ? a.link0 : __ldg(P.links + tl.x + i);
+            const unsigned hi = (unsigned)(L >> 32);
+            const float v = lds32(s_row0 + ((hi >> 7) & 31u) * ROWB + (((hi & 31u) << 2) + ((hi >> 5) & 3u)) * 4u);
+            *plane_of(P.dst + (unsigned)L, vol, (int)((hi >> 12) & 31u)) = v;
         }
     }
 }
 
-// One tile per warp (one launch of ceil(tiles / warps per CTA) CTAs).
+// One tile (32 consecutive entries of the packed quad list) per warp.
 template <bool FORCED, bool LES, bool POROUS, bool DRIVE, int BLOCK, bool COLLIDE, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) phys_chord_kernel(const __grid_constant__ StepArgs P) {
     __shared__ __align__(16) float stage[BLOCK / 32][CHORD_STAGE];
+    __shared__ float edge[BLOCK / 32][10][32];
     __shared__ __align__(8) float park[BLOCK / 32][4][64];
     const unsigned lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
     const int w = (blockIdx.x * BLOCK + threadIdx.x) >> 5;
     if (w >= P.n_items) return;                                          // warp-uniform
-    const uint4 e = __ldg(P.ctiles + P.item_begin + w);
-    const ChordGeom t = chord_decode(e, lane, P.g);
-    // dead lanes read lane 0's words -- benign values for the arithmetic they run along with the warp -- and write nothing
+    const size_t tile = (size_t)P.item_begin + (size_t)w;
+    const unsigned long long e = __ldg(P.quads + tile * 32 + lane);
+    const uint2 tl = __ldg(P.tile_links + tile);
+    const ChordGeom t = chord_decode(e, P.g);
     const unsigned s_row0 = (unsigned)__cvta_generic_to_shared(&stage[wib][4]);
-    const unsigned s_own = s_row0 + 16u * (t.live ? lane : 0u);
-    chord_issue_loads(P, t, lane, s_own);
+    const unsigned s_own = s_row0 + 16u * lane;
+    const unsigned s_edge = (unsigned)__cvta_generic_to_shared(&edge[wib][0][lane]);
+    chord_issue_loads(P, t, s_own, s_edge);
     ChordAux a{};
-    chord_load_aux<FORCED, DRIVE>(P, t, e, lane, a);
+    chord_load_aux<FORCED, DRIVE>(P, t, tl, lane, a);
     float F[3][4], ph[4];
     chord_force<FORCED, DRIVE>(P, t, a, F, ph);
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
-    chord_compute_store<FORCED, LES, POROUS, DRIVE, COLLIDE>(P, t, e, a, F, ph, lane, s_own, s_row0,
+    chord_compute_store<FORCED, LES, POROUS, DRIVE, COLLIDE>(P, t, tl, a, F, ph, lane, s_own, s_row0, s_edge,
                                                              (unsigned)__cvta_generic_to_shared(&park[wib][0][2 * lane]));
 }
 

@@ -103,9 +103,8 @@ static StepKernel tuned() {
         // 128-thread CTAs with plain (not lane-mask predicated) loads
         // VEC = 4 (chord kernel): BLOCK = 128 -> 4 CTAs of 128 threads (16 warps, 128 registers); the code 256 selects
         // 64-thread CTAs at 6 per SM (12 warps, 168 registers, no spills)
-        // VEC = 4 (chord kernel, default 64-thread CTAs, 8 per SM): block code 128 -> 9 CTAs per SM (112 registers), 256 -> 128-thread
-        // CTAs, 4 per SM
-        if constexpr (VEC == 4 && BLOCK == 256) return phys_chord_kernel<true, true, true, false, 128, true, 4>;
+        // VEC = 4 (chord kernel, default 64-thread CTAs, 8 per SM): block code 128 -> 9 CTAs per SM (112 registers)
+        if constexpr (VEC == 4 && BLOCK == 256) return nullptr;
         else if constexpr (VEC == 4) return phys_chord_kernel<true, true, true, false, 64, true, 9>;
         else return phys_walls_kernel<true, true, true, VEC, BLOCK, true, min_blocks_phys_walls<VEC, BLOCK>()>;
     } else return nullptr;
@@ -138,7 +137,7 @@ StepKernel LBM_LOOKUP(int forced, int les, int porous, int vec, int collide, int
     const int def_block = vec == 1 ? default_block<MAIN, 1>() : (vec == 2 ? default_block<MAIN, 2>() : default_block<MAIN, 4>());
     if (collide && forced == 1 && les && porous && *block && *block != def_block) {
         k = pick_tuned(vec, *block);
-        if (k) { if (*block == 65 || *block == 66) *block = 64; if (vec == 4) *block = (*block == 256 ? 128 : 64); return k; }
+        if (k) { if (*block == 65 || *block == 66) *block = 64; if (vec == 4) *block = 64; return k; }
     }
     if (collide) {
         if (vec == 4) k = pick_feat<MAIN, 4, true>(forced, les, porous);

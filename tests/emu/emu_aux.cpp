@@ -134,32 +134,39 @@ int emu_bounce_slots(int nx, int ny, int nz, int periodic, float *g, const uint8
     run_stride([&] { bounce_slots_kernel(G, g, flags, nbr, 0, nz); });
     return 0;
 }
-// chord-fitted tiles + wall links of the four-cell walls kernel (build_chord_lists without cub: the two exclusive sums run
-// here on the host).  Returns the number of tiles; tiles = [n][4] u32, links_out holds up to max_links entries.
-int emu_chord_lists(int nx, int ny, int nz, int periodic, const uint8_t *flags, const unsigned long long *nbr, unsigned *tiles_out, int max_tiles,
-                    unsigned *links_out, int max_links, int *n_links_out) {
+// packed quad list + wall links of the four-cell walls kernel (build_chord_lists without cub: the exclusive sums and the
+// per-plane padding run here on the host).  Returns the number of tiles; quads_out = 32 u64 per tile, tile_links_out = 2 u32 per
+// tile, links_out up to max_links u64, tile_off_out = nz + 1 ints.
+int emu_chord_lists(int nx, int ny, int nz, int periodic, const uint8_t *flags, const unsigned long long *nbr, unsigned long long *quads_out,
+                    int max_tiles, unsigned *tile_links_out, unsigned long long *links_out, int max_links, int *n_links_out, int *tile_off_out) {
     const Grid G = make_grid(nx, ny, nz, periodic);
     const int rows = nz * ny;
-    std::vector<int> cnt(rows + 1, 0), off(rows + 1, 0);
-    run(dim3((rows + 127) / 128, 1, 1), 128, [&] { chord_count_kernel(G, flags, cnt.data()); });
+    std::vector<int> cnt(rows + 1, 0), off(rows + 1, 0), plane_base(nz + 1, 0);
+    run(dim3((rows + 127) / 128, 1, 1), 128, [&] { quad_count_kernel(G, flags, cnt.data()); });
     for (int r = 0; r < rows; ++r) off[r + 1] = off[r] + cnt[r];
-    const int n_t = off[rows];
+    tile_off_out[0] = 0;
+    for (int z = 0; z < nz; ++z) {
+        const int nq = off[(z + 1) * ny] - off[z * ny];
+        tile_off_out[z + 1] = tile_off_out[z] + (nq + 31) / 32;
+        plane_base[z + 1] = tile_off_out[z + 1] * 32;
+    }
+    const int n_t = tile_off_out[nz];
     if (n_t > max_tiles) return -1;
-    std::vector<uint4> tiles(n_t > 0 ? n_t : 1);
-    std::vector<int> tl(n_t + 1, 0), lo(n_t + 1, 0);
-    run(dim3((rows + 127) / 128, 1, 1), 128, [&] { chord_fill_kernel(G, flags, nbr, off.data(), tiles.data(), tl.data()); });
-    for (int t = 0; t < n_t; ++t) lo[t + 1] = lo[t] + tl[t];
+    for (long long i = 0; i < (long long)n_t * 32; ++i) quads_out[i] = 0;
+    run(dim3((rows + 127) / 128, 1, 1), 128, [&] { quad_fill_kernel(G, flags, off.data(), plane_base.data(), quads_out); });
+    std::vector<int> tc(n_t + 1, 0), lo(n_t + 1, 0);
+    run(dim3((n_t + 127) / 128, 1, 1), 128, [&] { quad_links_kernel(G, flags, nbr, quads_out, n_t, 0, tc.data(), nullptr, nullptr, nullptr); });
+    for (int t = 0; t < n_t; ++t) lo[t + 1] = lo[t] + tc[t];
     if (lo[n_t] > max_links) return -2;
-    run(dim3((n_t + 127) / 128, 1, 1), 128, [&] { chord_links_kernel(G, flags, nbr, tiles.data(), lo.data(), n_t, links_out); });
-    for (int t = 0; t < n_t; ++t) { tiles_out[4 * t] = tiles[t].x; tiles_out[4 * t + 1] = tiles[t].y; tiles_out[4 * t + 2] = tiles[t].z; tiles_out[4 * t + 3] = tiles[t].w; }
+    run(dim3((n_t + 127) / 128, 1, 1), 128, [&] { quad_links_kernel(G, flags, nbr, quads_out, n_t, 1, nullptr, lo.data(), reinterpret_cast<uint2 *>(tile_links_out), links_out); });
     *n_links_out = lo[n_t];
     return n_t;
 }
-// pressure-gradient producer over the chord-fitted tiles
+// pressure-gradient producer over the packed quad list
 int emu_pressure_gradient_chord(int nx, int ny, int nz, const float *rho, const uint8_t *flags, float *bf, float max_force, float scale, int accumulate,
-                                const unsigned *tiles, int n_tiles) {
+                                const unsigned long long *quads, int n_tiles) {
     const Grid G = make_grid(nx, ny, nz);
-    run(dim3((n_tiles + 3) / 4, 1, 1), 128, [&] { pressure_gradient_chord_kernel(G, rho, flags, bf, max_force, scale, accumulate, reinterpret_cast<const uint4 *>(tiles), n_tiles); });
+    run(dim3((n_tiles + 3) / 4, 1, 1), 128, [&] { pressure_gradient_chord_kernel(G, rho, flags, bf, max_force, scale, accumulate, quads, n_tiles); });
     return 0;
 }
 int emu_add_reaction(int nx, int ny, int nz, const float *reaction, const uint8_t *flags, float *bf) {

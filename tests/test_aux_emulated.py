@@ -247,7 +247,7 @@ def test_emulated_physical_walls_kernel_obstacles_on_open_and_periodic_faces(aux
     _walls_case(aux, walls, (nx, ny, nz), periodic, solid, zone, les_mask, None, None, rho0, u0, steps, p)
 
 
-# ---- chord-fitted tiles + wall links of the four-cell walls kernel (csrc/lbm_phys_chord.cuh) ---------------------------------------
+# ---- packed quad list + wall links of the four-cell walls kernel (csrc/lbm_phys_chord.cuh) ----------------------------------------
 _CX = [0, 1, -1, 0, 0, 0, 0, 1, -1, 1, -1, 1, -1, 1, -1, 0, 0, 0, 0]
 _CY = [0, 0, 0, 1, -1, 0, 0, 1, 1, -1, -1, 0, 0, 0, 0, 1, -1, 1, -1]
 _CZ = [0, 0, 0, 0, 0, 1, -1, 0, 0, 0, 0, 1, 1, -1, -1, 1, 1, -1, -1]
@@ -258,19 +258,21 @@ def _chord_lists(aux, solid_zyx, periodic):
     nz, ny, nx = solid_zyx.shape
     flags = np.zeros_like(solid_zyx); nbr = np.zeros(solid_zyx.shape, np.uint64)
     aux.emu_pack_flags_and_masks(C.c_int(nx), C.c_int(ny), C.c_int(nz), C.c_int(periodic), _p(flags), _p(np.ascontiguousarray(solid_zyx)), None, None, _p(nbr))
-    max_t, max_l = nz * ny * (nx // 4 + 1), 18 * solid_zyx.size
-    tiles = np.zeros((max_t, 4), np.uint32); links = np.zeros(max_l, np.uint32); nl = C.c_int(0)
-    nt = aux.emu_chord_lists(C.c_int(nx), C.c_int(ny), C.c_int(nz), C.c_int(periodic), _p(flags), _p(nbr), _p(tiles), C.c_int(max_t), _p(links),
-                             C.c_int(max_l), C.byref(nl))
+    max_t, max_l = nz * (ny * (nx // 4) // 32 + 2), 18 * solid_zyx.size
+    quads = np.zeros((max_t, 32), np.uint64); tl = np.zeros((max_t, 2), np.uint32); links = np.zeros(max_l, np.uint64); nl = C.c_int(0)
+    tile_off = np.zeros(nz + 1, np.int32)
+    nt = aux.emu_chord_lists(C.c_int(nx), C.c_int(ny), C.c_int(nz), C.c_int(periodic), _p(flags), _p(nbr), _p(quads), C.c_int(max_t), _p(tl), _p(links),
+                             C.c_int(max_l), C.byref(nl), _p(tile_off))
     assert nt >= 0
-    return flags, nbr, tiles[:nt], links[:nl.value]
+    return flags, nbr, quads[:nt], tl[:nt], links[:nl.value], tile_off
 
 
 @pytest.mark.parametrize("case", ["v60_64", "random_40x12x9", "random_periodic_24x10x8", "two_chords_136x6x5"])
-def test_emulated_chord_tiles_cover_the_fluid_quads_once_and_links_are_the_wall_links(aux, case):
-    """build_chord_lists (lbm_aux.cu): every quad holding a fluid cell belongs to exactly one (tile, lane); tiles start at an active
-    quad, are sorted in memory order and never cross a row; the links of a tile are exactly the (fluid cell, q) pairs whose
-    target x + e_q is a solid cell inside the box, with the target coordinates and opp(q) packed as the kernel expects."""
+def test_emulated_quad_list_holds_every_active_quad_once_and_links_are_the_wall_links(aux, case):
+    """build_chord_lists (lbm_aux.cu): the list is every quad holding a fluid cell, once, in memory order, 32 per tile, only the last
+    tile of a plane padded with dead lanes; the adjacency bits say exactly when the neighbouring lane of the same tile holds the
+    neighbouring quad of the same row; the links of a tile are exactly the (fluid cell, q) pairs of its lanes whose target x + e_q is
+    a solid cell inside the box, with the target's linear index and opp(q) packed as the kernel expects."""
     rng = np.random.default_rng(5)
     periodic = 0
     if case == "v60_64":
@@ -282,34 +284,43 @@ def test_emulated_chord_tiles_cover_the_fluid_quads_once_and_links_are_the_wall_
     else:      # a row longer than one tile with a solid gap wider than a tile between two chords
         solid = np.ones((5, 6, 136 * 2), np.uint8); solid[:, :, 3:50] = 0; solid[:, :, 200:269] = 0; solid[2, 3, 120] = 0
     nz, ny, nx = solid.shape
-    flags, nbr, tiles, links = _chord_lists(aux, solid, periodic)
+    flags, nbr, quads, tl, links, tile_off = _chord_lists(aux, solid, periodic)
     fluid = solid == 0
     quad_active = fluid.reshape(nz, ny, nx // 4, 4).any(-1)
-    seen = np.zeros_like(quad_active, dtype=np.int32)
-    prev_key = -1
-    want_links = set(); got_links = set()
-    for t in range(len(tiles)):
-        q0 = int(tiles[t, 0] & 0xfff); nl = int(tiles[t, 0] >> 12); y = int(tiles[t, 1] & 0xffff); z = int(tiles[t, 1] >> 16)
-        mask = int(tiles[t, 2]); lb = int(tiles[t, 3])
-        assert mask & 1 and quad_active[z, y, q0]
-        key = (z * ny + y) * (nx // 4) + q0
-        assert key > prev_key; prev_key = key
+    LIVE, LEFT, RIGHT = 1 << 44, 1 << 45, 1 << 46
+    listed = []
+    got_links = set()
+    for t in range(len(quads)):
+        z_tile = int(np.searchsorted(tile_off, t, side="right") - 1)
         for l in range(32):
-            if (mask >> l) & 1:
-                assert q0 + l < nx // 4 and quad_active[z, y, q0 + l]
-                seen[z, y, q0 + l] += 1
-            elif q0 + l < nx // 4:
-                assert not quad_active[z, y, q0 + l]
-        for L in links[lb:lb + nl]:
+            e = int(quads[t, l])
+            if not e & LIVE:
+                assert e == 0 and t == tile_off[z_tile + 1] - 1          # padding only at the end of a plane's last tile
+                assert all(int(quads[t, m]) == 0 for m in range(l, 32))
+                break
+            q0, y, z = e & 0xfff, (e >> 12) & 0xffff, (e >> 28) & 0xffff
+            assert z == z_tile and quad_active[z, y, q0]
+            listed.append((z, y, q0))
+            prev = int(quads[t, l - 1]) if l > 0 else 0
+            nxt = int(quads[t, l + 1]) if l < 31 else 0
+            same_row = lambda o: bool(o & LIVE) and ((o >> 12) & 0xffff, (o >> 28) & 0xffff) == (y, z)
+            assert bool(e & LEFT) == (same_row(prev) and (prev & 0xfff) == q0 - 1)
+            assert bool(e & RIGHT) == (same_row(nxt) and (nxt & 0xfff) == q0 + 1)
+        lb, n = int(tl[t, 0]), int(tl[t, 1])
+        for L in links[lb:lb + n]:
             L = int(L)
-            l, c, q, qd, dy, dz, xt = L & 31, (L >> 5) & 3, (L >> 7) & 31, (L >> 12) & 31, ((L >> 17) & 3) - 1, ((L >> 19) & 3) - 1, L >> 21
-            assert (mask >> l) & 1
-            x = 4 * (q0 + l) + c
-            assert qd == _OPP[q] and dy == _CY[q] and dz == _CZ[q]
-            assert xt == (x + _CX[q]) % nx
+            target, l, c, q, qd = L & 0xffffffff, (L >> 32) & 31, (L >> 37) & 3, (L >> 39) & 31, (L >> 44) & 31
+            e = int(quads[t, l])
+            assert e & LIVE and qd == _OPP[q]
+            q0, y, z = e & 0xfff, (e >> 12) & 0xffff, (e >> 28) & 0xffff
+            x = 4 * q0 + c
+            assert target == (((z + _CZ[q]) % nz) * ny + (y + _CY[q]) % ny) * nx + (x + _CX[q]) % nx
             got_links.add((z, y, x, q))
-    assert np.array_equal(seen, quad_active.astype(np.int32))
+    want = [(int(z), int(y), int(q)) for z, y, q in zip(*np.nonzero(quad_active))]
+    assert listed == want                                                 # every active quad once, in memory order
+    assert tile_off[-1] == len(quads) and all(tile_off[z + 1] - tile_off[z] == -(-int(quad_active[z].sum()) // 32) for z in range(nz))
     per = [(periodic >> d) & 1 for d in range(3)]
+    want_links = set()
     for z, y, x in zip(*np.nonzero(fluid)):
         for q in range(1, 19):
             xt, yt, zt = x + _CX[q], y + _CY[q], z + _CZ[q]
@@ -320,15 +331,15 @@ def test_emulated_chord_tiles_cover_the_fluid_quads_once_and_links_are_the_wall_
     assert got_links == want_links and len(links) == len(want_links)
 
 
-def test_emulated_chord_tile_pressure_gradient_equals_the_grid_kernel(aux):
-    """pressure_gradient_chord_kernel (the producer over the four-cell kernel's tiles) against the recorded drive run."""
+def test_emulated_quad_list_pressure_gradient_equals_the_grid_kernel(aux):
+    """pressure_gradient_chord_kernel (the producer over the four-cell kernel's quad list) against the recorded drive run."""
     z = np.load(os.path.join(GOLD, "reference_run_neighbours.npz"))
     n = int(z["n"])
     solid = np.ascontiguousarray(H.to_dev_scalar(z["solid"]).astype(np.uint8))
-    flags, nbr, tiles, links = _chord_lists(aux, solid, 0)
+    flags, nbr, quads, tl, links, tile_off = _chord_lists(aux, solid, 0)
     rho, u = H.to_dev_scalar(z["rho"]), H.to_dev_vec(z["u"])
     for scale, key in ((1.0, "bf_force_drive"), (0.5, "bf_mixed_drive")):
         bf = np.zeros_like(u)
-        aux.emu_pressure_gradient_chord(*_dims(n), _p(rho), _p(flags), _p(bf), C.c_float(0.12), C.c_float(scale), C.c_int(1), _p(np.ascontiguousarray(tiles)),
-                                        C.c_int(len(tiles)))
+        aux.emu_pressure_gradient_chord(*_dims(n), _p(rho), _p(flags), _p(bf), C.c_float(0.12), C.c_float(scale), C.c_int(1), _p(np.ascontiguousarray(quads)),
+                                        C.c_int(len(quads)))
         assert np.array_equal(np.transpose(bf, (3, 2, 1, 0)), z[key])
