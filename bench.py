@@ -607,7 +607,7 @@ def run_multi(args, world, rank, local):
 
     def coupled(k):
         for _ in range(k):
-            particles_couple_slab(eng, ps, eng.body_force, relax=0.8, sparse_clear=True, sync="state")
+            particles_couple_slab(eng, ps, eng.body_force, relax=0.8, sparse_clear=True, interface_guard=True)
             eng.step(1, write_macro_every=1)
     l0 = eng.launch_count()
     head = timer.measure(coupled, args.steps, args.warmup)

@@ -60,7 +60,7 @@ def run_case(name, rank, world, local, nx, nzg, steps, make_engine, setup):
     return bool(flag.item())
 
 
-def run_particles(rank, world, local, nx, nzg, make_engine, setup, cfg, n_part=20000, steps=6):
+def run_particles(rank, world, local, nx, nzg, make_engine, setup, cfg, n_part=20000, steps=6, guard=False, z_hi=None):
     """Two-way coupling on slabs (replicated particles, owner computes, engine.particles_couple_slab over NCCL) against the single-GPU
     coupling: base-cell indices, fluid velocity at the particle and Reynolds number bit for bit; drag within 1e-6 (powf); the reaction
     field and the flow after `steps` coupled steps within 1e-5 of the field scale (a GPU's scatter atomics are unordered)."""
@@ -69,7 +69,8 @@ def run_particles(rank, world, local, nx, nzg, make_engine, setup, cfg, n_part=2
     def particles(dev):
         rng = np.random.default_rng(11)
         ps = ParticleState(n_part, dev)
-        pos = np.stack([rng.uniform(0.3 * nx, 0.7 * nx, n_part), rng.uniform(0.3 * nx, 0.7 * nx, n_part), rng.uniform(4.0, nzg - 4.0, n_part)])
+        pos = np.stack([rng.uniform(0.3 * nx, 0.7 * nx, n_part), rng.uniform(0.3 * nx, 0.7 * nx, n_part),
+                        rng.uniform(4.0, (nzg - 4.0) if z_hi is None else z_hi, n_part)])
         ps.pos.copy_(torch.from_numpy(pos.astype(np.float32)))
         ps.vel.copy_(torch.from_numpy((1e-3 * rng.standard_normal((3, n_part))).astype(np.float32)))
         rad = np.clip(rng.normal(3.25e-4, 1e-4, n_part), 1.6e-4, 4.9e-4).astype(np.float32)
@@ -87,7 +88,7 @@ def run_particles(rank, world, local, nx, nzg, make_engine, setup, cfg, n_part=2
     eng.body_force.zero_()          # sparse clear: the reaction target starts at zero and only the coupling writes it
     eng.step(3)
     for _ in range(steps):
-        particles_couple_slab(eng, ps, eng.body_force, relax=0.8, sparse_clear=True)
+        particles_couple_slab(eng, ps, eng.body_force, relax=0.8, sparse_clear=True, interface_guard=guard)
         eng.step(1)
     torch.cuda.synchronize()
     mine = (eng.rho[1:-1].cpu(), eng.u[:, 1:-1].cpu(), eng.body_force[:, 1:-1].cpu())
@@ -117,7 +118,7 @@ def run_particles(rank, world, local, nx, nzg, make_engine, setup, cfg, n_part=2
         e_rho = close(rho[fluid], ref.rho.cpu()[fluid], 1e-5)
         e_u = close(u[:, fluid], ref.u.cpu()[:, fluid], 1e-5)
         ok = e_cell and e_uf and e_drag and e_react and e_rho and e_u
-        print(f"[check_slabs] particles on slabs: world={world} particles={n_part} coupled steps={steps} cell indices (bit-exact)={e_cell} u_fluid={e_uf} "
+        print(f"[check_slabs] particles on slabs{' (interface guard, bed below the first cut)' if guard else ''}: world={world} particles={n_part} coupled steps={steps} cell indices (bit-exact)={e_cell} u_fluid={e_uf} "
               f"drag={e_drag} reaction field={e_react} rho={e_rho} u={e_u}", flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
@@ -168,6 +169,8 @@ def main():
     # the pressure-gradient drive fused into the step kernel reads rho across the interface (rho planes travel with the halo)
     ok &= run_case("V60 physical + fused pressure-gradient drive", rank, world, local, nx, nzg, 25, lambda **k: mk2(drive=True, **k), setup2)
     ok &= run_particles(rank, world, local, nx, nzg, mk2, setup2, cfg)
+    # a bed that stays planes away from every interface: the guarded calls skip the exchanges and must give the same answer
+    ok &= run_particles(rank, world, local, nx, nzg, mk2, setup2, cfg, guard=True, z_hi=0.3 * (nzg / world), steps=8)
 
     # ---- legacy solver (reference): FD-LES reads u across the interface ----------------------------------
     ok &= run_case("V60 compat=reference (water phase, FD-LES active)", rank, world, local, nx, nzg, 10,
