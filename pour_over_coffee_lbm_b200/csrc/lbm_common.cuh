@@ -76,6 +76,24 @@ __device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, fl
 __device__ __forceinline__ float pressure_gradient_diff(float r0, float lo, float hi, int pos) {
     return pos == 0 ? (hi - lo) * 0.5f : (pos < 0 ? hi - r0 : r0 - lo);
 }
+// Out of line on purpose: four inlined copies per thread (three IEEE divisions, a square root and their slow paths each) grew the
+// fused-drive step kernel past the instruction cache -- ncu: 1.5 of 14.4 stall cycles per issue on instruction fetch.
+#ifdef __CUDACC__
+#define LBM_NOINLINE __noinline__
+#else
+#define LBM_NOINLINE
+#endif
+static __device__ LBM_NOINLINE float3 pressure_gradient_force(float r0, float gx, float gy, float gz, float max_force, float scale) {
+    const float cs2 = (float)(1.0 / 3.0);
+    float fx = 0.0f, fy = 0.0f, fz = 0.0f;
+    if (r0 > 1e-12f) {
+        fx = -(gx * cs2) / r0; fy = -(gy * cs2) / r0; fz = -(gz * cs2) / r0;
+        const float mag = sqrtf(dot3(fx, fy, fz, fx, fy, fz));
+        if (mag > max_force) { const float s = max_force / mag; fx = fx * s; fy = fy * s; fz = fz * s; }
+    }
+    if (scale != 1.0f) { fx = scale * fx; fy = scale * fy; fz = scale * fz; }
+    return make_float3(fx, fy, fz);
+}
 __device__ __forceinline__ void pressure_gradient_value(float r0, float gx, float gy, float gz, float max_force, float scale,
                                                         float &fx, float &fy, float &fz) {
     const float cs2 = (float)(1.0 / 3.0);

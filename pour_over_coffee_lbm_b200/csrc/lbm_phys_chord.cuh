@@ -174,7 +174,8 @@ __device__ __forceinline__ void chord_force(const StepArgs &P, const ChordGeom &
             const float gx = pressure_gradient_diff(r0[c], lo[c], hi[c], x == 0 ? -1 : (x == G.nx - 1 ? 1 : 0));
             const float gy = pressure_gradient_diff(r0[c], ym[c], yq[c], ypos);
             const float gz = pressure_gradient_diff(r0[c], zm[c], zq[c], zpos);
-            pressure_gradient_value(r0[c], gx, gy, gz, P.drive_max_force, P.drive_scale, F[0][c], F[1][c], F[2][c]);
+            const float3 f = pressure_gradient_force(r0[c], gx, gy, gz, P.drive_max_force, P.drive_scale);
+            F[0][c] = f.x; F[1][c] = f.y; F[2][c] = f.z;
         }
     }
     if constexpr (FORCED) {
