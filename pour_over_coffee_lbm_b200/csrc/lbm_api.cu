@@ -21,7 +21,8 @@ cudaError_t launch_init_equilibrium(const Grid &, int, float *, const float *, c
 cudaError_t launch_v60_geometry(const Grid &, uint8_t *, int32_t *, const float[5], cudaStream_t);
 cudaError_t launch_pack_flags(const Grid &, uint8_t *, const uint8_t *, const int32_t *, const int32_t *, cudaStream_t);
 cudaError_t build_work_lists(const Grid &, const uint8_t *, int, int, unsigned **, unsigned **, std::vector<int> &, unsigned long long **, cudaStream_t);
-cudaError_t build_chord_lists(const Grid &, const uint8_t *, unsigned long long **, uint2 **, unsigned long long **, std::vector<int> &, unsigned long long **, long long *,
+cudaError_t launch_wall_values(const Grid &, const float *, const unsigned long long *, const uint2 *, const unsigned *, float *, int, cudaStream_t);
+cudaError_t build_chord_lists(const Grid &, const uint8_t *, unsigned long long **, uint2 **, unsigned **, float **, std::vector<int> &, unsigned long long **, long long *,
                               cudaStream_t);
 cudaError_t launch_convert_f(const Grid &, bool, const float *, const uint8_t *, float *, cudaStream_t);
 cudaError_t launch_face_bc(const Grid &, float *, const uint8_t *, cudaStream_t, int *);
@@ -111,7 +112,9 @@ struct lbm_ctx {
     unsigned *d_tile_mask = nullptr;           // per warp-tile: lanes that must load (unused by the current kernels)
     unsigned long long *d_ctiles = nullptr;    // vec = 4: packed quad list (lbm_phys_chord.cuh), one u64 per lane slot ...
     uint2 *d_tile_links = nullptr;             // ... per tile: first wall link, number of links ...
-    unsigned long long *d_links = nullptr;     // ... and the wall links
+    unsigned *d_links = nullptr;               // ... the wall links ...
+    float *d_wall = nullptr;                   // ... and the value waiting on each link (halfway bounce-back, lbm_aux.cu)
+    const float *wall_valid = nullptr;         // population buffer d_wall belongs to (nullptr: rebuild from the populations)
     long long n_links = 0;
     cudaStream_t window_stream = nullptr; bool window_set = false;
     unsigned long long *d_nbr = nullptr;       // neighbour masks [vol]
@@ -219,14 +222,15 @@ static bool chord_lists(const lbm_ctx *ctx, int vec) { return phys_walls(ctx->p)
 
 static int rebuild_lists(lbm_ctx *ctx, const uint8_t *flags, int vec, int ty, int block, cudaStream_t s) {
     if (chord_lists(ctx, vec) && ty == 1) {
-        CUDA_OK(ctx, build_chord_lists(ctx->g, flags, &ctx->d_ctiles, &ctx->d_tile_links, &ctx->d_links, ctx->tile_off, &ctx->d_nbr, &ctx->n_links, s));
+        CUDA_OK(ctx, build_chord_lists(ctx->g, flags, &ctx->d_ctiles, &ctx->d_tile_links, &ctx->d_links, &ctx->d_wall, ctx->tile_off, &ctx->d_nbr, &ctx->n_links, s));
+        ctx->wall_valid = nullptr;
         ctx->launches += 6;
     } else {
         CUDA_OK(ctx, build_work_lists(ctx->g, flags, vec, ty, &ctx->d_tiles, &ctx->d_tile_mask, ctx->tile_off, &ctx->d_nbr, s));
         ctx->launches += 6;
     }
     ctx->list_flags = flags; ctx->list_vec = vec; ctx->list_ty = ty; ctx->list_block = block; ctx->window_set = false;
-    ctx->slots_valid = nullptr;
+    ctx->slots_valid = nullptr; ctx->wall_valid = nullptr;
     return 0;
 }
 
@@ -324,7 +328,7 @@ int lbm_set_params(lbm_ctx *ctx, const lbm_params *p) {
     }
     if (p->vec != ctx->p.vec || p->periodic != ctx->p.periodic || p->compat != ctx->p.compat || p->features != ctx->p.features) ctx->list_flags = nullptr;
     ctx->maps.clear();
-    if (p->compat != ctx->p.compat || p->periodic != ctx->p.periodic || p->features != ctx->p.features) ctx->slots_valid = nullptr;
+    if (p->compat != ctx->p.compat || p->periodic != ctx->p.periodic || p->features != ctx->p.features) { ctx->slots_valid = nullptr; ctx->wall_valid = nullptr; }
     ctx->g = g; ctx->p = *p;
     return 0;
 }
@@ -338,6 +342,7 @@ void lbm_destroy(lbm_ctx *ctx) {
     if (ctx->d_tile_mask) cudaFree(ctx->d_tile_mask);
     if (ctx->d_ctiles) cudaFree(ctx->d_ctiles);
     if (ctx->d_links) cudaFree(ctx->d_links);
+    if (ctx->d_wall) cudaFree(ctx->d_wall);
     if (ctx->d_tile_links) cudaFree(ctx->d_tile_links);
     if (ctx->d_stat_scratch) cudaFree(ctx->d_stat_scratch);
     if (ctx->d_nbr) cudaFree(ctx->d_nbr);
@@ -361,7 +366,7 @@ int lbm_selftest_math(lbm_ctx *ctx, unsigned long long mismatches[7], void *stre
 
 int lbm_populations_changed(lbm_ctx *ctx) {
     if (!ctx) return fail(ctx, "null argument");
-    ctx->slots_valid = nullptr;
+    ctx->slots_valid = nullptr; ctx->wall_valid = nullptr;
     return 0;
 }
 
@@ -371,7 +376,7 @@ int lbm_init_equilibrium(lbm_ctx *ctx, float *g, const float *rho, const float *
     const float z[3] = {0, 0, 0};
     CUDA_OK(ctx, launch_init_equilibrium(ctx->g, ctx->p.compat, g, rho, u, rho0, u0 ? u0 : z, (cudaStream_t)stream));
     ctx->launches++;
-    ctx->slots_valid = nullptr;
+    ctx->slots_valid = nullptr; ctx->wall_valid = nullptr;
     return 0;
 }
 
@@ -445,6 +450,7 @@ struct Launcher {
     int block = 0, vec = 1;
     bool walls = false;
     bool tma = false;          // TMA-staged persistent kernel (compat = physical behind walls)
+    bool quads = false;        // four-cell kernel on the packed quad list: bounce-back through the per-link buffer, not through slots
     TmaKernelInfo tk{};
 };
 
@@ -463,6 +469,7 @@ static int make_launcher(lbm_ctx *ctx, const lbm_params &p, const lbm_fields *f,
     } else {
         L->main = lookup(p, vec, collide, &L->block);      // may fall back to the default CTA size for this variant
         if (!L->main) return fail(ctx, "no step kernel built for this feature combination");
+        L->quads = chord_lists(ctx, vec);
         if (chord_lists(ctx, vec))      // the chord kernels live on shared memory: take the largest carve-out
             cudaFuncSetAttribute((const void *)L->main, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     }
@@ -487,7 +494,7 @@ static int launch_planes(lbm_ctx *ctx, StepArgs &a, const Launcher &L, int z_beg
         const int t1 = both ? n_t + (ctx->tile_off[1] - ctx->tile_off[0]) + (ctx->tile_off[nz] - ctx->tile_off[nz - 1]) : ctx->tile_off[z_end];
         if (t1 <= t0) return 0;
         a.items = ctx->d_tiles; a.item_mask = ctx->d_tile_mask; a.item_begin = t0; a.n_items = t1 - t0; a.nbr = ctx->d_nbr;
-        a.quads = ctx->d_ctiles; a.tile_links = ctx->d_tile_links; a.links = ctx->d_links;
+        a.quads = ctx->d_ctiles; a.tile_links = ctx->d_tile_links; a.links = ctx->d_links; a.wall = ctx->d_wall;
         if (L.tma) {
             const TmaMaps *maps = nullptr;
             if (tensor_maps(ctx, a, L.tk.ty, &maps)) return 1;
@@ -584,6 +591,14 @@ static int ensure_slots(lbm_ctx *ctx, float *g, const uint8_t *flags, cudaStream
     ctx->slots_valid = g;
     return 0;
 }
+// four-cell kernel: the value waiting on every wall link (lbm_aux.cu) belongs to `g` (no-op when the step kernel left it there)
+static int ensure_wall(lbm_ctx *ctx, const float *g, cudaStream_t s) {
+    if (ctx->wall_valid == g) return 0;
+    CUDA_OK(ctx, launch_wall_values(ctx->g, g, ctx->d_ctiles, ctx->d_tile_links, ctx->d_links, ctx->d_wall, ctx->tile_off[ctx->g.nz], s));
+    ctx->launches++;
+    ctx->wall_valid = g;
+    return 0;
+}
 // after a halo exchange the incoming ghost planes have overwritten the slots that live in them
 static int refresh_boundary_slots(lbm_ctx *ctx, float *g, const uint8_t *flags, cudaStream_t s) {
     if (!phys_walls(ctx->p) || !ctx->g.zg) return 0;
@@ -616,7 +631,7 @@ int lbm_step(lbm_ctx *ctx, lbm_fields *f, int nsteps, int write_macro_every, voi
     cudaStream_t cs = (cudaStream_t)compute_stream, ms = (cudaStream_t)comm_stream;
     const bool slabs = ctx->g.zg == 1;
     const bool overlap = slabs && ctx->nranks > 1 && ms != nullptr && ms != cs && ctx->g.nz >= 3;
-    if (L.walls && nsteps > 0 && ensure_slots(ctx, f->f_src, f->flags, cs)) return 1;
+    if (L.walls && nsteps > 0 && (L.quads ? ensure_wall(ctx, f->f_src, cs) : ensure_slots(ctx, f->f_src, f->flags, cs))) return 1;
     for (int s = 0; s < nsteps; ++s) {
         StepArgs a;
         if (fill_args(ctx, f, &a)) return 1;
@@ -639,8 +654,11 @@ int lbm_step(lbm_ctx *ctx, lbm_fields *f, int nsteps, int write_macro_every, voi
             if (launch_planes(ctx, a, L, 0, ctx->g.nz, cs)) return 1;
             if (slabs && exchange(ctx, f->f_dst, (ref_les && a.write_macro) ? f->u_dst : nullptr, drive ? f->rho : nullptr, cs)) return 1;
         }
-        if (slabs && L.walls && refresh_boundary_slots(ctx, f->f_dst, f->flags, cs)) return 1;
-        if (phys_walls(p)) ctx->slots_valid = f->f_dst;
+        if (L.quads) { ctx->wall_valid = f->f_dst; ctx->slots_valid = nullptr; }      // the four-cell kernel does not keep slots
+        else {
+            if (slabs && L.walls && refresh_boundary_slots(ctx, f->f_dst, f->flags, cs)) return 1;
+            if (phys_walls(p)) { ctx->slots_valid = f->f_dst; ctx->wall_valid = nullptr; }
+        }
         float *t = f->f_src; f->f_src = f->f_dst; f->f_dst = t;
         if (a.write_macro && f->u_src && f->u_src != f->u_dst) { t = f->u_src; f->u_src = f->u_dst; f->u_dst = t; }
         if (drive) { t = f->rho; f->rho = f->rho_src; f->rho_src = t; }      // rho_src = the density this step wrote
@@ -666,7 +684,7 @@ int lbm_macroscopic(lbm_ctx *ctx, const lbm_fields *f, void *stream) {
     StepArgs a;
     if (fill_args(ctx, f, &a)) return 1;
     if (!f->rho || !f->u_dst) return fail(ctx, "rho/u_dst is NULL");
-    if (walls && ensure_slots(ctx, f->f_src, f->flags, (cudaStream_t)stream)) return 1;
+    if (walls && (L.quads ? ensure_wall(ctx, f->f_src, (cudaStream_t)stream) : ensure_slots(ctx, f->f_src, f->flags, (cudaStream_t)stream))) return 1;
     a.write_macro = 1;
     int rc = launch_planes(ctx, a, L, 0, ctx->g.nz, (cudaStream_t)stream);
     if (relist) {      // restore the lists of the step kernel
@@ -699,7 +717,7 @@ int lbm_import_f(lbm_ctx *ctx, const float *f_in, const uint8_t *flags, float *g
     cudaSetDevice(ctx->device);      // launches follow the context's device, whatever the caller's current device is
     CUDA_OK(ctx, launch_convert_f(ctx->g, false, f_in, flags, g, (cudaStream_t)stream));
     ctx->launches++;
-    ctx->slots_valid = nullptr;
+    ctx->slots_valid = nullptr; ctx->wall_valid = nullptr;
     return 0;
 }
 
@@ -960,7 +978,7 @@ int lbm_attach_nccl(lbm_ctx *ctx, const void *unique_id128, int rank, int nranks
 int lbm_halo_exchange(lbm_ctx *ctx, float *g, float *vec3_or_null, void *stream) {
     if (!ctx || !g) return fail(ctx, "null argument");
     cudaSetDevice(ctx->device);      // launches follow the context's device, whatever the caller's current device is
-    ctx->slots_valid = nullptr;      // the incoming ghost planes overwrite the bounce-back slots that live in them
+    ctx->slots_valid = nullptr; ctx->wall_valid = nullptr;      // the incoming ghost planes overwrite the bounce-back slots that live in them
     return exchange(ctx, g, vec3_or_null, nullptr, (cudaStream_t)stream);
 }
 

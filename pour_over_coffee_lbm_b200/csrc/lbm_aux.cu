@@ -412,24 +412,38 @@ cudaError_t build_work_lists(const Grid &G, const uint8_t *flags, int vec, int t
 #endif
 
 // ---- packed quad list and wall links of the four-cell walls kernel (lbm_phys_chord.cuh) --------------------------
-// A "quad" is 4 x-consecutive cells on a 16-byte boundary; it is active when it holds a fluid cell.  The kernel's work list is
-// the sequence of ALL active quads of a plane in memory order (y, then x), cut into tiles of 32 -- one warp per tile, one lane
-// per quad, tiles run across row ends.  A first version cut tiles per chord (<= 32 quads of ONE row): on the V60 512^3 mask
-// that launched 14.77 M lane slots for 12.05 M active quads (82 % of the lanes alive), and since a warp costs the same
+// A "quad" is 4 x-consecutive cells on a 16-byte boundary.  It is active when it or the other quad of its 32-byte sector holds a
+// fluid cell: the kernel stores whole quads, so both halves of every sector it touches are written and no sector reaches DRAM half
+// filled (a partly written sector costs a 32-byte fill read; at the chord ends of the V60 mask that was 0.37 GB per step).  The
+// kernel's work list is the sequence of ALL active quads of a plane in memory order (y, then x), cut into tiles of 32 -- one warp
+// per tile, one lane per quad, tiles run across row ends.  A first version cut tiles per chord (<= 32 quads of ONE row): on the
+// V60 512^3 mask that launched 14.77 M lane slots for 12.05 M active quads (82 % of the lanes alive), and since a warp costs the same
 // whether 11 or 32 of its lanes work, the step ran at 0.67 of the HBM peak where a periodic box (every lane alive) runs at
 // 0.86 (profiles/r02_exp_structure_cost_periodic_box.log).  Only the last tile of a plane is padded (slab launches address plane
 // ranges).  Per lane slot (u64): bits 0-11 quad index in the row, 12-27 y, 28-43 z, 44 live, 45 / 46 the previous / next lane
 // of the SAME tile holds the quad to the left / right in the same row (else the lane fetches that neighbour itself).
-// Wall link (u64) = one (fluid cell, direction q) pair whose target x + e_q is solid: the post-collision f_q goes to the solid
-// cell's slot of opp(q) (halfway bounce-back on the write side, lbm_phys.cuh): bits 0-31 target cell index in a scalar volume,
-// 32-36 source lane, 37-38 cell of the quad, 39-43 q, 44-48 opp(q).  Per tile (uint2): first link, number of links.
+// Wall link (u32) = one (fluid cell, direction q) pair whose target x + e_q is solid.  Halfway bounce-back hands the cell's
+// post-collision f_q back to the same cell as f_opp(q) one step later, so the value never has to visit the population arrays: it
+// waits in a per-link buffer (`wall`, one float per link, read and written by the tile that owns the link, coalesced).  The link
+// names two WORDS OF THE TILE'S STAGE (lbm_phys_chord.cuh: row r = 160 words: 4 per lane, then one edge word per lane):
+//   bits 0-11  where the waiting value goes before the collision: row opp(q), the word the cell pulls opp(q) from (its solid
+//              neighbour's place: word 4 lane + cell + cx(q), or the lane's edge word when that place lies outside the lane's quad
+//              and the neighbouring lane does not hold the neighbouring quad);
+//   bits 12-23 where the new value is taken from after the collision: row q, word 4 lane + cell.
+// Per tile (uint2): first link, number of links.  A first version stored the value into the solid neighbour's slot of the population
+// array instead (4-byte scattered stores, 8-byte links with the target index) and the fluid cells of chord-end quads one by one:
+// timing the kernel without those two loops showed 0.14 of 1.75 ms in them (profiles/r02_exp_copy_nolinks.log).
 // The kernels below are plain (one thread per row / per tile) so that tests/emu can run them on the CPU; they run once per
 // geometry change.
 #define LBM_QUAD_LIVE (1ull << 44)
 #define LBM_QUAD_LEFT (1ull << 45)
 #define LBM_QUAD_RIGHT (1ull << 46)
-__device__ __forceinline__ bool quad_active(const uint8_t *row, int q) {
+#define LBM_STAGE_ROW_WORDS 160
+__device__ __forceinline__ bool quad_has_fluid(const uint8_t *row, int q) {
     return !((row[4 * q] & row[4 * q + 1] & row[4 * q + 2] & row[4 * q + 3]) & LBM_FLAG_SOLID);
+}
+__device__ __forceinline__ bool quad_active(const uint8_t *row, int q, int nquads) {
+    return quad_has_fluid(row, q) || ((q ^ 1) < nquads && quad_has_fluid(row, q ^ 1));
 }
 __global__ void quad_count_kernel(Grid G, const uint8_t *flags, int *row_quads) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -437,7 +451,7 @@ __global__ void quad_count_kernel(Grid G, const uint8_t *flags, int *row_quads) 
     const int z = r / G.ny, y = r - z * G.ny;
     const uint8_t *row = flags + ((long long)(z + G.zg) * G.ny + y) * G.nx;
     int n = 0;
-    for (int q = 0; q < G.nx / 4; ++q) n += quad_active(row, q) ? 1 : 0;
+    for (int q = 0; q < G.nx / 4; ++q) n += quad_active(row, q, G.nx / 4) ? 1 : 0;
     row_quads[r] = n;
 }
 // row_off: exclusive prefix of row_quads over all rows; plane_base[z]: first lane slot of plane z (a multiple of 32)
@@ -449,17 +463,17 @@ __global__ void quad_fill_kernel(Grid G, const uint8_t *flags, const int *row_of
     int slot = plane_base[z] + (row_off[r] - row_off[z * G.ny]);
     int prev = -2;
     for (int q = 0; q < G.nx / 4; ++q) {
-        if (!quad_active(row, q)) continue;
+        if (!quad_active(row, q, G.nx / 4)) continue;
         unsigned long long e = (unsigned long long)q | ((unsigned long long)y << 12) | ((unsigned long long)z << 28) | LBM_QUAD_LIVE;
         if (prev == q - 1 && (slot & 31) != 0) e |= LBM_QUAD_LEFT;
-        if (q + 1 < G.nx / 4 && quad_active(row, q + 1) && ((slot + 1) & 31) != 0) e |= LBM_QUAD_RIGHT;
+        if (q + 1 < G.nx / 4 && quad_active(row, q + 1, G.nx / 4) && ((slot + 1) & 31) != 0) e |= LBM_QUAD_RIGHT;
         quads[slot++] = e;
         prev = q;
     }
 }
 // one thread per tile: number of wall links (fill == 0) or the links themselves
 __global__ void quad_links_kernel(Grid G, const uint8_t *flags, const unsigned long long *nbr, const unsigned long long *quads, int n_tiles,
-                                  int fill, int *tile_count, const int *link_off, uint2 *tile_links, unsigned long long *links) {
+                                  int fill, int *tile_count, const int *link_off, uint2 *tile_links, unsigned *links) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tiles) return;
     unsigned n = 0;
@@ -477,13 +491,11 @@ __global__ void quad_links_kernel(Grid G, const uint8_t *flags, const unsigned l
             for (int q = 1; q < Q; ++q) {
                 if (!((m >> opp(q)) & 1u)) continue;
                 if (fill) {
-                    int xt = x + cx(q), yt = y + cy(q), zt = z + G.zg + cz(q);          // periodic wrap (an open face is never "solid")
-                    if (xt < 0) xt = G.nx - 1; else if (xt >= G.nx) xt = 0;
-                    if (yt < 0) yt = G.ny - 1; else if (yt >= G.ny) yt = 0;
-                    if (!G.zg) { if (zt < 0) zt = G.nz - 1; else if (zt >= G.nz) zt = 0; }
-                    const unsigned long long target = (unsigned long long)(((long long)zt * G.ny + yt) * G.nx + xt);
-                    links[begin + n] = target | ((unsigned long long)l << 32) | ((unsigned long long)c << 37) | ((unsigned long long)q << 39) |
-                                       ((unsigned long long)opp(q) << 44);
+                    const int w = c + cx(q);                  // the solid neighbour's place in the stage row of opp(q)
+                    unsigned pos = (unsigned)(4 * l + w);
+                    if (w < 0 && !(e & LBM_QUAD_LEFT)) pos = 128u + (unsigned)l;
+                    if (w > 3 && !(e & LBM_QUAD_RIGHT)) pos = 128u + (unsigned)l;
+                    links[begin + n] = ((unsigned)opp(q) * LBM_STAGE_ROW_WORDS + pos) | (((unsigned)q * LBM_STAGE_ROW_WORDS + (unsigned)(4 * l + c)) << 12);
                 }
                 ++n;
             }
@@ -492,10 +504,30 @@ __global__ void quad_links_kernel(Grid G, const uint8_t *flags, const unsigned l
     if (fill) tile_links[t] = make_uint2(begin, n);
     else tile_count[t] = (int)n;
 }
+// wall[link] = the owning cell's own g[q] (g holds post-collision values): what the step kernel would have left there.  Runs after
+// the populations were written from outside the step kernel (initialisation, lbm_import_f, a halo refresh, another kernel variant).
+__global__ void wall_values_kernel(Grid G, const float *g, const unsigned long long *quads, const uint2 *tile_links, const unsigned *links,
+                                   float *wall, int n_tiles) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    const uint2 tl = tile_links[t];
+    for (unsigned i = 0; i < tl.y; ++i) {
+        const unsigned src = (links[tl.x + i] >> 12) & 0xfffu;
+        const int q = (int)(src / LBM_STAGE_ROW_WORDS), w = (int)(src % LBM_STAGE_ROW_WORDS);
+        const unsigned long long e = quads[(long long)t * 32 + (w >> 2)];
+        const int x = 4 * (int)(e & 0xfffu) + (w & 3), y = (int)((e >> 12) & 0xffffu), z = (int)((e >> 28) & 0xffffu);
+        wall[tl.x + i] = g[(long long)q * G.vol + ((long long)(z + G.zg) * G.ny + y) * G.nx + x];
+    }
+}
 #ifndef LBM_EMULATE_ON_HOST
+cudaError_t launch_wall_values(const Grid &G, const float *g, const unsigned long long *quads, const uint2 *tile_links, const unsigned *links,
+                               float *wall, int n_tiles, cudaStream_t s) {
+    if (n_tiles > 0) wall_values_kernel<<<(n_tiles + 127) / 128, 128, 0, s>>>(G, g, quads, tile_links, links, wall, n_tiles);
+    return cudaGetLastError();
+}
 // Builds the packed quad list, its per-plane TILE offsets (host vector of nz + 1 entries), the wall links and the neighbour
 // masks.  Synchronises the stream: geometry changes are rare.
-cudaError_t build_chord_lists(const Grid &G, const uint8_t *flags, unsigned long long **d_quads, uint2 **d_tile_links, unsigned long long **d_links,
+cudaError_t build_chord_lists(const Grid &G, const uint8_t *flags, unsigned long long **d_quads, uint2 **d_tile_links, unsigned **d_links, float **d_wall,
                               std::vector<int> &tile_off, unsigned long long **d_nbr, long long *n_links_out, cudaStream_t s) {
     cudaError_t e;
     if (G.nx % 4 != 0 || G.nx > 16384 || G.ny > 65535 || G.nz + 2 * G.zg > 65535 || G.vol >= (1ll << 32)) return cudaErrorInvalidValue;   // packing limits
@@ -526,6 +558,7 @@ cudaError_t build_chord_lists(const Grid &G, const uint8_t *flags, unsigned long
     if (*d_quads) { cudaFree(*d_quads); *d_quads = nullptr; }
     if (*d_tile_links) { cudaFree(*d_tile_links); *d_tile_links = nullptr; }
     if (*d_links) { cudaFree(*d_links); *d_links = nullptr; }
+    if (*d_wall) { cudaFree(*d_wall); *d_wall = nullptr; }
     const size_t nt_alloc = (size_t)(n_t + n_b > 0 ? n_t + n_b : 1);
     if ((e = cudaMalloc(d_quads, sizeof(unsigned long long) * 32 * nt_alloc)) != cudaSuccess) return e;
     if ((e = cudaMalloc(d_tile_links, sizeof(uint2) * nt_alloc)) != cudaSuccess) return e;
@@ -546,7 +579,8 @@ cudaError_t build_chord_lists(const Grid &G, const uint8_t *flags, unsigned long
         if ((e = cudaMemcpyAsync(&n_l, link_off + n_t, sizeof(int), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
         if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
     }
-    if ((e = cudaMalloc(d_links, sizeof(unsigned long long) * (size_t)(n_l > 0 ? n_l : 1))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(d_links, sizeof(unsigned) * (size_t)(n_l > 0 ? n_l : 1))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(d_wall, sizeof(float) * (size_t)(n_l > 0 ? n_l : 1))) != cudaSuccess) return e;
     if (n_t > 0) quad_links_kernel<<<(n_t + 127) / 128, 128, 0, s>>>(G, flags, *d_nbr, *d_quads, n_t, 1, nullptr, link_off, *d_tile_links, *d_links);
     if (n_b > 0) {      // the finished entries of the two boundary planes, once more, contiguous
         const int n0 = tile_off[1] - tile_off[0], n1 = tile_off[G.nz] - tile_off[G.nz - 1];

@@ -44,8 +44,8 @@ struct StepArgs {
     const unsigned *item_mask;   // VEC = 4 walls kernel: per list entry, the lanes that must load (lbm_phys.cuh)
     const unsigned long long *nbr;     // per cell (valid where NEAR): solid-source bits | out-of-box bits << 32
     // packed quad list of the four-cell walls kernel (lbm_phys_chord.cuh, lbm_aux.cu): one u64 per lane slot, one uint2 (first link,
-    // links) per tile, one u64 per wall link
-    const unsigned long long *quads; const uint2 *tile_links; const unsigned long long *links;
+    // links) per tile, one u32 per wall link, one float per wall link (the bounced-back value waiting for the next step)
+    const unsigned long long *quads; const uint2 *tile_links; const unsigned *links; float *wall;
     // fused pressure-gradient drive (LBM_FEAT_DRIVE): rho of the previous step, clamp and scale of the force
     const float *rho_src; float drive_max_force, drive_scale;
     int write_macro;

@@ -32,8 +32,11 @@ constexpr int min_blocks_phys_walls() { return VEC == 2 ? (BLOCK == 256 ? 2 : 64
 
 // chord kernel (lbm_phys_chord.cuh), 64-thread CTAs, one tile per warp: 10.1 KB of shared memory per warp, 8 CTAs per SM = 16
 // warps at 128 registers, no spills (measured on B200, V60 512^3: 16 warps 1.82 ms, 18 / 20 warps with ~90 B of spills 1.99 ms).
+#ifndef LBM_CHORD_WARPS
+#define LBM_CHORD_WARPS 16
+#endif
 template <int BLOCK>
-constexpr int chord_blocks() { return 512 / BLOCK; }
+constexpr int chord_blocks() { return LBM_CHORD_WARPS * 32 / BLOCK; }
 
 // CTA size: the walls path runs best with small CTAs (near-wall warps take longer; a CTA slot is held until its
 // slowest warp retires -- V60 512^3 sweep: 64 threads 2.17 ms, 128: 2.20, 256: 2.34)

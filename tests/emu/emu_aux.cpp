@@ -136,9 +136,9 @@ int emu_bounce_slots(int nx, int ny, int nz, int periodic, float *g, const uint8
 }
 // packed quad list + wall links of the four-cell walls kernel (build_chord_lists without cub: the exclusive sums and the
 // per-plane padding run here on the host).  Returns the number of tiles; quads_out = 32 u64 per tile, tile_links_out = 2 u32 per
-// tile, links_out up to max_links u64, tile_off_out = nz + 1 ints.
+// tile, links_out up to max_links u32, tile_off_out = nz + 1 ints.
 int emu_chord_lists(int nx, int ny, int nz, int periodic, const uint8_t *flags, const unsigned long long *nbr, unsigned long long *quads_out,
-                    int max_tiles, unsigned *tile_links_out, unsigned long long *links_out, int max_links, int *n_links_out, int *tile_off_out) {
+                    int max_tiles, unsigned *tile_links_out, unsigned *links_out, int max_links, int *n_links_out, int *tile_off_out) {
     const Grid G = make_grid(nx, ny, nz, periodic);
     const int rows = nz * ny;
     std::vector<int> cnt(rows + 1, 0), off(rows + 1, 0), plane_base(nz + 1, 0);
@@ -161,6 +161,13 @@ int emu_chord_lists(int nx, int ny, int nz, int periodic, const uint8_t *flags, 
     run(dim3((n_t + 127) / 128, 1, 1), 128, [&] { quad_links_kernel(G, flags, nbr, quads_out, n_t, 1, nullptr, lo.data(), reinterpret_cast<uint2 *>(tile_links_out), links_out); });
     *n_links_out = lo[n_t];
     return n_t;
+}
+// the value waiting on every wall link, taken from the populations (wall_values_kernel)
+int emu_wall_values(int nx, int ny, int nz, int periodic, const float *g, const unsigned long long *quads, const unsigned *tile_links, const unsigned *links,
+                    float *wall, int n_tiles) {
+    const Grid G = make_grid(nx, ny, nz, periodic);
+    run(dim3((n_tiles + 127) / 128, 1, 1), 128, [&] { wall_values_kernel(G, g, quads, reinterpret_cast<const uint2 *>(tile_links), links, wall, n_tiles); });
+    return 0;
 }
 // pressure-gradient producer over the packed quad list
 int emu_pressure_gradient_chord(int nx, int ny, int nz, const float *rho, const uint8_t *flags, float *bf, float max_force, float scale, int accumulate,

@@ -259,7 +259,7 @@ def _chord_lists(aux, solid_zyx, periodic):
     flags = np.zeros_like(solid_zyx); nbr = np.zeros(solid_zyx.shape, np.uint64)
     aux.emu_pack_flags_and_masks(C.c_int(nx), C.c_int(ny), C.c_int(nz), C.c_int(periodic), _p(flags), _p(np.ascontiguousarray(solid_zyx)), None, None, _p(nbr))
     max_t, max_l = nz * (ny * (nx // 4) // 32 + 2), 18 * solid_zyx.size
-    quads = np.zeros((max_t, 32), np.uint64); tl = np.zeros((max_t, 2), np.uint32); links = np.zeros(max_l, np.uint64); nl = C.c_int(0)
+    quads = np.zeros((max_t, 32), np.uint64); tl = np.zeros((max_t, 2), np.uint32); links = np.zeros(max_l, np.uint32); nl = C.c_int(0)
     tile_off = np.zeros(nz + 1, np.int32)
     nt = aux.emu_chord_lists(C.c_int(nx), C.c_int(ny), C.c_int(nz), C.c_int(periodic), _p(flags), _p(nbr), _p(quads), C.c_int(max_t), _p(tl), _p(links),
                              C.c_int(max_l), C.byref(nl), _p(tile_off))
@@ -269,10 +269,12 @@ def _chord_lists(aux, solid_zyx, periodic):
 
 @pytest.mark.parametrize("case", ["v60_64", "random_40x12x9", "random_periodic_24x10x8", "two_chords_136x6x5"])
 def test_emulated_quad_list_holds_every_active_quad_once_and_links_are_the_wall_links(aux, case):
-    """build_chord_lists (lbm_aux.cu): the list is every quad holding a fluid cell, once, in memory order, 32 per tile, only the last
-    tile of a plane padded with dead lanes; the adjacency bits say exactly when the neighbouring lane of the same tile holds the
-    neighbouring quad of the same row; the links of a tile are exactly the (fluid cell, q) pairs of its lanes whose target x + e_q is
-    a solid cell inside the box, with the target's linear index and opp(q) packed as the kernel expects."""
+    """build_chord_lists (lbm_aux.cu): the list is every quad whose 32-byte sector (the quad and its even / odd partner) holds a fluid
+    cell, once, in memory order, 32 per tile, only the last tile of a plane padded with dead lanes; the adjacency bits say exactly
+    when the neighbouring lane of the same tile holds the neighbouring quad of the same row; the links of a tile are exactly the
+    (fluid cell, q) pairs of its lanes whose target x + e_q is a solid cell inside the box; each names the stage word the waiting value
+    is put into (row opp(q), the solid neighbour's place or the lane's edge word) and the stage word the new value is taken from (row
+    q, the cell's own word); wall_values_kernel fills the per-link buffer with the owning cell's own population q."""
     rng = np.random.default_rng(5)
     periodic = 0
     if case == "v60_64":
@@ -286,10 +288,16 @@ def test_emulated_quad_list_holds_every_active_quad_once_and_links_are_the_wall_
     nz, ny, nx = solid.shape
     flags, nbr, quads, tl, links, tile_off = _chord_lists(aux, solid, periodic)
     fluid = solid == 0
-    quad_active = fluid.reshape(nz, ny, nx // 4, 4).any(-1)
+    has_fluid = fluid.reshape(nz, ny, nx // 4, 4).any(-1)
+    quad_active = has_fluid.copy()
+    nq = nx // 4
+    quad_active[:, :, 0:nq - nq % 2:2] |= has_fluid[:, :, 1:nq:2]
+    quad_active[:, :, 1:nq:2] |= has_fluid[:, :, 0:nq - nq % 2:2]
+    g = rng.random((19, nz, ny, nx)).astype(np.float32)
     LIVE, LEFT, RIGHT = 1 << 44, 1 << 45, 1 << 46
     listed = []
     got_links = set()
+    link_cells = []
     for t in range(len(quads)):
         z_tile = int(np.searchsorted(tile_off, t, side="right") - 1)
         for l in range(32):
@@ -309,13 +317,23 @@ def test_emulated_quad_list_holds_every_active_quad_once_and_links_are_the_wall_
         lb, n = int(tl[t, 0]), int(tl[t, 1])
         for L in links[lb:lb + n]:
             L = int(L)
-            target, l, c, q, qd = L & 0xffffffff, (L >> 32) & 31, (L >> 37) & 3, (L >> 39) & 31, (L >> 44) & 31
+            dst, src = L & 0xfff, (L >> 12) & 0xfff
+            q, w = divmod(src, 160)
+            l, c = divmod(w, 4)
+            assert w < 128 and 1 <= q < 19
             e = int(quads[t, l])
-            assert e & LIVE and qd == _OPP[q]
+            assert e & LIVE
             q0, y, z = e & 0xfff, (e >> 12) & 0xffff, (e >> 28) & 0xffff
             x = 4 * q0 + c
-            assert target == (((z + _CZ[q]) % nz) * ny + (y + _CY[q]) % ny) * nx + (x + _CX[q]) % nx
+            row, pos = divmod(dst, 160)
+            assert row == _OPP[q]
+            wn = c + _CX[q]
+            if 0 <= wn <= 3 or (wn < 0 and e & LEFT) or (wn > 3 and e & RIGHT):
+                assert pos == 4 * l + wn
+            else:
+                assert pos == 128 + l
             got_links.add((z, y, x, q))
+            link_cells.append((q, z, y, x))
     want = [(int(z), int(y), int(q)) for z, y, q in zip(*np.nonzero(quad_active))]
     assert listed == want                                                 # every active quad once, in memory order
     assert tile_off[-1] == len(quads) and all(tile_off[z + 1] - tile_off[z] == -(-int(quad_active[z].sum()) // 32) for z in range(nz))
@@ -329,6 +347,12 @@ def test_emulated_quad_list_holds_every_active_quad_once_and_links_are_the_wall_
             if solid[zt % nz, yt % ny, xt % nx]:
                 want_links.add((int(z), int(y), int(x), q))
     assert got_links == want_links and len(links) == len(want_links)
+    wall = np.full(len(links), -1.0, np.float32)
+    aux.emu_wall_values(C.c_int(nx), C.c_int(ny), C.c_int(nz), C.c_int(periodic), _p(g), _p(np.ascontiguousarray(quads)), _p(np.ascontiguousarray(tl)),
+                        _p(links), _p(wall), C.c_int(len(quads)))
+    order = [i for t in range(len(quads)) for i in range(int(tl[t, 0]), int(tl[t, 0]) + int(tl[t, 1]))]
+    assert order == list(range(len(links)))
+    assert np.array_equal(wall, np.array([g[c] for c in link_cells], np.float32))
 
 
 def test_emulated_quad_list_pressure_gradient_equals_the_grid_kernel(aux):
