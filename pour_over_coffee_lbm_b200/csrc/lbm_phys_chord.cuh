@@ -65,7 +65,7 @@ __device__ __forceinline__ float4 lds128(unsigned a) {
 #define LBM_CHORD_ORDERED 1
 #endif
 #ifndef LBM_CHORD_PREFETCH
-#define LBM_CHORD_PREFETCH 0
+#define LBM_CHORD_PREFETCH 1024
 #endif
 #if LBM_CHORD_ORDERED
 __device__ __forceinline__ unsigned long long ldo_u64(const void *p) { unsigned long long v; asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(v) : "l"(p)); return v; }
@@ -255,6 +255,7 @@ __device__ __forceinline__ void chord_compute_store(const StepArgs &P, const Cho
     const bool all_mine = mine_bits == 15u;
     // Halfway bounce-back: the value a cell sent towards a solid neighbour one step ago comes back as the opposite population.  It
     // waited in the per-link buffer and goes into the stage word the pull would have read from the solid cell (lbm_aux.cu).
+#pragma unroll 1
     for (unsigned i = lane; i < n_links; i += 32u) {
         const unsigned L = i < 32u ? a.link0 : __ldg(P.links + tl.x + i);
         const float v = i < 32u ? a.wall0 : __ldg(P.wall + tl.x + i);
@@ -275,10 +276,12 @@ __device__ __forceinline__ void chord_compute_store(const StepArgs &P, const Cho
     // results into words 0, 1 of every lane, so the two words of pair 1 that this would overwrite move into the edge line first: the next
     // lane's word 0 here, the lane's own word 1 once pair 0 has read the edge word.  The loop over the pairs is NOT unrolled (one copy of
     // the collision in the instruction cache); what differs between the pairs is three base addresses.
-    if (t.right_adj) {
+    if (t.right_adj) {                                     // five loads, then five stores: interleaved, every store waits for its load
+        float w0[Q];
+        static_for<0, Q>([&](auto qq) { constexpr int q = decltype(qq)::value; if constexpr (cx(q) < 0) w0[q] = lds32(s_own + q * ROWB + 16); });
         static_for<0, Q>([&](auto qq) {
             constexpr int q = decltype(qq)::value;
-            if constexpr (cx(q) < 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_edge + q * ROWB), "f"(lds32(s_own + q * ROWB + 16)) : "memory");
+            if constexpr (cx(q) < 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_edge + q * ROWB), "f"(w0[q]) : "memory");
         });
     }
     unsigned sa = s_own;                                   // the pair's own two words
@@ -294,19 +297,11 @@ __device__ __forceinline__ void chord_compute_store(const StepArgs &P, const Cho
             else fp[q] = p2_make(lds32(sa + q * ROWB + 4), lds32(sr + q * ROWB));
         });
         if (h == 0) {
+            float w1[Q];
+            static_for<0, Q>([&](auto qq) { constexpr int q = decltype(qq)::value; if constexpr (cx(q) > 0) w1[q] = lds32(s_own + q * ROWB + 4); });
             static_for<0, Q>([&](auto qq) {
                 constexpr int q = decltype(qq)::value;
-                if constexpr (cx(q) > 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_edge + q * ROWB), "f"(lds32(s_own + q * ROWB + 4)) : "memory");
-            });
-        }
-        // whole quads are stored, solid cells included: their lane of the pair collides the rest state w_q instead of whatever the pull
-        // brought (never read back -- pulls from a solid cell are replaced by the link values above -- but it keeps the arithmetic of
-        // that lane finite and on the fast paths)
-        const unsigned pm = (mine_bits >> (2 * h)) & 3u;
-        if (pm != 3u) {
-            static_for<0, Q>([&](auto qq) {
-                constexpr int q = decltype(qq)::value;
-                fp[q] = p2_make((pm & 1u) ? p2_lo(fp[q]) : wq(q), (pm & 2u) ? p2_hi(fp[q]) : wq(q));
+                if constexpr (cx(q) > 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_edge + q * ROWB), "f"(w1[q]) : "memory");
             });
         }
         CellIn<P2> in;
@@ -314,13 +309,14 @@ __device__ __forceinline__ void chord_compute_store(const StepArgs &P, const Cho
         in.Fy = h ? p2_make(F[1][2], F[1][3]) : p2_make(F[1][0], F[1][1]);
         in.Fz = h ? p2_make(F[2][2], F[2][3]) : p2_make(F[2][0], F[2][1]);
         in.phase = h ? p2_make(ph[2], ph[3]) : p2_make(ph[0], ph[1]);
-        const unsigned fw = a.flag_word >> (16 * h);
+        // dead lanes (the padding of a plane's last tile) count as solid
+        const unsigned fw = live ? a.flag_word >> (16 * h) : 0x0101u;
         in.flag[0] = fw & 0xffu; in.flag[1] = (fw >> 8) & 0xffu;
         CellMacro<P2> mac;
 #ifdef LBM_EXP_COPY      /* timing experiment: no collision (wrong results) */
         mac.rho = mac.ux = mac.uy = mac.uz = fp[0];
 #else
-        collide_phys<P2, HAS_F, LES, POROUS, COLLIDE>(fp, in, mac, P, has_phase, has_force);
+        collide_phys<P2, HAS_F, LES, POROUS, COLLIDE, true>(fp, in, mac, P, has_phase, has_force);
 #endif
         if constexpr (COLLIDE) {
             __syncwarp();                                                // every lane has read this pair's inputs
@@ -373,6 +369,7 @@ __device__ __forceinline__ void chord_compute_store(const StepArgs &P, const Cho
         }
         if (n_links) {                                                   // warp-uniform
             __syncwarp();                                                // results of every lane are in the stage
+#pragma unroll 1
             for (unsigned i = lane; i < n_links; i += 32u) {
                 const unsigned L = i < 32u ? a.link0 : __ldg(P.links + tl.x + i);
                 P.wall[tl.x + i] = lds32(s_row0 + 4u * ((L >> 12) & 0xfffu));
@@ -412,6 +409,20 @@ __global__ void __launch_bounds__(BLOCK, MINB) phys_chord_kernel(const __grid_co
 #endif
     float F[3][4], ph[4];
     chord_force<FORCED, DRIVE>(P, t, a, F, ph);
+#if LBM_CHORD_ORDERED
+    {   // Every register load above must be ISSUED before the wait below.  ptxas sinks a load towards its first use, and that lies
+        // behind the wait for the inputs the collision reads first: the warp then sat through a second DRAM round trip after the
+        // populations had landed (ncu: 14 % of all stall samples on the flag word).  One word that depends on every loaded register,
+        // stored into an unused edge word of the stage before the wait, pins them (11 instructions per tile).
+        unsigned k = a.flag_word ^ a.link0 ^ __float_as_uint(a.wall0);
+        if constexpr (FORCED) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) k ^= __float_as_uint(a.bf[d].x) ^ __float_as_uint(a.bf[d].y) ^ __float_as_uint(a.bf[d].z) ^ __float_as_uint(a.bf[d].w);
+            k ^= __float_as_uint(a.ph.x) ^ __float_as_uint(a.ph.y) ^ __float_as_uint(a.ph.z) ^ __float_as_uint(a.ph.w);
+        }
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(s_edge), "r"(k) : "memory");      // row 0 does not move in x: its edge line is free
+    }
+#endif
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
     chord_compute_store<FORCED, LES, POROUS, DRIVE, COLLIDE>(P, t, tl, a, F, ph, lane, s_own, s_row0, s_edge);

@@ -84,7 +84,9 @@ class D3Q19Engine:
         dev = self.device
         shp = (self.nzp, self.ny, self.nx)
         with torch.cuda.device(dev):
-            self.g = [torch.empty((L.Q,) + shp, dtype=torch.float32, device=dev) for _ in range(2)]
+            # zeros, not empty: the four-cell walls kernel pulls solid cells' words into lanes whose results nobody reads; NaN there
+            # would only cost speed (slow paths of rcp / sqrt), but it would
+            self.g = [torch.zeros((L.Q,) + shp, dtype=torch.float32, device=dev) for _ in range(2)]
             self.cur = 0                      # index of the buffer holding the newest populations
             # rho: one buffer; a ping-pong pair when the fused drive reads the previous step's density while this step's is written
             self.rho_buf = [torch.ones(shp, dtype=torch.float32, device=dev) for _ in range(2 if drive else 1)] if macro_fields else []
