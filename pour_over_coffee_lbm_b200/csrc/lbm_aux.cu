@@ -421,7 +421,10 @@ cudaError_t build_work_lists(const Grid &G, const uint8_t *flags, int vec, int t
 // whether 11 or 32 of its lanes work, the step ran at 0.67 of the HBM peak where a periodic box (every lane alive) runs at
 // 0.86 (profiles/r02_exp_structure_cost_periodic_box.log).  Only the last tile of a plane is padded (slab launches address plane
 // ranges).  Per lane slot (u64): bits 0-11 quad index in the row, 12-27 y, 28-43 z, 44 live, 45 / 46 the previous / next lane
-// of the SAME tile holds the quad to the left / right in the same row (else the lane fetches that neighbour itself).
+// of the SAME tile holds the quad to the left / right in the same row (else the lane fetches that neighbour itself), 47-54 one bit
+// per neighbouring row (dz, dy) != (0, 0), bit (dz + 1) * 3 + (dy + 1) (minus one behind the centre): the quad at the same x in that
+// row holds no fluid cell or lies outside an open face, so nothing the collision uses comes from it (a fluid cell that pulls from a
+// solid cell takes the link value, a source outside the box is w_q) and the kernel does not read it from DRAM.
 // Wall link (u32) = one (fluid cell, direction q) pair whose target x + e_q is solid.  Halfway bounce-back hands the cell's
 // post-collision f_q back to the same cell as f_opp(q) one step later, so the value never has to visit the population arrays: it
 // waits in a per-link buffer (`wall`, one float per link, read and written by the tile that owns the link, coalesced).  The link
@@ -467,6 +470,19 @@ __global__ void quad_fill_kernel(Grid G, const uint8_t *flags, const int *row_of
         unsigned long long e = (unsigned long long)q | ((unsigned long long)y << 12) | ((unsigned long long)z << 28) | LBM_QUAD_LIVE;
         if (prev == q - 1 && (slot & 31) != 0) e |= LBM_QUAD_LEFT;
         if (q + 1 < G.nx / 4 && quad_active(row, q + 1, G.nx / 4) && ((slot + 1) & 31) != 0) e |= LBM_QUAD_RIGHT;
+        for (int dz = -1; dz <= 1; ++dz)
+            for (int dy = -1; dy <= 1; ++dy) {
+                if (dz == 0 && dy == 0) continue;
+                int bit = (dz + 1) * 3 + (dy + 1); if (bit > 4) --bit;
+                int ys = y + dy, zs = z + dz;
+                bool dead = false;
+                if (ys < 0 || ys >= G.ny) { if (G.per_y) ys = (ys + G.ny) % G.ny; else dead = true; }
+                const int zglob = G.z0 + zs;
+                if (zglob < 0 || zglob >= G.nz_global) { if (!G.per_z) dead = true; }
+                if (!G.zg) { if (zs < 0) zs = G.nz - 1; else if (zs >= G.nz) zs = 0; }
+                if (!dead) dead = !quad_has_fluid(flags + ((long long)(zs + G.zg) * G.ny + ys) * G.nx, q);
+                if (dead) e |= 1ull << (47 + bit);
+            }
         quads[slot++] = e;
         prev = q;
     }

@@ -48,6 +48,10 @@ namespace lbm {
 __device__ __forceinline__ void cp_async16(unsigned smem_dst, const void *gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
+// 16 bytes, or 16 bytes of zeros without touching global memory when bytes == 0
+__device__ __forceinline__ void cp_async16_or_zero(unsigned smem_dst, const void *gsrc, unsigned bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async4(unsigned smem_dst, const void *gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
@@ -94,6 +98,7 @@ constexpr int CHORD_STAGE = Q * (int)(CHORD_ROWB / 4);   // floats per stage (on
 // neighbouring lane holds the neighbouring quad)
 struct ChordGeom {
     bool live, left_adj, right_adj;
+    unsigned dead_rows;              // bit per neighbouring row: its quad at this x brings nothing the collision uses (lbm_aux.cu)
     int x0, y, z;
     unsigned own, row0;
     int dym, dyq, dzm, dzq;          // neighbour rows as 32-bit index deltas: periodic wrap, else clamp (a clamped source lies
@@ -101,6 +106,7 @@ struct ChordGeom {
 __device__ __forceinline__ ChordGeom chord_decode(const unsigned long long e, const Grid &G) {
     ChordGeom t;
     t.live = ((e >> 44) & 1ull) != 0; t.left_adj = ((e >> 45) & 1ull) != 0; t.right_adj = ((e >> 46) & 1ull) != 0;
+    t.dead_rows = (unsigned)(e >> 47) & 0xffu;
     t.x0 = (int)(e & 0xfffull) * 4;         // dead lanes (padding of a plane's last tile) sit on cell (0, 0, 0): loaded, never stored
     t.y = (int)((e >> 12) & 0xffffull); t.z = (int)((e >> 28) & 0xffffull);
     t.row0 = ((unsigned)(t.z + G.zg) * (unsigned)G.ny + (unsigned)t.y) * (unsigned)G.nx;
@@ -128,7 +134,11 @@ __device__ __forceinline__ void chord_issue_loads(const StepArgs &P, const Chord
             rowp[dz + 1][dy + 1] = P.src + (t.own + (unsigned)(dy < 0 ? t.dym : (dy > 0 ? t.dyq : 0)) + (unsigned)(dz < 0 ? t.dzm : (dz > 0 ? t.dzq : 0)));
     static_for<0, Q>([&](auto qq) {
         constexpr int q = decltype(qq)::value;
-        cp_async16(s_own + q * CHORD_ROWB, plane_of(rowp[1 - cz(q)][1 - cy(q)], vol, q));
+        if constexpr (cy(q) == 0 && cz(q) == 0) cp_async16(s_own + q * CHORD_ROWB, plane_of(rowp[1][1], vol, q));
+        else {      // source row (y - cy, z - cz)
+            constexpr int b9 = (1 - cz(q)) * 3 + (1 - cy(q)), bit = b9 > 4 ? b9 - 1 : b9;
+            cp_async16_or_zero(s_own + q * CHORD_ROWB, plane_of(rowp[1 - cz(q)][1 - cy(q)], vol, q), ((t.dead_rows >> bit) & 1u) ? 0u : 16u);
+        }
     });
     // x-1 / x+4 neighbour of the quad when the neighbouring lane does not bring it
     if (!t.left_adj) {

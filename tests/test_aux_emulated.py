@@ -295,6 +295,7 @@ def test_emulated_quad_list_holds_every_active_quad_once_and_links_are_the_wall_
     quad_active[:, :, 1:nq:2] |= has_fluid[:, :, 0:nq - nq % 2:2]
     g = rng.random((19, nz, ny, nx)).astype(np.float32)
     LIVE, LEFT, RIGHT = 1 << 44, 1 << 45, 1 << 46
+    per = [(periodic >> d) & 1 for d in range(3)]
     listed = []
     got_links = set()
     link_cells = []
@@ -312,6 +313,15 @@ def test_emulated_quad_list_holds_every_active_quad_once_and_links_are_the_wall_
             prev = int(quads[t, l - 1]) if l > 0 else 0
             nxt = int(quads[t, l + 1]) if l < 31 else 0
             same_row = lambda o: bool(o & LIVE) and ((o >> 12) & 0xffff, (o >> 28) & 0xffff) == (y, z)
+            for dz in (-1, 0, 1):                                    # bits 47-54: neighbouring rows whose quad at this x brings nothing
+                for dy in (-1, 0, 1):
+                    if dz == 0 and dy == 0:
+                        continue
+                    bit = (dz + 1) * 3 + (dy + 1); bit -= bit > 4
+                    ys, zs = y + dy, z + dz
+                    outside = (not per[1] and not 0 <= ys < ny) or (not per[2] and not 0 <= zs < nz)
+                    dead = outside or not has_fluid[zs % nz, ys % ny, q0]
+                    assert bool((e >> (47 + bit)) & 1) == dead
             assert bool(e & LEFT) == (same_row(prev) and (prev & 0xfff) == q0 - 1)
             assert bool(e & RIGHT) == (same_row(nxt) and (nxt & 0xfff) == q0 + 1)
         lb, n = int(tl[t, 0]), int(tl[t, 1])
