@@ -574,6 +574,77 @@ def _interface_margin(engine: D3Q19Engine, ps: ParticleState, owned: torch.Tenso
     return min(max(margin - 1, 0), 4096)
 
 
+def particles_fluid_forces_slab(engine: D3Q19Engine, ps: ParticleState, force: torch.Tensor, counters: torch.Tensor,
+                                water_density: float, water_viscosity: float, gravity: float) -> None:
+    """CoffeeParticleSystem.apply_fluid_forces (coffee_particles.py:547-639) on a z-slab engine: replicated particles, the rank whose
+    slab holds the particle's base cell computes (the kernel reads u at that cell only, no ghost plane involved).  The kernel's side
+    effects on the owner -- the force, a velocity it reset, a particle it deactivated, the error counter -- reach every rank through
+    one packed all-reduce, so the replicated arrays stay identical."""
+    import ctypes as C
+    import torch.distributed as dist
+    from . import slab
+    active_all = ps.active
+    owned = slab.particle_owner_mask(ps.pos[2], active_all, engine.z0, engine.nz, engine.nz_global)
+    work = owned.clone()
+    local = torch.zeros_like(counters)
+    ps.active = work
+    try:
+        st = ps.struct()
+        engine._check(engine.lib.lbm_particles_fluid_forces(engine._ctx, _ptr(engine.u), C.byref(st), _ptr(force), float(water_density),
+                                                            float(water_viscosity), float(gravity), _ptr(local), engine.stream),
+                      "lbm_particles_fluid_forces")
+    finally:
+        ps.active = active_all
+    slab.allreduce_owned_packed([force, ps.vel, work], owned, active_all)      # work: 1 where the owner kept the particle
+    active_all.mul_(torch.where(active_all != 0, work, torch.ones_like(work)))
+    if engine.nranks > 1:
+        dist.all_reduce(local, op=dist.ReduceOp.SUM)
+    counters.add_(local)
+
+
+def particles_block_at_filter_slab(engine: D3Q19Engine, ps: ParticleState, accumulated: torch.Tensor, scale_length: float, noise: float,
+                                   seed: int) -> None:
+    """FilterPaperSystem.block_particles_at_filter (filter_paper.py:616-700) on a z-slab engine.  The reference takes the FIRST filter
+    cell among the planes gz - 2 .. gz + 2 of the particle's column; that range can straddle a slab interface.  Every rank looks up
+    the lowest such plane among the planes it OWNS, the ranks agree on the minimum (one all-reduce), and the rank that owns that plane
+    runs the kernel for the particle (no earlier filter cell exists anywhere, so the kernel's own search ends on that plane); particles
+    without a filter cell in range stay with the owner of their base cell, which leaves them unchanged.  One packed all-reduce brings
+    the velocities back."""
+    import ctypes as C
+    import torch.distributed as dist
+    from . import slab
+    active_all = ps.active
+    n_big = 1 << 30
+    sl = torch.tensor(scale_length, dtype=torch.float32, device=ps.pos.device)
+    g = torch.div(ps.pos, sl).to(torch.int32)                                   # (int)(pos / SCALE_LENGTH), f32 division as in the kernel
+    gx, gy, gz = g[0].long(), g[1].long(), g[2].long()
+    inside = (gx >= 0) & (gx < engine.nx) & (gy >= 0) & (gy < engine.ny) & (gz >= 0) & (gz < engine.nz_global) & (active_all != 0)
+    first = torch.full_like(gz, n_big)
+    flags = engine.flags                                                         # [nz + 2, ny, nx], plane zp = k - z0 + 1
+    cx_, cy_ = gx.clamp(0, engine.nx - 1), gy.clamp(0, engine.ny - 1)
+    for off in (2, 1, 0, -1, -2):                                                # descending: the last hit written is the lowest plane
+        k = gz + off
+        mine = inside & (k >= engine.z0) & (k < engine.z0 + engine.nz)
+        zp = (k - engine.z0 + 1).clamp(0, engine.nz + 1)
+        hit = mine & ((flags[zp, cy_, cx_] & L.FLAG_FILTER) != 0)
+        first = torch.where(hit, k, first)
+    if engine.nranks > 1:
+        dist.all_reduce(first, op=dist.ReduceOp.MIN)
+    has = first < n_big
+    base_owner = slab.particle_owner_mask(ps.pos[2], active_all, engine.z0, engine.nz, engine.nz_global) != 0
+    owner = torch.where(has, (first >= engine.z0) & (first < engine.z0 + engine.nz), base_owner) & (active_all != 0)
+    owned = owner.to(torch.int32)
+    ps.active = torch.where(has, owned, torch.zeros_like(owned))                 # the kernel runs for particles with a filter cell in range
+    try:
+        st = ps.struct()
+        engine._check(engine.lib.lbm_particles_block_at_filter(engine._ctx, C.byref(st), _ptr(engine.flags), _ptr(accumulated),
+                                                               float(scale_length), float(noise), int(seed) & 0xFFFFFFFF, engine.stream),
+                      "lbm_particles_block_at_filter")
+    finally:
+        ps.active = active_all
+    slab.allreduce_owned_packed([ps.vel], owned, active_all)
+
+
 def particles_advance(engine: D3Q19Engine, ps: ParticleState, dt: float, center_x: float, center_y: float, bottom_z: float,
                       bottom_radius_lu: float, top_radius_lu: float, force: Optional[torch.Tensor] = None,
                       counters: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -185,8 +185,10 @@ class FilterPaperSystem:
         self._block_calls = getattr(self, "_block_calls", 0) + 1
         e = self.lbm.engine
         if e.zghost:
-            raise NotImplementedError("block_particles_at_filter on z-slabs: replicated particles would bounce once per rank that sees the "
-                                      "filter cell; needs the ownership mask of the coupling path (not built)")
+            from .engine import particles_block_at_filter_slab
+            particles_block_at_filter_slab(e, ps.state, self._accumulated, float(np.float32(self.lbm.config.SCALE_LENGTH)), float(noise),
+                                           int(self._block_calls if seed is None else seed))
+            return
         st = ps.state.struct()
         import ctypes as C
         e._check(e.lib.lbm_particles_block_at_filter(e._ctx, C.byref(st), _ptr(e.flags), _ptr(self._accumulated),
@@ -529,8 +531,10 @@ class CoffeeParticleSystem:
             self.error_counters = torch.zeros(2, dtype=torch.int32, device=self.state.pos.device)
         e = self._solver.engine
         if e.zghost:
-            raise NotImplementedError("apply_fluid_forces on z-slabs: the replicated force array needs the owner / all-reduce treatment "
-                                      "of compute_two_way_coupling_forces; not built (the reference never calls this method)")
+            from .engine import particles_fluid_forces_slab
+            particles_fluid_forces_slab(e, self.state, self.force_tensor, self.error_counters, float(self.water_density),
+                                        float(self.water_viscosity), float(self.gravity))
+            return
         st = self.state.struct()
         e._check(e.lib.lbm_particles_fluid_forces(e._ctx, _ptr(e.u), C.byref(st), _ptr(self.force_tensor), float(self.water_density),
                                                   float(self.water_viscosity), float(self.gravity), _ptr(self.error_counters), e.stream),

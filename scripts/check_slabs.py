@@ -125,6 +125,75 @@ def run_particles(rank, world, local, nx, nzg, make_engine, setup, cfg, n_part=2
     return bool(flag.item())
 
 
+def run_particle_producers(rank, world, local, nx, nzg, make_engine, setup, cfg, n_part=20000):
+    """The two per-particle producers next to the coupling on slabs -- CoffeeParticleSystem.apply_fluid_forces (owner of the base cell
+    computes) and FilterPaperSystem.block_particles_at_filter (owner of the first filter plane in gz - 2 .. gz + 2 computes, the range
+    may straddle an interface) -- against the single-GPU kernels: force, velocities, the active flags (incl. particles the kernel
+    deactivates), the error counter and the accumulated-particles field, all bit for bit."""
+    import ctypes as C
+    from pour_over_coffee_lbm_b200.engine import ParticleState, particles_fluid_forces_slab, particles_block_at_filter_slab, _ptr
+    sl = float(np.float32(cfg.SCALE_LENGTH))
+
+    def particles(dev, scaled):
+        rng = np.random.default_rng(13)
+        ps = ParticleState(n_part, dev)
+        pos = np.stack([rng.uniform(0.2 * nx, 0.8 * nx, n_part), rng.uniform(0.2 * nx, 0.8 * nx, n_part), rng.uniform(1.0, nzg - 2.0, n_part)])
+        if scaled:
+            pos = pos * sl                      # quirk Q9: the filter lookup divides the position by SCALE_LENGTH
+        else:
+            pos[0, ::97] = np.nan; pos[2, 5::101] = 1e9     # invalid coordinates: deactivated by the kernel, counted
+        ps.pos.copy_(torch.from_numpy(pos.astype(np.float32)))
+        vel = (1e-2 * rng.standard_normal((3, n_part))).astype(np.float32)
+        ps.vel.copy_(torch.from_numpy(vel))
+        rad = np.clip(rng.normal(3.25e-4, 1e-4, n_part), 1.6e-4, 4.9e-4).astype(np.float32)
+        ps.radius.copy_(torch.from_numpy(rad))
+        ps.mass.copy_(torch.from_numpy(((np.float32(4 / 3) * np.float32(3.14159)) * rad ** 3 * np.float32(1200.0)).astype(np.float32)))
+        ps.active.fill_(1); ps.active[::19] = 0
+        return ps
+
+    rho_w, mu_w, grav = 997.0, 1.0e-3, 9.81
+    part = slab.partition_z(nzg, world)[rank]
+    eng = make_engine(nz=part.nz, zghost=1, z0=part.z0, nz_global=nzg, device=local)
+    eng.attach_process_group()
+    setup(eng, part.z0, part.nz, True)
+    eng.halo_exchange(with_u=True)
+    eng.step(3)
+    pa, pb = particles(eng.device, False), particles(eng.device, True)
+    force = torch.zeros_like(pa.pos); counters = torch.zeros(2, dtype=torch.int32, device=eng.device)
+    particles_fluid_forces_slab(eng, pa, force, counters, rho_w, mu_w, grav)
+    acc = torch.zeros_like(eng.rho)
+    particles_block_at_filter_slab(eng, pb, acc, sl, 0.01, 7)
+    torch.cuda.synchronize()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (part.z0, acc[1:-1].cpu()))
+    ok = True
+    if rank == 0:
+        gathered.sort(key=lambda t: t[0])
+        acc_all = torch.cat([m for _, m in gathered], dim=0)
+        ref = make_engine(nz=nzg, zghost=0, z0=0, nz_global=nzg, device=local)
+        setup(ref, 0, nzg, False)
+        ref.step(3)
+        ra, rb = particles(ref.device, False), particles(ref.device, True)
+        rforce = torch.zeros_like(ra.pos); rcount = torch.zeros(2, dtype=torch.int32, device=ref.device)
+        st = ra.struct()
+        ref._check(ref.lib.lbm_particles_fluid_forces(ref._ctx, _ptr(ref.u), C.byref(st), _ptr(rforce), rho_w, mu_w, grav, _ptr(rcount), ref.stream), "ff")
+        racc = torch.zeros_like(ref.rho)
+        st = rb.struct()
+        ref._check(ref.lib.lbm_particles_block_at_filter(ref._ctx, C.byref(st), _ptr(ref.flags), _ptr(racc), sl, 0.01, 7, ref.stream), "bf")
+        torch.cuda.synchronize()
+        same = lambda a, b: torch.equal(a.view(torch.int32), b.view(torch.int32)) if a.dtype == torch.float32 else torch.equal(a, b)
+        act = ra.active != 0
+        e_force = same(force[:, act], rforce[:, act]); e_vel = same(pa.vel, ra.vel); e_act = same(pa.active, ra.active); e_cnt = same(counters, rcount)
+        e_bvel = same(pb.vel, rb.vel); e_acc = same(acc_all, racc.cpu())
+        hits = int(round(float(racc.sum()) / 0.01)); deact = int(rcount[0])
+        ok = e_force and e_vel and e_act and e_cnt and e_bvel and e_acc and hits > 0 and deact > 0
+        print(f"[check_slabs] particle producers on slabs: world={world} particles={n_part} fluid forces: force={e_force} vel={e_vel} active={e_act} "
+              f"counters={e_cnt} (deactivated {deact}); filter interception: vel={e_bvel} accumulated={e_acc} ({hits} bounces)", flush=True)
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    return bool(flag.item())
+
+
 def main():
     rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -171,6 +240,8 @@ def main():
     ok &= run_particles(rank, world, local, nx, nzg, mk2, setup2, cfg)
     # a bed that stays planes away from every interface: the guarded calls skip the exchanges and must give the same answer
     ok &= run_particles(rank, world, local, nx, nzg, mk2, setup2, cfg, guard=True, z_hi=0.3 * (nzg / world), steps=8)
+
+    ok &= run_particle_producers(rank, world, local, nx, nzg, mk2, setup2, cfg)
 
     # ---- legacy solver (reference): FD-LES reads u across the interface ----------------------------------
     ok &= run_case("V60 compat=reference (water phase, FD-LES active)", rank, world, local, nx, nzg, 10,
