@@ -88,6 +88,11 @@ typedef struct {
                                  occupancy codes of the kernel `vec` selects, see csrc/lbm_step.cu) */
     float drive_max_force;    /* LBM_FEAT_DRIVE: clamp on |F| (PressureGradientDrive.MAX_PRESSURE_FORCE) ... */
     float drive_scale;        /* ... and the factor of the accumulation (1 in force mode, 0.5 in mixed mode) */
+    float mrt_magic;          /* compat = physical: 0 = BGK (one rate).  > 0 = multiple-relaxation-time collision in its two-rate
+                                 form: the even moments (density, stress: pair sums f_q + f_opp(q)) relax at 1/tau -- tau still sets
+                                 the viscosity, LES acts on it -- the odd moments (momentum flux: pair differences) at 1/tau_odd with
+                                 (tau - 1/2)(tau_odd - 1/2) = mrt_magic (3/16: exact wall location of halfway bounce-back, 1/4: most
+                                 stable).  The reference names MRT only in a docstring (legacy/lbm_solver.py:833). */
 } lbm_params;
 
 typedef struct {

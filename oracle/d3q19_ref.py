@@ -817,6 +817,7 @@ class PhysParams:
     porous: bool = False             # Guo-Zhao drag in filter-zone cells
     porous_darcy: float = 0.0        # nu/K          [1/ts]
     porous_forch: float = 0.0        # F_eps/sqrt(K) [1/lu]
+    mrt_magic: float = 0.0           # 0 = BGK; > 0: two-rate MRT, (tau - 1/2)(tau_odd - 1/2) = mrt_magic (include/lbm_b200.h)
 
 
 def equilibrium_phys(rho, ux, uy, uz, q: int):
@@ -977,6 +978,12 @@ def step_physical(g, p: PhysParams, solid=None, body_force=None, phase=None, fil
     with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
         omega = (one / tau).astype(F32)
     nom = F32(-1.0) * omega
+    omega_d, nom_d = omega, nom
+    if p.mrt_magic > 0.0:            # the pair differences (odd moments) relax at 1 / tau_odd
+        with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+            tau_d = _fma(F32(p.mrt_magic), (one / (tau + F32(-0.5))).astype(F32), half)
+            omega_d = (one / tau_d).astype(F32)
+        nom_d = F32(-1.0) * omega_d
     u_sq = _fma(uz, uz, _fma(uy, uy, ux * ux))
     base = _fma(F32(-1.5), u_sq, one)
     # "f - w rho (...)" is ONE fma with the negated prefactor: no product feeds an add / sub (lbm_phys.cuh header)
@@ -989,7 +996,8 @@ def step_physical(g, p: PhysParams, solid=None, body_force=None, phase=None, fil
         uF3 = F32(3.0) * _fma(uz, Fz, _fma(uy, Fy, ux * Fx))
         f0 = _fma((-W[0]) * pref, uF3, f0)
         c18 = (W1X18 * pref, W2X18 * pref)
-        c6 = (W1X6 * pref, W2X6 * pref)
+        pref_d = _fma(F32(-0.5), omega_d, one)
+        c6 = (W1X6 * pref_d, W2X6 * pref_d)
         nc2 = ((-W1X2) * pref, (-W2X2) * pref)
     out[0] = f0
     for k in range(9):
@@ -1001,7 +1009,7 @@ def step_physical(g, p: PhysParams, solid=None, body_force=None, phase=None, fil
         ns = _fma(nws1 if a == 0 else nws2, A, s[k])
         nd = _fma(nwd1 if a == 0 else nwd2, eu, d[k])
         sp = _fma(nom, ns, s[k])
-        dp = _fma(nom, nd, d[k])
+        dp = _fma(nom_d, nd, d[k])
         if forced:
             eF = _vedot(*e, Fx, Fy, Fz)
             sp = _fma(eu * eF, c18[a], sp)

@@ -29,7 +29,8 @@ class LbmParams(C.Structure):
                 ("cs_smag", C.c_float), ("tau_min", C.c_float), ("tau_max", C.c_float),
                 ("porous_darcy", C.c_float), ("porous_forch", C.c_float),
                 ("K_lu", C.c_float), ("beta_lu", C.c_float), ("c_darcy", C.c_float), ("c_forch", C.c_float),
-                ("vec", C.c_int), ("block", C.c_int), ("drive_max_force", C.c_float), ("drive_scale", C.c_float)]
+                ("vec", C.c_int), ("block", C.c_int), ("drive_max_force", C.c_float), ("drive_scale", C.c_float),
+                ("mrt_magic", C.c_float)]
 
 
 class LbmFields(C.Structure):

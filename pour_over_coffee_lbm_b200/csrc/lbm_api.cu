@@ -168,6 +168,10 @@ static bool tma_eligible_params(const lbm_ctx *ctx) {
 
 static int pick_vec(const lbm_ctx *ctx) {
     int vec = ctx->p.vec;
+    // the two-rate MRT collision is built into the one- and two-cell kernels only (lbm_phys.cuh:collide_phys)
+    const bool mrt = ctx->p.compat == LBM_COMPAT_PHYSICAL && ctx->p.mrt_magic > 0.0f;
+    if (mrt && phys_walls(ctx->p)) vec = (vec == 1) ? 1 : 2;
+    if (mrt && !phys_walls(ctx->p)) vec = 1;
     if (phys_walls(ctx->p)) {
         // four cells per thread on chord-fitted tiles (lbm_phys_chord.cuh) when rows are 16-byte multiples, else two cells per
         // thread on packed f32x2 registers (lbm_phys.cuh) on 8-byte rows, else one.  The TMA-staged kernel (LBM_TMA=1, works on
@@ -433,6 +437,7 @@ static int fill_args(lbm_ctx *ctx, const lbm_fields *f, StepArgs *a) {
     a->rho_src = f->rho_src; a->drive_max_force = p.drive_max_force; a->drive_scale = p.drive_scale;
     a->tau_water = p.tau_water; a->tau_air = p.tau_air; a->gravity_lu = p.gravity_lu;
     a->tau_min = p.tau_min; a->tau_max = p.tau_max;
+    a->mrt_magic = p.compat == LBM_COMPAT_PHYSICAL ? p.mrt_magic : 0.0f;
     if (p.compat == LBM_COMPAT_REFERENCE) a->les_k = (p.cs_smag * 1.0f) * (p.cs_smag * 1.0f);     // les_turbulence.py:369
     else a->les_k = (float)(18.0 * sqrt(2.0) * (double)p.cs_smag * (double)p.cs_smag);
     a->porous_darcy = p.porous_darcy; a->porous_forch = p.porous_forch;
@@ -625,6 +630,7 @@ int lbm_step(lbm_ctx *ctx, lbm_fields *f, int nsteps, int write_macro_every, voi
     if (ref_les && write_macro_every != 1) return fail(ctx, "compat=reference with LES needs u every step (write_macro_every must be 1)");
     if (ref_les && (!f->u_src || !f->u_dst || f->u_src == f->u_dst)) return fail(ctx, "compat=reference with LES needs distinct u_src/u_dst");
     const bool drive = (p.features & LBM_FEAT_DRIVE) != 0;
+    if (drive && p.mrt_magic > 0.0f) return fail(ctx, "LBM_FEAT_DRIVE is fused into the four-cell kernel, which is built for BGK only: run the MRT collision with the stand-alone pressure-gradient producer");
     if (drive && !(phys_walls(p) && vec == 4)) return fail(ctx, "LBM_FEAT_DRIVE is fused into the four-cell walls kernel of compat=physical (LBM_FEAT_WALLS, nx % 4 == 0, vec = 0 or 4)");
     if (drive && write_macro_every != 1) return fail(ctx, "LBM_FEAT_DRIVE reads the previous step's rho (write_macro_every must be 1)");
     if (drive && (!f->rho || !f->rho_src || f->rho == f->rho_src)) return fail(ctx, "LBM_FEAT_DRIVE needs distinct rho (written) and rho_src (previous step) fields");

@@ -51,6 +51,7 @@ struct StepArgs {
     int write_macro;
     float tau_water, tau_air, gravity_lu;
     float tau_min, tau_max;
+    float mrt_magic;       // physical: 0 = BGK, else (tau - 1/2)(tau_odd - 1/2) of the two-rate MRT collision
     float les_k;           // physical: 18*sqrt(2)*Cs^2 ; reference: (Cs*1)*(Cs*1)
     float porous_darcy, porous_forch;
     float K_lu, beta_lu, c_darcy, c_forch;

@@ -345,7 +345,7 @@ __device__ __forceinline__ void step_cells(const StepArgs &P, const int x0, cons
                 in.phase = FORCED ? ph[c] : 0.0f;
                 in.flag[0] = fl[c];
                 CellMacro<float> m;
-                collide_phys<float, FORCED, LES && COLLIDE, POROUS, COLLIDE>(fc, in, m, P, has_phase, has_force);
+                collide_phys<float, FORCED, LES && COLLIDE, POROUS, COLLIDE, false, true>(fc, in, m, P, has_phase, has_force);
                 if constexpr (COLLIDE) {
 #pragma unroll
                     for (int q = 0; q < Q; ++q) f[q][c] = fc[q];

@@ -37,7 +37,8 @@ class D3Q19Engine:
                  nz_global: Optional[int] = None, tau: Optional[float] = None, tau_air: Optional[float] = None,
                  gravity_lu: Optional[float] = None, cs_smag: Optional[float] = None,
                  porous_darcy: float = 0.0, porous_forch: float = 0.0, vec: int = 0, block: int = 0,
-                 macro_fields: bool = True, drive: bool = False, drive_max_force: float = 0.12, drive_scale: float = 1.0):
+                 macro_fields: bool = True, drive: bool = False, drive_max_force: float = 0.12, drive_scale: float = 1.0,
+                 mrt_magic: float = 0.0):
         if not torch.cuda.is_available():
             raise BackendInitializationError(
                 "no CUDA device visible: pour_over_coffee_lbm_b200 runs on B200 (sm_100a) only, there is no CPU fallback",
@@ -75,7 +76,7 @@ class D3Q19Engine:
             cs_smag=self.cfg.LES_CS if cs_smag is None else cs_smag, tau_min=0.55, tau_max=1.90,
             porous_darcy=porous_darcy, porous_forch=porous_forch,
             K_lu=k_lu, beta_lu=beta_lu, c_darcy=c_darcy, c_forch=c_forch, vec=vec, block=block,
-            drive_max_force=drive_max_force, drive_scale=drive_scale)
+            drive_max_force=drive_max_force, drive_scale=drive_scale, mrt_magic=mrt_magic)
         self._ctx = C.c_void_p()
         rc = self.lib.lbm_create(C.byref(self._ctx), device, C.byref(self.params))
         if rc != 0:

@@ -46,7 +46,7 @@ static void run(int nx, int ny, int nz, const float *g, float *g_out, float *rho
                 CellMacro<float> m;
                 const bool has_phase = FORCED && phase != nullptr;
                 const bool has_force = FORCED && (force != nullptr || (has_phase && P.gravity_lu != 0.0f));
-                collide_phys<float, FORCED, LES, POROUS, true>(f, in, m, P, has_phase, has_force);
+                collide_phys<float, FORCED, LES, POROUS, true, false, true>(f, in, m, P, has_phase, has_force);
                 for (int q = 0; q < Q; ++q) g_out[q * vol + c] = f[q];
                 rho[c] = m.rho; u[c] = m.ux; u[vol + c] = m.uy; u[2 * vol + c] = m.uz;
             }
@@ -54,9 +54,9 @@ static void run(int nx, int ny, int nz, const float *g, float *g_out, float *rho
 
 extern "C" int emu_collide_periodic(int nx, int ny, int nz, const float *g, float *g_out, float *rho, float *u, const float *force,
                                     const float *phase, const uint8_t *flags, int les, int porous, float tau_water, float tau_air, float gravity_lu,
-                                    float cs_smag, float tau_min, float tau_max, float porous_darcy, float porous_forch) {
+                                    float cs_smag, float tau_min, float tau_max, float porous_darcy, float porous_forch, float mrt_magic) {
     StepArgs P{};
-    P.tau_water = tau_water; P.tau_air = tau_air; P.gravity_lu = gravity_lu; P.tau_min = tau_min; P.tau_max = tau_max;
+    P.tau_water = tau_water; P.tau_air = tau_air; P.gravity_lu = gravity_lu; P.tau_min = tau_min; P.tau_max = tau_max; P.mrt_magic = mrt_magic;
     P.les_k = (float)(18.0 * sqrt(2.0) * (double)cs_smag * (double)cs_smag);          // as lbm_api.cu forms it
     P.porous_darcy = porous_darcy; P.porous_forch = porous_forch;
     const bool forced = force != nullptr || phase != nullptr;

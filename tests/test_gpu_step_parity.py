@@ -186,6 +186,65 @@ def test_physical_walls_obstacles_open_and_periodic_faces(periodic, nx, path, mo
     assert np.array_equal(H.from_dev_vec(eng.u)[fluid], u1[fluid])
 
 
+@pytest.mark.parametrize("case", ["periodic_dense", "v60_all_features", "ragged_obstacles"])
+def test_physical_mrt_two_rate_collision_bit_exact(case):
+    """lbm_params.mrt_magic > 0: the multiple-relaxation-time collision in its two-rate form (pair sums at 1 / tau, pair differences
+    at 1 / tau_odd, (tau - 1/2)(tau_odd - 1/2) = magic; Guo forcing split the same way) against oracle.step_physical with the same
+    parameter -- dense periodic box, the V60 box with LES + forcing + porous drag + bounce-back, a ragged box with obstacles on open
+    faces.  The library runs it on the one- / two-cell kernels (lbm_api.cu:pick_vec); magic = 0 stays the BGK path of every other test."""
+    magic = 0.1875
+    rng = np.random.default_rng(17)
+    if case == "periodic_dense":
+        n, steps = 24, 20
+        u0 = H.smooth_velocity(n, 0.04, 3); rho0 = H.smooth_density(n, 0.01, 3)
+        p = R.PhysParams(nx=n, ny=n, nz=n, tau_water=0.56, les=True, mrt_magic=magic)
+        g = R.init_equilibrium_phys(rho0, u0)
+        for _ in range(steps):
+            g, rho, u = R.step_physical(g, p)
+        eng = _engine(n, n, n, compat="physical", les=True, tau=0.56, mrt_magic=magic)
+        eng.init_equilibrium(rho=_torch(H.to_dev_scalar(rho0)), u=_torch(H.to_dev_vec(u0)))
+        eng.step(steps)
+        assert np.array_equal(H.from_dev_pop(eng.populations), g)
+        assert np.array_equal(H.from_dev_scalar(eng.rho), rho) and np.array_equal(H.from_dev_vec(eng.u), u)
+        # and it is not BGK: the same run with magic = 0 differs
+        bgk = _engine(n, n, n, compat="physical", les=True, tau=0.56)
+        bgk.init_equilibrium(rho=_torch(H.to_dev_scalar(rho0)), u=_torch(H.to_dev_vec(u0)))
+        bgk.step(steps)
+        assert not np.array_equal(H.from_dev_pop(bgk.populations), g)
+        return
+    if case == "v60_all_features":
+        nx = ny = nz = 32
+        cfg = R.RefConfig(NX=nx, NY=ny, NZ=nz)
+        solid = R.v60_solid(cfg); zone = R.filter_zones(cfg)
+        periodic = (False, False, False)
+    else:
+        nx, ny, nz = 30, 22, 14
+        solid = (rng.random((nx, ny, nz)) < 0.12).astype(np.uint8)
+        solid[0:2, 3:9, :] = 1; solid[nx - 1, :, 2:5] = 1; solid[:, 0, 6:9] = 1; solid[5:9, 5:9, 0] = 1
+        zone = (rng.random((nx, ny, nz)) < 0.1).astype(np.int32)
+        periodic = (True, False, False)
+    steps = 15
+    les_mask = (rng.random((nx, ny, nz)) < 0.8).astype(np.int32)
+    phase = (rng.random((nx, ny, nz)) < 0.5).astype(np.float32)
+    bf = (2e-5 * rng.standard_normal((nx, ny, nz, 3))).astype(np.float32)
+    u0 = H.smooth_velocity(nx, 0.02, 4, nz=nz, ny=ny); rho0 = H.smooth_density(nx, 0.01, 4, nz=nz, ny=ny)
+    p = R.PhysParams(nx=nx, ny=ny, nz=nz, tau_water=0.56, tau_air=0.8, gravity_lu=2e-5, periodic=periodic, use_force=True, use_phase=True,
+                     les=True, porous=True, porous_darcy=0.2, porous_forch=0.5, mrt_magic=magic)
+    g = R.init_equilibrium_phys(rho0, u0)
+    for _ in range(steps):
+        g, rho, u = R.step_physical(g, p, solid=solid, body_force=bf, phase=phase, filter_zone=zone, les_mask=les_mask)
+    eng = _engine(nx, ny, nz, compat="physical", periodic=periodic, walls=True, force=True, phase=True, les=True, porous=True, tau=0.56,
+                  tau_air=0.8, gravity_lu=2e-5, porous_darcy=0.2, porous_forch=0.5, mrt_magic=magic)
+    eng.solid.copy_(_torch(H.to_dev_scalar(solid))); eng.filter_zone.copy_(_torch(H.to_dev_scalar(np.asarray(zone, np.int32))))
+    eng.les_mask.copy_(_torch(H.to_dev_scalar(les_mask))); eng.pack_flags()
+    eng.phase.copy_(_torch(H.to_dev_scalar(phase))); eng.body_force.copy_(_torch(H.to_dev_vec(bf)))
+    eng.init_equilibrium(rho=_torch(H.to_dev_scalar(rho0)), u=_torch(H.to_dev_vec(u0)))
+    eng.step(steps)
+    fluid = np.asarray(solid) == 0
+    assert np.array_equal(H.from_dev_pop(eng.populations)[:, fluid], g[:, fluid])
+    assert np.array_equal(H.from_dev_scalar(eng.rho)[fluid], rho[fluid]) and np.array_equal(H.from_dev_vec(eng.u)[fluid], u[fluid])
+
+
 def test_physical_walls_direct_population_write_needs_notification():
     """Solid-cell slots of g are bounce-back scratch: after a direct write of the population buffer the caller
     announces it (lbm_populations_changed) and the library rebuilds the slots before the next step."""
