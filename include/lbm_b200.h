@@ -184,6 +184,11 @@ int  lbm_pressure_gradient_force(lbm_ctx *ctx, const float *rho, const uint8_t *
  * producer of the step, and saves the full-grid clear pass. */
 int  lbm_pressure_gradient_force_set(lbm_ctx *ctx, const float *rho, const uint8_t *flags, float *body_force,
                                      float max_force, float scale, void *stream);
+/* PressureGradientDrive.apply_density_drive pressure_gradient_drive.py:95-122 ("method A"): rho of every fluid cell moves towards
+ * the target profile by rate * (target - rho), at most max_adjust per call, clamped to [rho_min, rho_max].  target_z: device
+ * array, one value per z plane of the slab incl. ghost planes (the reference's target_density depends on z only, :54-72). */
+int  lbm_density_drive(lbm_ctx *ctx, float *rho, const uint8_t *flags, const float *target_z, float rate, float max_adjust,
+                       float rho_min, float rho_max, void *stream);
 /* FilterPaperSystem.compute_forchheimer_resistance filter_paper.py:471-536: body_force += F_drag. */
 int  lbm_forchheimer_force(lbm_ctx *ctx, const float *u, const uint8_t *flags, float *body_force,
                            float fmax, void *stream);

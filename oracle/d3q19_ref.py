@@ -513,6 +513,25 @@ def compute_forchheimer_resistance(st: State, scale_velocity: float = 0.01) -> N
         st.body_force[c + (comp,)] = np.where(sel, cur + np.where(big, r * s, r), cur)
 
 
+def density_drive_target(nz: int) -> np.ndarray:
+    """PressureGradientDrive.initialize_target_density, pressure_gradient_drive.py:54-72: the profile along z (the field does not
+    depend on i, j).  f32; expressions of Python floats fold in f64 before they meet a kernel value (Taichi's constant folding)."""
+    zr = np.arange(nz, dtype=F32) / F32(nz)
+    hi = F32(1.0) + ((zr - F32(0.8)) / F32(1.0 - 0.8)) * F32(1.8 - 1.0)
+    lo = F32(0.4) + (zr / F32(0.2)) * F32(1.0 - 0.4)
+    return np.where(zr >= F32(0.8), hi, np.where(zr <= F32(0.2), lo, F32(1.0))).astype(F32)
+
+
+def density_drive(rho: np.ndarray, solid: np.ndarray, target_z: np.ndarray, rate: float = 0.025, max_adjust: float = 0.001,
+                  rho_min: float = 0.5, rho_max: float = 2.0) -> np.ndarray:
+    """PressureGradientDrive.apply_density_drive, pressure_gradient_drive.py:95-122 (method A), one call.  rho [NX,NY,NZ]."""
+    diff = target_z[None, None, :].astype(F32) - rho
+    adj = diff * F32(rate)
+    adj = np.where(np.abs(adj) > F32(max_adjust), np.where(adj > 0, F32(max_adjust), F32(-max_adjust)), adj).astype(F32)
+    new = np.maximum(F32(rho_min), np.minimum(F32(rho_max), rho + adj)).astype(F32)
+    return np.where(solid == 0, new, rho).astype(F32)
+
+
 def pressure_gradient_force(st: State, max_force: float = 0.12) -> np.ndarray:
     """PressureGradientDrive.compute_pressure_gradient, pressure_gradient_drive.py:124-177.
     Returns pressure_force [NX,NY,NZ,3] (zero on solid cells, which the reference leaves untouched)."""

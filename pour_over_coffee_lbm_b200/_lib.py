@@ -76,6 +76,7 @@ SIGNATURES = {
     "lbm_pressure_gradient_force": (C.c_int, [_P, _P, _P, _P, C.c_float, C.c_float, _P]),
     "lbm_pressure_gradient_force_set": (C.c_int, [_P, _P, _P, _P, C.c_float, C.c_float, _P]),
     "lbm_forchheimer_force": (C.c_int, [_P, _P, _P, _P, C.c_float, _P]),
+    "lbm_density_drive": (C.c_int, [_P, _P, _P, _P, C.c_float, C.c_float, C.c_float, C.c_float, _P]),
     "lbm_field_statistics": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "lbm_add_reaction_force": (C.c_int, [_P, _P, _P, _P, _P]),
     "lbm_surface_tension": (C.c_int, [_P] * 11 + [C.c_float, _P]),

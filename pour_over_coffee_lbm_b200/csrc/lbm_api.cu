@@ -29,6 +29,7 @@ cudaError_t launch_face_bc(const Grid &, float *, const uint8_t *, cudaStream_t,
 cudaError_t launch_pressure_gradient(const Grid &, const float *, const uint8_t *, float *, float, float, int, const unsigned *, const unsigned long long *, int, int,
                                      cudaStream_t);
 cudaError_t launch_forchheimer_force(const Grid &, const float *, const uint8_t *, float *, float, float, float, float, float, cudaStream_t);
+cudaError_t launch_density_drive(const Grid &, float *, const uint8_t *, const float *, float, float, float, float, cudaStream_t);
 cudaError_t launch_add_reaction(const Grid &, const float *, const uint8_t *, float *, cudaStream_t);
 cudaError_t run_selftest_math(unsigned long long[7], const StepArgs &, cudaStream_t);
 cudaError_t launch_field_statistics(const Grid &, const float *, const float *, const uint8_t *, void *, int, double *, cudaStream_t);
@@ -768,6 +769,15 @@ int lbm_forchheimer_force(lbm_ctx *ctx, const float *u, const uint8_t *flags, fl
     cudaSetDevice(ctx->device);      // launches follow the context's device, whatever the caller's current device is
     const lbm_params &p = ctx->p;
     CUDA_OK(ctx, launch_forchheimer_force(ctx->g, u, flags, body_force, p.K_lu, p.beta_lu, p.c_darcy, p.c_forch, fmax, (cudaStream_t)stream));
+    ctx->launches++;
+    return 0;
+}
+
+int lbm_density_drive(lbm_ctx *ctx, float *rho, const uint8_t *flags, const float *target_z, float rate, float max_adjust, float rho_min,
+                      float rho_max, void *stream) {
+    if (!ctx || !rho || !flags || !target_z) return fail(ctx, "null argument");
+    cudaSetDevice(ctx->device);      // launches follow the context's device, whatever the caller's current device is
+    CUDA_OK(ctx, launch_density_drive(ctx->g, rho, flags, target_z, rate, max_adjust, rho_min, rho_max, (cudaStream_t)stream));
     ctx->launches++;
     return 0;
 }

@@ -411,6 +411,39 @@ cudaError_t build_work_lists(const Grid &G, const uint8_t *flags, int vec, int t
 }
 #endif
 
+// ---- PressureGradientDrive.apply_density_drive (pressure_gradient_drive.py:95-122, "method A") ---------------------------
+// rho of every fluid cell moves towards the target profile of its z plane by rate * (target - rho), at most max_adjust per
+// call, and is clamped to [rho_min, rho_max].  f32, the reference's statement order.  Four x-consecutive cells per thread on
+// 128-bit loads / stores when rows are 16-byte multiples (VEC = 4), else one.  target_z: one value per plane, ghost planes included.
+template <int VEC>
+__global__ void density_drive_kernel(Grid G, float *rho, const uint8_t *flags, const float *target_z, float rate, float max_adjust,
+                                     float rho_min, float rho_max) {
+    const long long n = (long long)G.nz * G.plane / VEC;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long c = (long long)G.zg * G.plane + i * VEC;
+        const float target = target_z[c / G.plane];
+        float r[VEC]; uint8_t fl[VEC];
+        if (VEC == 4) {
+            const float4 v = *reinterpret_cast<const float4 *>(rho + c);
+            const uchar4 f = *reinterpret_cast<const uchar4 *>(flags + c);
+            r[0] = v.x; r[VEC > 1 ? 1 : 0] = v.y; r[VEC > 2 ? 2 : 0] = v.z; r[VEC > 3 ? 3 : 0] = v.w;
+            fl[0] = f.x; fl[VEC > 1 ? 1 : 0] = f.y; fl[VEC > 2 ? 2 : 0] = f.z; fl[VEC > 3 ? 3 : 0] = f.w;
+        } else { r[0] = rho[c]; fl[0] = flags[c]; }
+        bool any = false;
+        for (int k = 0; k < VEC; ++k) {
+            if (fl[k] & LBM_FLAG_SOLID) continue;
+            const float diff = target - r[k];
+            float adj = diff * rate;
+            if (fabsf(adj) > max_adjust) adj = adj > 0.0f ? max_adjust : -max_adjust;
+            r[k] = fmaxf(rho_min, fminf(rho_max, r[k] + adj));
+            any = true;
+        }
+        if (!any) continue;
+        if (VEC == 4) *reinterpret_cast<float4 *>(rho + c) = make_float4(r[0], r[VEC > 1 ? 1 : 0], r[VEC > 2 ? 2 : 0], r[VEC > 3 ? 3 : 0]);
+        else rho[c] = r[0];
+    }
+}
+
 // ---- packed quad list and wall links of the four-cell walls kernel (lbm_phys_chord.cuh) --------------------------
 // A "quad" is 4 x-consecutive cells on a 16-byte boundary.  It is active when it or the other quad of its 32-byte sector holds a
 // fluid cell: the kernel stores whole quads, so both halves of every sector it touches are written and no sector reaches DRAM half
@@ -869,6 +902,13 @@ cudaError_t launch_pressure_gradient(const Grid &G, const float *rho, const uint
     const int b = G.nx >= 128 ? 128 : 64;
     const dim3 grid((unsigned)((G.nx + b - 1) / b), (unsigned)G.ny, (unsigned)G.nz);
     pressure_gradient_kernel<<<grid, b, 0, s>>>(G, rho, flags, bf, max_force, scale, accumulate);
+    return cudaGetLastError();
+}
+cudaError_t launch_density_drive(const Grid &G, float *rho, const uint8_t *flags, const float *target_z, float rate, float max_adjust,
+                                 float rho_min, float rho_max, cudaStream_t s) {
+    const int b = 256;
+    if (G.nx % 4 == 0) density_drive_kernel<4><<<grid_for((long long)G.nz * G.plane / 4, b), b, 0, s>>>(G, rho, flags, target_z, rate, max_adjust, rho_min, rho_max);
+    else density_drive_kernel<1><<<grid_for((long long)G.nz * G.plane, b), b, 0, s>>>(G, rho, flags, target_z, rate, max_adjust, rho_min, rho_max);
     return cudaGetLastError();
 }
 cudaError_t launch_forchheimer_force(const Grid &G, const float *u, const uint8_t *flags, float *bf, float K, float beta,

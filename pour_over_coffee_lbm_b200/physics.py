@@ -215,6 +215,7 @@ class PressureGradientDrive:
     def __init__(self, lbm_solver: Any):
         self.lbm = lbm_solver
         self.MAX_PRESSURE_FORCE = 0.12           # pressure_gradient_drive.py:30 (host-mutable, main.py:913-925)
+        self.ADJUSTMENT_RATE = 0.025             # :27
         self.force_drive_active = False
         self.mixed_drive_active = False
         self.density_drive_active = False
@@ -252,27 +253,41 @@ class PressureGradientDrive:
 
     def initialize_target_density(self):
         """pressure_gradient_drive.py:54-72: z profile 0.4 -> 1 over the bottom 20 %, 1 in the middle, 1 -> 1.8 over the top
-        20 % (global z)."""
+        20 % (global z).  f32 with the reference's constant folding: expressions of Python floats (1.0 - 0.8, 1.8 - 1.0, ...) fold
+        in f64 and are rounded to f32 when they meet a kernel value.  One value per plane of the slab, ghost planes included."""
         e = self.lbm.engine
         f = np.float32
         k = np.arange(e.z0 - e.zghost, e.z0 + e.nz + e.zghost, dtype=np.float32)
         zr = k / f(e.nz_global)
-        hi = f(1.0) + ((zr - f(0.8)) / (f(1.0) - f(0.8))) * (f(1.8) - f(1.0))
-        lo = f(0.4) + (zr / f(0.2)) * (f(1.0) - f(0.4))
+        hi = f(1.0) + ((zr - f(0.8)) / f(1.0 - 0.8)) * f(1.8 - 1.0)
+        lo = f(0.4) + (zr / f(0.2)) * f(1.0 - 0.4)
         prof = np.where(zr >= f(0.8), hi, np.where(zr <= f(0.2), lo, f(1.0))).astype(np.float32)
-        self._target_density = torch.from_numpy(prof).to(e.device)[:, None, None].expand(-1, e.ny, e.nx)
+        self._target_profile = torch.from_numpy(prof).to(e.device)
+        self._target_density = self._target_profile[:, None, None].expand(-1, e.ny, e.nx)
+
+    @property
+    def target_density(self):
+        """the reference's target_density field (logical [i, j, k] order, owned planes)"""
+        if getattr(self, "_target_profile", None) is None:
+            self.initialize_target_density()
+        e = self.lbm.engine
+        if getattr(self, "_target_field", None) is None:
+            self._target_full = self._target_profile[:, None, None].expand(-1, e.ny, e.nx).contiguous()
+            self._target_field = ScalarField(lambda: self._target_full, e.zghost)
+        return self._target_field
 
     def apply_density_drive(self):
-        """pressure_gradient_drive.py:95-122 (method A): nudges rho toward the target profile by at most 0.001 per call,
-        clamped to [0.5, 2].  LBMSolver recomputes rho from f before it is used, so this is cosmetic there."""
+        """pressure_gradient_drive.py:95-122 (method A, lbm_density_drive): nudges rho toward the target profile by 0.025 of the
+        difference, at most 0.001 per call, clamped to [0.5, 2].  LBMSolver recomputes rho from f before it is used, so this is
+        cosmetic there; bit-exact against the recorded reference run (tests/test_gpu_geometry_particles.py)."""
         if not self.density_drive_active:
             return
         e = self.lbm.engine
-        if getattr(self, "_target_density", None) is None:
+        if getattr(self, "_target_profile", None) is None:
             self.initialize_target_density()
-        adj = torch.clamp((self._target_density - e.rho) * 0.025, -0.001, 0.001)
-        new = torch.clamp(e.rho + adj, 0.5, 2.0)
-        e.rho.copy_(torch.where(e.solid == 0, new, e.rho) if e.solid is not None else new)
+        self.lbm._sync_flags()
+        e._check(e.lib.lbm_density_drive(e._ctx, _ptr(e.rho), _ptr(e.flags), _ptr(self._target_profile), float(np.float32(self.ADJUSTMENT_RATE)),
+                                         0.001, 0.5, 2.0, e.stream), "lbm_density_drive")
 
     def apply(self, step: int = 0):
         """pressure_gradient_drive.py:257-272"""

@@ -522,6 +522,29 @@ if __name__ == "__main__":
               " moving particles:", int((res["p_reynolds"] > 0).sum()), " max|reaction|", float(np.abs(res["p_reaction"]).max()))
         np.savez_compressed(os.path.join(HERE, "reference_run_coupled.npz"), **res)
         sys.exit(0 if all(ok.values()) else 1)
+    if len(sys.argv) > 2 and sys.argv[2] == "density_drive":
+        # PressureGradientDrive method A (pressure_gradient_drive.py:54-122): the target profile and three nudges of rho
+        with quiet():
+            from src.core.legacy.lbm_solver import LBMSolver
+            from src.physics.filter_paper import FilterPaperSystem
+            from src.physics.pressure_gradient_drive import PressureGradientDrive
+            s = LBMSolver(); s.init_fields()
+            fp = FilterPaperSystem(s); fp.initialize_filter_geometry()
+            pg = PressureGradientDrive(s)
+        rng = np.random.default_rng(53)
+        rho = (1.0 + 0.6 * rng.standard_normal((n, n, n))).astype(np.float32)      # well outside [0.5, 2] in places
+        rho[::5, ::3, ::2] = (1.0 + 1e-3 * rng.standard_normal(rho[::5, ::3, ::2].shape)).astype(np.float32)   # and inside the 0.001 band
+        s.rho.from_numpy(rho)
+        res = dict(n=n, rho=rho, solid=s.solid.to_numpy().astype(np.uint8), target=pg.target_density.to_numpy())
+        with quiet():
+            pg.activate_density_drive(True)
+            for t in range(3):
+                pg.apply(t)
+                res[f"rho_after_{t + 1}"] = s.rho.to_numpy()
+        changed = int((res["rho_after_3"] != rho).sum())
+        print("[reference run] density drive: cells changed", changed, "of", rho.size, " target profile", res["target"][0, 0, :])
+        np.savez_compressed(os.path.join(HERE, "reference_run_density_drive.npz"), **res)
+        sys.exit(0 if changed > 0 else 1)
     if len(sys.argv) > 2 and sys.argv[2] == "producers":
         res = run_multiphase_scenario(config, n, seed=43)
         ok = check_multiphase_against_oracle(res)

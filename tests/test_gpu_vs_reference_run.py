@@ -144,3 +144,22 @@ def test_neighbour_kernels_reproduce_the_reference_run():
         assert np.array_equal(ps.pos.cpu().numpy().T[a], z[f"adv{t}_pos"][a])
         assert np.array_equal(ps.vel.cpu().numpy().T[a], z[f"adv{t}_vel"][a], equal_nan=True)
     assert counters.cpu().tolist() == [int(v) for v in z["adv_counters"]]
+
+
+def test_density_drive_reproduces_the_reference_run():
+    """lbm_density_drive through the PressureGradientDrive facade (apply() in density mode, three calls) against the recorded run of
+    the reference's PressureGradientDrive method A: target profile and rho after every call, bit for bit."""
+    from pour_over_coffee_lbm_b200.solver import LBMSolver
+    from pour_over_coffee_lbm_b200.physics import PressureGradientDrive
+    z = np.load(os.path.join(GOLD, "reference_run_density_drive.npz"))
+    n = int(z["n"])
+    s = LBMSolver(config=_cfg(n, R.RefConfig().GRAVITY_LU)); s.init_fields()
+    s.engine.build_v60_geometry()
+    assert np.array_equal(H.from_dev_scalar(s.engine.solid), z["solid"])
+    pg = PressureGradientDrive(s)
+    assert np.array_equal(pg.target_density.to_numpy(), z["target"])
+    s.rho.from_numpy(z["rho"])
+    pg.activate_density_drive(True)
+    for t in range(3):
+        pg.apply(t)
+        assert np.array_equal(s.rho.to_numpy(), z[f"rho_after_{t + 1}"])

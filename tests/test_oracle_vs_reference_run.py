@@ -131,3 +131,17 @@ def test_oracle_neighbour_kernels_reproduce_the_reference_run():
         assert np.array_equal(active, z[f"adv{t}_active"])
         assert np.array_equal(pos[a], z[f"adv{t}_pos"][a]) and np.array_equal(vel[a], z[f"adv{t}_vel"][a], equal_nan=True)
     assert tot == [int(v) for v in z["adv_counters"]] and tot[1] > 0
+
+
+def test_density_drive_reproduces_the_reference_run():
+    """PressureGradientDrive method A (target profile + three nudges of rho, pressure_gradient_drive.py:54-122) recorded from the
+    reference's own source (make_reference_goldens.py 16 density_drive): oracle restatement bit for bit."""
+    z = np.load(os.path.join(GOLD, "reference_run_density_drive.npz"))
+    n = int(z["n"])
+    target = R.density_drive_target(n)
+    assert np.array_equal(z["target"], np.broadcast_to(target[None, None, :], (n, n, n)))
+    rho = z["rho"]
+    for t in range(3):
+        rho = R.density_drive(rho, z["solid"], target)
+        assert np.array_equal(rho, z[f"rho_after_{t + 1}"])
+    assert (rho != z["rho"]).sum() > 100
