@@ -44,6 +44,7 @@ METRIC = "MLUPS (D3Q19 fused step)"
 # force explicitly; at the reference's scale 1 the V60 state is non-finite within 200 steps, at 0.5 within 400, at <= 0.1 it is stable
 # for thousands (profiles/r02_exp_drive_stability.log).  The benchmark runs the drive at 0.1: same kernel, same arithmetic, finite state
 # (a non-finite state sends the packed reciprocal / square root down their scalar fall-backs and times those instead).
+CHORD_END_COST = float(os.environ.get('LBM_BENCH_CHORD_END_COST', '16'))      # slab cuts by kernel cost, not by fluid count (engine.v60_fluid_cells_per_plane)
 DRIVE_MAX_FORCE, DRIVE_SCALE = 0.12, 0.1
 
 
@@ -437,8 +438,9 @@ def run_single(args, local):
         "config": {"workload": f"BASELINE configs[2]: V60 geometry {n}^3, D3Q19 + Smagorinsky LES + Guo force (gravity*phase + pressure-gradient drive) + "
                                "filter-paper porous drag + halfway bounce-back, rho,u written every step",
                    "grid": [n, n, n], "fluid_cells": fluid, "MFLUPS": headline["MFLUPS"], "compat": "physical",
-                   "kernel": "phys_chord_kernel<FORCED,LES,POROUS,DRIVE>: chord-fitted 128-cell tiles, cp.async-staged populations, packed f32x2 collision, "
-                             "wall-link bounce-back, fused drive; explicitly rounded (one build, bit-exact vs the oracle)",
+                   "kernel": "phys_chord_kernel<FORCED,LES,POROUS,DRIVE>: packed list of active quads (32 per warp), cp.async-staged populations, packed f32x2 "
+                             "collision (one copy in the instruction cache), halfway bounce-back through a per-link value buffer, whole-quad stores, "
+                             "fused drive; explicitly rounded (one build, bit-exact vs the oracle)",
                    "cache": "working set 27 GB >> 126 MB L2 (inputs larger than L2, no flush needed)",
                    "timing": f"median of {head['blocks']} blocks of {args.steps} steps (min {head['ms_min']:.4f} / max {head['ms_max']:.4f} ms per step)",
                    "drive": {"max_force": DRIVE_MAX_FORCE, "scale": DRIVE_SCALE, "why": "scale 1 of the explicit lagged-density drive is unstable in compat = physical"},
@@ -549,7 +551,7 @@ def slab_parity_check(world, rank, local, n=64, steps=12):
     from pour_over_coffee_lbm_b200.engine import v60_fluid_cells_per_plane
     from pour_over_coffee_lbm_b200.config import LBMConfig
     cfg = LBMConfig(NX=n, NY=n, NZ=n, GRAVITY_LU=1e-5)
-    part = slab.partition_z_balanced(v60_fluid_cells_per_plane(cfg, local), world, min_planes=3)[rank]
+    part = slab.partition_z_balanced(v60_fluid_cells_per_plane(cfg, local, chord_end_cost=CHORD_END_COST), world, min_planes=3)[rank]
     # one global random state, cut per rank: the per-slab generator of v60_engine would differ from the whole-box run
     g = torch.Generator(device="cuda"); g.manual_seed(777)
     u_all = 1e-3 * torch.randn((3, n, n, n), device="cuda", generator=g)
@@ -592,7 +594,7 @@ def run_multi(args, world, rank, local):
     # ---- headline: configs[4], V60 1024^3 + particles on fluid-balanced z-slabs ----------------------------------
     n = args.size_multi
     cfg = LBMConfig(NX=n, NY=n, NZ=n, GRAVITY_LU=1e-5)
-    part = slab.partition_z_balanced(v60_fluid_cells_per_plane(cfg, local), world, min_planes=3)[rank]
+    part = slab.partition_z_balanced(v60_fluid_cells_per_plane(cfg, local, chord_end_cost=CHORD_END_COST), world, min_planes=3)[rank]
     torch.cuda.empty_cache()
     eng = v60_engine(n, nz_global=n, z0=part.z0, nz=part.nz, zghost=1, device=local, drive=True, force=True, vec=args.vec)
     eng.attach_process_group()
