@@ -25,6 +25,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import datetime
 import os
 import statistics
 import subprocess
@@ -161,9 +162,20 @@ class Timer:
         """run(k) enqueues k steps.  Returns dict(ms_per_step, ms_min, ms_max, blocks, steps_per_block)."""
         import torch
         run(max(warmup, 3))
-        # clock ramp: a B200 coming from idle needs ~100 ms under load before it boosts
+        # clock ramp: a B200 coming from idle needs ~100 ms under load before it boosts.  The number of calls is agreed between the
+        # ranks (rank 0 times one call and broadcasts the count): `run` may contain collectives -- the particle coupling on slabs
+        # all-reduces on every n-th call -- and a loop bounded by each rank's own wall clock lets the ranks drift apart in call count
+        # until one of them waits in a collective the others never enter.
+        self.barrier()
         t0 = time.perf_counter()
-        while time.perf_counter() - t0 < 0.25:
+        run(max(1, steps)); torch.cuda.synchronize()
+        reps = int(min(200, max(1, np.ceil(0.25 / max(time.perf_counter() - t0, 1e-4)))))
+        if self.world > 1:
+            import torch.distributed as dist
+            nr = torch.tensor([reps], dtype=torch.int64, device="cuda")
+            dist.broadcast(nr, src=0)
+            reps = int(nr.item())
+        for _ in range(reps):
             run(max(1, steps)); torch.cuda.synchronize()
         first = self._block(run, steps)
         blocks = int(min(self.max_blocks, max(3, np.ceil(self.min_seconds * 1e3 / max(first, 1e-3)))))
@@ -585,7 +597,7 @@ def run_multi(args, world, rank, local):
     from pour_over_coffee_lbm_b200 import slab
     from pour_over_coffee_lbm_b200.config import LBMConfig
     from pour_over_coffee_lbm_b200.engine import D3Q19Engine, particles_couple_slab, v60_fluid_cells_per_plane
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=150))      # a mismatched collective aborts in minutes, not in ten
     timer = Timer(world)
     peak, peak_src = measured_peak()
     sampler = ClockSampler(local) if rank == 0 else None

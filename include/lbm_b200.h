@@ -280,6 +280,12 @@ int  lbm_particles_couple(lbm_ctx *ctx, const float *u, float *reaction, lbm_par
  * and nothing else writes it; ps->cell is not modified between calls.  On z-slabs the interface planes are cleared whole. */
 int  lbm_particles_couple_sparse(lbm_ctx *ctx, const float *u, float *reaction, lbm_particles *ps,
                                  float water_density, float water_viscosity, float relax, void *stream);
+/* lbm_particles_couple_sparse for z-slabs with a say on the interface planes: they only have to be cleared whole when a neighbour's
+ * deposits were added to them since the last call (slab.reduce_ghost_up); while the bed stays away from the cuts -- the interface
+ * guard of engine.particles_couple_slab -- clear_interface_planes = 0 saves six plane-sized memsets per call.  The kernel itself
+ * skips particles whose base cell lies in another slab (replicated particles, owner computes), so `active` needs no masking. */
+int  lbm_particles_couple_slab(lbm_ctx *ctx, const float *u, float *reaction, lbm_particles *ps,
+                               float water_density, float water_viscosity, float relax, int clear_interface_planes, void *stream);
 
 /* CoffeeParticleSystem.apply_under_relaxation coffee_particles.py:1200-1212 as a separate call
  * (lbm_particles_couple fuses it when relax >= 0; pass relax < 0 there to skip). */

@@ -91,6 +91,7 @@ SIGNATURES = {
     "lbm_pouring_phase_change": (C.c_int, [_P, C.POINTER(LbmPour), _P, _P, _P]),
     "lbm_particles_couple": (C.c_int, [_P, _P, _P, C.POINTER(LbmParticles), C.c_float, C.c_float, C.c_float, _P]),
     "lbm_particles_couple_sparse": (C.c_int, [_P, _P, _P, C.POINTER(LbmParticles), C.c_float, C.c_float, C.c_float, _P]),
+    "lbm_particles_couple_slab": (C.c_int, [_P, _P, _P, C.POINTER(LbmParticles), C.c_float, C.c_float, C.c_float, C.c_int, _P]),
     "lbm_particles_under_relax": (C.c_int, [_P, C.POINTER(LbmParticles), C.c_float, _P]),
     "lbm_particles_advance": (C.c_int, [_P, C.POINTER(LbmParticles), _P, C.POINTER(LbmParticleBounds), C.c_float, _P, _P]),
     "lbm_particles_fluid_forces": (C.c_int, [_P, _P, C.POINTER(LbmParticles), _P, C.c_double, C.c_double, C.c_double, _P, _P]),

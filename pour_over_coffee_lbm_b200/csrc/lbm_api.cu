@@ -935,12 +935,17 @@ int lbm_particles_couple(lbm_ctx *ctx, const float *u, float *reaction, lbm_part
 
 int lbm_particles_couple_sparse(lbm_ctx *ctx, const float *u, float *reaction, lbm_particles *ps, float water_density,
                                 float water_viscosity, float relax, void *stream) {
+    return lbm_particles_couple_slab(ctx, u, reaction, ps, water_density, water_viscosity, relax, 1, stream);
+}
+
+int lbm_particles_couple_slab(lbm_ctx *ctx, const float *u, float *reaction, lbm_particles *ps, float water_density,
+                              float water_viscosity, float relax, int clear_interface_planes, void *stream) {
     if (!ctx || !u || !reaction || !ps || !ps->cell) return fail(ctx, "null argument");
     cudaSetDevice(ctx->device);
     const Grid &G = ctx->g;
     cudaStream_t s = (cudaStream_t)stream;
     CUDA_OK(ctx, launch_particles_clear_deposits(G, reaction, *ps, s));
-    if (G.zg) {      // slabs: what the neighbours' particles left in the interface planes (slab.reduce_ghost_up) is not in this rank's cell list
+    if (G.zg && clear_interface_planes) {      // slabs: what the neighbours' particles left in the interface planes (slab.reduce_ghost_up) is not in this rank's cell list
         for (int d = 0; d < 3; ++d) {
             float *r = reaction + (size_t)d * G.vol;
             CUDA_OK(ctx, cudaMemsetAsync(r, 0, (size_t)G.plane * 2 * sizeof(float), s));

@@ -38,7 +38,12 @@ __global__ void __launch_bounds__(256) particles_couple_kernel(const ParticleArg
     const int n = P.n;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = p < n;
-    const bool act = valid && P.active[p] != 0;
+    bool act = valid && P.active[p] != 0;
+    if (act && G.zg) {       // z-slabs, replicated particles: the rank whose slab holds the base cell computes (slab.particle_owner_mask)
+        float fz_;
+        const int kg_ = base_cell(P.pos[2 * n + p], G.nz_global, fz_);
+        act = kg_ >= G.z0 && kg_ < G.z0 + G.nz;
+    }
 
     float rx = 0.0f, ry = 0.0f, rz = 0.0f;     // reaction force of this particle
     float w[8];

@@ -529,7 +529,7 @@ def particles_couple_slab(engine: D3Q19Engine, ps: ParticleState, reaction: torc
                           water_density: Optional[float] = None, water_viscosity: Optional[float] = None, sparse_clear: bool = False,
                           sync: str = "all", interface_guard: bool = False):
     """Two-way coupling on a z-slab engine: every rank holds all particles; a particle is computed by the rank whose slab holds
-    its base cell.  The kernel is the single-GPU one -- it is handed an `active` array masked to the owned particles.  Around
+    its base cell (the kernel tests that itself on a slab engine).  Around
     it: ghost planes of u in (the trilinear gather reaches one plane up), the top ghost plane of the reaction field out and
     added to the rank above (the scatter reaches one plane up), then ONE packed all-reduce of the output arrays so that the
     replicated state stays identical (torch.distributed: NCCL on the device, gloo in tests/test_slab_gloo.py, where the kernel
@@ -545,18 +545,32 @@ def particles_couple_slab(engine: D3Q19Engine, ps: ParticleState, reaction: torc
     per_z = engine.periodic[2]
     guard_left = getattr(ps, "_interface_guard", 0) if interface_guard else 0
     active_all = ps.active
-    owned = slab.particle_owner_mask(ps.pos[2], active_all, engine.z0, engine.nz, engine.nz_global)
-    if guard_left <= 0:
-        slab.exchange_planes(engine.u, engine.rank, engine.nranks, per_z)
-    ps.active = owned
-    try:
-        particles_couple(engine, ps, reaction, relax=relax, water_density=water_density, water_viscosity=water_viscosity,
-                         sparse_clear=sparse_clear)
-    finally:
-        ps.active = active_all
+    cfg = engine.cfg
+    rho_w = np.float32(cfg.WATER_DENSITY_90C if water_density is None else water_density)
+    mu_w = np.float32(cfg.WATER_VISCOSITY_90C * cfg.WATER_DENSITY_90C if water_viscosity is None else water_viscosity)
+
+    def couple():
+        # the kernel itself skips particles whose base cell lies in another slab: `active` needs no masking (a guarded call is
+        # two launches and no torch op).  The interface planes of `reaction` are cleared whole only when a neighbour's deposits
+        # were added to them since the last call.
+        st = ps.struct()
+        if sparse_clear:
+            dirty = getattr(ps, "_interface_dirty", True)
+            engine._check(engine.lib.lbm_particles_couple_slab(engine._ctx, _ptr(engine.u), _ptr(reaction), C.byref(st), float(rho_w), float(mu_w),
+                                                               float(relax), 1 if dirty else 0, engine.stream), "lbm_particles_couple_slab")
+            ps._interface_dirty = False
+        else:
+            engine._check(engine.lib.lbm_particles_couple(engine._ctx, _ptr(engine.u), _ptr(reaction), C.byref(st), float(rho_w), float(mu_w),
+                                                          float(relax), engine.stream), "lbm_particles_couple")
+
     if guard_left > 0:
+        couple()
         ps._interface_guard = guard_left - 1
         return
+    owned = slab.particle_owner_mask(ps.pos[2], active_all, engine.z0, engine.nz, engine.nz_global)
+    slab.exchange_planes(engine.u, engine.rank, engine.nranks, per_z)
+    couple()
+    ps._interface_dirty = True
     slab.reduce_ghost_up(reaction, engine.rank, engine.nranks, per_z)
     if sync == "state" and relax >= 0.0 and not interface_guard:
         # what the next step needs on whichever rank owns the particle then: the under-relaxed drag (the kernel leaves

@@ -8,6 +8,7 @@ Every rank owns a z-slab (+1 ghost plane per side), steps with the NCCL halo exc
 box.  Cases: periodic box with LES (physical), V60 box with every feature (physical), legacy solver (reference, FD-LES
 needs the u ghost planes too).
 """
+import datetime
 import os
 import sys
 
@@ -197,7 +198,7 @@ def run_particle_producers(rank, world, local, nx, nzg, make_engine, setup, cfg,
 def main():
     rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=150))      # a mismatched collective aborts in minutes, not in ten
     nx = 64
     nzg = 32 * world
     ok = True
