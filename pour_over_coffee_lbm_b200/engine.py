@@ -512,17 +512,22 @@ class ParticleState:
 
 
 def particles_couple(engine: D3Q19Engine, ps: ParticleState, reaction: torch.Tensor, relax: float = 0.8,
-                     water_density: Optional[float] = None, water_viscosity: Optional[float] = None, sparse_clear: bool = False):
+                     water_density: Optional[float] = None, water_viscosity: Optional[float] = None, sparse_clear: bool = False,
+                     clear_interface: bool = True):
     """CoffeeParticleSystem.compute_two_way_coupling_forces + apply_under_relaxation (one kernel).  sparse_clear: `reaction` is
     written by this call only (and was zero before the first one): the previous call's deposits are cleared cell by cell instead of
-    zeroing the whole field (lbm_particles_couple_sparse, include/lbm_b200.h)."""
+    zeroing the whole field (lbm_particles_couple_sparse, include/lbm_b200.h); on a slab engine clear_interface = False skips the
+    whole-plane clear of the interface planes (lbm_particles_couple_slab)."""
     cfg = engine.cfg
     rho_w = np.float32(cfg.WATER_DENSITY_90C if water_density is None else water_density)
     mu_w = np.float32(cfg.WATER_VISCOSITY_90C * cfg.WATER_DENSITY_90C if water_viscosity is None else water_viscosity)
     st = ps.struct()
-    fn = engine.lib.lbm_particles_couple_sparse if sparse_clear else engine.lib.lbm_particles_couple
-    engine._check(fn(engine._ctx, _ptr(engine.u), _ptr(reaction), C.byref(st), float(rho_w), float(mu_w), float(relax), engine.stream),
-                  "lbm_particles_couple")
+    if sparse_clear:
+        engine._check(engine.lib.lbm_particles_couple_slab(engine._ctx, _ptr(engine.u), _ptr(reaction), C.byref(st), float(rho_w), float(mu_w),
+                                                           float(relax), 1 if clear_interface else 0, engine.stream), "lbm_particles_couple_slab")
+    else:
+        engine._check(engine.lib.lbm_particles_couple(engine._ctx, _ptr(engine.u), _ptr(reaction), C.byref(st), float(rho_w), float(mu_w),
+                                                      float(relax), engine.stream), "lbm_particles_couple")
 
 
 def particles_couple_slab(engine: D3Q19Engine, ps: ParticleState, reaction: torch.Tensor, relax: float = 0.8,
@@ -545,23 +550,15 @@ def particles_couple_slab(engine: D3Q19Engine, ps: ParticleState, reaction: torc
     per_z = engine.periodic[2]
     guard_left = getattr(ps, "_interface_guard", 0) if interface_guard else 0
     active_all = ps.active
-    cfg = engine.cfg
-    rho_w = np.float32(cfg.WATER_DENSITY_90C if water_density is None else water_density)
-    mu_w = np.float32(cfg.WATER_VISCOSITY_90C * cfg.WATER_DENSITY_90C if water_viscosity is None else water_viscosity)
 
     def couple():
         # the kernel itself skips particles whose base cell lies in another slab: `active` needs no masking (a guarded call is
         # two launches and no torch op).  The interface planes of `reaction` are cleared whole only when a neighbour's deposits
         # were added to them since the last call.
-        st = ps.struct()
-        if sparse_clear:
-            dirty = getattr(ps, "_interface_dirty", True)
-            engine._check(engine.lib.lbm_particles_couple_slab(engine._ctx, _ptr(engine.u), _ptr(reaction), C.byref(st), float(rho_w), float(mu_w),
-                                                               float(relax), 1 if dirty else 0, engine.stream), "lbm_particles_couple_slab")
-            ps._interface_dirty = False
-        else:
-            engine._check(engine.lib.lbm_particles_couple(engine._ctx, _ptr(engine.u), _ptr(reaction), C.byref(st), float(rho_w), float(mu_w),
-                                                          float(relax), engine.stream), "lbm_particles_couple")
+        dirty = getattr(ps, "_interface_dirty", True)
+        particles_couple(engine, ps, reaction, relax=relax, water_density=water_density, water_viscosity=water_viscosity,
+                         sparse_clear=sparse_clear, clear_interface=dirty)
+        ps._interface_dirty = False
 
     if guard_left > 0:
         couple()

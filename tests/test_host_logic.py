@@ -196,9 +196,9 @@ def test_multiphase_facade_call_sequence_and_lazy_fields():
 
 
 def test_particle_coupling_on_a_slab_masks_ownership_and_exchanges(monkeypatch):
-    """CoffeeParticleSystem._couple_on_slab (host logic, stubbed engine): ghost planes of u in, the single-GPU kernel on an
-    `active` array masked to the particles whose base cell lies in the slab, reaction ghost plane up, outputs all-reduced; the
-    replicated `active` array is restored."""
+    """CoffeeParticleSystem._couple_on_slab (host logic, stubbed engine): ghost planes of u in, the coupling kernel on the replicated
+    `active` array (on a slab engine the kernel itself skips particles whose base cell lies in another slab), reaction ghost plane up,
+    outputs all-reduced with the ownership mask (active AND base cell in the slab); the replicated `active` array is untouched."""
     import torch
     from pour_over_coffee_lbm_b200 import engine as engine_mod, physics, slab
     calls = []
@@ -220,7 +220,7 @@ def test_particle_coupling_on_a_slab_masks_ownership_and_exchanges(monkeypatch):
     monkeypatch.setattr(slab, "allreduce_owned_packed", lambda ts, own, act, group=None: calls.append(("allreduce", len(ts), own.tolist(), act.tolist())))
     monkeypatch.setattr(engine_mod, "particles_couple", lambda e, st, react, **kw: calls.append(("kernel", st.active.tolist(), kw["relax"])))
     ps.compute_two_way_coupling_forces(None, relax=0.8)
-    assert calls == [("ghosts_in", (3, 10, 4, 4)), ("kernel", [0, 1, 0, 1], 0.8), ("ghost_up", (3, 10, 4, 4)),
+    assert calls == [("ghosts_in", (3, 10, 4, 4)), ("kernel", [1, 1, 0, 1], 0.8), ("ghost_up", (3, 10, 4, 4)),
                      ("allreduce", 7, [0, 1, 0, 1], [1, 1, 0, 1])]
     assert ps.state.active.tolist() == [1, 1, 0, 1]
 
