@@ -68,4 +68,13 @@ int emu_particles_fluid_forces(int nx, int ny, int nz, const float *u, lbm_parti
     run((unsigned)ps->n, 256, [&] { particles_fluid_forces_kernel(G, u, *ps, force, (float)water_density, mu_safe, (float)gravity, vol_k, max_coord, counters); });
     return 0;
 }
+// z-slab: nz owned planes from global plane z0, one ghost plane per side (u is [3][nz + 2][ny][nx])
+int emu_particles_fluid_forces_slab(int nx, int ny, int nz, int z0, int nz_global, const float *u, lbm_particles *ps, float *force, double water_density,
+                                    double water_viscosity, double gravity, int *counters) {
+    const Grid G = make_grid(nx, ny, nz, 1, z0, nz_global);
+    const float max_coord = (float)std::max(nx, std::max(ny, nz_global));
+    const float mu_safe = (float)std::max(1e-8, water_viscosity), vol_k = (float)((4.0 / 3.0) * 3.14159);
+    run((unsigned)ps->n, 256, [&] { particles_fluid_forces_kernel(G, u, *ps, force, (float)water_density, mu_safe, (float)gravity, vol_k, max_coord, counters); });
+    return 0;
+}
 }  // extern "C"

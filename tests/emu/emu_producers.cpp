@@ -123,6 +123,14 @@ int emu_particles_block_at_filter(int nx, int ny, int nz, int n, float *pos, flo
     run(dim3((n + b - 1) / b, 1, 1), b, [&] { particles_block_at_filter_kernel(G, P, flags, accumulated, scale_length, noise, seed); });
     return 0;
 }
+// z-slab: nz owned planes from global plane z0, one ghost plane per side (flags and accumulated are [nz + 2][ny][nx])
+int emu_particles_block_at_filter_slab(int nx, int ny, int nz, int z0, int nz_global, lbm_particles *ps, const uint8_t *flags, float *accumulated,
+                                       float scale_length, float noise, unsigned seed) {
+    const Grid G = make_grid(nx, ny, nz, 1, z0, nz_global);
+    const unsigned b = 256;
+    run(dim3((ps->n + b - 1) / b, 1, 1), b, [&] { particles_block_at_filter_kernel(G, *ps, flags, accumulated, scale_length, noise, seed); });
+    return 0;
+}
 int emu_pour(int mode, int nx, int ny, int nz, float pour_x, float pour_y, float radius, int pour_z, float velocity, float flow_rate, float dt,
              const uint8_t *flags, float *field) {
     const Grid G = make_grid(nx, ny, nz);

@@ -243,6 +243,112 @@ def test_two_gloo_ranks_particle_coupling_reproduces_the_reference_run(cuts):
     assert out.get(timeout=5) is True
 
 
+# ---- apply_fluid_forces / block_particles_at_filter on z-slabs: the product's slab functions over gloo, kernels CPU-emulated -------------------
+def _producer_worker(rank, world, port, out, cuts):
+    import ctypes as C
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pour_over_coffee_lbm_b200 import engine as E
+    here = os.path.dirname(os.path.abspath(__file__))
+    emu_p = C.CDLL(os.path.join(here, "emu", "_build", "libemu_particles.so"))
+    emu_f = C.CDLL(os.path.join(here, "emu", "_build", "libemu_producers.so"))
+    n = 16
+    z0, nz = cuts[rank]
+    rng = np.random.default_rng(23)
+    cfg = R.RefConfig(NX=n, NY=n, NZ=n)
+    sl = float(np.float32(cfg.SCALE_LENGTH))
+    u_glob = (0.05 * rng.standard_normal((3, n, n, n))).astype(np.float32)                   # [3][z][y][x]
+    flags_glob = np.where(rng.random((n, n, n)) < 0.25, 2, 0).astype(np.uint8)               # LBM_FLAG_FILTER on a quarter of the cells
+    npart = 600
+
+    def particles(scaled):
+        r = np.random.default_rng(29)
+        ps = E.ParticleState(npart, "cpu")
+        pos = r.uniform(0.5, n - 1.5, (3, npart))
+        if scaled:
+            pos = pos * sl
+        else:
+            pos[0, ::41] = np.nan; pos[2, 7::43] = 1e9                                       # invalid: deactivated and counted by the kernel
+        ps.pos.copy_(torch.from_numpy(pos.astype(np.float32)))
+        ps.vel.copy_(torch.from_numpy((0.02 * r.standard_normal((3, npart))).astype(np.float32)))
+        rad = np.clip(r.normal(3.25e-4, 1e-4, npart), 1.6e-4, 4.9e-4).astype(np.float32)
+        ps.radius.copy_(torch.from_numpy(rad))
+        ps.mass.copy_(torch.from_numpy(((np.float32(4 / 3) * np.float32(3.14159)) * rad ** 3 * np.float32(1200.0)).astype(np.float32)))
+        ps.active.fill_(1); ps.active[::13] = 0
+        return ps
+
+    pad = lambda a, ax: np.ascontiguousarray(np.pad(a, [(1, 1) if i == ax else (0, 0) for i in range(a.ndim)]))
+
+    class Lib:      # the two C-ABI entry points the slab functions call, on the CPU-emulated kernel source
+        def lbm_particles_fluid_forces(self, ctx, u, st, force, rho_w, mu_w, grav, counters, stream):
+            return emu_p.emu_particles_fluid_forces_slab(n, n, nz, z0, n, u, st, force, C.c_double(rho_w), C.c_double(mu_w), C.c_double(grav), counters)
+
+        def lbm_particles_block_at_filter(self, ctx, st, flags, acc, scale, noise, seed, stream):
+            return emu_f.emu_particles_block_at_filter_slab(n, n, nz, z0, n, st, flags, acc, C.c_float(scale), C.c_float(noise), C.c_uint(seed))
+
+    class Eng:
+        lib, _ctx, stream = Lib(), None, None
+        nx = ny = n
+        zghost = 1
+        def _check(self, rc, what): assert rc == 0, what
+    eng = Eng()
+    eng.z0, eng.nz, eng.nz_global, eng.rank, eng.nranks = z0, nz, n, rank, world
+    # ghost planes: the neighbour's boundary planes (flags), zeros for u (the kernel reads the base cell only)
+    fl = np.zeros((nz + 2, n, n), np.uint8); fl[1:-1] = flags_glob[z0:z0 + nz]
+    if z0 > 0: fl[0] = flags_glob[z0 - 1]
+    if z0 + nz < n: fl[-1] = flags_glob[z0 + nz]
+    eng.flags = torch.from_numpy(fl)
+    eng.u = torch.from_numpy(pad(u_glob[:, z0:z0 + nz], 1))
+
+    pa, pb = particles(False), particles(True)
+    force = torch.zeros_like(pa.pos); counters = torch.zeros(2, dtype=torch.int32)
+    E.particles_fluid_forces_slab(eng, pa, force, counters, 997.0, 1.0e-3, 9.81)
+    acc = torch.zeros((nz + 2, n, n), dtype=torch.float32)
+    E.particles_block_at_filter_slab(eng, pb, acc, sl, 0.01, 7)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (z0, acc[1:-1].numpy().copy(), force.numpy().copy(), pa.vel.numpy().copy(), pa.active.numpy().copy(), counters.numpy().copy(),
+                                      pb.vel.numpy().copy()))
+    if rank == 0:
+        parts = sorted(gathered, key=lambda g: g[0])
+        ok = all(np.array_equal(p[k].view(np.int32), parts[0][k].view(np.int32)) for p in parts for k in (2, 3, 4, 5, 6))      # replicated state identical
+        # the single-domain kernels on the whole box
+        ra, rb = particles(False), particles(True)
+        rforce = np.zeros((3, npart), np.float32); rcount = np.zeros(2, np.int32)
+        P = lambda a: a.ctypes.data_as(C.c_void_p)
+        st = ra.struct()
+        emu_p.emu_particles_fluid_forces(n, n, n, P(u_glob), C.byref(st), P(rforce), C.c_double(997.0), C.c_double(1.0e-3), C.c_double(9.81), P(rcount))
+        racc = np.zeros((n, n, n), np.float32)
+        emu_f.emu_particles_block_at_filter(n, n, n, npart, C.c_void_p(rb.pos.data_ptr()), C.c_void_p(rb.vel.data_ptr()), C.c_void_p(rb.active.data_ptr()),
+                                            P(flags_glob), P(racc), C.c_float(sl), C.c_float(0.01), C.c_uint(7))
+        act = ra.active.numpy() != 0
+        same = lambda a, b: np.array_equal(np.ascontiguousarray(a).view(np.int32), np.ascontiguousarray(b).view(np.int32))
+        ok &= same(parts[0][2][:, act], rforce[:, act]) and same(parts[0][3], ra.vel.numpy()) and same(parts[0][4], ra.active.numpy()) and same(parts[0][5], rcount)
+        ok &= same(parts[0][6], rb.vel.numpy()) and same(np.concatenate([p[1] for p in parts], axis=0), racc)
+        ok &= int(rcount[0]) > 0 and float(racc.sum()) > 0.05 and int((rb.vel.numpy() != particles(True).vel.numpy()).any(0).sum()) > 5
+        out.put(bool(ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("cuts", [((0, 8), (8, 8)), ((0, 11), (11, 5))], ids=["equal", "unequal"])
+def test_two_gloo_ranks_particle_producers_on_slabs_equal_the_single_domain_kernels(cuts):
+    """engine.particles_fluid_forces_slab (owner of the base cell computes; force, reset velocities, deactivations and the error counter
+    all-reduced) and engine.particles_block_at_filter_slab (the ranks agree on the first filter plane of gz - 2 .. gz + 2, a range that
+    straddles the cut for many particles here; its owner computes) -- the product's own functions over gloo, their two C-ABI calls routed to
+    the CPU-emulated kernel source -- against the same kernels on the undivided box: every array bit for bit."""
+    H.build_emu("emu_particles", ["lbm_particles.cu", "lbm_common.cuh"])
+    H.build_emu("emu_producers", ["lbm_producers.cu", "lbm_common.cuh"])
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_producer_worker, args=(r, 2, port, out, cuts)) for r in range(2)]
+    for p in procs: p.start()
+    for p in procs: p.join(timeout=240)
+    for p in procs:
+        assert p.exitcode == 0
+    assert out.get(timeout=5) is True
+
+
 # ---- the legacy-compatible step on z-slabs: product kernel source (CPU-emulated) + slab.exchange_halo over gloo ---------------
 def _step_worker(rank, world, port, out, cuts, fixture):
     import ctypes as C
