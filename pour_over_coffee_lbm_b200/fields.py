@@ -15,6 +15,8 @@ import torch
 
 
 class _FieldBase:
+    owner = None          # the solver whose engine holds the tensor behind this field (set by LBMSolver / MultiphaseFlow3D)
+
     def __init__(self, on_write: Optional[Callable[[], None]] = None):
         self._on_write = on_write
 

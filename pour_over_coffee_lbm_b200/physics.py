@@ -18,6 +18,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
+from . import config as cfgmod
 from .engine import ParticleState, particles_advance, particles_couple, _ptr
 from .fields import ScalarField, VectorField
 
@@ -437,6 +438,8 @@ class CoffeeParticleSystem:
         (up to 2000 particles, 10-30 layers, radius concentrated toward the axis, Gaussian grain sizes).  The reference
         draws with the unseeded global NumPy generator one particle at a time; here each layer is drawn in one
         vectorised batch from `seed` (same distributions and acceptance tests), then uploaded once."""
+        if self._solver is None:             # main.py:477 constructs the system bare; the filter system knows the solver
+            self.bind(filter_paper_system.lbm)
         cfg = self._solver.config
         rng = np.random.default_rng(seed)
         self.clear_all_particles()
@@ -607,6 +610,7 @@ class MultiphaseFlow3D:
         self._normal, self._grad_phi, self._grad_mu, self._sf = vc(), vc(), vc(), vc()
         zg = e.zghost
         self.phi = ScalarField(lambda: self._phi, zg); self.phi_new = ScalarField(lambda: self._phi_new, zg)
+        self.phi.owner = self.phi_new.owner = getattr(lbm_solver, "_solver", lbm_solver)
         self.mu = ScalarField(lambda: self._mu, zg)
         self.laplacian_phi = ScalarField(lambda: self._lap, zg)
         fresh = self._fresh
@@ -762,9 +766,9 @@ class PrecisePouringSystem:
 
     def __init__(self, solver: Any = None, config: Any = None):
         self.lbm = solver
-        cfg = config if config is not None else (solver.config if solver is not None else None)
-        if cfg is None:
-            raise ValueError("PrecisePouringSystem needs a solver or a config")
+        # main.py:482 constructs `PrecisePouringSystem()` bare (the reference reads its global `config` module): the package
+        # default then, and the solver that owns the fields arrives with bind() or through the first field argument
+        cfg = config if config is not None else (solver.config if solver is not None else cfgmod.DEFAULT)
         self.config = cfg
         self.POUR_DIAMETER_CM = 0.5
         self.POUR_DIAMETER_GRID = self.POUR_DIAMETER_CM / cfg.GRID_SIZE_CM
@@ -823,9 +827,14 @@ class PrecisePouringSystem:
     def _tensor(field_or_tensor):
         return field_or_tensor._get() if hasattr(field_or_tensor, "_get") else field_or_tensor
 
-    def _engine(self):
+    def _engine(self, *fields):
+        if self.lbm is None:               # constructed bare like the reference's: the first field argument names its solver
+            for fld in fields:
+                if getattr(fld, "owner", None) is not None:
+                    self.lbm = fld.owner
+                    break
         if self.lbm is None:
-            raise ValueError("PrecisePouringSystem is not bound to a solver (pass solver= or call bind())")
+            raise ValueError("PrecisePouringSystem is not bound to a solver (pass solver=, call bind(), or hand it the solver's fields)")
         self.lbm._sync_flags()
         return self.lbm.engine
 
@@ -836,13 +845,13 @@ class PrecisePouringSystem:
         if self.pouring_active[None] != 1:
             return
         self.pour_time[None] = self.pour_time[None] + np.float32(dt)
-        self._engine().pouring_force(self._pour_struct(dt), self._tensor(lbm_body_force))
+        self._engine(lbm_body_force, solid).pouring_force(self._pour_struct(dt), self._tensor(lbm_body_force))
 
     def apply_gradual_phase_change(self, multiphase_phi, solid, dt: float) -> None:
         """precise_pouring.py:165-196."""
         if self.pouring_active[None] != 1:
             return
-        self._engine().pouring_phase_change(self._pour_struct(dt), self._tensor(multiphase_phi))
+        self._engine(solid, multiphase_phi).pouring_phase_change(self._pour_struct(dt), self._tensor(multiphase_phi))
 
     def create_water_impact_force(self, particle_system, max_force: float, dt: float) -> None:
         raise NotImplementedError("create_water_impact_force (precise_pouring.py:196-233) is not on main.py's step path and is not built")

@@ -1,0 +1,257 @@
+"""SURVEY 8f row 1 -- `main.py` orchestration on the facade, pinned to a RECORDED run of the reference's own main.py.
+
+tests/golden/make_reference_main_trace.py constructed the reference's `CoffeeSimulation` (main.py:445-935) unmodified under the
+Taichi stand-in on a 16^3 grid, stepped it, and logged every call main.py made on the solver and the physics modules, the
+attribute probes that pick main.py's code path, and rho / u / phase / solid / phi after the constructor and after every step
+(tests/golden/reference_main_trace.json, reference_main_trace_fields.npz).  `/root/reference` and a GPU never meet in one place
+(the reference is absent on the GPU box, the authoring container has no GPU), so the drop-in claim is carried by the recording:
+  CPU  every recorded call binds against the facade class's signature (and a call the reference rejected with TypeError is
+       rejected here too); the facade answers main.py's `hasattr` probes like the reference's LBMSolver;
+  GPU  the whole recorded call sequence -- constructor phases and the step_stable loop -- is replayed on the device through an
+       adapter with main.py's attribute contract; return values and the recorded fields are compared.
+"""
+import inspect
+import json
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+TRACE_JSON = os.path.join(HERE, "golden", "reference_main_trace.json")
+TRACE_NPZ = os.path.join(HERE, "golden", "reference_main_trace_fields.npz")
+
+
+def load_trace():
+    with open(TRACE_JSON) as fh:
+        return json.load(fh)
+
+
+def role_classes():
+    from pour_over_coffee_lbm_b200 import physics as P
+    from pour_over_coffee_lbm_b200.solver import LBMSolver
+    return {"lbm": LBMSolver, "multiphase": P.MultiphaseFlow3D, "pouring": P.PrecisePouringSystem, "filter_paper": P.FilterPaperSystem,
+            "pressure_drive": P.PressureGradientDrive, "particle_system": P.CoffeeParticleSystem, "boundary_manager": P.BoundaryConditionManager}
+
+
+FIELD_OPS = {"to_numpy", "from_numpy", "fill", "copy_from"}
+
+
+def test_recorded_trace_is_the_whole_run():
+    t = load_trace()
+    assert t["solver_class"] == "LBMSolver" and t["all_steps_ok"] and t["grid"] == 16
+    calls = [(r["on"], r["call"]) for r in t["trace"]]
+    # the constructor phases of main.py:596-690 and the loop of main.py:735-935 are all in the recording
+    for must in [("lbm", "init_fields"), ("lbm", "step"), ("multiphase", "standardize_initial_state"), ("multiphase", "update_density_from_phase"),
+                 ("filter_paper", "initialize_filter_geometry"), ("boundary_manager", "initialize_all_boundaries"),
+                 ("particle_system", "initialize_coffee_bed_confined"), ("particle_system", "update_particle_physics"),
+                 ("lbm", "clear_body_force"), ("pressure_drive", "apply"), ("lbm", "step_with_particles"),
+                 ("filter_paper", "update_dynamic_resistance"), ("multiphase", "step"), ("pouring", "start_pouring"),
+                 ("multiphase", "accumulate_surface_tension_pre_collision")]:
+        assert must in calls, must
+    assert t["marks"][0]["phase"] == "constructed" and len(t["marks"]) == t["steps"] + 1
+    z = np.load(TRACE_NPZ)
+    assert z["init_rho"].shape == (16, 16, 16) and z[f"step{t['steps'] - 1}_u"].shape == (16, 16, 16, 3)
+    assert np.isfinite(z[f"step{t['steps'] - 1}_rho"]).all()
+
+
+def test_every_recorded_main_py_call_binds_to_the_facade():
+    """Signature compatibility without a device: for every call main.py made, the facade class has the method and
+    `inspect.signature(...).bind` accepts the recorded arguments; calls the reference itself rejected with TypeError (main.py:778
+    passes four arguments to apply_pouring_force and swallows the error) must be rejected by the facade as well."""
+    t = load_trace()
+    classes = role_classes()
+    checked = 0
+    for r in t["trace"]:
+        if r["call"] in FIELD_OPS and "." in r["on"]:
+            continue                                   # field access from main.py: covered on the device
+        cls = classes[r["on"]]
+        assert hasattr(cls, r["call"]), f"{cls.__name__}.{r['call']} is called by main.py and missing on the facade"
+        sig = inspect.signature(getattr(cls, r["call"]))
+        args = [object()] + [object() for _ in r["args"]]
+        kwargs = {k: object() for k in r["kwargs"]}
+        if r.get("raised") == "TypeError":
+            with pytest.raises(TypeError):
+                sig.bind(*args, **kwargs)
+        else:
+            sig.bind(*args, **kwargs)
+        checked += 1
+    assert checked >= 100
+
+
+def test_facade_answers_main_py_attribute_probes_like_the_reference():
+    """main.py picks its stepping path with hasattr on the solver (main.py:417-439, 803-824).  Method names the reference's
+    LBMSolver has must exist on the facade, and names it lacks must be absent -- otherwise main.py would take another branch
+    than the recorded run (e.g. `step_ultra_optimized()` instead of `step_with_particles(particle_system)`)."""
+    from pour_over_coffee_lbm_b200.solver import LBMSolver
+    t = load_trace()
+    for name, p in t["probes"].items():
+        if p["kind"] == "method":
+            assert callable(getattr(LBMSolver, name, None)), name
+        elif not p["present"]:
+            assert not hasattr(LBMSolver, name), f"LBMSolver.{name}: absent in the reference, main.py branches on it"
+    src = inspect.getsource(LBMSolver.__init__)
+    for name, p in t["probes"].items():
+        if p["present"] and p["kind"] != "method":
+            assert f"self.{name}" in src, f"instance attribute {name} (main.py reads it through its adapter)"
+
+
+# ---- replay on the device -------------------------------------------------------------------------------------------------
+class RecordedAdapter:
+    """What main.py wraps the solver in (main.py:378-442), rebuilt from the RECORDED probes: the probed attributes are looked up
+    once with getattr(..., None), step / clear_body_force / init_fields forward, everything else goes through __getattr__."""
+
+    def __init__(self, solver, probes):
+        self._solver = solver
+        for name, p in probes.items():
+            if p["kind"] != "method" and name != "fluid_solver":
+                setattr(self, name, getattr(solver, name, None))
+
+    def step(self):
+        return self._solver.step()
+
+    def clear_body_force(self):
+        return self._solver.clear_body_force()
+
+    def init_fields(self):
+        return self._solver.init_fields()
+
+    def __getattr__(self, name):
+        return getattr(self.__dict__["_solver"], name)
+
+
+def _close(a, b, path=""):
+    if isinstance(b, dict) and set(b) == {"dict"}:
+        assert isinstance(a, dict), path
+        for k, v in b["dict"].items():
+            if isinstance(v, dict) and "other" in v:
+                assert k in a, f"{path}.{k}"
+                continue
+            assert k in a, f"{path}.{k} missing"
+            _close(a[k], v, f"{path}.{k}")
+    elif isinstance(b, dict) and set(b) == {"list"}:
+        assert len(a) == len(b["list"]), path
+        for i, v in enumerate(b["list"]):
+            _close(a[i], v, f"{path}[{i}]")
+    elif isinstance(b, bool) or b is None or isinstance(b, str):
+        assert (bool(a) == b) if isinstance(b, bool) else (a == b), f"{path}: {a!r} != {b!r}"
+    elif isinstance(b, (int, float)):
+        assert float(a) == pytest.approx(float(b), rel=1e-5, abs=1e-7), f"{path}: {a!r} != {b!r}"
+
+
+def replay(t, fields, upto=None, compare=True, report=None):
+    """Runs the recorded call sequence on the device.  Returns the objects by role."""
+    import torch
+    from pour_over_coffee_lbm_b200 import config as cfgmod
+    classes = role_classes()
+    n = t["grid"]
+    old_default = cfgmod.DEFAULT
+    cfgmod.DEFAULT = cfgmod.LBMConfig(NX=n, NY=n, NZ=n)       # the recording patched config.core the same way (load_reference)
+    try:
+        # main.py:549 `UnifiedLBMSolver(preferred_backend='auto')` -> (fallback, main.py:556) `LBMSolver()`: no arguments
+        solver = classes["lbm"]()
+        assert solver.engine.nx == n and solver.config.GRAVITY_LU == pytest.approx(t["constants"]["GRAVITY_LU"], rel=1e-6)
+        objs = {"lbm": RecordedAdapter(solver, t["probes"]), "boundary_manager": solver.boundary_manager}
+        raw = {"lbm": solver}
+
+        def resolve(v):
+            if isinstance(v, dict):
+                if "obj" in v:
+                    return objs[v["obj"]]
+                if "field" in v:
+                    role, attr = v["field"].split(".", 1)
+                    return getattr(objs[role], attr)
+                if "dict" in v:
+                    return {k: resolve(w) for k, w in v["dict"].items()}
+                if "list" in v:
+                    return [resolve(w) for w in v["list"]]
+                raise AssertionError(f"unreplayable argument {v}")
+            return v
+
+        marks = {m["calls"]: m["phase"] for m in t["marks"]}
+        for i, r in enumerate(t["trace"]):
+            if upto is not None and i >= upto:
+                break
+            args = [resolve(a) for a in r["args"]]; kwargs = {k: resolve(a) for k, a in r["kwargs"].items()}
+            if r["call"] == "__init__":
+                objs[r["on"]] = classes[r["on"]](*args, **kwargs)
+            elif r["call"] in FIELD_OPS and "." in r["on"]:
+                role, attr = r["on"].split(".", 1)
+                getattr(getattr(objs[role], attr), r["call"])(*args, **kwargs)
+            else:
+                fn = getattr(objs[r["on"]], r["call"])
+                if "raised" in r:
+                    with pytest.raises(Exception) as ei:
+                        fn(*args, **kwargs)
+                    assert type(ei.value).__name__ == r["raised"], (r, ei.value)
+                else:
+                    out = fn(*args, **kwargs)
+                    if compare and r["call"] not in ("initialize_coffee_bed_confined",):     # particle count: other generator, below
+                        _close(out, r.get("returns"), f"{r['on']}.{r['call']}")
+            if (i + 1) in marks:
+                tag = "init" if marks[i + 1] == "constructed" else marks[i + 1].replace("_", "")
+                got = {"rho": solver.rho.to_numpy(), "u": solver.u.to_numpy(), "phase": solver.phase.to_numpy(),
+                       "solid": solver.solid.to_numpy().astype(np.uint8), "phi": objs["multiphase"].phi.to_numpy(),
+                       "body_force": solver.body_force.to_numpy()}
+                for k, a in got.items():
+                    b = fields[f"{tag}_{k}"]
+                    assert a.shape == b.shape, (tag, k)
+                    assert np.isfinite(a).all(), (tag, k)
+                    if report is not None:
+                        report.append((tag, k, float(np.abs(a.astype(np.float64) - b).max()), float(np.abs(b).max()), bool(np.array_equal(a, b))))
+        torch.cuda.synchronize()
+        return objs, raw
+    finally:
+        cfgmod.DEFAULT = old_default
+
+
+@pytest.mark.gpu
+def test_gpu_replay_of_the_recorded_main_py_run():
+    """CoffeeSimulation.__init__ (pre-stabilisation, multiphase, filter geometry, boundary manager, coffee bed, particle
+    pre-stabilisation) and the step_stable loop, call by call as main.py made them, on the device.  Every call executes, return
+    values agree with the recorded ones, the fields stay finite, the V60 mask equals the reference's bit for bit and the
+    hydrodynamic fields equal the recorded run's bit for bit."""
+    t = load_trace()
+    fields = np.load(TRACE_NPZ)
+    report = []
+    objs, raw = replay(t, fields, report=report)
+    by = {(tag, k): (err, ref, same) for tag, k, err, ref, same in report}
+    last = f"step{t['steps'] - 1}"
+    assert len(by) == 6 * (t["steps"] + 1) and ("init", "solid") in by and (last, "rho") in by
+    # measured on B200 (profiles/r02_main_trace_replay.log): all 90 snapshot comparisons are bit-exact -- every kernel behind these
+    # calls is bit-exact on its own against a recording of the reference, and main.py composes nothing else on this path
+    for (tag, k), (err, ref, same) in by.items():
+        assert same, (tag, k, f"max|diff| = {err:.3e} against the recorded run (max|ref| = {ref:.3e})")
+    # the particle system holds a coffee bed inside the cone (another generator than the reference's unseeded one: counts may differ)
+    stats = objs["particle_system"].get_particle_statistics()
+    assert isinstance(stats, dict)
+    assert raw["lbm"].step_count == sum(1 for r in t["trace"] if r["on"] == "lbm" and r["call"] in ("step", "step_with_particles"))
+
+
+@pytest.mark.gpu
+def test_gpu_bare_constructed_pouring_system_finds_its_engine_through_the_fields():
+    """main.py:482 constructs `PrecisePouringSystem()` without arguments and hands it fields per call (main.py:778-780; the
+    four-argument call there fails in the reference too).  With the correct three arguments the bare object resolves the
+    engine through the fields' owner and pours: same body force as a system constructed with the solver."""
+    import torch
+    from pour_over_coffee_lbm_b200 import config as cfgmod
+    from pour_over_coffee_lbm_b200.physics import MultiphaseFlow3D, PrecisePouringSystem
+    from pour_over_coffee_lbm_b200.solver import LBMSolver
+    old = cfgmod.DEFAULT
+    cfgmod.DEFAULT = cfgmod.LBMConfig(NX=16, NY=16, NZ=16)
+    try:
+        out = []
+        for bare in (True, False):
+            s = LBMSolver(); s.init_fields()
+            mp = MultiphaseFlow3D(s); mp.standardize_initial_state(force_dry_state=True)
+            pp = PrecisePouringSystem() if bare else PrecisePouringSystem(s)
+            pp.POUR_DIAMETER_GRID = 5.0; pp.POUR_HEIGHT = 10
+            pp.start_pouring(pattern="center"); pp.adjust_flow_rate(0.3)
+            s.clear_body_force()
+            pp.apply_pouring_force(s.body_force, s.solid, 1.0)
+            pp.apply_gradual_phase_change(mp.phi, s.solid, 1.0)
+            out.append((s.body_force.to_numpy(), mp.phi.to_numpy()))
+        assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+        assert float(out[0][0][..., 2].min()) < 0.0
+    finally:
+        cfgmod.DEFAULT = old
