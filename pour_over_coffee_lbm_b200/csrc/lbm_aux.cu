@@ -226,15 +226,58 @@ __global__ void pressure_gradient_tiles_kernel(Grid G, const float *rho, const u
     }
 }
 
-// Same over the packed quad list of the four-cell walls kernel (one thread per lane slot).
+// Same over the packed quad list of the four-cell walls kernel: one thread per listed quad, the four flag bytes as one word, rho and
+// its y / z neighbours as 128-bit vectors, the force of an all-fluid quad as three 128-bit stores (the cell-at-a-time form issued
+// every load and store with a 16-byte lane stride: 0.42 ms at V60 512^3 for 0.9 GB).  Same statements per cell as
+// pressure_gradient_cell, so the values are the same bits.
 __global__ void pressure_gradient_chord_kernel(Grid G, const float *rho, const uint8_t *flags, float *bf, float max_force, float scale,
                                                int accumulate, const unsigned long long *quads, int n_items) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= (long long)n_items * 32) return;
     const unsigned long long e = quads[i];
     if (!(e & (1ull << 44))) return;
-    const int xb = (int)(e & 0xfffu) * 4;
-    for (int k = 0; k < 4; ++k) pressure_gradient_cell(G, rho, flags, bf, max_force, scale, accumulate, xb + k, (int)((e >> 12) & 0xffffu), (int)((e >> 28) & 0xffffu));
+    const int xb = (int)(e & 0xfffu) * 4, y = (int)((e >> 12) & 0xffffu), z = (int)((e >> 28) & 0xffffu);
+    const long long n = G.vol;
+    const long long c = ((long long)(z + G.zg) * G.ny + y) * G.nx + xb;
+    const unsigned fw = flags ? *reinterpret_cast<const unsigned *>(flags + c) : 0u;
+    constexpr unsigned SOLID4 = 0x01010101u * LBM_FLAG_SOLID;
+    if ((fw & SOLID4) == SOLID4) return;
+    const int k = G.z0 + z;
+    const float4 r = *reinterpret_cast<const float4 *>(rho + c);
+    const float4 ym = y > 0 ? *reinterpret_cast<const float4 *>(rho + c - G.nx) : r;
+    const float4 yq = y < G.ny - 1 ? *reinterpret_cast<const float4 *>(rho + c + G.nx) : r;
+    const float4 zm = k > 0 ? *reinterpret_cast<const float4 *>(rho + c - G.plane) : r;
+    const float4 zq = k < G.nz_global - 1 ? *reinterpret_cast<const float4 *>(rho + c + G.plane) : r;
+    const float xm = xb > 0 ? rho[c - 1] : r.x, xq = xb + 4 < G.nx ? rho[c + 4] : r.w;
+    const float r0[4] = {r.x, r.y, r.z, r.w}, lo[4] = {xm, r.x, r.y, r.z}, hi[4] = {r.y, r.z, r.w, xq};
+    const float ylo[4] = {ym.x, ym.y, ym.z, ym.w}, yhi[4] = {yq.x, yq.y, yq.z, yq.w};
+    const float zlo[4] = {zm.x, zm.y, zm.z, zm.w}, zhi[4] = {zq.x, zq.y, zq.z, zq.w};
+    const int ypos = y == 0 ? -1 : (y == G.ny - 1 ? 1 : 0), zpos = k == 0 ? -1 : (k == G.nz_global - 1 ? 1 : 0);
+    float f[3][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int x = xb + j;
+        const float gx = pressure_gradient_diff(r0[j], lo[j], hi[j], x == 0 ? -1 : (x == G.nx - 1 ? 1 : 0));
+        const float gy = pressure_gradient_diff(r0[j], ylo[j], yhi[j], ypos);
+        const float gz = pressure_gradient_diff(r0[j], zlo[j], zhi[j], zpos);
+        pressure_gradient_value(r0[j], gx, gy, gz, max_force, scale, f[0][j], f[1][j], f[2][j]);
+    }
+    if ((fw & SOLID4) == 0u) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            float4 *p = reinterpret_cast<float4 *>(bf + d * n + c);
+            float4 v = make_float4(f[d][0], f[d][1], f[d][2], f[d][3]);
+            if (accumulate) { const float4 o = *p; v = make_float4(o.x + v.x, o.y + v.y, o.z + v.z, o.w + v.w); }
+            *p = v;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if ((fw >> (8 * j)) & LBM_FLAG_SOLID) continue;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) bf[d * n + c + j] = accumulate ? bf[d * n + c + j] + f[d][j] : f[d][j];
+        }
+    }
 }
 
 // filter_paper.py:471-536
@@ -811,27 +854,76 @@ __device__ __forceinline__ StatPartial stat_block_reduce(StatPartial s) {
     }
     return s;
 }
+// Per-thread accumulator: the maxima / minima and the counters stay in 32-bit registers (a float max of floats is exact, the counters
+// of one thread stay far below 2^32); only the two sums run in f64.  With all eight values in f64 the loop body was ~150 instructions
+// per cell (SASS: DSETP + SEL pairs for every fmin / fmax, F2F conversions, 64-bit register moves) and the kernel was issue-bound.
+struct StatLocal {
+    float umax = 0.0f, rmin = INFINITY, rmax = -INFINITY;      // +-inf = "no finite value seen" (a non-finite rho never enters)
+    unsigned nan = 0u, inf = 0u, cells = 0u;
+    double mass = 0.0, ke = 0.0;
+};
+__device__ __forceinline__ void stat_cell(StatLocal &s, const float r, const float ux, const float uy, const float uz) {
+    const float um = sqrtf(dot3(ux, uy, uz, ux, uy, uz));
+    s.cells += 1u;
+    const bool r_nan = r != r, r_inf = isinf(r), u_nan = um != um, u_inf = isinf(um);
+    s.nan += (r_nan ? 1u : 0u) + (u_nan ? 1u : 0u);
+    s.inf += (r_inf ? 1u : 0u) + (u_inf ? 1u : 0u);
+    const bool r_ok = !r_nan && !r_inf;
+    if (r_ok) { s.rmin = fminf(s.rmin, r); s.rmax = fmaxf(s.rmax, r); s.mass += (double)r; }
+    if (!u_nan && !u_inf) {
+        s.umax = fmaxf(s.umax, um);
+        if (r_ok) s.ke += 0.5 * (double)r * ((double)ux * ux + (double)uy * uy + (double)uz * uz);
+    }
+}
+__device__ __forceinline__ StatPartial stat_widen(const StatLocal &l) {
+    StatPartial s;
+    s.v[0] = (double)l.umax; s.v[1] = l.rmin == INFINITY ? 1e300 : (double)l.rmin; s.v[2] = l.rmax == -INFINITY ? -1e300 : (double)l.rmax;
+    s.v[3] = l.mass; s.v[4] = l.ke; s.v[5] = (double)l.nan; s.v[6] = (double)l.inf; s.v[7] = (double)l.cells;
+    return s;
+}
+// VEC = 4 (nx % 4 == 0, 16-byte aligned fields): one thread per quad of x-consecutive cells -- the four flag bytes as ONE 32-bit
+// load, and only quads holding a fluid cell fetch rho and u (4 x 128 bit).  Four quads per loop trip, their flag words loaded
+// first: the solid 65 % of a V60 box costs one byte per cell and the data loads of up to four quads are in flight together.
+// The scalar form (ragged nx) read one flag BYTE per thread and then, dependent on it, four 4-byte words: 0.74 ms at V60 512^3
+// (ncu launch list of the bench command, profiles/r02_final_launches_*), five times the 0.9 GB it has to move.
+template <int VEC>
 __global__ void __launch_bounds__(256) field_statistics_kernel(Grid G, const float *rho, const float *u, const uint8_t *flags, StatPartial *partials) {
-    StatPartial s = stat_identity();
+    StatLocal s;
     const long long per = G.plane, n = per * G.nz, off = per * G.zg;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const long long c = off + i;
-        if (flags && (flags[c] & LBM_FLAG_SOLID)) continue;
-        const float r = rho[c], ux = u[c], uy = u[G.vol + c], uz = u[2 * G.vol + c];
-        const float um = sqrtf(dot3(ux, uy, uz, ux, uy, uz));
-        s.v[7] += 1.0;
-        if (r != r) s.v[5] += 1.0;
-        else if (isinf(r)) s.v[6] += 1.0;
-        else { s.v[1] = fmin(s.v[1], (double)r); s.v[2] = fmax(s.v[2], (double)r); s.v[3] += (double)r; }
-        if (um != um) s.v[5] += 1.0;
-        else if (isinf(um)) s.v[6] += 1.0;
-        else {
-            s.v[0] = fmax(s.v[0], (double)um);
-            if (r == r && !isinf(r)) s.v[4] += 0.5 * (double)r * ((double)ux * ux + (double)uy * uy + (double)uz * uz);
+    if constexpr (VEC == 4) {
+        constexpr int TRIP = 4;
+        const long long nq = n >> 2, stride = (long long)gridDim.x * blockDim.x;
+        const unsigned *fw4 = reinterpret_cast<const unsigned *>(flags ? flags + off : nullptr);
+        for (long long q0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; q0 < nq; q0 += stride * TRIP) {
+            unsigned fw[TRIP];
+#pragma unroll
+            for (int t = 0; t < TRIP; ++t) {
+                const long long q = q0 + t * stride;
+                fw[t] = q < nq ? (fw4 ? __ldg(fw4 + q) : 0u) : 0x01010101u;          // past the end: all solid
+            }
+#pragma unroll
+            for (int t = 0; t < TRIP; ++t) {
+                if ((fw[t] & 0x01010101u) == 0x01010101u) continue;                   // LBM_FLAG_SOLID in all four bytes
+                const long long c = off + 4 * (q0 + t * stride);
+                const float4 r = __ldcs(reinterpret_cast<const float4 *>(rho + c));
+                const float4 x = __ldcs(reinterpret_cast<const float4 *>(u + c));
+                const float4 y = __ldcs(reinterpret_cast<const float4 *>(u + G.vol + c));
+                const float4 z = __ldcs(reinterpret_cast<const float4 *>(u + 2 * G.vol + c));
+                if (!(fw[t] & 0x00000001u)) stat_cell(s, r.x, x.x, y.x, z.x);
+                if (!(fw[t] & 0x00000100u)) stat_cell(s, r.y, x.y, y.y, z.y);
+                if (!(fw[t] & 0x00010000u)) stat_cell(s, r.z, x.z, y.z, z.z);
+                if (!(fw[t] & 0x01000000u)) stat_cell(s, r.w, x.w, y.w, z.w);
+            }
+        }
+    } else {
+        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+            const long long c = off + i;
+            if (flags && (flags[c] & LBM_FLAG_SOLID)) continue;
+            stat_cell(s, rho[c], u[c], u[G.vol + c], u[2 * G.vol + c]);
         }
     }
-    s = stat_block_reduce(s);
-    if (threadIdx.x == 0) partials[blockIdx.x] = s;
+    const StatPartial b = stat_block_reduce(stat_widen(s));
+    if (threadIdx.x == 0) partials[blockIdx.x] = b;
 }
 __global__ void __launch_bounds__(256) field_statistics_fold_kernel(const StatPartial *partials, int n, double *out) {
     // thread t folds partials t, t + 256, ... in index order; the block reduction order is fixed as well
@@ -844,7 +936,9 @@ __global__ void __launch_bounds__(256) field_statistics_fold_kernel(const StatPa
     }
 }
 cudaError_t launch_field_statistics(const Grid &G, const float *rho, const float *u, const uint8_t *flags, void *scratch, int blocks, double *out, cudaStream_t s) {
-    field_statistics_kernel<<<blocks, 256, 0, s>>>(G, rho, u, flags, (StatPartial *)scratch);
+    const bool vec4 = G.nx % 4 == 0 && G.vol % 4 == 0 && (((uintptr_t)rho | (uintptr_t)u) & 15u) == 0 && ((uintptr_t)flags & 3u) == 0;
+    if (vec4) field_statistics_kernel<4><<<blocks, 256, 0, s>>>(G, rho, u, flags, (StatPartial *)scratch);
+    else field_statistics_kernel<1><<<blocks, 256, 0, s>>>(G, rho, u, flags, (StatPartial *)scratch);
     field_statistics_fold_kernel<<<1, 256, 0, s>>>((const StatPartial *)scratch, blocks, out);
     return cudaGetLastError();
 }

@@ -501,11 +501,13 @@ class CoffeeParticleSystem:
         ok = act & np.isfinite(r) & np.isfinite(p).all(1) & (r >= self.MIN_RADIUS) & (r <= self.MAX_RADIUS) & \
             (p[:, 0] >= 0) & (p[:, 0] <= cfg.NX) & (p[:, 1] >= 0) & (p[:, 1] <= cfg.NY) & (p[:, 2] >= 0) & (p[:, 2] <= cfg.NZ)
         rr = r[ok]
-        out = {"count": int(ok.sum()), "invalid_particles": int((act & ~ok).sum()), "mean_radius": float(rr.mean()) if rr.size else 0.0,
-               "std_radius": float(rr.std()) if rr.size else 0.0, "min_radius": float(rr.min()) if rr.size else 0.0,
-               "max_radius": float(rr.max()) if rr.size else 0.0, "radii": rr, "positions": p[ok],
-               "coordinate_errors": self.coordinate_errors, "boundary_violations": self.boundary_violations}
-        return out
+        valid, invalid = int(ok.sum()), int((act & ~ok).sum())
+        # key for key what the reference returns (main.py:1046-1067 reads count / mean_radius / ...; recorded in reference_main_trace.json)
+        return {"count": valid, "invalid_count": invalid, "coordinate_errors": self.coordinate_errors,
+                "boundary_violations": self.boundary_violations, "mean_radius": float(rr.mean()) if rr.size else 0.0,
+                "std_radius": float(rr.std()) if rr.size else 0.0, "min_radius": float(rr.min()) if rr.size else 0.0,
+                "max_radius": float(rr.max()) if rr.size else 0.0, "positions": p[ok], "radii": rr,
+                "success_rate": valid / max(1, valid + invalid) * 100}
 
     def compute_two_way_coupling_forces(self, fluid_u=None, relax: float = -1.0):
         """coffee_particles.py:1107-1154; relax >= 0 also applies the under-relaxation in the same kernel.

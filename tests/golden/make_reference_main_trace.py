@@ -15,7 +15,7 @@ with a tuple), so the legacy solver IS the path main.py can run.
 Output: tests/golden/reference_main_trace.json (+ reference_main_trace_fields.npz).  tests/test_main_trace.py binds every
 recorded call against the facade's signatures on the CPU and replays the whole trace on the device.
 
-    python tests/golden/make_reference_main_trace.py [n=16] [steps=12]
+    python tests/golden/make_reference_main_trace.py [n=16] [steps=12] [pressure_mode=none] [out.json]
 """
 import functools
 import inspect
@@ -39,7 +39,12 @@ TRACE = []                 # ordered calls made from main.py
 READERS = {}               # "module" -> sorted set of "field.op"
 ROLES = {}                 # id(obj) -> role
 FIELD_NAMES = {}           # id(field) -> "role.attr"
-KEEP = []                  # keeps wrapped objects alive so that ids stay unique
+SIM = []
+KEEP = {}                  # id -> object: keeps wrapped objects alive so that ids stay unique
+
+
+class StopRecording(BaseException):
+    pass
 
 
 def caller_file(depth=2):
@@ -47,19 +52,21 @@ def caller_file(depth=2):
 
 
 def register(obj, role):
-    ROLES[id(obj)] = role; KEEP.append(obj)
+    ROLES[id(obj)] = role; KEEP[id(obj)] = obj
     for k, v in list(vars(obj).items()):
-        if type(v).__name__ in ("Field", "VectorField", "ScalarField", "MatrixField") or hasattr(v, "to_numpy"):
-            FIELD_NAMES.setdefault(id(v), f"{role}.{k}"); KEEP.append(v)
+        if hasattr(v, "to_numpy"):
+            if id(v) not in FIELD_NAMES:
+                FIELD_NAMES[id(v)] = f"{role}.{k}"; KEEP[id(v)] = v
         elif isinstance(v, list) and v and hasattr(v[0], "to_numpy"):
             for i, w in enumerate(v):
-                FIELD_NAMES.setdefault(id(w), f"{role}.{k}[{i}]"); KEEP.append(w)
+                if id(w) not in FIELD_NAMES:
+                    FIELD_NAMES[id(w)] = f"{role}.{k}[{i}]"; KEEP[id(w)] = w
 
 
 def rescan():
-    for o in list(KEEP):
-        if id(o) in ROLES:
-            register(o, ROLES[id(o)])
+    """Fields created after __init__ (lazily allocated ones): look through the registered objects again."""
+    for i, role in list(ROLES.items()):
+        register(KEEP[i], role)
 
 
 def enc(v):
@@ -78,10 +85,11 @@ def enc(v):
     inner = getattr(v, "_solver", None)                    # MinimalAdapter
     if inner is not None and id(inner) in ROLES:
         return {"obj": ROLES[id(inner)]}
-    if id(v) not in FIELD_NAMES:
-        rescan()
-    if id(v) in FIELD_NAMES:
-        return {"field": FIELD_NAMES[id(v)]}
+    if hasattr(v, "to_numpy"):
+        if id(v) not in FIELD_NAMES:
+            rescan()
+        if id(v) in FIELD_NAMES:
+            return {"field": FIELD_NAMES[id(v)]}
     if isinstance(v, np.ndarray):
         return {"ndarray": list(v.shape), "dtype": str(v.dtype)}
     return {"other": type(v).__name__}
@@ -183,7 +191,8 @@ def snapshot(sim, tag, store):
 if __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 16
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 12
-    out_json = sys.argv[3] if len(sys.argv) > 3 else os.path.join(HERE, "reference_main_trace.json")
+    pressure_mode = sys.argv[3] if len(sys.argv) > 3 else "none"
+    out_json = sys.argv[4] if len(sys.argv) > 4 else os.path.join(HERE, "reference_main_trace.json")
     config = load_reference(n)
     for m in ["matplotlib", "matplotlib.pyplot", "matplotlib.colors", "matplotlib.patches", "matplotlib.cm", "matplotlib.gridspec",
               "matplotlib.animation", "mpl_toolkits", "mpl_toolkits.mplot3d", "mpl_toolkits.axes_grid1", "seaborn"]:
@@ -212,28 +221,48 @@ if __name__ == "__main__":
     sys.argv = ["main.py"]
     np.random.seed(20240601); random.seed(20240601)
     t0 = time.time()
+    fields = {}
+    marks = []
+    ok_flags = []
     with quiet():
         spec.loader.exec_module(ref_main)
-        # the adapter's hand-written forwards (main.py:417-439) call the solver from main.py: logged by the class wrappers
-        sim = ref_main.CoffeeSimulation()
-    print(f"CoffeeSimulation constructed in {time.time() - t0:.0f} s, {len(TRACE)} calls recorded", flush=True)
-    fields = {}
-    marks = [{"phase": "constructed", "calls": len(TRACE)}]
-    snapshot(sim, "init", fields)
-    ok_all = True
-    for it in range(steps):
-        with quiet():
-            ok = sim.step()
-        ok_all &= bool(ok)
+    # `python main.py debug <steps> <pressure_mode>` = run_debug_simulation (main.py:1250-1357, BASELINE configs[0]); the two hooks only
+    # take snapshots: after the constructor returns and after every CoffeeSimulation.step()
+    ctor, step = ref_main.CoffeeSimulation.__init__, ref_main.CoffeeSimulation.step
+
+    def ctor_hook(self, *a, **kw):
+        ctor(self, *a, **kw)
+        marks.append({"phase": "constructed", "calls": len(TRACE)})
+        snapshot(self, "init", fields)
+        SIM.append(self)
+        print(f"CoffeeSimulation constructed in {time.time() - t0:.0f} s, {len(TRACE)} calls recorded", file=sys.stderr, flush=True)
+
+    def step_hook(self):
+        ok = step(self)
+        it = len(ok_flags)
+        ok_flags.append(bool(ok))
         marks.append({"phase": f"step_{it}", "calls": len(TRACE), "ok": bool(ok)})
-        snapshot(sim, f"step{it}", fields)
-        print(f"step {it}: ok={ok}, {len(TRACE)} calls, max|u| = {np.abs(fields[f'step{it}_u']).max():.3e}", flush=True)
+        snapshot(self, f"step{it}", fields)
+        print(f"step {it}: ok={ok}, {len(TRACE)} calls, max|u| = {np.abs(fields[f'step{it}_u']).max():.3e}", file=sys.stderr, flush=True)
+        if len(ok_flags) == steps:
+            raise StopRecording()          # what follows in run() is report generation through matplotlib (mocked here: it never ends)
+        return ok
+
+    ref_main.CoffeeSimulation.__init__ = ctor_hook
+    ref_main.CoffeeSimulation.step = step_hook
+    try:
+        with quiet():
+            ref_main.run_debug_simulation(max_steps=steps, pressure_mode=pressure_mode)
+    except StopRecording:
+        pass
+    marks.append({"phase": "finished", "calls": len(TRACE)})
+    ok_all = all(ok_flags) and len(ok_flags) == steps
     out = {
-        "grid": n, "steps": steps, "all_steps_ok": ok_all,
-        "solver_class": type(sim.lbm._solver).__name__,
+        "grid": n, "steps": steps, "all_steps_ok": ok_all, "command": f"python main.py debug {steps} {pressure_mode}",
+        "solver_class": type(SIM[0].lbm._solver).__name__,
         "constants": {"GRAVITY_LU": float(config.GRAVITY_LU), "DT": float(config.DT), "SCALE_TIME": float(config.SCALE_TIME),
                       "SCALE_LENGTH": float(config.SCALE_LENGTH), "TAU_WATER": float(config.TAU_WATER), "TAU_AIR": float(config.TAU_AIR)},
-        "probes": probes(sim),
+        "probes": probes(SIM[0]),
         "marks": marks,
         "trace": TRACE,
         "field_readers": {k: sorted(v) for k, v in sorted(READERS.items())},
