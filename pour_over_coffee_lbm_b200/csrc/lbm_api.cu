@@ -32,7 +32,7 @@ cudaError_t launch_forchheimer_force(const Grid &, const float *, const uint8_t 
 cudaError_t launch_density_drive(const Grid &, float *, const uint8_t *, const float *, float, float, float, float, cudaStream_t);
 cudaError_t launch_add_reaction(const Grid &, const float *, const uint8_t *, float *, cudaStream_t);
 cudaError_t run_selftest_math(unsigned long long[7], const StepArgs &, cudaStream_t);
-cudaError_t launch_field_statistics(const Grid &, const float *, const float *, const uint8_t *, void *, int, double *, cudaStream_t);
+cudaError_t launch_field_statistics(const Grid &, const float *, const float *, const uint8_t *, const unsigned long long *, long long, void *, int, double *, cudaStream_t);
 cudaError_t launch_bounce_slots(const Grid &, float *, const uint8_t *, const unsigned long long *, int, int, cudaStream_t);
 cudaError_t launch_particles_couple(const Grid &, const float *, float *, const lbm_particles &, float, float, float, cudaStream_t);
 cudaError_t launch_particles_under_relax(const lbm_particles &, float, cudaStream_t);
@@ -759,7 +759,12 @@ int lbm_field_statistics(lbm_ctx *ctx, const float *rho, const float *u, const u
     cudaSetDevice(ctx->device);      // launches follow the context's device, whatever the caller's current device is
     const int blocks = ctx->sm_count * 8;
     if (!ctx->d_stat_scratch) CUDA_OK(ctx, cudaMalloc(&ctx->d_stat_scratch, (size_t)blocks * 8 * sizeof(double)));
-    CUDA_OK(ctx, launch_field_statistics(ctx->g, rho, u, flags, ctx->d_stat_scratch, blocks, out8, (cudaStream_t)stream));
+    // the packed quad list of the four-cell walls kernel, when it was built for exactly this flag field: the solid part of the box is
+    // never visited and a quad's flags and data are fetched together (lbm_aux.cu)
+    const bool listed = flags && ctx->list_flags == flags && ctx->list_ty == 1 && chord_lists(ctx, ctx->list_vec) && ctx->d_ctiles != nullptr &&
+                        (int)ctx->tile_off.size() == ctx->g.nz + 1;
+    CUDA_OK(ctx, launch_field_statistics(ctx->g, rho, u, flags, listed ? ctx->d_ctiles : nullptr, listed ? (long long)ctx->tile_off[ctx->g.nz] * 32 : 0,
+                                         ctx->d_stat_scratch, blocks, out8, (cudaStream_t)stream));
     ctx->launches += 2;
     return 0;
 }

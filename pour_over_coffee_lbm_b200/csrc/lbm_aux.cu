@@ -239,16 +239,19 @@ __global__ void pressure_gradient_chord_kernel(Grid G, const float *rho, const u
     const int xb = (int)(e & 0xfffu) * 4, y = (int)((e >> 12) & 0xffffu), z = (int)((e >> 28) & 0xffffu);
     const long long n = G.vol;
     const long long c = ((long long)(z + G.zg) * G.ny + y) * G.nx + xb;
-    const unsigned fw = flags ? *reinterpret_cast<const unsigned *>(flags + c) : 0u;
+    // every load is issued before anything branches on the flag word (a flags -> branch -> rho chain is one more DRAM round trip per
+    // thread, and 99 % of the listed quads hold a fluid cell); a neighbour outside the box re-reads the quad itself
+    const unsigned fw = flags ? __ldg(reinterpret_cast<const unsigned *>(flags + c)) : 0u;
     constexpr unsigned SOLID4 = 0x01010101u * LBM_FLAG_SOLID;
-    if ((fw & SOLID4) == SOLID4) return;
     const int k = G.z0 + z;
-    const float4 r = *reinterpret_cast<const float4 *>(rho + c);
-    const float4 ym = y > 0 ? *reinterpret_cast<const float4 *>(rho + c - G.nx) : r;
-    const float4 yq = y < G.ny - 1 ? *reinterpret_cast<const float4 *>(rho + c + G.nx) : r;
-    const float4 zm = k > 0 ? *reinterpret_cast<const float4 *>(rho + c - G.plane) : r;
-    const float4 zq = k < G.nz_global - 1 ? *reinterpret_cast<const float4 *>(rho + c + G.plane) : r;
-    const float xm = xb > 0 ? rho[c - 1] : r.x, xq = xb + 4 < G.nx ? rho[c + 4] : r.w;
+    const float *pr = rho + c;
+    const float4 r = __ldg(reinterpret_cast<const float4 *>(pr));
+    const float4 ym = __ldg(reinterpret_cast<const float4 *>(pr - (y > 0 ? G.nx : 0)));
+    const float4 yq = __ldg(reinterpret_cast<const float4 *>(pr + (y < G.ny - 1 ? G.nx : 0)));
+    const float4 zm = __ldg(reinterpret_cast<const float4 *>(pr - (k > 0 ? G.plane : 0)));
+    const float4 zq = __ldg(reinterpret_cast<const float4 *>(pr + (k < G.nz_global - 1 ? G.plane : 0)));
+    const float xm = __ldg(pr - (xb > 0 ? 1 : 0)), xq = __ldg(pr + (xb + 4 < G.nx ? 4 : 3));
+    if ((fw & SOLID4) == SOLID4) return;
     const float r0[4] = {r.x, r.y, r.z, r.w}, lo[4] = {xm, r.x, r.y, r.z}, hi[4] = {r.y, r.z, r.w, xq};
     const float ylo[4] = {ym.x, ym.y, ym.z, ym.w}, yhi[4] = {yq.x, yq.y, yq.z, yq.w};
     const float zlo[4] = {zm.x, zm.y, zm.z, zm.w}, zhi[4] = {zq.x, zq.y, zq.z, zq.w};
@@ -925,6 +928,39 @@ __global__ void __launch_bounds__(256) field_statistics_kernel(Grid G, const flo
     const StatPartial b = stat_block_reduce(stat_widen(s));
     if (threadIdx.x == 0) partials[blockIdx.x] = b;
 }
+// Over the packed quad list of the four-cell walls kernel (every quad whose 32-byte sector holds a fluid cell, in memory order; owned
+// planes only): the list entry gives the address, so the flag word and the four data vectors of a quad are ONE round trip -- the dense
+// scan above has to see a flag word before it may fetch the data behind it.  Two list entries per loop trip, loads of both first.
+__global__ void __launch_bounds__(256) field_statistics_quads_kernel(Grid G, const float *rho, const float *u, const uint8_t *flags,
+                                                                     const unsigned long long *quads, long long n_slots, StatPartial *partials) {
+    StatLocal s;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < n_slots; i0 += 2 * stride) {
+        unsigned long long e[2];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) e[t] = i0 + t * stride < n_slots ? __ldg(quads + i0 + t * stride) : 0ull;      // bit 44 clear: skipped
+        unsigned fw[2]; float4 r[2], x[2], y[2], z[2];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {        // dead slots sit on cell (0, 0, 0): loaded, never counted
+            const long long c = ((long long)((int)((e[t] >> 28) & 0xffffu) + G.zg) * G.ny + (int)((e[t] >> 12) & 0xffffu)) * G.nx + (int)(e[t] & 0xfffu) * 4;
+            fw[t] = __ldg(reinterpret_cast<const unsigned *>(flags + c));
+            r[t] = __ldcs(reinterpret_cast<const float4 *>(rho + c));
+            x[t] = __ldcs(reinterpret_cast<const float4 *>(u + c));
+            y[t] = __ldcs(reinterpret_cast<const float4 *>(u + G.vol + c));
+            z[t] = __ldcs(reinterpret_cast<const float4 *>(u + 2 * G.vol + c));
+        }
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            if (!(e[t] & (1ull << 44))) continue;
+            if (!(fw[t] & 0x00000001u)) stat_cell(s, r[t].x, x[t].x, y[t].x, z[t].x);
+            if (!(fw[t] & 0x00000100u)) stat_cell(s, r[t].y, x[t].y, y[t].y, z[t].y);
+            if (!(fw[t] & 0x00010000u)) stat_cell(s, r[t].z, x[t].z, y[t].z, z[t].z);
+            if (!(fw[t] & 0x01000000u)) stat_cell(s, r[t].w, x[t].w, y[t].w, z[t].w);
+        }
+    }
+    const StatPartial b = stat_block_reduce(stat_widen(s));
+    if (threadIdx.x == 0) partials[blockIdx.x] = b;
+}
 __global__ void __launch_bounds__(256) field_statistics_fold_kernel(const StatPartial *partials, int n, double *out) {
     // thread t folds partials t, t + 256, ... in index order; the block reduction order is fixed as well
     StatPartial s = stat_identity();
@@ -935,7 +971,13 @@ __global__ void __launch_bounds__(256) field_statistics_fold_kernel(const StatPa
         for (int k = 0; k < 8; ++k) out[k] = s.v[k];
     }
 }
-cudaError_t launch_field_statistics(const Grid &G, const float *rho, const float *u, const uint8_t *flags, void *scratch, int blocks, double *out, cudaStream_t s) {
+cudaError_t launch_field_statistics(const Grid &G, const float *rho, const float *u, const uint8_t *flags, const unsigned long long *quads, long long n_slots,
+                                    void *scratch, int blocks, double *out, cudaStream_t s) {
+    if (quads && flags && n_slots > 0 && (((uintptr_t)rho | (uintptr_t)u) & 15u) == 0 && ((uintptr_t)flags & 3u) == 0) {
+        field_statistics_quads_kernel<<<blocks, 256, 0, s>>>(G, rho, u, flags, quads, n_slots, (StatPartial *)scratch);
+        field_statistics_fold_kernel<<<1, 256, 0, s>>>((const StatPartial *)scratch, blocks, out);
+        return cudaGetLastError();
+    }
     const bool vec4 = G.nx % 4 == 0 && G.vol % 4 == 0 && (((uintptr_t)rho | (uintptr_t)u) & 15u) == 0 && ((uintptr_t)flags & 3u) == 0;
     if (vec4) field_statistics_kernel<4><<<blocks, 256, 0, s>>>(G, rho, u, flags, (StatPartial *)scratch);
     else field_statistics_kernel<1><<<blocks, 256, 0, s>>>(G, rho, u, flags, (StatPartial *)scratch);

@@ -237,10 +237,11 @@ def test_pressure_gradient_and_forchheimer_force_bit_exact():
     assert np.abs(got[zone]).max() > 0          # tests/test_forchheimer.py:31-74: non-zero in the zone
 
 
-def test_fused_field_statistics_match_numpy_and_are_deterministic():
-    """lbm_field_statistics (one pass, device result) against NumPy on a V60 mask with injected NaN / Inf."""
+@pytest.mark.parametrize("compat,n", [("reference", 48), ("physical", 48), ("reference", 30)], ids=["dense_scan_vec4", "quad_list", "dense_scan_ragged"])
+def test_fused_field_statistics_match_numpy_and_are_deterministic(compat, n):
+    """lbm_field_statistics (one pass, device result) against NumPy on a V60 mask with injected NaN / Inf: the dense scans (four cells
+    per thread / one cell per thread on a ragged nx) and the scan over the packed quad list of the four-cell walls kernel."""
     import torch
-    n = 48
     st = H.reference_v60_state(n, seed=7)
     rng = np.random.default_rng(2)
     rho = (1.0 + 0.05 * rng.standard_normal(st.rho.shape)).astype(np.float32)
@@ -249,7 +250,7 @@ def test_fused_field_statistics_match_numpy_and_are_deterministic():
     idx = np.argwhere(fluid)
     rho[tuple(idx[3])] = np.nan; rho[tuple(idx[40])] = np.inf; u[tuple(idx[77])][1] = np.nan; u[tuple(idx[90])][2] = -np.inf
     from pour_over_coffee_lbm_b200.config import LBMConfig
-    eng = _engine(n, n, n, compat="reference", periodic=(False, False, False), walls=True, config=LBMConfig(NX=n, NY=n, NZ=n))
+    eng = _engine(n, n, n, compat=compat, periodic=(False, False, False), walls=True, config=LBMConfig(NX=n, NY=n, NZ=n))
     eng.solid.copy_(_torch(H.to_dev_scalar(st.solid))); eng.pack_flags()
     eng.rho.copy_(_torch(H.to_dev_scalar(rho))); eng.u.copy_(_torch(H.to_dev_vec(u)))
     a = eng.field_statistics().clone(); b = eng.field_statistics().clone()
