@@ -164,14 +164,14 @@ static bool phys_walls(const lbm_params &p) { return p.compat == LBM_COMPAT_PHYS
 static bool tma_eligible(const lbm_ctx *ctx);
 static bool tma_eligible_params(const lbm_ctx *ctx) {
     const lbm_params &p = ctx->p;
-    return phys_walls(p) && ctx->tma_enabled && p.vec == 0 && !(p.periodic & 3) && p.nx % 16 == 0 && p.nx >= 16;
+    return phys_walls(p) && ctx->tma_enabled && p.vec == 0 && !(p.periodic & 3) && p.nx % 16 == 0 && p.nx >= 16 && !(p.mrt_magic > 0.0f);
 }
 
 static int pick_vec(const lbm_ctx *ctx) {
     int vec = ctx->p.vec;
-    // the two-rate MRT collision is built into the one- and two-cell kernels only (lbm_phys.cuh:collide_phys)
+    // the two-rate MRT collision: behind walls every kernel has it (the four-cell kernel as a separate instantiation, the one- /
+    // two-cell kernels at run time); the dense periodic path only in its one-cell form (lbm_phys.cuh:collide_phys)
     const bool mrt = ctx->p.compat == LBM_COMPAT_PHYSICAL && ctx->p.mrt_magic > 0.0f;
-    if (mrt && phys_walls(ctx->p)) vec = (vec == 1) ? 1 : 2;
     if (mrt && !phys_walls(ctx->p)) vec = 1;
     if (phys_walls(ctx->p)) {
         // four cells per thread on chord-fitted tiles (lbm_phys_chord.cuh) when rows are 16-byte multiples, else two cells per
@@ -206,7 +206,7 @@ static StepKernel lookup(const lbm_params &p, int vec, int collide, int *block);
 // for every field incl. the u8 flags, and the caller left `vec` on auto (vec = 1 / 2 select the register-staged kernels).
 static bool tma_eligible(const lbm_ctx *ctx) {
     const lbm_params &p = ctx->p;
-    return phys_walls(p) && ctx->tma_enabled && p.vec == 0 && !(p.periodic & 3) && p.nx % 16 == 0 && p.nx >= 16;
+    return phys_walls(p) && ctx->tma_enabled && p.vec == 0 && !(p.periodic & 3) && p.nx % 16 == 0 && p.nx >= 16 && !(p.mrt_magic > 0.0f);
 }
 static void feature_bits(const lbm_params &p, int *forced, int *les, int *porous) {
     *forced = ((p.features & (LBM_FEAT_FORCE | LBM_FEAT_PHASE)) != 0 ? 1 : 0) | ((p.features & LBM_FEAT_DRIVE) ? 2 : 0);
@@ -413,6 +413,7 @@ static StepKernel lookup(const lbm_params &p, int vec, int collide, int *block) 
     int forced, les, porous;
     feature_bits(p, &forced, &les, &porous);
     if (!collide) forced &= 1;                       // moments only: the drive does not enter
+    else if (p.compat == LBM_COMPAT_PHYSICAL && walls && vec == 4 && p.mrt_magic > 0.0f) forced |= 4;      // MRT instantiation of the four-cell kernel
     const int group = p.compat * 2 + walls;
     const bool strict = (p.features & LBM_FEAT_STRICT) != 0;
 #define LBM_PICK(g) (strict ? lookup_strict_g##g##_fn(forced, les, porous, vec, collide, block) \
@@ -631,7 +632,6 @@ int lbm_step(lbm_ctx *ctx, lbm_fields *f, int nsteps, int write_macro_every, voi
     if (ref_les && write_macro_every != 1) return fail(ctx, "compat=reference with LES needs u every step (write_macro_every must be 1)");
     if (ref_les && (!f->u_src || !f->u_dst || f->u_src == f->u_dst)) return fail(ctx, "compat=reference with LES needs distinct u_src/u_dst");
     const bool drive = (p.features & LBM_FEAT_DRIVE) != 0;
-    if (drive && p.mrt_magic > 0.0f) return fail(ctx, "LBM_FEAT_DRIVE is fused into the four-cell kernel, which is built for BGK only: run the MRT collision with the stand-alone pressure-gradient producer");
     if (drive && !(phys_walls(p) && vec == 4)) return fail(ctx, "LBM_FEAT_DRIVE is fused into the four-cell walls kernel of compat=physical (LBM_FEAT_WALLS, nx % 4 == 0, vec = 0 or 4)");
     if (drive && write_macro_every != 1) return fail(ctx, "LBM_FEAT_DRIVE reads the previous step's rho (write_macro_every must be 1)");
     if (drive && (!f->rho || !f->rho_src || f->rho == f->rho_src)) return fail(ctx, "LBM_FEAT_DRIVE needs distinct rho (written) and rho_src (previous step) fields");

@@ -246,7 +246,7 @@ static __device__ __noinline__ void chord_open_faces(const unsigned s_own, const
 
 // (3) + (4): collide the tile staged at s_own (after its cp.async group has landed and the warp has synchronised), write back.
 // s_row0 = shared-window address of lane 0's words in row 0 of the stage.
-template <bool FORCED, bool LES, bool POROUS, bool DRIVE, bool COLLIDE>
+template <bool FORCED, bool LES, bool POROUS, bool DRIVE, bool COLLIDE, bool MRT>
 __device__ __forceinline__ void chord_compute_store(const StepArgs &P, const ChordGeom &t, const uint2 tl, const ChordAux &a, const float (&F)[3][4],
                                                     const float (&ph)[4], const unsigned lane, const unsigned s_own, const unsigned s_row0,
                                                     const unsigned s_edge) {
@@ -326,7 +326,7 @@ __device__ __forceinline__ void chord_compute_store(const StepArgs &P, const Cho
 #ifdef LBM_EXP_COPY      /* timing experiment: no collision (wrong results) */
         mac.rho = mac.ux = mac.uy = mac.uz = fp[0];
 #else
-        collide_phys<P2, HAS_F, LES, POROUS, COLLIDE, true>(fp, in, mac, P, has_phase, has_force);
+        collide_phys<P2, HAS_F, LES, POROUS, COLLIDE, true, MRT>(fp, in, mac, P, has_phase, has_force);
 #endif
         if constexpr (COLLIDE) {
             __syncwarp();                                                // every lane has read this pair's inputs
@@ -388,8 +388,9 @@ __device__ __forceinline__ void chord_compute_store(const StepArgs &P, const Cho
     }
 }
 
-// One tile (32 consecutive entries of the packed quad list) per warp.
-template <bool FORCED, bool LES, bool POROUS, bool DRIVE, int BLOCK, bool COLLIDE, int MINB>
+// One tile (32 consecutive entries of the packed quad list) per warp.  MRT = true: the instantiation for lbm_params.mrt_magic > 0 (two-rate
+// collision, three more live register pairs); the BGK instantiations, which carry the roofline numbers, are built without it.
+template <bool FORCED, bool LES, bool POROUS, bool DRIVE, int BLOCK, bool COLLIDE, int MINB, bool MRT = false>
 __global__ void __launch_bounds__(BLOCK, MINB) phys_chord_kernel(const __grid_constant__ StepArgs P) {
     __shared__ __align__(16) float stage[BLOCK / 32][CHORD_STAGE];
     const unsigned lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
@@ -435,7 +436,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) phys_chord_kernel(const __grid_co
 #endif
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
-    chord_compute_store<FORCED, LES, POROUS, DRIVE, COLLIDE>(P, t, tl, a, F, ph, lane, s_own, s_row0, s_edge);
+    chord_compute_store<FORCED, LES, POROUS, DRIVE, COLLIDE, MRT>(P, t, tl, a, F, ph, lane, s_own, s_row0, s_edge);
 }
 
 #endif  // LBM_EMULATE_ON_HOST

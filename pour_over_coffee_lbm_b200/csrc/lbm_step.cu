@@ -43,51 +43,52 @@ constexpr int chord_blocks() { return LBM_CHORD_WARPS * 32 / BLOCK; }
 template <int MODE, int VEC>
 constexpr int default_block() { return MODE == MODE_BULK ? 64 : (VEC == 1 ? 256 : 128); }
 
-template <int MODE, bool FORCED, bool LES, bool POROUS, int VEC, bool COLLIDE, bool DRIVE = false>
+template <int MODE, bool FORCED, bool LES, bool POROUS, int VEC, bool COLLIDE, bool DRIVE = false, bool MRT = false>
 static StepKernel pick() {
     constexpr int BLOCK = default_block<MODE, VEC>();
     if constexpr (POROUS && !G_WALLS) return nullptr;          // the filter zone lives in the flag byte
     else if constexpr (!COLLIDE && LES) return nullptr;
     else if constexpr (G_WALLS && G_COMPAT == LBM_COMPAT_PHYSICAL) {
-        // VEC = 4: chord-fitted tiles + wall links (lbm_phys_chord.cuh), the only kernel that fuses the pressure drive
-        if constexpr (VEC == 4) return phys_chord_kernel<FORCED, LES, POROUS, DRIVE, BLOCK, COLLIDE, chord_blocks<BLOCK>()>;
-        else if constexpr (DRIVE) return nullptr;
+        // VEC = 4: packed quad list + wall links (lbm_phys_chord.cuh), the only kernel that fuses the pressure drive; the MRT
+        // instantiations of it serve lbm_params.mrt_magic > 0 (the one- / two-cell kernels decide MRT at run time)
+        if constexpr (VEC == 4) return phys_chord_kernel<FORCED, LES, POROUS, DRIVE, BLOCK, COLLIDE, chord_blocks<BLOCK>(), MRT>;
+        else if constexpr (DRIVE || MRT) return nullptr;
         else return phys_walls_kernel<FORCED, LES, POROUS, VEC, BLOCK, COLLIDE, min_blocks_phys_walls<VEC, BLOCK>()>;
     }
-    else if constexpr (DRIVE) return nullptr;
+    else if constexpr (DRIVE || MRT) return nullptr;
     else if constexpr (VEC == 2) return nullptr;
     else if constexpr (!COLLIDE && VEC != 1) return nullptr;
     else return step_kernel<LBM_STRICT_BUILD, G_COMPAT, MODE, FORCED, LES, POROUS, VEC, BLOCK, COLLIDE, min_blocks<VEC, BLOCK>()>;
 }
 
-// `forced`: bit 0 = body_force / phase inputs, bit 1 = fused pressure-gradient drive (LBM_FEAT_DRIVE)
+template <int MODE, int VEC, bool COLLIDE, bool DRIVE, bool MRT>
+static StepKernel pick_key(int key) {
+    switch (key) {
+        case 0: return pick<MODE, false, false, false, VEC, COLLIDE, DRIVE, MRT>();
+        case 1: return pick<MODE, false, false, true, VEC, COLLIDE, DRIVE, MRT>();
+        case 2: return pick<MODE, false, true, false, VEC, COLLIDE, DRIVE, MRT>();
+        case 3: return pick<MODE, false, true, true, VEC, COLLIDE, DRIVE, MRT>();
+        case 4: return pick<MODE, true, false, false, VEC, COLLIDE, DRIVE, MRT>();
+        case 5: return pick<MODE, true, false, true, VEC, COLLIDE, DRIVE, MRT>();
+        case 6: return pick<MODE, true, true, false, VEC, COLLIDE, DRIVE, MRT>();
+        default: return pick<MODE, true, true, true, VEC, COLLIDE, DRIVE, MRT>();
+    }
+}
+// `forced`: bit 0 = body_force / phase inputs, bit 1 = fused pressure-gradient drive (LBM_FEAT_DRIVE), bit 2 = the MRT instantiation
+// of the four-cell kernel (the caller sets it only for vec = 4 behind walls in compat = physical with mrt_magic > 0)
 template <int MODE, int VEC, bool COLLIDE>
 static StepKernel pick_feat(int forced, int les, int porous) {
     const int key = ((forced & 1) ? 4 : 0) | (les ? 2 : 0) | (porous ? 1 : 0);
-    if (forced & 2) {
+    if (forced & 6) {
         if constexpr (COLLIDE && VEC == 4) {
-            switch (key) {
-                case 0: return pick<MODE, false, false, false, VEC, COLLIDE, true>();
-                case 1: return pick<MODE, false, false, true, VEC, COLLIDE, true>();
-                case 2: return pick<MODE, false, true, false, VEC, COLLIDE, true>();
-                case 3: return pick<MODE, false, true, true, VEC, COLLIDE, true>();
-                case 4: return pick<MODE, true, false, false, VEC, COLLIDE, true>();
-                case 5: return pick<MODE, true, false, true, VEC, COLLIDE, true>();
-                case 6: return pick<MODE, true, true, false, VEC, COLLIDE, true>();
-                default: return pick<MODE, true, true, true, VEC, COLLIDE, true>();
+            switch (forced & 6) {
+                case 2: return pick_key<MODE, VEC, COLLIDE, true, false>(key);
+                case 4: return pick_key<MODE, VEC, COLLIDE, false, true>(key);
+                default: return pick_key<MODE, VEC, COLLIDE, true, true>(key);
             }
         } else return nullptr;
     }
-    switch (key) {
-        case 0: return pick<MODE, false, false, false, VEC, COLLIDE>();
-        case 1: return pick<MODE, false, false, true, VEC, COLLIDE>();
-        case 2: return pick<MODE, false, true, false, VEC, COLLIDE>();
-        case 3: return pick<MODE, false, true, true, VEC, COLLIDE>();
-        case 4: return pick<MODE, true, false, false, VEC, COLLIDE>();
-        case 5: return pick<MODE, true, false, true, VEC, COLLIDE>();
-        case 6: return pick<MODE, true, true, false, VEC, COLLIDE>();
-        default: return pick<MODE, true, true, true, VEC, COLLIDE>();
-    }
+    return pick_key<MODE, VEC, COLLIDE, false, false>(key);
 }
 
 #define LBM_CAT2(a, b, c) a##b##_##c
@@ -138,7 +139,7 @@ StepKernel LBM_LOOKUP(int forced, int les, int porous, int vec, int collide, int
     StepKernel k = nullptr;
     constexpr int MAIN = G_WALLS ? MODE_BULK : MODE_DENSE;
     const int def_block = vec == 1 ? default_block<MAIN, 1>() : (vec == 2 ? default_block<MAIN, 2>() : default_block<MAIN, 4>());
-    if (collide && forced == 1 && les && porous && *block && *block != def_block) {
+    if (collide && forced == 1 && les && porous && *block && *block != def_block) {      // BGK, no fused drive
         k = pick_tuned(vec, *block);
         if (k) { if (*block == 65 || *block == 66) *block = 64; if (vec == 4) *block = 64; return k; }
     }

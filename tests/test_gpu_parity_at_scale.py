@@ -101,8 +101,8 @@ def test_physical_v60_512_every_feature_bit_exact(n):
     _run_physical_against_c_twin(eng, p, 2, walls=True)
 
 
-@pytest.mark.parametrize("with_body_force", [True, False])
-def test_fused_pressure_gradient_drive_equals_producer_plus_step(with_body_force):
+@pytest.mark.parametrize("with_body_force,mrt_magic", [(True, 0.0), (False, 0.0), (True, 0.1875)], ids=["body_force", "drive_only", "body_force_mrt"])
+def test_fused_pressure_gradient_drive_equals_producer_plus_step(with_body_force, mrt_magic):
     """LBM_FEAT_DRIVE (the drive evaluated inside the step kernel from the previous step's rho) against
     lbm_pressure_gradient_force(_set) + lbm_step on a V60 96^3 box, 10 steps: populations, rho, u bit for bit."""
     import torch
@@ -116,7 +116,7 @@ def test_fused_pressure_gradient_drive_equals_producer_plus_step(with_body_force
                            u=1e-3 * torch.randn((3, n, n, n), device="cuda", generator=g))
         if e.body_force is not None:
             e.body_force.copy_(1e-6 * torch.randn((3, n, n, n), device="cuda", generator=g))
-        e.set_params(drive_max_force=0.12, drive_scale=0.5)
+        e.set_params(drive_max_force=0.12, drive_scale=0.5, mrt_magic=mrt_magic)      # mrt_magic > 0: the MRT instantiation of the four-cell kernel
         return e
     a = make(False, True)
     base = a.body_force.clone()

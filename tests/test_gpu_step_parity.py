@@ -186,12 +186,13 @@ def test_physical_walls_obstacles_open_and_periodic_faces(periodic, nx, path, mo
     assert np.array_equal(H.from_dev_vec(eng.u)[fluid], u1[fluid])
 
 
-@pytest.mark.parametrize("case", ["periodic_dense", "v60_all_features", "ragged_obstacles"])
+@pytest.mark.parametrize("case", ["periodic_dense", "v60_all_features", "v60_all_features_two_cell", "v60_all_features_one_cell", "ragged_obstacles"])
 def test_physical_mrt_two_rate_collision_bit_exact(case):
     """lbm_params.mrt_magic > 0: the multiple-relaxation-time collision in its two-rate form (pair sums at 1 / tau, pair differences
     at 1 / tau_odd, (tau - 1/2)(tau_odd - 1/2) = magic; Guo forcing split the same way) against oracle.step_physical with the same
     parameter -- dense periodic box, the V60 box with LES + forcing + porous drag + bounce-back, a ragged box with obstacles on open
-    faces.  The library runs it on the one- / two-cell kernels (lbm_api.cu:pick_vec); magic = 0 stays the BGK path of every other test."""
+    faces.  Behind walls the V60 box runs the MRT instantiation of the four-cell quad-list kernel (default) and, with vec = 2 / 1, the
+    two- / one-cell kernels; the ragged box (nx = 30) the two-cell kernel; magic = 0 stays the BGK path of every other test."""
     magic = 0.1875
     rng = np.random.default_rng(17)
     if case == "periodic_dense":
@@ -212,7 +213,8 @@ def test_physical_mrt_two_rate_collision_bit_exact(case):
         bgk.step(steps)
         assert not np.array_equal(H.from_dev_pop(bgk.populations), g)
         return
-    if case == "v60_all_features":
+    vec = {"v60_all_features_two_cell": 2, "v60_all_features_one_cell": 1}.get(case, 0)
+    if case.startswith("v60_all_features"):
         nx = ny = nz = 32
         cfg = R.RefConfig(NX=nx, NY=ny, NZ=nz)
         solid = R.v60_solid(cfg); zone = R.filter_zones(cfg)
@@ -234,7 +236,7 @@ def test_physical_mrt_two_rate_collision_bit_exact(case):
     for _ in range(steps):
         g, rho, u = R.step_physical(g, p, solid=solid, body_force=bf, phase=phase, filter_zone=zone, les_mask=les_mask)
     eng = _engine(nx, ny, nz, compat="physical", periodic=periodic, walls=True, force=True, phase=True, les=True, porous=True, tau=0.56,
-                  tau_air=0.8, gravity_lu=2e-5, porous_darcy=0.2, porous_forch=0.5, mrt_magic=magic)
+                  tau_air=0.8, gravity_lu=2e-5, porous_darcy=0.2, porous_forch=0.5, mrt_magic=magic, vec=vec)
     eng.solid.copy_(_torch(H.to_dev_scalar(solid))); eng.filter_zone.copy_(_torch(H.to_dev_scalar(np.asarray(zone, np.int32))))
     eng.les_mask.copy_(_torch(H.to_dev_scalar(les_mask))); eng.pack_flags()
     eng.phase.copy_(_torch(H.to_dev_scalar(phase))); eng.body_force.copy_(_torch(H.to_dev_vec(bf)))
