@@ -169,10 +169,8 @@ static bool tma_eligible_params(const lbm_ctx *ctx) {
 
 static int pick_vec(const lbm_ctx *ctx) {
     int vec = ctx->p.vec;
-    // the two-rate MRT collision: behind walls every kernel has it (the four-cell kernel as a separate instantiation, the one- /
-    // two-cell kernels at run time); the dense periodic path only in its one-cell form (lbm_phys.cuh:collide_phys)
-    const bool mrt = ctx->p.compat == LBM_COMPAT_PHYSICAL && ctx->p.mrt_magic > 0.0f;
-    if (mrt && !phys_walls(ctx->p)) vec = 1;
+    // the two-rate MRT collision (lbm_phys.cuh:collide_phys): the four-cell kernels (quad list behind walls, dense on periodic boxes) have
+    // separate instantiations for it (lookup), the one- / two-cell kernels decide at run time
     if (phys_walls(ctx->p)) {
         // four cells per thread on chord-fitted tiles (lbm_phys_chord.cuh) when rows are 16-byte multiples, else two cells per
         // thread on packed f32x2 registers (lbm_phys.cuh) on 8-byte rows, else one.  The TMA-staged kernel (LBM_TMA=1, works on
@@ -413,7 +411,7 @@ static StepKernel lookup(const lbm_params &p, int vec, int collide, int *block) 
     int forced, les, porous;
     feature_bits(p, &forced, &les, &porous);
     if (!collide) forced &= 1;                       // moments only: the drive does not enter
-    else if (p.compat == LBM_COMPAT_PHYSICAL && walls && vec == 4 && p.mrt_magic > 0.0f) forced |= 4;      // MRT instantiation of the four-cell kernel
+    else if (p.compat == LBM_COMPAT_PHYSICAL && vec == 4 && p.mrt_magic > 0.0f) forced |= 4;      // MRT instantiation of the four-cell kernels
     const int group = p.compat * 2 + walls;
     const bool strict = (p.features & LBM_FEAT_STRICT) != 0;
 #define LBM_PICK(g) (strict ? lookup_strict_g##g##_fn(forced, les, porous, vec, collide, block) \

@@ -55,7 +55,12 @@ static StepKernel pick() {
         else if constexpr (DRIVE || MRT) return nullptr;
         else return phys_walls_kernel<FORCED, LES, POROUS, VEC, BLOCK, COLLIDE, min_blocks_phys_walls<VEC, BLOCK>()>;
     }
-    else if constexpr (DRIVE || MRT) return nullptr;
+    else if constexpr (DRIVE) return nullptr;
+    else if constexpr (MRT) {      // dense periodic boxes of compat = physical: the packed VEC = 4 collision with the two-rate relaxation
+        if constexpr (G_COMPAT == LBM_COMPAT_PHYSICAL && !G_WALLS && VEC == 4 && COLLIDE)
+            return step_kernel<LBM_STRICT_BUILD, G_COMPAT, MODE, FORCED, LES, POROUS, VEC, BLOCK, COLLIDE, min_blocks<VEC, BLOCK>(), true>;
+        else return nullptr;
+    }
     else if constexpr (VEC == 2) return nullptr;
     else if constexpr (!COLLIDE && VEC != 1) return nullptr;
     else return step_kernel<LBM_STRICT_BUILD, G_COMPAT, MODE, FORCED, LES, POROUS, VEC, BLOCK, COLLIDE, min_blocks<VEC, BLOCK>()>;
@@ -75,7 +80,8 @@ static StepKernel pick_key(int key) {
     }
 }
 // `forced`: bit 0 = body_force / phase inputs, bit 1 = fused pressure-gradient drive (LBM_FEAT_DRIVE), bit 2 = the MRT instantiation
-// of the four-cell kernel (the caller sets it only for vec = 4 behind walls in compat = physical with mrt_magic > 0)
+// of the four-cell kernels (the caller sets it only for vec = 4 in compat = physical with mrt_magic > 0: quad-list kernel behind walls,
+// dense kernel on periodic boxes)
 template <int MODE, int VEC, bool COLLIDE>
 static StepKernel pick_feat(int forced, int les, int porous) {
     const int key = ((forced & 1) ? 4 : 0) | (les ? 2 : 0) | (porous ? 1 : 0);

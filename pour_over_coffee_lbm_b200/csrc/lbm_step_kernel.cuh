@@ -189,7 +189,7 @@ enum { MODE_DENSE = 0, MODE_BULK = 1 };
 
 // The work of one thread: VEC x-consecutive cells starting at (x0, y, z).  No early exit and no branch on the flag
 // byte before the loads (see the comments inside).
-template <int COMPAT, int MODE, bool FORCED, bool LES, bool POROUS, int VEC, bool COLLIDE>
+template <int COMPAT, int MODE, bool FORCED, bool LES, bool POROUS, int VEC, bool COLLIDE, bool MRT = false>
 __device__ __forceinline__ void step_cells(const StepArgs &P, const int x0, const int y, const int z, const bool active,
                                            const unsigned lane) {
     constexpr bool WALLS = MODE != MODE_DENSE;
@@ -326,7 +326,7 @@ __device__ __forceinline__ void step_cells(const StepArgs &P, const int x0, cons
                 in.phase = FORCED ? p2_make(ph[c], ph[c + 1]) : p2_make(0.0f, 0.0f);
                 in.flag[0] = fl[c]; in.flag[1] = fl[c + 1];
                 CellMacro<P2> m;
-                collide_phys<P2, FORCED, LES && COLLIDE, POROUS, COLLIDE>(fp, in, m, P, has_phase, has_force);
+                collide_phys<P2, FORCED, LES && COLLIDE, POROUS, COLLIDE, false, MRT>(fp, in, m, P, has_phase, has_force);
                 if constexpr (COLLIDE) {
 #pragma unroll
                     for (int q = 0; q < Q; ++q) { f[q][c] = p2_lo(fp[q]); f[q][c + 1] = p2_hi(fp[q]); }
@@ -428,7 +428,9 @@ __device__ __forceinline__ void step_cells(const StepArgs &P, const int x0, cons
 
 // BUILD (0 = fast, 1 = strict/-fmad=false) only makes the two builds distinct symbols: without it the
 // linker would merge the identically-named instantiations of the two translation units (ODR).
-template <int BUILD, int COMPAT, int MODE, bool FORCED, bool LES, bool POROUS, int VEC, int BLOCK, bool COLLIDE = true, int MINB = 1>
+// MRT = true: the instantiation of the packed (VEC = 4) collision that honours lbm_params.mrt_magic (compat = physical); the BGK
+// instantiations, which carry the roofline numbers, are built without it.  The one-cell form decides at run time.
+template <int BUILD, int COMPAT, int MODE, bool FORCED, bool LES, bool POROUS, int VEC, int BLOCK, bool COLLIDE = true, int MINB = 1, bool MRT = false>
 __global__ void __launch_bounds__(BLOCK, MINB) step_kernel(const __grid_constant__ StepArgs P) {
     const Grid &G = P.g;
     const unsigned lane = threadIdx.x & 31u;
@@ -441,7 +443,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) step_kernel(const __grid_constant
         int x0 = (int)(e & 0xffu) * (32 * VEC) + (int)lane * VEC;
         const bool active = x0 < G.nx;
         if (!active) x0 = G.nx - VEC;                                    // duplicate of the last lane: loads stay in bounds
-        step_cells<COMPAT, MODE, FORCED, LES, POROUS, VEC, COLLIDE>(P, x0, (int)((e >> 8) & 0xfffu), (int)(e >> 20), active, lane);
+        step_cells<COMPAT, MODE, FORCED, LES, POROUS, VEC, COLLIDE, MRT>(P, x0, (int)((e >> 8) & 0xfffu), (int)(e >> 20), active, lane);
     } else {
         const int nxv = G.nx / VEC;
         const int per_plane = nxv * G.ny;
@@ -451,7 +453,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) step_kernel(const __grid_constant
         if (!active) t = per_plane - 1;
         const int y = t / nxv;
         const int x0 = (t - y * nxv) * VEC;
-        step_cells<COMPAT, MODE, FORCED, LES, POROUS, VEC, COLLIDE>(P, x0, y, z, active, lane);
+        step_cells<COMPAT, MODE, FORCED, LES, POROUS, VEC, COLLIDE, MRT>(P, x0, y, z, active, lane);
     }
 }
 
