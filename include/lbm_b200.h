@@ -92,7 +92,8 @@ typedef struct {
                                  form: the even moments (density, stress: pair sums f_q + f_opp(q)) relax at 1/tau -- tau still sets
                                  the viscosity, LES acts on it -- the odd moments (momentum flux: pair differences) at 1/tau_odd with
                                  (tau - 1/2)(tau_odd - 1/2) = mrt_magic (3/16: exact wall location of halfway bounce-back, 1/4: most
-                                 stable).  The reference names MRT only in a docstring (legacy/lbm_solver.py:833). */
+                                 stable).  Every kernel of compat = physical has it (the four-cell kernels as separate instantiations,
+                                 the fused drive included).  The reference names MRT only in a docstring (legacy/lbm_solver.py:833). */
 } lbm_params;
 
 typedef struct {
@@ -171,7 +172,9 @@ int  lbm_import_f(lbm_ctx *ctx, const float *f_in, const uint8_t *flags, float *
  *   [7] fluid cells.
  * Replaces visualizer.compute_statistics / get_statistics (src/visualization/visualizer.py:130-183),
  * NumericalStabilityMonitor.check_field_stability (src/core/numerical_stability.py:52-110) and the host-side
- * reductions of main.py:907-912.  flags may be NULL (every cell is fluid). */
+ * reductions of main.py:907-912.  flags may be NULL (every cell is fluid).  When `flags` is the field the four-cell walls kernel's
+ * quad list was built for (lbm_pack_flags), the pass walks that list and never visits the solid part of the box; the sums then
+ * add up in another (still fixed) order than the dense scan's. */
 int  lbm_field_statistics(lbm_ctx *ctx, const float *rho, const float *u, const uint8_t *flags, double *out8, void *stream);
 
 /* ---- neighbours that feed body_force --------------------- */
