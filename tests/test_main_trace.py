@@ -281,3 +281,28 @@ def test_gpu_bare_constructed_pouring_system_finds_its_engine_through_the_fields
         assert float(out[0][0][..., 2].min()) < 0.0
     finally:
         cfgmod.DEFAULT = old
+
+
+def test_bare_pouring_system_host_state_follows_the_recorded_values():
+    """`PrecisePouringSystem()` as main.py:482 constructs it needs no device: the nozzle state is host scalars.  The values main.py
+    printed in the recorded run (flow rate in ml/s after each adjust_flow_rate, get_pouring_info) come out of the facade's host
+    arithmetic; without a solver, a field owner or bind() the kernels refuse to run."""
+    from pour_over_coffee_lbm_b200 import config as cfgmod
+    from pour_over_coffee_lbm_b200.physics import PrecisePouringSystem
+    t = load_trace()
+    old = cfgmod.DEFAULT
+    cfgmod.DEFAULT = cfgmod.LBMConfig(NX=t["grid"], NY=t["grid"], NZ=t["grid"])
+    try:
+        pp = PrecisePouringSystem()
+        checked = 0
+        for r in t["trace"]:
+            if r["on"] != "pouring" or r["call"] in ("__init__", "apply_pouring_force", "apply_gradual_phase_change"):
+                continue
+            out = getattr(pp, r["call"])(*r["args"], **{k: v for k, v in r["kwargs"].items()})
+            _close(out, r.get("returns"), f"pouring.{r['call']}")
+            checked += 1
+        assert checked >= 20
+        with pytest.raises(ValueError):
+            pp.apply_pouring_force(object(), object(), 1.0)          # pouring is active, nothing names an engine
+    finally:
+        cfgmod.DEFAULT = old
