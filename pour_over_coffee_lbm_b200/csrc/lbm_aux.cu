@@ -283,20 +283,11 @@ __global__ void pressure_gradient_chord_kernel(Grid G, const float *rho, const u
     }
 }
 
-// filter_paper.py:471-536
-__global__ void forchheimer_force_kernel(Grid G, const float *u, const uint8_t *flags, float *bf, float K, float beta,
-                                         float c_darcy, float c_forch, float fmax) {
-    const long long n = G.vol;
-    const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (c >= n) return;
-    const int x = (int)(c % G.nx);
-    const int y = (int)((c / G.nx) % G.ny);
-    const int zp = (int)(c / G.plane);
-    const int k = G.z0 + zp - G.zg;
-    if (zp - G.zg < 0 || zp - G.zg >= G.nz) return;
-    if (x < 1 || x > G.nx - 2 || y < 1 || y > G.ny - 2 || k < 1 || k > G.nz_global - 2) return;
-    const unsigned f = flags[c];
-    if (!(f & LBM_FLAG_FILTER) || (f & LBM_FLAG_SOLID)) return;
+// filter_paper.py:471-536.  (x-chunk, y, owned z) launch grid, VEC x-consecutive cells per thread: the coordinates come from the
+// block index (the first version derived them from a linear index over the whole volume with 64-bit divisions) and the flag bytes
+// of a quad are one 32-bit load -- the filter zone is a thin shell, so nearly every thread ends after that word.
+__device__ __forceinline__ void forchheimer_cell(const long long n, const long long c, const float *u, float *bf, float K, float beta, float c_darcy,
+                                                 float c_forch, float fmax) {
     const float ux = u[c], uy = u[n + c], uz = u[2 * n + c];
     const float umag = sqrtf(dot3(ux, uy, uz, ux, uy, uz));
     if (!(umag > 1e-8f) || !(K > 1e-12f)) return;
@@ -306,14 +297,58 @@ __global__ void forchheimer_force_kernel(Grid G, const float *u, const uint8_t *
     if (mag > fmax) { const float s = fmax / mag; rx = rx * s; ry = ry * s; rz = rz * s; }
     bf[c] = bf[c] + rx; bf[n + c] = bf[n + c] + ry; bf[2 * n + c] = bf[2 * n + c] + rz;
 }
+template <int VEC>
+__global__ void forchheimer_force_kernel(Grid G, const float *u, const uint8_t *flags, float *bf, float K, float beta,
+                                         float c_darcy, float c_forch, float fmax) {
+    const int x0 = (int)(blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    if (x0 >= G.nx) return;
+    const int y = (int)blockIdx.y, z = (int)blockIdx.z, k = G.z0 + z;
+    if (y < 1 || y > G.ny - 2 || k < 1 || k > G.nz_global - 2) return;
+    const long long c0 = ((long long)(z + G.zg) * G.ny + y) * G.nx + x0;
+    unsigned fw;
+    if constexpr (VEC == 4) fw = *reinterpret_cast<const unsigned *>(flags + c0);
+    else fw = flags[c0];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+        const int x = x0 + j;
+        const unsigned f = (fw >> (8 * j)) & 0xffu;
+        if (x < 1 || x > G.nx - 2 || !(f & LBM_FLAG_FILTER) || (f & LBM_FLAG_SOLID)) continue;
+        forchheimer_cell(G.vol, c0 + j, u, bf, K, beta, c_darcy, c_forch, fmax);
+    }
+}
 
-// legacy/lbm_solver.py:1478-1483
+// legacy/lbm_solver.py:1478-1483.  VEC = 4: one quad per trip, flags as one word, all-fluid quads as 128-bit vectors.
+template <int VEC>
 __global__ void add_reaction_kernel(Grid G, const float *reaction, const uint8_t *flags, float *bf) {
     const long long n = G.vol;
-    for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x) {
-        if (flags && (flags[c] & LBM_FLAG_SOLID)) continue;
+    if constexpr (VEC == 4) {
+        for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n / 4; q += (long long)gridDim.x * blockDim.x) {
+            const long long c = 4 * q;
+            const unsigned fw = flags ? *reinterpret_cast<const unsigned *>(flags + c) : 0u;
+            constexpr unsigned SOLID4 = 0x01010101u * LBM_FLAG_SOLID;
+            if ((fw & SOLID4) == SOLID4) continue;
+            if ((fw & SOLID4) == 0u) {
 #pragma unroll
-        for (int d = 0; d < 3; ++d) bf[d * n + c] = bf[d * n + c] + reaction[d * n + c];
+                for (int d = 0; d < 3; ++d) {
+                    float4 *p = reinterpret_cast<float4 *>(bf + d * n + c);
+                    const float4 a = *p, r = *reinterpret_cast<const float4 *>(reaction + d * n + c);
+                    *p = make_float4(a.x + r.x, a.y + r.y, a.z + r.z, a.w + r.w);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if ((fw >> (8 * j)) & LBM_FLAG_SOLID) continue;
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) bf[d * n + c + j] = bf[d * n + c + j] + reaction[d * n + c + j];
+                }
+            }
+        }
+    } else {
+        for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x) {
+            if (flags && (flags[c] & LBM_FLAG_SOLID)) continue;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) bf[d * n + c] = bf[d * n + c] + reaction[d * n + c];
+        }
     }
 }
 
@@ -1049,8 +1084,14 @@ cudaError_t launch_density_drive(const Grid &G, float *rho, const uint8_t *flags
 }
 cudaError_t launch_forchheimer_force(const Grid &G, const float *u, const uint8_t *flags, float *bf, float K, float beta,
                                      float c_darcy, float c_forch, float fmax, cudaStream_t s) {
-    const int b = 256; const long long gr = (G.vol + b - 1) / b;
-    forchheimer_force_kernel<<<(unsigned)gr, b, 0, s>>>(G, u, flags, bf, K, beta, c_darcy, c_forch, fmax);
+    if (G.ny > 65535 || G.nz > 65535) return cudaErrorInvalidValue;
+    if (G.nx % 4 == 0 && ((uintptr_t)flags & 3u) == 0) {
+        const int per_row = G.nx / 4, b = per_row >= 128 ? 128 : 64;
+        forchheimer_force_kernel<4><<<dim3((unsigned)((per_row + b - 1) / b), (unsigned)G.ny, (unsigned)G.nz), b, 0, s>>>(G, u, flags, bf, K, beta, c_darcy, c_forch, fmax);
+    } else {
+        const int b = G.nx >= 128 ? 128 : 64;
+        forchheimer_force_kernel<1><<<dim3((unsigned)((G.nx + b - 1) / b), (unsigned)G.ny, (unsigned)G.nz), b, 0, s>>>(G, u, flags, bf, K, beta, c_darcy, c_forch, fmax);
+    }
     return cudaGetLastError();
 }
 cudaError_t launch_bounce_slots(const Grid &G, float *g, const uint8_t *flags, const unsigned long long *nbr, int z_begin, int z_end, cudaStream_t s) {
@@ -1060,8 +1101,10 @@ cudaError_t launch_bounce_slots(const Grid &G, float *g, const uint8_t *flags, c
     return cudaGetLastError();
 }
 cudaError_t launch_add_reaction(const Grid &G, const float *reaction, const uint8_t *flags, float *bf, cudaStream_t s) {
-    const int b = 256, gr = grid_for(G.vol, b);
-    add_reaction_kernel<<<gr, b, 0, s>>>(G, reaction, flags, bf);
+    const int b = 256;
+    const bool vec4 = G.vol % 4 == 0 && (((uintptr_t)reaction | (uintptr_t)bf) & 15u) == 0 && ((uintptr_t)flags & 3u) == 0;
+    if (vec4) add_reaction_kernel<4><<<grid_for(G.vol / 4, b), b, 0, s>>>(G, reaction, flags, bf);
+    else add_reaction_kernel<1><<<grid_for(G.vol, b), b, 0, s>>>(G, reaction, flags, bf);
     return cudaGetLastError();
 }
 

@@ -37,3 +37,10 @@ if __name__ == "__main__":
     tm = timer.measure(lambda k: [eng.add_pressure_gradient_force(0.12, 0.1) for _ in range(k)], 20, 3)
     gb = (n ** 3 + 28 * fl) / 1e9
     print(f"lbm_pressure_gradient_force (accumulate) V60 {n}^3: {tm['ms_per_step']:.4f} ms per call (min {tm['ms_min']:.4f}), {gb:.3f} GB algorithmic = {gb / tm['ms_per_step'] * 1e3:.0f} GB/s")
+    # the two reference-mode producers that were still cell-at-a-time: Forchheimer force (filter shell only) and the reaction add
+    tm = timer.measure(lambda k: [eng.add_forchheimer_force() for _ in range(k)], 20, 3)
+    print(f"lbm_forchheimer_force V60 {n}^3: {tm['ms_per_step']:.4f} ms per call (min {tm['ms_min']:.4f})")
+    reaction = torch.zeros_like(eng.body_force)
+    tm = timer.measure(lambda k: [eng.add_reaction_force(reaction) for _ in range(k)], 20, 3)
+    gb = (n ** 3 + 36 * fl) / 1e9
+    print(f"lbm_add_reaction_force V60 {n}^3: {tm['ms_per_step']:.4f} ms per call (min {tm['ms_min']:.4f}), {gb:.3f} GB algorithmic = {gb / tm['ms_per_step'] * 1e3:.0f} GB/s")

@@ -125,8 +125,9 @@ int emu_pressure_gradient_tiles(int nx, int ny, int nz, int vec, const float *rh
 int emu_forchheimer(int nx, int ny, int nz, const float *u, const uint8_t *flags, float *bf, float K, float beta, float c_darcy, float c_forch,
                     float fmax) {
     const Grid G = make_grid(nx, ny, nz);
-    const unsigned b = 256;
-    run(dim3((unsigned)((G.vol + b - 1) / b), 1, 1), b, [&] { forchheimer_force_kernel(G, u, flags, bf, K, beta, c_darcy, c_forch, fmax); });
+    const unsigned b = 64;             // the launch geometry of launch_forchheimer_force: (x-chunk, y, z), 4 cells per thread when nx % 4 == 0
+    if (nx % 4 == 0) run(dim3((unsigned)((nx / 4 + b - 1) / b), (unsigned)ny, (unsigned)nz), b, [&] { forchheimer_force_kernel<4>(G, u, flags, bf, K, beta, c_darcy, c_forch, fmax); });
+    else run(dim3((unsigned)((nx + b - 1) / b), (unsigned)ny, (unsigned)nz), b, [&] { forchheimer_force_kernel<1>(G, u, flags, bf, K, beta, c_darcy, c_forch, fmax); });
     return 0;
 }
 int emu_bounce_slots(int nx, int ny, int nz, int periodic, float *g, const uint8_t *flags, const unsigned long long *nbr) {
@@ -178,7 +179,8 @@ int emu_pressure_gradient_chord(int nx, int ny, int nz, const float *rho, const 
 }
 int emu_add_reaction(int nx, int ny, int nz, const float *reaction, const uint8_t *flags, float *bf) {
     const Grid G = make_grid(nx, ny, nz);
-    run_stride([&] { add_reaction_kernel(G, reaction, flags, bf); });
+    if (G.vol % 4 == 0) run_stride([&] { add_reaction_kernel<4>(G, reaction, flags, bf); });
+    else run_stride([&] { add_reaction_kernel<1>(G, reaction, flags, bf); });
     return 0;
 }
 }  // extern "C"

@@ -377,3 +377,36 @@ def test_emulated_quad_list_pressure_gradient_equals_the_grid_kernel(aux):
         aux.emu_pressure_gradient_chord(*_dims(n), _p(rho), _p(flags), _p(bf), C.c_float(0.12), C.c_float(scale), C.c_int(1), _p(np.ascontiguousarray(quads)),
                                         C.c_int(len(quads)))
         assert np.array_equal(np.transpose(bf, (3, 2, 1, 0)), z[key])
+
+
+@pytest.mark.parametrize("shape,seed", [((20, 9, 7), 5), ((18, 10, 6), 6), ((13, 8, 5), 7)], ids=["vec4", "ragged_nx", "ragged_odd"])
+def test_emulated_forchheimer_and_reaction_kernels_on_ragged_boxes(aux, shape, seed):
+    """forchheimer_force_kernel<4 | 1> ((x-chunk, y, z) launch grid, flags of a quad as one word) against the oracle's restatement of
+    FilterPaperSystem.compute_forchheimer_resistance on non-cubic boxes with random solids / filter zones, velocities large enough to hit
+    the force clamp; add_reaction_kernel<4 | 1> (LBMSolver.add_particle_reaction_forces) against body_force + reaction on fluid cells."""
+    nx, ny, nz = shape
+    rng = np.random.default_rng(seed)
+    cfg_o = R.RefConfig(NX=nx, NY=ny, NZ=nz)
+    st = R.init_fields(cfg_o)
+    st.solid = (rng.random(shape) < 0.3).astype(np.uint8)
+    st.filter_zone = ((rng.random(shape) < 0.4) & (rng.random(shape) < 0.9)).astype(np.int32)          # some filter cells are solid too
+    st.K_lu, st.beta_lu = R.forchheimer_params(cfg_o)
+    st.u = (rng.choice([1e-9, 1e-4, 0.05], shape + (1,)) * rng.standard_normal(shape + (3,))).astype(np.float32)
+    st.body_force = (1e-5 * rng.standard_normal(shape + (3,))).astype(np.float32)
+    bf = H.to_dev_vec(st.body_force); u = H.to_dev_vec(st.u)
+    flags = H.to_dev_scalar((st.solid | (2 * (st.filter_zone != 0))).astype(np.uint8))
+    c_darcy, c_forch = R.filter_constants(cfg_o)
+    before = st.body_force.copy()
+    R.compute_forchheimer_resistance(st)
+    changed = np.any(st.body_force != before, axis=-1)
+    assert changed.any() and not changed[st.solid == 1].any() and not changed[st.filter_zone == 0].any()      # the scenario is not trivial
+    aux.emu_forchheimer(C.c_int(nx), C.c_int(ny), C.c_int(nz), _p(u), _p(flags), _p(bf), C.c_float(st.K_lu), C.c_float(st.beta_lu),
+                        C.c_float(c_darcy), C.c_float(c_forch), C.c_float(0.01 * 0.01 / cfg_o.DT))
+    assert np.array_equal(np.transpose(bf, (3, 2, 1, 0)), st.body_force)
+    # reaction accumulation
+    reaction = (1e-4 * rng.standard_normal(bf.shape)).astype(np.float32)
+    want = bf.copy()
+    fluid = (flags & 1) == 0
+    want[:, fluid] = bf[:, fluid] + reaction[:, fluid]
+    aux.emu_add_reaction(C.c_int(nx), C.c_int(ny), C.c_int(nz), _p(reaction), _p(flags), _p(bf))
+    assert np.array_equal(bf, want)
