@@ -189,3 +189,32 @@ class ConstField:
 
     def __getitem__(self, i):
         return self._a[i]
+
+
+class TensorField(torch.Tensor):
+    """A device tensor that also answers the Taichi-field calls the reference's readers make on the particle arrays
+    (`particle_system.position.to_numpy()`, `.active.to_numpy()`: lbm_diagnostics.py, visualizer.py; recorded in
+    tests/golden/reference_main_trace.json, "field_readers").  It stays a tensor for everything else: `wrap(t)` is a view of `t`."""
+
+    @staticmethod
+    def wrap(t: torch.Tensor) -> "TensorField":
+        return t.as_subclass(TensorField)
+
+    def to_numpy(self) -> np.ndarray:
+        return np.ascontiguousarray(self.detach().as_subclass(torch.Tensor).cpu().numpy())
+
+    def from_numpy(self, arr) -> None:
+        self.copy_(torch.as_tensor(np.ascontiguousarray(arr)).to(self.device, self.dtype))
+
+    def fill(self, value) -> None:
+        self.fill_(value)
+
+    def to_torch(self) -> torch.Tensor:
+        return self.as_subclass(torch.Tensor)
+
+
+class ScalarCount(int):
+    """An int that can be read the way the reference reads its 0-D fields: `particle_count[None]`."""
+
+    def __getitem__(self, _):
+        return int(self)

@@ -20,7 +20,7 @@ import torch
 from . import _lib as L
 from . import config as cfgmod
 from .engine import ParticleState, particles_advance, particles_couple, _ptr
-from .fields import ScalarField, VectorField
+from .fields import ScalarCount, ScalarField, TensorField, VectorField
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -344,20 +344,29 @@ class CoffeeParticleSystem:
 
     # field-like accessors in the reference's [P,3] order
     def _pv(self, t):  # [3,n] -> [n,3]
-        return t.t()
+        return TensorField.wrap(t.t())
 
+    # tensors that also answer to_numpy / from_numpy / fill, the calls the reference's diagnostics make on these arrays
     position = property(lambda self: self._pv(self.state.pos))
     velocity = property(lambda self: self._pv(self.state.vel))
     drag_force = property(lambda self: self._pv(self.state.drag))
     drag_force_new = property(lambda self: self._pv(self.state.drag_new))
     drag_force_old = property(lambda self: self._pv(self.state.drag_old))
     fluid_velocity_at_particle = property(lambda self: self._pv(self.state.u_fluid))
-    radius = property(lambda self: self.state.radius)
-    mass = property(lambda self: self.state.mass)
-    active = property(lambda self: self.state.active)
-    particle_reynolds = property(lambda self: self.state.reynolds)
-    drag_coefficient = property(lambda self: self.state.cd)
+    radius = property(lambda self: TensorField.wrap(self.state.radius))
+    mass = property(lambda self: TensorField.wrap(self.state.mass))
+    active = property(lambda self: TensorField.wrap(self.state.active))
+    particle_reynolds = property(lambda self: TensorField.wrap(self.state.reynolds))
+    drag_coefficient = property(lambda self: TensorField.wrap(self.state.cd))
     cell_index = property(lambda self: self._pv(self.state.cell))
+
+    @property
+    def particle_count(self) -> ScalarCount:          # the reference reads `particle_count[None]` (a 0-D Taichi field)
+        return ScalarCount(self._particle_count)
+
+    @particle_count.setter
+    def particle_count(self, n: int) -> None:
+        self._particle_count = int(n)
 
     def set_particles(self, pos, vel=None, radius=None, mass=None):
         """Inject explicit particle arrays ([P,3] positions in lattice units; SI radius/mass -- quirk Q9/Q10)."""

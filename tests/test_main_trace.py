@@ -306,3 +306,31 @@ def test_bare_pouring_system_host_state_follows_the_recorded_values():
             pp.apply_pouring_force(object(), object(), 1.0)          # pouring is active, nothing names an engine
     finally:
         cfgmod.DEFAULT = old
+
+
+def test_recorded_field_readers_find_the_taichi_field_surface_on_the_facade():
+    """The reference's diagnostics / visualisation modules and main.py read solver, multiphase and particle arrays through the Taichi
+    field surface (`to_numpy`; the recording lists which, per module).  The facade's fields answer the same calls: the grid fields are
+    field shims, the particle arrays tensors with the field methods, `particle_count[None]` reads like a 0-D field."""
+    import torch
+    from pour_over_coffee_lbm_b200 import fields as F
+    from pour_over_coffee_lbm_b200.engine import ParticleState
+    from pour_over_coffee_lbm_b200.physics import CoffeeParticleSystem
+    t = load_trace()
+    read = sorted({r for mod in t["field_readers"].values() for r in mod})
+    assert "particle_system.position.to_numpy" in read and "lbm.rho.to_numpy" in read and "multiphase.phi.to_numpy" in read
+    ps = CoffeeParticleSystem.__new__(CoffeeParticleSystem)          # no device: the accessors only need the state's tensors
+    ps.state = ParticleState(5, torch.device("cpu"))
+    ps.particle_count = 3
+    ps.state.pos[:, :3] = torch.arange(9, dtype=torch.float32).reshape(3, 3)
+    ps.state.active[:3] = 1
+    for r in read:
+        role, attr, op = r.split(".")
+        if role == "particle_system":
+            assert callable(getattr(getattr(ps, attr), op)), r
+        else:
+            cls = {"lbm": (F.ScalarField, F.VectorField, F.ComponentField), "multiphase": (F.ScalarField,)}[role]
+            assert all(callable(getattr(c, op, None)) for c in cls), r
+    pos = ps.position.to_numpy()
+    assert pos.shape == (5, 3) and pos.flags["C_CONTIGUOUS"] and np.array_equal(pos[1], [1.0, 4.0, 7.0])
+    assert ps.active.to_numpy().sum() == 3 and ps.particle_count[None] == 3 and int((ps.active == 1).sum()) == 3
