@@ -16,6 +16,9 @@ Output: tests/golden/reference_main_trace.json (+ reference_main_trace_fields.np
 recorded call against the facade's signatures on the CPU and replays the whole trace on the device.
 
     python tests/golden/make_reference_main_trace.py [n=16] [steps=12] [pressure_mode=none] [out.json]
+
+Deterministic (NumPy / random seeded before the constructor): a second run reproduced the committed JSON and .npz byte for byte.
+About 5 minutes of CPU per recording at 16^3 (the Taichi stand-in executes the reference's kernels as Python loops).
 """
 import functools
 import inspect
