@@ -508,6 +508,23 @@ if __name__ == "__main__":
         np.savez_compressed(os.path.join(HERE, f"reference_run_long_air_{steps}.npz"), n=n, steps=steps, gravity=2e-5, seed=36,
                             phase_mode="air_random", **inp, **geom, **out)
         sys.exit(0 if ok else 1)
+    if len(sys.argv) > 2 and sys.argv[2] == "long2":
+        # a second long run in the legacy solver's stable (air) regime on another grid: `20 long2 1000` = 20^3 (1591 fluid cells), 50 x the
+        # gravity of the first one (rho spreads over [0.996, 1.007]), another seed; ~100 min of emulation
+        steps = int(sys.argv[3]) if len(sys.argv) > 3 else 1000
+        seed, gravity = 41, 1e-3
+        t = time.time()
+        inp, geom, out, st = run_step_scenario(config, n, steps, seed=seed, gravity=gravity, phase_mode="air_random")
+        from oracle import ref_cpu as RC
+        cs = RC.CState(st); cs.step(steps)
+        fluid = geom["solid"] == 0
+        ok = np.array_equal(out["rho"][fluid], cs.rho[fluid]) and np.array_equal(out["u"][fluid], cs.u[fluid]) and \
+            np.array_equal(out["f_out"][:, fluid], cs.f[:, fluid])
+        print(f"[reference run] air_random_{steps} n={n} g={gravity}: reference {time.time() - t:.0f} s  C oracle bit-exact: {ok}  "
+              f"max|u| {np.abs(out['u'][fluid]).max():.3e}  rho [{out['rho'][fluid].min():.5f}, {out['rho'][fluid].max():.5f}]")
+        np.savez_compressed(os.path.join(HERE, f"reference_run_long_air_{steps}_n{n}.npz"), n=n, steps=steps, gravity=gravity, seed=seed,
+                            phase_mode="air_random", **inp, **geom, **out)
+        sys.exit(0 if ok else 1)
     if len(sys.argv) > 2 and sys.argv[2] == "coupled":
         t = time.time()
         res = run_coupled_scenario(config, n, seed=51)

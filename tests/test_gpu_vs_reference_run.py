@@ -56,11 +56,16 @@ def test_step_kernel_reproduces_the_reference_run(path, vec):
     assert np.array_equal(H.from_dev_pop(eng.export_f())[:, fluid], z["f_out"][:, fluid])
 
 
+LONG_FILES = sorted(glob.glob(os.path.join(GOLD, "reference_run_long_air_*.npz")))
+
+
 @pytest.mark.parametrize("vec", [1, 4])
-def test_step_kernel_reproduces_1000_steps_of_the_reference_run(vec):
+@pytest.mark.parametrize("path", LONG_FILES, ids=[os.path.basename(p)[19:-4] for p in LONG_FILES])
+def test_step_kernel_reproduces_1000_steps_of_the_reference_run(path, vec):
     """BASELINE: "rho and u must agree within 1e-5 relative (fp32) after 1000 steps" -- against 1000 recorded calls of the
-    reference's own LBMSolver.step() (tests/golden/reference_run_long_air_1000.npz): the strict build agrees bit for bit."""
-    z = np.load(os.path.join(GOLD, "reference_run_long_air_1000.npz"))
+    reference's own LBMSolver.step() (tests/golden/reference_run_long_air_1000.npz: V60 16^3; ..._n20.npz: V60 20^3, 50 x the gravity,
+    another seed): the strict build agrees bit for bit."""
+    z = np.load(path)
     n, steps, gravity = int(z["n"]), int(z["steps"]), float(z["gravity"])
     assert steps == 1000
     eng = _engine(n, n, n, compat="reference", periodic=(False, False, False), walls=True, force=True, phase=True, les=True,

@@ -20,7 +20,7 @@ from oracle import d3q19_ref as R
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = os.path.join(HERE, "golden")
-FILES = sorted(glob.glob(os.path.join(GOLD, "reference_run_step_*.npz"))) + [os.path.join(GOLD, "reference_run_long_air_1000.npz")]
+FILES = sorted(glob.glob(os.path.join(GOLD, "reference_run_step_*.npz"))) + sorted(glob.glob(os.path.join(GOLD, "reference_run_long_air_*.npz")))
 
 
 @pytest.fixture(scope="module")
