@@ -83,7 +83,8 @@ typedef struct {
     float c_darcy, c_forch;   /* reference: constant folds of filter_paper.py:578-586 */
     int vec;                  /* tuning: cells per thread along x (1, 2 or 4; 0 = auto: 4 in periodic boxes and behind walls in
                                  compat = physical -- chord-fitted tiles, csrc/lbm_phys_chord.cuh -- when nx % 4 == 0 and
-                                 nx <= 2048, else 2 / 1; 1 behind walls in compat = reference) */
+                                 nx <= 2048, else 2 / 1; 1 behind walls in compat = reference, where 2 selects the legacy arithmetic
+                                 on packed cell pairs, csrc/lbm_step_kernel.cuh:collide_reference_t) */
     int block;                /* tuning: threads per CTA (0 = auto; 64 / 128 / 256; behind walls in compat = physical these are
                                  occupancy codes of the kernel `vec` selects, see csrc/lbm_step.cu) */
     float drive_max_force;    /* LBM_FEAT_DRIVE: clamp on |F| (PressureGradientDrive.MAX_PRESSURE_FORCE) ... */

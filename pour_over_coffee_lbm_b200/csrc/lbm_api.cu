@@ -184,8 +184,9 @@ static int pick_vec(const lbm_ctx *ctx) {
     // 128-bit path for dense periodic boxes (99 % of the copy bandwidth); compat = reference behind a flag field
     // runs one cell per thread (partially filled warps at every chord end make wider threads slower there)
     if (vec == 0) vec = (ctx->p.features & LBM_FEAT_WALLS) ? 1 : 4;
-    if (vec == 2) vec = 1;
-    if (ctx->g.nx % 4 != 0 || ctx->g.nx < 8) vec = 1;
+    // vec = 2 (opt-in): compat = reference with the legacy arithmetic on packed cell pairs (lbm_step_kernel.cuh:collide_reference_t)
+    if (vec == 2 && (ctx->p.compat != LBM_COMPAT_REFERENCE || ctx->g.nx % 2 != 0 || ctx->g.nx < 4)) vec = 1;
+    if (vec == 4 && (ctx->g.nx % 4 != 0 || ctx->g.nx < 8)) vec = 1;
     return vec;
 }
 

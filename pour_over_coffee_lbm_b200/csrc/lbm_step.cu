@@ -61,8 +61,9 @@ static StepKernel pick() {
             return step_kernel<LBM_STRICT_BUILD, G_COMPAT, MODE, FORCED, LES, POROUS, VEC, BLOCK, COLLIDE, min_blocks<VEC, BLOCK>(), true>;
         else return nullptr;
     }
-    else if constexpr (VEC == 2) return nullptr;
     else if constexpr (!COLLIDE && VEC != 1) return nullptr;
+    // VEC = 2: compat = reference only -- two cells per thread, the legacy arithmetic on packed f32x2 (collide_reference_t<P2>; opt-in)
+    else if constexpr (VEC == 2 && G_COMPAT != LBM_COMPAT_REFERENCE) return nullptr;
     else return step_kernel<LBM_STRICT_BUILD, G_COMPAT, MODE, FORCED, LES, POROUS, VEC, BLOCK, COLLIDE, min_blocks<VEC, BLOCK>()>;
 }
 

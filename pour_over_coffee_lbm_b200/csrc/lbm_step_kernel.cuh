@@ -20,9 +20,18 @@
 // Arithmetic order follows oracle/d3q19_ref.py exactly; the translation unit is compiled
 // twice, with -fmad=false ("strict", bit-exact against the oracle) and with FMA contraction.
 #pragma once
+#include <type_traits>
 #include "lbm_common.cuh"
 #include "lbm_phys.cuh"
 #include "lbm_phys_chord.cuh"
+#ifndef LBM_REF_GENERIC_COLLISION
+#define LBM_REF_GENERIC_COLLISION 0      /* 1 (tests/emu only): the one-cell legacy collision runs through collide_reference_t<float> */
+#endif
+#ifdef LBM_EMULATE_ON_HOST
+#define LBM_EMU_ALL_EDGE true            /* no neighbouring lane on the host: every thread fetches its own x -+ 1 words */
+#else
+#define LBM_EMU_ALL_EDGE false
+#endif
 
 namespace lbm {
 
@@ -55,9 +64,13 @@ template <> __device__ __forceinline__ void st_stream<4>(float *p, const float (
 // adjacent lane holds.  Written in PTX because the compiler otherwise turns the 10 conditional loads into divergent
 // regions (+80 issue slots per warp, measured 0.408 -> 0.430 ms on the headline config).
 __device__ __forceinline__ float ldg_if(const float *p, bool pred, float other) {
+#ifdef LBM_EMULATE_ON_HOST
+    return pred ? *p : other;
+#else
     float v = other;
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p ld.global.nc.f32 %0, [%1];\n\t}" : "+f"(v) : "l"(p), "r"((int)pred));
     return v;
+#endif
 }
 
 struct CellAux {
@@ -149,6 +162,148 @@ __device__ __forceinline__ void collide_reference(float (&f)[Q], const CellAux &
 }
 
 // ---------------------------------------------------------------------------------------------
+// The same collision on V = float (one cell) or V = P2 (two x-adjacent cells, packed f32x2): collide_reference above, statement by
+// statement, with every product written as Ops<V>::mul0 -- a product that keeps its own rounding in front of the add / sub that
+// consumes it (the packed mul.rn would be contracted into it by ptxas; lbm_phys.cuh) -- so both instantiations round exactly where
+// the scalar code under -fmad=false does.  What has no packed instruction (divisions, square roots, min / max clamps, the
+// per-cell conditions) runs lane by lane.  e . v of a direction with a negative leading component is evaluated as
+// sigma * (magnitude) with the sign carried at compile time: -(a) + (-(b)) = -(a + b) and (-a) + b = b - a round identically, the
+// products 3 eu and 9 eus uf are odd in it, (4.5 eu) eu is even, and the +-0.5 clamp of the Guo term is symmetric.  Differences
+// against collide_reference are confined to the SIGN of exact zeros (and to NaN inputs), which no sum with a non-zero term keeps.
+// tests/emu runs both instantiations on the CPU against the recorded runs of the reference (test_step_reference_emulated.py).
+// ---------------------------------------------------------------------------------------------
+template <class V> struct CellAuxT {
+    V Fx, Fy, Fz, phase;
+    float nu_sgs[Ops<V>::L], blockage[Ops<V>::L];
+    unsigned flag[Ops<V>::L];
+    bool interior[Ops<V>::L];
+};
+// magnitude and compile-time sign of e . v for e in {0, +1, -1}^3 with at most two non-zero components (D3Q19)
+template <class V, int X, int Y, int Z> struct SignedDot {
+    static constexpr int n = (X != 0) + (Y != 0) + (Z != 0);
+    static_assert(n <= 2, "D3Q19: at most two non-zero components");
+    static constexpr int first = X != 0 ? X : (Y != 0 ? Y : Z);                                  // sign of the leading term
+    static constexpr int second = n < 2 ? 0 : (X != 0 ? (Y != 0 ? Y : Z) : Z);                   // sign of the other one
+    static constexpr int sign = (n == 2 && first < 0 && second < 0) || (n == 1 && first < 0) ? -1 : 1;
+    static __device__ __forceinline__ V mag(V vx, V vy, V vz) {
+        using O = Ops<V>;
+        if constexpr (n == 0) return O::bc(0.0f);
+        else if constexpr (n == 1) return X != 0 ? vx : (Y != 0 ? vy : vz);
+        else {
+            const V a = X != 0 ? vx : vy, b = X != 0 ? (Y != 0 ? vy : vz) : vz;
+            if constexpr (first > 0 && second > 0) return O::add(a, b);
+            else if constexpr (first > 0) return O::sub(a, b);
+            else if constexpr (second > 0) return O::sub(b, a);          // (-a) + b
+            else return O::add(a, b);                                    // (-a) + (-b) = -(a + b)
+        }
+    }
+};
+template <class V, bool FORCED, bool LES, bool POROUS>
+__device__ __forceinline__ void collide_reference_t(V (&f)[Q], const CellAuxT<V> &a, CellMacro<V> &o, const StepArgs &P) {
+    using O = Ops<V>;
+    constexpr int L = O::L;
+    V rho = f[0];                                                        // 0 + f[0]
+    static_for<1, Q>([&](auto qq) { constexpr int q = decltype(qq)::value; rho = O::add(rho, f[q]); });
+    V mx = f[1], my = f[3], mz = f[5];                                   // the first term of each sum: 0 + f * (+1)
+    static_for<2, Q>([&](auto qq) {
+        constexpr int q = decltype(qq)::value;
+        if constexpr (cx(q) != 0) mx = cx(q) > 0 ? O::add(mx, f[q]) : O::sub(mx, f[q]);
+        if constexpr (cy(q) != 0 && q > 3) my = cy(q) > 0 ? O::add(my, f[q]) : O::sub(my, f[q]);
+        if constexpr (cz(q) != 0 && q > 5) mz = cz(q) > 0 ? O::add(mz, f[q]) : O::sub(mz, f[q]);
+    });
+    V Fx = O::bc(0.0f), Fy = O::bc(0.0f), Fz = O::bc(0.0f);
+    float ph[L];
+#pragma unroll
+    for (int l = 0; l < L; ++l) ph[l] = FORCED ? O::get(a.phase, l) : 0.0f;
+    if constexpr (FORCED) {
+        float gz[L];
+#pragma unroll
+        for (int l = 0; l < L; ++l) gz[l] = ph[l] > 0.001f ? -(P.gravity_lu * ph[l]) : 0.0f;
+        Fx = O::add(O::bc(0.0f), a.Fx); Fy = O::add(O::bc(0.0f), a.Fy); Fz = O::add(O::make(gz), a.Fz);
+    }
+    // per cell: velocity, relaxation time, the prerequisites of the clamped Guo term (legacy/lbm_solver.py:521-585)
+    float uxl[L], uyl[L], uzl[L], oml[L], usx[L], usy[L], usz[L], fsx[L], fsy[L], fsz[L], ufl[L], c0[L], c1[L], c2[L];
+    bool forced[L];
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+        const float r = O::get(rho, l), fx = O::get(Fx, l), fy = O::get(Fy, l), fz = O::get(Fz, l);
+        float ux = 0.0f, uy = 0.0f, uz = 0.0f;
+        if (r > 1e-12f) {
+            ux = (O::get(mx, l) + 0.5f * fx) / r; uy = (O::get(my, l) + 0.5f * fy) / r; uz = (O::get(mz, l) + 0.5f * fz) / r;
+        }
+        float tau = ph[l] > 0.5f ? P.tau_water : P.tau_air;
+        if constexpr (LES) tau = tau + 3.0f * a.nu_sgs[l];
+        tau = fmaxf(P.tau_min, fminf(P.tau_max, tau));
+        oml[l] = 1.0f / tau;
+        uxl[l] = ux; uyl[l] = uy; uzl[l] = uz;
+        forced[l] = false; usx[l] = ux; usy[l] = uy; usz[l] = uz; fsx[l] = fsy[l] = fsz[l] = 0.0f; ufl[l] = 0.0f; c0[l] = c1[l] = c2[l] = 0.0f;
+        if constexpr (FORCED) {
+            const float fnorm = sqrtf(dot3(fx, fy, fz, fx, fy, fz));
+            forced[l] = fnorm > 1e-15f;
+            const float tau_safe = fminf(fmaxf(tau, 0.6f), 1.5f);
+            const float sf = fnorm > 10.0f ? 10.0f / fnorm : 1.0f;
+            fsx[l] = fx * sf; fsy[l] = fy * sf; fsz[l] = fz * sf;
+            const float unorm = sqrtf(dot3(ux, uy, uz, ux, uy, uz));
+            if (unorm > 0.2f) { const float s = 0.2f / unorm; usx[l] = ux * s; usy[l] = uy * s; usz[l] = uz * s; }
+            ufl[l] = dot3(usx[l], usy[l], usz[l], fsx[l], fsy[l], fsz[l]);
+            const float pref = 1.0f - 0.5f / tau_safe;
+            c0[l] = wq(0) * pref; c1[l] = wq(1) * pref; c2[l] = wq(7) * pref;
+        }
+    }
+    const V ux = O::make(uxl), uy = O::make(uyl), uz = O::make(uzl), omega = O::make(oml);
+    const V vsx = O::make(usx), vsy = O::make(usy), vsz = O::make(usz), vfx = O::make(fsx), vfy = O::make(fsy), vfz = O::make(fsz);
+    const V uf = O::make(ufl), k0 = O::make(c0), k1 = O::make(c1), k2 = O::make(c2);
+    bool any_forced = false;
+#pragma unroll
+    for (int l = 0; l < L; ++l) any_forced |= forced[l];
+    const V u_sq = O::add(O::add(O::mul0(ux, ux), O::mul0(uy, uy)), O::mul0(uz, uz));
+    const V k15 = O::mul0(O::bc(1.5f), u_sq);
+    const V wr0 = O::mul0(O::bc(wq(0)), rho), wr1 = O::mul0(O::bc(wq(1)), rho), wr2 = O::mul0(O::bc(wq(7)), rho);
+    static_for<0, Q>([&](auto qq) {
+        constexpr int q = decltype(qq)::value;
+        using E = SignedDot<V, ex(q), ey(q), ez(q)>;                     // quirk Q1: the equilibrium's own table
+        const V s = E::mag(ux, uy, uz);
+        const V t3 = O::mul0(O::bc(3.0f), s);
+        const V A = E::sign > 0 ? O::add(O::bc(1.0f), t3) : O::sub(O::bc(1.0f), t3);
+        const V B = O::add(A, O::mul0(O::mul0(O::bc(4.5f), s), s));
+        const V feq = O::mul0(q == 0 ? wr0 : (q < 7 ? wr1 : wr2), O::sub(B, k15));
+        V fn = O::sub(f[q], O::mul0(omega, O::sub(f[q], feq)));
+        if constexpr (FORCED) {
+            if (any_forced) {
+                using C = SignedDot<V, cx(q), cy(q), cz(q)>;
+                const V eus = C::mag(vsx, vsy, vsz), ef = C::mag(vfx, vfy, vfz);
+                const V g = O::add(O::mul0(O::bc(3.0f), ef), O::mul0(O::mul0(O::bc(9.0f), eus), uf));
+                const V Fq = O::mul0(q == 0 ? k0 : (q < 7 ? k1 : k2), g);
+                float fl[L];
+#pragma unroll
+                for (int l = 0; l < L; ++l) fl[l] = forced[l] ? fmaxf(-0.5f, fminf(0.5f, O::get(Fq, l))) : 0.0f;
+                fn = C::sign > 0 ? O::add(fn, O::make(fl)) : O::sub(fn, O::make(fl));
+            }
+        }
+        f[q] = fn;
+    });
+    // externally visible u: filter damping applied after the step (quirk Q5)
+    if constexpr (POROUS) {
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+            if ((a.flag[l] & LBM_FLAG_FILTER) && a.interior[l]) {
+                const float umag = sqrtf(dot3(uxl[l], uyl[l], uzl[l], uxl[l], uyl[l], uzl[l]));
+                if (umag > 1e-8f && P.K_lu > 1e-12f) {
+                    const float darcy = P.c_darcy / P.K_lu;
+                    const float forch = ((P.c_forch * P.beta_lu) * umag) / sqrtf(P.K_lu);
+                    const float total = (darcy + forch) * (1.0f + a.blockage[l]);
+                    float r = expf((-total) * 0.5f);
+                    r = fmaxf(0.1f, r);
+                    const float hf = (r + 1.0f) * 0.5f;
+                    uzl[l] = uzl[l] * r; uxl[l] = uxl[l] * hf; uyl[l] = uyl[l] * hf;
+                }
+            }
+        }
+    }
+    o.rho = rho; o.ux = O::make(uxl); o.uy = O::make(uyl); o.uz = O::make(uzl);
+}
+
+// ---------------------------------------------------------------------------------------------
 // reference-mode LES pre-pass fused as a stencil read of the previous step's u
 // (les_turbulence.py:318-380).  `c` = linear index of the cell in a scalar volume.
 // ---------------------------------------------------------------------------------------------
@@ -217,7 +372,7 @@ __device__ __forceinline__ void step_cells(const StepArgs &P, const int x0, cons
         zm = z - 1; if (zm < 0) zm = G.per_z ? G.nz - 1 : 0;
         zq = z + 1; if (zq >= G.nz) zq = G.per_z ? 0 : G.nz - 1;
     }
-    const bool edge_lo = lane == 0 || x0 == 0, edge_hi = lane == 31 || x0 == G.nx - VEC;   // no lane holds my x-1 / x+VEC
+    const bool edge_lo = LBM_EMU_ALL_EDGE || lane == 0 || x0 == 0, edge_hi = LBM_EMU_ALL_EDGE || lane == 31 || x0 == G.nx - VEC;   // no lane holds my x-1 / x+VEC
     int xm = x0 - 1; if (xm < 0) xm = G.per_x ? G.nx - 1 : 0;
     int xq = x0 + VEC; if (xq >= G.nx) xq = G.per_x ? 0 : G.nx - 1;
 
@@ -351,6 +506,51 @@ __device__ __forceinline__ void step_cells(const StepArgs &P, const int x0, cons
                     for (int q = 0; q < Q; ++q) f[q][c] = fc[q];
                 }
                 out[c].rho = m.rho; out[c].ux = m.ux; out[c].uy = m.uy; out[c].uz = m.uz;
+            }
+        }
+    } else if constexpr (VEC == 2 || LBM_REF_GENERIC_COLLISION) {
+        // compat = reference on packed cell pairs (VEC = 2): collide_reference_t<P2>.  LBM_REF_GENERIC_COLLISION (tests/emu only) sends
+        // the one-cell form through the same template, V = float, so its logic is checked against the recordings on the CPU.
+        using V = std::conditional_t<VEC % 2 == 0, P2, float>;
+        constexpr int L = Ops<V>::L;
+#pragma unroll
+        for (int c = 0; c < VEC; c += L) {
+            CellAuxT<V> a;
+            float fx[L], fy[L], fz[L], pl[L];
+#pragma unroll
+            for (int l = 0; l < L; ++l) {
+                a.flag[l] = fl[c + l];
+                fx[l] = FORCED ? bf[0][c + l] : 0.0f; fy[l] = FORCED ? bf[1][c + l] : 0.0f; fz[l] = FORCED ? bf[2][c + l] : 0.0f;
+                pl[l] = FORCED ? ph[c + l] : 0.0f;
+                a.blockage[l] = 0.0f; a.nu_sgs[l] = 0.0f;
+                const int x = x0 + c + l, zg_ = G.z0 + z;
+                a.interior[l] = x >= 1 && x <= G.nx - 2 && y >= 1 && y <= G.ny - 2 && zg_ >= 1 && zg_ <= G.nz_global - 2;
+                if constexpr (POROUS) { if (P.blockage) a.blockage[l] = __ldg(P.blockage + own + c + l); }
+                if constexpr (LES && COLLIDE) {
+                    if (mine[c + l] && a.interior[l] && (fl[c + l] & LBM_FLAG_LES))
+                        a.nu_sgs[l] = les_fd_nu(P.u_src, own + c + l, G.nx, G.plane, G.vol, pl[l], P.les_k);
+                }
+            }
+            a.Fx = Ops<V>::make(fx); a.Fy = Ops<V>::make(fy); a.Fz = Ops<V>::make(fz); a.phase = Ops<V>::make(pl);
+            V fp[Q];
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                float t[L];
+#pragma unroll
+                for (int l = 0; l < L; ++l) t[l] = f[q][c + l];
+                fp[q] = Ops<V>::make(t);
+            }
+            CellMacro<V> m;
+            if constexpr (COLLIDE) collide_reference_t<V, FORCED, LES, POROUS>(fp, a, m, P);
+            else collide_reference_t<V, FORCED, false, false>(fp, a, m, P);      // moments only: populations untouched below
+#pragma unroll
+            for (int l = 0; l < L; ++l) {
+                if constexpr (COLLIDE) {
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) f[q][c + l] = Ops<V>::get(fp[q], l);
+                }
+                out[c + l].rho = Ops<V>::get(m.rho, l); out[c + l].ux = Ops<V>::get(m.ux, l);
+                out[c + l].uy = Ops<V>::get(m.uy, l); out[c + l].uz = Ops<V>::get(m.uz, l);
             }
         }
     } else {

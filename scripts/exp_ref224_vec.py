@@ -14,7 +14,7 @@ if __name__ == "__main__":
     m = 224
     timer = bench.Timer(1, min_seconds=0.3)
     ref = None
-    for vec, block in ((1, 0), (1, 128), (4, 0), (4, 128), (1, 0)):
+    for vec, block in ((1, 0), (1, 128), (2, 0), (4, 0), (4, 128), (1, 0)):
         try:
             eng = bench.v60_engine(m, compat="reference", vec=vec, block=block)
         except Exception as e:

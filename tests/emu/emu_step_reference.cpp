@@ -31,13 +31,18 @@ static inline float __shfl_down_sync(unsigned, float v, int) { return v; }
 
 using namespace lbm;
 
+// EMU_VEC (cells per thread of the legacy-compatible step; emu_step_reference_vec2.cpp sets 2: the packed collision
+// collide_reference_t<P2> on host stand-ins of the f32x2 primitives, x -+ 1 words fetched by every thread itself)
+#ifndef EMU_VEC
+#define EMU_VEC 1
+#endif
 template <bool LES, bool POROUS>
 static void run(const StepArgs &P) {
     const Grid &G = P.g;
     for (int z = 0; z < G.nz; ++z)
         for (int y = 0; y < G.ny; ++y)
-            for (int x = 0; x < G.nx; ++x)
-                step_cells<LBM_COMPAT_REFERENCE, MODE_BULK, true, LES, POROUS, 1, true>(P, x, y, z, true, (unsigned)(x & 31));
+            for (int x = 0; x < G.nx; x += EMU_VEC)
+                step_cells<LBM_COMPAT_REFERENCE, MODE_BULK, true, LES, POROUS, EMU_VEC, true>(P, x, y, z, true, (unsigned)((x / EMU_VEC) & 31));
 }
 
 extern "C" int emu_step_reference_slab(int nx, int ny, int nz, int z0, int nz_global, const float *src, float *dst, float *rho, const float *u_src,

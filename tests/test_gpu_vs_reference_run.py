@@ -34,7 +34,7 @@ def _cfg(n, gravity):
     return LBMConfig(NX=n, NY=n, NZ=n, TAU_FLUID=c.TAU_WATER, TAU_AIR=c.TAU_AIR, GRAVITY_LU=gravity)
 
 
-@pytest.mark.parametrize("vec", [1, 4])
+@pytest.mark.parametrize("vec", [1, 2, 4])
 @pytest.mark.parametrize("path", STEP_FILES, ids=[os.path.basename(p)[19:-4] for p in STEP_FILES])
 def test_step_kernel_reproduces_the_reference_run(path, vec):
     """lbm_build_v60_geometry + lbm_pack_flags + lbm_import_f + lbm_step (compat = reference, strict) from the recorded
@@ -59,7 +59,7 @@ def test_step_kernel_reproduces_the_reference_run(path, vec):
 LONG_FILES = sorted(glob.glob(os.path.join(GOLD, "reference_run_long_air_*.npz")))
 
 
-@pytest.mark.parametrize("vec", [1, 4])
+@pytest.mark.parametrize("vec", [1, 2, 4])
 @pytest.mark.parametrize("path", LONG_FILES, ids=[os.path.basename(p)[19:-4] for p in LONG_FILES])
 def test_step_kernel_reproduces_1000_steps_of_the_reference_run(path, vec):
     """BASELINE: "rho and u must agree within 1e-5 relative (fp32) after 1000 steps" -- against 1000 recorded calls of the
@@ -81,7 +81,7 @@ def test_step_kernel_reproduces_1000_steps_of_the_reference_run(path, vec):
     assert np.array_equal(H.from_dev_pop(eng.export_f())[:, fluid], z["f_out"][:, fluid])
 
 
-@pytest.mark.parametrize("vec", [1, 4])
+@pytest.mark.parametrize("vec", [1, 2, 4])
 def test_open_box_step_and_face_bc_reproduce_the_reference_run(vec):
     """No V60 mask, no filter system: open faces (stale w_q inflow), boundary-manager face writes (lbm_face_bc), obstacles
     touching the faces -- the first 30 steps of main.py."""

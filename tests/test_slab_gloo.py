@@ -409,10 +409,14 @@ def _step_worker(rank, world, port, out, cuts, fixture):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("fixture,cuts", [("reference_run_step_split_phase_small_gravity.npz", ((0, 8), (8, 8))),
-                                          ("reference_run_step_water_default_gravity.npz", ((0, 5), (5, 11))),
-                                          ("reference_run_long_air_1000.npz", ((0, 9), (9, 7)))],
-                         ids=["les_active_equal", "default_gravity_unequal", "1000_steps_unequal"])
+_SLAB_RUNS = [("reference_run_step_split_phase_small_gravity.npz", ((0, 8), (8, 8)), "les_active_equal"),
+              ("reference_run_step_water_default_gravity.npz", ((0, 5), (5, 11)), "default_gravity_unequal"),
+              ("reference_run_long_air_1000.npz", ((0, 9), (9, 7)), "1000_steps_unequal")]
+if os.path.exists(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_run_long_air_1000_n20.npz")):
+    _SLAB_RUNS.append(("reference_run_long_air_1000_n20.npz", ((0, 13), (13, 7)), "1000_steps_20cubed_unequal"))
+
+
+@pytest.mark.parametrize("fixture,cuts", [r[:2] for r in _SLAB_RUNS], ids=[r[2] for r in _SLAB_RUNS])
 def test_two_gloo_ranks_legacy_step_kernel_reproduces_the_reference_run(fixture, cuts):
     """The product's legacy-compatible step kernel source (CPU-emulated, slab geometry: one ghost plane per side, global-z tests)
     on two z-slabs with slab.exchange_halo (5 + 5 outgoing populations per interface, u planes for the lagged FD-LES) over gloo:

@@ -23,9 +23,21 @@ GOLD = os.path.join(HERE, "golden")
 FILES = sorted(glob.glob(os.path.join(GOLD, "reference_run_step_*.npz"))) + sorted(glob.glob(os.path.join(GOLD, "reference_run_long_air_*.npz")))
 
 
+# three host builds of the same kernel source: the one-cell step as the device runs it (collide_reference), the one-cell step with the
+# collision routed through the V-generic template (collide_reference_t<float>), and the two-cells-per-thread step with the packed
+# collision (collide_reference_t<P2> on host stand-ins of the f32x2 primitives) -- opt-in on the device (vec = 2)
+DEPS = ['lbm_step_kernel.cuh', 'lbm_phys.cuh', 'lbm_common.cuh', '../../tests/emu/emu_step_reference.cpp']
+
+
+@pytest.fixture(scope="module", params=["emu_step_reference", "emu_step_reference_generic", "emu_step_reference_vec2"],
+                ids=["one_cell", "one_cell_generic_collision", "two_cells_packed"])
+def emu(request):
+    return H.build_emu(request.param, DEPS)
+
+
 @pytest.fixture(scope="module")
-def emu():
-    return H.build_emu("emu_step_reference", ['lbm_step_kernel.cuh', 'lbm_phys.cuh', 'lbm_common.cuh'])
+def emu_dense():
+    return H.build_emu("emu_step_reference", DEPS)
 
 
 def _p(a):
@@ -142,9 +154,10 @@ def test_emulated_reference_step_kernel_on_the_open_box_recording(emu):
 
 # ---- compat = physical, the headline configuration: step_cells<PHYSICAL, DENSE, ..., VEC = 1> ---------------------------
 @pytest.mark.parametrize("les", [False, True])
-def test_emulated_dense_physical_step_kernel_matches_the_oracle_and_its_golden(emu, les):
+def test_emulated_dense_physical_step_kernel_matches_the_oracle_and_its_golden(emu_dense, les):
     """pull with in-kernel periodic wrap + collide_phys<float> + write-back, 10 steps at 24^3 from the committed fixture's
     initial state: bit-exact against oracle.step_physical (and, with LES, against tests/golden/step_physical_24.npz)."""
+    emu = emu_dense
     z = np.load(os.path.join(GOLD, "step_physical_24.npz"))
     n, steps = int(z["n"]), int(z["steps"])
     p = R.PhysParams(nx=n, ny=n, nz=n, tau_water=float(z["tau"]), les=les)
@@ -163,10 +176,11 @@ def test_emulated_dense_physical_step_kernel_matches_the_oracle_and_its_golden(e
 
 
 @pytest.mark.parametrize("tau", [0.53, 0.8])
-def test_emulated_taylor_green_decay_rate(emu, tau):
+def test_emulated_taylor_green_decay_rate(emu_dense, tau):
     """BASELINE's third criterion on the CPU, with the product's kernel source: the z-invariant Taylor-Green vortex (exact
     Navier-Stokes solution) on a periodic 128 x 128 x 2 box, u0 = 0.01, 1000 steps; ln E fitted over steps 200..1000 against
     -4 nu k^2, nu = (tau - 1/2)/3, within 0.5 %.  (The GPU test does the same at 256^3.)"""
+    emu = emu_dense
     n, nz, u0, steps, every = 128, 2, 0.01, 1000, 50
     k = 2 * np.pi / n
     x = np.arange(n)[:, None, None] * k; y = np.arange(n)[None, :, None] * k
