@@ -525,6 +525,23 @@ if __name__ == "__main__":
         np.savez_compressed(os.path.join(HERE, f"reference_run_long_air_{steps}_n{n}.npz"), n=n, steps=steps, gravity=gravity, seed=seed,
                             phase_mode="air_random", **inp, **geom, **out)
         sys.exit(0 if ok else 1)
+    if len(sys.argv) > 2 and sys.argv[2] == "coupled_long":
+        # the coupled sequence over ten times as many steps (particles cross cells, the cone constraint and the deactivation of stray
+        # particles act repeatedly): the oracle must follow the reference's run through all of them
+        steps = int(sys.argv[3]) if len(sys.argv) > 3 else 60
+        t = time.time()
+        res = run_coupled_scenario(config, n, seed=57, steps=steps)
+        st, pos, vel, active, drag, drag_old, react, re_p = oracle_coupled(res)
+        fluid = res["solid"] == 0; a = res["p_active_out"] == 1
+        ok = dict(rho=np.array_equal(st.rho[fluid], res["rho"][fluid]), u=np.array_equal(st.u[fluid], res["u"][fluid]),
+                  f=np.array_equal(st.f[:, fluid], res["f_out"][:, fluid]), active=np.array_equal(active, res["p_active_out"]),
+                  pos=np.array_equal(pos[a], res["p_pos_out"][a]), vel=np.array_equal(vel[a], res["p_vel_out"][a]),
+                  drag=bool(np.allclose(drag[a], res["p_drag"][a], rtol=1e-6, atol=1e-20)),
+                  reaction=bool(np.allclose(react, res["p_reaction"], rtol=1e-5, atol=1e-14)))
+        print(f"[reference run] coupled step x{steps} ({time.time() - t:.0f} s) vs oracle:", ok, " active in / out:", int(res["p_active"].sum()),
+              int(res["p_active_out"].sum()), " max|reaction|", float(np.abs(res["p_reaction"]).max()))
+        np.savez_compressed(os.path.join(HERE, f"reference_run_coupled_{steps}.npz"), **res)
+        sys.exit(0 if all(ok.values()) else 1)
     if len(sys.argv) > 2 and sys.argv[2] == "coupled":
         t = time.time()
         res = run_coupled_scenario(config, n, seed=51)
